@@ -1,0 +1,320 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so) -- TEST INFRASTRUCTURE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm import
+this module.  The product package (orb_slam_fusion_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+TRIG_LIBM, TRIG_CR = 0, 1
+
+
+class Params(C.Structure):
+    _fields_ = [("num_feats", C.c_int), ("scale_factor", C.c_float), ("num_levs", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+class GridGeom(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_w", C.c_float),
+                ("inv_h", C.c_float), ("cols", C.c_int), ("rows", C.c_int)]
+
+
+WQ_DTYPE = np.dtype([("u", "<f4"), ("v", "<f4"), ("r", "<f4"), ("min_level", "<i4"),
+                     ("max_level", "<i4")])
+WR_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "<i4"),
+                     ("best_dist2", "<i4"), ("best_level2", "<i4")])
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborb_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("cvprim.c", "orb_oracle.c", "cvprim.h", "orb_oracle.h")]
+    stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, i, f, sz, u64, i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_uint64, C.c_int64
+        L.orc_create.restype = vp
+        L.orc_create.argtypes = [C.POINTER(Params)]
+        L.orc_destroy.argtypes = [vp]
+        L.orc_set_trig.argtypes = [vp, i]
+        L.orc_tables.argtypes = [vp] + [vp] * 6
+        L.orc_compute_pyramid.argtypes = [vp, vp, i, i, sz]
+        L.orc_level.restype = vp
+        L.orc_level.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(sz)]
+        L.orc_blurred_level.restype = vp
+        L.orc_blurred_level.argtypes = [vp, i, C.POINTER(sz)]
+        L.orc_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, C.POINTER(i), C.POINTER(i)]
+        L.orc_candidates.argtypes = [vp, i, vp, i]
+        L.orc_selected.argtypes = [vp, i, vp, i]
+        L.orc_fast_grid.argtypes = [vp, i, i, sz, i, i, vp, i]
+        L.orc_octree.argtypes = [vp, i, i, i, i, i, i, vp, i]
+        L.orc_ic_angle.restype = f
+        L.orc_ic_angle.argtypes = [vp, sz, i, i]
+        L.orc_rbrief.argtypes = [vp, sz, i, i, f, i, vp]
+        L.orc_hamming.argtypes = [vp, vp]
+        L.orc_knn2.argtypes = [vp, i, vp, i64, vp, vp, i]
+        L.orc_ratio_accept.argtypes = [i, i, i, C.c_double]
+        L.orc_stereo_rowband.argtypes = [vp, vp, i, vp, vp, i, vp, i, f, f, vp, vp]
+        L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
+        L.orc_splitmix64.restype = u64
+        L.orc_splitmix64.argtypes = [u64]
+        L.orc_synth_blocks_v1.argtypes = [vp, i, i, sz, u64, u64, i, u64]
+        L.orc_synth_uniform_v1.argtypes = [vp, i, i, sz, u64, u64]
+        L.orc_synth_descriptors.argtypes = [vp, i64, i64, u64]
+        for name, rt, at in [
+            ("cvp_resize_linear_u8", None, [vp, i, i, sz, vp, i, i, sz]),
+            ("cvp_border_reflect101_u8", None, [vp, i, i, sz, vp, sz, i]),
+            ("cvp_fast9_nms_u8", i, [vp, i, i, sz, i, vp, i]),
+            ("cvp_gauss7x7_u8", None, [vp, i, i, sz, vp, sz]),
+            ("cvp_fast_atan2", f, [f, f]),
+        ]:
+            fn = getattr(L, name)
+            fn.restype = rt
+            fn.argtypes = at
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8img(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img
+
+
+# ---------------------------------------------------------------- primitives
+def resize_linear(img, dw, dh):
+    img = _u8img(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().cvp_resize_linear_u8(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, dw)
+    return out
+
+
+def border_reflect101(img, b):
+    img = _u8img(img)
+    h, w = img.shape
+    out = np.empty((h + 2 * b, w + 2 * b), np.uint8)
+    lib().cvp_border_reflect101_u8(_p(img), w, h, img.strides[0], _p(out), w + 2 * b, b)
+    return out
+
+
+def fast9_nms(img, threshold):
+    img = _u8img(img)
+    h, w = img.shape
+    cap = max(16, w * h // 2)
+    out = np.empty((cap, 3), np.int32)
+    n = lib().cvp_fast9_nms_u8(_p(img), w, h, img.strides[0], threshold, _p(out), cap)
+    return out[:n].copy()
+
+
+def gauss7x7(img):
+    img = _u8img(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().cvp_gauss7x7_u8(_p(img), w, h, img.strides[0], _p(out), w)
+    return out
+
+
+def fast_atan2(y, x):
+    return lib().cvp_fast_atan2(float(y), float(x))
+
+
+# ---------------------------------------------------------------- stages
+def fast_grid(level, ini_th=20, min_th=7):
+    level = _u8img(level)
+    h, w = level.shape
+    cap = max(64, w * h // 4)
+    out = np.empty((cap, 3), np.int32)
+    n = lib().orc_fast_grid(_p(level), w, h, level.strides[0], ini_th, min_th, _p(out), cap)
+    return out[:n].copy()
+
+
+def octree(xyr, w, h, quota):
+    """DistributeOctTree on candidates (x, y, response) relative to (16,16) of a w x h level.
+    Returns indices into xyr in the reference's output order."""
+    xyr = np.ascontiguousarray(xyr, np.int32).reshape(-1, 3)
+    cap = quota + 8 + len(xyr)
+    out = np.empty(cap, np.int32)
+    n = lib().orc_octree(_p(xyr), len(xyr), 16, w - 16, 16, h - 16, quota, _p(out), cap)
+    if n < 0:
+        raise ValueError("octree: degenerate geometry")
+    return out[:n].copy()
+
+
+def ic_angle(level, cx, cy):
+    level = _u8img(level)
+    return lib().orc_ic_angle(_p(level), level.strides[0], int(cx), int(cy))
+
+
+def rbrief(blurred, cx, cy, angle_deg, trig=TRIG_LIBM):
+    blurred = _u8img(blurred)
+    d = np.empty(32, np.uint8)
+    lib().orc_rbrief(_p(blurred), blurred.strides[0], int(cx), int(cy), float(angle_deg), trig, _p(d))
+    return d
+
+
+class Extractor:
+    """Oracle counterpart of ORB_SLAM_FUSION::OrbExtractor (orb_extractor.h:44-104)."""
+
+    def __init__(self, num_feats=1000, scale_factor=1.2, num_levs=8, ini_th_fast=20, min_th_fast=7,
+                 trig=TRIG_LIBM):
+        self.params = Params(num_feats, scale_factor, num_levs, ini_th_fast, min_th_fast)
+        self.h = lib().orc_create(C.byref(self.params))
+        if not self.h:
+            raise ValueError("bad parameters")
+        self.num_levs = num_levs
+        lib().orc_set_trig(self.h, trig)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        L = self.num_levs
+        sc, isc, s2, is2 = (np.empty(L, np.float32) for _ in range(4))
+        quota = np.empty(L, np.int32)
+        umax = np.empty(16, np.int32)
+        lib().orc_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(quota), _p(umax))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, quota=quota, umax=umax)
+
+    def compute_pyramid(self, img):
+        img = _u8img(img)
+        rc = lib().orc_compute_pyramid(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0])
+        if rc:
+            raise ValueError("pyramid rc=%d" % rc)
+        return [self.level(l) for l in range(self.num_levs)]
+
+    def level(self, lev, with_border=False):
+        w, h, st = C.c_int(), C.c_int(), C.c_size_t()
+        p = lib().orc_level(self.h, lev, C.byref(w), C.byref(h), C.byref(st))
+        b = 19
+        buf = (C.c_uint8 * (st.value * (h.value + 2 * b))).from_address(p - b * st.value - b)
+        a = np.frombuffer(buf, np.uint8).reshape(h.value + 2 * b, st.value).copy()
+        return a if with_border else a[b:b + h.value, b:b + w.value].copy()
+
+    def blurred(self, lev):
+        st = C.c_size_t()
+        w, h = C.c_int(), C.c_int()
+        lib().orc_level(self.h, lev, C.byref(w), C.byref(h), None)
+        p = lib().orc_blurred_level(self.h, lev, C.byref(st))
+        buf = (C.c_uint8 * (w.value * h.value)).from_address(p)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, w.value).copy()
+
+    def __call__(self, img, lapping=(0, 0)):
+        """Returns (n_mono, kps[KP_DTYPE], desc[N,32])."""
+        if img is None or img.size == 0:
+            return -1, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        img = _u8img(img)
+        cap = self.params.num_feats * 2 + 64 * self.num_levs
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n, nm = C.c_int(), C.c_int()
+        rc = lib().orc_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                               int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap,
+                               C.byref(n), C.byref(nm))
+        if rc:
+            raise RuntimeError("orc_extract rc=%d" % rc)
+        return nm.value, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def candidates(self, lev):
+        n = lib().orc_candidates(self.h, lev, None, 0)
+        out = np.empty((max(n, 1), 3), np.int32)
+        lib().orc_candidates(self.h, lev, _p(out), n)
+        return out[:n]
+
+    def selected(self, lev):
+        n = lib().orc_selected(self.h, lev, None, 0)
+        out = np.empty(max(n, 1), KP_DTYPE)
+        lib().orc_selected(self.h, lev, _p(out), n)
+        return out[:n]
+
+
+# ---------------------------------------------------------------- matching
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming(_p(a), _p(b))
+
+
+def knn2(q, d, nthreads=1):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    d = np.ascontiguousarray(d, np.uint8).reshape(-1, 32)
+    idx = np.empty((len(q), 2), np.int64)
+    dist = np.empty((len(q), 2), np.int32)
+    lib().orc_knn2(_p(q), len(q), _p(d), len(d), _p(idx), _p(dist), nthreads)
+    return idx, dist
+
+
+def ratio_accept(idx, dist, ratio=0.7):
+    return np.array([bool(lib().orc_ratio_accept(int(d[0]), int(d[1]), int(i[1] >= 0), ratio))
+                     for i, d in zip(idx, dist)], bool)
+
+
+def stereo_rowband(kl, dl, kr, dr, scale_factors, n_rows, min_d, max_d):
+    kl = np.ascontiguousarray(kl, KP_DTYPE)
+    kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl = np.ascontiguousarray(dl, np.uint8)
+    dr = np.ascontiguousarray(dr, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    bi = np.empty(len(kl), np.int32)
+    bd = np.empty(len(kl), np.int32)
+    lib().orc_stereo_rowband(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), int(n_rows),
+                             float(min_d), float(max_d), _p(bi), _p(bd))
+    return bi, bd
+
+
+def window_search(kps, desc, geom, queries, qdesc, skip=None):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, WQ_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    out = np.empty(len(queries), WR_DTYPE)
+    g = GridGeom(*geom)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    lib().orc_window_search(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc),
+                            len(queries), None if sk is None else _p(sk), _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- synthetic inputs
+def splitmix64(x):
+    return lib().orc_splitmix64(x & 0xFFFFFFFFFFFFFFFF)
+
+
+def blocks_v1(w, h, seed=1, frame=0, shift_x=0, noise_seed=None):
+    img = np.empty((h, w), np.uint8)
+    lib().orc_synth_blocks_v1(_p(img), w, h, w, seed, frame, shift_x,
+                              seed if noise_seed is None else noise_seed)
+    return img
+
+
+def uniform_v1(w, h, seed=1, frame=0):
+    img = np.empty((h, w), np.uint8)
+    lib().orc_synth_uniform_v1(_p(img), w, h, w, seed, frame)
+    return img
+
+
+def synth_descriptors(first, n, seed):
+    out = np.empty((n, 32), np.uint8)
+    lib().orc_synth_descriptors(_p(out), first, n, seed)
+    return out

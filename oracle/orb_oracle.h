@@ -1,0 +1,134 @@
+/*
+ * oracle/orb_oracle.h -- TEST INFRASTRUCTURE (CPU oracle), not product code.
+ *
+ * Plain-C restatement of the reference's ORB front-end hot path:
+ *   OrbExtractor (src/cam/orb_feature/orb_extractor.cc:407-465, 744-849, 1011-1117)
+ *   ORBmatcher::DescriptorDistance (src/cam/orb_feature/orb_matcher.cc:1877-1891)
+ *   and the data-parallel matcher call patterns (frame.cc:836-900, 1154-1162,
+ *   orb_matcher.cc:66-113).
+ * Pinned against cv2 4.13.0 (tests/test_oracle_cv2.py), against the committed
+ * golden vectors (tests/golden/) and against the reference's own orb_extractor.cc
+ * compiled on the mini-cv shim (oracle/_ref, tests/test_oracle_vs_ref.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * arm may link or call this.
+ */
+#ifndef ORB_ORACLE_H
+#define ORB_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_MAX_LEVELS 16
+
+typedef struct {
+  int num_feats;
+  float scale_factor;
+  int num_levs;
+  int ini_th_fast;
+  int min_th_fast;
+} orc_params;
+
+/* Same field order and size (28 B) as cv::KeyPoint. */
+typedef struct {
+  float x, y, size, angle, response;
+  int octave, class_id;
+} orc_kp;
+
+typedef struct orc_extractor orc_extractor;
+
+enum { ORC_TRIG_LIBM = 0, ORC_TRIG_CR = 1 };
+
+orc_extractor* orc_create(const orc_params* p);
+void orc_destroy(orc_extractor* e);
+/* trig mode for the rBRIEF steering: ORC_TRIG_LIBM = cosf/sinf as the reference
+ * (orb_extractor.cc:106); ORC_TRIG_CR = (float)cos((double)a) (correctly rounded). */
+void orc_set_trig(orc_extractor* e, int mode);
+
+/* A.1 tables; arrays must hold num_levs entries (umax: 16). */
+void orc_tables(const orc_extractor* e, float* scale, float* inv_scale, float* sigma2,
+                float* inv_sigma2, int* quota, int* umax);
+
+/* orb_extractor.cc:1093-1117.  Levels are kept with the 19-px REFLECT_101 border. */
+int orc_compute_pyramid(orc_extractor* e, const uint8_t* img, int w, int h, size_t stride);
+/* pointer to pixel (0,0) of level lev (inside its bordered buffer) */
+const uint8_t* orc_level(const orc_extractor* e, int lev, int* w, int* h, size_t* stride);
+/* blurred copy of level lev as used for descriptors (valid after orc_extract for
+ * levels that had keypoints; recomputed on demand otherwise) */
+const uint8_t* orc_blurred_level(orc_extractor* e, int lev, size_t* stride);
+
+/* orb_extractor.cc:1011-1091.  Returns 0 on success, -1 for an empty image,
+ * -2 if cap is too small.  *n_mono is the reference's return value. */
+int orc_extract(orc_extractor* e, const uint8_t* img, int w, int h, size_t stride,
+                int lap0, int lap1, orc_kp* kps, uint8_t* desc, int cap, int* n, int* n_mono);
+
+/* Stage intermediates of the last orc_extract call (per level).
+ * candidates: FAST survivors in to_dist_kps order, coords relative to (16,16)
+ *             (orb_extractor.cc:816-823) as (x, y, response) int triples.
+ * selected:   DistributeOctTree output order, level coords incl. the +16 shift,
+ *             with angle (orb_extractor.cc:834-848). */
+int orc_candidates(const orc_extractor* e, int lev, int* xyr, int cap);
+int orc_selected(const orc_extractor* e, int lev, orc_kp* out, int cap);
+
+/* Stand-alone stages for stage-wise parity */
+int orc_fast_grid(const uint8_t* lvl, int w, int h, size_t stride, int ini_th, int min_th,
+                  int* xyr, int cap);
+int orc_octree(const int* xyr, int n, int min_x, int max_x, int min_y, int max_y, int quota,
+               int* out_index, int cap);
+float orc_ic_angle(const uint8_t* lvl, size_t stride, int cx, int cy);
+void orc_rbrief(const uint8_t* blurred, size_t stride, int cx, int cy, float angle_deg,
+                int trig_mode, uint8_t desc[32]);
+
+/* ---- matching ---- */
+int orc_hamming(const uint8_t* a, const uint8_t* b); /* orb_matcher.cc:1877-1891 */
+
+/* cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) as used at frame.cc:1154: per query the two
+ * nearest train rows ordered by (distance, index).  idx/dist are [nq][2]; missing
+ * entries (nd < 2) are idx=-1, dist=INT32_MAX.  nthreads>1 splits queries over threads. */
+void orc_knn2(const uint8_t* q, int nq, const uint8_t* d, int64_t nd, int64_t* idx, int* dist,
+              int nthreads);
+/* frame.cc:1162 ratio test: accept iff two neighbours and d0 < d1*ratio */
+int orc_ratio_accept(int d0, int d1, int have2, double ratio);
+
+/* frame.cc:836-900: best right keypoint per left keypoint in the row band.
+ * best_dist[i]=TH_HIGH(100) and best_idx[i]=-1 when nothing beats the threshold
+ * (the reference leaves bestIdxR=0 in that case but never reads it). */
+void orc_stereo_rowband(const orc_kp* kl, const uint8_t* dl, int nl, const orc_kp* kr,
+                        const uint8_t* dr, int nr, const float* scale_factors, int n_rows,
+                        float min_d, float max_d, int* best_idx, int* best_dist);
+
+/* Frame grid (frame.cc:438-465 AssignFeaturesToGrid + :679-746 GetFeaturesInArea) and the
+ * best / second-best inner loop of SearchByProjection (orb_matcher.cc:66-113). */
+typedef struct {
+  float min_x, min_y, inv_w, inv_h; /* mnMinX, mnMinY, mfGridElementWidthInv/HeightInv */
+  int cols, rows;                   /* FRAME_GRID_COLS=64, FRAME_GRID_ROWS=48 */
+} orc_grid_geom;
+
+typedef struct {
+  float u, v, r;
+  int min_level, max_level;
+} orc_window_query;
+
+typedef struct {
+  int best_dist, best_idx, best_level, best_dist2, best_level2;
+} orc_window_result;
+
+void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                       const orc_window_query* q, const uint8_t* qdesc, int nq,
+                       const uint8_t* skip /* n bytes or NULL */, orc_window_result* out);
+
+/* ---- deterministic synthetic inputs ---- */
+uint64_t orc_splitmix64(uint64_t x);
+void orc_synth_blocks_v1(uint8_t* img, int w, int h, size_t stride, uint64_t seed, uint64_t frame,
+                         int shift_x, uint64_t noise_seed);
+void orc_synth_uniform_v1(uint8_t* img, int w, int h, size_t stride, uint64_t seed, uint64_t frame);
+void orc_synth_descriptors(uint8_t* rows, int64_t first, int64_t n, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

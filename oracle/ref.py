@@ -1,0 +1,117 @@
+"""ctypes binding of oracle/_ref/liborb_ref.so -- TEST INFRASTRUCTURE.
+
+The library is the reference's own src/cam/orb_feature/orb_extractor.cc compiled unmodified on
+the mini-cv shim (oracle/minicv), plus DescriptorDistance.  It is built in the development
+container (`make -C oracle ref`, needs /root/reference) and travels to the GPU box as a binary.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from .oracle import KP_DTYPE, _p, _u8img
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_ref", "liborb_ref.so")
+_LIB = None
+
+
+def available(try_build=True):
+    if os.path.exists(_SO):
+        return True
+    if try_build and os.path.isdir("/root/reference/src"):
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+        except Exception:
+            return False
+        return os.path.exists(_SO)
+    return False
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not available():
+            raise RuntimeError("oracle/_ref/liborb_ref.so not built (needs /root/reference)")
+        L = C.CDLL(_SO)
+        vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [i, f, i, i, i]
+        L.ref_destroy.argtypes = [vp]
+        L.ref_extract.argtypes = [vp, vp, i, i, sz, i, i, vp, vp, i, C.POINTER(i)]
+        L.ref_level.argtypes = [vp, i, vp, sz, C.POINTER(i), C.POINTER(i)]
+        L.ref_pyramid.argtypes = [vp, vp, i, i, sz]
+        L.ref_octree.argtypes = [vp, vp, i, i, i, i, i, i, i, vp, i]
+        L.ref_tables.argtypes = [vp, vp, vp, vp, vp]
+        L.ref_hamming.argtypes = [vp, vp]
+        L.ref_knn2.argtypes = [vp, i, vp, C.c_longlong, vp, vp, i]
+        _LIB = L
+    return _LIB
+
+
+class Extractor:
+    def __init__(self, num_feats=1000, scale_factor=1.2, num_levs=8, ini_th_fast=20, min_th_fast=7):
+        self.h = lib().ref_create(num_feats, scale_factor, num_levs, ini_th_fast, min_th_fast)
+        self.num_feats, self.num_levs = num_feats, num_levs
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img, lapping=(0, 0)):
+        if img is None or img.size == 0:
+            n = C.c_int()
+            rc = lib().ref_extract(self.h, None, 0, 0, 0, 0, 0, None, None, 0, C.byref(n))
+            return rc, np.empty(0, KP_DTYPE), np.empty((0, 32), np.uint8)
+        img = _u8img(img)
+        cap = self.num_feats * 2 + 64 * self.num_levs
+        kps = np.empty(cap, KP_DTYPE)
+        desc = np.empty((cap, 32), np.uint8)
+        n = C.c_int()
+        rc = lib().ref_extract(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0],
+                               int(lapping[0]), int(lapping[1]), _p(kps), _p(desc), cap, C.byref(n))
+        assert n.value <= cap
+        return rc, kps[:n.value].copy(), desc[:n.value].copy()
+
+    def compute_pyramid(self, img):
+        img = _u8img(img)
+        lib().ref_pyramid(self.h, _p(img), img.shape[1], img.shape[0], img.strides[0])
+        return [self.level(l) for l in range(self.num_levs)]
+
+    def level(self, lev, with_border=False):
+        w, h = C.c_int(), C.c_int()
+        lib().ref_level(self.h, lev, None, 0, C.byref(w), C.byref(h))
+        out = np.empty((h.value + 38, w.value + 38), np.uint8)
+        lib().ref_level(self.h, lev, _p(out), out.strides[0], C.byref(w), C.byref(h))
+        return out if with_border else out[19:-19, 19:-19].copy()
+
+    def tables(self):
+        L = self.num_levs
+        a, b, c, d = (np.empty(L, np.float32) for _ in range(4))
+        lib().ref_tables(self.h, _p(a), _p(b), _p(c), _p(d))
+        return dict(scale=a, inv_scale=b, sigma2=c, inv_sigma2=d)
+
+    def octree(self, xyr, w, h, quota, lev=0):
+        xyr = np.ascontiguousarray(xyr, np.int32).reshape(-1, 3)
+        cap = quota + 8 + len(xyr)
+        out = np.empty((cap, 3), np.int32)
+        n = lib().ref_octree(self.h, _p(xyr), len(xyr), 16, w - 16, 16, h - 16, quota, lev, _p(out), cap)
+        return out[:n].copy()
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().ref_hamming(_p(a), _p(b))
+
+
+def knn2(q, d, nthreads=1):
+    q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+    d = np.ascontiguousarray(d, np.uint8).reshape(-1, 32)
+    idx = np.empty((len(q), 2), np.int64)
+    dist = np.empty((len(q), 2), np.int32)
+    lib().ref_knn2(_p(q), len(q), _p(d), len(d), _p(idx), _p(dist), nthreads)
+    return idx, dist
