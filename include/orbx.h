@@ -1,0 +1,221 @@
+/*
+ * orbx.h -- C ABI of liborbx_b200.so: the B200 (sm_100a) ORB front end.
+ *
+ * This is the drop-in boundary for the reference's ORB hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the orb_slam_fusion tree).  Only plain
+ * pointers and sizes cross the boundary; there are no C++ or torch types, no exceptions and no
+ * exit().  All functions return ORBX_OK (0) or a negative ORBX_E_* code; outputs are written
+ * only on success.
+ *
+ * Ownership: the caller owns every buffer it passes in; a handle owns its device memory,
+ * pinned staging memory and one CUDA stream.  Threading: distinct handles may be used
+ * concurrently from different host threads (the reference runs the left and right extractor
+ * on two threads, src/map/frame.cc:179-182); one handle is not re-entrant, exactly like the
+ * reference object (it mutates img_pyramid_).
+ *
+ * There is no CPU fallback: every function that computes needs a CUDA device.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_E_EMPTY (-1)       /* empty image: OrbExtractor::operator() returns -1 (orb_extractor.cc:1016) */
+#define ORBX_E_ARG (-2)         /* bad argument */
+#define ORBX_E_CAP (-3)         /* an output buffer is too small */
+#define ORBX_E_CUDA (-4)        /* a CUDA call failed; see orbx_last_error() */
+#define ORBX_E_NOMEM (-5)
+#define ORBX_E_UNSUPPORTED (-6) /* geometry / parameter outside what the kernels support */
+
+#define ORBX_MEM_HOST 0
+#define ORBX_MEM_DEVICE 1
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE 19 /* kEdgeThreshold: border kept around every pyramid level (orb_extractor.cc:74) */
+
+/* The five constructor arguments of OrbExtractor (include/cam/orb_feature/orb_extractor.h:48-49;
+ * read from OrbExtractor.* in settings/EuRoC.yaml:85-98 by src/tracking.cc:189-204). */
+typedef struct {
+  int num_feats;
+  float scale_factor;
+  int num_levs;
+  int ini_th_fast;
+  int min_th_fast;
+} orbx_params;
+
+/* Same field order and size (28 bytes) as cv::KeyPoint, so a std::vector<cv::KeyPoint> can be
+ * filled with one memcpy.  pt in level-0 pixels, size = int(31*scale), angle in degrees,
+ * response = FAST score, octave = pyramid level, class_id = -1 (orb_extractor.cc:834-843). */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orbx_kp;
+
+typedef struct orbx_extractor orbx_t;
+
+/* ------------------------------------------------------------------ extractor */
+
+/* OrbExtractor::OrbExtractor (orb_extractor.cc:407-465).  `device` is the CUDA ordinal;
+ * `max_batch` is the largest number of frames one orbx_extract_batch call may carry
+ * (1 is enough for the operator() drop-in).  Device buffers are sized lazily for the first
+ * image geometry and re-sized when it changes. */
+int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** out);
+void orbx_destroy(orbx_t* h);
+/* Message for the last failing call on this handle (never NULL). */
+const char* orbx_last_error(const orbx_t* h);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (orb_extractor.h:64-74) and the per-level feature quotas num_feats_per_lev_
+ * (orb_extractor.cc:433-444).  Arrays hold num_levs entries; NULL pointers are skipped. */
+int orbx_tables(const orbx_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                int* quota);
+/* Upper bound on keypoints per frame: sum over levels of (quota + 3) (orb_extractor.cc:713). */
+int orbx_max_keypoints(const orbx_t* h);
+
+/* OrbExtractor::operator() (orb_extractor.cc:1011-1091) for one host image, blocking.
+ *   img/w/h/stride : CV_8UC1 image; NULL or zero size -> ORBX_E_EMPTY.
+ *   lap0, lap1     : lapping_areas[0..1] (orb_extractor.cc:1075-1076).
+ *   kps, desc      : host outputs, `cap` entries / cap*32 bytes.
+ *   *n             : number of keypoints; *n_mono: the reference's return value (monoIndex).
+ * If cap < *n the call fails with ORBX_E_CAP and *n still reports the needed size. */
+int orbx_extract(orbx_t* h, const uint8_t* img, int w, int h_, size_t stride, int lap0, int lap1,
+                 orbx_kp* kps, uint8_t* desc, int cap, int* n, int* n_mono);
+
+/* OrbExtractor::ComputePyramid (orb_extractor.cc:1093-1117; public, orb_extractor.h:78). */
+int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int h_, size_t stride);
+
+/* img_pyramid_[lev] of the last single-frame call (public member, orb_extractor.h:76, read by
+ * Frame::ComputeStereoMatches, frame.cc:834,913-931).  Writes the level WITH its 19-px
+ * BORDER_REFLECT_101 frame into dst ((h+38) rows of (w+38) bytes, row pitch dst_stride) and
+ * returns the interior size in *w,*h.  dst == NULL only queries the size. */
+int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int* w, int* h_);
+
+/* Batched operator(): n_frames images of equal size, frame f at imgs + f*frame_stride.
+ * `mem` says where ALL pointers of this call live (ORBX_MEM_HOST: pageable or pinned host
+ * memory, the call blocks until the outputs are written; ORBX_MEM_DEVICE: device memory on
+ * the handle's GPU, the call only enqueues work on `stream` (NULL = the handle's stream) and
+ * returns; use orbx_sync).  Outputs: kps[f*cap + i], desc[(f*cap + i)*32], n[f], n_mono[f].
+ * Frames with more than cap keypoints report n[f] = -(needed) and write nothing for f.
+ * n_frames may exceed max_batch: the call loops over chunks. */
+int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int h_, size_t row_stride,
+                       size_t frame_stride, int mem, int lap0, int lap1, orbx_kp* kps, uint8_t* desc,
+                       int cap, int32_t* n, int32_t* n_mono, void* stream);
+int orbx_sync(orbx_t* h);
+
+/* Number of kernels the handle has launched so far (bench.py's gpu_launches claim). */
+long long orbx_launch_count(const orbx_t* h);
+
+/* Stage intermediates of frame `frame` of the last call, for stage-wise parity tests
+ * (SURVEY.md section 7 step 3).  All write to HOST memory.
+ *   ORBX_STAGE_LEVEL   : u8 level pixels, w*h bytes, no border        -> *count = w*h
+ *   ORBX_STAGE_BLUR    : u8 blurred level, w*h bytes                   -> *count = w*h
+ *   ORBX_STAGE_CAND    : int32 (x, y, response) triples of the FAST survivors handed to the
+ *                        quadtree, coordinates relative to (16,16) as orb_extractor.cc:816-823,
+ *                        in UNSPECIFIED order (sort before comparing)  -> *count = triples
+ *   ORBX_STAGE_SELECTED: int32 (x, y, response) of the quadtree output in the reference's
+ *                        order, level coordinates                      -> *count = triples */
+#define ORBX_STAGE_LEVEL 0
+#define ORBX_STAGE_BLUR 1
+#define ORBX_STAGE_CAND 2
+#define ORBX_STAGE_SELECTED 3
+int orbx_stage_download(orbx_t* h, int frame, int stage, int lev, void* dst, size_t dst_bytes,
+                        int* count);
+
+/* Deterministic synthetic frames, generated on the device for benchmarks:
+ * kind 0 = blocks-v1, 1 = uniform-v1.  Frame f uses (seed, first_frame + f).  `dst` is device
+ * memory, n_frames * frame_stride bytes. */
+int orbx_synth_frames(int device, int kind, uint8_t* dst, int n_frames, int w, int h_, size_t row_stride,
+                      size_t frame_stride, uint64_t seed, uint64_t first_frame, int shift_x,
+                      uint64_t noise_seed, void* stream);
+
+/* ------------------------------------------------------------------ matcher */
+
+typedef struct orbm_matcher orbm_t;
+
+int orbm_create(int device, orbm_t** out);
+void orbm_destroy(orbm_t* m);
+const char* orbm_last_error(const orbm_t* m);
+int orbm_sync(orbm_t* m);
+long long orbm_launch_count(const orbm_t* m);
+
+/* ORBmatcher::DescriptorDistance (orb_matcher.cc:1877-1891) for n independent pairs:
+ * out[i] = popcount(a[i] xor b[i]) over 256 bits. */
+int orbm_hamming_pairs(orbm_t* m, const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, int mem,
+                       void* stream);
+
+/* Brute-force 2-nearest-neighbour search, cv::BFMatcher(NORM_HAMMING).knnMatch(q, db, k=2) as
+ * called at frame.cc:1154: for each of nq queries the two nearest of nd database rows, ordered by
+ * (distance, index) so the lowest index wins ties.  idx/dist are [nq][2]; idx is the database
+ * row plus db_index_base (lets a shard report global rows); missing neighbours (nd < 2) are
+ * idx = -1, dist = INT32_MAX. */
+int orbm_knn2(orbm_t* m, const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t db_index_base,
+              int64_t* idx, int32_t* dist, int mem, void* stream);
+
+/* Merge n_parts partial top-2 lists ([n_parts][nq][2], e.g. the all-gathered per-GPU results of
+ * a sharded database) into the global top-2 by the same (distance, index) order. */
+int orbm_top2_merge(orbm_t* m, const int64_t* idx_parts, const int32_t* dist_parts, int n_parts, int nq,
+                    int64_t* idx, int32_t* dist, int mem, void* stream);
+
+/* Lowe ratio test of frame.cc:1162: accept[i] = have two neighbours && d0 < d1 * ratio
+ * (float distances, double product). */
+int orbm_ratio_test(orbm_t* m, const int64_t* idx, const int32_t* dist, int nq, double ratio,
+                    uint8_t* accept, int mem, void* stream);
+
+/* Row-band stereo search of Frame::ComputeStereoMatches (frame.cc:836-900): for every left
+ * keypoint the right keypoint of minimum distance among those whose row band
+ * [floor(yR - 2*sf[octR]), ceil(yR + 2*sf[octR])] holds int(yL), with octave within +-1 and
+ * uL - max_d <= uR <= uL - min_d; best_dist starts at TH_HIGH = 100 (strict <, lowest right
+ * index wins ties); best_idx = -1 where nothing beats it. */
+int orbm_stereo_rowband(orbm_t* m, const orbx_kp* kl, const uint8_t* dl, int nl, const orbx_kp* kr,
+                        const uint8_t* dr, int nr, const float* scale_factors, int n_levels, int n_rows,
+                        float min_d, float max_d, int32_t* best_idx, int32_t* best_dist, int mem,
+                        void* stream);
+
+/* Frame grid geometry (frame.cc:199-204: mnMinX, mnMinY, mfGridElementWidthInv/HeightInv;
+ * frame.h:40-41: FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48). */
+typedef struct {
+  float min_x, min_y, inv_w, inv_h;
+  int32_t cols, rows;
+} orbm_grid_geom;
+
+/* One projected map point: window centre (u, v), radius r, octave gate
+ * (GetFeaturesInArea arguments, frame.cc:679-683). */
+typedef struct {
+  float u, v, r;
+  int32_t min_level, max_level;
+} orbm_window_query;
+
+/* bestDist / bestIdx / bestLevel / bestDist2 / bestLevel2 of orb_matcher.cc:81-113
+ * (256 / -1 / -1 / 256 / -1 when the window is empty). */
+typedef struct {
+  int32_t best_dist, best_idx, best_level, best_dist2, best_level2;
+} orbm_window_result;
+
+/* Inner loop of ORBmatcher::SearchByProjection (orb_matcher.cc:66-113): for each query, the
+ * best and second-best frame keypoint among GetFeaturesInArea(u, v, r, min_level, max_level)
+ * (frame.cc:679-746, candidates visited cell-major then in insertion order, strict <).
+ * `skip` (n bytes, may be NULL) marks frame keypoints that are already matched
+ * (orb_matcher.cc:86-87).  The greedy claim of matches between queries stays with the caller. */
+int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n,
+                       const orbm_grid_geom* geom, const orbm_window_query* queries,
+                       const uint8_t* qdesc, int nq, const uint8_t* skip, orbm_window_result* out,
+                       int mem, void* stream);
+
+/* Deterministic synthetic descriptors: 64-bit word j of row i is
+ * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
+int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);
+
+/* Integer-pipe micro-benchmark: runs `iters` dependent-free popc.b32 per thread on every SM and
+ * returns the measured popc.b32 per second (the matching roofline denominator). */
+int orbm_popc_peak(int device, double* popc_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

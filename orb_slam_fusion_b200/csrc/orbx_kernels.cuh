@@ -1,0 +1,67 @@
+// orbx_kernels.cuh -- internal launch interface between the C ABI (orbx_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "orbx_geom.h"
+
+namespace orbx {
+
+// Device-side view of one batch's working set (all pointers are device memory).
+struct BatchBuffers {
+  uint8_t* pyr;         // [frames][pyr_frame_bytes]   padded level planes
+  uint8_t* blur;        // [frames][pyr_frame_bytes]   blurred planes, same layout
+  uint32_t* cand_xy;    // [frames][cand_frame_cap]    (y << 16) | x, relative to (16,16)
+  uint8_t* cand_sc;     // [frames][cand_frame_cap]    FAST response
+  int32_t* node_of;     // [frames][cand_frame_cap]    quadtree scratch
+  int32_t* n_cand;      // [frames][ORBX_MAX_LEVELS]
+  uint32_t* sel_xy;     // [frames][sel_frame_cap]     (y << 16) | x, level coordinates
+  uint8_t* sel_sc;      // [frames][sel_frame_cap]
+  int32_t* n_sel;       // [frames][ORBX_MAX_LEVELS]
+  uint32_t* work;       // [frames][sel_frame_cap]     per output slot: (level << 28) | index into sel
+  // resize coefficient tables of the current geometry, per level at tab_off
+  const int16_t* xofs;   // source column of destination column
+  const int16_t* xalpha; // 2 coefficients per destination column
+  const int16_t* yofs;   // source row of destination row (already clamped pair in yofs2)
+  const int16_t* ybeta;  // 2 coefficients per destination row
+};
+
+// Each launcher enqueues on `st` and returns the number of kernels it launched.
+int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
+                  size_t frame_stride, int frames, cudaStream_t st);
+int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_blur(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_kp* kps, uint8_t* desc,
+                    int cap, int32_t* n, int32_t* n_mono, cudaStream_t st);
+int launch_synth(int kind, uint8_t* dst, int frames, int w, int h, size_t row_stride, size_t frame_stride,
+                 uint64_t seed, uint64_t first_frame, int shift_x, uint64_t noise_seed, cudaStream_t st);
+
+cudaError_t octree_configure(int node_cap);  // opt in to the dynamic shared memory the tree needs
+size_t octree_smem_bytes(int node_cap);
+
+// ---- matcher ----
+int launch_hamming_pairs(const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, cudaStream_t st);
+// partial top-2 per (block, query) then merge; `partials` must hold knn2_partial_bytes()
+size_t knn2_partial_bytes(int nq, int64_t nd);
+int launch_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t index_base, void* partials,
+                int64_t* idx, int32_t* dist, cudaStream_t st);
+int launch_top2_merge(const int64_t* idx_parts, const int32_t* dist_parts, int n_parts, int nq, int64_t* idx,
+                      int32_t* dist, cudaStream_t st);
+int launch_ratio_test(const int64_t* idx, const int32_t* dist, int nq, double ratio, uint8_t* accept,
+                      cudaStream_t st);
+int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const orbx_kp* kr, const uint8_t* dr,
+                          int nr, const float* sf, int n_levels, int n_rows, float min_d, float max_d,
+                          int32_t* best_idx, int32_t* best_dist, cudaStream_t st);
+// scratch: window_scratch_ints(n, cells) int32
+size_t window_scratch_ints(int n, int cells);
+int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom,
+                         const orbm_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                         int32_t* scratch, orbm_window_result* out, cudaStream_t st);
+int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t seed, cudaStream_t st);
+int popc_peak(double* popc_per_s);
+
+}  // namespace orbx
