@@ -75,7 +75,9 @@ const char* orbx_last_error(const orbx_t* h);
  * (orb_extractor.cc:433-444).  Arrays hold num_levs entries; NULL pointers are skipped. */
 int orbx_tables(const orbx_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                 int* quota);
-/* Upper bound on keypoints per frame: sum over levels of (quota + 3) (orb_extractor.cc:713). */
+/* Upper bound on keypoints per frame: per level quota + 3 (orb_extractor.cc:713), or the 4 children
+ * of every initial node where that is more (tiny quotas).  Exact once an image geometry is known,
+ * conservative before. */
 int orbx_max_keypoints(const orbx_t* h);
 
 /* OrbExtractor::operator() (orb_extractor.cc:1011-1091) for one host image, blocking.
@@ -211,9 +213,11 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
  * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);
 
-/* Integer-pipe micro-benchmark: runs `iters` dependent-free popc.b32 per thread on every SM and
- * returns the measured popc.b32 per second (the matching roofline denominator). */
-int orbm_popc_peak(int device, double* popc_per_s);
+/* Integer-pipe micro-benchmark on every SM of `device` (the matching roofline denominators):
+ *   mode 0: independent popc.b32 per second;
+ *   mode 1: 256-bit distances per second of the plain xor + 8 popc + add sequence;
+ *   mode 2: 256-bit distances per second of the distance routine the kernels are built with. */
+int orbm_popc_peak(int device, int mode, double* per_s);
 
 #ifdef __cplusplus
 }

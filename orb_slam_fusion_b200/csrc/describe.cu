@@ -1,0 +1,189 @@
+// describe.cu -- orientation, steered rBRIEF descriptors and output assembly.
+//
+// Replaces computeOrientation / IC_Angle (orb_extractor.cc:76-100, 467-474),
+// ComputeDescriptors / ComputeOrbDescriptor (:102-146, 1002-1009) and the output loop of
+// operator() (:1030-1090: scale to level-0 pixels, mono block from the front, lapping block
+// from the back).  Arithmetic: SURVEY.md A.5, A.7, A.8.
+//
+//   k_plan     one CTA per frame: output slot of every selected keypoint (prefix sum of the
+//              lapping flags in the reference's traversal order), n and n_mono.
+//   k_describe one warp per keypoint: lanes = the 31 patch columns for the intensity centroid
+//              (each row is one coalesced 31-byte read), then lane L builds descriptor byte L
+//              (16 gathers from the blurred level) and the warp stores the 32-byte row at once.
+#include "orbx_kernels.cuh"
+#include "orbx_math.cuh"
+
+namespace orbx {
+
+__constant__ int8_t c_pattern[1024] = {
+#include "../../include/orb_pattern31.inc"
+};
+// umax_ of orb_extractor.cc:452-464 for kHalfPatchSize = 15
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+constexpr int kPlanThreads = 256;
+
+__global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ sel_xy,
+                                                       const int32_t* __restrict__ n_sel, int32_t* __restrict__ work,
+                                                       int cap, int32_t* __restrict__ n_out, int32_t* __restrict__ n_mono_out,
+                                                       int out_frame0) {
+  __shared__ int lev_start[ORBX_MAX_LEVELS + 1];
+  __shared__ int warp_sums[kPlanThreads / 32];
+  __shared__ int carry, bad;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) {
+    int s = 0, b = 0;
+    for (int l = 0; l < g.nlev; l++) {
+      int n = n_sel[f * ORBX_MAX_LEVELS + l];
+      if (n < 0) { b = 1; n = 0; }
+      lev_start[l] = s;
+      s += n;
+    }
+    lev_start[g.nlev] = s;
+    carry = 0;
+    bad = b;
+  }
+  __syncthreads();
+  const int N = lev_start[g.nlev];
+  int32_t* wk = work + (size_t)f * g.sel_frame_cap;
+  const uint32_t* sxy = sel_xy + (size_t)f * g.sel_frame_cap;
+  const bool fits = N <= cap && !bad;
+  for (int base = 0; base < N; base += kPlanThreads) {
+    const int i = base + tid;
+    int flag = 0, lev = 0, idx = 0;
+    if (i < N) {
+      while (i >= lev_start[lev + 1]) lev++;
+      idx = i - lev_start[lev];
+      float x = (float)(sxy[g.lv[lev].sel_off + idx] & 0xFFFFu);
+      if (lev != 0) x = f_mul(x, g.lv[lev].scale);                 // :1071-1073
+      flag = (x >= (float)g.lap0 && x <= (float)g.lap1) ? 1 : 0;    // :1075-1076
+    }
+    // block-wide exclusive scan of the flags
+    int s = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane == 31) warp_sums[wid] = s;
+    __syncthreads();
+    int before = carry;
+    for (int w = 0; w < wid; w++) before += warp_sums[w];
+    const int laps_before = before + s - flag;
+    if (i < N) {
+      // lapping keypoints fill the tail backwards (stereoIndex--), the rest the head (monoIndex++)
+      const int slot = flag ? (N - 1 - laps_before) : (i - laps_before);
+      wk[g.lv[lev].sel_off + idx] = fits ? slot : -1;
+    }
+    __syncthreads();
+    if (tid == kPlanThreads - 1) carry = before + s;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    n_out[out_frame0 + f] = bad ? INT32_MIN : (fits ? N : -N);
+    n_mono_out[out_frame0 + f] = fits ? N - carry : 0;
+  }
+}
+
+constexpr int kDescWarps = 8;
+
+__global__ void __launch_bounds__(32 * kDescWarps) k_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+                                                              const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel_xy,
+                                                              const uint8_t* __restrict__ sel_sc, const int32_t* __restrict__ n_sel,
+                                                              const int32_t* __restrict__ work, orbx_kp* __restrict__ kps,
+                                                              uint8_t* __restrict__ desc, int cap, int out_frame0) {
+  // pattern transposed so that lane L reads word [k][L]: (x0,y0,x1,y1) of bit k of byte L
+  __shared__ uint32_t pat[8][32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  {
+    const int L = tid >> 3, k = tid & 7;  // 256 threads = 32 bytes x 8 bits
+    const int8_t* p = &c_pattern[(L * 8 + k) * 4];
+    pat[k][L] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
+                ((uint32_t)(uint8_t)p[3] << 24);
+  }
+  __syncthreads();
+  const int f = blockIdx.y;
+  const int s = blockIdx.x * kDescWarps + wid;  // position in the frame's selected list
+  if (s >= g.sel_frame_cap) return;
+  int lev = 0;
+  while (lev + 1 < g.nlev && s >= g.lv[lev + 1].sel_off) lev++;
+  const LevelGeom& L = g.lv[lev];
+  const int idx = s - L.sel_off;
+  if (idx >= n_sel[f * ORBX_MAX_LEVELS + lev]) return;
+  const size_t so = (size_t)f * g.sel_frame_cap + s;
+  const int slot = work[so];
+  if (slot < 0) return;
+  const uint32_t xy = sel_xy[so];
+  const int cx = (int)(xy & 0xFFFFu), cy = (int)(xy >> 16);
+  const size_t fo = (size_t)f * g.pyr_frame_bytes;
+
+  // ---- IC_Angle (:76-100): lane = column u, loop over rows v
+  const int u = lane - kHalfPatch;
+  const int au = u < 0 ? -u : u;
+  int m10 = 0, m01 = 0;
+  if (lane < kPatch) {
+    const uint8_t* c = pyr + fo + px_off(L, cx + u, cy);
+#pragma unroll
+    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
+      const int av = v < 0 ? -v : v;
+      if (au <= c_umax[av]) {
+        const int val = __ldg(c + v * L.pitch);
+        m10 += u * val;
+        m01 += v * val;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+
+  // ---- steered rBRIEF (:102-146).  cos/sin are the correctly rounded float values
+  // (float of the double-precision result); see SURVEY.md A.7 for the libm tolerance class.
+  const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
+  const float rad = f_mul(angle, factor_pi);
+  const float a = (float)cos((double)rad), b = (float)sin((double)rad);
+  const uint8_t* bc = blur + fo + px_off(L, cx, cy);
+  uint32_t byte = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t p = pat[k][lane];
+    int r0, c0, r1, c1;
+    rbrief_offset(a, b, (int)(int8_t)(p & 255), (int)(int8_t)((p >> 8) & 255), r0, c0);
+    rbrief_offset(a, b, (int)(int8_t)((p >> 16) & 255), (int)(int8_t)(p >> 24), r1, c1);
+    const int t0 = __ldg(bc + r0 * L.pitch + c0), t1 = __ldg(bc + r1 * L.pitch + c1);
+    byte |= (uint32_t)(t0 < t1) << k;
+  }
+  const size_t o = (size_t)(out_frame0 + f) * cap + slot;
+  desc[o * 32 + lane] = (uint8_t)byte;
+
+  // ---- keypoint record (:834-843, 1071-1073)
+  if (lane < 7) {
+    float fx = (float)cx, fy = (float)cy;
+    if (lev != 0) { fx = f_mul(fx, L.scale); fy = f_mul(fy, L.scale); }
+    float v;
+    switch (lane) {
+      case 0: v = fx; break;
+      case 1: v = fy; break;
+      case 2: v = (float)L.scaled_patch; break;
+      case 3: v = angle; break;
+      case 4: v = (float)sel_sc[so]; break;
+      case 5: v = __int_as_float(lev); break;
+      default: v = __int_as_float(-1); break;
+    }
+    reinterpret_cast<float*>(kps + o)[lane] = v;
+  }
+}
+
+int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_kp* kps, uint8_t* desc, int cap,
+                    int32_t* n, int32_t* n_mono, int out_frame0, cudaStream_t st) {
+  k_plan<<<frames, kPlanThreads, 0, st>>>(g, b.sel_xy, b.n_sel, b.work, cap, n, n_mono, out_frame0);
+  dim3 grid((g.sel_frame_cap + kDescWarps - 1) / kDescWarps, frames);
+  k_describe<<<grid, 32 * kDescWarps, 0, st>>>(g, b.pyr, b.blur, b.sel_xy, b.sel_sc, b.n_sel, b.work, kps, desc, cap,
+                                              out_frame0);
+  return 2;
+}
+
+}  // namespace orbx

@@ -1,0 +1,451 @@
+// matcher.cu -- 256-bit Hamming matching kernels.
+//
+// Replaces ORBmatcher::DescriptorDistance (orb_matcher.cc:1877-1891) and the data-parallel call
+// patterns around it: cv::BFMatcher::knnMatch(k=2) + ratio test (frame.cc:1154-1162), the stereo
+// row-band search (frame.cc:836-900) and the best / second-best window search of
+// SearchByProjection (orb_matcher.cc:66-113 with Frame::GetFeaturesInArea, frame.cc:679-746).
+// Arithmetic: SURVEY.md A.9.  Everything is integer: xor + popc over eight 32-bit words, and
+// every "strict <, first candidate wins" loop of the reference is restated as a minimum over the
+// lexicographic key (distance, visiting position), which makes the reductions associative and
+// therefore exact under any parallel order.
+#include <limits.h>
+
+#include "orbx_kernels.cuh"
+#include "orbx_math.cuh"
+
+namespace orbx {
+
+#ifndef ORBM_CSA
+#define ORBM_CSA 1
+#endif
+
+// popcount of the xor of two 256-bit rows held as 8 words.
+// ORBM_CSA: two carry-save adder steps move work from the quarter-rate POPC pipe to LOP3:
+// 8 popc -> 5 popc + 6 lop3 (sum = a^b^c, carry = maj(a,b,c) are one LOP3 each).
+__device__ __forceinline__ int ham256(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+  uint32_t x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = a[i] ^ b[i];
+#if ORBM_CSA
+  const uint32_t s0 = x[0] ^ x[1] ^ x[2], c0 = (x[0] & x[1]) | (x[2] & (x[0] | x[1]));
+  const uint32_t s1 = x[3] ^ x[4] ^ x[5], c1 = (x[3] & x[4]) | (x[5] & (x[3] | x[4]));
+  const uint32_t s2 = s0 ^ s1 ^ x[6], c2 = (s0 & s1) | (x[6] & (s0 | s1));
+  return __popc(s2) + __popc(x[7]) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+#else
+  int d = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) d += __popc(x[i]);
+  return d;
+#endif
+}
+
+__device__ __forceinline__ void load_row(const uint8_t* p, uint32_t (&r)[8]) {
+  const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p)), hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w; r[4] = hi.x; r[5] = hi.y; r[6] = hi.z; r[7] = hi.w;
+}
+// rows that are only 4-byte aligned (cv::Mat rows of a caller-owned buffer)
+__device__ __forceinline__ void load_row_any(const uint8_t* p, uint32_t (&r)[8]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) { load_row(p, r); return; }
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    r[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+}
+
+// ------------------------------------------------------------------ DescriptorDistance, n pairs
+__global__ void __launch_bounds__(256) k_hamming_pairs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int64_t n,
+                                                       int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t ra[8], rb[8];
+  load_row_any(a + 32 * i, ra);
+  load_row_any(b + 32 * i, rb);
+  out[i] = ham256(ra, rb);
+}
+
+int launch_hamming_pairs(const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, cudaStream_t st) {
+  if (n <= 0) return 0;
+  k_hamming_pairs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, n, out);
+  return 1;
+}
+
+// ------------------------------------------------------------------ brute-force 2-NN
+// Queries live in registers (kQpt per thread, kKnnThreads*kQpt per CTA), database rows stream
+// through shared memory and are read as warp-wide broadcasts, so the inner loop is
+// 2 LDS.128 per row per thread against kQpt distance evaluations: the popc / integer pipes are
+// the only limiter.  Per (thread, query) the running top-2 is two packed 32-bit keys
+// (distance << 20 | row-in-chunk), updated with 3 min/max.
+constexpr int kKnnThreads = 256, kQpt = 4, kKnnTile = 256;
+constexpr int kKnnQBlock = kKnnThreads * kQpt;
+constexpr int kKeyShift = 20;
+constexpr int64_t kKeyRows = (int64_t)1 << kKeyShift;
+constexpr int kPartShift = 40;  // partial key: distance << 40 | database row
+
+__global__ void __launch_bounds__(kKnnThreads) k_knn2(const uint8_t* __restrict__ q, int nq, const uint8_t* __restrict__ db,
+                                                      int64_t nd, int64_t chunk_rows, unsigned long long* __restrict__ partial) {
+  __shared__ __align__(16) uint4 tile[2][kKnnTile * 2];
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * chunk_rows;
+  const int64_t row1 = row0 + chunk_rows < nd ? row0 + chunk_rows : nd;
+  const int qbase = blockIdx.y * kKnnQBlock;
+
+  uint32_t qr[kQpt][8];
+  uint32_t k0[kQpt], k1[kQpt];
+#pragma unroll
+  for (int j = 0; j < kQpt; j++) {
+    const int qi = qbase + j * kKnnThreads + tid;
+    if (qi < nq) load_row_any(q + 32 * (size_t)qi, qr[j]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; i++) qr[j][i] = 0;
+    }
+    k0[j] = k1[j] = 0xFFFFFFFFu;
+  }
+
+  const int n_tiles = (int)((row1 - row0 + kKnnTile - 1) / kKnnTile);
+  // software pipeline: the next tile's row is in flight while the current tile is scanned
+  uint4 nlo = make_uint4(0, 0, 0, 0), nhi = nlo;
+  if (n_tiles > 0 && row0 + tid < row1) {
+    const uint4* p = reinterpret_cast<const uint4*>(db + 32 * (row0 + tid));
+    nlo = __ldg(p); nhi = __ldg(p + 1);
+  }
+  for (int t = 0; t < n_tiles; t++) {
+    const int buf = t & 1;
+    tile[buf][2 * tid] = nlo;
+    tile[buf][2 * tid + 1] = nhi;
+    __syncthreads();  // one barrier per tile: buffer `buf` is rewritten two tiles later
+    const int64_t next = row0 + (int64_t)(t + 1) * kKnnTile + tid;
+    if (t + 1 < n_tiles && next < row1) {
+      const uint4* p = reinterpret_cast<const uint4*>(db + 32 * next);
+      nlo = __ldg(p); nhi = __ldg(p + 1);
+    }
+    const int64_t tbase = row0 + (int64_t)t * kKnnTile;
+    const int rows = (int)(row1 - tbase < kKnnTile ? row1 - tbase : kKnnTile);
+    const uint32_t kbase = (uint32_t)(t * kKnnTile);
+#pragma unroll 2
+    for (int r = 0; r < rows; r++) {
+      const uint4 lo = tile[buf][2 * r], hi = tile[buf][2 * r + 1];
+      const uint32_t rr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+      for (int j = 0; j < kQpt; j++) {
+        const uint32_t key = ((uint32_t)ham256(qr[j], rr) << kKeyShift) | (kbase + r);
+        k1[j] = min(k1[j], max(k0[j], key));
+        k0[j] = min(k0[j], key);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kQpt; j++) {
+    const int qi = qbase + j * kKnnThreads + tid;
+    if (qi >= nq) continue;
+    unsigned long long o0 = ~0ull, o1 = ~0ull;
+    if (k0[j] != 0xFFFFFFFFu)
+      o0 = ((unsigned long long)(k0[j] >> kKeyShift) << kPartShift) | (unsigned long long)(row0 + (k0[j] & (kKeyRows - 1)));
+    if (k1[j] != 0xFFFFFFFFu)
+      o1 = ((unsigned long long)(k1[j] >> kKeyShift) << kPartShift) | (unsigned long long)(row0 + (k1[j] & (kKeyRows - 1)));
+    unsigned long long* p = partial + ((size_t)blockIdx.x * nq + qi) * 2;
+    p[0] = o0;
+    p[1] = o1;
+  }
+}
+
+// merge the per-chunk partial keys of one query; thread per query
+__global__ void __launch_bounds__(128) k_knn2_merge(const unsigned long long* __restrict__ partial, int n_chunks, int nq,
+                                                    int64_t index_base, int64_t* __restrict__ idx, int32_t* __restrict__ dist) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  for (int c = 0; c < n_chunks; c++) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((size_t)c * nq + qi) * 2);
+    b1 = min(b1, max(b0, v.x));
+    b0 = min(b0, v.x);
+    b1 = min(b1, v.y);  // v.y >= v.x
+  }
+  const unsigned long long mask = (1ull << kPartShift) - 1;
+  idx[2 * qi] = b0 == ~0ull ? -1 : (int64_t)(b0 & mask) + index_base;
+  dist[2 * qi] = b0 == ~0ull ? INT_MAX : (int32_t)(b0 >> kPartShift);
+  idx[2 * qi + 1] = b1 == ~0ull ? -1 : (int64_t)(b1 & mask) + index_base;
+  dist[2 * qi + 1] = b1 == ~0ull ? INT_MAX : (int32_t)(b1 >> kPartShift);
+}
+
+static int knn2_chunks(int64_t nd, int64_t* chunk_rows) {
+  // two waves of CTAs over 148 SMs for large databases, >= one tile per chunk for small ones
+  int64_t n_chunks = 296;
+  const int64_t tiles = (nd + kKnnTile - 1) / kKnnTile;
+  if (n_chunks > tiles) n_chunks = tiles > 0 ? tiles : 1;
+  int64_t rows = (nd + n_chunks - 1) / n_chunks;
+  rows = (rows + kKnnTile - 1) / kKnnTile * kKnnTile;
+  if (rows > kKeyRows) rows = kKeyRows;
+  if (rows < kKnnTile) rows = kKnnTile;
+  *chunk_rows = rows;
+  return (int)((nd + rows - 1) / rows > 0 ? (nd + rows - 1) / rows : 1);
+}
+
+size_t knn2_partial_bytes(int nq, int64_t nd) {
+  int64_t rows;
+  const int chunks = knn2_chunks(nd, &rows);
+  return (size_t)chunks * (size_t)(nq > 0 ? nq : 1) * 2 * sizeof(unsigned long long);
+}
+
+int launch_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t index_base, void* partials,
+                int64_t* idx, int32_t* dist, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  int64_t rows;
+  const int chunks = knn2_chunks(nd, &rows);
+  dim3 grid(chunks, (nq + kKnnQBlock - 1) / kKnnQBlock);
+  k_knn2<<<grid, kKnnThreads, 0, st>>>(q, nq, db, nd, rows, reinterpret_cast<unsigned long long*>(partials));
+  k_knn2_merge<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const unsigned long long*>(partials), chunks, nq,
+                                                 index_base, idx, dist);
+  return 2;
+}
+
+// ------------------------------------------------------------------ merge of sharded top-2 lists
+__device__ __forceinline__ bool key_less(int32_t da, int64_t ia, int32_t db_, int64_t ib) {
+  // missing entries (idx < 0) sort last; otherwise (distance, index) ascending
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return da < db_ || (da == db_ && ia < ib);
+}
+
+__global__ void __launch_bounds__(128) k_top2_merge(const int64_t* __restrict__ idx_parts, const int32_t* __restrict__ dist_parts,
+                                                    int n_parts, int nq, int64_t* __restrict__ idx, int32_t* __restrict__ dist) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  int64_t i0 = -1, i1 = -1;
+  int32_t d0 = INT_MAX, d1 = INT_MAX;
+  for (int p = 0; p < n_parts; p++)
+    for (int k = 0; k < 2; k++) {
+      const int64_t ii = idx_parts[((size_t)p * nq + qi) * 2 + k];
+      const int32_t dd = dist_parts[((size_t)p * nq + qi) * 2 + k];
+      if (ii < 0) continue;
+      if (key_less(dd, ii, d0, i0)) { d1 = d0; i1 = i0; d0 = dd; i0 = ii; }
+      else if (key_less(dd, ii, d1, i1)) { d1 = dd; i1 = ii; }
+    }
+  idx[2 * qi] = i0; idx[2 * qi + 1] = i1;
+  dist[2 * qi] = d0; dist[2 * qi + 1] = d1;
+}
+
+int launch_top2_merge(const int64_t* idx_parts, const int32_t* dist_parts, int n_parts, int nq, int64_t* idx,
+                      int32_t* dist, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  k_top2_merge<<<(nq + 127) / 128, 128, 0, st>>>(idx_parts, dist_parts, n_parts, nq, idx, dist);
+  return 1;
+}
+
+// frame.cc:1162: (*it)[0].distance < (*it)[1].distance * 0.7 -- float distances, double product
+__global__ void __launch_bounds__(128) k_ratio(const int64_t* __restrict__ idx, const int32_t* __restrict__ dist, int nq,
+                                               double ratio, uint8_t* __restrict__ accept) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const bool have2 = idx[2 * qi] >= 0 && idx[2 * qi + 1] >= 0;
+  accept[qi] = have2 && ((double)(float)dist[2 * qi] < __dmul_rn((double)(float)dist[2 * qi + 1], ratio));
+}
+
+int launch_ratio_test(const int64_t* idx, const int32_t* dist, int nq, double ratio, uint8_t* accept, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  k_ratio<<<(nq + 127) / 128, 128, 0, st>>>(idx, dist, nq, ratio, accept);
+  return 1;
+}
+
+// ------------------------------------------------------------------ warp top-2 of 64-bit keys
+__device__ __forceinline__ void warp_top2(unsigned long long& b0, unsigned long long& b1) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
+    const unsigned long long hi = max(b0, o0);
+    b0 = min(b0, o0);
+    b1 = min(hi, min(b1, o1));
+  }
+}
+
+// ------------------------------------------------------------------ stereo row band
+// One warp per left keypoint; lanes stride over the right keypoints.  The reference visits the
+// candidates of row int(vL) in ascending right index and keeps the first minimum below TH_HIGH
+// (frame.cc:862-900) == min over (distance, right index) with distance < 100.
+__global__ void __launch_bounds__(256) k_stereo_rowband(const orbx_kp* __restrict__ kl, const uint8_t* __restrict__ dl, int nl,
+                                                        const orbx_kp* __restrict__ kr, const uint8_t* __restrict__ dr, int nr,
+                                                        const float* __restrict__ sf, int n_levels, int n_rows, float min_d,
+                                                        float max_d, int32_t* __restrict__ best_idx,
+                                                        int32_t* __restrict__ best_dist) {
+  const int il = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (il >= nl) return;
+  const orbx_kp L = kl[il];
+  const int row = (int)L.y;  // vRowIndices[vL]: truncation (frame.cc:868)
+  const float min_u = f_sub(L.x, max_d), max_u = f_sub(L.x, min_d);
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  if (row >= 0 && row < n_rows && !(max_u < 0)) {
+    uint32_t ql[8];
+    load_row_any(dl + 32 * (size_t)il, ql);
+    for (int ir = lane; ir < nr; ir += 32) {
+      const orbx_kp R = kr[ir];
+      if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
+      const int oc = R.octave < 0 ? 0 : (R.octave >= n_levels ? n_levels - 1 : R.octave);
+      const float r = f_mul(2.0f, sf[oc]);
+      const int maxr = (int)ceilf(f_add(R.y, r)), minr = (int)floorf(f_sub(R.y, r));
+      if (row < minr || row > maxr) continue;
+      if (!(R.x >= min_u && R.x <= max_u)) continue;
+      uint32_t qr[8];
+      load_row_any(dr + 32 * (size_t)ir, qr);
+      const int d = ham256(ql, qr);
+      if (d < 100) {  // ORBmatcher::TH_HIGH: bestDist starts there, strict <
+        const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)ir;
+        b1 = min(b1, max(b0, key));
+        b0 = min(b0, key);
+      }
+    }
+  }
+  warp_top2(b0, b1);
+  if (lane == 0) {
+    best_idx[il] = b0 == ~0ull ? -1 : (int32_t)(b0 & 0xFFFFFFFFu);
+    best_dist[il] = b0 == ~0ull ? 100 : (int32_t)(b0 >> 32);
+  }
+}
+
+int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const orbx_kp* kr, const uint8_t* dr, int nr,
+                          const float* sf, int n_levels, int n_rows, float min_d, float max_d, int32_t* best_idx,
+                          int32_t* best_dist, cudaStream_t st) {
+  if (nl <= 0) return 0;
+  k_stereo_rowband<<<(nl + 7) / 8, 256, 0, st>>>(kl, dl, nl, kr, dr, nr, sf, n_levels, n_rows, min_d, max_d, best_idx,
+                                                 best_dist);
+  return 1;
+}
+
+// ------------------------------------------------------------------ projection window search
+// One warp per query.  GetFeaturesInArea visits cells column-major (ix outer, iy inner) and the
+// keypoints of a cell in insertion (= index) order (frame.cc:438-465, 718-743); the
+// best / second-best recurrences of orb_matcher.cc:98-112 equal the two smallest keys
+// (distance, cell = ix*rows + iy, keypoint index), so no cell lists have to be built.
+__global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                       const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
+                                                       const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                       orbm_window_result* __restrict__ out) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  const orbm_window_query Q = q[qi];
+  // frame.cc:684-712 cell range of the window
+  int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
+  int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
+  int c0y = (int)floorf(f_mul(f_sub(f_sub(Q.v, g.min_y), Q.r), g.inv_h));
+  int c1y = (int)ceilf(f_mul(f_add(f_sub(Q.v, g.min_y), Q.r), g.inv_h));
+  c0x = c0x < 0 ? 0 : c0x;
+  c1x = c1x > g.cols - 1 ? g.cols - 1 : c1x;
+  c0y = c0y < 0 ? 0 : c0y;
+  c1y = c1y > g.rows - 1 ? g.rows - 1 : c1y;
+  const bool ok = !(c0x >= g.cols || c1x < 0 || c0y >= g.rows || c1y < 0);
+  const bool check_levels = Q.min_level >= 0 || Q.max_level >= 0;
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  if (ok) {
+    uint32_t qd[8];
+    load_row_any(qdesc + 32 * (size_t)qi, qd);
+    for (int i = lane; i < n; i += 32) {
+      const orbx_kp K = kps[i];
+      // Frame::PosInGrid (frame.cc:748-760): round, keypoints outside the grid are in no cell
+      const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
+      const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
+      if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
+      if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
+      if (check_levels) {
+        if (K.octave < Q.min_level) continue;
+        if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
+      }
+      const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
+      if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+      if (skip && skip[i]) continue;
+      uint32_t kd[8];
+      load_row_any(desc + 32 * (size_t)i, kd);
+      const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
+                                     ((unsigned long long)(px * g.rows + py) << 24) | (unsigned long long)i;
+      b1 = min(b1, max(b0, key));
+      b0 = min(b0, key);
+    }
+  }
+  warp_top2(b0, b1);
+  if (lane == 0) {
+    orbm_window_result r = {256, -1, -1, 256, -1};
+    if (b0 != ~0ull) {
+      r.best_dist = (int32_t)(b0 >> 44);
+      r.best_idx = (int32_t)(b0 & 0xFFFFFFu);
+      r.best_level = kps[r.best_idx].octave;
+    }
+    if (b1 != ~0ull) {
+      r.best_dist2 = (int32_t)(b1 >> 44);
+      r.best_level2 = kps[(int32_t)(b1 & 0xFFFFFFu)].octave;
+    }
+    out[qi] = r;
+  }
+}
+
+int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
+                         const uint8_t* qdesc, int nq, const uint8_t* skip, orbm_window_result* out, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, out);
+  return 1;
+}
+
+// ------------------------------------------------------------------ popc pipe micro-benchmark
+// mode 0: popc only; mode 1: the xor + popc + add mix of a plain distance; mode 2: ham256 as built.
+__global__ void __launch_bounds__(256) k_popc_bench(uint32_t* out, int iters, int mode) {
+  uint32_t x[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x; acc[i] = 0; }
+  if (mode == 0) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { acc[i] += __popc(x[i]); x[i] += acc[i]; }
+    }
+  } else {
+    uint32_t y[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) y[i] = x[i] * 3u + 1u;
+    for (int it = 0; it < iters; it++) {
+      int d;
+      if (mode == 1) {
+        d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d += __popc(x[i] ^ y[i]);
+      } else {
+        d = ham256(x, y);
+      }
+      acc[0] += d;
+      y[it & 7] += d + it;
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += acc[i];
+  if (s == 0xDEADBEEFu) out[0] = s;
+}
+
+int popc_bench(int mode, double* per_s) {
+  uint32_t* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return -1;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaGetDeviceProperties(&prop, dev);
+  const int blocks = prop.multiProcessorCount * 8, iters = mode == 0 ? 20000 : 4000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_popc_bench<<<blocks, 256>>>(d, iters / 10, mode);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    k_popc_bench<<<blocks, 256>>>(d, iters, mode);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (err != cudaSuccess) return -1;
+  // mode 0 counts popc instructions; modes 1-2 count 256-bit distance evaluations
+  const double units = (double)blocks * 256.0 * iters * (mode == 0 ? 8.0 : 1.0);
+  *per_s = units / (best * 1e-3);
+  return 0;
+}
+
+}  // namespace orbx

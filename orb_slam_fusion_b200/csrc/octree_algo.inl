@@ -24,6 +24,7 @@
 
 #if defined(ORBX_HOST_EMUL)
 #define OT_DEV inline
+#define OT_HD inline
 #define OT_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define OT_SYNC() ((void)0)
 #define OT_TID0 true
@@ -32,6 +33,7 @@ static inline void ot_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 static inline void ot_atomic_min_u(unsigned* p, unsigned v) { if (v < *p) *p = v; }
 #else
 #define OT_DEV __device__ __forceinline__
+#define OT_HD __host__ __device__ __forceinline__
 #define OT_FOR(i, n) for (int i = threadIdx.x; i < (n); i += blockDim.x)
 #define OT_SYNC() __syncthreads()
 #define OT_TID0 (threadIdx.x == 0)
@@ -58,7 +60,7 @@ struct OtWork {
 
 enum { SV_N = 0, SV_F, SV_M, SV_MEFF, SV_TOTALC, SV_DONE, SV_PHASE, SV_TOEXP, SV_CUR, SV_ERR };
 
-OT_DEV int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1) + 2 * (cap + 1) + 16; }
+OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1) + 2 * (cap + 1) + 16; }
 
 OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.cap = cap;

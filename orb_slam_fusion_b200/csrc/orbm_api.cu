@@ -1,0 +1,294 @@
+// orbm_api.cu -- C ABI of the matcher half of liborbx_b200.so (include/orbx.h, orbm_*).
+// Host buffers are staged through a per-handle device arena; device buffers are used in place.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "orbx_kernels.cuh"
+
+using namespace orbx;
+
+struct orbm_matcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint8_t* arena = nullptr;  // staging for host-memory calls
+  size_t arena_bytes = 0, arena_used = 0;
+  void* partials = nullptr;  // knn2 per-chunk top-2
+  size_t partial_bytes = 0;
+  long long launches = 0;
+  char err[256] = "";
+};
+
+namespace {
+
+int fail(orbm_t* m, int code, const char* fmt, ...) {
+  if (m) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(m->err, sizeof(m->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(m, call)                                                                              \
+  do {                                                                                           \
+    const cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail(m, ORBX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int arena_reserve(orbm_t* m, size_t bytes) {
+  m->arena_used = 0;
+  if (bytes <= m->arena_bytes) return ORBX_OK;
+  CU(m, cudaStreamSynchronize(m->stream));
+  if (m->arena) cudaFree(m->arena);
+  m->arena = nullptr;
+  m->arena_bytes = 0;
+  CU(m, cudaMalloc((void**)&m->arena, bytes));
+  m->arena_bytes = bytes;
+  return ORBX_OK;
+}
+
+size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
+
+template <class T>
+T* arena_take(orbm_t* m, size_t count) {
+  T* p = reinterpret_cast<T*>(m->arena + m->arena_used);
+  m->arena_used += pad256(count * sizeof(T));
+  return p;
+}
+
+// device copy of a host input (or the pointer itself for device memory)
+template <class T>
+int stage_in(orbm_t* m, int mem, const T* src, size_t count, const T** out, cudaStream_t st) {
+  if (mem == ORBX_MEM_DEVICE || !src) { *out = src; return ORBX_OK; }
+  T* d = arena_take<T>(m, count);
+  if (count) CU(m, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  *out = d;
+  return ORBX_OK;
+}
+
+template <class T>
+T* stage_out(orbm_t* m, int mem, T* dst, size_t count) {
+  return mem == ORBX_MEM_DEVICE ? dst : arena_take<T>(m, count);
+}
+
+template <class T>
+int finish_out(orbm_t* m, int mem, T* dst, const T* dev, size_t count, cudaStream_t st) {
+  if (mem == ORBX_MEM_DEVICE || !count) return ORBX_OK;
+  CU(m, cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+  return ORBX_OK;
+}
+
+int begin(orbm_t* m, int mem, void* stream, cudaStream_t* st) {
+  if (!m) return ORBX_E_ARG;
+  if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) return fail(m, ORBX_E_ARG, "bad mem kind");
+  CU(m, cudaSetDevice(m->device));
+  *st = (mem == ORBX_MEM_DEVICE && stream) ? (cudaStream_t)stream : m->stream;
+  return ORBX_OK;
+}
+
+int end(orbm_t* m, int mem, cudaStream_t st) {
+  if (mem == ORBX_MEM_HOST) CU(m, cudaStreamSynchronize(st));
+  CU(m, cudaGetLastError());
+  return ORBX_OK;
+}
+
+#define TRY(x)                \
+  do {                        \
+    const int rc_ = (x);      \
+    if (rc_) return rc_;      \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+
+int orbm_create(int device, orbm_t** out) {
+  if (!out) return ORBX_E_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ORBX_E_CUDA;
+  orbm_t* m = new (std::nothrow) orbm_matcher();
+  if (!m) return ORBX_E_NOMEM;
+  m->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete m;
+    return ORBX_E_CUDA;
+  }
+  *out = m;
+  return ORBX_OK;
+}
+
+void orbm_destroy(orbm_t* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  cudaStreamSynchronize(m->stream);
+  if (m->arena) cudaFree(m->arena);
+  if (m->partials) cudaFree(m->partials);
+  cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const char* orbm_last_error(const orbm_t* m) { return m ? m->err : "null handle"; }
+
+int orbm_sync(orbm_t* m) {
+  if (!m) return ORBX_E_ARG;
+  CU(m, cudaSetDevice(m->device));
+  CU(m, cudaStreamSynchronize(m->stream));
+  return ORBX_OK;
+}
+
+long long orbm_launch_count(const orbm_t* m) { return m ? m->launches : 0; }
+
+int orbm_hamming_pairs(orbm_t* m, const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(m, ORBX_E_ARG, "bad argument");
+  if (n == 0) return ORBX_OK;
+  if (mem == ORBX_MEM_HOST) TRY(arena_reserve(m, 2 * pad256((size_t)n * 32) + pad256((size_t)n * 4)));
+  const uint8_t *da, *db;
+  TRY(stage_in(m, mem, a, (size_t)n * 32, &da, st));
+  TRY(stage_in(m, mem, b, (size_t)n * 32, &db, st));
+  int32_t* dout = stage_out(m, mem, out, (size_t)n);
+  m->launches += launch_hamming_pairs(da, db, n, dout, st);
+  TRY(finish_out(m, mem, out, dout, (size_t)n, st));
+  return end(m, mem, st);
+}
+
+int orbm_knn2(orbm_t* m, const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t db_index_base, int64_t* idx,
+              int32_t* dist, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nq < 0 || nd < 0 || (nq > 0 && (!q || !idx || !dist)) || (nd > 0 && !db)) return fail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  if (((uintptr_t)db & 15) != 0 && mem == ORBX_MEM_DEVICE) return fail(m, ORBX_E_ARG, "device database must be 16-byte aligned");
+  const size_t pb = knn2_partial_bytes(nq, nd);
+  if (pb > m->partial_bytes) {
+    CU(m, cudaStreamSynchronize(st));
+    if (m->partials) cudaFree(m->partials);
+    m->partials = nullptr;
+    m->partial_bytes = 0;
+    CU(m, cudaMalloc(&m->partials, pb));
+    m->partial_bytes = pb;
+  }
+  if (mem == ORBX_MEM_HOST)
+    TRY(arena_reserve(m, pad256((size_t)nq * 32) + pad256((size_t)nd * 32) + pad256((size_t)nq * 16) + pad256((size_t)nq * 8)));
+  const uint8_t *dq, *ddb;
+  TRY(stage_in(m, mem, q, (size_t)nq * 32, &dq, st));
+  TRY(stage_in(m, mem, db, (size_t)nd * 32, &ddb, st));
+  int64_t* didx = stage_out(m, mem, idx, (size_t)nq * 2);
+  int32_t* ddist = stage_out(m, mem, dist, (size_t)nq * 2);
+  m->launches += launch_knn2(dq, nq, ddb, nd, db_index_base, m->partials, didx, ddist, st);
+  TRY(finish_out(m, mem, idx, didx, (size_t)nq * 2, st));
+  TRY(finish_out(m, mem, dist, ddist, (size_t)nq * 2, st));
+  return end(m, mem, st);
+}
+
+int orbm_top2_merge(orbm_t* m, const int64_t* idx_parts, const int32_t* dist_parts, int n_parts, int nq, int64_t* idx,
+                    int32_t* dist, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nq < 0 || n_parts < 0 || (nq > 0 && (!idx || !dist)) || (nq > 0 && n_parts > 0 && (!idx_parts || !dist_parts)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  const size_t np = (size_t)n_parts * nq * 2;
+  if (mem == ORBX_MEM_HOST) TRY(arena_reserve(m, pad256(np * 8) + pad256(np * 4) + pad256((size_t)nq * 16) + pad256((size_t)nq * 8)));
+  const int64_t* di;
+  const int32_t* dd;
+  TRY(stage_in(m, mem, idx_parts, np, &di, st));
+  TRY(stage_in(m, mem, dist_parts, np, &dd, st));
+  int64_t* didx = stage_out(m, mem, idx, (size_t)nq * 2);
+  int32_t* ddist = stage_out(m, mem, dist, (size_t)nq * 2);
+  m->launches += launch_top2_merge(di, dd, n_parts, nq, didx, ddist, st);
+  TRY(finish_out(m, mem, idx, didx, (size_t)nq * 2, st));
+  TRY(finish_out(m, mem, dist, ddist, (size_t)nq * 2, st));
+  return end(m, mem, st);
+}
+
+int orbm_ratio_test(orbm_t* m, const int64_t* idx, const int32_t* dist, int nq, double ratio, uint8_t* accept, int mem,
+                    void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nq < 0 || (nq > 0 && (!idx || !dist || !accept))) return fail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  if (mem == ORBX_MEM_HOST) TRY(arena_reserve(m, pad256((size_t)nq * 16) + pad256((size_t)nq * 8) + pad256((size_t)nq)));
+  const int64_t* di;
+  const int32_t* dd;
+  TRY(stage_in(m, mem, idx, (size_t)nq * 2, &di, st));
+  TRY(stage_in(m, mem, dist, (size_t)nq * 2, &dd, st));
+  uint8_t* dacc = stage_out(m, mem, accept, (size_t)nq);
+  m->launches += launch_ratio_test(di, dd, nq, ratio, dacc, st);
+  TRY(finish_out(m, mem, accept, dacc, (size_t)nq, st));
+  return end(m, mem, st);
+}
+
+int orbm_stereo_rowband(orbm_t* m, const orbx_kp* kl, const uint8_t* dl, int nl, const orbx_kp* kr, const uint8_t* dr,
+                        int nr, const float* scale_factors, int n_levels, int n_rows, float min_d, float max_d,
+                        int32_t* best_idx, int32_t* best_dist, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nl < 0 || nr < 0 || n_levels < 1 || !scale_factors || (nl > 0 && (!kl || !dl || !best_idx || !best_dist)) ||
+      (nr > 0 && (!kr || !dr)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (nl == 0) return ORBX_OK;
+  if (mem == ORBX_MEM_HOST)
+    TRY(arena_reserve(m, pad256((size_t)nl * 28) + pad256((size_t)nl * 32) + pad256((size_t)nr * 28) + pad256((size_t)nr * 32) +
+                             pad256((size_t)n_levels * 4) + 2 * pad256((size_t)nl * 4)));
+  const orbx_kp *dkl, *dkr;
+  const uint8_t *ddl, *ddr;
+  const float* dsf;
+  TRY(stage_in(m, mem, kl, (size_t)nl, &dkl, st));
+  TRY(stage_in(m, mem, dl, (size_t)nl * 32, &ddl, st));
+  TRY(stage_in(m, mem, kr, (size_t)nr, &dkr, st));
+  TRY(stage_in(m, mem, dr, (size_t)nr * 32, &ddr, st));
+  TRY(stage_in(m, mem, scale_factors, (size_t)n_levels, &dsf, st));
+  int32_t* dbi = stage_out(m, mem, best_idx, (size_t)nl);
+  int32_t* dbd = stage_out(m, mem, best_dist, (size_t)nl);
+  m->launches += launch_stereo_rowband(dkl, ddl, nl, dkr, ddr, nr, dsf, n_levels, n_rows, min_d, max_d, dbi, dbd, st);
+  TRY(finish_out(m, mem, best_idx, dbi, (size_t)nl, st));
+  TRY(finish_out(m, mem, best_dist, dbd, (size_t)nl, st));
+  return end(m, mem, st);
+}
+
+int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                       const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                       orbm_window_result* out, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (n < 0 || nq < 0 || !geom || geom->cols < 1 || geom->rows < 1 || (int64_t)geom->cols * geom->rows >= (1 << 20) ||
+      n >= (1 << 24) || (n > 0 && (!kps || !desc)) || (nq > 0 && (!queries || !qdesc || !out)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (nq == 0) return ORBX_OK;
+  if (mem == ORBX_MEM_HOST)
+    TRY(arena_reserve(m, pad256((size_t)n * 28) + pad256((size_t)n * 32) + pad256((size_t)nq * sizeof(orbm_window_query)) +
+                             pad256((size_t)nq * 32) + pad256((size_t)n) + pad256((size_t)nq * sizeof(orbm_window_result))));
+  const orbx_kp* dk;
+  const uint8_t *dd, *dqd, *dskip;
+  const orbm_window_query* dq;
+  TRY(stage_in(m, mem, kps, (size_t)n, &dk, st));
+  TRY(stage_in(m, mem, desc, (size_t)n * 32, &dd, st));
+  TRY(stage_in(m, mem, queries, (size_t)nq, &dq, st));
+  TRY(stage_in(m, mem, qdesc, (size_t)nq * 32, &dqd, st));
+  TRY(stage_in(m, mem, skip, (size_t)n, &dskip, st));
+  orbm_window_result* dout = stage_out(m, mem, out, (size_t)nq);
+  m->launches += launch_window_search(dk, dd, n, *geom, dq, dqd, nq, dskip, dout, st);
+  TRY(finish_out(m, mem, out, dout, (size_t)nq, st));
+  return end(m, mem, st);
+}
+
+int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream) {
+  if (!dst || n < 0) return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  launch_synth_descriptors(dst, first, n, seed, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+}
+
+int orbm_popc_peak(int device, int mode, double* per_s) {
+  if (!per_s || mode < 0 || mode > 2) return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  return popc_bench(mode, per_s) == 0 ? ORBX_OK : ORBX_E_CUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,527 @@
+// orbx_api.cu -- the C ABI of liborbx_b200.so (include/orbx.h): handles, geometry, memory and
+// the per-batch kernel sequence.  Host-side restatement of the OrbExtractor constructor tables
+// (orb_extractor.cc:407-465) and of cv::resize's coefficient tables (A.2).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "orbx_kernels.cuh"
+#include "orbx_math.cuh"
+
+using namespace orbx;
+
+namespace {
+
+constexpr int kSlots = 2;  // ping-pong working sets so host-memory batches overlap copies and kernels
+
+struct Slot {
+  BatchBuffers b{};
+  uint8_t* d_img = nullptr;     // staged host frames [max_batch][img_pitch * h]
+  orbx_kp* d_kps = nullptr;     // [max_batch][out_cap]
+  uint8_t* d_desc = nullptr;    // [max_batch][out_cap][32]
+  int32_t* d_n = nullptr;       // [max_batch] n, then [max_batch] n_mono
+  int32_t* h_n = nullptr;       // pinned mirror of d_n
+  cudaStream_t stream = nullptr;
+  std::vector<void*> allocs;
+};
+
+}  // namespace
+
+struct orbx_extractor {
+  orbx_params p{};
+  int device = 0, max_batch = 1;
+  float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS], sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
+  int quota[ORBX_MAX_LEVELS];
+  FrameGeom g{};
+  bool geom_valid = false;
+  size_t img_pitch = 0;
+  int out_cap = 0;
+  Slot slot[kSlots];
+  void* d_tables = nullptr;
+  int last_frames = 0;       // frames of the last chunk processed on slot 0
+  bool border_done = false;  // REFLECT_101 frames of slot 0's pyramid are up to date
+  long long launches = 0;
+  char err[256] = "";
+};
+
+namespace {
+
+int fail(orbx_t* h, int code, const char* fmt, ...) {
+  if (h) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define CU(h, call)                                                                              \
+  do {                                                                                           \
+    const cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) return fail(h, ORBX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+int round_half_even(float v) { return (int)lrintf(v); }  // cvRound
+
+void build_tables(orbx_t* h) {
+  const int L = h->p.num_levs;
+  const double sf = (double)h->p.scale_factor;  // scale_factor_ is a double member (orb_extractor.h:91)
+  h->scale[0] = 1.0f;
+  h->sigma2[0] = 1.0f;
+  for (int i = 1; i < L; i++) {
+    h->scale[i] = (float)((double)h->scale[i - 1] * sf);
+    h->sigma2[i] = h->scale[i] * h->scale[i];
+  }
+  for (int i = 0; i < L; i++) {
+    h->inv_scale[i] = 1.0f / h->scale[i];
+    h->inv_sigma2[i] = 1.0f / h->sigma2[i];
+  }
+  const float factor = (float)(1.0 / sf);
+  float per_lev = ((float)h->p.num_feats * (1 - factor)) / (1 - (float)pow((double)factor, (double)L));
+  int sum = 0;
+  for (int l = 0; l < L - 1; l++) {
+    h->quota[l] = round_half_even(per_lev);
+    sum += h->quota[l];
+    per_lev *= factor;
+  }
+  h->quota[L - 1] = h->p.num_feats - sum > 0 ? h->p.num_feats - sum : 0;
+}
+
+short sat16(float v) {
+  int r = round_half_even(v);
+  return (short)(r > 32767 ? 32767 : (r < -32768 ? -32768 : r));
+}
+
+// cv::resize INTER_LINEAR 8U tables for one axis
+void resize_axis(int src, int dst, int16_t* ofs, int16_t* coef, bool pair_ofs) {
+  const double scale = 1.0 / ((double)dst / src);
+  for (int d = 0; d < dst; d++) {
+    float f = (float)((d + 0.5) * scale - 0.5);
+    int s = (int)floorf(f);
+    f -= s;
+    if (pair_ofs) {
+      // rows: the coefficients are kept, the two source rows are clamped (VResize over clipped rows)
+      const int s0 = s < 0 ? 0 : (s >= src ? src - 1 : s), s1 = s + 1 < 0 ? 0 : (s + 1 >= src ? src - 1 : s + 1);
+      ofs[2 * d] = (int16_t)s0;
+      ofs[2 * d + 1] = (int16_t)s1;
+    } else {
+      if (s < 0) { f = 0; s = 0; }
+      if (s >= src - 1) { f = 0; s = src - 1; }
+      ofs[d] = (int16_t)s;
+    }
+    coef[2 * d] = sat16((1.f - f) * 2048.f);
+    coef[2 * d + 1] = sat16(f * 2048.f);
+  }
+}
+
+void free_slot(Slot& s) {
+  for (void* p : s.allocs) cudaFree(p);
+  s.allocs.clear();
+  if (s.h_n) cudaFreeHost(s.h_n);
+  s.h_n = nullptr;
+  s.b = BatchBuffers{};
+  s.d_img = nullptr; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr;
+}
+
+void free_geometry(orbx_t* h) {
+  for (auto& s : h->slot) free_slot(s);
+  if (h->d_tables) cudaFree(h->d_tables);
+  h->d_tables = nullptr;
+  h->geom_valid = false;
+}
+
+template <class T>
+cudaError_t dmalloc(Slot& s, T** p, size_t n) {
+  void* v = nullptr;
+  const cudaError_t e = cudaMalloc(&v, (n ? n : 1) * sizeof(T));
+  if (e == cudaSuccess) { s.allocs.push_back(v); *p = (T*)v; }
+  return e;
+}
+
+// Geometry of all levels for a w x h input, device buffers for max_batch frames per slot.
+int ensure_geometry(orbx_t* h, int w, int hh) {
+  if (h->geom_valid && h->g.w0 == w && h->g.h0 == hh) return ORBX_OK;
+  free_geometry(h);
+  if (w > 32767 || hh > 32767) return fail(h, ORBX_E_UNSUPPORTED, "image larger than 32767 px");
+  FrameGeom g{};
+  g.nlev = h->p.num_levs;
+  g.w0 = w; g.h0 = hh;
+  g.ini_th = h->p.ini_th_fast; g.min_th = h->p.min_th_fast;
+  int plane = 0, cells = 0, cand = 0, sel = 0, tab = 0, tiles = 0, node_cap = 0;
+  for (int l = 0; l < g.nlev; l++) {
+    LevelGeom& L = g.lv[l];
+    L.w = round_half_even((float)w * h->inv_scale[l]);  // orb_extractor.cc:1096
+    L.h = round_half_even((float)hh * h->inv_scale[l]);
+    const float width = (float)(L.w - 2 * kFastBorder), height = (float)(L.h - 2 * kFastBorder);
+    L.ncols = (int)(width / 35.f);  // :759-765
+    L.nrows = (int)(height / 35.f);
+    if (L.w < 1 || L.h < 1 || L.ncols < 1 || L.nrows < 1)
+      return fail(h, ORBX_E_UNSUPPORTED, "level %d (%dx%d) is smaller than one 35-px FAST cell plus borders", l, L.w, L.h);
+    L.wcell = (int)ceilf(width / L.ncols);
+    L.hcell = (int)ceilf(height / L.nrows);
+    L.pitch = (kPadX + L.w + kEdge + 15) / 16 * 16;
+    L.plane_off = plane;
+    plane += (L.pitch * (L.h + 2 * kPadY) + 255) / 256 * 256;
+    L.cell_base = cells;
+    cells += L.ncols * L.nrows;
+    // NMS survivors are never 8-adjacent: <= ceil(a/2)*ceil(b/2) per a x b cell domain
+    const int dom_w = L.w - 2 * kEdge, dom_h = L.h - 2 * kEdge;
+    L.cand_cap = ((dom_w + 1) / 2 + L.ncols) * ((dom_h + 1) / 2 + L.nrows);
+    L.cand_off = cand;
+    cand += (L.cand_cap + 3) / 4 * 4;
+    L.quota = h->quota[l];
+    L.sel_off = sel;
+    L.n_roots = (int)roundf(width / height);  // :548
+    if (L.n_roots < 1) return fail(h, ORBX_E_UNSUPPORTED, "level %d is taller than 2:1 (the reference divides by zero)", l);
+    L.root_hx = width / L.n_roots;
+    int nc = L.quota + 4;
+    if (4 * L.n_roots > nc) nc = 4 * L.n_roots;
+    nc += 1;
+    if (nc > node_cap) node_cap = nc;
+    sel += nc;  // a level's list never holds more than its node table
+    L.scale = h->scale[l];
+    L.scaled_patch = (int)((float)kPatch * h->scale[l]);  // :834
+    L.tab_off = tab;
+    tab += (L.w > L.h ? L.w : L.h);
+    L.blur_tiles_x = (L.w + 127) / 128;
+    L.blur_tile_base = tiles;
+    tiles += L.blur_tiles_x * ((L.h + 31) / 32);
+  }
+  g.total_cells = cells;
+  g.pyr_frame_bytes = plane;
+  g.cand_frame_cap = cand;
+  g.sel_frame_cap = sel;
+  g.node_cap = node_cap;
+  g.total_blur_tiles = tiles;
+  if (octree_smem_bytes(node_cap) > 200 * 1024)
+    return fail(h, ORBX_E_UNSUPPORTED, "per-level quota %d needs more shared memory than one SM has", node_cap);
+  CU(h, octree_configure(node_cap));
+
+  // resize tables: per level xofs[w], xalpha[2w], yofs[2h], ybeta[2h], all at tab_off
+  std::vector<int16_t> t((size_t)tab * 7, 0);
+  int16_t* xofs = t.data();
+  int16_t* xalpha = xofs + tab;
+  int16_t* yofs = xalpha + 2 * (size_t)tab;
+  int16_t* ybeta = yofs + 2 * (size_t)tab;
+  for (int l = 1; l < g.nlev; l++) {
+    const LevelGeom &D = g.lv[l], &S = g.lv[l - 1];
+    resize_axis(S.w, D.w, xofs + D.tab_off, xalpha + 2 * (size_t)D.tab_off, false);
+    resize_axis(S.h, D.h, yofs + 2 * (size_t)D.tab_off, ybeta + 2 * (size_t)D.tab_off, true);
+  }
+  CU(h, cudaMalloc(&h->d_tables, t.size() * sizeof(int16_t)));
+  CU(h, cudaMemcpy(h->d_tables, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+  const int16_t* dt = (const int16_t*)h->d_tables;
+
+  h->img_pitch = ((size_t)w + 15) / 16 * 16;
+  h->out_cap = sel;
+  const size_t B = (size_t)h->max_batch;
+  for (auto& s : h->slot) {
+    CU(h, dmalloc(s, &s.b.pyr, B * plane));
+    CU(h, dmalloc(s, &s.b.blur, B * plane));
+    CU(h, dmalloc(s, &s.b.cand_xy, B * cand));
+    CU(h, dmalloc(s, &s.b.cand_sc, B * cand));
+    CU(h, dmalloc(s, &s.b.node_of, B * cand));
+    CU(h, dmalloc(s, &s.b.n_cand, B * ORBX_MAX_LEVELS));
+    CU(h, dmalloc(s, &s.b.sel_xy, B * sel));
+    CU(h, dmalloc(s, &s.b.sel_sc, B * sel));
+    CU(h, dmalloc(s, &s.b.n_sel, B * ORBX_MAX_LEVELS));
+    CU(h, dmalloc(s, &s.b.work, B * sel));
+    s.b.xofs = dt;
+    s.b.xalpha = dt + tab;
+    s.b.yofs = dt + 3 * (size_t)tab;
+    s.b.ybeta = dt + 5 * (size_t)tab;
+    CU(h, dmalloc(s, &s.d_img, B * h->img_pitch * hh));
+    CU(h, dmalloc(s, &s.d_kps, B * sel));
+    CU(h, dmalloc(s, &s.d_desc, B * sel * 32));
+    CU(h, dmalloc(s, &s.d_n, 2 * B));
+    CU(h, cudaMallocHost((void**)&s.h_n, 2 * B * sizeof(int32_t)));
+    // the padding of the planes is never written by the pipeline kernels; define it once
+    CU(h, cudaMemset(s.b.pyr, 0, B * plane));
+    CU(h, cudaMemset(s.b.blur, 0, B * plane));
+  }
+  h->g = g;
+  h->geom_valid = true;
+  h->last_frames = 0;
+  h->border_done = false;
+  return ORBX_OK;
+}
+
+// The kernel sequence of OrbExtractor::operator() for `frames` device-resident frames.
+void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int frames,
+                      int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono,
+                      int out_frame0, cudaStream_t st) {
+  FrameGeom g = h->g;
+  g.lap0 = lap0;
+  g.lap1 = lap1;
+  int n = 0;
+  n += launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
+  n += launch_pyramid(g, s.b, frames, st);
+  n += launch_fast(g, s.b, frames, st);
+  n += launch_octree(g, s.b, frames, st);
+  n += launch_blur(g, s.b, frames, st);
+  n += launch_describe(g, s.b, frames, d_kps, d_desc, cap, d_n, d_nmono, out_frame0, st);
+  h->launches += n;
+}
+
+int check_image(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {
+  if (!h) return ORBX_E_ARG;
+  if (!img || w <= 0 || hh <= 0) return fail(h, ORBX_E_EMPTY, "empty image");
+  if (stride < (size_t)w) return fail(h, ORBX_E_ARG, "stride smaller than the row");
+  return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** out) {
+  if (!params || !out || params->num_levs < 1 || params->num_levs > ORBX_MAX_LEVELS || params->num_feats < 1 ||
+      !(params->scale_factor > 1.0f) || max_batch < 1)
+    return ORBX_E_ARG;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return ORBX_E_CUDA;
+  orbx_t* h = new (std::nothrow) orbx_extractor();
+  if (!h) return ORBX_E_NOMEM;
+  h->p = *params;
+  h->device = device;
+  h->max_batch = max_batch;
+  build_tables(h);
+  if (cudaSetDevice(device) != cudaSuccess) { delete h; return ORBX_E_CUDA; }
+  for (auto& s : h->slot)
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
+  *out = h;
+  return ORBX_OK;
+}
+
+void orbx_destroy(orbx_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& s : h->slot)
+    if (s.stream) cudaStreamSynchronize(s.stream);
+  free_geometry(h);
+  for (auto& s : h->slot)
+    if (s.stream) cudaStreamDestroy(s.stream);
+  delete h;
+}
+
+const char* orbx_last_error(const orbx_t* h) { return h ? h->err : "null handle"; }
+
+int orbx_tables(const orbx_t* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2, int* quota) {
+  if (!h) return ORBX_E_ARG;
+  const size_t L = (size_t)h->p.num_levs;
+  if (scale) memcpy(scale, h->scale, L * sizeof(float));
+  if (inv_scale) memcpy(inv_scale, h->inv_scale, L * sizeof(float));
+  if (sigma2) memcpy(sigma2, h->sigma2, L * sizeof(float));
+  if (inv_sigma2) memcpy(inv_sigma2, h->inv_sigma2, L * sizeof(float));
+  if (quota) memcpy(quota, h->quota, L * sizeof(int));
+  return ORBX_OK;
+}
+
+int orbx_max_keypoints(const orbx_t* h) {
+  if (!h) return ORBX_E_ARG;
+  if (h->geom_valid) return h->out_cap;
+  int s = 0;
+  for (int l = 0; l < h->p.num_levs; l++) s += (h->quota[l] + 3 > 64 ? h->quota[l] + 3 : 64) + 2;
+  return s;
+}
+
+int orbx_sync(orbx_t* h) {
+  if (!h) return ORBX_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
+  return ORBX_OK;
+}
+
+long long orbx_launch_count(const orbx_t* h) { return h ? h->launches : 0; }
+
+int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int hh, size_t row_stride,
+                       size_t frame_stride, int mem, int lap0, int lap1, orbx_kp* kps, uint8_t* desc, int cap,
+                       int32_t* n, int32_t* n_mono, void* stream) {
+  if (!h) return ORBX_E_ARG;
+  if (n_frames <= 0) return fail(h, ORBX_E_EMPTY, "no frames");
+  int rc = check_image(h, imgs, w, hh, row_stride);
+  if (rc) return rc;
+  if (!kps || !desc || !n || !n_mono || cap < 1) return fail(h, ORBX_E_ARG, "null output");
+  if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) return fail(h, ORBX_E_ARG, "bad mem kind");
+  CU(h, cudaSetDevice(h->device));
+  rc = ensure_geometry(h, w, hh);
+  if (rc) return rc;
+  const int B = h->max_batch;
+  h->border_done = false;
+
+  if (mem == ORBX_MEM_DEVICE) {
+    Slot& s = h->slot[0];
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    for (int f0 = 0; f0 < n_frames; f0 += B) {
+      const int nf = n_frames - f0 < B ? n_frames - f0 : B;
+      enqueue_pipeline(h, s, imgs + (size_t)f0 * frame_stride, row_stride, frame_stride, nf, lap0, lap1, kps, desc, cap,
+                       n, n_mono, f0, st);
+      h->last_frames = nf;
+    }
+    CU(h, cudaGetLastError());
+    return ORBX_OK;
+  }
+
+  // host memory: chunks alternate between two working sets, each on its own stream, so the
+  // copies of one chunk overlap the kernels of the other
+  const int dcap = cap < h->out_cap ? cap : h->out_cap;
+  int chunk = 0;
+  for (int f0 = 0; f0 < n_frames; f0 += B, chunk++) {
+    Slot& s = h->slot[chunk % kSlots];
+    const int nf = n_frames - f0 < B ? n_frames - f0 : B;
+    const uint8_t* src = imgs + (size_t)f0 * frame_stride;
+    if (frame_stride == row_stride * (size_t)hh) {
+      CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, src, row_stride, (size_t)w, (size_t)hh * nf, cudaMemcpyHostToDevice,
+                              s.stream));
+    } else {
+      for (int f = 0; f < nf; f++)
+        CU(h, cudaMemcpy2DAsync(s.d_img + (size_t)f * h->img_pitch * hh, h->img_pitch, src + (size_t)f * frame_stride,
+                                row_stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
+    }
+    enqueue_pipeline(h, s, s.d_img, h->img_pitch, h->img_pitch * hh, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n,
+                     s.d_n + B, 0, s.stream);
+    CU(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), s.d_kps, (size_t)dcap * sizeof(orbx_kp),
+                            (size_t)dcap * sizeof(orbx_kp), nf, cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, s.d_desc, (size_t)dcap * 32, (size_t)dcap * 32, nf,
+                            cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(n + f0, s.d_n, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(n_mono + f0, s.d_n + B, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    if (chunk % kSlots == 0) h->last_frames = nf;
+  }
+  for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
+  CU(h, cudaGetLastError());
+  return ORBX_OK;
+}
+
+int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, int lap0, int lap1, orbx_kp* kps,
+                 uint8_t* desc, int cap, int* n, int* n_mono) {
+  if (!h) return ORBX_E_ARG;
+  int rc = check_image(h, img, w, hh, stride);
+  if (rc) return rc;
+  if (!n || !n_mono) return fail(h, ORBX_E_ARG, "null output");
+  CU(h, cudaSetDevice(h->device));
+  rc = ensure_geometry(h, w, hh);
+  if (rc) return rc;
+  Slot& s = h->slot[0];
+  const int B = h->max_batch;
+  h->border_done = false;
+  CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, img, stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
+  enqueue_pipeline(h, s, s.d_img, h->img_pitch, h->img_pitch * hh, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n,
+                   s.d_n + B, 0, s.stream);
+  h->last_frames = 1;
+  CU(h, cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+  CU(h, cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+  CU(h, cudaStreamSynchronize(s.stream));
+  const int N = s.h_n[0];
+  if (N < 0) return fail(h, ORBX_E_UNSUPPORTED, "quadtree node table overflow");
+  *n = N;
+  if (N > cap) return fail(h, ORBX_E_CAP, "%d keypoints, capacity %d", N, cap);
+  if (N > 0) {
+    if (!kps || !desc) return fail(h, ORBX_E_ARG, "null output");
+    CU(h, cudaMemcpyAsync(kps, s.d_kps, (size_t)N * sizeof(orbx_kp), cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(desc, s.d_desc, (size_t)N * 32, cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaStreamSynchronize(s.stream));
+  }
+  *n_mono = s.h_n[1];
+  return ORBX_OK;
+}
+
+int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {
+  if (!h) return ORBX_E_ARG;
+  int rc = check_image(h, img, w, hh, stride);
+  if (rc) return rc;
+  CU(h, cudaSetDevice(h->device));
+  rc = ensure_geometry(h, w, hh);
+  if (rc) return rc;
+  Slot& s = h->slot[0];
+  CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, img, stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
+  int nl = launch_import(h->g, s.b, s.d_img, h->img_pitch, h->img_pitch * hh, 1, s.stream);
+  nl += launch_pyramid(h->g, s.b, 1, s.stream);
+  nl += launch_border(h->g, s.b, 1, s.stream);
+  h->launches += nl;
+  h->last_frames = 1;
+  h->border_done = true;
+  CU(h, cudaStreamSynchronize(s.stream));
+  return ORBX_OK;
+}
+
+int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int* w, int* hh) {
+  if (!h) return ORBX_E_ARG;
+  if (!h->geom_valid || h->last_frames < 1) return fail(h, ORBX_E_ARG, "no pyramid has been computed");
+  if (lev < 0 || lev >= h->g.nlev) return fail(h, ORBX_E_ARG, "bad level");
+  const LevelGeom& L = h->g.lv[lev];
+  if (w) *w = L.w;
+  if (hh) *hh = L.h;
+  if (!dst) return ORBX_OK;
+  if (dst_stride < (size_t)(L.w + 2 * kEdge)) return fail(h, ORBX_E_ARG, "dst_stride too small");
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slot[0];
+  if (!h->border_done) {
+    h->launches += launch_border(h->g, s.b, h->last_frames, s.stream);
+    h->border_done = true;
+  }
+  CU(h, cudaMemcpy2DAsync(dst, dst_stride, s.b.pyr + px_off(L, -kEdge, -kEdge), (size_t)L.pitch, (size_t)(L.w + 2 * kEdge),
+                          (size_t)(L.h + 2 * kEdge), cudaMemcpyDeviceToHost, s.stream));
+  CU(h, cudaStreamSynchronize(s.stream));
+  return ORBX_OK;
+}
+
+int orbx_stage_download(orbx_t* h, int frame, int stage, int lev, void* dst, size_t dst_bytes, int* count) {
+  if (!h || !count) return ORBX_E_ARG;
+  if (!h->geom_valid || frame < 0 || frame >= h->last_frames) return fail(h, ORBX_E_ARG, "no such frame in the last call");
+  if (lev < 0 || lev >= h->g.nlev) return fail(h, ORBX_E_ARG, "bad level");
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slot[0];
+  const FrameGeom& g = h->g;
+  const LevelGeom& L = g.lv[lev];
+  CU(h, cudaStreamSynchronize(s.stream));
+  if (stage == ORBX_STAGE_LEVEL || stage == ORBX_STAGE_BLUR) {
+    const size_t need = (size_t)L.w * L.h;
+    *count = (int)need;
+    if (!dst) return ORBX_OK;
+    if (dst_bytes < need) return fail(h, ORBX_E_CAP, "need %zu bytes", need);
+    const uint8_t* base = (stage == ORBX_STAGE_LEVEL ? s.b.pyr : s.b.blur) + (size_t)frame * g.pyr_frame_bytes;
+    CU(h, cudaMemcpy2D(dst, (size_t)L.w, base + px_off(L, 0, 0), (size_t)L.pitch, (size_t)L.w, (size_t)L.h,
+                       cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+  }
+  if (stage != ORBX_STAGE_CAND && stage != ORBX_STAGE_SELECTED) return fail(h, ORBX_E_ARG, "bad stage");
+  const bool cand = stage == ORBX_STAGE_CAND;
+  int32_t cnt = 0;
+  CU(h, cudaMemcpy(&cnt, (cand ? s.b.n_cand : s.b.n_sel) + frame * ORBX_MAX_LEVELS + lev, sizeof(int32_t),
+                   cudaMemcpyDeviceToHost));
+  if (cnt < 0) return fail(h, ORBX_E_UNSUPPORTED, "quadtree node table overflow");
+  *count = cnt;
+  if (!dst || cnt == 0) return ORBX_OK;
+  if (dst_bytes < (size_t)cnt * 3 * sizeof(int32_t)) return fail(h, ORBX_E_CAP, "need %zu bytes", (size_t)cnt * 12);
+  std::vector<uint32_t> xy((size_t)cnt);
+  std::vector<uint8_t> sc((size_t)cnt);
+  const size_t off = cand ? (size_t)frame * g.cand_frame_cap + L.cand_off : (size_t)frame * g.sel_frame_cap + L.sel_off;
+  CU(h, cudaMemcpy(xy.data(), (cand ? s.b.cand_xy : s.b.sel_xy) + off, (size_t)cnt * 4, cudaMemcpyDeviceToHost));
+  CU(h, cudaMemcpy(sc.data(), (cand ? s.b.cand_sc : s.b.sel_sc) + off, (size_t)cnt, cudaMemcpyDeviceToHost));
+  int32_t* o = (int32_t*)dst;
+  for (int i = 0; i < cnt; i++) {
+    o[3 * i] = (int32_t)(xy[i] & 0xFFFFu);
+    o[3 * i + 1] = (int32_t)(xy[i] >> 16);
+    o[3 * i + 2] = sc[i];
+  }
+  return ORBX_OK;
+}
+
+int orbx_synth_frames(int device, int kind, uint8_t* dst, int n_frames, int w, int hh, size_t row_stride,
+                      size_t frame_stride, uint64_t seed, uint64_t first_frame, int shift_x, uint64_t noise_seed,
+                      void* stream) {
+  if (!dst || n_frames < 1 || w < 2 || hh < 1 || row_stride < (size_t)w || (kind != 0 && kind != 1)) return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  launch_synth(kind, dst, n_frames, w, hh, row_stride, frame_stride, seed, first_frame, shift_x, noise_seed,
+               (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
+}
+
+}  // extern "C"

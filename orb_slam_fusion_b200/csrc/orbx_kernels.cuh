@@ -19,7 +19,7 @@ struct BatchBuffers {
   uint32_t* sel_xy;     // [frames][sel_frame_cap]     (y << 16) | x, level coordinates
   uint8_t* sel_sc;      // [frames][sel_frame_cap]
   int32_t* n_sel;       // [frames][ORBX_MAX_LEVELS]
-  uint32_t* work;       // [frames][sel_frame_cap]     per output slot: (level << 28) | index into sel
+  int32_t* work;        // [frames][sel_frame_cap]     output slot of each selected keypoint (-1: does not fit)
   // resize coefficient tables of the current geometry, per level at tab_off
   const int16_t* xofs;   // source column of destination column
   const int16_t* xalpha; // 2 coefficients per destination column
@@ -35,8 +35,9 @@ int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStr
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_blur(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+// writes frame f of the batch to kps[(out_frame0 + f) * cap + slot], n[out_frame0 + f], ...
 int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_kp* kps, uint8_t* desc,
-                    int cap, int32_t* n, int32_t* n_mono, cudaStream_t st);
+                    int cap, int32_t* n, int32_t* n_mono, int out_frame0, cudaStream_t st);
 int launch_synth(int kind, uint8_t* dst, int frames, int w, int h, size_t row_stride, size_t frame_stride,
                  uint64_t seed, uint64_t first_frame, int shift_x, uint64_t noise_seed, cudaStream_t st);
 
@@ -56,12 +57,11 @@ int launch_ratio_test(const int64_t* idx, const int32_t* dist, int nq, double ra
 int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const orbx_kp* kr, const uint8_t* dr,
                           int nr, const float* sf, int n_levels, int n_rows, float min_d, float max_d,
                           int32_t* best_idx, int32_t* best_dist, cudaStream_t st);
-// scratch: window_scratch_ints(n, cells) int32
-size_t window_scratch_ints(int n, int cells);
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom,
                          const orbm_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
-                         int32_t* scratch, orbm_window_result* out, cudaStream_t st);
+                         orbm_window_result* out, cudaStream_t st);
 int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t seed, cudaStream_t st);
-int popc_peak(double* popc_per_s);
+// mode 0: popc.b32 per second; 1: plain 8-popc distances per second; 2: ham256 as built, per second
+int popc_bench(int mode, double* per_s);
 
 }  // namespace orbx

@@ -1,0 +1,164 @@
+"""Host-side mirror of ORB_SLAM_FUSION::ORBmatcher's data-parallel kernels
+(include/cam/orb_feature/orb_matcher.h:36-129) over the C ABI: DescriptorDistance
+(orb_matcher.cc:1877-1891), knnMatch(k=2) + ratio test (frame.cc:1154-1162), the stereo row-band
+search (frame.cc:836-900) and the best / second-best window search of SearchByProjection
+(orb_matcher.cc:66-113).  The greedy, pointer-chasing parts of the Search* methods stay with the
+caller, exactly as SURVEY.md section 3.3 scopes them."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+class ORBmatcher:
+    TH_LOW = 50        # orb_matcher.cc:35-37
+    TH_HIGH = 100
+    HISTO_LENGTH = 30
+
+    def __init__(self, nnratio=0.6, check_ori=True, device=0):
+        self.nnratio, self.check_ori, self.device = float(nnratio), bool(check_ori), int(device)
+        self._lib = A.lib()
+        self._m = A.vp()
+        rc = self._lib.orbm_create(self.device, C.byref(self._m))
+        if rc:
+            self._m = None
+            raise A.OrbxError(rc, "orbm_create failed (no CUDA device %d)" % self.device)
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.orbm_destroy(self._m)
+            self._m = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise A.OrbxError(rc, self._lib.orbm_last_error(self._m).decode())
+
+    def _stream(self, t):
+        import torch
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def launch_count(self):
+        return self._lib.orbm_launch_count(self._m)
+
+    def sync(self):
+        self._check(self._lib.orbm_sync(self._m))
+
+    # ---- DescriptorDistance
+    def DescriptorDistance(self, a, b):
+        """Hamming distance of two 32-byte descriptors, or row-wise of two [n,32] arrays."""
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.empty(len(a), np.int32)
+        self._check(self._lib.orbm_hamming_pairs(self._m, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data,
+                                                 A.MEM_HOST, None))
+        return int(out[0]) if len(out) == 1 else out
+
+    # ---- brute force 2-NN + ratio
+    def knn2(self, q, db, index_base=0):
+        """(idx[nq,2] int64, dist[nq,2] int32) ordered by (distance, index); numpy in -> numpy out,
+        CUDA tensors in -> CUDA tensors out (asynchronous on the current stream)."""
+        if _is_torch(q):
+            import torch
+            nq, nd = q.shape[0], db.shape[0]
+            idx = torch.empty((nq, 2), dtype=torch.int64, device=q.device)
+            dist = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+            self._check(self._lib.orbm_knn2(self._m, q.data_ptr(), nq, db.data_ptr(), nd, index_base, idx.data_ptr(),
+                                            dist.data_ptr(), A.MEM_DEVICE, self._stream(q)))
+            return idx, dist
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        db = np.ascontiguousarray(db, np.uint8).reshape(-1, 32)
+        idx = np.empty((len(q), 2), np.int64)
+        dist = np.empty((len(q), 2), np.int32)
+        self._check(self._lib.orbm_knn2(self._m, q.ctypes.data, len(q), db.ctypes.data, len(db), index_base,
+                                        idx.ctypes.data, dist.ctypes.data, A.MEM_HOST, None))
+        return idx, dist
+
+    def top2_merge(self, idx_parts, dist_parts):
+        """Merge [P,nq,2] partial top-2 lists into the global top-2."""
+        if _is_torch(idx_parts):
+            import torch
+            P, nq = idx_parts.shape[0], idx_parts.shape[1]
+            idx = torch.empty((nq, 2), dtype=torch.int64, device=idx_parts.device)
+            dist = torch.empty((nq, 2), dtype=torch.int32, device=idx_parts.device)
+            self._check(self._lib.orbm_top2_merge(self._m, idx_parts.data_ptr(), dist_parts.data_ptr(), P, nq,
+                                                  idx.data_ptr(), dist.data_ptr(), A.MEM_DEVICE, self._stream(idx_parts)))
+            return idx, dist
+        idx_parts = np.ascontiguousarray(idx_parts, np.int64)
+        dist_parts = np.ascontiguousarray(dist_parts, np.int32)
+        P, nq = idx_parts.shape[0], idx_parts.shape[1]
+        idx = np.empty((nq, 2), np.int64)
+        dist = np.empty((nq, 2), np.int32)
+        self._check(self._lib.orbm_top2_merge(self._m, idx_parts.ctypes.data, dist_parts.ctypes.data, P, nq,
+                                              idx.ctypes.data, dist.ctypes.data, A.MEM_HOST, None))
+        return idx, dist
+
+    def ratio_test(self, idx, dist, ratio=0.7):
+        if _is_torch(idx):
+            import torch
+            acc = torch.empty(idx.shape[0], dtype=torch.uint8, device=idx.device)
+            self._check(self._lib.orbm_ratio_test(self._m, idx.data_ptr(), dist.data_ptr(), idx.shape[0], ratio,
+                                                  acc.data_ptr(), A.MEM_DEVICE, self._stream(idx)))
+            return acc
+        idx = np.ascontiguousarray(idx, np.int64)
+        dist = np.ascontiguousarray(dist, np.int32)
+        acc = np.empty(len(idx), np.uint8)
+        self._check(self._lib.orbm_ratio_test(self._m, idx.ctypes.data, dist.ctypes.data, len(idx), ratio,
+                                              acc.ctypes.data, A.MEM_HOST, None))
+        return acc.astype(bool)
+
+    # ---- stereo row band
+    def stereo_rowband(self, kl, dl, kr, dr, scale_factors, n_rows, min_d, max_d):
+        kl = np.ascontiguousarray(kl, A.KP_DTYPE)
+        kr = np.ascontiguousarray(kr, A.KP_DTYPE)
+        dl = np.ascontiguousarray(dl, np.uint8)
+        dr = np.ascontiguousarray(dr, np.uint8)
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        bi = np.empty(len(kl), np.int32)
+        bd = np.empty(len(kl), np.int32)
+        self._check(self._lib.orbm_stereo_rowband(self._m, kl.ctypes.data, dl.ctypes.data, len(kl), kr.ctypes.data,
+                                                  dr.ctypes.data, len(kr), sf.ctypes.data, len(sf), int(n_rows),
+                                                  float(min_d), float(max_d), bi.ctypes.data, bd.ctypes.data,
+                                                  A.MEM_HOST, None))
+        return bi, bd
+
+    # ---- projection window
+    def window_search(self, kps, desc, geom, queries, qdesc, skip=None):
+        kps = np.ascontiguousarray(kps, A.KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        queries = np.ascontiguousarray(queries, A.WQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        out = np.empty(len(queries), A.WR_DTYPE)
+        g = A.GridGeom(*geom)
+        self._check(self._lib.orbm_window_search(self._m, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(g),
+                                                 queries.ctypes.data, qdesc.ctypes.data, len(queries),
+                                                 None if sk is None else sk.ctypes.data, out.ctypes.data, A.MEM_HOST, None))
+        return out
+
+
+def synth_descriptors(first, n, seed, device=0, out=None):
+    """[n,32] uint8 CUDA tensor of SURVEY.md 8(d) config-5 descriptors."""
+    import torch
+    dev = torch.device("cuda", device)
+    if out is None:
+        out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    rc = A.lib().orbm_synth_descriptors(device, out.data_ptr(), first, n, seed, torch.cuda.current_stream(dev).cuda_stream)
+    if rc:
+        raise A.OrbxError(rc, "orbm_synth_descriptors")
+    return out
+
+
+def popc_peak(mode=0, device=0):
+    v = C.c_double()
+    rc = A.lib().orbm_popc_peak(device, mode, C.byref(v))
+    if rc:
+        raise A.OrbxError(rc, "orbm_popc_peak")
+    return v.value

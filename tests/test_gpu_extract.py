@@ -1,0 +1,203 @@
+"""GPU parity of the extractor through the C ABI: every stage and the final outputs, bit for bit,
+against the committed golden vectors and the CPU oracle (correctly-rounded trig mode)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import EXTRACT_CASES, golden_image, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def P():
+    import orb_slam_fusion_b200 as P
+    return P
+
+
+def grid_geom(w, h):
+    width, height = np.float32(w - 32), np.float32(h - 32)
+    ncols, nrows = int(width / np.float32(35)), int(height / np.float32(35))
+    return int(np.ceil(width / np.float32(ncols))), int(np.ceil(height / np.float32(nrows))), ncols
+
+
+def reference_order(cand, w, h):
+    """Sort (x, y, r) candidates the way the reference's grid loop emits them (orb_extractor.cc:767-823)."""
+    wcell, hcell, ncols = grid_geom(w, h)
+    x, y = cand[:, 0].astype(np.int64), cand[:, 1].astype(np.int64)
+    key = (((y - 3) // hcell * ncols + (x - 3) // wcell) * hcell + (y - 3) % hcell) * wcell + (x - 3) % wcell
+    return cand[np.argsort(key, kind="stable")]
+
+
+@pytest.mark.parametrize("name", EXTRACT_CASES)
+def test_extract_matches_golden_and_oracle(P, oracle, name):
+    g = load_golden(name)
+    img = golden_image(g)
+    nf, nl, lap = int(g["num_feats"]), int(g["num_levs"]), tuple(int(v) for v in g["lap"])
+    ex = P.OrbExtractor(nf, 1.2, nl, 20, 7)
+    n_mono, kps, desc = ex(img, None, lap)
+    from orb_slam_fusion_b200 import _abi as A
+    for lev in range(nl):
+        lvl = ex.stage(A.STAGE_LEVEL, lev)
+        assert sha(lvl) == str(g["level_sha"][lev]), "pyramid level %d" % lev
+        cand = reference_order(ex.stage(A.STAGE_CAND, lev), lvl.shape[1], lvl.shape[0])
+        assert len(cand) == int(g["n_cand"][lev])
+        assert sha(cand) == str(g["cand_sha"][lev]), "FAST candidates level %d" % lev
+        assert len(ex.stage(A.STAGE_SELECTED, lev)) == int(g["n_sel"][lev])
+        if str(g["blur_sha"][lev]):
+            assert sha(ex.stage(A.STAGE_BLUR, lev)) == str(g["blur_sha"][lev]), "blur level %d" % lev
+    assert n_mono == int(g["n_mono"])
+    assert kps.tobytes() == g["kps"].tobytes()   # order, coordinates, angle, response: bit for bit
+    ref = oracle.Extractor(nf, 1.2, nl, 20, 7, trig=oracle.TRIG_CR)
+    rn, rk, rd = ref(img, lap)
+    assert rk.tobytes() == kps.tobytes() and np.array_equal(desc, rd)
+    # libm cosf/sinf (what the golden vectors were made with) may differ from the correctly rounded
+    # values by 1 ulp; a descriptor bit flips only if a rotated coordinate sits on a .5 tie
+    bad_rows = int((desc != g["desc"]).any(axis=1).sum())
+    assert bad_rows <= max(1, len(desc) // 500), bad_rows
+
+
+def test_stagewise_small_frame(P, oracle):
+    from orb_slam_fusion_b200 import _abi as A
+    g = load_golden("stages_320x240_300_l4")
+    img = g["img"]
+    ex = P.OrbExtractor(300, 1.2, 4, 20, 7)
+    n_mono, kps, desc = ex(img)
+    assert kps.tobytes() == g["kps"].tobytes()
+    assert int((desc != g["desc"]).any(axis=1).sum()) <= 1
+    for lev in range(4):
+        lvl = g["level%d" % lev]
+        assert np.array_equal(ex.stage(A.STAGE_LEVEL, lev), lvl)
+        assert np.array_equal(reference_order(ex.stage(A.STAGE_CAND, lev), lvl.shape[1], lvl.shape[0]), g["cand%d" % lev])
+        gs = g["sel%d" % lev]
+        sel = ex.stage(A.STAGE_SELECTED, lev)
+        assert np.array_equal(sel[:, 0], gs["x"].astype(np.int32)) and np.array_equal(sel[:, 1], gs["y"].astype(np.int32))
+        assert np.array_equal(sel[:, 2], gs["response"].astype(np.int32))
+        assert np.array_equal(ex.stage(A.STAGE_BLUR, lev), g["blur%d" % lev])
+
+
+def test_pyramid_with_border_and_tables(P, oracle):
+    img = oracle.blocks_v1(640, 480, 5, 2)
+    ex = P.OrbExtractor(1000, 1.2, 8, 20, 7)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    ref.compute_pyramid(img)
+    ex.ComputePyramid(img)
+    for lev in range(8):
+        want = ref.level(lev, with_border=True)
+        got = ex.pyramid_level(lev, with_border=True)
+        assert got.shape == want.shape and np.array_equal(got, want), lev
+    pyr = ex.img_pyramid_
+    assert pyr[3].shape == ref.level(3).shape and np.array_equal(pyr[3], ref.level(3))
+    t = ref.tables()
+    assert np.array_equal(ex.GetScaleFactors(), t["scale"]) and np.array_equal(ex.GetInverseScaleFactors(), t["inv_scale"])
+    assert np.array_equal(ex.GetScaleSigmaSquares(), t["sigma2"]) and np.array_equal(ex.GetInverseScaleSigmaSquares(), t["inv_sigma2"])
+    assert np.array_equal(ex.features_per_level(), t["quota"]) and ex.GetLevels() == 8
+    # the border is also available after operator() (frame.cc:834,913-931 read img_pyramid_)
+    ex(img)
+    assert np.array_equal(ex.pyramid_level(2, with_border=True), ref.level(2, with_border=True))
+
+
+def test_error_behaviour(P, oracle):
+    from orb_slam_fusion_b200 import _abi as A
+    ex = P.OrbExtractor(1000, 1.2, 8, 20, 7)
+    n_mono, kps, desc = ex(np.empty((0, 0), np.uint8))
+    assert n_mono == -1 and len(kps) == 0 and desc.shape == (0, 32)   # orb_extractor.cc:1016
+    with pytest.raises(P.OrbxError) as e:   # level 7 of 200x150 is smaller than one FAST cell
+        ex(oracle.blocks_v1(200, 150, 1, 0))
+    assert e.value.code == A.E_UNSUPPORTED
+    with pytest.raises(P.OrbxError):
+        P.OrbExtractor(1000, 1.2, 99, 20, 7)
+    # flat image: no corners anywhere -> zero keypoints, n_mono 0 (descs.release(), :1033-1034)
+    n_mono, kps, desc = ex(np.full((480, 752), 90, np.uint8))
+    assert n_mono == 0 and len(kps) == 0
+    # same handle, new geometry
+    img = oracle.blocks_v1(752, 480, 1, 0)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    assert ex(img)[1].tobytes() == ref(img)[1].tobytes()
+
+
+@pytest.mark.parametrize("kind,w,h,nf", [("uniform", 640, 480, 1500), ("blocks", 1241, 376, 2000), ("blocks", 511, 389, 600),
+                                         ("blocks", 1920, 1080, 5000)])
+def test_more_geometries_vs_oracle(P, oracle, kind, w, h, nf):
+    img = (oracle.uniform_v1 if kind == "uniform" else oracle.blocks_v1)(w, h, 9, 1)
+    ex = P.OrbExtractor(nf, 1.2, 8, 20, 7)
+    ref = oracle.Extractor(nf, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    n_mono, kps, desc = ex(img)
+    rn, rk, rd = ref(img)
+    assert n_mono == rn and kps.tobytes() == rk.tobytes() and np.array_equal(desc, rd)
+
+
+def test_other_parameters_vs_oracle(P, oracle):
+    img = oracle.blocks_v1(800, 600, 4, 7)
+    for (nf, sf, nl, ini, mn) in [(500, 1.5, 5, 30, 10), (1200, 1.1, 10, 12, 12), (300, 2.0, 3, 9, 20)]:
+        ex = P.OrbExtractor(nf, sf, nl, ini, mn)
+        ref = oracle.Extractor(nf, sf, nl, ini, mn, trig=oracle.TRIG_CR)
+        n_mono, kps, desc = ex(img, None, (100, 300))
+        rn, rk, rd = ref(img, (100, 300))
+        assert n_mono == rn and kps.tobytes() == rk.tobytes() and np.array_equal(desc, rd), (nf, sf, nl)
+
+
+def test_batch_host_and_device(P, oracle):
+    import torch
+    F, w, h = 11, 752, 480
+    imgs = np.stack([oracle.blocks_v1(w, h, 1, f) for f in range(F)])
+    ex = P.OrbExtractor(1000, 1.2, 8, 20, 7, max_batch=4)      # 3 chunks, ping-pong working sets
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    want = [ref(imgs[f]) for f in range(F)]
+    n, nm, kps, desc = ex.extract_batch(imgs)
+    dimgs = torch.from_numpy(imgs).cuda()
+    dn, dnm, dkps, ddesc = ex.extract_batch(dimgs)
+    torch.cuda.synchronize()
+    dkps = dkps.cpu().numpy().view(P.KP_DTYPE).reshape(F, -1)
+    for f in range(F):
+        rn, rk, rd = want[f]
+        for (a_n, a_nm, a_k, a_d) in [(n, nm, kps, desc), (dn.cpu().numpy(), dnm.cpu().numpy(), dkps, ddesc.cpu().numpy())]:
+            assert a_n[f] == len(rk) and a_nm[f] == rn
+            assert a_k[f, :len(rk)].tobytes() == rk.tobytes() and np.array_equal(a_d[f, :len(rk)], rd)
+    # a capacity that is too small is reported per frame and nothing is written for that frame
+    n2, _, _, _ = ex.extract_batch(imgs[:2], cap=500)
+    assert (n2 == -np.array([len(want[0][1]), len(want[1][1])])).all()
+
+
+def test_device_synth_equals_oracle_generators(P, oracle):
+    fr = P.synth_frames("blocks", 3, 752, 480, seed=1, first_frame=5).cpu().numpy()
+    for f in range(3):
+        assert np.array_equal(fr[f], oracle.blocks_v1(752, 480, 1, 5 + f))
+    fr = P.synth_frames("blocks", 1, 752, 480, seed=1, first_frame=2, shift_x=12, noise_seed=2).cpu().numpy()
+    assert np.array_equal(fr[0], oracle.blocks_v1(752, 480, 1, 2, shift_x=12, noise_seed=2))
+    fr = P.synth_frames("uniform", 2, 400, 300, seed=7).cpu().numpy()
+    assert np.array_equal(fr[1], oracle.uniform_v1(400, 300, 7, 1))
+
+
+def test_full_size_batch_properties(P, oracle):
+    """BASELINE config 3 (64 KITTI-shaped frames, 2000 features) on device-generated frames:
+    spot frames equal the oracle, the run is deterministic, and every frame obeys the quotas."""
+    import torch
+    F, w, h = 64, 1241, 376
+    frames = P.synth_frames("blocks", F, w, h, seed=1)
+    ex = P.OrbExtractor(2000, 1.2, 8, 20, 7, max_batch=32)
+    n, nm, kps, desc = ex.extract_batch(frames)
+    n2, nm2, kps2, desc2 = ex.extract_batch(frames)
+    torch.cuda.synchronize()
+    assert torch.equal(n, n2) and torch.equal(nm, nm2)
+    n = n.cpu().numpy()
+    for f in range(F):   # rows beyond n[f] are not written
+        assert torch.equal(desc[f, :n[f]], desc2[f, :n[f]])
+        assert torch.equal(kps[f, :n[f]].view(torch.int32), kps2[f, :n[f]].view(torch.int32))
+    quota = ex.features_per_level()
+    assert (n > 1900).all() and (n <= quota.sum() + 3 * 8).all() and (nm.cpu().numpy() == n).all()
+    k = kps.cpu().numpy().view(P.KP_DTYPE).reshape(F, -1)
+    ref = oracle.Extractor(2000, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    for f in (0, 31, 32, 63):
+        rn, rk, rd = ref(frames[f].cpu().numpy())
+        assert n[f] == len(rk) and k[f, :n[f]].tobytes() == rk.tobytes()
+        assert np.array_equal(desc[f, :n[f]].cpu().numpy(), rd)
+    for f in range(F):
+        oc = k[f, :n[f]]["octave"]
+        assert (np.diff(oc) >= 0).all()                      # levels ascending (mono block, lap {0,0})
+        assert (np.bincount(oc, minlength=8) <= quota + 3).all()

@@ -1,0 +1,195 @@
+"""GPU parity of the Hamming matching kernels through the C ABI against the golden BFMatcher vectors
+and the CPU oracle: distances, 2-NN with ties, sharded merge, ratio test, stereo row band, windows."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def P():
+    import orb_slam_fusion_b200 as P
+    return P
+
+
+@pytest.fixture(scope="module")
+def m(P):
+    return P.ORBmatcher(0.7, True)
+
+
+def test_descriptor_distance(P, m, oracle):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (5000, 32), dtype=np.uint8)
+    b[:100] = a[:100]
+    b[100:200] = ~a[100:200]
+    want = np.array([oracle.hamming(x, y) for x, y in zip(a, b)], np.int32)
+    assert np.array_equal(m.DescriptorDistance(a, b), want)
+    assert want[:100].max() == 0 and want[100:200].min() == 256
+    assert m.DescriptorDistance(a[7], b[7]) == want[7]
+    # 4-byte aligned rows, as cv::Mat::ptr<int32_t> (orb_matcher.cc:1879-1880)
+    buf = np.zeros(5000 * 32 + 4, np.uint8)
+    buf[4:] = a.reshape(-1)
+    assert np.array_equal(m.DescriptorDistance(buf[4:].reshape(-1, 32), b), want)
+    assert P.ORBmatcher.TH_LOW == 50 and P.ORBmatcher.TH_HIGH == 100 and P.ORBmatcher.HISTO_LENGTH == 30
+
+
+def test_knn2_golden_bfmatcher(m, oracle):
+    g = load_golden("knn2_200x5000")
+    idx, dist = m.knn2(g["q"], g["db"])
+    assert np.array_equal(idx, g["idx"]) and np.array_equal(dist, g["dist"])
+    assert np.array_equal(m.ratio_test(idx, dist, 0.7), g["accept"])
+
+
+def test_knn2_ties_and_small_databases(m, oracle):
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (1100, 32), dtype=np.uint8)       # > one 1024-query block
+    base = rng.integers(0, 256, (40, 32), dtype=np.uint8)
+    db = base[rng.integers(0, 40, 3000)].copy()                 # many exact duplicates -> ties
+    flips = rng.integers(0, 256, 3000)
+    db[np.arange(3000), flips % 32] ^= (1 << (flips // 32)).astype(np.uint8)
+    q[:40] = base
+    for nd in (3000, 257, 256, 2, 1, 0):
+        idx, dist = m.knn2(q, db[:nd])
+        ri, rd = oracle.knn2(q, db[:nd])
+        assert np.array_equal(idx, ri) and np.array_equal(dist, rd), nd
+        acc = m.ratio_test(idx, dist, 0.7)
+        assert np.array_equal(acc, oracle.ratio_accept(ri, rd, 0.7))
+    idx, dist = m.knn2(q[:0], db)
+    assert idx.shape == (0, 2)
+
+
+def test_sharded_top2_merge_equals_whole(m, oracle):
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    db = rng.integers(0, 4, (20000, 32), dtype=np.uint8)        # low-entropy rows: plenty of distance ties
+    whole_i, whole_d = m.knn2(q, db)
+    ri, rd = oracle.knn2(q, db)
+    assert np.array_equal(whole_i, ri) and np.array_equal(whole_d, rd)
+    for G in (2, 3, 8):
+        bounds = [len(db) * s // G for s in range(G + 1)]
+        parts = [m.knn2(q, db[bounds[s]:bounds[s + 1]], index_base=bounds[s]) for s in range(G)]
+        pi = np.stack([p[0] for p in parts])
+        pd = np.stack([p[1] for p in parts])
+        mi, md = m.top2_merge(pi[::-1].copy(), pd[::-1].copy())   # shard order must not matter
+        assert np.array_equal(mi, whole_i) and np.array_equal(md, whole_d), G
+    # a shard with a single row contributes one neighbour and a missing entry
+    parts = [m.knn2(q, db[:1]), m.knn2(q, db[1:], index_base=1)]
+    mi, md = m.top2_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    assert np.array_equal(mi, whole_i) and np.array_equal(md, whole_d)
+
+
+def test_config5_reduced_with_planted_matches(P, m, oracle):
+    """BASELINE config 5 at 1/50 size: device-generated database, planted matches and decoys."""
+    import torch
+    nq, nd = 1000, 200_000
+    db = P.synth_descriptors(0, nd, seed=101)
+    q = P.synth_descriptors(0, nq, seed=202)
+    assert np.array_equal(db[:64].cpu().numpy(), oracle.synth_descriptors(0, 64, 101))
+    dbh, qh = db.cpu().numpy().copy(), q.cpu().numpy()
+    rng = np.random.default_rng(1)
+    rows = rng.choice(nd, nq, replace=False)
+    for i in range(nq):
+        d = qh[i].copy()
+        bits = rng.choice(256, 5 + int(rng.integers(0, 36)), replace=False)
+        np.bitwise_xor.at(d, bits // 8, (1 << (bits % 8)).astype(np.uint8))
+        dbh[rows[i]] = d
+        if i % 10 == 0:
+            e = d.copy()
+            bits = rng.choice(256, int(rng.integers(0, 11)), replace=False)
+            np.bitwise_xor.at(e, bits // 8, (1 << (bits % 8)).astype(np.uint8))
+            dbh[(rows[i] + 1) % nd] = e
+    db = torch.from_numpy(dbh).cuda()
+    idx, dist = m.knn2(q, db)
+    acc = m.ratio_test(idx, dist, 0.7)
+    torch.cuda.synchronize()
+    ri, rd = oracle.knn2(qh, dbh, nthreads=8)
+    assert np.array_equal(idx.cpu().numpy(), ri) and np.array_equal(dist.cpu().numpy(), rd)
+    racc = oracle.ratio_accept(ri, rd, 0.7)
+    assert np.array_equal(acc.cpu().numpy().astype(bool), racc)
+    assert 0.85 < racc.mean() < 0.95     # the decoys (every 10th query) fail the ratio test
+
+
+def test_full_size_database_properties(P, m):
+    """Config 5 at full size (1000 x 10M): the planted rows are found (known answer by construction)
+    and an 8-way sharded search merged with top2_merge equals the single search."""
+    import torch
+    nq, nd = 1000, 10_000_000
+    db = P.synth_descriptors(0, nd, seed=7)
+    q = P.synth_descriptors(0, nq, seed=8)
+    rows = torch.arange(nq, device="cuda", dtype=torch.int64) * 9973 + 12345
+    planted = q.clone()
+    planted[:, 0] ^= 0xFF          # 8 flipped bits: distance 8, random rows sit near 128
+    db[rows] = planted
+    idx, dist = m.knn2(q, db)
+    torch.cuda.synchronize()
+    assert torch.equal(idx[:, 0], rows) and (dist[:, 0] == 8).all()
+    assert (dist[:, 1] > 60).all() and (dist[:, 1] < 128).all()
+    assert m.ratio_test(idx, dist, 0.7).all()
+    G = 8
+    parts = [m.knn2(q, db[nd * s // G: nd * (s + 1) // G], index_base=nd * s // G) for s in range(G)]
+    mi, md = m.top2_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    torch.cuda.synchronize()
+    assert torch.equal(mi, idx) and torch.equal(md, dist)
+
+
+def test_stereo_rowband_config2(P, m, oracle):
+    """BASELINE config 2: EuRoC-shaped stereo pair, 1200 features per side, left-right search."""
+    w, h = 752, 480
+    left = oracle.blocks_v1(w, h, 1, 3)
+    right = oracle.blocks_v1(w, h, 1, 3, shift_x=12, noise_seed=2)
+    exl, exr = P.OrbExtractor(1200, 1.2, 8, 20, 7), P.OrbExtractor(1200, 1.2, 8, 20, 7)
+    _, kl, dl = exl(left)
+    _, kr, dr = exr(right)
+    sf = exl.GetScaleFactors()
+    for (min_d, max_d) in [(0.0, 458.654), (0.0, 20.0), (5.0, 60.0)]:
+        bi, bd = m.stereo_rowband(kl, dl, kr, dr, sf, h, min_d, max_d)
+        ri, rd = oracle.stereo_rowband(kl, dl, kr, dr, sf, h, min_d, max_d)
+        assert np.array_equal(bi, ri) and np.array_equal(bd, rd)
+    assert (ri >= 0).sum() > 300
+    # degenerate sides
+    bi, bd = m.stereo_rowband(kl, dl, kr[:0], dr[:0], sf, h, 0.0, 458.654)
+    assert (bi == -1).all() and (bd == 100).all()
+
+
+def test_window_search(P, m, oracle):
+    w, h = 752, 480
+    img = oracle.blocks_v1(w, h, 1, 0)
+    ex = P.OrbExtractor(1000, 1.2, 8, 20, 7)
+    _, kps, desc = ex(img)
+    geom = (0.0, 0.0, 64.0 / w, 48.0 / h, 64, 48)       # frame.cc:199-204, frame.h:40-41
+    rng = np.random.default_rng(2)
+    nq = 1500
+    src = rng.integers(0, len(kps), nq)
+    q = np.zeros(nq, P.WQ_DTYPE)
+    q["u"] = kps["x"][src] + rng.normal(0, 6, nq).astype(np.float32)
+    q["v"] = kps["y"][src] + rng.normal(0, 6, nq).astype(np.float32)
+    q["r"] = rng.choice([3.0, 7.0, 15.0, 40.0, 120.0], nq).astype(np.float32)
+    lv = kps["octave"][src]
+    q["min_level"] = np.where(rng.random(nq) < 0.5, lv - 1, -1)
+    q["max_level"] = np.where(rng.random(nq) < 0.5, lv + 1, -1)
+    q["u"][:20] = -500.0                                  # windows that miss the image
+    q["v"][20:40] = 5000.0
+    qdesc = desc[src].copy()
+    flips = rng.integers(0, 256, (nq, 12))
+    for j in range(12):
+        qdesc[np.arange(nq), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+    qdesc[::7] = desc[src[::7]]                           # exact duplicates -> distance-0 ties
+    for skip in (None, (rng.random(len(kps)) < 0.3).astype(np.uint8)):
+        got = m.window_search(kps, desc, geom, q, qdesc, skip)
+        want = oracle.window_search(kps, desc, geom, q, qdesc, skip)
+        assert got.tobytes() == want.tobytes()
+    assert (want["best_idx"] >= 0).mean() > 0.5
+    # duplicated keypoints make (distance) ties that only the visiting order resolves
+    k2 = np.concatenate([kps, kps[:200]])
+    d2 = np.concatenate([desc, desc[:200]])
+    got = m.window_search(k2, d2, geom, q, qdesc)
+    want = oracle.window_search(k2, d2, geom, q, qdesc)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_popc_peak_microbenchmark(P):
+    peak = P.popc_peak(0)
+    assert 1e12 < peak < 2e13      # 148 SMs x 16 popc/clk x ~1.9 GHz = 4.5e12
