@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py -- ORB front-end throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one pass of OrbExtractor::operator() over one batch of synthetic EuRoC-shaped frames
+(blocks-v1, 752x480, 1000 features, 8 levels, 1.2, FAST 20/7).  `value` is frames/s with the
+frames resident in HBM; `e2e` is the same batch through the C ABI with pinned HOST buffers
+(H2D of the frames and D2H of keypoints + descriptors inside the timed region).  Also reported:
+p50 latency of one blocking single-frame call, brute-force Hamming search (config 5:
+1000 queries x 10M rows sharded over the ranks, NCCL all-gather of the per-rank top-2), the
+roofline of the dominant kernel from live CUDA-event stage timings, and the reference's CPU
+extractor timed on this host (oracle/_ref: the reference's orb_extractor.cc on the mini-cv shim).
+With --impl reference only that CPU implementation is timed (all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NFEAT, NLEV, SCALE, INI_TH, MIN_TH = 752, 480, 1000, 8, 1.2, 20, 7
+METRIC = "orb_frames_per_s_752x480_1000kp"
+DB_ROWS, N_QUERIES = 10_000_000, 1000
+
+
+def level_sizes(w, h):
+    s, out = np.float32(1.0), []
+    for l in range(NLEV):
+        if l:
+            s = np.float32(np.float64(s) * np.float64(np.float32(SCALE)))
+        inv = np.float32(1.0) / s
+        out.append((int(np.rint(np.float32(w) * inv)), int(np.rint(np.float32(h) * inv))))
+    return out
+
+
+def algorithmic_bytes(w, h, n_kp):
+    """compulsory bytes per frame, per stage (every stage reads its input once and
+    writes its output once, u8)."""
+    px = [a * b for a, b in level_sizes(w, h)]
+    return {
+        "pyramid": sum(px[:-1]) + sum(px[1:]),
+        "fast": sum(px),
+        "blur": 2 * sum(px),
+        "describe": n_kp * 749 + n_kp * (512 + 32 + 28),
+    }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_rate(threads, frames_per_thread, first_frame=0):
+    """Frames/s of the reference's own orb_extractor.cc (oracle/_ref) or, where that binary is
+    missing, of the oracle port; one extractor object per thread (frame.cc:179-182 runs one
+    extractor per image thread).  Returns (frames/s, kind)."""
+    from oracle import oracle as O
+    from oracle import ref as R
+    kind = "reference" if R.available(try_build=False) else "port"
+    mk = (lambda: R.Extractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH)) if kind == "reference" else \
+         (lambda: O.Extractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH))
+    imgs = [[O.blocks_v1(W, H, 1, first_frame + t * frames_per_thread + f) for f in range(frames_per_thread)]
+            for t in range(threads)]
+    exs = [mk() for _ in range(threads)]
+    counts = [0] * threads
+
+    def work(t):
+        for im in imgs[t]:
+            exs[t](im)
+            counts[t] += 1
+
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return sum(counts) / dt, kind, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_thread = 4
+    for _ in range(args.warmup):
+        cpu_reference_rate(threads, 1)
+    rates, total = [], 0.0
+    for s in range(args.steps):
+        r, kind, dt = cpu_reference_rate(threads, per_thread, first_frame=s * threads * per_thread)
+        rates.append(r)
+        total += dt
+    value = threads * per_thread * args.steps / total
+    sample = "%d steps x %d frames (%d threads x %d), blocks-v1 752x480" % (args.steps, threads * per_thread, threads, per_thread)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
+                   "frames_per_step": threads * per_thread},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------- B200 arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import orb_slam_fusion_b200 as P
+    from orb_slam_fusion_b200 import _abi as A
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    B = args.batch
+    frames = P.synth_frames("blocks", B, W, H, seed=1, first_frame=rank * B, device=local)
+    ex = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=B)
+    cap = ex.max_keypoints() + 8
+    kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
+    desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    n = torch.empty(B, dtype=torch.int32, device=dev)
+    nm = torch.empty(B, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def step():
+        ex.extract_batch_into(frames.data_ptr(), B, W, H, frames.stride(1), frames.stride(0), A.MEM_DEVICE, (0, 0),
+                              kps.data_ptr(), desc.data_ptr(), cap, n.data_ptr(), nm.data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ex.set_profiling(True)
+    ex.stage_times(reset=True)
+    launches0 = ex.launch_count()
+    clocks = ClockSampler(local)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    clk = clocks.stop()
+    stage_ms, chunks = ex.stage_times(reset=True)
+    ex.set_profiling(False)
+    launches = ex.launch_count() - launches0
+    n_host = n.cpu().numpy()
+    assert (n_host > 0).all(), "extraction failed"
+    mean_kp = float(n_host.mean())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    eb = ex_e2e = None
+    eb = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=min(64, B))
+    h_frames = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
+    h_frames.copy_(frames)
+    h_kps = torch.empty((B, cap, 7), dtype=torch.float32, pin_memory=True)
+    h_desc = torch.empty((B, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_n = torch.empty(B, dtype=torch.int32, pin_memory=True)
+    h_nm = torch.empty(B, dtype=torch.int32, pin_memory=True)
+
+    def step_e2e():
+        eb.extract_batch_into(h_frames.data_ptr(), B, W, H, W, W * H, A.MEM_HOST, (0, 0), h_kps.data_ptr(),
+                              h_desc.data_ptr(), cap, h_n.data_ptr(), h_nm.data_ptr(), None)
+
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert np.array_equal(h_n.numpy(), n_host), "host-memory path disagrees with device-memory path"
+    e2e = {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
+           "d2h_bytes_per_step": B * (cap * (28 + 32) + 8), "ms_per_step": 1e3 * e2e_s / args.steps}
+    del eb, h_kps, h_desc
+
+    # ---- p50 latency of one blocking single-frame call (config 1), rank 0
+    p50 = None
+    if rank == 0:
+        ex1 = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=1)
+        img = h_frames[0].numpy()
+        for _ in range(20):
+            ex1(img)
+        lat = []
+        for _ in range(300):
+            t0 = time.perf_counter()
+            ex1(img)
+            lat.append(time.perf_counter() - t0)
+        p50 = 1e3 * float(np.median(lat))
+        del ex1
+
+    # ---- Hamming search: 1000 queries x 10M rows, rows sharded over the ranks (config 5)
+    m = P.ORBmatcher(0.7, device=local)
+    r0, r1 = DB_ROWS * rank // world, DB_ROWS * (rank + 1) // world
+    db = P.synth_descriptors(r0, r1 - r0, seed=7, device=local)
+    q = P.synth_descriptors(0, N_QUERIES, seed=8, device=local)
+    gi = torch.empty((world, N_QUERIES, 2), dtype=torch.int64, device=dev)
+    gd = torch.empty((world, N_QUERIES, 2), dtype=torch.int32, device=dev)
+
+    def match_step():
+        idx, dd = m.knn2(q, db, index_base=r0)
+        if world > 1:
+            dist.all_gather_into_tensor(gi, idx)
+            dist.all_gather_into_tensor(gd, dd)
+            idx, dd = m.top2_merge(gi, gd)
+        return idx, dd, m.ratio_test(idx, dd, 0.7)
+
+    for _ in range(2):
+        match_step()
+    barrier()
+    m0 = torch.cuda.Event(enable_timing=True)
+    m1 = torch.cuda.Event(enable_timing=True)
+    reps = 5
+    m0.record()
+    for _ in range(reps):
+        match_step()
+    m1.record()
+    torch.cuda.synchronize()
+    match_ms = max_over_ranks(m0.elapsed_time(m1)) / reps
+    barrier()
+    pairs_per_s = N_QUERIES * DB_ROWS / (match_ms * 1e-3)
+    matching = {"value": pairs_per_s, "unit": "pair-distances/s", "ms_per_search": match_ms,
+                "queries_per_s": N_QUERIES / (match_ms * 1e-3), "workload": "1000 queries x 10M rows, top-2 + ratio 0.7",
+                "sharding": "database rows over %d rank(s), all-gather of per-rank top-2" % world}
+    if rank == 0:
+        popc = P.popc_peak(0, local)
+        plain = P.popc_peak(1, local)
+        matching.update({"popc_peak_per_s": popc, "plain_distance_peak_per_s": plain,
+                         "frac_of_popc_roofline": 8 * pairs_per_s / (world * popc),
+                         "frac_of_plain_distance_peak": pairs_per_s / (world * plain)})
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event stage times over the timed region)
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(W, H, mean_kp)
+    per_launch_ms = {k: v / max(chunks, 1) for k, v in stage_ms.items()}
+    dom = max(per_launch_ms, key=per_launch_ms.get)
+    # algorithmic bytes of stages outside SURVEY 8(d)'s formula: the import copy is overhead (0), the
+    # quadtree reads the candidate list once and writes the selection (5 B per entry)
+    alg_stage = dict(alg)
+    alg_stage["import"] = 0
+    alg_stage["octree"] = 5 * mean_kp * 2
+    dom_bytes = alg_stage[dom] * B
+    achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
+    total_alg = sum(alg.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_frame": alg_stage[dom], "frames_per_launch": B,
+                "launch_ms": per_launch_ms[dom],
+                "pipeline": {"algorithmic_bytes_per_frame": total_alg,
+                             "achieved": total_alg * (value / world) / 1e9, "frac": total_alg * (value / world) / 1e9 / peak},
+                "stage_ms_per_launch": per_launch_ms,
+                "stage_share": {k: v / sum(per_launch_ms.values()) for k, v in per_launch_ms.items()}}
+
+    # ---- the reference's CPU extractor on this host, bounded sample, 1 thread
+    cpu = None
+    if world == 1:
+        nfr = 0
+        t0 = time.perf_counter()
+        rate, kind, dt = cpu_reference_rate(1, 40)
+        nfr += 40
+        # extend the sample to ~10 s of CPU work
+        extra = int(min(2000, max(0, (10.0 - dt) * rate)))
+        if extra > 40:
+            rate2, kind, dt2 = cpu_reference_rate(1, extra, first_frame=40)
+            rate = (40 + extra) / (dt + dt2)
+            nfr += extra
+        cpu = {"value": rate, "unit": "frames/s", "cores": 1, "kind": kind,
+               "sample": "%d blocks-v1 752x480 frames, one extractor object on one thread; host has %d logical cores"
+                         % (nfr, os.cpu_count() or 0)}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
+                   "frames_per_step_per_gpu": B, "mean_keypoints_per_frame": mean_kp,
+                   "l2": "inputs larger than L2 (%.0f MB of frames + %.1f GB working set per step)"
+                         % (B * W * H / 1e6, B * 7.5e6 / 1e9)},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "p50_ms_per_frame": p50, "matching": matching,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,6 +46,12 @@ struct orbx_extractor {
   int last_frames = 0;       // frames of the last chunk processed on slot 0
   bool border_done = false;  // REFLECT_101 frames of slot 0's pyramid are up to date
   long long launches = 0;
+  // optional per-stage timing (orbx_set_profiling): one event set per enqueued chunk
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;   // free events
+  std::vector<cudaEvent_t> ev_used;   // ORBX_N_STAGES + 1 events per chunk, in order
+  double stage_ms[ORBX_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  long long stage_chunks = 0;
   char err[256] = "";
 };
 
@@ -260,12 +266,27 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   g.lap0 = lap0;
   g.lap1 = lap1;
   int n = 0;
+  auto mark = [&]() {
+    if (!h->profiling) return;
+    cudaEvent_t e;
+    if (!h->ev_pool.empty()) { e = h->ev_pool.back(); h->ev_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    h->ev_used.push_back(e);
+  };
+  mark();
   n += launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
+  mark();
   n += launch_pyramid(g, s.b, frames, st);
+  mark();
   n += launch_fast(g, s.b, frames, st);
+  mark();
   n += launch_octree(g, s.b, frames, st);
+  mark();
   n += launch_blur(g, s.b, frames, st);
+  mark();
   n += launch_describe(g, s.b, frames, d_kps, d_desc, cap, d_n, d_nmono, out_frame0, st);
+  mark();
   h->launches += n;
 }
 
@@ -305,6 +326,8 @@ void orbx_destroy(orbx_t* h) {
   for (auto& s : h->slot)
     if (s.stream) cudaStreamSynchronize(s.stream);
   free_geometry(h);
+  for (cudaEvent_t e : h->ev_used) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (auto& s : h->slot)
     if (s.stream) cudaStreamDestroy(s.stream);
   delete h;
@@ -339,6 +362,36 @@ int orbx_sync(orbx_t* h) {
 }
 
 long long orbx_launch_count(const orbx_t* h) { return h ? h->launches : 0; }
+
+int orbx_set_profiling(orbx_t* h, int on) {
+  if (!h) return ORBX_E_ARG;
+  h->profiling = on != 0;
+  return ORBX_OK;
+}
+
+int orbx_stage_times(orbx_t* h, double* ms, long long* chunks, int reset) {
+  if (!h) return ORBX_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  const size_t per = ORBX_N_STAGES + 1;
+  for (size_t c = 0; c + per <= h->ev_used.size(); c += per) {
+    CU(h, cudaEventSynchronize(h->ev_used[c + per - 1]));
+    for (int k = 0; k < ORBX_N_STAGES; k++) {
+      float t = 0;
+      CU(h, cudaEventElapsedTime(&t, h->ev_used[c + k], h->ev_used[c + k + 1]));
+      h->stage_ms[k] += t;
+    }
+    h->stage_chunks++;
+  }
+  for (cudaEvent_t e : h->ev_used) h->ev_pool.push_back(e);
+  h->ev_used.clear();
+  if (ms) for (int k = 0; k < ORBX_N_STAGES; k++) ms[k] = h->stage_ms[k];
+  if (chunks) *chunks = h->stage_chunks;
+  if (reset) {
+    for (int k = 0; k < ORBX_N_STAGES; k++) h->stage_ms[k] = 0;
+    h->stage_chunks = 0;
+  }
+  return ORBX_OK;
+}
 
 int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int hh, size_t row_stride,
                        size_t frame_stride, int mem, int lap0, int lap1, orbx_kp* kps, uint8_t* desc, int cap,

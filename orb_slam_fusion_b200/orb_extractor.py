@@ -143,6 +143,18 @@ class OrbExtractor:
     def launch_count(self):
         return self._lib.orbx_launch_count(self._h)
 
+    STAGE_NAMES = ("import", "pyramid", "fast", "octree", "blur", "describe")
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.orbx_set_profiling(self._h, int(on)))
+
+    def stage_times(self, reset=True):
+        """({stage: accumulated ms}, chunks) measured with CUDA events on the launching stream."""
+        ms = np.zeros(6, np.float64)
+        ch = C.c_longlong()
+        self._check(self._lib.orbx_stage_times(self._h, ms.ctypes.data, C.byref(ch), int(reset)))
+        return dict(zip(self.STAGE_NAMES, ms.tolist())), ch.value
+
     # ---- ComputePyramid / img_pyramid_, orb_extractor.h:76-78
     def ComputePyramid(self, img):
         img = np.ascontiguousarray(img, np.uint8)
