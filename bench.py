@@ -186,7 +186,7 @@ def run_ours(args):
     desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
     n = torch.empty(B, dtype=torch.int32, device=dev)
     nm = torch.empty(B, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    stream = A.torch_stream(dev)
 
     def step():
         ex.extract_batch_into(frames.data_ptr(), B, W, H, frames.stride(1), frames.stride(0), A.MEM_DEVICE, (0, 0),

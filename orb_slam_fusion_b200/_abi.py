@@ -105,3 +105,13 @@ def ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return a.data_ptr()  # torch.Tensor
+
+
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the C ABI reads a NULL stream as "the handle's own stream"
+
+
+def torch_stream(device):
+    """cudaStream_t of torch's current stream on `device`; torch's default stream has handle 0, which
+    the C ABI would take for "use the handle's stream", so it is passed as cudaStreamLegacy."""
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream or CUDA_STREAM_LEGACY

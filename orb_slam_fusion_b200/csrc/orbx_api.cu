@@ -21,7 +21,8 @@ constexpr int kSlots = 2;  // ping-pong working sets so host-memory batches over
 
 struct Slot {
   BatchBuffers b{};
-  uint8_t* d_img = nullptr;     // staged host frames [max_batch][img_pitch * h]
+  uint8_t* d_img = nullptr;     // staged host frames (grown on demand)
+  size_t img_bytes = 0;
   orbx_kp* d_kps = nullptr;     // [max_batch][out_cap]
   uint8_t* d_desc = nullptr;    // [max_batch][out_cap][32]
   int32_t* d_n = nullptr;       // [max_batch] n, then [max_batch] n_mono
@@ -132,6 +133,8 @@ void free_slot(Slot& s) {
   if (s.h_n) cudaFreeHost(s.h_n);
   s.h_n = nullptr;
   s.b = BatchBuffers{};
+  if (s.d_img) cudaFree(s.d_img);
+  s.img_bytes = 0;
   s.d_img = nullptr; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr;
 }
 
@@ -242,7 +245,6 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     s.b.xalpha = dt + tab;
     s.b.yofs = dt + 3 * (size_t)tab;
     s.b.ybeta = dt + 5 * (size_t)tab;
-    CU(h, dmalloc(s, &s.d_img, B * h->img_pitch * hh));
     CU(h, dmalloc(s, &s.d_kps, B * sel));
     CU(h, dmalloc(s, &s.d_desc, B * sel * 32));
     CU(h, dmalloc(s, &s.d_n, 2 * B));
@@ -288,6 +290,35 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   n += launch_describe(g, s.b, frames, d_kps, d_desc, cap, d_n, d_nmono, out_frame0, st);
   mark();
   h->launches += n;
+}
+
+// Host frames -> device staging buffer of slot `s`.  Rows that are (nearly) contiguous go over PCIe
+// as ONE linear copy with their padding (a 2-D copy is one DMA descriptor per 752-byte row and runs
+// at a fraction of the link rate); the import kernel reads any row stride.
+int stage_frames(orbx_t* h, Slot& s, const uint8_t* src, int w, int hh, size_t row_stride, size_t frame_stride, int nf,
+                 size_t* d_row_stride, size_t* d_frame_stride) {
+  const bool linear = row_stride <= (size_t)w + 64 && (nf == 1 || frame_stride == row_stride * (size_t)hh);
+  const size_t rs = linear ? row_stride : h->img_pitch, fs = rs * (size_t)hh;
+  const size_t need = fs * (size_t)nf + 16;
+  if (need > s.img_bytes) {
+    CU(h, cudaStreamSynchronize(s.stream));
+    if (s.d_img) cudaFree(s.d_img);
+    s.d_img = nullptr;
+    s.img_bytes = 0;
+    CU(h, cudaMalloc((void**)&s.d_img, need));
+    s.img_bytes = need;
+  }
+  if (linear) {
+    CU(h, cudaMemcpyAsync(s.d_img, src, fs * (size_t)(nf - 1) + row_stride * (size_t)(hh - 1) + (size_t)w,
+                          cudaMemcpyHostToDevice, s.stream));
+  } else {
+    for (int f = 0; f < nf; f++)
+      CU(h, cudaMemcpy2DAsync(s.d_img + (size_t)f * fs, rs, src + (size_t)f * frame_stride, row_stride, (size_t)w,
+                              (size_t)hh, cudaMemcpyHostToDevice, s.stream));
+  }
+  *d_row_stride = rs;
+  *d_frame_stride = fs;
+  return ORBX_OK;
 }
 
 int check_image(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {
@@ -429,16 +460,10 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     Slot& s = h->slot[chunk % kSlots];
     const int nf = n_frames - f0 < B ? n_frames - f0 : B;
     const uint8_t* src = imgs + (size_t)f0 * frame_stride;
-    if (frame_stride == row_stride * (size_t)hh) {
-      CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, src, row_stride, (size_t)w, (size_t)hh * nf, cudaMemcpyHostToDevice,
-                              s.stream));
-    } else {
-      for (int f = 0; f < nf; f++)
-        CU(h, cudaMemcpy2DAsync(s.d_img + (size_t)f * h->img_pitch * hh, h->img_pitch, src + (size_t)f * frame_stride,
-                                row_stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
-    }
-    enqueue_pipeline(h, s, s.d_img, h->img_pitch, h->img_pitch * hh, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n,
-                     s.d_n + B, 0, s.stream);
+    size_t drs, dfs;
+    rc = stage_frames(h, s, src, w, hh, row_stride, frame_stride, nf, &drs, &dfs);
+    if (rc) return rc;
+    enqueue_pipeline(h, s, s.d_img, drs, dfs, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n, s.d_n + B, 0, s.stream);
     CU(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), s.d_kps, (size_t)dcap * sizeof(orbx_kp),
                             (size_t)dcap * sizeof(orbx_kp), nf, cudaMemcpyDeviceToHost, s.stream));
     CU(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, s.d_desc, (size_t)dcap * 32, (size_t)dcap * 32, nf,
@@ -464,9 +489,10 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   Slot& s = h->slot[0];
   const int B = h->max_batch;
   h->border_done = false;
-  CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, img, stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
-  enqueue_pipeline(h, s, s.d_img, h->img_pitch, h->img_pitch * hh, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n,
-                   s.d_n + B, 0, s.stream);
+  size_t drs, dfs;
+  rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
+  if (rc) return rc;
+  enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
   h->last_frames = 1;
   CU(h, cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
   CU(h, cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -493,8 +519,10 @@ int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int hh, size_t st
   rc = ensure_geometry(h, w, hh);
   if (rc) return rc;
   Slot& s = h->slot[0];
-  CU(h, cudaMemcpy2DAsync(s.d_img, h->img_pitch, img, stride, (size_t)w, (size_t)hh, cudaMemcpyHostToDevice, s.stream));
-  int nl = launch_import(h->g, s.b, s.d_img, h->img_pitch, h->img_pitch * hh, 1, s.stream);
+  size_t drs, dfs;
+  rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
+  if (rc) return rc;
+  int nl = launch_import(h->g, s.b, s.d_img, drs, dfs, 1, s.stream);
   nl += launch_pyramid(h->g, s.b, 1, s.stream);
   nl += launch_border(h->g, s.b, 1, s.stream);
   h->launches += nl;

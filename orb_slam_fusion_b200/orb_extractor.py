@@ -110,7 +110,7 @@ class OrbExtractor:
             desc = torch.empty((F, cap, 32), dtype=torch.uint8, device=dev)
             n = torch.empty(F, dtype=torch.int32, device=dev)
             nm = torch.empty(F, dtype=torch.int32, device=dev)
-            st = stream if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+            st = stream if stream is not None else A.torch_stream(dev)
             self._check(self._lib.orbx_extract_batch(self._h, imgs.data_ptr(), F, w, h, imgs.stride(1), imgs.stride(0),
                                                      A.MEM_DEVICE, int(lapping_areas[0]), int(lapping_areas[1]),
                                                      kps.data_ptr(), desc.data_ptr(), cap, n.data_ptr(), nm.data_ptr(), st))
@@ -197,7 +197,7 @@ def synth_frames(kind, n_frames, w, h, seed=1, first_frame=0, shift_x=0, noise_s
         out = torch.empty((n_frames, h, w), dtype=torch.uint8, device=dev)
     rc = A.lib().orbx_synth_frames(device, 0 if kind == "blocks" else 1, out.data_ptr(), n_frames, w, h, out.stride(1),
                                    out.stride(0), seed, first_frame, shift_x, seed if noise_seed is None else noise_seed,
-                                   torch.cuda.current_stream(dev).cuda_stream)
+                                   A.torch_stream(dev))
     if rc:
         raise A.OrbxError(rc, "orbx_synth_frames")
     return out

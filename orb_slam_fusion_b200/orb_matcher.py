@@ -41,8 +41,7 @@ class ORBmatcher:
             raise A.OrbxError(rc, self._lib.orbm_last_error(self._m).decode())
 
     def _stream(self, t):
-        import torch
-        return torch.cuda.current_stream(t.device).cuda_stream
+        return A.torch_stream(t.device)
 
     def launch_count(self):
         return self._lib.orbm_launch_count(self._m)
@@ -150,7 +149,7 @@ def synth_descriptors(first, n, seed, device=0, out=None):
     dev = torch.device("cuda", device)
     if out is None:
         out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
-    rc = A.lib().orbm_synth_descriptors(device, out.data_ptr(), first, n, seed, torch.cuda.current_stream(dev).cuda_stream)
+    rc = A.lib().orbm_synth_descriptors(device, out.data_ptr(), first, n, seed, A.torch_stream(dev))
     if rc:
         raise A.OrbxError(rc, "orbm_synth_descriptors")
     return out
