@@ -264,16 +264,10 @@ def run_ours(args):
     r0, r1 = DB_ROWS * rank // world, DB_ROWS * (rank + 1) // world
     db = P.synth_descriptors(r0, r1 - r0, seed=7, device=local)
     q = P.synth_descriptors(0, N_QUERIES, seed=8, device=local)
-    gi = torch.empty((world, N_QUERIES, 2), dtype=torch.int64, device=dev)
-    gd = torch.empty((world, N_QUERIES, 2), dtype=torch.int32, device=dev)
+    from orb_slam_fusion_b200 import sharding
 
     def match_step():
-        idx, dd = m.knn2(q, db, index_base=r0)
-        if world > 1:
-            dist.all_gather_into_tensor(gi, idx)
-            dist.all_gather_into_tensor(gd, dd)
-            idx, dd = m.top2_merge(gi, gd)
-        return idx, dd, m.ratio_test(idx, dd, 0.7)
+        return sharding.sharded_knn2(m, q, db, r0, 0.7)
 
     for _ in range(2):
         match_step()

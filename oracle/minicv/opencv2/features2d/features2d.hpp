@@ -22,6 +22,14 @@ inline void FAST(InputArray img_, std::vector<KeyPoint>& kps, int threshold, boo
     kps.push_back(KeyPoint((float)xyr[3 * i], (float)xyr[3 * i + 1], 7.f, -1.f, (float)xyr[3 * i + 2]));
 }
 
+// cv::DMatch as returned by BFMatcher::knnMatch (frame.cc:1154-1162); used by the C++ facade tests.
+struct DMatch {
+  int queryIdx, trainIdx, imgIdx;
+  float distance;
+  DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.4e38f) {}
+  DMatch(int q, int t, float d) : queryIdx(q), trainIdx(t), imgIdx(-1), distance(d) {}
+};
+
 // Only referenced by the reference's dead ComputeKeyPointsOld (orb_extractor.cc:977,992).
 struct KeyPointsFilter {
   static void retainBest(std::vector<KeyPoint>& kps, int n) {

@@ -1,0 +1,56 @@
+// GPU counterparts of the data-parallel loops around ORBmatcher::DescriptorDistance
+// (orb_matcher.cc:1877-1891) over the C ABI of include/orbx.h.  The reference's ORBmatcher class
+// (orb_matcher.h:36-129) keeps its 13 pointer-chasing Search*/Fuse methods; the call sites that are
+// pure descriptor work switch to these (INTEGRATION.md shows the three-line patches):
+//   Frame::ComputeStereoMatches       frame.cc:836-900   -> StereoRowBand
+//   Frame::ComputeStereoFishEyeMatches frame.cc:1154-1162 -> KnnMatch2 + RatioTest
+//   SearchByProjection inner loop      orb_matcher.cc:66-113 -> WindowSearch (greedy claim stays on the host)
+#ifndef ORBMATCHER_GPU_H
+#define ORBMATCHER_GPU_H
+
+#include <cstdint>
+#include <opencv2/opencv.hpp>
+#include <vector>
+
+struct orbm_matcher;  // include/orbx.h
+
+namespace ORB_SLAM_FUSION {
+
+class ORBmatcherGpu {
+ public:
+  static const int TH_LOW = 50;  // orb_matcher.cc:35-37
+  static const int TH_HIGH = 100;
+  static const int HISTO_LENGTH = 30;
+
+  explicit ORBmatcherGpu(int device = 0);
+  ~ORBmatcherGpu();
+  ORBmatcherGpu(const ORBmatcherGpu&) = delete;
+  ORBmatcherGpu& operator=(const ORBmatcherGpu&) = delete;
+
+  // ORBmatcher::DescriptorDistance for row i of a against row i of b (n x 32 CV_8U each).
+  std::vector<int> DescriptorDistance(const cv::Mat& a, const cv::Mat& b);
+
+  // cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, matches, 2): per query the two nearest train
+  // rows ordered by (distance, index); fewer entries when train has fewer than 2 rows.
+  void KnnMatch2(const cv::Mat& query, const cv::Mat& train, std::vector<std::vector<cv::DMatch> >& matches);
+
+  // frame.cc:836-900: best right keypoint and distance per left keypoint (-1 / TH_HIGH when none).
+  void StereoRowBand(const std::vector<cv::KeyPoint>& keys_left, const cv::Mat& desc_left,
+                     const std::vector<cv::KeyPoint>& keys_right, const cv::Mat& desc_right,
+                     const std::vector<float>& scale_factors, int n_rows, float min_d, float max_d,
+                     std::vector<int>& best_idx_right, std::vector<int>& best_dist);
+
+  struct Window { float u, v, r; int min_level, max_level; };
+  struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };
+  // orb_matcher.cc:66-113 with Frame::GetFeaturesInArea (frame.cc:679-746) for a batch of projections.
+  void WindowSearch(const std::vector<cv::KeyPoint>& keys_un, const cv::Mat& desc, float min_x, float min_y,
+                    float grid_inv_w, float grid_inv_h, int grid_cols, int grid_rows, const std::vector<Window>& windows,
+                    const cv::Mat& window_desc, const std::vector<uint8_t>* already_matched, std::vector<WindowBest>& out);
+
+ private:
+  orbm_matcher* m_;
+};
+
+}  // namespace ORB_SLAM_FUSION
+
+#endif

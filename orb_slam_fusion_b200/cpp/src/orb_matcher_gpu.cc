@@ -1,0 +1,81 @@
+#include "cam/orb_feature/orb_matcher_gpu.h"
+
+#include <climits>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "orbx.h"
+
+namespace ORB_SLAM_FUSION {
+
+const int ORBmatcherGpu::TH_HIGH;  // orb_matcher.cc:35-37
+const int ORBmatcherGpu::TH_LOW;
+const int ORBmatcherGpu::HISTO_LENGTH;
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_kp), "cv::KeyPoint layout");
+static_assert(sizeof(ORBmatcherGpu::Window) == sizeof(orbm_window_query), "window layout");
+static_assert(sizeof(ORBmatcherGpu::WindowBest) == sizeof(orbm_window_result), "result layout");
+
+namespace {
+// descriptors as one dense n x 32 block (cv::Mat rows may be strided views)
+std::vector<uint8_t> dense_rows(const cv::Mat& m) {
+  std::vector<uint8_t> v((size_t)m.rows * 32);
+  for (int i = 0; i < m.rows; ++i) std::memcpy(v.data() + 32 * (size_t)i, m.ptr(i), 32);
+  return v;
+}
+void check(orbm_matcher* m, int rc) {
+  if (rc != ORBX_OK) throw std::runtime_error(std::string("ORBmatcherGpu: ") + orbm_last_error(m));
+}
+}  // namespace
+
+ORBmatcherGpu::ORBmatcherGpu(int device) : m_(nullptr) {
+  const int rc = orbm_create(device, &m_);
+  if (rc != ORBX_OK) throw std::runtime_error("ORBmatcherGpu: orbm_create failed with code " + std::to_string(rc));
+}
+
+ORBmatcherGpu::~ORBmatcherGpu() { orbm_destroy(m_); }
+
+std::vector<int> ORBmatcherGpu::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+  const std::vector<uint8_t> da = dense_rows(a), db = dense_rows(b);
+  std::vector<int> out((size_t)a.rows);
+  check(m_, orbm_hamming_pairs(m_, da.data(), db.data(), a.rows, out.data(), ORBX_MEM_HOST, nullptr));
+  return out;
+}
+
+void ORBmatcherGpu::KnnMatch2(const cv::Mat& query, const cv::Mat& train, std::vector<std::vector<cv::DMatch> >& matches) {
+  const std::vector<uint8_t> q = dense_rows(query), t = dense_rows(train);
+  std::vector<int64_t> idx((size_t)query.rows * 2);
+  std::vector<int32_t> dist((size_t)query.rows * 2);
+  check(m_, orbm_knn2(m_, q.data(), query.rows, t.data(), train.rows, 0, idx.data(), dist.data(), ORBX_MEM_HOST, nullptr));
+  matches.assign((size_t)query.rows, std::vector<cv::DMatch>());
+  for (int i = 0; i < query.rows; ++i)
+    for (int k = 0; k < 2; ++k)
+      if (idx[2 * i + k] >= 0) matches[i].push_back(cv::DMatch(i, (int)idx[2 * i + k], (float)dist[2 * i + k]));
+}
+
+void ORBmatcherGpu::StereoRowBand(const std::vector<cv::KeyPoint>& kl, const cv::Mat& dl, const std::vector<cv::KeyPoint>& kr,
+                                  const cv::Mat& dr, const std::vector<float>& sf, int n_rows, float min_d, float max_d,
+                                  std::vector<int>& best_idx_right, std::vector<int>& best_dist) {
+  const std::vector<uint8_t> l = dense_rows(dl), r = dense_rows(dr);
+  best_idx_right.assign(kl.size(), -1);
+  best_dist.assign(kl.size(), TH_HIGH);
+  check(m_, orbm_stereo_rowband(m_, reinterpret_cast<const orbx_kp*>(kl.data()), l.data(), (int)kl.size(),
+                                reinterpret_cast<const orbx_kp*>(kr.data()), r.data(), (int)kr.size(), sf.data(),
+                                (int)sf.size(), n_rows, min_d, max_d, best_idx_right.data(), best_dist.data(),
+                                ORBX_MEM_HOST, nullptr));
+}
+
+void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,
+                                 float inv_w, float inv_h, int cols, int rows, const std::vector<Window>& windows,
+                                 const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out) {
+  const std::vector<uint8_t> d = dense_rows(desc), qd = dense_rows(window_desc);
+  const orbm_grid_geom g = {min_x, min_y, inv_w, inv_h, cols, rows};
+  out.resize(windows.size());
+  check(m_, orbm_window_search(m_, reinterpret_cast<const orbx_kp*>(keys.data()), d.data(), (int)keys.size(), &g,
+                               reinterpret_cast<const orbm_window_query*>(windows.data()), qd.data(), (int)windows.size(),
+                               already ? already->data() : nullptr, reinterpret_cast<orbm_window_result*>(out.data()),
+                               ORBX_MEM_HOST, nullptr));
+}
+
+}  // namespace ORB_SLAM_FUSION

@@ -1,0 +1,68 @@
+// tests/cpp/facade_test.cc -- exercises the C++ drop-in classes (orb_slam_fusion_b200/cpp) the way
+// the reference's Frame does (frame.cc:467-476, 834, 1154), compiled against the mini-cv stand-in
+// for OpenCV (oracle/minicv, test infrastructure).  Writes its outputs to a binary file that
+// tests/test_cpp_facade.py compares with the oracle.
+//   facade_test <in.raw> <w> <h> <num_feats> <lap0> <lap1> <out.bin>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "cam/orb_feature/orb_extractor.h"
+#include "cam/orb_feature/orb_matcher_gpu.h"
+
+using namespace ORB_SLAM_FUSION;
+
+static void put(FILE* f, const void* p, size_t n) { fwrite(p, 1, n, f); }
+
+int main(int argc, char** argv) {
+  if (argc != 8) return 2;
+  const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]);
+  std::vector<int> lap = {atoi(argv[5]), atoi(argv[6])};
+  std::vector<uint8_t> buf((size_t)w * h);
+  FILE* fi = fopen(argv[1], "rb");
+  if (!fi || fread(buf.data(), 1, buf.size(), fi) != buf.size()) return 3;
+  fclose(fi);
+  cv::Mat img(h, w, CV_8UC1, buf.data());
+
+  OrbExtractor* extractor = new OrbExtractor(nf, 1.2f, 8, 20, 7);  // tracking.cc:195
+  std::vector<cv::KeyPoint> keys;
+  cv::Mat desc;
+  const int mono = (*extractor)(img, cv::Mat(), keys, desc, lap);  // frame.cc:472-475
+  std::vector<cv::KeyPoint> none;
+  cv::Mat nodesc(3, 32, CV_8U);
+  const int empty_rc = (*extractor)(cv::Mat(), cv::Mat(), none, nodesc, lap);  // :1016
+
+  FILE* fo = fopen(argv[7], "wb");
+  const int32_t hdr[6] = {mono, (int32_t)keys.size(), desc.rows, desc.cols, empty_rc, extractor->GetLevels()};
+  put(fo, hdr, sizeof(hdr));
+  put(fo, keys.data(), keys.size() * sizeof(cv::KeyPoint));
+  for (int i = 0; i < desc.rows; i++) put(fo, desc.ptr(i), 32);
+  const std::vector<float> sf = extractor->GetScaleFactors();
+  put(fo, sf.data(), sf.size() * sizeof(float));
+  // img_pyramid_ as Frame::ComputeStereoMatches reads it (frame.cc:834, 913-931): rows/cols and pixels
+  for (int lev = 0; lev < extractor->GetLevels(); lev++) {
+    const cv::Mat& m = extractor->img_pyramid_[lev];
+    const int32_t wh[2] = {m.cols, m.rows};
+    put(fo, wh, sizeof(wh));
+    for (int y = -19; y < m.rows + 19; y++) put(fo, m.data + (ptrdiff_t)y * (ptrdiff_t)m.step - 19, (size_t)m.cols + 38);
+  }
+  // brute-force 2-NN of the first 64 descriptors against all of them (frame.cc:1154 pattern)
+  ORBmatcherGpu matcher(0);
+  std::vector<std::vector<cv::DMatch> > matches;
+  const int nq = desc.rows < 64 ? desc.rows : 64;
+  matcher.KnnMatch2(desc.rowRange(0, nq), desc, matches);
+  for (int i = 0; i < nq; i++) {
+    int32_t rec[4] = {-1, -1, -1, -1};
+    for (size_t k = 0; k < matches[i].size(); k++) { rec[2 * k] = matches[i][k].trainIdx; rec[2 * k + 1] = (int32_t)matches[i][k].distance; }
+    put(fo, rec, sizeof(rec));
+  }
+  // stereo row band of the frame against itself: every keypoint must find itself at distance 0
+  std::vector<int> bi, bd;
+  matcher.StereoRowBand(keys, desc, keys, desc, sf, h, 0.f, 40.f, bi, bd);
+  put(fo, bi.data(), bi.size() * sizeof(int));
+  put(fo, bd.data(), bd.size() * sizeof(int));
+  fclose(fo);
+  delete extractor;
+  return 0;
+}

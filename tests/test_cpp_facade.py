@@ -1,0 +1,62 @@
+"""The C++ drop-in classes (orb_slam_fusion_b200/cpp): they must compile against an OpenCV-shaped API
+(CPU test: oracle/minicv stands in for the absent OpenCV headers) and, on the GPU, return exactly what
+the reference's OrbExtractor returns to Frame (frame.cc:467-476, 834, 1154)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EXE = os.path.join(HERE, "cpp", "facade_test")
+
+
+def build():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "cpp")], stdout=subprocess.DEVNULL)
+    return EXE
+
+
+def test_facade_compiles_and_links_against_the_c_abi():
+    exe = build()
+    assert os.path.exists(exe)
+    # the facade binds only to the exported C ABI
+    syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    used = {l.split()[-1] for l in syms.splitlines() if " orbx_" in l or " orbm_" in l}
+    assert {"orbx_create", "orbx_extract", "orbx_pyramid_level", "orbm_knn2", "orbm_stereo_rowband"} <= used
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,nf,lap", [(752, 480, 1200, (0, 0)), (640, 480, 1000, (0, 1000)), (640, 480, 800, (150, 480))])
+def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
+    exe = build()
+    img = oracle.blocks_v1(w, h, 2, 4)
+    raw, out = tmp_path / "in.raw", tmp_path / "out.bin"
+    img.tofile(raw)
+    subprocess.check_call([exe, str(raw), str(w), str(h), str(nf), str(lap[0]), str(lap[1]), str(out)])
+    buf = out.read_bytes()
+    hdr = np.frombuffer(buf, np.int32, 6)
+    mono, n, drows, dcols, empty_rc, levels = (int(v) for v in hdr)
+    off = 24
+    kps = np.frombuffer(buf, oracle.KP_DTYPE, n, off); off += 28 * n
+    desc = np.frombuffer(buf, np.uint8, 32 * n, off).reshape(n, 32); off += 32 * n
+    sf = np.frombuffer(buf, np.float32, levels, off); off += 4 * levels
+    ref = oracle.Extractor(nf, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    rn, rk, rd = ref(img, lap)
+    assert (mono, n, drows, dcols, empty_rc, levels) == (rn, len(rk), len(rk), 32, -1, 8)
+    assert kps.tobytes() == rk.tobytes() and np.array_equal(desc, rd)
+    assert np.array_equal(sf, ref.tables()["scale"])
+    for lev in range(8):
+        lw, lh = (int(v) for v in np.frombuffer(buf, np.int32, 2, off)); off += 8
+        want = ref.level(lev, with_border=True)
+        assert (lh + 38, lw + 38) == want.shape
+        got = np.frombuffer(buf, np.uint8, want.size, off).reshape(want.shape); off += want.size
+        assert np.array_equal(got, want), lev
+    nq = min(64, n)
+    rec = np.frombuffer(buf, np.int32, 4 * nq, off).reshape(nq, 4); off += 16 * nq
+    ri, rdist = oracle.knn2(rd[:nq], rd)
+    assert np.array_equal(rec[:, 0], ri[:, 0]) and np.array_equal(rec[:, 2], ri[:, 1])
+    assert np.array_equal(rec[:, 1], rdist[:, 0]) and np.array_equal(rec[:, 3], rdist[:, 1])
+    bi = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    bd = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    wi, wd = oracle.stereo_rowband(rk, rd, rk, rd, sf, h, 0.0, 40.0)
+    assert np.array_equal(bi, wi) and np.array_equal(bd, wd) and off == len(buf)
