@@ -86,14 +86,17 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
 }
 
 constexpr int kDescWarps = 8;
+constexpr int kPatchRows = 37, kPatchWords = 11;  // rotated pattern offsets stay within +-18 px (A.7)
 
-__global__ void __launch_bounds__(32 * kDescWarps) k_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(32 * kDescWarps, 4) k_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                                               const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel_xy,
                                                               const uint8_t* __restrict__ sel_sc, const int32_t* __restrict__ n_sel,
                                                               const int32_t* __restrict__ work, orbx_kp* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int cap, int out_frame0) {
   // pattern transposed so that lane L reads word [k][L]: (x0,y0,x1,y1) of bit k of byte L
   __shared__ uint32_t pat[8][32];
+  // per warp: the 37 x 37 blurred patch around the keypoint as 37 rows of 11 aligned words
+  __shared__ uint32_t patch[kDescWarps][kPatchRows * kPatchWords];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   {
     const int L = tid >> 3, k = tid & 7;  // 256 threads = 32 bytes x 8 bits
@@ -116,6 +119,22 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(const __grid_const
   const uint32_t xy = sel_xy[so];
   const int cx = (int)(xy & 0xFFFFu), cy = (int)(xy >> 16);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
+
+  // Blurred 37 x 37 patch for the descriptor: issue its coalesced word loads first so that they are in
+  // flight together with the orientation loads (the 512 samples of a descriptor are single-byte
+  // gathers over 37 rows: straight from global memory each would cost one L1 wavefront per lane).
+  const int xb = (cx - 18) & ~3;  // >= 0: keypoints are >= 19 px inside; interior rows are 16-byte aligned
+  constexpr int kStage = (kPatchRows * kPatchWords + 31) / 32;
+  uint32_t pv[kStage];
+  {
+    const uint8_t* bsrc = blur + fo + px_off(L, xb, cy - 18);
+#pragma unroll
+    for (int t = 0; t < kStage; t++) {
+      const int i = lane + 32 * t;
+      const int r = i / kPatchWords, c = i - r * kPatchWords;
+      pv[t] = i < kPatchRows * kPatchWords ? __ldg(reinterpret_cast<const uint32_t*>(bsrc + r * L.pitch) + c) : 0u;
+    }
+  }
 
   // ---- IC_Angle (:76-100): lane = column u, loop over rows v
   const int u = lane - kHalfPatch;
@@ -144,8 +163,17 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(const __grid_const
   // (float of the double-precision result); see SURVEY.md A.7 for the libm tolerance class.
   const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
   const float rad = f_mul(angle, factor_pi);
-  const float a = (float)cos((double)rad), b = (float)sin((double)rad);
-  const uint8_t* bc = blur + fo + px_off(L, cx, cy);
+  double sd, cd;
+  sincos((double)rad, &sd, &cd);
+  const float a = (float)cd, b = (float)sd;
+  uint32_t* pw = patch[wid];
+#pragma unroll
+  for (int t = 0; t < kStage; t++) {
+    const int i = lane + 32 * t;
+    if (i < kPatchRows * kPatchWords) pw[i] = pv[t];
+  }
+  __syncwarp();
+  const uint8_t* bc = reinterpret_cast<const uint8_t*>(pw) + 18 * (kPatchWords * 4) + (cx - xb);
   uint32_t byte = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -153,7 +181,7 @@ __global__ void __launch_bounds__(32 * kDescWarps) k_describe(const __grid_const
     int r0, c0, r1, c1;
     rbrief_offset(a, b, (int)(int8_t)(p & 255), (int)(int8_t)((p >> 8) & 255), r0, c0);
     rbrief_offset(a, b, (int)(int8_t)((p >> 16) & 255), (int)(int8_t)(p >> 24), r1, c1);
-    const int t0 = __ldg(bc + r0 * L.pitch + c0), t1 = __ldg(bc + r1 * L.pitch + c1);
+    const int t0 = bc[r0 * (kPatchWords * 4) + c0], t1 = bc[r1 * (kPatchWords * 4) + c1];
     byte |= (uint32_t)(t0 < t1) << k;
   }
   const size_t o = (size_t)(out_frame0 + f) * cap + slot;

@@ -4,165 +4,189 @@
 // Replaces the per-cell cv::FAST loop of OrbExtractor::ComputeKeyPointsOctTree
 // (orb_extractor.cc:744-825).  Arithmetic: SURVEY.md A.3.
 //
-// One CTA per grid cell.  A cell's detection domain (its ROI minus cv::FAST's 3-px frame) never
-// overlaps a neighbour's and non-maximum suppression counts pixels of other cells as 0, so a CTA
-// needs its own (wcell+6) x (hcell+6) raw pixels and nothing else:
-//   1. raw ROI -> shared memory (u8)
-//   2. every domain pixel runs the opposite-pair rejection test at the LOW threshold; the
-//      survivors of a warp are compacted with one ballot + one shared atomic per warp
-//   3. the compacted list is scored densely (full 16-ring arc test, response = best - 1)
-//   4. 3x3 strict NMS on the shared score map; if any NMS survivor reaches the HIGH threshold
-//      only those are kept, otherwise all (FAST(20,nms) == FAST(7,nms) filtered by
-//      response >= 20, and the retry of :799-801 is decided after NMS)
-//   5. survivors are appended to the level's candidate list (one global atomic per CTA).
+// The reference calls cv::FAST on 700 overlapping ~42x44 ROIs per frame.  The detection domains of
+// the cells (ROI minus cv::FAST's 3-px frame) tile [19, w-19) x [19, h-19) exactly, so the level is
+// processed as one streaming stencil over aligned 128x32 tiles, and the cell structure is applied
+// where it matters:
+//   * non-maximum suppression treats a neighbour in another cell as 0 (a pixel on a cell edge
+//     simply skips the neighbours across it);
+//   * the retry rule of :799-801 ("if the cell is empty at iniThFAST, detect again at minThFAST",
+//     decided after NMS) is FAST(min,nms) filtered by response >= ini when any survivor of the
+//     cell reaches ini: the kernel emits every FAST(min,nms) survivor together with its cell and
+//     sets a per-cell "strong" flag; the quadtree kernel applies the filter when it reads the list.
+// Per tile: raw pixels (+4 halo) -> shared memory as aligned words; opposite-pair rejection test on
+// four pixels per thread with byte SIMD (VABSDIFF4); survivors compacted per warp; dense 16-ring
+// scoring; NMS on the shared score map; one global atomic per CTA to append.
 // The list order is unspecified; the quadtree re-derives the reference order from coordinates.
 #include "orbx_kernels.cuh"
 #include "orbx_math.cuh"
 
 namespace orbx {
 
-constexpr int kFastMaxCell = 70;                   // wcell, hcell < 70 (cells are >= 35 px, < 2x)
-constexpr int kFastRawPitch = kFastMaxCell + 6 + 4;  // 80
-constexpr int kFastScPitch = kFastMaxCell + 2;     // score map with a zero frame
+constexpr int kFtW = 128, kFtH = 32;          // tile of owned pixels (same tiling as the blur kernel)
+constexpr int kFtRawW = 34;                   // raw words per row: bytes X0-4 .. X0+131
+constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the raw and score planes
+constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
+constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
+constexpr int kFtMaxOut = 1536;               // NMS survivors of one tile (<= (64+4)*(16+2))
+
+// byte-wise |a - b| > t for four pixels at once; t <= 126.  VABSDIFF4 is a native instruction,
+// the compare is the high-bit trick (no byte carries: (d & 0x7f) + (0x7f - t) <= 0xfe).
+__device__ __forceinline__ uint32_t exceeds4(uint32_t a, uint32_t b, uint32_t k) {
+  const uint32_t d = __vabsdiffu4(a, b);
+  return (((d & 0x7f7f7f7fu) + k) | d) & 0x80808080u;
+}
 
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
-                                              int32_t* __restrict__ n_cand) {
-  __shared__ __align__(16) uint8_t raw[(kFastMaxCell + 6) * kFastRawPitch];
-  __shared__ __align__(16) uint8_t score[(kFastMaxCell + 2) * kFastScPitch];
-  __shared__ uint16_t list[kFastMaxCell * kFastMaxCell];  // packed (yr << 8) | xr of pixels to score
-  __shared__ uint16_t outl[kFastMaxCell * kFastMaxCell / 4 + 64];  // NMS survivors (<= ceil/2 x ceil/2)
-  __shared__ int n_list, n_out, n_strong, out_base;
+                                              int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
+                                              int32_t* __restrict__ cell_strong) {
+  __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawW];
+  __shared__ __align__(16) uint8_t score[kFtScH * kFtPitch];
+  __shared__ uint16_t list[kFtScH * kFtPitch];  // (score row << 8) | byte column of pixels to score
+  __shared__ uint16_t outl[kFtMaxOut];
+  __shared__ int n_list, n_out, out_base;
+  const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
   int lev = 0;
-  while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].cell_base) lev++;
+  while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].blur_tile_base) lev++;
   const LevelGeom& L = g.lv[lev];
-  const int cell = blockIdx.x - L.cell_base;
-  const int ci = cell / L.ncols, cj = cell - ci * L.ncols;
-  const int f = blockIdx.y;
-  // detection domain of this cell in level coordinates
-  const int dx0 = kEdge + cj * L.wcell, dy0 = kEdge + ci * L.hcell;
-  const int dw = min(L.wcell, L.w - kEdge - dx0), dh = min(L.hcell, L.h - kEdge - dy0);
-  if (dw <= 0 || dh <= 0) return;
-  const int tid = threadIdx.x;
+  const int tile = blockIdx.x - L.blur_tile_base;
+  const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
+  const int X0 = tx * kFtW, Y0 = ty * kFtH;
+  // owned pixels inside the detection domain [19, w-19) x [19, h-19)
+  if (X0 >= L.w - kEdge || Y0 >= L.h - kEdge || X0 + kFtW <= kEdge || Y0 + kFtH <= kEdge) return;
+  const int f = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int lo = min(g.ini_th, g.min_th);
 
-  if (tid == 0) { n_list = 0; n_out = 0; n_strong = 0; }
-  // zero the score map (with its frame)
-  for (int i = tid; i < (kFastMaxCell + 2) * kFastScPitch / 4; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
-  // raw ROI: rows dy0-3 .. dy0+dh+2, cols dx0-3 .. dx0+dw+2
-  const uint8_t* src = pyr + (size_t)f * g.pyr_frame_bytes + px_off(L, dx0 - 3, dy0 - 3);
-  const int rw = dw + 6, rh = dh + 6;
-  for (int i = tid; i < rh * kFastRawPitch; i += 256) {
-    const int r = i / kFastRawPitch, c = i - r * kFastRawPitch;
-    if (c < rw) raw[i] = __ldg(src + (size_t)r * L.pitch + c);
+  if (tid == 0) { n_list = 0; n_out = 0; }
+  for (int i = tid; i < kFtScH * kFtRawW; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
+  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r
+  {
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame_bytes;
+    const int base = px_off(L, X0 - 4, Y0 - 4);
+    for (int i = tid; i < kFtRawH * kFtRawW; i += 256) {
+      const int r = i / kFtRawW, c = i - r * kFtRawW;
+      const int y = Y0 - 4 + r, x = X0 - 4 + 4 * c;
+      uint32_t v = 0;
+      if (y >= 0 && y < L.h && x < L.w + 16)  // the plane has 32 B left / >= 19 B right padding
+        v = __ldg(reinterpret_cast<const uint32_t*>(src + base + r * L.pitch + 4 * c));
+      raw_w[i] = v;
+    }
   }
   __syncthreads();
 
-  // ---- 2. rejection test + warp compaction
-  const int npx = dw * dh;
-  for (int base = 0; base < npx; base += 256) {
-    const int p = base + tid;
-    bool keep = false;
-    int xr = 0, yr = 0;
-    if (p < npx) {
-      yr = p / dw;
-      xr = p - yr * dw;
-      const uint8_t* c = &raw[(yr + 3) * kFastRawPitch + xr + 3];
-      const int v = c[0], tb = v + lo, td = v - lo;
-      // every 9-arc holds one pixel of each opposite pair (k, k+8)
-      const int a0 = c[3 * kFastRawPitch], a8 = c[-3 * kFastRawPitch];  // ring 0 / 8
-      const int a4 = c[3], a12 = c[-3];                                  // ring 4 / 12
-      const bool bright = ((a0 > tb) | (a8 > tb)) & ((a4 > tb) | (a12 > tb));
-      const bool dark = ((a0 < td) | (a8 < td)) & ((a4 < td) | (a12 < td));
-      keep = bright | dark;
+  // ---- 2. rejection test, four pixels per thread, + warp compaction.
+  // Every 9-arc holds one pixel of each opposite pair (k, k+8), so a corner needs a ring pixel that
+  // differs from the centre by more than t in the pair (0,8) AND in the pair (4,12).
+  // Item (rr, wc): score row rr (y = Y0-1+rr, raw row rr+3), raw word wc (x = X0-4+4wc+j).
+  const uint32_t kthr = (uint32_t)(0x7f - lo) * 0x01010101u;
+  const int xlo = max(kEdge, X0 - 1), xhi = min(L.w - kEdge, X0 + kFtW + 1);  // scored columns [xlo, xhi)
+  for (int base = 0; base < kFtScH * kFtRawW; base += 256) {
+    const int it = base + tid;
+    uint32_t keep = 0;
+    int rr = 0, col0 = 0;
+    if (it < kFtScH * kFtRawW) {
+      rr = it / kFtRawW;
+      const int wc = it - rr * kFtRawW;
+      col0 = 4 * wc;
+      const int y = Y0 - 1 + rr, x = X0 - 4 + col0;
+      if (y >= kEdge && y < L.h - kEdge && x + 3 >= xlo && x < xhi) {
+        const uint32_t* row = &raw_w[(rr + 3) * kFtRawW + wc];
+        const uint32_t c = row[0];
+        const uint32_t up = row[-3 * kFtRawW], dn = row[3 * kFtRawW];
+        const uint32_t lf = __byte_perm(row[wc > 0 ? -1 : 0], c, 0x4321);               // pixels x-3
+        const uint32_t rt = __byte_perm(c, row[wc < kFtRawW - 1 ? 1 : 0], 0x6543);      // pixels x+3
+        if (lo <= 126)
+          keep = (exceeds4(dn, c, kthr) | exceeds4(up, c, kthr)) & (exceeds4(rt, c, kthr) | exceeds4(lf, c, kthr));
+        else
+          keep = 0x80808080u;  // thresholds beyond the byte trick: score everything
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (x + j < xlo || x + j >= xhi) keep &= ~(0x80u << (8 * j));
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (m) {
+    const int cnt = __popc(keep);
+    if (__any_sync(0xffffffffu, cnt != 0)) {
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
       int wbase = 0;
-      const int lane = tid & 31;
-      if (lane == 0) wbase = atomicAdd(&n_list, __popc(m));
-      wbase = __shfl_sync(0xffffffffu, wbase, 0);
-      if (keep) list[wbase + __popc(m & ((1u << lane) - 1))] = (uint16_t)((yr << 8) | xr);
+      if (lane == 31) wbase = atomicAdd(&n_list, incl);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      int pos = wbase + incl - cnt;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (keep & (0x80u << (8 * j))) list[pos++] = (uint16_t)((rr << 8) | (col0 + j));
     }
   }
   __syncthreads();
 
-  // ---- 3. dense scoring of the compacted list
+  // ---- 3. dense scoring of the compacted list (response = best - 1, 0 if not a corner at `lo`)
   const int nl = n_list;
   for (int i = tid; i < nl; i += 256) {
-    const int yr = list[i] >> 8, xr = list[i] & 255;
-    const uint8_t* c = &raw[(yr + 3) * kFastRawPitch + xr + 3];
+    const int rr = list[i] >> 8, cb = list[i] & 255;
+    const uint8_t* c = &raw[(rr + 3) * kFtPitch + cb];
     const int dxs[16] = ORBX_RING_DX, dys[16] = ORBX_RING_DY;
     int r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFastRawPitch + dxs[k]];
+    for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtPitch + dxs[k]];
     const int s = fast9_score(c[0], r, lo);
-    if (s > 0) score[(yr + 1) * kFastScPitch + xr + 1] = (uint8_t)s;
+    if (s > 0) score[rr * kFtPitch + cb] = (uint8_t)s;
   }
   __syncthreads();
 
-  // ---- 4. NMS (only pixels on the list can be corners)
+  // ---- 4. NMS of the owned pixels; neighbours across a cell edge count as 0
   for (int i = tid; i < nl; i += 256) {
-    const int yr = list[i] >> 8, xr = list[i] & 255;
-    const uint8_t* sp = &score[(yr + 1) * kFastScPitch + xr + 1];
+    const int rr = list[i] >> 8, cb = list[i] & 255;
+    if (rr < 1 || rr > kFtH || cb < 4 || cb >= 4 + kFtW) continue;  // halo pixel
+    const uint8_t* sp = &score[rr * kFtPitch + cb];
     const int s = sp[0];
     if (s == 0) continue;
-    const bool is_max = s > sp[-1] && s > sp[1] && s > sp[-kFastScPitch - 1] && s > sp[-kFastScPitch] &&
-                        s > sp[-kFastScPitch + 1] && s > sp[kFastScPitch - 1] && s > sp[kFastScPitch] &&
-                        s > sp[kFastScPitch + 1];
+    const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
+    const int xm = (x - kEdge) % L.wcell, ym = (y - kEdge) % L.hcell;
+    const bool l_ok = xm != 0, r_ok = xm != L.wcell - 1, u_ok = ym != 0, d_ok = ym != L.hcell - 1;
+    bool is_max = (!l_ok || s > sp[-1]) && (!r_ok || s > sp[1]) && (!u_ok || s > sp[-kFtPitch]) && (!d_ok || s > sp[kFtPitch]);
+    is_max = is_max && (!(l_ok && u_ok) || s > sp[-kFtPitch - 1]) && (!(r_ok && u_ok) || s > sp[-kFtPitch + 1]) &&
+             (!(l_ok && d_ok) || s > sp[kFtPitch - 1]) && (!(r_ok && d_ok) || s > sp[kFtPitch + 1]);
     if (is_max) {
-      outl[atomicAdd(&n_out, 1)] = list[i];
-      if (s >= g.ini_th) n_strong = 1;
+      const int o = atomicAdd(&n_out, 1);
+      if (o < kFtMaxOut) outl[o] = list[i];
     }
   }
   __syncthreads();
 
-  // ---- 5. retry rule + append
-  const int no = n_out;
+  // ---- 5. append to the level's candidate list
+  const int no = min(n_out, kFtMaxOut);
   if (no == 0) return;
-  const bool strong_only = (g.ini_th > lo) && n_strong;
-  // at most ceil(70/2)^2 = 1225 survivors -> up to 5 per thread; handled in rounds of 256
-  int32_t* counter = n_cand + f * ORBX_MAX_LEVELS + lev;
+  if (tid == 0) out_base = atomicAdd(n_cand + f * ORBX_MAX_LEVELS + lev, no);
+  __syncthreads();
   const size_t cbase = (size_t)f * g.cand_frame_cap + L.cand_off;
-  for (int base = 0; base < no; base += 256) {
-    const int i = base + tid;
-    bool emit = false;
-    uint32_t xy = 0;
-    int s = 0;
-    if (i < no) {
-      const int yr = outl[i] >> 8, xr = outl[i] & 255;
-      s = score[(yr + 1) * kFastScPitch + xr + 1];
-      emit = !strong_only || s >= g.ini_th;
+  for (int i = tid; i < no; i += 256) {
+    const int rr = outl[i] >> 8, cb = outl[i] & 255;
+    const int s = score[rr * kFtPitch + cb];
+    const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
+    const int cell = ((y - kEdge) / L.hcell) * L.ncols + (x - kEdge) / L.wcell;
+    const int pos = out_base + i;
+    if (pos < L.cand_cap) {
       // coordinates relative to (16,16) as orb_extractor.cc:816-823
-      xy = ((uint32_t)(3 + ci * L.hcell + yr) << 16) | (uint32_t)(3 + cj * L.wcell + xr);
+      cand_xy[cbase + pos] = ((uint32_t)(y - kFastBorder) << 16) | (uint32_t)(x - kFastBorder);
+      cand_sc[cbase + pos] = (uint8_t)s;
+      cand_cell[cbase + pos] = cell;
     }
-    const int total = __syncthreads_count(emit);
-    if (total == 0) continue;
-    // rank of this thread among the emitting threads of the round
-    __shared__ int warp_cnt[8];
-    const unsigned m = __ballot_sync(0xffffffffu, emit);
-    const int lane = tid & 31, wid = tid >> 5;
-    if (lane == 0) warp_cnt[wid] = __popc(m);
-    if (tid == 0) out_base = atomicAdd(counter, total);
-    __syncthreads();
-    if (emit) {
-      int before = __popc(m & ((1u << lane) - 1));
-      for (int w = 0; w < wid; w++) before += warp_cnt[w];
-      const int pos = out_base + before;
-      if (pos < L.cand_cap) {
-        cand_xy[cbase + pos] = xy;
-        cand_sc[cbase + pos] = (uint8_t)s;
-      }
-    }
-    __syncthreads();
+    if (s >= g.ini_th) cell_strong[(size_t)f * g.total_cells + L.cell_base + cell] = 1;
   }
 }
 
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   cudaMemsetAsync(b.n_cand, 0, sizeof(int32_t) * ORBX_MAX_LEVELS * (size_t)frames, st);
-  dim3 grid(g.total_cells, frames);
-  k_fast<<<grid, 256, 0, st>>>(g, b.pyr, b.cand_xy, b.cand_sc, b.n_cand);
+  cudaMemsetAsync(b.cell_strong, 0, sizeof(int32_t) * (size_t)g.total_cells * frames, st);
+  dim3 grid(g.total_blur_tiles, 1, frames);
+  k_fast<<<grid, 256, 0, st>>>(g, b.pyr, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong);
   return 1;
 }
 

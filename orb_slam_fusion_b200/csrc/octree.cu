@@ -8,10 +8,12 @@
 
 namespace orbx {
 
-__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ cand_xy,
-                                                const uint8_t* __restrict__ cand_sc, int32_t* __restrict__ node_of,
-                                                const int32_t* __restrict__ n_cand, uint32_t* __restrict__ sel_xy,
-                                                uint8_t* __restrict__ sel_sc, int32_t* __restrict__ n_sel) {
+__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
+                                                const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
+                                                uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
+                                                int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
+                                                uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
+                                                int32_t* __restrict__ n_sel) {
   extern __shared__ int ot_mem[];
   const int lev = blockIdx.x, f = blockIdx.y;
   const LevelGeom& L = g.lv[lev];
@@ -21,7 +23,42 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeo
   const size_t sbase = (size_t)f * g.sel_frame_cap + L.sel_off;
   int P = n_cand[f * ORBX_MAX_LEVELS + lev];
   if (P > L.cand_cap) P = L.cand_cap;
-  __shared__ int nsel_sh;
+  __shared__ int nsel_sh, n_keep;
+  // The iniThFAST -> minThFAST retry of orb_extractor.cc:783-801: k_fast emitted every FAST(min, nms)
+  // survivor with its cell (in node_of); a cell that holds a survivor with response >= ini keeps only
+  // those, any other cell keeps all.  The filtered list is what the reference hands to the quadtree.
+  if (threadIdx.x == 0) n_keep = 0;
+  __syncthreads();
+  {
+    const bool filter = g.ini_th > g.min_th;
+    const int32_t* strong = cell_strong + (size_t)f * g.total_cells + L.cell_base;
+    for (int p0 = 0; p0 < P; p0 += blockDim.x) {
+      const int p = p0 + threadIdx.x;
+      bool keep = false;
+      uint32_t v = 0;
+      uint8_t sc = 0;
+      if (p < P) {
+        v = raw_xy[cbase + p];
+        sc = raw_sc[cbase + p];
+        keep = !filter || (int)sc >= g.ini_th || !strong[node_of[cbase + p]];
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (m) {
+        int wb = 0;
+        const int lane = threadIdx.x & 31;
+        if (lane == 0) wb = atomicAdd(&n_keep, __popc(m));
+        wb = __shfl_sync(0xffffffffu, wb, 0);
+        if (keep) {
+          const int pos = wb + __popc(m & ((1u << lane) - 1));
+          cand_xy[cbase + pos] = v;
+          cand_sc[cbase + pos] = sc;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  P = n_keep;
+  if (threadIdx.x == 0) n_cand[f * ORBX_MAX_LEVELS + lev] = P;  // the count ORBX_STAGE_CAND reports
   ot_select(cand_xy + cbase, cand_sc + cbase, P, node_of + cbase, w, L.w - 2 * kFastBorder, L.h - 2 * kFastBorder,
             L.n_roots, L.root_hx, L.quota, L.wcell, L.hcell, L.ncols, sel_xy + sbase, sel_sc + sbase, &nsel_sh);
   __syncthreads();
@@ -36,8 +73,8 @@ cudaError_t octree_configure(int node_cap) {
 
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   dim3 grid(g.nlev, frames);
-  k_octree<<<grid, 256, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_xy, b.cand_sc, b.node_of, b.n_cand, b.sel_xy,
-                                                            b.sel_sc, b.n_sel);
+  k_octree<<<grid, 256, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_raw_xy, b.cand_raw_sc, b.cell_strong, b.cand_xy,
+                                                            b.cand_sc, b.node_of, b.n_cand, b.sel_xy, b.sel_sc, b.n_sel);
   return 1;
 }
 

@@ -197,7 +197,7 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     L.scale = h->scale[l];
     L.scaled_patch = (int)((float)kPatch * h->scale[l]);  // :834
     L.tab_off = tab;
-    tab += (L.w > L.h ? L.w : L.h);
+    tab += ((L.w > L.h ? L.w : L.h) + 7) / 8 * 8;  // keeps every level's tables 16-byte aligned
     L.blur_tiles_x = (L.w + 127) / 128;
     L.blur_tile_base = tiles;
     tiles += L.blur_tiles_x * ((L.h + 31) / 32);
@@ -233,6 +233,9 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   for (auto& s : h->slot) {
     CU(h, dmalloc(s, &s.b.pyr, B * plane));
     CU(h, dmalloc(s, &s.b.blur, B * plane));
+    CU(h, dmalloc(s, &s.b.cand_raw_xy, B * cand));
+    CU(h, dmalloc(s, &s.b.cand_raw_sc, B * cand));
+    CU(h, dmalloc(s, &s.b.cell_strong, B * cells));
     CU(h, dmalloc(s, &s.b.cand_xy, B * cand));
     CU(h, dmalloc(s, &s.b.cand_sc, B * cand));
     CU(h, dmalloc(s, &s.b.node_of, B * cand));

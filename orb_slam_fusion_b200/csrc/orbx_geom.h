@@ -59,9 +59,9 @@ __host__ __device__ __forceinline__
 #else
 inline
 #endif
-    long long
+    int
     px_off(const LevelGeom& g, int x, int y) {
-  return (long long)g.plane_off + (long long)(y + kPadY) * g.pitch + kPadX + x;
+  return g.plane_off + (y + kPadY) * g.pitch + kPadX + x;  // < pyr_frame_bytes, an int
 }
 
 }  // namespace orbx

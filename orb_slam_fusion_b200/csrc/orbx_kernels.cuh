@@ -12,9 +12,12 @@ namespace orbx {
 struct BatchBuffers {
   uint8_t* pyr;         // [frames][pyr_frame_bytes]   padded level planes
   uint8_t* blur;        // [frames][pyr_frame_bytes]   blurred planes, same layout
-  uint32_t* cand_xy;    // [frames][cand_frame_cap]    (y << 16) | x, relative to (16,16)
-  uint8_t* cand_sc;     // [frames][cand_frame_cap]    FAST response
-  int32_t* node_of;     // [frames][cand_frame_cap]    quadtree scratch
+  uint32_t* cand_raw_xy; // [frames][cand_frame_cap]   FAST(min, nms) survivors: (y << 16) | x, relative to (16,16)
+  uint8_t* cand_raw_sc;  // [frames][cand_frame_cap]   FAST response
+  int32_t* cell_strong;  // [frames][total_cells]      1 if a survivor of the cell reaches iniThFAST
+  uint32_t* cand_xy;    // [frames][cand_frame_cap]    candidates after the ini/min retry rule
+  uint8_t* cand_sc;     // [frames][cand_frame_cap]
+  int32_t* node_of;     // [frames][cand_frame_cap]    cell of each raw survivor, then quadtree scratch
   int32_t* n_cand;      // [frames][ORBX_MAX_LEVELS]
   uint32_t* sel_xy;     // [frames][sel_frame_cap]     (y << 16) | x, level coordinates
   uint8_t* sel_sc;      // [frames][sel_frame_cap]

@@ -49,48 +49,93 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 }
 
 // ------------------------------------------------------------------ bilinear resize
-// Level `lev` from level `lev-1` (orb_extractor.cc:1106).  Block 32x8 threads, 4 px per thread.
+// Level `lev` from level `lev-1` (orb_extractor.cc:1106), cv::resize INTER_LINEAR 8U arithmetic
+// (SURVEY.md A.2): H[x] = S[sx]*a0 + S[sx+1]*a1, dst = (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
+// CTA = 128 output columns x `th` output rows.  The horizontal pass runs ONCE per source row the tile
+// needs (adjacent output rows share source rows) and keeps H>>4 (15 bits) as u16 in shared memory;
+// the vertical pass combines two shared rows per output row.  4 px per thread, 32-bit stores.
+constexpr int kRsTW = 128, kRsMaxTH = 16, kRsRows = 2 * kRsMaxTH + 4;
+
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                 const int16_t* __restrict__ xofs, const int16_t* __restrict__ xalpha,
                                                 const int16_t* __restrict__ yofs, const int16_t* __restrict__ ybeta,
-                                                int lev) {
+                                                int lev, int th) {
+  __shared__ __align__(16) uint16_t hq[kRsRows * kRsTW];
   const LevelGeom& D = g.lv[lev];
   const LevelGeom& S = g.lv[lev - 1];
-  const int dy = blockIdx.y * 8 + threadIdx.y;
-  const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  if (dy >= D.h || dx0 >= D.w) return;
+  const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
+  const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
+  const int t = D.tab_off, tid = threadIdx.x;
   uint8_t* frame = pyr + (size_t)blockIdx.z * g.pyr_frame_bytes;
-  const int t = D.tab_off;
-  const int sy0 = yofs[2 * (t + dy)], sy1 = yofs[2 * (t + dy) + 1];
-  const int b0 = ybeta[2 * (t + dy)], b1 = ybeta[2 * (t + dy) + 1];
-  const uint8_t* r0 = frame + px_off(S, 0, sy0);
-  const uint8_t* r1 = frame + px_off(S, 0, sy1);
-  uint32_t packed = 0;
+  // source rows [row_lo, row_hi] used by this tile (yofs holds the clamped pair of every output row)
+  const int row_lo = yofs[2 * (t + y0)], row_hi = yofs[2 * (t + y1 - 1) + 1];
+  const int n_rows = min(row_hi - row_lo + 1, kRsRows);
+  const int src_base = px_off(S, 0, row_lo);
+
+  for (int i = tid; i < n_rows * 32; i += 256) {  // horizontal pass: (source row, quad of output columns)
+    const int r = i >> 5, q = i & 31;
+    const int dx0 = x0 + 4 * q;
+    if (dx0 >= D.w) continue;
+    const uint8_t* sp = frame + src_base + r * S.pitch;
+    uint32_t o[4] = {0, 0, 0, 0};
+    if (dx0 + 4 <= D.w) {
+      // tables are 8-byte (xofs) / 16-byte (xalpha) aligned at multiples of 4 columns: tab_off % 4 == 0
+      const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
+      const int4 al = *reinterpret_cast<const int4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column
+      const int sxs[4] = {sx.x, sx.y, sx.z, sx.w};
+      const int als[4] = {al.x, al.y, al.z, al.w};
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int dx = dx0 + k;
-    if (dx < D.w) {
-      const int sx = xofs[t + dx];
-      const int sx1 = min(sx + 1, S.w - 1);
-      const int a0 = xalpha[2 * (t + dx)], a1 = xalpha[2 * (t + dx) + 1];
-      const int h0 = r0[sx] * a0 + r0[sx1] * a1;
-      const int h1 = r1[sx] * a0 + r1[sx1] * a1;
-      packed |= (uint32_t)resize_vcombine(h0, h1, b0, b1) << (8 * k);
+      for (int k = 0; k < 4; k++) {
+        // a1 == 0 where sx is the last column, so sx+1 may read the (allocated) padding
+        const int h = sp[sxs[k]] * (int)(int16_t)(als[k] & 0xFFFF) + sp[sxs[k] + 1] * (als[k] >> 16);
+        o[k] = (uint32_t)(h >> 4);
+      }
+    } else {
+      for (int k = 0; dx0 + k < D.w; k++) {
+        const int sx = xofs[t + dx0 + k];
+        const int h = sp[sx] * xalpha[2 * (t + dx0 + k)] + sp[sx + 1] * xalpha[2 * (t + dx0 + k) + 1];
+        o[k] = (uint32_t)(h >> 4);
+      }
     }
+    *reinterpret_cast<uint2*>(&hq[r * kRsTW + 4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
   }
-  uint8_t* d = frame + px_off(D, dx0, dy);
-  if (dx0 + 4 <= D.w) {
-    *reinterpret_cast<uint32_t*>(d) = packed;
-  } else {
-    for (int k = 0; dx0 + k < D.w; k++) d[k] = (uint8_t)(packed >> (8 * k));
+  __syncthreads();
+
+  for (int i = tid; i < (y1 - y0) * 32; i += 256) {  // vertical pass
+    const int yy = i >> 5, q = i & 31;
+    const int dy = y0 + yy, dx0 = x0 + 4 * q;
+    if (dx0 >= D.w) continue;
+    const int r0 = yofs[2 * (t + dy)] - row_lo, r1 = yofs[2 * (t + dy) + 1] - row_lo;
+    const int b0 = ybeta[2 * (t + dy)], b1 = ybeta[2 * (t + dy) + 1];
+    const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
+    const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
+    const int h0[4] = {(int)(u0.x & 0xFFFF), (int)(u0.x >> 16), (int)(u0.y & 0xFFFF), (int)(u0.y >> 16)};
+    const int h1[4] = {(int)(u1.x & 0xFFFF), (int)(u1.x >> 16), (int)(u1.y & 0xFFFF), (int)(u1.y >> 16)};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      packed |= (uint32_t)v << (8 * k);
+    }
+    uint8_t* d = frame + px_off(D, dx0, dy);
+    if (dx0 + 4 <= D.w) {
+      *reinterpret_cast<uint32_t*>(d) = packed;
+    } else {
+      for (int k = 0; dx0 + k < D.w; k++) d[k] = (uint8_t)(packed >> (8 * k));
+    }
   }
 }
 
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   int n = 0;
   for (int lev = 1; lev < g.nlev; lev++) {
-    dim3 grid((g.lv[lev].w + 127) / 128, (g.lv[lev].h + 7) / 8, frames);
-    k_resize<<<grid, dim3(32, 8), 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev);
+    // rows per tile so that the source rows of a tile fit the shared buffer (any scale factor)
+    const double ratio = (double)g.lv[lev - 1].h / g.lv[lev].h;
+    int th = (int)((kRsRows - 3) / ratio);
+    th = th < 1 ? 1 : (th > kRsMaxTH ? kRsMaxTH : th);
+    dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
+    k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
     n++;
   }
   return n;
@@ -130,12 +175,14 @@ int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStr
 
 // ------------------------------------------------------------------ 7x7 Gaussian blur
 // All levels in one launch; CTA = one 128x32 output tile.  Raw tile (38 rows x 136 B, reflect-101
-// at the true image edge) -> horizontal Q8.8 pass into u16 -> vertical pass -> packed u32 stores.
-constexpr int kBlurTW = 128, kBlurTH = 32, kBlurRawPitch = 136;
+// at the true image edge) -> horizontal Q8.8 pass with DP4A (two 4-tap dot products per pixel on
+// funnel-shifted byte windows) into u16 -> vertical pass with DP2A on the packed u16 pairs ->
+// packed u32 stores.  Kernel [18,34,48,56,48,34,18].
+constexpr int kBlurTW = 128, kBlurTH = 32, kBlurRawW = 34;  // raw row: 34 words = bytes x0-4 .. x0+131
 
 __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
-  __shared__ __align__(16) uint8_t raw[(kBlurTH + 6) * kBlurRawPitch];
+  __shared__ __align__(16) uint32_t raw[(kBlurTH + 6) * kBlurRawW];
   __shared__ __align__(16) uint16_t tmp[(kBlurTH + 6) * kBlurTW];
   int lev = 0;
   while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].blur_tile_base) lev++;
@@ -147,46 +194,45 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FrameGeom 
   const uint8_t* src = pyr + fo;
   const int tid = threadIdx.x;
 
-  // raw[r][c]: image pixel (x0 + c - 4, y0 + r - 3); c = 1..134 used
-  for (int i = tid; i < (kBlurTH + 6) * 32; i += 256) {  // the 128 aligned middle columns, 4 at a time
-    const int r = i >> 5, q = i & 31;
-    const int y = reflect101(y0 + r - 3, L.h);
-    const int x = x0 + 4 * q;
+  // raw word c of row r: image pixels x0 - 4 + 4c .. +3 of row reflect(y0 + r - 3).  Only what the
+  // tile's valid outputs read is loaded (partial tiles at the right / bottom edge skip the rest).
+  const int rows_needed = min(kBlurTH, L.h - y0) + 6, words_needed = (min(kBlurTW, L.w - x0) + 3 + 3) / 4 + 1;
+  const int base = px_off(L, 0, 0);
+  for (int i = tid; i < rows_needed * kBlurRawW; i += 256) {
+    const int r = i / kBlurRawW, c = i - r * kBlurRawW;
+    if (c >= words_needed) continue;
+    int y = y0 + r - 3;
+    y = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);  // reflect-101, one fold (levels are >= 67 px)
+    const int x = x0 - 4 + 4 * c;
+    const uint8_t* rowp = src + base + y * L.pitch;
     uint32_t v;
-    if (x + 4 <= L.w) {
-      v = *reinterpret_cast<const uint32_t*>(src + px_off(L, x, y));
+    if (x >= 0 && x + 4 <= L.w) {
+      v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
     } else {
       v = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++) v |= (uint32_t)src[px_off(L, reflect101(x + k, L.w), y)] << (8 * k);
+      for (int k = 0; k < 4; k++) {
+        int xx = x + k;
+        xx = xx < 0 ? -xx : (xx >= L.w ? 2 * (L.w - 1) - xx : xx);
+        v |= (uint32_t)rowp[xx] << (8 * k);
+      }
     }
-    *reinterpret_cast<uint32_t*>(&raw[r * kBlurRawPitch + 4 + 4 * q]) = v;
-  }
-  for (int i = tid; i < (kBlurTH + 6) * 6; i += 256) {  // 3 + 3 halo columns
-    const int r = i / 6, k = i - r * 6;
-    const int c = k < 3 ? 1 + k : 132 + (k - 3);
-    const int y = reflect101(y0 + r - 3, L.h);
-    raw[r * kBlurRawPitch + c] = src[px_off(L, reflect101(x0 + c - 4, L.w), y)];
+    raw[i] = v;
   }
   __syncthreads();
 
-  for (int i = tid; i < (kBlurTH + 6) * 32; i += 256) {  // horizontal pass, 4 px per step
+  const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
+  for (int i = tid; i < rows_needed * 32; i += 256) {  // horizontal pass, 4 px per step
     const int r = i >> 5, q = i & 31;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&raw[r * kBlurRawPitch + 4 * q]);
+    if (x0 + 4 * q >= L.w) continue;
+    const uint32_t* w = &raw[r * kBlurRawW + q];
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    int p[12];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      p[k] = (w0 >> (8 * k)) & 255;
-      p[4 + k] = (w1 >> (8 * k)) & 255;
-      p[8 + k] = (w2 >> (8 * k)) & 255;
-    }
-    uint16_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++)  // output x = 4q+k is centred on raw column 4q+k+4
-      o[k] = (uint16_t)gauss7_h(p[k + 1], p[k + 2], p[k + 3], p[k + 4], p[k + 5], p[k + 6], p[k + 7]);
-    *reinterpret_cast<uint2*>(&tmp[r * kBlurTW + 4 * q]) =
-        make_uint2((uint32_t)o[0] | ((uint32_t)o[1] << 16), (uint32_t)o[2] | ((uint32_t)o[3] << 16));
+    // output x0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
+    const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
+    const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
+    const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
+    const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
+    *reinterpret_cast<uint2*>(&tmp[r * kBlurTW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
   }
   __syncthreads();
 
@@ -195,16 +241,17 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FrameGeom 
     const int yy = i >> 5, q = i & 31;
     const int y = y0 + yy, x = x0 + 4 * q;
     if (y >= L.h || x >= L.w) continue;
-    int t[7][4];
+    uint32_t a0 = 32768u, a1 = 32768u, a2 = 32768u, a3 = 32768u;
+    const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
 #pragma unroll
     for (int j = 0; j < 7; j++) {
       const uint2 v = *reinterpret_cast<const uint2*>(&tmp[(yy + j) * kBlurTW + 4 * q]);
-      t[j][0] = v.x & 0xFFFF; t[j][1] = v.x >> 16; t[j][2] = v.y & 0xFFFF; t[j][3] = v.y >> 16;
+      a0 = __dp2a_lo(v.x, kv[j], a0);        // low u16 x k
+      a1 = __dp2a_lo(v.x, kv[j] << 8, a1);   // high u16 x k
+      a2 = __dp2a_lo(v.y, kv[j], a2);
+      a3 = __dp2a_lo(v.y, kv[j] << 8, a3);
     }
-    uint32_t packed = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      packed |= (uint32_t)gauss7_v(t[0][k], t[1][k], t[2][k], t[3][k], t[4][k], t[5][k], t[6][k]) << (8 * k);
+    const uint32_t packed = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
     uint8_t* d = dst + px_off(L, x, y);
     if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(d) = packed;
     else for (int k = 0; x + k < L.w; k++) d[k] = (uint8_t)(packed >> (8 * k));
