@@ -28,6 +28,7 @@ constexpr int kFtRawW = 34;                   // raw words per row: bytes X0-4 .
 constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the raw and score planes
 constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
 constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
+constexpr int kFtStrip = 5;                   // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
 constexpr int kFtMaxOut = 1536;               // NMS survivors of one tile (<= (64+4)*(16+2))
 
 // byte-wise |a - b| > t for four pixels at once; t <= 126.  VABSDIFF4 is a native instruction,
@@ -37,7 +38,7 @@ __device__ __forceinline__ uint32_t exceeds4(uint32_t a, uint32_t b, uint32_t k)
   return (((d & 0x7f7f7f7fu) + k) | d) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong) {
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom 
   __shared__ uint16_t list[kFtScH * kFtPitch];  // (score row << 8) | byte column of pixels to score
   __shared__ uint16_t outl[kFtMaxOut];
   __shared__ int n_list, n_out, out_base;
+  __shared__ uint8_t xedge[kFtPitch], yedge[kFtScH];  // bit 0: first column / row of a cell, bit 1: last
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
   int lev = 0;
@@ -61,18 +63,28 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom 
   const int lo = min(g.ini_th, g.min_th);
 
   if (tid == 0) { n_list = 0; n_out = 0; }
+  if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
+    const int m = (X0 - 4 + tid - kEdge + 64 * L.wcell) % L.wcell;
+    xedge[tid] = (uint8_t)((m == 0) | ((m == L.wcell - 1) << 1));
+  } else if (tid < kFtPitch + kFtScH) {
+    const int m = (Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell) % L.hcell;
+    yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
+  }
   for (int i = tid; i < kFtScH * kFtRawW; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
-  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r
+  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r; thread = (column, 6 rows)
   {
-    const uint8_t* src = pyr + (size_t)f * g.pyr_frame_bytes;
-    const int base = px_off(L, X0 - 4, Y0 - 4);
-    for (int i = tid; i < kFtRawH * kFtRawW; i += 256) {
-      const int r = i / kFtRawW, c = i - r * kFtRawW;
-      const int y = Y0 - 4 + r, x = X0 - 4 + 4 * c;
-      uint32_t v = 0;
-      if (y >= 0 && y < L.h && x < L.w + 16)  // the plane has 32 B left / >= 19 B right padding
-        v = __ldg(reinterpret_cast<const uint32_t*>(src + base + r * L.pitch + 4 * c));
-      raw_w[i] = v;
+    const int c = tid % kFtRawW, r0 = (tid / kFtRawW) * 6;
+    const int x = X0 - 4 + 4 * c;
+    const bool col_ok = x < L.w + 16;  // the plane has 32 B left / >= 19 B right padding
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame_bytes + px_off(L, x, Y0 - 4 + r0);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int r = r0 + i, y = Y0 - 4 + r;
+      if (r < kFtRawH) {
+        uint32_t v = 0;
+        if (col_ok && y >= 0 && y < L.h) v = __ldg(reinterpret_cast<const uint32_t*>(src + i * L.pitch));
+        raw_w[r * kFtRawW + c] = v;
+      }
     }
   }
   __syncthreads();
@@ -81,33 +93,41 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom 
   // Every 9-arc holds one pixel of each opposite pair (k, k+8), so a corner needs a ring pixel that
   // differs from the centre by more than t in the pair (0,8) AND in the pair (4,12).
   // Item (rr, wc): score row rr (y = Y0-1+rr, raw row rr+3), raw word wc (x = X0-4+4wc+j).
+  // Thread (wc, rg) walks raw word column wc (x = X0-4+4wc+j) down the kFtStrip score rows of row
+  // group rg (y = Y0-1+rr, raw row rr+3): column masks, neighbour indices and addresses are set up
+  // once per thread, and the warp scan + shared atomic of the compaction run once per strip.
   const uint32_t kthr = (uint32_t)(0x7f - lo) * 0x01010101u;
   const int xlo = max(kEdge, X0 - 1), xhi = min(L.w - kEdge, X0 + kFtW + 1);  // scored columns [xlo, xhi)
-  for (int base = 0; base < kFtScH * kFtRawW; base += 256) {
-    const int it = base + tid;
-    uint32_t keep = 0;
-    int rr = 0, col0 = 0;
-    if (it < kFtScH * kFtRawW) {
-      rr = it / kFtRawW;
-      const int wc = it - rr * kFtRawW;
-      col0 = 4 * wc;
-      const int y = Y0 - 1 + rr, x = X0 - 4 + col0;
-      if (y >= kEdge && y < L.h - kEdge && x + 3 >= xlo && x < xhi) {
-        const uint32_t* row = &raw_w[(rr + 3) * kFtRawW + wc];
-        const uint32_t c = row[0];
-        const uint32_t up = row[-3 * kFtRawW], dn = row[3 * kFtRawW];
-        const uint32_t lf = __byte_perm(row[wc > 0 ? -1 : 0], c, 0x4321);               // pixels x-3
-        const uint32_t rt = __byte_perm(c, row[wc < kFtRawW - 1 ? 1 : 0], 0x6543);      // pixels x+3
-        if (lo <= 126)
-          keep = (exceeds4(dn, c, kthr) | exceeds4(up, c, kthr)) & (exceeds4(rt, c, kthr) | exceeds4(lf, c, kthr));
-        else
-          keep = 0x80808080u;  // thresholds beyond the byte trick: score everything
+  {
+    const int wc = tid % kFtRawW, rg = tid / kFtRawW;
+    const int x = X0 - 4 + 4 * wc;
+    uint32_t lane_mask = 0;  // 0x80 per byte lane inside the scored column range
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (x + j < xlo || x + j >= xhi) keep &= ~(0x80u << (8 * j));
+    for (int j = 0; j < 4; j++)
+      if (x + j >= xlo && x + j < xhi) lane_mask |= 0x80u << (8 * j);
+    const bool score_all = lo > 126;  // thresholds beyond the byte trick: score everything
+    const int wl = wc > 0 ? -1 : 0, wr = wc < kFtRawW - 1 ? 1 : 0;
+    const int rr0 = rg * kFtStrip;
+    const uint32_t* row = &raw_w[(rr0 + 3) * kFtRawW + wc];
+    uint32_t keep[kFtStrip];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kFtStrip; i++) {
+      const int rr = rr0 + i, y = Y0 - 1 + rr;
+      uint32_t k = 0;
+      if (lane_mask && rr < kFtScH && y >= kEdge && y < L.h - kEdge) {
+        const uint32_t* rp = row + i * kFtRawW;
+        const uint32_t c = rp[0];
+        const uint32_t up = rp[-3 * kFtRawW], dn = rp[3 * kFtRawW];
+        const uint32_t lf = __byte_perm(rp[wl], c, 0x4321);   // pixels x-3
+        const uint32_t rt = __byte_perm(c, rp[wr], 0x6543);   // pixels x+3
+        k = (exceeds4(dn, c, kthr) | exceeds4(up, c, kthr)) & (exceeds4(rt, c, kthr) | exceeds4(lf, c, kthr));
+        if (score_all) k = 0x80808080u;
+        k &= lane_mask;
       }
+      keep[i] = k;
+      cnt += __popc(k);
     }
-    const int cnt = __popc(keep);
     if (__any_sync(0xffffffffu, cnt != 0)) {
       int incl = cnt;
 #pragma unroll
@@ -118,10 +138,20 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom 
       int wbase = 0;
       if (lane == 31) wbase = atomicAdd(&n_list, incl);
       wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      int pos = wbase + incl - cnt;
+      if (cnt) {
+        uint16_t* lp = &list[wbase + incl - cnt];
 #pragma unroll
-      for (int j = 0; j < 4; j++)
-        if (keep & (0x80u << (8 * j))) list[pos++] = (uint16_t)((rr << 8) | (col0 + j));
+        for (int i = 0; i < kFtStrip; i++) {
+          const uint32_t b = keep[i] >> 7;  // bit 0 / 8 / 16 / 24 = lane kept
+          if (b) {
+            const uint16_t val = (uint16_t)(((rr0 + i) << 8) | (4 * wc));
+            if (b & 0x00000001u) *lp++ = val;
+            if (b & 0x00000100u) *lp++ = val + 1;
+            if (b & 0x00010000u) *lp++ = val + 2;
+            if (b & 0x01000000u) *lp++ = val + 3;
+          }
+        }
+      }
     }
   }
   __syncthreads();
@@ -147,9 +177,8 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ FrameGeom 
     const uint8_t* sp = &score[rr * kFtPitch + cb];
     const int s = sp[0];
     if (s == 0) continue;
-    const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
-    const int xm = (x - kEdge) % L.wcell, ym = (y - kEdge) % L.hcell;
-    const bool l_ok = xm != 0, r_ok = xm != L.wcell - 1, u_ok = ym != 0, d_ok = ym != L.hcell - 1;
+    const int xe = xedge[cb], ye = yedge[rr];
+    const bool l_ok = !(xe & 1), r_ok = !(xe & 2), u_ok = !(ye & 1), d_ok = !(ye & 2);
     bool is_max = (!l_ok || s > sp[-1]) && (!r_ok || s > sp[1]) && (!u_ok || s > sp[-kFtPitch]) && (!d_ok || s > sp[kFtPitch]);
     is_max = is_max && (!(l_ok && u_ok) || s > sp[-kFtPitch - 1]) && (!(r_ok && u_ok) || s > sp[-kFtPitch + 1]) &&
              (!(l_ok && d_ok) || s > sp[kFtPitch - 1]) && (!(r_ok && d_ok) || s > sp[kFtPitch + 1]);

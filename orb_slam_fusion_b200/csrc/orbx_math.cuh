@@ -106,46 +106,48 @@ ORBX_HD bool has_run9(uint32_t mask16) {
 ORBX_HD int imin(int a, int b) { return a < b ? a : b; }
 ORBX_HD int imax(int a, int b) { return a > b ? a : b; }
 
-// max over the 16 cyclic 9-arcs of min(v[k..k+8]) for a 16-vector v (sliding minima by doubling)
-ORBX_HD int max_arc9_min(const int (&v)[16]) {
-  int a[16], b[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) a[k] = imin(v[k], v[(k + 1) & 15]);        // window 2
-#pragma unroll
-  for (int k = 0; k < 16; k++) b[k] = imin(a[k], a[(k + 2) & 15]);        // window 4
-#pragma unroll
-  for (int k = 0; k < 16; k++) a[k] = imin(b[k], b[(k + 4) & 15]);        // window 8
-  int best = -256;
-#pragma unroll
-  for (int k = 0; k < 16; k++) best = imax(best, imin(a[k], v[(k + 8) & 15]));  // window 9
-  return best;
+ORBX_HD int imin3(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+  return __vimin3_s32(a, b, c);  // one VIMNMX3
+#else
+  return imin(a, imin(b, c));
+#endif
+}
+ORBX_HD int imax3(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+  return __vimax3_s32(a, b, c);
+#else
+  return imax(a, imax(b, c));
+#endif
 }
 
 // FAST-9 "best" value of a pixel with centre c and ring r[16]:
-//   max over arcs of max(min_arc(c - r), -max_arc(c - r)).
+//   best = max over the 16 cyclic 9-arcs of max(min_arc(c - r), -max_arc(c - r)).
 // The pixel is a corner at threshold t iff best > t; cv::FAST reports response = best - 1.
 // Returns 0 when the pixel is not a corner at threshold t (best <= t).
+// Sliding 9-window minima / maxima by composition of 3-windows: 16 + 16 three-input ops each.
 ORBX_HD int fast9_score(int c, const int (&r)[16], int t) {
-  uint32_t dark = 0, bright = 0;  // ring darker / brighter than the centre by more than t
+  int d[16], a[16], b[16];
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const int d = c - r[k];
-    dark |= (uint32_t)(d > t) << k;
-    bright |= (uint32_t)(d < -t) << k;
-  }
-  int v[16];
-  if (has_run9(dark)) {
+  for (int k = 0; k < 16; k++) d[k] = c - r[k];
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = c - r[k];
-  } else if (has_run9(bright)) {
+  for (int k = 0; k < 16; k++) a[k] = imin3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);   // min of 3
 #pragma unroll
-    for (int k = 0; k < 16; k++) v[k] = r[k] - c;
-  } else {
-    return 0;
-  }
-  // A 9-arc of one polarity excludes any 9-arc of the other (two 9-arcs of a 16-ring overlap),
-  // so the passing polarity alone attains the maximum.
-  return max_arc9_min(v) - 1;
+  for (int k = 0; k < 16; k++) b[k] = imin3(a[k], a[(k + 3) & 15], a[(k + 6) & 15]);   // min of 9
+  int best = imax3(b[0], b[1], b[2]);
+#pragma unroll
+  for (int k = 3; k < 15; k += 2) best = imax3(best, b[k], b[k + 1]);
+  best = imax(best, b[15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) a[k] = imax3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);   // max of 3
+#pragma unroll
+  for (int k = 0; k < 16; k++) b[k] = imax3(a[k], a[(k + 3) & 15], a[(k + 6) & 15]);   // max of 9
+  int worst = imin3(b[0], b[1], b[2]);
+#pragma unroll
+  for (int k = 3; k < 15; k += 2) worst = imin3(worst, b[k], b[k + 1]);
+  worst = imin(worst, b[15]);
+  best = imax(best, -worst);
+  return best > t ? best - 1 : 0;
 }
 
 // ---- bilinear resize, 8U fixed point -----------------------------------

@@ -72,57 +72,81 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
   const int n_rows = min(row_hi - row_lo + 1, kRsRows);
   const int src_base = px_off(S, 0, row_lo);
 
-  for (int i = tid; i < n_rows * 32; i += 256) {  // horizontal pass: (source row, quad of output columns)
-    const int r = i >> 5, q = i & 31;
+  // ---- horizontal pass: thread = (quad q of output columns, 5 source rows); the column tables are
+  // read once per thread
+  {
+    const int rpg = (n_rows + 7) >> 3;  // source rows per warp: the 8 warps share the rows evenly
+    const int q = tid & 31, r0 = (tid >> 5) * rpg;
     const int dx0 = x0 + 4 * q;
-    if (dx0 >= D.w) continue;
-    const uint8_t* sp = frame + src_base + r * S.pitch;
-    uint32_t o[4] = {0, 0, 0, 0};
-    if (dx0 + 4 <= D.w) {
-      // tables are 8-byte (xofs) / 16-byte (xalpha) aligned at multiples of 4 columns: tab_off % 4 == 0
-      const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
-      const int4 al = *reinterpret_cast<const int4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column
-      const int sxs[4] = {sx.x, sx.y, sx.z, sx.w};
-      const int als[4] = {al.x, al.y, al.z, al.w};
+    if (dx0 < D.w && r0 < n_rows) {
+      int sxs[4] = {0, 0, 0, 0}, a0s[4] = {0, 0, 0, 0}, a1s[4] = {0, 0, 0, 0};
+      if (dx0 + 4 <= D.w) {
+        // tables are 8-byte (xofs) / 16-byte (xalpha) aligned at multiples of 4 columns: tab_off % 8 == 0
+        const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
+        const int4 al = *reinterpret_cast<const int4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column
+        sxs[0] = sx.x; sxs[1] = sx.y; sxs[2] = sx.z; sxs[3] = sx.w;
+        const int als[4] = {al.x, al.y, al.z, al.w};
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        // a1 == 0 where sx is the last column, so sx+1 may read the (allocated) padding
-        const int h = sp[sxs[k]] * (int)(int16_t)(als[k] & 0xFFFF) + sp[sxs[k] + 1] * (als[k] >> 16);
-        o[k] = (uint32_t)(h >> 4);
+        for (int k = 0; k < 4; k++) { a0s[k] = (int)(int16_t)(als[k] & 0xFFFF); a1s[k] = als[k] >> 16; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (dx0 + k < D.w) {
+            sxs[k] = xofs[t + dx0 + k];
+            a0s[k] = xalpha[2 * (t + dx0 + k)];
+            a1s[k] = xalpha[2 * (t + dx0 + k) + 1];
+          }
+        }
       }
-    } else {
-      for (int k = 0; dx0 + k < D.w; k++) {
-        const int sx = xofs[t + dx0 + k];
-        const int h = sp[sx] * xalpha[2 * (t + dx0 + k)] + sp[sx + 1] * xalpha[2 * (t + dx0 + k) + 1];
-        o[k] = (uint32_t)(h >> 4);
+      // a1 == 0 where sx is the last column, so sx+1 may read the (allocated) padding
+      const uint8_t* sp = frame + src_base + r0 * S.pitch;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        if (i < rpg && r0 + i < n_rows) {
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; k++) o[k] = (uint32_t)((sp[sxs[k]] * a0s[k] + sp[sxs[k] + 1] * a1s[k]) >> 4);
+          *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+          sp += S.pitch;
+        }
       }
     }
-    *reinterpret_cast<uint2*>(&hq[r * kRsTW + 4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
   }
   __syncthreads();
 
-  for (int i = tid; i < (y1 - y0) * 32; i += 256) {  // vertical pass
-    const int yy = i >> 5, q = i & 31;
-    const int dy = y0 + yy, dx0 = x0 + 4 * q;
-    if (dx0 >= D.w) continue;
-    const int r0 = yofs[2 * (t + dy)] - row_lo, r1 = yofs[2 * (t + dy) + 1] - row_lo;
-    const int b0 = ybeta[2 * (t + dy)], b1 = ybeta[2 * (t + dy) + 1];
-    const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
-    const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
-    const int h0[4] = {(int)(u0.x & 0xFFFF), (int)(u0.x >> 16), (int)(u0.y & 0xFFFF), (int)(u0.y >> 16)};
-    const int h1[4] = {(int)(u1.x & 0xFFFF), (int)(u1.x >> 16), (int)(u1.y & 0xFFFF), (int)(u1.y >> 16)};
-    uint32_t packed = 0;
+  // ---- vertical pass: thread = (quad q, 2 output rows)
+  {
+    const int q = tid & 31, yy0 = (tid >> 5) * 2;
+    const int dx0 = x0 + 4 * q;
+    if (dx0 < D.w) {
+      uint8_t* d = frame + px_off(D, dx0, y0 + yy0);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;
-      v = v < 0 ? 0 : (v > 255 ? 255 : v);
-      packed |= (uint32_t)v << (8 * k);
-    }
-    uint8_t* d = frame + px_off(D, dx0, dy);
-    if (dx0 + 4 <= D.w) {
-      *reinterpret_cast<uint32_t*>(d) = packed;
-    } else {
-      for (int k = 0; dx0 + k < D.w; k++) d[k] = (uint8_t)(packed >> (8 * k));
+      for (int i = 0; i < 2; i++) {
+        const int dy = y0 + yy0 + i;
+        if (dy < y1) {
+          const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));   // (row0 | row1 << 16)
+          const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));  // (b0 | b1 << 16)
+          const int r0 = (int)(yo & 0xFFFF) - row_lo, r1 = (int)(yo >> 16) - row_lo;
+          const int b0 = (int)(int16_t)(yb & 0xFFFF), b1 = (int)yb >> 16;
+          const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
+          const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
+          const int h0[4] = {(int)(u0.x & 0xFFFF), (int)(u0.x >> 16), (int)(u0.y & 0xFFFF), (int)(u0.y >> 16)};
+          const int h1[4] = {(int)(u1.x & 0xFFFF), (int)(u1.x >> 16), (int)(u1.y & 0xFFFF), (int)(u1.y >> 16)};
+          uint32_t packed = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            packed |= (uint32_t)v << (8 * k);
+          }
+          uint8_t* dp = d + i * D.pitch;
+          if (dx0 + 4 <= D.w) {
+            *reinterpret_cast<uint32_t*>(dp) = packed;
+          } else {
+            for (int k = 0; dx0 + k < D.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
+          }
+        }
+      }
     }
   }
 }
@@ -178,12 +202,19 @@ int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStr
 // at the true image edge) -> horizontal Q8.8 pass with DP4A (two 4-tap dot products per pixel on
 // funnel-shifted byte windows) into u16 -> vertical pass with DP2A on the packed u16 pairs ->
 // packed u32 stores.  Kernel [18,34,48,56,48,34,18].
+// Every phase gives a thread a fixed column and a short run of rows, so that column tests, table
+// look-ups and address arithmetic happen once per thread instead of once per pixel.
 constexpr int kBlurTW = 128, kBlurTH = 32, kBlurRawW = 34;  // raw row: 34 words = bytes x0-4 .. x0+131
+constexpr int kBlurRawH = kBlurTH + 6;
 
-__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+__device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one fold (|overshoot| < len)
+  return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
+}
+
+__global__ void __launch_bounds__(256, 8) k_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur) {
-  __shared__ __align__(16) uint32_t raw[(kBlurTH + 6) * kBlurRawW];
-  __shared__ __align__(16) uint16_t tmp[(kBlurTH + 6) * kBlurTW];
+  __shared__ __align__(16) uint32_t raw[kBlurRawH * kBlurRawW];
+  __shared__ __align__(16) uint16_t tmp[kBlurRawH * kBlurTW];
   int lev = 0;
   while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].blur_tile_base) lev++;
   const LevelGeom& L = g.lv[lev];
@@ -191,70 +222,100 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ FrameGeom 
   const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
   const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
   const size_t fo = (size_t)blockIdx.z * g.pyr_frame_bytes;
-  const uint8_t* src = pyr + fo;
   const int tid = threadIdx.x;
+  const int rows_out = min(kBlurTH, L.h - y0), rows_needed = rows_out + 6;
+  const int cols_out = min(kBlurTW, L.w - x0);
 
-  // raw word c of row r: image pixels x0 - 4 + 4c .. +3 of row reflect(y0 + r - 3).  Only what the
-  // tile's valid outputs read is loaded (partial tiles at the right / bottom edge skip the rest).
-  const int rows_needed = min(kBlurTH, L.h - y0) + 6, words_needed = (min(kBlurTW, L.w - x0) + 3 + 3) / 4 + 1;
-  const int base = px_off(L, 0, 0);
-  for (int i = tid; i < rows_needed * kBlurRawW; i += 256) {
-    const int r = i / kBlurRawW, c = i - r * kBlurRawW;
-    if (c >= words_needed) continue;
-    int y = y0 + r - 3;
-    y = y < 0 ? -y : (y >= L.h ? 2 * (L.h - 1) - y : y);  // reflect-101, one fold (levels are >= 67 px)
+  // ---- raw tile: thread = (word column c, 6 rows).  Word c holds x = x0-4+4c .. +3 of row
+  // reflect(y0 + r - 3); words that straddle the image edge are assembled byte by byte.
+  {
+    const int c = tid % kBlurRawW, r0 = (tid / kBlurRawW) * 6;
     const int x = x0 - 4 + 4 * c;
-    const uint8_t* rowp = src + base + y * L.pitch;
-    uint32_t v;
-    if (x >= 0 && x + 4 <= L.w) {
-      v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
-    } else {
-      v = 0;
+    const bool needed = 4 * c < cols_out + 8;       // bytes up to column cols_out + 3 + 4
+    const bool interior = x >= 0 && x + 4 <= L.w;
+    const uint8_t* src = pyr + fo + px_off(L, 0, 0);
+    int xs[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        int xx = x + k;
-        xx = xx < 0 ? -xx : (xx >= L.w ? 2 * (L.w - 1) - xx : xx);
-        v |= (uint32_t)rowp[xx] << (8 * k);
+    for (int k = 0; k < 4; k++) xs[k] = reflect1(x + k, L.w);
+    if (needed) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        const int r = r0 + i;
+        if (r < rows_needed) {
+          const uint8_t* rowp = src + reflect1(y0 + r - 3, L.h) * L.pitch;
+          uint32_t v;
+          if (interior) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
+          } else {
+            v = (uint32_t)rowp[xs[0]] | ((uint32_t)rowp[xs[1]] << 8) | ((uint32_t)rowp[xs[2]] << 16) | ((uint32_t)rowp[xs[3]] << 24);
+          }
+          raw[r * kBlurRawW + c] = v;
+        }
       }
     }
-    raw[i] = v;
   }
   __syncthreads();
 
-  const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
-  for (int i = tid; i < rows_needed * 32; i += 256) {  // horizontal pass, 4 px per step
-    const int r = i >> 5, q = i & 31;
-    if (x0 + 4 * q >= L.w) continue;
-    const uint32_t* w = &raw[r * kBlurRawW + q];
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    // output x0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
-    const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
-    const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
-    const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
-    const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
-    *reinterpret_cast<uint2*>(&tmp[r * kBlurTW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
-  }
-  __syncthreads();
-
-  uint8_t* dst = blur + fo;
-  for (int i = tid; i < kBlurTH * 32; i += 256) {  // vertical pass
-    const int yy = i >> 5, q = i & 31;
-    const int y = y0 + yy, x = x0 + 4 * q;
-    if (y >= L.h || x >= L.w) continue;
-    uint32_t a0 = 32768u, a1 = 32768u, a2 = 32768u, a3 = 32768u;
-    const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
+  // ---- horizontal pass: thread = (quad q of output columns, 5 raw rows)
+  {
+    const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
+    const int q = tid & 31, r0 = (tid >> 5) * 5;
+    if (4 * q < cols_out) {
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-      const uint2 v = *reinterpret_cast<const uint2*>(&tmp[(yy + j) * kBlurTW + 4 * q]);
-      a0 = __dp2a_lo(v.x, kv[j], a0);        // low u16 x k
-      a1 = __dp2a_lo(v.x, kv[j] << 8, a1);   // high u16 x k
-      a2 = __dp2a_lo(v.y, kv[j], a2);
-      a3 = __dp2a_lo(v.y, kv[j] << 8, a3);
+      for (int i = 0; i < 5; i++) {
+        const int r = r0 + i;
+        if (r < rows_needed) {
+          const uint32_t* w = &raw[r * kBlurRawW + q];
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          // output x0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
+          const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
+          const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
+          const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
+          const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
+          *reinterpret_cast<uint2*>(&tmp[r * kBlurTW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
+        }
+      }
     }
-    const uint32_t packed = (a0 >> 16) | ((a1 >> 16) << 8) | ((a2 >> 16) << 16) | ((a3 >> 16) << 24);
-    uint8_t* d = dst + px_off(L, x, y);
-    if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(d) = packed;
-    else for (int k = 0; x + k < L.w; k++) d[k] = (uint8_t)(packed >> (8 * k));
+  }
+  __syncthreads();
+
+  // ---- vertical pass: thread = (quad q, 4 output rows); the 10 rows it needs are read once
+  {
+    const int q = tid & 31, yy0 = (tid >> 5) * 4;
+    const int x = x0 + 4 * q;
+    if (4 * q < cols_out && yy0 < rows_out) {
+      uint32_t acc[4][4];
+#pragma unroll
+      for (int o = 0; o < 4; o++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[o][k] = 32768u;
+      const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+      for (int j = 0; j < 10; j++) {
+        // rows past the tile's last needed row are never used by a stored output
+        const uint2 v = *reinterpret_cast<const uint2*>(&tmp[min(yy0 + j, kBlurRawH - 1) * kBlurTW + 4 * q]);
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          const int tap = j - o;
+          if (tap >= 0 && tap < 7) {
+            acc[o][0] = __dp2a_lo(v.x, kv[tap], acc[o][0]);        // low u16 x k
+            acc[o][1] = __dp2a_lo(v.x, kv[tap] << 8, acc[o][1]);   // high u16 x k
+            acc[o][2] = __dp2a_lo(v.y, kv[tap], acc[o][2]);
+            acc[o][3] = __dp2a_lo(v.y, kv[tap] << 8, acc[o][3]);
+          }
+        }
+      }
+      uint8_t* d = blur + fo + px_off(L, x, y0 + yy0);
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        if (yy0 + o < rows_out) {
+          const uint32_t packed = (acc[o][0] >> 16) | ((acc[o][1] >> 16) << 8) | ((acc[o][2] >> 16) << 16) | ((acc[o][3] >> 16) << 24);
+          uint8_t* dp = d + o * L.pitch;
+          if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(dp) = packed;
+          else for (int k = 0; x + k < L.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
+        }
+      }
+    }
   }
 }
 
