@@ -70,7 +70,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,7 +84,7 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.t.join(timeout=2)
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
@@ -161,9 +161,16 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    debug = bool(os.environ.get("BENCH_DEBUG"))
+
+    def log(msg):
+        if debug:
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout for the one JSON line: NCCL's own banner / debug output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -178,6 +185,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    log('process group ready')
     B = args.batch
     frames = P.synth_frames("blocks", B, W, H, seed=1, first_frame=rank * B, device=local)
     ex = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=B)
@@ -216,6 +224,7 @@ def run_ours(args):
     mean_kp = float(n_host.mean())
     value = world * B * args.steps / (ms * 1e-3)
 
+    log('device-resident timing done: %.3f ms' % ms)
     # ---- end to end through the C ABI with pinned host buffers
     eb = ex_e2e = None
     eb = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=min(64, B))
@@ -244,6 +253,7 @@ def run_ours(args):
            "d2h_bytes_per_step": B * (cap * (28 + 32) + 8), "ms_per_step": 1e3 * e2e_s / args.steps}
     del eb, h_kps, h_desc
 
+    log('e2e done')
     # ---- p50 latency of one blocking single-frame call (config 1), rank 0
     p50 = None
     if rank == 0:
@@ -259,6 +269,7 @@ def run_ours(args):
         p50 = 1e3 * float(np.median(lat))
         del ex1
 
+    log('latency done')
     # ---- Hamming search: 1000 queries x 10M rows, rows sharded over the ranks (config 5)
     m = P.ORBmatcher(0.7, device=local)
     r0, r1 = DB_ROWS * rank // world, DB_ROWS * (rank + 1) // world
@@ -282,6 +293,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     match_ms = max_over_ranks(m0.elapsed_time(m1)) / reps
     barrier()
+    log('matching done')
     pairs_per_s = N_QUERIES * DB_ROWS / (match_ms * 1e-3)
     matching = {"value": pairs_per_s, "unit": "pair-distances/s", "ms_per_search": match_ms,
                 "queries_per_s": N_QUERIES / (match_ms * 1e-3), "workload": "1000 queries x 10M rows, top-2 + ratio 0.7",
@@ -356,7 +368,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
