@@ -47,8 +47,7 @@ def algorithmic_bytes(w, h, n_kp):
     px = [a * b for a, b in level_sizes(w, h)]
     return {
         "pyramid": sum(px[:-1]) + sum(px[1:]),
-        "fast": sum(px),
-        "blur": 2 * sum(px),
+        "fast_blur": sum(px) + 2 * sum(px),   # FAST read + blur read/write (one fused kernel, reads the tile once)
         "describe": n_kp * 749 + n_kp * (512 + 32 + 28),
     }
 

@@ -117,13 +117,12 @@ long long orbx_launch_count(const orbx_t* h);
  * stages of every enqueued chunk while profiling is on.  ms[k] accumulates milliseconds of stage k
  * (ORBX_STAGE_T_*), *chunks the number of chunks (kernel sequences) measured; `reset` clears the
  * accumulators after reading.  Blocks until the measured chunks have finished. */
-#define ORBX_N_STAGES 6
-#define ORBX_STAGE_T_IMPORT 0   /* copy into the padded level-0 plane */
-#define ORBX_STAGE_T_PYRAMID 1  /* 7 bilinear resizes */
-#define ORBX_STAGE_T_FAST 2     /* grid FAST + NMS + retry + compaction */
-#define ORBX_STAGE_T_OCTREE 3   /* DistributeOctTree */
-#define ORBX_STAGE_T_BLUR 4     /* 7x7 Gaussian */
-#define ORBX_STAGE_T_DESCRIBE 5 /* slot plan + IC_Angle + rBRIEF + keypoint records */
+#define ORBX_N_STAGES 5
+#define ORBX_STAGE_T_IMPORT 0    /* copy into the padded level-0 plane */
+#define ORBX_STAGE_T_PYRAMID 1   /* 7 bilinear resizes */
+#define ORBX_STAGE_T_FAST_BLUR 2 /* one kernel per tile: 7x7 Gaussian + grid FAST / NMS / candidate lists */
+#define ORBX_STAGE_T_OCTREE 3    /* ini/min retry filter + DistributeOctTree */
+#define ORBX_STAGE_T_DESCRIBE 4  /* slot plan + IC_Angle + rBRIEF + keypoint records */
 int orbx_set_profiling(orbx_t* h, int on);
 int orbx_stage_times(orbx_t* h, double* ms, long long* chunks, int reset);
 

@@ -1,8 +1,10 @@
-// fast.cu -- grid FAST-9 with the iniThFAST -> minThFAST retry, all levels of all frames in one
-// launch.
+// fast.cu -- 7x7 Gaussian blur and grid FAST-9 (with the iniThFAST -> minThFAST retry) fused in one
+// tile kernel, all levels of all frames in one launch.
 //
 // Replaces the per-cell cv::FAST loop of OrbExtractor::ComputeKeyPointsOctTree
-// (orb_extractor.cc:744-825).  Arithmetic: SURVEY.md A.3.
+// (orb_extractor.cc:744-825) and the clone() + cv::GaussianBlur of :1054-1055.
+// Arithmetic: SURVEY.md A.3 / A.6.  Both stencils need the same 128x32 tile with a 4-px halo, so
+// the tile is read from HBM once.
 //
 // The reference calls cv::FAST on 700 overlapping ~42x44 ROIs per frame.  The detection domains of
 // the cells (ROI minus cv::FAST's 3-px frame) tile [19, w-19) x [19, h-19) exactly, so the level is
@@ -38,14 +40,25 @@ __device__ __forceinline__ uint32_t exceeds4(uint32_t a, uint32_t b, uint32_t k)
   return (((d & 0x7f7f7f7fu) + k) | d) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
-                                              uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
+__device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one fold (|overshoot| < len)
+  return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
+}
+
+__global__ void __launch_bounds__(256, 6) k_fast_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+                                              uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong) {
   __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawW];
-  __shared__ __align__(16) uint8_t score[kFtScH * kFtPitch];
-  __shared__ uint16_t list[kFtScH * kFtPitch];  // (score row << 8) | byte column of pixels to score
-  __shared__ uint16_t outl[kFtMaxOut];
+  // The blur's u16 intermediate and the detector's score map / lists are live in different phases
+  // and share one buffer.
+  constexpr int kScoreBytes = kFtScH * kFtPitch, kListBytes = 2 * kFtScH * kFtPitch, kOutBytes = 2 * kFtMaxOut;
+  constexpr int kTmpBytes = 2 * (kFtH + 6) * kFtW;
+  constexpr int kUnionBytes = kScoreBytes + kListBytes + kOutBytes > kTmpBytes ? kScoreBytes + kListBytes + kOutBytes : kTmpBytes;
+  __shared__ __align__(16) uint8_t u_mem[kUnionBytes];
+  uint8_t* score = u_mem;
+  uint16_t* list = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes);   // (score row << 8) | byte column of pixels to score
+  uint16_t* outl = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes + kListBytes);
+  uint16_t* tmp = reinterpret_cast<uint16_t*>(u_mem);                  // blur: (kFtH + 6) rows x kFtW u16
   __shared__ int n_list, n_out, out_base;
   __shared__ uint8_t xedge[kFtPitch], yedge[kFtScH];  // bit 0: first column / row of a cell, bit 1: last
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
@@ -56,11 +69,102 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ FrameGe
   const int tile = blockIdx.x - L.blur_tile_base;
   const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
   const int X0 = tx * kFtW, Y0 = ty * kFtH;
-  // owned pixels inside the detection domain [19, w-19) x [19, h-19)
-  if (X0 >= L.w - kEdge || Y0 >= L.h - kEdge || X0 + kFtW <= kEdge || Y0 + kFtH <= kEdge) return;
   const int f = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
   const int lo = min(g.ini_th, g.min_th);
+  const size_t fo = (size_t)f * g.pyr_frame_bytes;
+
+  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r, with
+  // BORDER_REFLECT_101 outside the image (the blur needs it; the detector never looks there).
+  // Thread = (word column c, 6 rows): column class and reflected byte columns once per thread.
+  {
+    const int c = tid % kFtRawW, r0 = (tid / kFtRawW) * 6;
+    const int x = X0 - 4 + 4 * c;
+    const bool interior = x >= 0 && x + 4 <= L.w;
+    const bool needed = x < L.w + 4;           // at most 3 reflected columns are read
+    const uint8_t* src = pyr + fo + px_off(L, 0, 0);
+    int xs[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) xs[k] = reflect1(x + k, L.w);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      const int r = r0 + i, y = Y0 - 4 + r;
+      if (r < kFtRawH) {
+        uint32_t v = 0;
+        if (needed && y < L.h + 4) {
+          const uint8_t* rowp = src + reflect1(y, L.h) * L.pitch;
+          if (interior) v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
+          else v = (uint32_t)rowp[xs[0]] | ((uint32_t)rowp[xs[1]] << 8) | ((uint32_t)rowp[xs[2]] << 16) | ((uint32_t)rowp[xs[3]] << 24);
+        }
+        raw_w[r * kFtRawW + c] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 1b. 7x7 Gaussian blur of the tile's owned pixels (clone() + GaussianBlur, orb_extractor.cc:1054-1055;
+  // Q8.8 kernel [18,34,48,56,48,34,18]): horizontal pass with DP4A on funnel-shifted byte
+  // windows into u16, vertical pass with DP2A on the packed u16 pairs, 32-bit stores.
+  {
+    const int rows_out = min(kFtH, L.h - Y0), cols_out = min(kFtW, L.w - X0);
+    const int q = tid & 31;
+    if (4 * q < cols_out) {  // horizontal: thread = (quad q, 5 of the rows_out + 6 rows); blur row b = raw row b + 1
+      const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
+      const int b0 = (tid >> 5) * 5;
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        const int b = b0 + i;
+        if (b < rows_out + 6) {
+          const uint32_t* w = &raw_w[(b + 1) * kFtRawW + q];
+          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+          // output X0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
+          const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
+          const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
+          const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
+          const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
+          *reinterpret_cast<uint2*>(&tmp[b * kFtW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
+        }
+      }
+    }
+    __syncthreads();
+    const int yy0 = (tid >> 5) * 4;
+    if (4 * q < cols_out && yy0 < rows_out) {  // vertical: thread = (quad q, 4 output rows), 10 rows read once
+      uint32_t acc[4][4];
+#pragma unroll
+      for (int o = 0; o < 4; o++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[o][k] = 32768u;
+      const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+      for (int j = 0; j < 10; j++) {
+        const uint2 v = *reinterpret_cast<const uint2*>(&tmp[min(yy0 + j, kFtH + 5) * kFtW + 4 * q]);
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+          const int tap = j - o;
+          if (tap >= 0 && tap < 7) {
+            acc[o][0] = __dp2a_lo(v.x, kv[tap], acc[o][0]);        // low u16 x k
+            acc[o][1] = __dp2a_lo(v.x, kv[tap] << 8, acc[o][1]);   // high u16 x k
+            acc[o][2] = __dp2a_lo(v.y, kv[tap], acc[o][2]);
+            acc[o][3] = __dp2a_lo(v.y, kv[tap] << 8, acc[o][3]);
+          }
+        }
+      }
+      const int x = X0 + 4 * q;
+      uint8_t* d = blur + fo + px_off(L, x, Y0 + yy0);
+#pragma unroll
+      for (int o = 0; o < 4; o++) {
+        if (yy0 + o < rows_out) {
+          const uint32_t packed = (acc[o][0] >> 16) | ((acc[o][1] >> 16) << 8) | ((acc[o][2] >> 16) << 16) | ((acc[o][3] >> 16) << 24);
+          uint8_t* dp = d + o * L.pitch;
+          if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(dp) = packed;
+          else for (int k = 0; x + k < L.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
+        }
+      }
+    }
+  }
+  // tiles without pixels of the detection domain [19, w-19) x [19, h-19) are done
+  if (X0 >= L.w - kEdge || Y0 >= L.h - kEdge || X0 + kFtW <= kEdge || Y0 + kFtH <= kEdge) return;
+  __syncthreads();  // tmp is dead: its memory becomes the score map and the lists
 
   if (tid == 0) { n_list = 0; n_out = 0; }
   if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
@@ -71,22 +175,6 @@ __global__ void __launch_bounds__(256, 6) k_fast(const __grid_constant__ FrameGe
     yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
   }
   for (int i = tid; i < kFtScH * kFtRawW; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
-  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r; thread = (column, 6 rows)
-  {
-    const int c = tid % kFtRawW, r0 = (tid / kFtRawW) * 6;
-    const int x = X0 - 4 + 4 * c;
-    const bool col_ok = x < L.w + 16;  // the plane has 32 B left / >= 19 B right padding
-    const uint8_t* src = pyr + (size_t)f * g.pyr_frame_bytes + px_off(L, x, Y0 - 4 + r0);
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const int r = r0 + i, y = Y0 - 4 + r;
-      if (r < kFtRawH) {
-        uint32_t v = 0;
-        if (col_ok && y >= 0 && y < L.h) v = __ldg(reinterpret_cast<const uint32_t*>(src + i * L.pitch));
-        raw_w[r * kFtRawW + c] = v;
-      }
-    }
-  }
   __syncthreads();
 
   // ---- 2. rejection test, four pixels per thread, + warp compaction.
@@ -215,7 +303,7 @@ int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStrea
   cudaMemsetAsync(b.n_cand, 0, sizeof(int32_t) * ORBX_MAX_LEVELS * (size_t)frames, st);
   cudaMemsetAsync(b.cell_strong, 0, sizeof(int32_t) * (size_t)g.total_cells * frames, st);
   dim3 grid(g.total_blur_tiles, 1, frames);
-  k_fast<<<grid, 256, 0, st>>>(g, b.pyr, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong);
+  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong);
   return 1;
 }
 

@@ -51,7 +51,7 @@ struct orbx_extractor {
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // free events
   std::vector<cudaEvent_t> ev_used;   // ORBX_N_STAGES + 1 events per chunk, in order
-  double stage_ms[ORBX_N_STAGES] = {0, 0, 0, 0, 0, 0};
+  double stage_ms[ORBX_N_STAGES] = {0, 0, 0, 0, 0};
   long long stage_chunks = 0;
   char err[256] = "";
 };
@@ -287,8 +287,6 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   n += launch_fast(g, s.b, frames, st);
   mark();
   n += launch_octree(g, s.b, frames, st);
-  mark();
-  n += launch_blur(g, s.b, frames, st);
   mark();
   n += launch_describe(g, s.b, frames, d_kps, d_desc, cap, d_n, d_nmono, out_frame0, st);
   mark();

@@ -1,10 +1,9 @@
-// pyramid.cu -- image pyramid (bilinear 8U resize, REFLECT_101 border) and the 7x7 Gaussian blur.
+// pyramid.cu -- image pyramid: level-0 import, bilinear 8U resize chain, REFLECT_101 border.
 //
 // Replaces OrbExtractor::ComputePyramid (orb_extractor.cc:1093-1117: cv::resize INTER_LINEAR +
-// copyMakeBorder) and the clone()+cv::GaussianBlur of orb_extractor.cc:1054-1055.
-// Arithmetic: SURVEY.md A.2 / A.6, bit-exact with OpenCV 4.13's 8-bit fixed-point paths.
-// Both stages are HBM/L2-bound byte streams: one read and one write per pixel, 16-byte aligned
-// interior rows, 32-bit packed stores, no tensor-core work.
+// copyMakeBorder).  Arithmetic: SURVEY.md A.2, bit-exact with OpenCV 4.13's 8-bit fixed-point path.
+// Byte streams with 16-byte aligned interior rows and 32-bit packed stores; no tensor-core work.
+// (The 7x7 Gaussian blur lives in fast.cu: it shares the detector's shared-memory tile.)
 #include "orbx_kernels.cuh"
 #include "orbx_math.cuh"
 
@@ -194,134 +193,6 @@ __global__ void __launch_bounds__(256) k_border(const __grid_constant__ FrameGeo
 int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   dim3 grid(32, g.nlev, frames);
   k_border<<<grid, 256, 0, st>>>(g, b.pyr);
-  return 1;
-}
-
-// ------------------------------------------------------------------ 7x7 Gaussian blur
-// All levels in one launch; CTA = one 128x32 output tile.  Raw tile (38 rows x 136 B, reflect-101
-// at the true image edge) -> horizontal Q8.8 pass with DP4A (two 4-tap dot products per pixel on
-// funnel-shifted byte windows) into u16 -> vertical pass with DP2A on the packed u16 pairs ->
-// packed u32 stores.  Kernel [18,34,48,56,48,34,18].
-// Every phase gives a thread a fixed column and a short run of rows, so that column tests, table
-// look-ups and address arithmetic happen once per thread instead of once per pixel.
-constexpr int kBlurTW = 128, kBlurTH = 32, kBlurRawW = 34;  // raw row: 34 words = bytes x0-4 .. x0+131
-constexpr int kBlurRawH = kBlurTH + 6;
-
-__device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one fold (|overshoot| < len)
-  return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
-}
-
-__global__ void __launch_bounds__(256, 8) k_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
-                                              uint8_t* __restrict__ blur) {
-  __shared__ __align__(16) uint32_t raw[kBlurRawH * kBlurRawW];
-  __shared__ __align__(16) uint16_t tmp[kBlurRawH * kBlurTW];
-  int lev = 0;
-  while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].blur_tile_base) lev++;
-  const LevelGeom& L = g.lv[lev];
-  const int tile = blockIdx.x - L.blur_tile_base;
-  const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
-  const int x0 = tx * kBlurTW, y0 = ty * kBlurTH;
-  const size_t fo = (size_t)blockIdx.z * g.pyr_frame_bytes;
-  const int tid = threadIdx.x;
-  const int rows_out = min(kBlurTH, L.h - y0), rows_needed = rows_out + 6;
-  const int cols_out = min(kBlurTW, L.w - x0);
-
-  // ---- raw tile: thread = (word column c, 6 rows).  Word c holds x = x0-4+4c .. +3 of row
-  // reflect(y0 + r - 3); words that straddle the image edge are assembled byte by byte.
-  {
-    const int c = tid % kBlurRawW, r0 = (tid / kBlurRawW) * 6;
-    const int x = x0 - 4 + 4 * c;
-    const bool needed = 4 * c < cols_out + 8;       // bytes up to column cols_out + 3 + 4
-    const bool interior = x >= 0 && x + 4 <= L.w;
-    const uint8_t* src = pyr + fo + px_off(L, 0, 0);
-    int xs[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) xs[k] = reflect1(x + k, L.w);
-    if (needed) {
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const int r = r0 + i;
-        if (r < rows_needed) {
-          const uint8_t* rowp = src + reflect1(y0 + r - 3, L.h) * L.pitch;
-          uint32_t v;
-          if (interior) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
-          } else {
-            v = (uint32_t)rowp[xs[0]] | ((uint32_t)rowp[xs[1]] << 8) | ((uint32_t)rowp[xs[2]] << 16) | ((uint32_t)rowp[xs[3]] << 24);
-          }
-          raw[r * kBlurRawW + c] = v;
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- horizontal pass: thread = (quad q of output columns, 5 raw rows)
-  {
-    const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
-    const int q = tid & 31, r0 = (tid >> 5) * 5;
-    if (4 * q < cols_out) {
-#pragma unroll
-      for (int i = 0; i < 5; i++) {
-        const int r = r0 + i;
-        if (r < rows_needed) {
-          const uint32_t* w = &raw[r * kBlurRawW + q];
-          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-          // output x0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
-          const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
-          const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
-          const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
-          const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
-          *reinterpret_cast<uint2*>(&tmp[r * kBlurTW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
-        }
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- vertical pass: thread = (quad q, 4 output rows); the 10 rows it needs are read once
-  {
-    const int q = tid & 31, yy0 = (tid >> 5) * 4;
-    const int x = x0 + 4 * q;
-    if (4 * q < cols_out && yy0 < rows_out) {
-      uint32_t acc[4][4];
-#pragma unroll
-      for (int o = 0; o < 4; o++)
-#pragma unroll
-        for (int k = 0; k < 4; k++) acc[o][k] = 32768u;
-      const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
-#pragma unroll
-      for (int j = 0; j < 10; j++) {
-        // rows past the tile's last needed row are never used by a stored output
-        const uint2 v = *reinterpret_cast<const uint2*>(&tmp[min(yy0 + j, kBlurRawH - 1) * kBlurTW + 4 * q]);
-#pragma unroll
-        for (int o = 0; o < 4; o++) {
-          const int tap = j - o;
-          if (tap >= 0 && tap < 7) {
-            acc[o][0] = __dp2a_lo(v.x, kv[tap], acc[o][0]);        // low u16 x k
-            acc[o][1] = __dp2a_lo(v.x, kv[tap] << 8, acc[o][1]);   // high u16 x k
-            acc[o][2] = __dp2a_lo(v.y, kv[tap], acc[o][2]);
-            acc[o][3] = __dp2a_lo(v.y, kv[tap] << 8, acc[o][3]);
-          }
-        }
-      }
-      uint8_t* d = blur + fo + px_off(L, x, y0 + yy0);
-#pragma unroll
-      for (int o = 0; o < 4; o++) {
-        if (yy0 + o < rows_out) {
-          const uint32_t packed = (acc[o][0] >> 16) | ((acc[o][1] >> 16) << 8) | ((acc[o][2] >> 16) << 16) | ((acc[o][3] >> 16) << 24);
-          uint8_t* dp = d + o * L.pitch;
-          if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(dp) = packed;
-          else for (int k = 0; x + k < L.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
-        }
-      }
-    }
-  }
-}
-
-int launch_blur(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
-  dim3 grid(g.total_blur_tiles, 1, frames);
-  k_blur<<<grid, 256, 0, st>>>(g, b.pyr, b.blur);
   return 1;
 }
 

@@ -143,14 +143,14 @@ class OrbExtractor:
     def launch_count(self):
         return self._lib.orbx_launch_count(self._h)
 
-    STAGE_NAMES = ("import", "pyramid", "fast", "octree", "blur", "describe")
+    STAGE_NAMES = ("import", "pyramid", "fast_blur", "octree", "describe")
 
     def set_profiling(self, on=True):
         self._check(self._lib.orbx_set_profiling(self._h, int(on)))
 
     def stage_times(self, reset=True):
         """({stage: accumulated ms}, chunks) measured with CUDA events on the launching stream."""
-        ms = np.zeros(6, np.float64)
+        ms = np.zeros(len(self.STAGE_NAMES), np.float64)
         ch = C.c_longlong()
         self._check(self._lib.orbx_stage_times(self._h, ms.ctypes.data, C.byref(ch), int(reset)))
         return dict(zip(self.STAGE_NAMES, ms.tolist())), ch.value
