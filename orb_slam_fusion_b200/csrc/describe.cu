@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
 constexpr int kDescWarps = 8;
 constexpr int kPatchRows = 37, kPatchWords = 11;  // rotated pattern offsets stay within +-18 px (A.7)
 
-__global__ void __launch_bounds__(32 * kDescWarps, 4) k_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+#ifndef ORBX_DESC_MINB
+#define ORBX_DESC_MINB 8
+#endif
+__global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                                               const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel_xy,
                                                               const uint8_t* __restrict__ sel_sc, const int32_t* __restrict__ n_sel,
                                                               const int32_t* __restrict__ work, orbx_kp* __restrict__ kps,
@@ -125,15 +128,19 @@ __global__ void __launch_bounds__(32 * kDescWarps, 4) k_describe(const __grid_co
   // gathers over 37 rows: straight from global memory each would cost one L1 wavefront per lane).
   const int xb = (cx - 18) & ~3;  // >= 0: keypoints are >= 19 px inside; interior rows are 16-byte aligned
   constexpr int kStage = (kPatchRows * kPatchWords + 31) / 32;
-  uint32_t pv[kStage];
+  uint32_t* pw = patch[wid];
   {
+    // LDGSTS: global -> shared without staging registers; completes while the orientation is computed
     const uint8_t* bsrc = blur + fo + px_off(L, xb, cy - 18);
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(pw);
 #pragma unroll
     for (int t = 0; t < kStage; t++) {
       const int i = lane + 32 * t;
       const int r = i / kPatchWords, c = i - r * kPatchWords;
-      pv[t] = i < kPatchRows * kPatchWords ? __ldg(reinterpret_cast<const uint32_t*>(bsrc + r * L.pitch) + c) : 0u;
+      if (i < kPatchRows * kPatchWords)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sbase + 4u * i), "l"(bsrc + r * L.pitch + 4 * c));
     }
+    asm volatile("cp.async.commit_group;\n" ::);
   }
 
   // ---- IC_Angle (:76-100): lane = column u, loop over rows v
@@ -166,12 +173,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, 4) k_describe(const __grid_co
   double sd, cd;
   sincos((double)rad, &sd, &cd);
   const float a = (float)cd, b = (float)sd;
-  uint32_t* pw = patch[wid];
-#pragma unroll
-  for (int t = 0; t < kStage; t++) {
-    const int i = lane + 32 * t;
-    if (i < kPatchRows * kPatchWords) pw[i] = pv[t];
-  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncwarp();
   const uint8_t* bc = reinterpret_cast<const uint8_t*>(pw) + 18 * (kPatchWords * 4) + (cx - xb);
   uint32_t byte = 0;

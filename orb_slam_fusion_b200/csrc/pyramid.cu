@@ -53,13 +53,18 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 // CTA = 128 output columns x `th` output rows.  The horizontal pass runs ONCE per source row the tile
 // needs (adjacent output rows share source rows) and keeps H>>4 (15 bits) as u16 in shared memory;
 // the vertical pass combines two shared rows per output row.  4 px per thread, 32-bit stores.
-constexpr int kRsTW = 128, kRsMaxTH = 16, kRsRows = 2 * kRsMaxTH + 4;
+#ifndef ORBX_RS_TH
+#define ORBX_RS_TH 16
+#endif
+constexpr int kRsTW = 128, kRsMaxTH = ORBX_RS_TH, kRsRows = 2 * kRsMaxTH + 4;
+constexpr int kRsSrcChunks = 19, kRsSrcPitch = 16 * kRsSrcChunks;  // staged source columns per tile (scale <= ~2.2)
 
 __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                 const int16_t* __restrict__ xofs, const int16_t* __restrict__ xalpha,
                                                 const int16_t* __restrict__ yofs, const int16_t* __restrict__ ybeta,
                                                 int lev, int th) {
   __shared__ __align__(16) uint16_t hq[kRsRows * kRsTW];
+  __shared__ __align__(16) uint8_t src_sm[kRsRows * kRsSrcPitch];  // source rows, columns sx_lo ..
   const LevelGeom& D = g.lv[lev];
   const LevelGeom& S = g.lv[lev - 1];
   const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
@@ -71,14 +76,32 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
   const int n_rows = min(row_hi - row_lo + 1, kRsRows);
   const int src_base = px_off(S, 0, row_lo);
 
-  // ---- horizontal pass: thread = (quad q of output columns, 5 source rows); the column tables are
-  // read once per thread
+  // ---- source rows of the tile -> shared memory with 16-byte LDGSTS (cp.async): one asynchronous,
+  // coalesced round trip instead of dependent single-byte gathers from global memory
+  const int sx_lo = xofs[t + x0] & ~15;                                  // first source column, 16-byte aligned
+  const int sx_hi = xofs[t + min(x0 + kRsTW, D.w) - 1] + 2;             // one past the last byte read
+  const int n_chunks = (sx_hi - sx_lo + 15) >> 4;
+  const bool staged = n_chunks <= kRsSrcChunks;                           // scale factors beyond ~2.2 gather from global
+  if (staged) {
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(src_sm);
+    const uint8_t* gsrc = frame + src_base + sx_lo;
+    for (int i = tid; i < n_rows * n_chunks; i += 256) {
+      const int r = i / n_chunks, c = i - r * n_chunks;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (unsigned)(r * kRsSrcPitch + 16 * c)),
+                   "l"(gsrc + r * S.pitch + 16 * c));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+
+  // ---- horizontal pass: thread = (quad q of output columns, up to 5 source rows); the column tables
+  // are read once per thread (while the LDGSTS copies are in flight)
   {
     const int rpg = (n_rows + 7) >> 3;  // source rows per warp: the 8 warps share the rows evenly
     const int q = tid & 31, r0 = (tid >> 5) * rpg;
     const int dx0 = x0 + 4 * q;
-    if (dx0 < D.w && r0 < n_rows) {
-      int sxs[4] = {0, 0, 0, 0}, a0s[4] = {0, 0, 0, 0}, a1s[4] = {0, 0, 0, 0};
+    const bool active = dx0 < D.w && r0 < n_rows;
+    int sxs[4] = {0, 0, 0, 0}, a0s[4] = {0, 0, 0, 0}, a1s[4] = {0, 0, 0, 0};
+    if (active) {
       if (dx0 + 4 <= D.w) {
         // tables are 8-byte (xofs) / 16-byte (xalpha) aligned at multiples of 4 columns: tab_off % 8 == 0
         const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
@@ -97,8 +120,15 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
           }
         }
       }
+    }
+    if (staged) {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+      __syncthreads();
+    }
+    if (active) {
       // a1 == 0 where sx is the last column, so sx+1 may read the (allocated) padding
-      const uint8_t* sp = frame + src_base + r0 * S.pitch;
+      const uint8_t* sp = staged ? src_sm + r0 * kRsSrcPitch - sx_lo : frame + src_base + r0 * S.pitch;
+      const int sp_pitch = staged ? kRsSrcPitch : S.pitch;
 #pragma unroll
       for (int i = 0; i < 5; i++) {
         if (i < rpg && r0 + i < n_rows) {
@@ -106,7 +136,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
 #pragma unroll
           for (int k = 0; k < 4; k++) o[k] = (uint32_t)((sp[sxs[k]] * a0s[k] + sp[sxs[k] + 1] * a1s[k]) >> 4);
           *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-          sp += S.pitch;
+          sp += sp_pitch;
         }
       }
     }
