@@ -47,6 +47,13 @@ struct orbx_extractor {
   int last_frames = 0;       // frames of the last chunk processed on slot 0
   bool border_done = false;  // REFLECT_101 frames of slot 0's pyramid are up to date
   long long launches = 0;
+  // single-frame path: the kernel sequence + result copies captured once as a CUDA graph
+  cudaGraphExec_t graph = nullptr;
+  int graph_lap0 = 0, graph_lap1 = 0;
+  size_t graph_rs = 0, graph_fs = 0;
+  const void* graph_img = nullptr;   // staging buffer the graph reads
+  int graph_launches = 0;            // kernels one replay launches
+  uint8_t* h_out = nullptr;          // pinned: out_cap keypoint records, then out_cap descriptor rows
   // optional per-stage timing (orbx_set_profiling): one event set per enqueued chunk
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // free events
@@ -139,6 +146,10 @@ void free_slot(Slot& s) {
 }
 
 void free_geometry(orbx_t* h) {
+  if (h->graph) cudaGraphExecDestroy(h->graph);
+  h->graph = nullptr;
+  if (h->h_out) cudaFreeHost(h->h_out);
+  h->h_out = nullptr;
   for (auto& s : h->slot) free_slot(s);
   if (h->d_tables) cudaFree(h->d_tables);
   h->d_tables = nullptr;
@@ -493,10 +504,44 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   size_t drs, dfs;
   rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
   if (rc) return rc;
-  enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
   h->last_frames = 1;
-  CU(h, cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-  CU(h, cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+  const size_t kp_bytes = (size_t)h->out_cap * sizeof(orbx_kp), desc_bytes = (size_t)h->out_cap * 32;
+  if (!h->h_out) CU(h, cudaMallocHost((void**)&h->h_out, kp_bytes + desc_bytes));
+  if (h->profiling) {
+    // stage events cannot be timed inside a graph: plain launches
+    enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
+    CU(h, cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(h->h_out, s.d_kps, kp_bytes, cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaMemcpyAsync(h->h_out + kp_bytes, s.d_desc, desc_bytes, cudaMemcpyDeviceToHost, s.stream));
+  } else {
+    // 12 kernels + 2 memsets + 4 result copies replayed as one graph launch (single-frame latency is
+    // launch- and dependency-bound, SURVEY.md section 7 "hard parts")
+    if (h->graph && (h->graph_lap0 != lap0 || h->graph_lap1 != lap1 || h->graph_rs != drs || h->graph_fs != dfs ||
+                     h->graph_img != s.d_img)) {
+      cudaGraphExecDestroy(h->graph);
+      h->graph = nullptr;
+    }
+    if (!h->graph) {
+      cudaGraph_t graph = nullptr;
+      CU(h, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+      const long long launches_before = h->launches;
+      enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
+      cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream);
+      cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream);
+      cudaMemcpyAsync(h->h_out, s.d_kps, kp_bytes, cudaMemcpyDeviceToHost, s.stream);
+      cudaMemcpyAsync(h->h_out + kp_bytes, s.d_desc, desc_bytes, cudaMemcpyDeviceToHost, s.stream);
+      h->graph_launches = (int)(h->launches - launches_before);
+      h->launches = launches_before;
+      CU(h, cudaStreamEndCapture(s.stream, &graph));
+      const cudaError_t ie = cudaGraphInstantiate(&h->graph, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) { h->graph = nullptr; return fail(h, ORBX_E_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ie)); }
+      h->graph_lap0 = lap0; h->graph_lap1 = lap1; h->graph_rs = drs; h->graph_fs = dfs; h->graph_img = s.d_img;
+    }
+    CU(h, cudaGraphLaunch(h->graph, s.stream));
+    h->launches += h->graph_launches;
+  }
   CU(h, cudaStreamSynchronize(s.stream));
   const int N = s.h_n[0];
   if (N < 0) return fail(h, ORBX_E_UNSUPPORTED, "quadtree node table overflow");
@@ -504,9 +549,8 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   if (N > cap) return fail(h, ORBX_E_CAP, "%d keypoints, capacity %d", N, cap);
   if (N > 0) {
     if (!kps || !desc) return fail(h, ORBX_E_ARG, "null output");
-    CU(h, cudaMemcpyAsync(kps, s.d_kps, (size_t)N * sizeof(orbx_kp), cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaMemcpyAsync(desc, s.d_desc, (size_t)N * 32, cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaStreamSynchronize(s.stream));
+    memcpy(kps, h->h_out, (size_t)N * sizeof(orbx_kp));
+    memcpy(desc, h->h_out + kp_bytes, (size_t)N * 32);
   }
   *n_mono = s.h_n[1];
   return ORBX_OK;
