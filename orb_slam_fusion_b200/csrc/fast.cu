@@ -50,7 +50,7 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
 __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
-                                              int32_t* __restrict__ cell_strong) {
+                                              int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
   __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawW];
   // The blur's u16 intermediate and the detector's score map / lists are live in different phases
   // and share one buffer.
@@ -66,44 +66,56 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   __shared__ uint8_t xedge[kFtPitch], yedge[kFtScH];  // bit 0: first column / row of a cell, bit 1: last
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
-  int lev = 0;
-  while (lev + 1 < g.nlev && (int)blockIdx.x >= g.lv[lev + 1].blur_tile_base) lev++;
+  // tile -> (level, tile column, tile row), precomputed on the host
+  const uint32_t tinfo = __ldg(tile_tab + blockIdx.x);
+  const int lev = (int)(tinfo >> 24), tx = (int)(tinfo & 0xFFFu), ty = (int)((tinfo >> 12) & 0xFFFu);
   const LevelGeom& L = g.lv[lev];
-  const int tile = blockIdx.x - L.blur_tile_base;
-  const int ty = tile / L.blur_tiles_x, tx = tile - ty * L.blur_tiles_x;
   const int X0 = tx * kFtW, Y0 = ty * kFtH;
   const int f = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
   const int lo = min(g.ini_th, g.min_th);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
 
-  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r, with
-  // BORDER_REFLECT_101 outside the image (the blur needs it; the detector never looks there).
-  // Thread = (word column c, 6 rows): column class and reflected byte columns once per thread.
+  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r.  Plain aligned
+  // word loads (thread = word column c, 6 rows); the BORDER_REFLECT_101 halo the blur needs at the
+  // image edges (3 px) is patched in afterwards from the tile itself, only in edge tiles.
   {
     const int c = tid % kFtRawW, r0 = (tid / kFtRawW) * 6;
     const int x = X0 - 4 + 4 * c;
-    const bool interior = x >= 0 && x + 4 <= L.w;
-    const bool needed = x < L.w + 4;           // at most 3 reflected columns are read
-    const uint8_t* src = pyr + fo + px_off(L, 0, 0);
-    int xs[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) xs[k] = reflect1(x + k, L.w);
+    const bool col_ok = x < L.w + 16;  // the plane has 32 B left / >= 19 B right padding
+    const uint8_t* src = pyr + fo + px_off(L, x, Y0 - 4 + r0);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
       const int r = r0 + i, y = Y0 - 4 + r;
       if (r < kFtRawH) {
         uint32_t v = 0;
-        if (needed && y < L.h + 4) {
-          const uint8_t* rowp = src + reflect1(y, L.h) * L.pitch;
-          if (interior) v = __ldg(reinterpret_cast<const uint32_t*>(rowp + x));
-          else v = (uint32_t)rowp[xs[0]] | ((uint32_t)rowp[xs[1]] << 8) | ((uint32_t)rowp[xs[2]] << 16) | ((uint32_t)rowp[xs[3]] << 24);
-        }
+        if (col_ok && y >= 0 && y < L.h) v = __ldg(reinterpret_cast<const uint32_t*>(src + i * L.pitch));
         raw_w[r * kFtRawW + c] = v;
       }
     }
   }
   __syncthreads();
+  {
+    uint8_t* rawb = reinterpret_cast<uint8_t*>(raw_w);
+    const bool left = X0 == 0, right = X0 + kFtW + 3 > L.w, top = Y0 == 0, bottom = Y0 + kFtH + 3 > L.h;
+    if (left || right) {  // columns: x = -k <- k and x = w-1+k <- w-1-k (k = 1..3), rows inside the image
+      const int r = tid >> 2, k = (tid & 3) + 1, y = Y0 - 4 + r;
+      if (r < kFtRawH && k <= 3 && y >= 0 && y < L.h) {
+        if (left) rawb[r * kFtPitch + 4 - k] = rawb[r * kFtPitch + 4 + k];
+        if (right && L.w - 1 + k <= X0 + kFtW + 2) rawb[r * kFtPitch + (L.w - 1 + k - X0 + 4)] = rawb[r * kFtPitch + (L.w - 1 - k - X0 + 4)];
+      }
+    }
+    if (top || bottom) {
+      if (left || right) __syncthreads();  // rows copy the patched columns
+      // rows: y = -k <- k and y = h-1+k <- h-1-k (k = 1..3), all 34 words
+      for (int i = tid; i < 3 * kFtRawW; i += 256) {
+        const int k = i / kFtRawW + 1, c = i - (k - 1) * kFtRawW;
+        if (top) raw_w[(4 - k) * kFtRawW + c] = raw_w[(4 + k) * kFtRawW + c];
+        if (bottom && L.h - 1 + k <= Y0 + kFtH + 2) raw_w[(L.h - 1 + k - Y0 + 4) * kFtRawW + c] = raw_w[(L.h - 1 - k - Y0 + 4) * kFtRawW + c];
+      }
+    }
+    if (left || right || top || bottom) __syncthreads();
+  }
 
   // ---- 1b. 7x7 Gaussian blur of the tile's owned pixels (clone() + GaussianBlur, orb_extractor.cc:1054-1055;
   // Q8.8 kernel [18,34,48,56,48,34,18]): horizontal pass with DP4A on funnel-shifted byte
@@ -306,7 +318,7 @@ int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStrea
   cudaMemsetAsync(b.n_cand, 0, sizeof(int32_t) * ORBX_MAX_LEVELS * (size_t)frames, st);
   cudaMemsetAsync(b.cell_strong, 0, sizeof(int32_t) * (size_t)g.total_cells * frames, st);
   dim3 grid(g.total_blur_tiles, 1, frames);
-  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong);
+  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
   return 1;
 }
 

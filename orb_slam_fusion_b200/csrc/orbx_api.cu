@@ -44,6 +44,7 @@ struct orbx_extractor {
   int out_cap = 0;
   Slot slot[kSlots];
   void* d_tables = nullptr;
+  uint32_t* d_tile_tab = nullptr;
   int last_frames = 0;       // frames of the last chunk processed on slot 0
   bool border_done = false;  // REFLECT_101 frames of slot 0's pyramid are up to date
   long long launches = 0;
@@ -153,6 +154,8 @@ void free_geometry(orbx_t* h) {
   for (auto& s : h->slot) free_slot(s);
   if (h->d_tables) cudaFree(h->d_tables);
   h->d_tables = nullptr;
+  if (h->d_tile_tab) cudaFree(h->d_tile_tab);
+  h->d_tile_tab = nullptr;
   h->geom_valid = false;
 }
 
@@ -237,6 +240,17 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   CU(h, cudaMalloc(&h->d_tables, t.size() * sizeof(int16_t)));
   CU(h, cudaMemcpy(h->d_tables, t.data(), t.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
   const int16_t* dt = (const int16_t*)h->d_tables;
+  {
+    std::vector<uint32_t> tt((size_t)tiles);
+    for (int l = 0; l < g.nlev; l++) {
+      const LevelGeom& L = g.lv[l];
+      const int n = (l + 1 < g.nlev ? g.lv[l + 1].blur_tile_base : tiles) - L.blur_tile_base;
+      for (int i = 0; i < n; i++)
+        tt[L.blur_tile_base + i] = ((uint32_t)l << 24) | ((uint32_t)(i / L.blur_tiles_x) << 12) | (uint32_t)(i % L.blur_tiles_x);
+    }
+    CU(h, cudaMalloc((void**)&h->d_tile_tab, tt.size() * sizeof(uint32_t)));
+    CU(h, cudaMemcpy(h->d_tile_tab, tt.data(), tt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
 
   h->img_pitch = ((size_t)w + 15) / 16 * 16;
   h->out_cap = sel;
@@ -259,6 +273,7 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     s.b.xalpha = dt + tab;
     s.b.yofs = dt + 3 * (size_t)tab;
     s.b.ybeta = dt + 5 * (size_t)tab;
+    s.b.tile_tab = h->d_tile_tab;
     CU(h, dmalloc(s, &s.d_kps, B * sel));
     CU(h, dmalloc(s, &s.d_desc, B * sel * 32));
     CU(h, dmalloc(s, &s.d_n, 2 * B));

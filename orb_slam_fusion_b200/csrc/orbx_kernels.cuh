@@ -28,6 +28,7 @@ struct BatchBuffers {
   const int16_t* xalpha; // 2 coefficients per destination column
   const int16_t* yofs;   // source row of destination row (already clamped pair in yofs2)
   const int16_t* ybeta;  // 2 coefficients per destination row
+  const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
 };
 
 // Each launcher enqueues on `st` and returns the number of kernels it launched.

@@ -122,7 +122,11 @@ def test_error_behaviour(P, oracle):
 
 
 @pytest.mark.parametrize("kind,w,h,nf", [("uniform", 640, 480, 1500), ("blocks", 1241, 376, 2000), ("blocks", 511, 389, 600),
-                                         ("blocks", 1920, 1080, 5000)])
+                                         ("blocks", 1920, 1080, 5000),
+                                         # widths / heights 1, 2 and 3 past a multiple of the 128x32 tile: the
+                                         # reflect-101 halo of the blur straddles two tiles
+                                         ("blocks", 770, 514, 900), ("uniform", 769, 513, 900), ("blocks", 643, 483, 700),
+                                         ("blocks", 512, 384, 700)])
 def test_more_geometries_vs_oracle(P, oracle, kind, w, h, nf):
     img = (oracle.uniform_v1 if kind == "uniform" else oracle.blocks_v1)(w, h, 9, 1)
     ex = P.OrbExtractor(nf, 1.2, 8, 20, 7)
