@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   int lev = 0;
   while (lev + 1 < g.nlev && s >= g.lv[lev + 1].sel_off) lev++;
   const LevelGeom& L = g.lv[lev];
+  const int pitch = L.pitch;  // level fields live in the parameter bank behind a run-time index: read once
   const int idx = s - L.sel_off;
   if (idx >= n_sel[f * ORBX_MAX_LEVELS + lev]) return;
   const size_t so = (size_t)f * g.sel_frame_cap + s;
@@ -132,13 +133,14 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   {
     // LDGSTS: global -> shared without staging registers; completes while the orientation is computed
     const uint8_t* bsrc = blur + fo + px_off(L, xb, cy - 18);
+    const int spitch = pitch;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(pw);
 #pragma unroll
     for (int t = 0; t < kStage; t++) {
       const int i = lane + 32 * t;
       const int r = i / kPatchWords, c = i - r * kPatchWords;
       if (i < kPatchRows * kPatchWords)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sbase + 4u * i), "l"(bsrc + r * L.pitch + 4 * c));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sbase + 4u * i), "l"(bsrc + r * spitch + 4 * c));
     }
     asm volatile("cp.async.commit_group;\n" ::);
   }
@@ -148,15 +150,18 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   const int au = u < 0 ? -u : u;
   int m10 = 0, m01 = 0;
   if (lane < kPatch) {
-    const uint8_t* c = pyr + fo + px_off(L, cx + u, cy);
+    // walk down the column with one pointer increment per row; rows with umax[|v|] < |u| are skipped
+    const uint8_t* p = pyr + fo + px_off(L, cx + u, cy - kHalfPatch);
 #pragma unroll
     for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
       const int av = v < 0 ? -v : v;
-      if (au <= c_umax[av]) {
-        const int val = __ldg(c + v * L.pitch);
+      const int um = av <= 3 ? 15 : (av <= 6 ? 14 : (av <= 8 ? 13 : (av == 9 ? 12 : (av == 10 ? 11 : (av == 11 ? 10 : (av == 12 ? 9 : (av == 13 ? 8 : (av == 14 ? 6 : 3))))))));
+      if (au <= um) {
+        const int val = __ldg(p);
         m10 += u * val;
         m01 += v * val;
       }
+      p += pitch;
     }
   }
 #pragma unroll

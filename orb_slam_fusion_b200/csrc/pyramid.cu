@@ -54,12 +54,15 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 // needs (adjacent output rows share source rows) and keeps H>>4 (15 bits) as u16 in shared memory;
 // the vertical pass combines two shared rows per output row.  4 px per thread, 32-bit stores.
 #ifndef ORBX_RS_TH
-#define ORBX_RS_TH 16
+#define ORBX_RS_TH 32
 #endif
 constexpr int kRsTW = 128, kRsMaxTH = ORBX_RS_TH, kRsRows = 2 * kRsMaxTH + 4;
 constexpr int kRsSrcChunks = 19, kRsSrcPitch = 16 * kRsSrcChunks;  // staged source columns per tile (scale <= ~2.2)
 
-__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
+#ifndef ORBX_RS_MINB
+#define ORBX_RS_MINB 1
+#endif
+__global__ void __launch_bounds__(256, ORBX_RS_MINB) k_resize(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                 const int16_t* __restrict__ xofs, const int16_t* __restrict__ xalpha,
                                                 const int16_t* __restrict__ yofs, const int16_t* __restrict__ ybeta,
                                                 int lev, int th) {
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
       const uint8_t* sp = staged ? src_sm + r0 * kRsSrcPitch - sx_lo : frame + src_base + r0 * S.pitch;
       const int sp_pitch = staged ? kRsSrcPitch : S.pitch;
 #pragma unroll
-      for (int i = 0; i < 5; i++) {
+      for (int i = 0; i < (kRsRows + 7) / 8; i++) {
         if (i < rpg && r0 + i < n_rows) {
           uint32_t o[4];
 #pragma unroll
@@ -143,14 +146,15 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ FrameGeo
   }
   __syncthreads();
 
-  // ---- vertical pass: thread = (quad q, 2 output rows)
+  // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows)
   {
-    const int q = tid & 31, yy0 = (tid >> 5) * 2;
+    constexpr int kVRows = kRsMaxTH / 8;
+    const int q = tid & 31, yy0 = (tid >> 5) * kVRows;
     const int dx0 = x0 + 4 * q;
     if (dx0 < D.w) {
       uint8_t* d = frame + px_off(D, dx0, y0 + yy0);
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
+      for (int i = 0; i < kVRows; i++) {
         const int dy = y0 + yy0 + i;
         if (dy < y1) {
           const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));   // (row0 | row1 << 16)
