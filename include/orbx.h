@@ -35,6 +35,7 @@ extern "C" {
 
 #define ORBX_MEM_HOST 0
 #define ORBX_MEM_DEVICE 1
+#define ORBX_MEM_HOST_ASYNC 2 /* pinned host memory; the call only enqueues, outputs are valid after orbx_sync */
 
 #define ORBX_MAX_LEVELS 16
 #define ORBX_EDGE 19 /* kEdgeThreshold: border kept around every pyramid level (orb_extractor.cc:74) */
@@ -100,7 +101,9 @@ int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int*
 
 /* Batched operator(): n_frames images of equal size, frame f at imgs + f*frame_stride.
  * `mem` says where ALL pointers of this call live (ORBX_MEM_HOST: pageable or pinned host
- * memory, the call blocks until the outputs are written; ORBX_MEM_DEVICE: device memory on
+ * memory, the call blocks until the outputs are written; ORBX_MEM_HOST_ASYNC: pinned host memory,
+ * the call returns once everything is enqueued so consecutive calls pipeline their copies and
+ * kernels, outputs are valid after orbx_sync; ORBX_MEM_DEVICE: device memory on
  * the handle's GPU, the call only enqueues work on `stream` (NULL = the handle's stream) and
  * returns; use orbx_sync).  Outputs: kps[f*cap + i], desc[(f*cap + i)*32], n[f], n_mono[f].
  * Frames with more than cap keypoints report n[f] = -(needed) and write nothing for f.

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ORBX_LIB") or os.path.join(_HERE, "liborbx_b200.so")  # ORBX_LIB: A/B builds
 
 OK, E_EMPTY, E_ARG, E_CAP, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
-MEM_HOST, MEM_DEVICE = 0, 1
+MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 STAGE_LEVEL, STAGE_BLUR, STAGE_CAND, STAGE_SELECTED = 0, 1, 2, 3
 MAX_LEVELS = 16
 EDGE = 19

@@ -17,7 +17,10 @@ using namespace orbx;
 
 namespace {
 
-constexpr int kSlots = 2;  // ping-pong working sets so host-memory batches overlap copies and kernels
+#ifndef ORBX_SLOTS
+#define ORBX_SLOTS 2
+#endif
+constexpr int kSlots = ORBX_SLOTS;  // ping-pong working sets so host-memory batches overlap copies and kernels
 
 struct Slot {
   BatchBuffers b{};
@@ -459,7 +462,7 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
   int rc = check_image(h, imgs, w, hh, row_stride);
   if (rc) return rc;
   if (!kps || !desc || !n || !n_mono || cap < 1) return fail(h, ORBX_E_ARG, "null output");
-  if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) return fail(h, ORBX_E_ARG, "bad mem kind");
+  if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE && mem != ORBX_MEM_HOST_ASYNC) return fail(h, ORBX_E_ARG, "bad mem kind");
   CU(h, cudaSetDevice(h->device));
   rc = ensure_geometry(h, w, hh);
   if (rc) return rc;
@@ -499,7 +502,8 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     CU(h, cudaMemcpyAsync(n_mono + f0, s.d_n + B, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     if (chunk % kSlots == 0) h->last_frames = nf;
   }
-  for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
+  if (mem == ORBX_MEM_HOST)
+    for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
   CU(h, cudaGetLastError());
   return ORBX_OK;
 }

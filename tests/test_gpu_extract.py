@@ -163,6 +163,23 @@ def test_batch_host_and_device(P, oracle):
         for (a_n, a_nm, a_k, a_d) in [(n, nm, kps, desc), (dn.cpu().numpy(), dnm.cpu().numpy(), dkps, ddesc.cpu().numpy())]:
             assert a_n[f] == len(rk) and a_nm[f] == rn
             assert a_k[f, :len(rk)].tobytes() == rk.tobytes() and np.array_equal(a_d[f, :len(rk)], rd)
+    # asynchronous host-memory mode on pinned buffers: two pipelined calls, one sync
+    from orb_slam_fusion_b200 import _abi as A
+    cap = kps.shape[1]
+    pin = torch.from_numpy(imgs).pin_memory()
+    outs = []
+    for _ in range(2):
+        o = (torch.empty((F, cap, 7), dtype=torch.float32).pin_memory(), torch.empty((F, cap, 32), dtype=torch.uint8).pin_memory(),
+             torch.empty(F, dtype=torch.int32).pin_memory(), torch.empty(F, dtype=torch.int32).pin_memory())
+        ex.extract_batch_into(pin.data_ptr(), F, w, h, w, w * h, A.MEM_HOST_ASYNC, (0, 0), o[0].data_ptr(), o[1].data_ptr(),
+                              cap, o[2].data_ptr(), o[3].data_ptr(), None)
+        outs.append(o)
+    ex.sync()
+    for o in outs:
+        assert np.array_equal(o[2].numpy(), n) and np.array_equal(o[3].numpy(), nm)
+        for f in range(F):
+            assert o[0].numpy().view(P.KP_DTYPE).reshape(F, -1)[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes()
+            assert np.array_equal(o[1].numpy()[f, :n[f]], desc[f, :n[f]])
     # a capacity that is too small is reported per frame and nothing is written for that frame
     n2, _, _, _ = ex.extract_batch(imgs[:2], cap=500)
     assert (n2 == -np.array([len(want[0][1]), len(want[1][1])])).all()
