@@ -16,21 +16,30 @@
 namespace orbx {
 
 #ifndef ORBM_CSA
-#define ORBM_CSA 1
+#define ORBM_CSA 2  // carry-save steps: 0 = 8 popc, 1 = 7 popc + 2 lop3, 2 = 6 popc + 4 lop3, 3 = 5 popc + 6 lop3
+// measured on B200, 1000 x 10M search: 18.7 / 16.5 / 15.0 / 15.7 ms for 0 / 1 / 2 / 3 steps: POPC issues on the XU pipe,
+// LOP3 / IADD3 / VIMNMX on the ALU pipe; two steps balance them (ncu: ALU 92 %, XU 70 % active at 3 steps)
 #endif
 
 // popcount of the xor of two 256-bit rows held as 8 words.
-// ORBM_CSA: two carry-save adder steps move work from the quarter-rate POPC pipe to LOP3:
-// 8 popc -> 5 popc + 6 lop3 (sum = a^b^c, carry = maj(a,b,c) are one LOP3 each).
+// ORBM_CSA: carry-save adder steps move work from the quarter-rate POPC (XU) pipe to LOP3 (ALU pipe):
+// each step replaces 3 popc by 2 popc + 2 lop3 (sum = a^b^c, carry = maj(a,b,c) are one LOP3 each).
 __device__ __forceinline__ int ham256(const uint32_t (&a)[8], const uint32_t (&b)[8]) {
   uint32_t x[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) x[i] = a[i] ^ b[i];
-#if ORBM_CSA
+#if ORBM_CSA == 3
   const uint32_t s0 = x[0] ^ x[1] ^ x[2], c0 = (x[0] & x[1]) | (x[2] & (x[0] | x[1]));
   const uint32_t s1 = x[3] ^ x[4] ^ x[5], c1 = (x[3] & x[4]) | (x[5] & (x[3] | x[4]));
   const uint32_t s2 = s0 ^ s1 ^ x[6], c2 = (s0 & s1) | (x[6] & (s0 | s1));
   return __popc(s2) + __popc(x[7]) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+#elif ORBM_CSA == 2
+  const uint32_t s0 = x[0] ^ x[1] ^ x[2], c0 = (x[0] & x[1]) | (x[2] & (x[0] | x[1]));
+  const uint32_t s1 = x[3] ^ x[4] ^ x[5], c1 = (x[3] & x[4]) | (x[5] & (x[3] | x[4]));
+  return __popc(s0) + __popc(s1) + __popc(x[6]) + __popc(x[7]) + 2 * (__popc(c0) + __popc(c1));
+#elif ORBM_CSA == 1
+  const uint32_t s0 = x[0] ^ x[1] ^ x[2], c0 = (x[0] & x[1]) | (x[2] & (x[0] | x[1]));
+  return __popc(s0) + __popc(x[3]) + __popc(x[4]) + __popc(x[5]) + __popc(x[6]) + __popc(x[7]) + 2 * __popc(c0);
 #else
   int d = 0;
 #pragma unroll
