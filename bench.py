@@ -326,8 +326,15 @@ def run_ours(args):
     dom_bytes = alg_stage[dom] * B
     achieved = dom_bytes / (per_launch_ms[dom] * 1e-3) / 1e9
     total_alg = sum(alg.values())
+    traffic = None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture, scaled per launch
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        if tr:
+            traffic = tr["bytes_per_launch"] * B / tr["frames_per_launch"]
+    except OSError:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": alg_stage[dom], "frames_per_launch": B,
                 "launch_ms": per_launch_ms[dom],
                 "pipeline": {"algorithmic_bytes_per_frame": total_alg,
