@@ -195,6 +195,17 @@ int orbm_stereo_rowband(orbm_t* m, const orbx_kp* kl, const uint8_t* dl, int nl,
                         float min_d, float max_d, int32_t* best_idx, int32_t* best_dist, int mem,
                         void* stream);
 
+/* The rest of Frame::ComputeStereoMatches (frame.cc:903-985): for every left
+ * keypoint with best_dist < th_orb_dist ((TH_HIGH + TH_LOW) / 2 = 75 at frame.cc:832), the 11x11 SAD
+ * search over 11 shifts on the keypoint's pyramid level of the two extractors' LAST frames (the
+ * reference reads orb_extractor_left_/right_->img_pyramid_, frame.cc:913-931), parabola sub-pixel
+ * fit, disparity gate [min_d, max_d), and the median-distance outlier cut.  Outputs per left
+ * keypoint: u_right (mvuRight), depth (mvDepth = bf / disparity), both -1 without a match, and the
+ * SAD distance of accepted matches (-1 otherwise).  Both extractors must live on the matcher's device. */
+int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const orbx_kp* kl, int nl, const orbx_kp* kr,
+                       int nr, const int32_t* best_idx, const int32_t* best_dist, int th_orb_dist, float min_d, float max_d,
+                       float bf, float* u_right, float* depth, int32_t* sad, int mem, void* stream);
+
 /* Frame grid geometry (frame.cc:199-204: mnMinX, mnMinY, mfGridElementWidthInv/HeightInv;
  * frame.h:40-41: FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48). */
 typedef struct {

@@ -71,6 +71,7 @@ def lib():
         L.orc_knn2.argtypes = [vp, i, vp, i64, vp, vp, i]
         L.orc_ratio_accept.argtypes = [i, i, i, C.c_double]
         L.orc_stereo_rowband.argtypes = [vp, vp, i, vp, vp, i, vp, i, f, f, vp, vp]
+        L.orc_stereo_refine.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i, f, f, f, vp, vp, vp]
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_splitmix64.restype = u64
         L.orc_splitmix64.argtypes = [u64]
@@ -281,6 +282,40 @@ def stereo_rowband(kl, dl, kr, dr, scale_factors, n_rows, min_d, max_d):
     lib().orc_stereo_rowband(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), int(n_rows),
                              float(min_d), float(max_d), _p(bi), _p(bd))
     return bi, bd
+
+
+class LevelView(C.Structure):
+    _fields_ = [("px", C.c_void_p), ("w", C.c_int), ("h", C.c_int), ("stride", C.c_size_t)]
+
+
+def stereo_refine(levels_left, levels_right, kl, kr, best_idx, best_dist, scale_factors, inv_scale_factors,
+                  th_orb_dist, min_d, max_d, bf):
+    """levels_*: lists of level images WITH their 19-px border (Extractor.level(l, with_border=True)).
+    Returns (u_right, depth, sad)."""
+    nlev = len(levels_left)
+    keep = []
+
+    def views(levels):
+        arr = (LevelView * nlev)()
+        for l, im in enumerate(levels):
+            im = np.ascontiguousarray(im, np.uint8)
+            keep.append(im)
+            arr[l] = LevelView(im.ctypes.data + 19 * im.strides[0] + 19, im.shape[1] - 38, im.shape[0] - 38, im.strides[0])
+        return arr
+
+    vl, vr = views(levels_left), views(levels_right)
+    kl = np.ascontiguousarray(kl, KP_DTYPE)
+    kr = np.ascontiguousarray(kr, KP_DTYPE)
+    bi = np.ascontiguousarray(best_idx, np.int32)
+    bd = np.ascontiguousarray(best_dist, np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    isf = np.ascontiguousarray(inv_scale_factors, np.float32)
+    ur = np.empty(len(kl), np.float32)
+    dp = np.empty(len(kl), np.float32)
+    sad = np.empty(len(kl), np.int32)
+    lib().orc_stereo_refine(C.cast(vl, C.c_void_p), C.cast(vr, C.c_void_p), nlev, _p(kl), len(kl), _p(kr), _p(bi), _p(bd),
+                            _p(sf), _p(isf), int(th_orb_dist), float(min_d), float(max_d), float(bf), _p(ur), _p(dp), _p(sad))
+    return ur, dp, sad
 
 
 def window_search(kps, desc, geom, queries, qdesc, skip=None):

@@ -622,6 +622,76 @@ void orc_stereo_rowband(const orc_kp* kl, const uint8_t* dl, int nl, const orc_k
   free(rows); free(cnt);
 }
 
+/* ---- frame.cc:903-985 ---- */
+typedef struct { int dist; int il; } sad_rec;
+static int sad_rec_cmp(const void* a, const void* b) { /* std::sort of pair<int,int> */
+  const sad_rec* x = (const sad_rec*)a; const sad_rec* y = (const sad_rec*)b;
+  if (x->dist != y->dist) return x->dist < y->dist ? -1 : 1;
+  return x->il < y->il ? -1 : (x->il > y->il ? 1 : 0);
+}
+
+void orc_stereo_refine(const orc_level_view* left, const orc_level_view* right, int n_levels,
+                       const orc_kp* kl, int nl, const orc_kp* kr, const int* best_idx,
+                       const int* best_dist, const float* sf, const float* isf, int th_orb_dist,
+                       float min_d, float max_d, float bf, float* u_right, float* depth, int* sad) {
+  sad_rec* recs = (sad_rec*)malloc(sizeof(sad_rec) * (size_t)(nl ? nl : 1));
+  int nrec = 0;
+  for (int il = 0; il < nl; il++) {
+    u_right[il] = -1.0f; depth[il] = -1.0f; sad[il] = -1;
+    if (best_idx[il] < 0 || !(best_dist[il] < th_orb_dist)) continue; /* :903 */
+    const orc_kp* kpl = &kl[il];
+    const int oct = kpl->octave;
+    if (oct < 0 || oct >= n_levels) continue;
+    const float ur0 = kr[best_idx[il]].x;
+    const float scale = isf[oct];
+    const float sul = roundf(kpl->x * scale), svl = roundf(kpl->y * scale), sur0 = roundf(ur0 * scale); /* :907-909 */
+    const int w = 5, L = 5;
+    const orc_level_view* pl = &left[oct];
+    const orc_level_view* pr = &right[oct];
+    const float iniu = sur0 + L - w, endu = sur0 + L + w + 1; /* :923-927 */
+    if (iniu < 0 || endu >= (float)pr->w) continue;
+    int best = INT_MAX, best_inc = 0;
+    float dists[11];
+    const int y0 = (int)(svl - w), xl0 = (int)(sul - w);
+    for (int inc = -L; inc <= L; inc++) { /* :929-942 */
+      const int xr0 = (int)(sur0 + inc - w);
+      int acc = 0;
+      for (int dy = 0; dy < 2 * w + 1; dy++)
+        for (int dx = 0; dx < 2 * w + 1; dx++) {
+          const int a = pl->px[(ptrdiff_t)(y0 + dy) * (ptrdiff_t)pl->stride + xl0 + dx];
+          const int b = pr->px[(ptrdiff_t)(y0 + dy) * (ptrdiff_t)pr->stride + xr0 + dx];
+          acc += a > b ? a - b : b - a;
+        }
+      const float dist = (float)acc; /* cv::norm(..., NORM_L1) */
+      if (dist < (float)best) { best = (int)dist; best_inc = inc; }
+      dists[L + inc] = dist;
+    }
+    if (best_inc == -L || best_inc == L) continue; /* :944 */
+    const float d1 = dists[L + best_inc - 1], d2 = dists[L + best_inc], d3 = dists[L + best_inc + 1];
+    const float delta = (d1 - d3) / (2.0f * (d1 + d3 - 2.0f * d2)); /* :951-952 */
+    if (delta < -1 || delta > 1) continue;
+    float best_ur = sf[oct] * ((float)sur0 + (float)best_inc + delta); /* :957-958 */
+    float disparity = kpl->x - best_ur;
+    if (disparity >= min_d && disparity < max_d) { /* :962-970 */
+      if (disparity <= 0) { disparity = 0.01f; best_ur = (float)((double)kpl->x - 0.01); }
+      depth[il] = bf / disparity;
+      u_right[il] = best_ur;
+      sad[il] = best;
+      recs[nrec].dist = best; recs[nrec].il = il; nrec++;
+    }
+  }
+  if (nrec > 0) { /* :974-985 (the reference indexes an empty vector when nothing matched) */
+    qsort(recs, (size_t)nrec, sizeof(sad_rec), sad_rec_cmp);
+    const float median = (float)recs[nrec / 2].dist;
+    const float th = 1.5f * 1.4f * median;
+    for (int i = nrec - 1; i >= 0; i--) {
+      if ((float)recs[i].dist < th) break;
+      u_right[recs[i].il] = -1.0f; depth[recs[i].il] = -1.0f;
+    }
+  }
+  free(recs);
+}
+
 void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
                        const orc_window_query* q, const uint8_t* qdesc, int nq,
                        const uint8_t* skip, orc_window_result* out) {

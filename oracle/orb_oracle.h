@@ -101,6 +101,24 @@ void orc_stereo_rowband(const orc_kp* kl, const uint8_t* dl, int nl, const orc_k
                         const uint8_t* dr, int nr, const float* scale_factors, int n_rows,
                         float min_d, float max_d, int* best_idx, int* best_dist);
 
+/* frame.cc:903-985, the rest of Frame::ComputeStereoMatches: for every left
+ * keypoint whose row-band match has best_dist < th_orb_dist, an 11x11 SAD search over 11 horizontal
+ * shifts on the keypoint's pyramid level, parabola sub-pixel fit, disparity gate, then the
+ * median-distance outlier cut over all accepted matches.  Levels are given WITH their 19-px
+ * REFLECT_101 border (pointer to pixel (0,0), like img_pyramid_).  Outputs: u_right[i], depth[i]
+ * (-1 where there is no stereo match), sad[i] (the SAD of accepted matches, -1 otherwise).
+ * Parity unpinned: frame.cc cannot be compiled here (Eigen/Sophus/DBoW2), this is a restatement. */
+typedef struct {
+  const uint8_t* px;
+  int w, h;
+  size_t stride;
+} orc_level_view;
+void orc_stereo_refine(const orc_level_view* left, const orc_level_view* right, int n_levels,
+                       const orc_kp* kl, int nl, const orc_kp* kr, const int* best_idx,
+                       const int* best_dist, const float* scale_factors, const float* inv_scale_factors,
+                       int th_orb_dist, float min_d, float max_d, float bf, float* u_right, float* depth,
+                       int* sad);
+
 /* Frame grid (frame.cc:438-465 AssignFeaturesToGrid + :679-746 GetFeaturesInArea) and the
  * best / second-best inner loop of SearchByProjection (orb_matcher.cc:66-113). */
 typedef struct {

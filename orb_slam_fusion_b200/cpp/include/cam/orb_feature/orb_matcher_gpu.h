@@ -13,6 +13,7 @@
 #include <vector>
 
 struct orbm_matcher;  // include/orbx.h
+struct orbx_extractor;
 
 namespace ORB_SLAM_FUSION {
 
@@ -39,6 +40,14 @@ class ORBmatcherGpu {
                      const std::vector<cv::KeyPoint>& keys_right, const cv::Mat& desc_right,
                      const std::vector<float>& scale_factors, int n_rows, float min_d, float max_d,
                      std::vector<int>& best_idx_right, std::vector<int>& best_dist);
+
+  // Frame::ComputeStereoMatches (frame.cc:828-986) on the device, for the frames the two extractors
+  // processed last (the reference reads their img_pyramid_): fills mvuRight / mvDepth (-1 = no match).
+  // bf and mb are Frame::bf_ and Frame::mb (minZ = mb, maxD = bf / minZ, frame.cc:853-856).
+  void ComputeStereoMatches(orbx_extractor* left, orbx_extractor* right, const std::vector<cv::KeyPoint>& keys_left,
+                            const cv::Mat& desc_left, const std::vector<cv::KeyPoint>& keys_right, const cv::Mat& desc_right,
+                            const std::vector<float>& scale_factors, int n_rows, float bf, float mb,
+                            std::vector<float>& u_right, std::vector<float>& depth);
 
   struct Window { float u, v, r; int min_level, max_level; };
   struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };

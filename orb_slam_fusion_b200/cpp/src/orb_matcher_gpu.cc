@@ -66,6 +66,22 @@ void ORBmatcherGpu::StereoRowBand(const std::vector<cv::KeyPoint>& kl, const cv:
                                 ORBX_MEM_HOST, nullptr));
 }
 
+void ORBmatcherGpu::ComputeStereoMatches(orbx_extractor* left, orbx_extractor* right, const std::vector<cv::KeyPoint>& kl,
+                                         const cv::Mat& dl, const std::vector<cv::KeyPoint>& kr, const cv::Mat& dr,
+                                         const std::vector<float>& sf, int n_rows, float bf, float mb,
+                                         std::vector<float>& u_right, std::vector<float>& depth) {
+  const float min_d = 0.f, max_d = bf / mb;  // frame.cc:853-856
+  std::vector<int> best_idx, best_dist;
+  StereoRowBand(kl, dl, kr, dr, sf, n_rows, min_d, max_d, best_idx, best_dist);
+  u_right.assign(kl.size(), -1.0f);
+  depth.assign(kl.size(), -1.0f);
+  std::vector<int> sad(kl.size(), -1);
+  const int th_orb_dist = (TH_HIGH + TH_LOW) / 2;  // frame.cc:832
+  check(m_, orbm_stereo_refine(m_, left, right, reinterpret_cast<const orbx_kp*>(kl.data()), (int)kl.size(),
+                               reinterpret_cast<const orbx_kp*>(kr.data()), (int)kr.size(), best_idx.data(), best_dist.data(),
+                               th_orb_dist, min_d, max_d, bf, u_right.data(), depth.data(), sad.data(), ORBX_MEM_HOST, nullptr));
+}
+
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,
                                  float inv_w, float inv_h, int cols, int rows, const std::vector<Window>& windows,
                                  const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out) {

@@ -318,6 +318,136 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
   return 1;
 }
 
+// ------------------------------------------------------------------ stereo sub-pixel refinement
+// The rest of Frame::ComputeStereoMatches (frame.cc:903-985): for every left keypoint whose row-band
+// match is closer than thOrbDist, an 11x11 SAD over 11 horizontal shifts on the keypoint's pyramid
+// level (cv::norm(IL, IR, NORM_L1)), parabola sub-pixel fit, disparity gate.  One warp per left
+// keypoint; lanes split the 121 patch pixels, the left patch stays in registers across the shifts.
+// Levels are read from the two extractors' device pyramids; img_pyramid_'s REFLECT_101 border is
+// reproduced by reflecting the coordinates.
+struct StereoLevels {
+  FrameGeom gl, gr;
+  float sf[ORBX_MAX_LEVELS], isf[ORBX_MAX_LEVELS];
+};
+
+__device__ __forceinline__ int refl(int p, int len) { return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p); }
+
+__global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ StereoLevels P, const uint8_t* __restrict__ pyr_l,
+                                                       const uint8_t* __restrict__ pyr_r, const orbx_kp* __restrict__ kl, int nl,
+                                                       const orbx_kp* __restrict__ kr, const int32_t* __restrict__ best_idx,
+                                                       const int32_t* __restrict__ best_dist, int th_orb_dist, float min_d,
+                                                       float max_d, float bf, float* __restrict__ u_right,
+                                                       float* __restrict__ depth, int32_t* __restrict__ sad) {
+  const int il = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (il >= nl) return;
+  float o_ur = -1.0f, o_depth = -1.0f;
+  int o_sad = -1;
+  const int bi = best_idx[il];
+  const orbx_kp L = kl[il];
+  const int oct = L.octave;
+  if (bi >= 0 && best_dist[il] < th_orb_dist && oct >= 0 && oct < P.gl.nlev) {
+    const float ur0 = kr[bi].x;
+    const float scale = P.isf[oct];
+    const float sul = roundf(f_mul(L.x, scale)), svl = roundf(f_mul(L.y, scale)), sur0 = roundf(f_mul(ur0, scale));
+    const LevelGeom& GL = P.gl.lv[oct];
+    const LevelGeom& GR = P.gr.lv[oct];
+    const float iniu = sur0, endu = f_add(sur0, 11.0f);  // scaleduR0 + L - w, scaleduR0 + L + w + 1 with L = w = 5
+    if (!(iniu < 0 || endu >= (float)GR.w)) {
+      const int y0 = (int)svl - 5, xl0 = (int)sul - 5, xr_c = (int)sur0 - 5;
+      // this lane's patch pixels e = lane, lane+32, ... < 121
+      int a[4], ey[4], ex[4];
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const int e = lane + 32 * t;
+        ey[t] = e / 11;
+        ex[t] = e - ey[t] * 11;
+        a[t] = e < 121 ? pyr_l[px_off(GL, refl(xl0 + ex[t], GL.w), refl(y0 + ey[t], GL.h))] : 0;
+      }
+      float dists[11];
+      int best = INT_MAX, best_inc = 0;
+#pragma unroll
+      for (int inc = -5; inc <= 5; inc++) {
+        int acc = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+          if (lane + 32 * t < 121) {
+            const int b = pyr_r[px_off(GR, refl(xr_c + inc + ex[t], GR.w), refl(y0 + ey[t], GR.h))];
+            acc += abs(a[t] - b);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        const float dist = (float)acc;
+        if (dist < (float)best) { best = acc; best_inc = inc; }
+        dists[inc + 5] = dist;
+      }
+      if (best_inc != -5 && best_inc != 5) {
+        float d1 = 0, d2 = 0, d3 = 0;
+#pragma unroll
+        for (int k = 1; k < 10; k++)
+          if (k == best_inc + 5) { d1 = dists[k - 1]; d2 = dists[k]; d3 = dists[k + 1]; }
+        const float delta = f_div(f_sub(d1, d3), f_mul(2.0f, f_sub(f_add(d1, d3), f_mul(2.0f, d2))));
+        if (!(delta < -1 || delta > 1)) {
+          float best_ur = f_mul(P.sf[oct], f_add(f_add(sur0, (float)best_inc), delta));
+          float disparity = f_sub(L.x, best_ur);
+          if (disparity >= min_d && disparity < max_d) {
+            if (disparity <= 0) { disparity = 0.01f; best_ur = (float)((double)L.x - 0.01); }
+            o_depth = f_div(bf, disparity);
+            o_ur = best_ur;
+            o_sad = best;
+          }
+        }
+      }
+    }
+  }
+  if (lane == 0) { u_right[il] = o_ur; depth[il] = o_depth; sad[il] = o_sad; }
+}
+
+// frame.cc:974-985: median of the accepted SAD distances (element size/2 of the list sorted by
+// (distance, left index)); every match with distance >= 1.5 * 1.4 * median is dropped.  One CTA.
+__global__ void __launch_bounds__(1024) k_stereo_median_cut(int nl, const int32_t* __restrict__ sad, float* __restrict__ u_right,
+                                                            float* __restrict__ depth) {
+  __shared__ int n_acc;
+  __shared__ float th;
+  if (threadIdx.x == 0) { n_acc = 0; th = 0.f; }
+  __syncthreads();
+  int cnt = 0;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) cnt += sad[i] >= 0;
+  if (cnt) atomicAdd(&n_acc, cnt);
+  __syncthreads();
+  const int n = n_acc;
+  if (n == 0) return;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    const int d = sad[i];
+    if (d < 0) continue;
+    int rank = 0;  // number of accepted (distance, index) pairs below this one
+    for (int j = 0; j < nl; j++) {
+      const int e = sad[j];
+      rank += (e >= 0) && (e < d || (e == d && j < i));
+    }
+    if (rank == n / 2) th = f_mul(f_mul(1.5f, 1.4f), (float)d);
+  }
+  __syncthreads();
+  const float t = th;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x)
+    if (sad[i] >= 0 && !((float)sad[i] < t)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+}
+
+int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
+                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, const int32_t* best_idx,
+                         const int32_t* best_dist, int th_orb_dist, float min_d, float max_d, float bf, float* u_right,
+                         float* depth, int32_t* sad, cudaStream_t st) {
+  if (nl <= 0) return 0;
+  StereoLevels P;
+  P.gl = gl;
+  P.gr = gr;
+  for (int i = 0; i < ORBX_MAX_LEVELS; i++) { P.sf[i] = i < gl.nlev ? sf[i] : 1.f; P.isf[i] = i < gl.nlev ? isf[i] : 1.f; }
+  k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(P, pyr_l, pyr_r, kl, nl, kr, best_idx, best_dist, th_orb_dist, min_d, max_d, bf,
+                                                u_right, depth, sad);
+  k_stereo_median_cut<<<1, 1024, 0, st>>>(nl, sad, u_right, depth);
+  return 2;
+}
+
 // ------------------------------------------------------------------ projection window search
 // One warp per query.  GetFeaturesInArea visits cells column-major (ix outer, iy inner) and the
 // keypoints of a cell in insertion (= index) order (frame.cc:438-465, 718-743); the

@@ -252,6 +252,40 @@ int orbm_stereo_rowband(orbm_t* m, const orbx_kp* kl, const uint8_t* dl, int nl,
   return end(m, mem, st);
 }
 
+int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const orbx_kp* kl, int nl, const orbx_kp* kr,
+                       int nr, const int32_t* best_idx, const int32_t* best_dist, int th_orb_dist, float min_d, float max_d,
+                       float bf, float* u_right, float* depth, int32_t* sad, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nl < 0 || nr < 0 || (nl > 0 && (!kl || !best_idx || !best_dist || !u_right || !depth || !sad)) || (nr > 0 && !kr))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  FrameGeom gl, gr;
+  const uint8_t *pl, *pr;
+  const float *sf, *isf, *sf_r, *isf_r;
+  int dl, dr;
+  if (!orbx_peek_pyramid(left, &gl, &pl, &sf, &isf, &dl) || !orbx_peek_pyramid(right, &gr, &pr, &sf_r, &isf_r, &dr))
+    return fail(m, ORBX_E_ARG, "both extractors must hold the pyramid of their last frame");
+  if (dl != m->device || dr != m->device || gl.nlev != gr.nlev) return fail(m, ORBX_E_ARG, "extractors on another device / level count");
+  if (nl == 0) return ORBX_OK;
+  if (mem == ORBX_MEM_HOST)
+    TRY(arena_reserve(m, pad256((size_t)nl * 28) + pad256((size_t)nr * 28) + 2 * pad256((size_t)nl * 4) + 3 * pad256((size_t)nl * 4)));
+  const orbx_kp *dkl, *dkr;
+  const int32_t *dbi, *dbd;
+  TRY(stage_in(m, mem, kl, (size_t)nl, &dkl, st));
+  TRY(stage_in(m, mem, kr, (size_t)nr, &dkr, st));
+  TRY(stage_in(m, mem, best_idx, (size_t)nl, &dbi, st));
+  TRY(stage_in(m, mem, best_dist, (size_t)nl, &dbd, st));
+  float* dur = stage_out(m, mem, u_right, (size_t)nl);
+  float* ddp = stage_out(m, mem, depth, (size_t)nl);
+  int32_t* dsad = stage_out(m, mem, sad, (size_t)nl);
+  m->launches += launch_stereo_refine(gl, pl, gr, pr, sf, isf, dkl, nl, dkr, dbi, dbd, th_orb_dist, min_d, max_d, bf, dur, ddp,
+                                      dsad, st);
+  TRY(finish_out(m, mem, u_right, dur, (size_t)nl, st));
+  TRY(finish_out(m, mem, depth, ddp, (size_t)nl, st));
+  TRY(finish_out(m, mem, sad, dsad, (size_t)nl, st));
+  return end(m, mem, st);
+}
+
 int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
                        const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
                        orbm_window_result* out, int mem, void* stream) {

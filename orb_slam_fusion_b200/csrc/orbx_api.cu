@@ -360,6 +360,19 @@ int check_image(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {
 
 }  // namespace
 
+namespace orbx {
+bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
+                       int* device) {
+  if (!h || !h->geom_valid || h->last_frames < 1) return false;
+  *g = h->g;
+  *pyr = h->slot[0].b.pyr;
+  *sf = h->scale;
+  *isf = h->inv_scale;
+  *device = h->device;
+  return true;
+}
+}  // namespace orbx
+
 extern "C" {
 
 int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** out) {

@@ -63,6 +63,13 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom,
                          const orbm_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
                          orbm_window_result* out, cudaStream_t st);
+int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
+                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, const int32_t* best_idx,
+                         const int32_t* best_dist, int th_orb_dist, float min_d, float max_d, float bf, float* u_right,
+                         float* depth, int32_t* sad, cudaStream_t st);
+// the pyramid of frame 0 of an extractor's last single-frame / first-chunk call (defined in orbx_api.cu)
+bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
+                       int* device);
 int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t seed, cudaStream_t st);
 // mode 0: popc.b32 per second; 1: plain 8-popc distances per second; 2: ham256 as built, per second
 int popc_bench(int mode, double* per_s);

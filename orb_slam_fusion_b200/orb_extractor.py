@@ -168,6 +168,11 @@ class OrbExtractor:
         self._check(self._lib.orbx_pyramid_level(self._h, lev, buf.ctypes.data, buf.strides[0], C.byref(w), C.byref(h)))
         return buf if with_border else buf[A.EDGE:-A.EDGE, A.EDGE:-A.EDGE]
 
+    def pyramid_level_size(self, lev):
+        w, h = C.c_int(), C.c_int()
+        self._check(self._lib.orbx_pyramid_level(self._h, lev, None, 0, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
     @property
     def img_pyramid_(self):
         """Level images of the last single-frame call; like the reference's Mats they are views into

@@ -128,6 +128,30 @@ class ORBmatcher:
                                                   A.MEM_HOST, None))
         return bi, bd
 
+    def stereo_refine(self, ex_left, ex_right, kl, kr, best_idx, best_dist, min_d, max_d, bf, th_orb_dist=None):
+        """frame.cc:903-985 on the two extractors' last frames: (u_right, depth, sad) per left keypoint."""
+        th = (self.TH_HIGH + self.TH_LOW) // 2 if th_orb_dist is None else int(th_orb_dist)   # frame.cc:832
+        kl = np.ascontiguousarray(kl, A.KP_DTYPE)
+        kr = np.ascontiguousarray(kr, A.KP_DTYPE)
+        bi = np.ascontiguousarray(best_idx, np.int32)
+        bd = np.ascontiguousarray(best_dist, np.int32)
+        ur = np.empty(len(kl), np.float32)
+        dp = np.empty(len(kl), np.float32)
+        sad = np.empty(len(kl), np.int32)
+        self._check(self._lib.orbm_stereo_refine(self._m, ex_left._h, ex_right._h, kl.ctypes.data, len(kl), kr.ctypes.data,
+                                                 len(kr), bi.ctypes.data, bd.ctypes.data, th, float(min_d), float(max_d),
+                                                 float(bf), ur.ctypes.data, dp.ctypes.data, sad.ctypes.data, A.MEM_HOST, None))
+        return ur, dp, sad
+
+    def ComputeStereoMatches(self, ex_left, ex_right, kl, dl, kr, dr, bf, mb):
+        """Frame::ComputeStereoMatches (frame.cc:828-986) for the extractors' last frames:
+        returns (mvuRight, mvDepth).  minZ = mb, minD = 0, maxD = bf / minZ (:853-856)."""
+        n_rows = ex_left.pyramid_level_size(0)[1]
+        min_d, max_d = 0.0, float(np.float32(bf) / np.float32(mb))
+        bi, bd = self.stereo_rowband(kl, dl, kr, dr, ex_left.GetScaleFactors(), n_rows, min_d, max_d)
+        ur, dp, _ = self.stereo_refine(ex_left, ex_right, kl, kr, bi, bd, min_d, max_d, bf)
+        return ur, dp
+
     # ---- projection window
     def window_search(self, kps, desc, geom, queries, qdesc, skip=None):
         kps = np.ascontiguousarray(kps, A.KP_DTYPE)

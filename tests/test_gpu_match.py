@@ -154,6 +154,39 @@ def test_stereo_rowband_config2(P, m, oracle):
     assert (bi == -1).all() and (bd == 100).all()
 
 
+def test_stereo_refine_and_full_stereo_matches(P, m, oracle):
+    """SURVEY.md 8(f) row 1: the SAD / parabola / median part of Frame::ComputeStereoMatches
+    (frame.cc:903-985) on the two extractors' device pyramids, BASELINE config 2 end to end."""
+    w, h = 752, 480
+    exl, exr = P.OrbExtractor(1200, 1.2, 8, 20, 7), P.OrbExtractor(1200, 1.2, 8, 20, 7)
+    rl, rr = oracle.Extractor(1200, 1.2, 8, 20, 7), oracle.Extractor(1200, 1.2, 8, 20, 7)
+    bf, mb = np.float32(47.90639384423901), np.float32(0.11)     # EuRoC.yaml: fx * baseline, ThDepth-free minZ
+    for frame, shift in [(3, 12), (5, 30), (6, 0)]:
+        left = oracle.blocks_v1(w, h, 1, frame)
+        right = oracle.blocks_v1(w, h, 1, frame, shift_x=shift, noise_seed=2)
+        _, kl, dl = exl(left)
+        _, kr, dr = exr(right)
+        rl.compute_pyramid(left)
+        rr.compute_pyramid(right)
+        ll = [rl.level(l, with_border=True) for l in range(8)]
+        lr = [rr.level(l, with_border=True) for l in range(8)]
+        sf, isf = exl.GetScaleFactors(), exl.GetInverseScaleFactors()
+        max_d = float(bf / mb)
+        bi, bd = m.stereo_rowband(kl, dl, kr, dr, sf, h, 0.0, max_d)
+        ur, dp, sad = m.stereo_refine(exl, exr, kl, kr, bi, bd, 0.0, max_d, bf)
+        wur, wdp, wsad = oracle.stereo_refine(ll, lr, kl, kr, bi, bd, sf, isf, 75, 0.0, max_d, bf)
+        assert np.array_equal(sad, wsad) and ur.tobytes() == wur.tobytes() and dp.tobytes() == wdp.tobytes()
+        ur2, dp2 = m.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, bf, mb)
+        assert ur2.tobytes() == wur.tobytes() and dp2.tobytes() == wdp.tobytes()
+        ok = wur >= 0
+        assert ok.sum() > 400
+        assert abs(np.median(kl["x"][ok] - wur[ok]) - shift) < 0.6 or shift == 0
+        assert (wsad[~ok & (wsad >= 0)]).size > 0        # the median cut dropped some accepted matches
+    # nothing to refine
+    ur, dp, sad = m.stereo_refine(exl, exr, kl, kr, np.full(len(kl), -1, np.int32), np.full(len(kl), 100, np.int32), 0.0, 400.0, bf)
+    assert (ur == -1).all() and (dp == -1).all() and (sad == -1).all()
+
+
 def test_window_search(P, m, oracle):
     w, h = 752, 480
     img = oracle.blocks_v1(w, h, 1, 0)
