@@ -222,3 +222,53 @@ def test_full_size_batch_properties(P, oracle):
         oc = k[f, :n[f]]["octave"]
         assert (np.diff(oc) >= 0).all()                      # levels ascending (mono block, lap {0,0})
         assert (np.bincount(oc, minlength=8) <= quota + 3).all()
+
+
+def test_two_extractors_on_two_threads(P, oracle):
+    """Frame::Frame runs the left and the right extractor on two threads (frame.cc:179-182):
+    distinct handles must be usable concurrently."""
+    import threading
+    imgs = [oracle.blocks_v1(752, 480, 1, f) for f in range(4)]
+    imgs_r = [oracle.blocks_v1(752, 480, 1, f, shift_x=9, noise_seed=3) for f in range(4)]
+    ref = oracle.Extractor(1200, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    want_l = [ref(im) for im in imgs]
+    want_r = [ref(im) for im in imgs_r]
+    exl, exr = P.OrbExtractor(1200, 1.2, 8, 20, 7), P.OrbExtractor(1200, 1.2, 8, 20, 7)
+    errors = []
+
+    def work(ex, ims, want):
+        try:
+            for rep in range(25):
+                k = rep % len(ims)
+                n_mono, kps, desc = ex(ims[k])
+                if n_mono != want[k][0] or kps.tobytes() != want[k][1].tobytes() or not np.array_equal(desc, want[k][2]):
+                    errors.append((rep, k))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(exl, imgs, want_l)), threading.Thread(target=work, args=(exr, imgs_r, want_r))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:3]
+
+
+def test_config4_shaped_batch(P, oracle):
+    """BASELINE config 4 geometry (1280x720, 1000 features) on device-generated frames sharded as
+    frame f -> rank f mod G: every rank's frames equal the oracle's for the same global frame index."""
+    import torch
+    from orb_slam_fusion_b200 import sharding
+    G, total = 8, 32
+    ex = P.OrbExtractor(1000, 1.2, 8, 20, 7, max_batch=4)
+    ref = oracle.Extractor(1000, 1.2, 8, 20, 7, trig=oracle.TRIG_CR)
+    for rank in (0, 5):
+        mine = sharding.local_frames(total, rank, G)
+        frames = torch.cat([P.synth_frames("blocks", 1, 1280, 720, seed=1, first_frame=f) for f in mine])
+        n, nm, kps, desc = ex.extract_batch(frames)
+        torch.cuda.synchronize()
+        k = kps.cpu().numpy().view(P.KP_DTYPE).reshape(len(mine), -1)
+        for j, f in enumerate(mine):
+            rn, rk, rd = ref(oracle.blocks_v1(1280, 720, 1, f))
+            assert int(n[j]) == len(rk) and k[j, :len(rk)].tobytes() == rk.tobytes()
+            assert np.array_equal(desc[j, :len(rk)].cpu().numpy(), rd)
