@@ -171,8 +171,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
         if (yy0 + o < rows_out) {
           const uint32_t packed = (acc[o][0] >> 16) | ((acc[o][1] >> 16) << 8) | ((acc[o][2] >> 16) << 16) | ((acc[o][3] >> 16) << 24);
           uint8_t* dp = d + o * L.pitch;
-          if (x + 4 <= L.w) *reinterpret_cast<uint32_t*>(dp) = packed;
-          else for (int k = 0; x + k < L.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
+          *reinterpret_cast<uint32_t*>(dp) = packed;  // <= 3 bytes of a straddling quad land in unused row padding
         }
       }
     }

@@ -130,16 +130,31 @@ __global__ void __launch_bounds__(256, ORBX_RS_MINB) k_resize(const __grid_const
     }
     if (active) {
       // a1 == 0 where sx is the last column, so sx+1 may read the (allocated) padding
-      const uint8_t* sp = staged ? src_sm + r0 * kRsSrcPitch - sx_lo : frame + src_base + r0 * S.pitch;
-      const int sp_pitch = staged ? kRsSrcPitch : S.pitch;
+      if (staged) {
+        // constant row pitch: the 8 byte addresses are formed once, rows are immediate offsets
+        const uint8_t* sp = src_sm + r0 * kRsSrcPitch - sx_lo;
+        const uint8_t* p0 = sp + sxs[0];
+        const uint8_t* p1 = sp + sxs[1];
+        const uint8_t* p2 = sp + sxs[2];
+        const uint8_t* p3 = sp + sxs[3];
 #pragma unroll
-      for (int i = 0; i < (kRsRows + 7) / 8; i++) {
-        if (i < rpg && r0 + i < n_rows) {
+        for (int i = 0; i < (kRsRows + 7) / 8; i++) {
+          if (i < rpg && r0 + i < n_rows) {
+            const uint32_t o0 = (uint32_t)((p0[i * kRsSrcPitch] * a0s[0] + p0[i * kRsSrcPitch + 1] * a1s[0]) >> 4);
+            const uint32_t o1 = (uint32_t)((p1[i * kRsSrcPitch] * a0s[1] + p1[i * kRsSrcPitch + 1] * a1s[1]) >> 4);
+            const uint32_t o2 = (uint32_t)((p2[i * kRsSrcPitch] * a0s[2] + p2[i * kRsSrcPitch + 1] * a1s[2]) >> 4);
+            const uint32_t o3 = (uint32_t)((p3[i * kRsSrcPitch] * a0s[3] + p3[i * kRsSrcPitch + 1] * a1s[3]) >> 4);
+            *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+          }
+        }
+      } else {
+        const uint8_t* sp = frame + src_base + r0 * S.pitch;
+        for (int i = 0; i < rpg && r0 + i < n_rows; i++) {
           uint32_t o[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) o[k] = (uint32_t)((sp[sxs[k]] * a0s[k] + sp[sxs[k] + 1] * a1s[k]) >> 4);
           *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-          sp += sp_pitch;
+          sp += S.pitch;
         }
       }
     }
@@ -168,16 +183,15 @@ __global__ void __launch_bounds__(256, ORBX_RS_MINB) k_resize(const __grid_const
           uint32_t packed = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++) {
-            int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;
-            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
+            // cv::resize can never clip and is not spelled out
+            const int v = (((b0 * h0[k]) >> 16) + ((b1 * h1[k]) >> 16) + 2) >> 2;
             packed |= (uint32_t)v << (8 * k);
           }
           uint8_t* dp = d + i * D.pitch;
-          if (dx0 + 4 <= D.w) {
-            *reinterpret_cast<uint32_t*>(dp) = packed;
-          } else {
-            for (int k = 0; dx0 + k < D.w; k++) dp[k] = (uint8_t)(packed >> (8 * k));
-          }
+          // a quad that straddles the right edge spills <= 3 bytes into the row padding, which nothing
+          // reads before k_border rewrites it
+          *reinterpret_cast<uint32_t*>(dp) = packed;
         }
       }
     }
