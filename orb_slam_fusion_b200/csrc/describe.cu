@@ -96,16 +96,15 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
                                                               const uint8_t* __restrict__ sel_sc, const int32_t* __restrict__ n_sel,
                                                               const int32_t* __restrict__ work, orbx_kp* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int cap, int out_frame0) {
-  // pattern transposed so that lane L reads word [k][L]: (x0,y0,x1,y1) of bit k of byte L
-  __shared__ uint32_t pat[8][32];
+  // pattern as floats, transposed so that lane L reads entry [k][L] = (x0, y0, x1, y1) of bit k of byte L
+  __shared__ float4 pat[8][32];
   // per warp: the 37 x 37 blurred patch around the keypoint as 37 rows of 11 aligned words
   __shared__ uint32_t patch[kDescWarps][kPatchRows * kPatchWords];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   {
     const int L = tid >> 3, k = tid & 7;  // 256 threads = 32 bytes x 8 bits
     const int8_t* p = &c_pattern[(L * 8 + k) * 4];
-    pat[k][L] = (uint32_t)(uint8_t)p[0] | ((uint32_t)(uint8_t)p[1] << 8) | ((uint32_t)(uint8_t)p[2] << 16) |
-                ((uint32_t)(uint8_t)p[3] << 24);
+    pat[k][L] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
   }
   __syncthreads();
   const int f = blockIdx.y;
@@ -184,10 +183,10 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   uint32_t byte = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const uint32_t p = pat[k][lane];
-    int r0, c0, r1, c1;
-    rbrief_offset(a, b, (int)(int8_t)(p & 255), (int)(int8_t)((p >> 8) & 255), r0, c0);
-    rbrief_offset(a, b, (int)(int8_t)((p >> 16) & 255), (int)(int8_t)(p >> 24), r1, c1);
+    const float4 p = pat[k][lane];
+    int r0, c0, r1, c1;  // orb_extractor.cc:108-113: row = cvRound(x*b + y*a), col = cvRound(x*a - y*b), float32, no FMA
+    rbrief_offset_f(a, b, p.x, p.y, r0, c0);
+    rbrief_offset_f(a, b, p.z, p.w, r1, c1);
     const int t0 = bc[r0 * (kPatchWords * 4) + c0], t1 = bc[r1 * (kPatchWords * 4) + c1];
     byte |= (uint32_t)(t0 < t1) << k;
   }

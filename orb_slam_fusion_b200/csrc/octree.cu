@@ -75,8 +75,11 @@ cudaError_t octree_configure(int node_cap) {
 
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   dim3 grid(g.nlev, frames);
-  // 128 threads: the passes are short and barrier-bound, smaller CTAs waste fewer idle warps (measured 0.31 vs 0.45 ms / 512 frames)
-  static const int threads = [] { const char* e = getenv("ORBX_OCTREE_THREADS"); const int t = e ? atoi(e) : 128; return t >= 64 && t <= 256 && t % 32 == 0 ? t : 128; }();
+  // The passes are short and barrier-bound.  Batches: 128-thread CTAs waste fewer idle warps (0.31 vs 0.45 ms per
+  // 512 frames); a single frame has only 8 CTAs in flight and wants the shorter point loops of 256 threads
+  // (54 vs 65 us).  ORBX_OCTREE_THREADS overrides (A/B runs).
+  static const int forced = [] { const char* e = getenv("ORBX_OCTREE_THREADS"); const int t = e ? atoi(e) : 0; return t >= 64 && t <= 256 && t % 32 == 0 ? t : 0; }();
+  const int threads = forced ? forced : (frames >= 16 ? 128 : 256);
   k_octree<<<grid, threads, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_raw_xy, b.cand_raw_sc, b.cell_strong, b.cand_xy,
                                                             b.cand_sc, b.node_of, b.n_cand, b.sel_xy, b.sel_sc, b.n_sel);
   return 1;

@@ -174,10 +174,12 @@ ORBX_HD int reflect101(int p, int len) {
 
 // ---- rBRIEF steering (orb_extractor.cc:105-113) ------------------------------------------
 // (a, b) = (cos, sin) of the keypoint angle; returns the sampling offset of pattern point (px,py)
-ORBX_HD void rbrief_offset(float a, float b, int px, int py, int& row, int& col) {
-  const float fx = (float)px, fy = (float)py;
+ORBX_HD void rbrief_offset_f(float a, float b, float fx, float fy, int& row, int& col) {
   row = f_round(f_add(f_mul(fx, b), f_mul(fy, a)));
   col = f_round(f_sub(f_mul(fx, a), f_mul(fy, b)));
+}
+ORBX_HD void rbrief_offset(float a, float b, int px, int py, int& row, int& col) {
+  rbrief_offset_f(a, b, (float)px, (float)py, row, col);
 }
 
 // ---- splitmix64 and the synthetic frame generators ------------------------
