@@ -206,6 +206,15 @@ int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const
                        int nr, const int32_t* best_idx, const int32_t* best_dist, int th_orb_dist, float min_d, float max_d,
                        float bf, float* u_right, float* depth, int32_t* sad, int mem, void* stream);
 
+/* MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-428) for a batch of
+ * map points: point p owns descriptor rows [offsets[p], offsets[p+1]) of `desc`; per point the row
+ * with the least median Hamming distance to all rows of the point (median = element
+ * int(0.5*(N-1)) of the sorted distances incl. the 0 self-distance; the first such row wins).
+ * best_idx[p] is relative to offsets[p] (-1 for a point without rows).  max_rows >= the largest
+ * group (<= 6000).  With ORBX_MEM_DEVICE the caller guarantees that bound. */
+int orbm_distinctive(orbm_t* m, const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
+                     int32_t* best_median, int mem, void* stream);
+
 /* Frame grid geometry (frame.cc:199-204: mnMinX, mnMinY, mfGridElementWidthInv/HeightInv;
  * frame.h:40-41: FRAME_GRID_COLS = 64, FRAME_GRID_ROWS = 48). */
 typedef struct {

@@ -71,6 +71,7 @@ def lib():
         L.orc_knn2.argtypes = [vp, i, vp, i64, vp, vp, i]
         L.orc_ratio_accept.argtypes = [i, i, i, C.c_double]
         L.orc_stereo_rowband.argtypes = [vp, vp, i, vp, vp, i, vp, i, f, f, vp, vp]
+        L.orc_distinctive.argtypes = [vp, vp, i, vp, vp]
         L.orc_stereo_refine.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i, f, f, f, vp, vp, vp]
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_splitmix64.restype = u64
@@ -282,6 +283,16 @@ def stereo_rowband(kl, dl, kr, dr, scale_factors, n_rows, min_d, max_d):
     lib().orc_stereo_rowband(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), int(n_rows),
                              float(min_d), float(max_d), _p(bi), _p(bd))
     return bi, bd
+
+
+def distinctive(desc, offsets):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    bi = np.empty(n, np.int32)
+    bm = np.empty(n, np.int32)
+    lib().orc_distinctive(_p(desc), _p(offsets), n, _p(bi), _p(bm))
+    return bi, bm
 
 
 class LevelView(C.Structure):

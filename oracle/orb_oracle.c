@@ -622,6 +622,26 @@ void orc_stereo_rowband(const orc_kp* kl, const uint8_t* dl, int nl, const orc_k
   free(rows); free(cnt);
 }
 
+/* ---- mappoint.cc:365-428 ---- */
+static int int_cmp(const void* a, const void* b) { return *(const int*)a - *(const int*)b; }
+void orc_distinctive(const uint8_t* desc, const int* offsets, int n_points, int* best_idx, int* best_median) {
+  for (int p = 0; p < n_points; p++) {
+    const int o = offsets[p], N = offsets[p + 1] - o;
+    best_idx[p] = -1; best_median[p] = INT_MAX;
+    if (N <= 0) continue;
+    int* row = (int*)malloc(sizeof(int) * (size_t)N);
+    int bm = INT_MAX, bi = 0;
+    for (int i = 0; i < N; i++) {
+      for (int j = 0; j < N; j++) row[j] = i == j ? 0 : orc_hamming(desc + 32 * (size_t)(o + i), desc + 32 * (size_t)(o + j));
+      qsort(row, (size_t)N, sizeof(int), int_cmp);
+      const int median = row[(int)(0.5 * (N - 1))]; /* :414 */
+      if (median < bm) { bm = median; bi = i; }
+    }
+    free(row);
+    best_idx[p] = bi; best_median[p] = bm;
+  }
+}
+
 /* ---- frame.cc:903-985 ---- */
 typedef struct { int dist; int il; } sad_rec;
 static int sad_rec_cmp(const void* a, const void* b) { /* std::sort of pair<int,int> */

@@ -119,6 +119,13 @@ void orc_stereo_refine(const orc_level_view* left, const orc_level_view* right, 
                        int th_orb_dist, float min_d, float max_d, float bf, float* u_right, float* depth,
                        int* sad);
 
+/* MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-428) for a batch of
+ * map points: point p owns descriptor rows [offsets[p], offsets[p+1]); all-pairs Hamming distances,
+ * per row the median (sorted row incl. the 0 self-distance, element int(0.5*(N-1))), the first row
+ * with the least median wins.  best_idx[p] is relative to offsets[p] (-1 for a point without rows),
+ * best_median[p] its median.  Parity unpinned (mappoint.cc cannot be compiled here). */
+void orc_distinctive(const uint8_t* desc, const int* offsets, int n_points, int* best_idx, int* best_median);
+
 /* Frame grid (frame.cc:438-465 AssignFeaturesToGrid + :679-746 GetFeaturesInArea) and the
  * best / second-best inner loop of SearchByProjection (orb_matcher.cc:66-113). */
 typedef struct {

@@ -49,6 +49,11 @@ class ORBmatcherGpu {
                             const std::vector<float>& scale_factors, int n_rows, float bf, float mb,
                             std::vector<float>& u_right, std::vector<float>& depth);
 
+  // MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-428) for many map points at once:
+  // observations[p] holds the descriptor rows of point p (the vDescriptors of :367-398); returns for
+  // each point the index of the row with the least median distance to the others (-1 if empty).
+  std::vector<int> ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& observations);
+
   struct Window { float u, v, r; int min_level, max_level; };
   struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };
   // orb_matcher.cc:66-113 with Frame::GetFeaturesInArea (frame.cc:679-746) for a batch of projections.

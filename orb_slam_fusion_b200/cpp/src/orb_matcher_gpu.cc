@@ -82,6 +82,22 @@ void ORBmatcherGpu::ComputeStereoMatches(orbx_extractor* left, orbx_extractor* r
                                th_orb_dist, min_d, max_d, bf, u_right.data(), depth.data(), sad.data(), ORBX_MEM_HOST, nullptr));
 }
 
+std::vector<int> ORBmatcherGpu::ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& obs) {
+  std::vector<int32_t> offsets(obs.size() + 1, 0);
+  int max_rows = 0;
+  for (size_t p = 0; p < obs.size(); ++p) {
+    offsets[p + 1] = offsets[p] + (int32_t)obs[p].size();
+    if ((int)obs[p].size() > max_rows) max_rows = (int)obs[p].size();
+  }
+  std::vector<uint8_t> desc((size_t)offsets.back() * 32);
+  for (size_t p = 0; p < obs.size(); ++p)
+    for (size_t i = 0; i < obs[p].size(); ++i) std::memcpy(desc.data() + 32 * (size_t)(offsets[p] + i), obs[p][i].ptr(0), 32);
+  std::vector<int> best((size_t)obs.size(), -1), median((size_t)obs.size(), 0);
+  check(m_, orbm_distinctive(m_, desc.data(), offsets.data(), (int)obs.size(), max_rows, best.data(), median.data(),
+                             ORBX_MEM_HOST, nullptr));
+  return best;
+}
+
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,
                                  float inv_w, float inv_h, int cols, int rows, const std::vector<Window>& windows,
                                  const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out) {

@@ -448,6 +448,59 @@ int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameG
   return 2;
 }
 
+// ------------------------------------------------------------------ distinctive descriptor per map point
+// MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-428) for a batch of map points: one CTA
+// per point, one thread per observation row.  The median of a row (element int(0.5*(N-1)) of the
+// sorted distances, self-distance 0 included) is found without sorting: the k-th smallest of
+// integers in [0, 256] is the smallest v with #{d <= v} >= k+1, 9 bisection steps over the row.
+// "First row with the least median" = min over the key (median, row).
+constexpr int kDistinctThreads = 128;
+
+__global__ void __launch_bounds__(kDistinctThreads) k_distinctive(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                                  int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median) {
+  extern __shared__ uint32_t rows[];  // the point's descriptors, 8 words each
+  __shared__ unsigned int best_key;
+  const int p = blockIdx.x, o = offsets[p], N = offsets[p + 1] - o;
+  if (N <= 0) {
+    if (threadIdx.x == 0) { best_idx[p] = -1; best_median[p] = INT_MAX; }
+    return;
+  }
+  if (threadIdx.x == 0) best_key = 0xFFFFFFFFu;
+  for (int i = threadIdx.x; i < 8 * N; i += blockDim.x)
+    rows[i] = reinterpret_cast<const uint32_t*>(desc + 32 * (size_t)o)[i];  // rows are 4-byte aligned (32-byte records)
+  __syncthreads();
+  const int k = (int)(0.5 * (N - 1));
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    uint32_t a[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) a[w] = rows[8 * i + w];
+    int lo = 0, hi = 256;  // smallest v in [lo, hi] with count(d <= v) >= k + 1
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+      for (int j = 0; j < N; j++) {
+        uint32_t b[8];
+#pragma unroll
+        for (int w = 0; w < 8; w++) b[w] = rows[8 * j + w];
+        cnt += ham256(a, b) <= mid;
+      }
+      if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    atomicMin(&best_key, ((unsigned)lo << 20) | (unsigned)i);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { best_idx[p] = (int32_t)(best_key & 0xFFFFFu); best_median[p] = (int32_t)(best_key >> 20); }
+}
+
+int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
+                       int32_t* best_median, cudaStream_t st) {
+  if (n_points <= 0) return 0;
+  const size_t smem = (size_t)(max_rows > 0 ? max_rows : 1) * 32;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_distinctive<<<n_points, kDistinctThreads, smem, st>>>(desc, offsets, best_idx, best_median);
+  return 1;
+}
+
 // ------------------------------------------------------------------ projection window search
 // One warp per query.  GetFeaturesInArea visits cells column-major (ix outer, iy inner) and the
 // keypoints of a cell in insertion (= index) order (frame.cc:438-465, 718-743); the

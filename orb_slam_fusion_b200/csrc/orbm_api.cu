@@ -286,6 +286,32 @@ int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const
   return end(m, mem, st);
 }
 
+int orbm_distinctive(orbm_t* m, const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
+                     int32_t* best_median, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (n_points < 0 || max_rows < 0 || max_rows > 6000 || (n_points > 0 && (!offsets || !best_idx || !best_median)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (n_points == 0) return ORBX_OK;
+  size_t total = 0;
+  if (mem == ORBX_MEM_HOST) {
+    total = (size_t)offsets[n_points];
+    for (int p = 0; p < n_points; p++)
+      if (offsets[p + 1] - offsets[p] > max_rows) return fail(m, ORBX_E_ARG, "a point owns more rows than max_rows");
+    TRY(arena_reserve(m, pad256(total * 32) + pad256((size_t)(n_points + 1) * 4) + 2 * pad256((size_t)n_points * 4)));
+  }
+  const uint8_t* dd;
+  const int32_t* doff;
+  TRY(stage_in(m, mem, desc, total * 32, &dd, st));
+  TRY(stage_in(m, mem, offsets, (size_t)n_points + 1, &doff, st));
+  int32_t* dbi = stage_out(m, mem, best_idx, (size_t)n_points);
+  int32_t* dbm = stage_out(m, mem, best_median, (size_t)n_points);
+  m->launches += launch_distinctive(dd, doff, n_points, max_rows, dbi, dbm, st);
+  TRY(finish_out(m, mem, best_idx, dbi, (size_t)n_points, st));
+  TRY(finish_out(m, mem, best_median, dbm, (size_t)n_points, st));
+  return end(m, mem, st);
+}
+
 int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
                        const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
                        orbm_window_result* out, int mem, void* stream) {

@@ -70,6 +70,9 @@ int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameG
 // the pyramid of frame 0 of an extractor's last single-frame / first-chunk call (defined in orbx_api.cu)
 bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
                        int* device);
+// max_rows: the largest number of rows any point owns (sizes the shared memory; <= 6000)
+int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
+                       int32_t* best_median, cudaStream_t st);
 int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t seed, cudaStream_t st);
 // mode 0: popc.b32 per second; 1: plain 8-popc distances per second; 2: ham256 as built, per second
 int popc_bench(int mode, double* per_s);

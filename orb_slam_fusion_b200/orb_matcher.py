@@ -152,6 +152,18 @@ class ORBmatcher:
         ur, dp, _ = self.stereo_refine(ex_left, ex_right, kl, kr, bi, bd, min_d, max_d, bf)
         return ur, dp
 
+    def ComputeDistinctiveDescriptors(self, desc, offsets):
+        """mappoint.cc:365-428 for a batch of map points: (best row per point, its median distance)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        n = len(offsets) - 1
+        bi = np.empty(n, np.int32)
+        bm = np.empty(n, np.int32)
+        max_rows = int(np.diff(offsets).max()) if n else 0
+        self._check(self._lib.orbm_distinctive(self._m, desc.ctypes.data, offsets.ctypes.data, n, max_rows, bi.ctypes.data,
+                                               bm.ctypes.data, A.MEM_HOST, None))
+        return bi, bm
+
     # ---- projection window
     def window_search(self, kps, desc, geom, queries, qdesc, skip=None):
         kps = np.ascontiguousarray(kps, A.KP_DTYPE)

@@ -187,6 +187,26 @@ def test_stereo_refine_and_full_stereo_matches(P, m, oracle):
     assert (ur == -1).all() and (dp == -1).all() and (sad == -1).all()
 
 
+def test_distinctive_descriptors(m, oracle):
+    """SURVEY.md 8(f) row 3: MapPoint::ComputeDistinctiveDescriptors batched over map points."""
+    rng = np.random.default_rng(11)
+    sizes = np.concatenate([[0, 1, 2, 3], rng.integers(2, 40, 300), [150, 257]])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = np.empty((offsets[-1], 32), np.uint8)
+    for p, (o, n) in enumerate(zip(offsets[:-1], sizes)):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)          # observations of one point: noisy copies
+        desc[o:o + n] = base
+        flips = rng.integers(0, 256, (n, 20))
+        for j in range(20):
+            desc[o + np.arange(n), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+        if n > 4 and p % 3 == 0:
+            desc[o + 1] = desc[o]                                  # duplicates: equal medians, first row wins
+    bi, bm = m.ComputeDistinctiveDescriptors(desc, offsets)
+    wi, wm = oracle.distinctive(desc, offsets)
+    assert np.array_equal(bi, wi) and np.array_equal(bm, wm)
+    assert bi[0] == -1 and bi[1] == 0 and bm[1] == 0
+
+
 def test_window_search(P, m, oracle):
     w, h = 752, 480
     img = oracle.blocks_v1(w, h, 1, 0)
