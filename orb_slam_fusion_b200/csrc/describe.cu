@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
 }
 
 constexpr int kDescWarps = 8;
-constexpr int kPatchRows = 37, kPatchWords = 11;  // rotated pattern offsets stay within +-18 px (A.7)
+constexpr int kPatchRows = 37;    // rotated pattern offsets stay within +-18 px (A.7)
+constexpr int kPatchPitch = 80;   // bytes per staged row: 4 x 16-byte chunks from a 16-byte aligned column (<= 15 + 37 bytes used);
+                                  // 20 words of pitch spread vertical neighbours over the banks
 
 #ifndef ORBX_DESC_MINB
 #define ORBX_DESC_MINB 8
@@ -98,8 +100,8 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
                                                               uint8_t* __restrict__ desc, int cap, int out_frame0) {
   // pattern as floats, transposed so that lane L reads entry [k][L] = (x0, y0, x1, y1) of bit k of byte L
   __shared__ float4 pat[8][32];
-  // per warp: the 37 x 37 blurred patch around the keypoint as 37 rows of 11 aligned words
-  __shared__ uint32_t patch[kDescWarps][kPatchRows * kPatchWords];
+  // per warp: the 37 x 37 blurred patch around the keypoint, rows of kPatchPitch bytes
+  __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   {
     const int L = tid >> 3, k = tid & 7;  // 256 threads = 32 bytes x 8 bits
@@ -126,20 +128,19 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   // Blurred 37 x 37 patch for the descriptor: issue its coalesced word loads first so that they are in
   // flight together with the orientation loads (the 512 samples of a descriptor are single-byte
   // gathers over 37 rows: straight from global memory each would cost one L1 wavefront per lane).
-  const int xb = (cx - 18) & ~3;  // >= 0: keypoints are >= 19 px inside; interior rows are 16-byte aligned
-  constexpr int kStage = (kPatchRows * kPatchWords + 31) / 32;
-  uint32_t* pw = patch[wid];
+  const int xb = (cx - 18) & ~15;  // >= 0: keypoints are >= 19 px inside; interior rows are 16-byte aligned
+  uint8_t* pw = patch[wid];
   {
-    // LDGSTS: global -> shared without staging registers; completes while the orientation is computed
+    // 16-byte LDGSTS: global -> shared without staging registers; completes while the orientation is computed
     const uint8_t* bsrc = blur + fo + px_off(L, xb, cy - 18);
-    const int spitch = pitch;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(pw);
 #pragma unroll
-    for (int t = 0; t < kStage; t++) {
+    for (int t = 0; t < (4 * kPatchRows + 31) / 32; t++) {
       const int i = lane + 32 * t;
-      const int r = i / kPatchWords, c = i - r * kPatchWords;
-      if (i < kPatchRows * kPatchWords)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sbase + 4u * i), "l"(bsrc + r * spitch + 4 * c));
+      const int r = i >> 2, c = i & 3;
+      if (i < 4 * kPatchRows)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sbase + (unsigned)(r * kPatchPitch + 16 * c)),
+                     "l"(bsrc + r * pitch + 16 * c));
     }
     asm volatile("cp.async.commit_group;\n" ::);
   }
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   const float a = (float)cd, b = (float)sd;
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncwarp();
-  const uint8_t* bc = reinterpret_cast<const uint8_t*>(pw) + 18 * (kPatchWords * 4) + (cx - xb);
+  const uint8_t* bc = pw + 18 * kPatchPitch + (cx - xb);
   uint32_t byte = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
     int r0, c0, r1, c1;  // orb_extractor.cc:108-113: row = cvRound(x*b + y*a), col = cvRound(x*a - y*b), float32, no FMA
     rbrief_offset_f(a, b, p.x, p.y, r0, c0);
     rbrief_offset_f(a, b, p.z, p.w, r1, c1);
-    const int t0 = bc[r0 * (kPatchWords * 4) + c0], t1 = bc[r1 * (kPatchWords * 4) + c1];
+    const int t0 = bc[r0 * kPatchPitch + c0], t1 = bc[r1 * kPatchPitch + c1];
     byte |= (uint32_t)(t0 < t1) << k;
   }
   const size_t o = (size_t)(out_frame0 + f) * cap + slot;
