@@ -164,11 +164,8 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
       p += pitch;
     }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-  }
+  m10 = __reduce_add_sync(0xffffffffu, m10);  // REDUX.SUM: one instruction instead of a 5-step shuffle tree
+  m01 = __reduce_add_sync(0xffffffffu, m01);
   const float angle = fast_atan2_deg((float)m01, (float)m10);
 
   // ---- steered rBRIEF (:102-146).  cos/sin are the correctly rounded float values

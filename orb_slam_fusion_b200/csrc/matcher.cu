@@ -375,8 +375,7 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ S
             acc += abs(a[t] - b);
           }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc = __reduce_add_sync(0xffffffffu, acc);  // REDUX.SUM
         const float dist = (float)acc;
         if (dist < (float)best) { best = acc; best_inc = inc; }
         dists[inc + 5] = dist;
