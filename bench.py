@@ -60,7 +60,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region."""
+    """nvidia-smi clocks and throttle reasons.  The sampler is started well before the timed region
+    (nvidia-smi takes ~0.1 s to produce its first row) and every row is stamped on arrival;
+    summary(t0, t1) reports the rows that fell inside the timed region [t0, t1]."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -69,8 +71,8 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -78,20 +80,33 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def wait_first(self, timeout=3.0):
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.01)
 
     def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self, t0, t1):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        self.t.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.02 and len(r) >= 6]
+        where = "inside the timed region"
+        if not rows:  # region shorter than the sampling period: the rows right around it
+            near = sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]
+            rows = [r for (_, r) in near if len(r) >= 6]
+            where = "nearest to the timed region (region shorter than the sampling period)"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) >= 6 and r[2 + k] == "Active" for r in self.rows)]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k] == "Active" for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "where": where}
 
 
 # ---------------------------------------------------------------------------- reference arm (CPU)
@@ -185,6 +200,7 @@ def run_ours(args):
         return float(t.item())
 
     log('process group ready')
+    clocks = ClockSampler(local)
     B = args.batch
     frames = P.synth_frames("blocks", B, W, H, seed=1, first_frame=rank * B, device=local)
     ex = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=B)
@@ -205,16 +221,19 @@ def run_ours(args):
     ex.set_profiling(True)
     ex.stage_times(reset=True)
     launches0 = ex.launch_count()
-    clocks = ClockSampler(local)
+    clocks.wait_first()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_region1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     barrier()
-    clk = clocks.stop()
+    clocks.stop()
+    clk = clocks.summary(t_region0, t_region1)
     stage_ms, chunks = ex.stage_times(reset=True)
     ex.set_profiling(False)
     launches = ex.launch_count() - launches0
