@@ -26,8 +26,10 @@
 namespace orbx {
 
 constexpr int kFtW = 128, kFtH = 32;          // tile of owned pixels (same tiling as the blur kernel)
-constexpr int kFtRawW = 34;                   // raw words per row: bytes X0-4 .. X0+131
-constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the raw and score planes
+constexpr int kFtRawW = 34;                   // words per row the stencils use: bytes X0-4 .. X0+131
+constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the score plane (column cb = x - X0 + 4)
+constexpr int kFtRawPitch = 160;              // raw rows are ten 16-byte chunks from X0-16 (128-bit LDGSTS): column = cb + 12
+constexpr int kFtRawPW = kFtRawPitch / 4, kFtRawOrg = 3;  // words per raw row; raw word of stencil word 0
 constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
 constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
 constexpr int kFtStrip = 5;                   // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
-  __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawW];
+  __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawPW];
   // The blur's u16 intermediate and the detector's score map / lists are live in different phases
   // and share one buffer.
   constexpr int kScoreBytes = kFtScH * kFtPitch, kListBytes = 2 * kFtScH * kFtPitch, kOutBytes = 2 * kFtMaxOut;
@@ -76,23 +78,24 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   const int lo = min(g.ini_th, g.min_th);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
 
-  // ---- 1. raw tile: word (r, c) holds pixels x = X0-4+4c .. +3 of row y = Y0-4+r.  Plain aligned
-  // word loads (thread = word column c, 6 rows); the BORDER_REFLECT_101 halo the blur needs at the
-  // image edges (3 px) is patched in afterwards from the tile itself, only in edge tiles.
+  // ---- 1. raw tile: rows y = Y0-4 .. Y0+35, each ten 16-byte chunks from x = X0-16 (interior rows of the
+  // planes are 16-byte aligned), global -> shared with 128-bit LDGSTS; rows / chunks outside the plane are
+  // zero-filled.  The BORDER_REFLECT_101 halo the blur needs at the image edges (3 px) is patched in
+  // afterwards from the tile itself, only in edge tiles.
   {
-    const int c = tid % kFtRawW, r0 = (tid / kFtRawW) * 6;
-    const int x = X0 - 4 + 4 * c;
-    const bool col_ok = x < L.w + 16;  // the plane has 32 B left / >= 19 B right padding
-    const uint8_t* src = pyr + fo + px_off(L, x, Y0 - 4 + r0);
-#pragma unroll
-    for (int i = 0; i < 6; i++) {
-      const int r = r0 + i, y = Y0 - 4 + r;
-      if (r < kFtRawH) {
-        uint32_t v = 0;
-        if (col_ok && y >= 0 && y < L.h) v = __ldg(reinterpret_cast<const uint32_t*>(src + i * L.pitch));
-        raw_w[r * kFtRawW + c] = v;
-      }
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(raw_w);
+    const uint8_t* src = pyr + fo + px_off(L, X0 - 16, Y0 - 4);
+    for (int i = tid; i < kFtRawH * (kFtRawPitch / 16); i += 256) {
+      const int r = i / (kFtRawPitch / 16), c = i - r * (kFtRawPitch / 16);
+      const int y = Y0 - 4 + r, x = X0 - 16 + 16 * c;
+      // the plane has 32 B left / >= 19 B right padding: chunks up to x < w + 3 are inside the row
+      const bool ok = y >= 0 && y < L.h && x < L.w + 3;
+      const uint8_t* gp = ok ? src + r * L.pitch + 16 * c : pyr + fo;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sbase + (unsigned)(r * kFtRawPitch + 16 * c)), "l"(gp),
+                   "r"(ok ? 16 : 0));
     }
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
   __syncthreads();
   {
@@ -101,17 +104,17 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     if (left || right) {  // columns: x = -k <- k and x = w-1+k <- w-1-k (k = 1..3), rows inside the image
       const int r = tid >> 2, k = (tid & 3) + 1, y = Y0 - 4 + r;
       if (r < kFtRawH && k <= 3 && y >= 0 && y < L.h) {
-        if (left) rawb[r * kFtPitch + 4 - k] = rawb[r * kFtPitch + 4 + k];
-        if (right && L.w - 1 + k <= X0 + kFtW + 2) rawb[r * kFtPitch + (L.w - 1 + k - X0 + 4)] = rawb[r * kFtPitch + (L.w - 1 - k - X0 + 4)];
+        if (left) rawb[r * kFtRawPitch + 16 - k] = rawb[r * kFtRawPitch + 16 + k];
+        if (right && L.w - 1 + k <= X0 + kFtW + 2) rawb[r * kFtRawPitch + (L.w - 1 + k - X0 + 16)] = rawb[r * kFtRawPitch + (L.w - 1 - k - X0 + 16)];
       }
     }
     if (top || bottom) {
       if (left || right) __syncthreads();  // rows copy the patched columns
       // rows: y = -k <- k and y = h-1+k <- h-1-k (k = 1..3), all 34 words
-      for (int i = tid; i < 3 * kFtRawW; i += 256) {
-        const int k = i / kFtRawW + 1, c = i - (k - 1) * kFtRawW;
-        if (top) raw_w[(4 - k) * kFtRawW + c] = raw_w[(4 + k) * kFtRawW + c];
-        if (bottom && L.h - 1 + k <= Y0 + kFtH + 2) raw_w[(L.h - 1 + k - Y0 + 4) * kFtRawW + c] = raw_w[(L.h - 1 - k - Y0 + 4) * kFtRawW + c];
+      for (int i = tid; i < 3 * kFtRawPW; i += 256) {
+        const int k = i / kFtRawPW + 1, c = i - (k - 1) * kFtRawPW;
+        if (top) raw_w[(4 - k) * kFtRawPW + c] = raw_w[(4 + k) * kFtRawPW + c];
+        if (bottom && L.h - 1 + k <= Y0 + kFtH + 2) raw_w[(L.h - 1 + k - Y0 + 4) * kFtRawPW + c] = raw_w[(L.h - 1 - k - Y0 + 4) * kFtRawPW + c];
       }
     }
     if (left || right || top || bottom) __syncthreads();
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
       for (int i = 0; i < 5; i++) {
         const int b = b0 + i;
         if (b < rows_out + 6) {
-          const uint32_t* w = &raw_w[(b + 1) * kFtRawW + q];
+          const uint32_t* w = &raw_w[(b + 1) * kFtRawPW + kFtRawOrg + q];
           const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
           // output X0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
           const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     const bool score_all = lo > 126;  // thresholds beyond the byte trick: score everything
     const int wl = wc > 0 ? -1 : 0, wr = wc < kFtRawW - 1 ? 1 : 0;
     const int rr0 = rg * kFtStrip;
-    const uint32_t* row = &raw_w[(rr0 + 3) * kFtRawW + wc];
+    const uint32_t* row = &raw_w[(rr0 + 3) * kFtRawPW + kFtRawOrg + wc];
     uint32_t keep[kFtStrip];
     int cnt = 0;
 #pragma unroll
@@ -218,9 +221,9 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
       const int rr = rr0 + i, y = Y0 - 1 + rr;
       uint32_t k = 0;
       if (lane_mask && rr < kFtScH && y >= kEdge && y < L.h - kEdge) {
-        const uint32_t* rp = row + i * kFtRawW;
+        const uint32_t* rp = row + i * kFtRawPW;
         const uint32_t c = rp[0];
-        const uint32_t up = rp[-3 * kFtRawW], dn = rp[3 * kFtRawW];
+        const uint32_t up = rp[-3 * kFtRawPW], dn = rp[3 * kFtRawPW];
         const uint32_t lf = __byte_perm(rp[wl], c, 0x4321);   // pixels x-3
         const uint32_t rt = __byte_perm(c, rp[wr], 0x6543);   // pixels x+3
         k = (exceeds4(dn, c, kthr) | exceeds4(up, c, kthr)) & (exceeds4(rt, c, kthr) | exceeds4(lf, c, kthr));
@@ -262,11 +265,11 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   const int nl = n_list;
   for (int i = tid; i < nl; i += 256) {
     const int rr = list[i] >> 8, cb = list[i] & 255;
-    const uint8_t* c = &raw[(rr + 3) * kFtPitch + cb];
+    const uint8_t* c = &raw[(rr + 3) * kFtRawPitch + cb + 4 * kFtRawOrg];
     const int dxs[16] = ORBX_RING_DX, dys[16] = ORBX_RING_DY;
     int r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtPitch + dxs[k]];
+    for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtRawPitch + dxs[k]];
     const int s = fast9_score(c[0], r, lo);
     if (s > 0) score[rr * kFtPitch + cb] = (uint8_t)s;
   }
