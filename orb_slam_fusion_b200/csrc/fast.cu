@@ -95,8 +95,16 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
                    "r"(ok ? 16 : 0));
     }
     asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   }
+  // (while the copies are in flight)
+  if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
+    const int m = (X0 - 4 + tid - kEdge + 64 * L.wcell) % L.wcell;
+    xedge[tid] = (uint8_t)((m == 0) | ((m == L.wcell - 1) << 1));
+  } else if (tid < kFtPitch + kFtScH) {
+    const int m = (Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell) % L.hcell;
+    yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
   __syncthreads();
   {
     uint8_t* rawb = reinterpret_cast<uint8_t*>(raw_w);
@@ -184,13 +192,6 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   __syncthreads();  // tmp is dead: its memory becomes the score map and the lists
 
   if (tid == 0) { n_list = 0; n_out = 0; }
-  if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
-    const int m = (X0 - 4 + tid - kEdge + 64 * L.wcell) % L.wcell;
-    xedge[tid] = (uint8_t)((m == 0) | ((m == L.wcell - 1) << 1));
-  } else if (tid < kFtPitch + kFtScH) {
-    const int m = (Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell) % L.hcell;
-    yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
-  }
   for (int i = tid; i < kFtScH * kFtRawW; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
   __syncthreads();
 

@@ -13,12 +13,14 @@ namespace orbx {
 // Copies the caller's frames into the padded level-0 planes.  16 bytes per thread.
 __global__ void __launch_bounds__(256) k_import(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                 const uint8_t* __restrict__ src, size_t row_stride,
-                                                size_t frame_stride, int aligned16) {
-  const int f = blockIdx.z;
-  const int y = blockIdx.y;
-  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+                                                size_t frame_stride, int aligned16, int chunks_per_row) {
+  // one thread per 16-byte chunk of a frame (rows x chunks flattened, so narrow images still fill the CTAs)
+  const int f = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const LevelGeom& L = g.lv[0];
-  if (x >= L.w) return;
+  const int y = i / chunks_per_row;
+  if (y >= L.h) return;
+  const int x = (i - y * chunks_per_row) * 16;
   const uint8_t* s = src + (size_t)f * frame_stride + (size_t)y * row_stride + x;
   uint8_t* d = pyr + (size_t)f * g.pyr_frame_bytes + px_off(L, x, y);
   if (x + 16 <= L.w) {
@@ -42,8 +44,9 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ FrameGeo
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
                   size_t frame_stride, int frames, cudaStream_t st) {
   const int aligned = ((reinterpret_cast<uintptr_t>(src) | row_stride | frame_stride) & 15) == 0;
-  dim3 grid((g.lv[0].w + 16 * 256 - 1) / (16 * 256), g.lv[0].h, frames);
-  k_import<<<grid, 256, 0, st>>>(g, b.pyr, src, row_stride, frame_stride, aligned);
+  const int cpr = (g.lv[0].w + 15) / 16;
+  dim3 grid((cpr * g.lv[0].h + 255) / 256, frames);
+  k_import<<<grid, 256, 0, st>>>(g, b.pyr, src, row_stride, frame_stride, aligned, cpr);
   return 1;
 }
 
