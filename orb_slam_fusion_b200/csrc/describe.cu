@@ -18,6 +18,16 @@ namespace orbx {
 __constant__ int8_t c_pattern[1024] = {
 #include "../../include/orb_pattern31.inc"
 };
+// the same pattern as floats, transposed: entry [k][L] = (x0, y0, x1, y1) of bit k of descriptor byte L, so that a
+// warp reads one coalesced 512-byte line per bit (filled once per device by k_pattern_init)
+__device__ float4 g_pattern_f[8 * 32];
+__global__ void k_pattern_init() {
+  const int t = threadIdx.x;  // 256 threads = 32 bytes x 8 bits
+  const int L = t >> 3, k = t & 7;
+  const int8_t* p = &c_pattern[(L * 8 + k) * 4];
+  g_pattern_f[k * 32 + L] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+}
+
 // umax_ of orb_extractor.cc:452-464 for kHalfPatchSize = 15
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
@@ -98,22 +108,15 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
                                                               const uint8_t* __restrict__ sel_sc, const int32_t* __restrict__ n_sel,
                                                               const int32_t* __restrict__ work, orbx_kp* __restrict__ kps,
                                                               uint8_t* __restrict__ desc, int cap, int out_frame0) {
-  // pattern as floats, transposed so that lane L reads entry [k][L] = (x0, y0, x1, y1) of bit k of byte L
-  __shared__ float4 pat[8][32];
   // per warp: the 37 x 37 blurred patch around the keypoint, rows of kPatchPitch bytes
   __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  {
-    const int L = tid >> 3, k = tid & 7;  // 256 threads = 32 bytes x 8 bits
-    const int8_t* p = &c_pattern[(L * 8 + k) * 4];
-    pat[k][L] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
-  }
-  __syncthreads();
   const int f = blockIdx.y;
   const int s = blockIdx.x * kDescWarps + wid;  // position in the frame's selected list
   if (s >= g.sel_frame_cap) return;
   int lev = 0;
-  while (lev + 1 < g.nlev && s >= g.lv[lev + 1].sel_off) lev++;
+#pragma unroll
+  for (int l = 1; l < ORBX_MAX_LEVELS; l++) lev += (l < g.nlev && s >= g.lv[l].sel_off);  // static parameter offsets
   const LevelGeom& L = g.lv[lev];
   const int pitch = L.pitch;  // level fields live in the parameter bank behind a run-time index: read once
   const int idx = s - L.sel_off;
@@ -145,23 +148,32 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
     asm volatile("cp.async.commit_group;\n" ::);
   }
 
-  // ---- IC_Angle (:76-100): lane = column u, loop over rows v
-  const int u = lane - kHalfPatch;
-  const int au = u < 0 ? -u : u;
+  // ---- IC_Angle (:76-100): m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  The 31 rows are read as
+  // aligned 32-bit words (9 per row cover any alignment): item = (row v, word wc), 279 items over the 32
+  // lanes = 9 loads per lane instead of 31 byte loads; DP4A with per-byte weights (u inside the disc, else 0).
   int m10 = 0, m01 = 0;
-  if (lane < kPatch) {
-    // walk down the column with one pointer increment per row; rows with umax[|v|] < |u| are skipped
-    const uint8_t* p = pyr + fo + px_off(L, cx + u, cy - kHalfPatch);
+  {
+    const int xa = (cx - kHalfPatch) & ~3, a = (cx - kHalfPatch) - xa;  // aligned start, 0..3 bytes before the patch
+    const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);
 #pragma unroll
-    for (int v = -kHalfPatch; v <= kHalfPatch; v++) {
-      const int av = v < 0 ? -v : v;
-      const int um = av <= 3 ? 15 : (av <= 6 ? 14 : (av <= 8 ? 13 : (av == 9 ? 12 : (av == 10 ? 11 : (av == 11 ? 10 : (av == 12 ? 9 : (av == 13 ? 8 : (av == 14 ? 6 : 3))))))));
-      if (au <= um) {
-        const int val = __ldg(p);
-        m10 += u * val;
-        m01 += v * val;
+    for (int t = 0; t < (31 * 9 + 31) / 32; t++) {
+      const int i = lane + 32 * t;
+      if (i < 31 * 9) {
+        const int r = i / 9, wc = i - r * 9;
+        const int v = r - kHalfPatch, av = v < 0 ? -v : v;
+        const int d = c_umax[av];
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + r * pitch) + wc);
+        const int u0 = 4 * wc - a - kHalfPatch;  // u of byte 0 of this word
+        uint32_t wu = 0, wm = 0;                 // per-byte weights inside the disc: u + 16 (1..31, unsigned) and 1
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int u = u0 + j;
+          if (u >= -d && u <= d) { wu |= (uint32_t)(u + 16) << (8 * j); wm |= 1u << (8 * j); }
+        }
+        const int s0 = (int)__dp4a(w, wm, 0u), s1 = (int)__dp4a(w, wu, 0u);  // sum I, sum (u + 16) * I
+        m10 += s1 - 16 * s0;
+        m01 += v * s0;
       }
-      p += pitch;
     }
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);  // REDUX.SUM: one instruction instead of a 5-step shuffle tree
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   uint32_t byte = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const float4 p = pat[k][lane];
+    const float4 p = __ldg(&g_pattern_f[k * 32 + lane]);
     int r0, c0, r1, c1;  // orb_extractor.cc:108-113: row = cvRound(x*b + y*a), col = cvRound(x*a - y*b), float32, no FMA
     rbrief_offset_f(a, b, p.x, p.y, r0, c0);
     rbrief_offset_f(a, b, p.z, p.w, r1, c1);
@@ -207,6 +219,11 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
     }
     reinterpret_cast<float*>(kps + o)[lane] = v;
   }
+}
+
+int launch_pattern_init(cudaStream_t st) {
+  k_pattern_init<<<1, 256, 0, st>>>();
+  return 1;
 }
 
 int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_kp* kps, uint8_t* desc, int cap,

@@ -228,6 +228,8 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   if (octree_smem_bytes(node_cap) > 200 * 1024)
     return fail(h, ORBX_E_UNSUPPORTED, "per-level quota %d needs more shared memory than one SM has", node_cap);
   CU(h, octree_configure(node_cap));
+  h->launches += launch_pattern_init(h->slot[0].stream);
+  CU(h, cudaStreamSynchronize(h->slot[0].stream));
 
   // resize tables: per level xofs[w], xalpha[2w], yofs[2h], ybeta[2h], all at tab_off
   std::vector<int16_t> t((size_t)tab * 7, 0);

@@ -38,6 +38,7 @@ int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaSt
 int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // blur + FAST, one kernel
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+int launch_pattern_init(cudaStream_t st);  // fills the device-resident float pattern table (once per device / geometry)
 // writes frame f of the batch to kps[(out_frame0 + f) * cap + slot], n[out_frame0 + f], ...
 int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_kp* kps, uint8_t* desc,
                     int cap, int32_t* n, int32_t* n_mono, int out_frame0, cudaStream_t st);

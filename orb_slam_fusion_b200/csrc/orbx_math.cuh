@@ -53,10 +53,12 @@ ORBX_HD float f_div(float a, float b) {
   return a / b;
 #endif
 }
-// cvRound(float): round half to even
+// cvRound(float): round half to even.  On the device the conversion instruction (F2I) issues on the
+// quarter-rate XU pipe through the MIO queue; for |v| < 2^22 adding 1.5 * 2^23 rounds to the nearest
+// integer (ties to even, the FADD's own rounding) and leaves it in the low mantissa bits.
 ORBX_HD int f_round(float v) {
 #if defined(__CUDA_ARCH__)
-  return __float2int_rn(v);
+  return __float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000;
 #else
   return (int)lrintf(v);
 #endif
