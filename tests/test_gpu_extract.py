@@ -272,3 +272,42 @@ def test_config4_shaped_batch(P, oracle):
             rn, rk, rd = ref(oracle.blocks_v1(1280, 720, 1, f))
             assert int(n[j]) == len(rk) and k[j, :len(rk)].tobytes() == rk.tobytes()
             assert np.array_equal(desc[j, :len(rk)].cpu().numpy(), rd)
+
+
+def test_fuzz_geometries_and_parameters(P, oracle):
+    """Seeded fuzz: random image sizes (tile-boundary cases included), feature counts, level counts, scale
+    factors, thresholds and lapping areas; every output must equal the oracle's bit for bit."""
+    rng = np.random.default_rng(20261018)
+    done = 0
+    for trial in range(60):
+        nl = int(rng.integers(1, 9))
+        sf = float(rng.choice([1.1, 1.2, 1.2, 1.25, 1.5, 2.0]))
+        while 70 * sf ** (nl - 1) + 60 >= 780:
+            nl -= 1
+        top = sf ** (nl - 1)
+        w = int(rng.integers(int(70 * top) + 40, 1100))
+        h = int(rng.integers(int(70 * top) + 40, 800))
+        if trial % 4 == 0:
+            w = 128 * int(rng.integers(2, 8)) + int(rng.integers(0, 4))     # widths 0..3 px past a tile multiple
+        if trial % 5 == 0:
+            h = 32 * int(rng.integers(6, 20)) + int(rng.integers(0, 4))
+        if round((w / top - 32) / (h / top - 32)) < 1:                       # the reference divides by zero here
+            continue
+        nf = int(rng.integers(50, 3000))
+        ini, mn = int(rng.integers(5, 60)), int(rng.integers(2, 40))
+        lap = (int(rng.integers(0, w)), int(rng.integers(0, 2 * w))) if trial % 3 == 0 else (0, 0)
+        kind = "uniform" if trial % 7 == 0 else "blocks"
+        img = (oracle.uniform_v1 if kind == "uniform" else oracle.blocks_v1)(w, h, 100 + trial, trial)
+        if trial % 6 == 0:
+            img = (img // 4 + 96).astype(np.uint8)                           # low contrast: cells that need the retry
+        try:
+            ex = P.OrbExtractor(nf, sf, nl, ini, mn)
+            got = ex(img, None, lap)
+        except P.OrbxError as e:
+            assert e.code == -6, (trial, w, h, nl, sf, str(e))               # geometry the kernels reject (documented)
+            continue
+        ref = oracle.Extractor(nf, sf, nl, ini, mn, trig=oracle.TRIG_CR)
+        rn, rk, rd = ref(img, lap)
+        assert got[0] == rn and got[1].tobytes() == rk.tobytes() and np.array_equal(got[2], rd), (trial, w, h, nf, nl, sf, ini, mn, lap, kind)
+        done += 1
+    assert done >= 40
