@@ -173,6 +173,8 @@ cudaError_t dmalloc(Slot& s, T** p, size_t n) {
 // Geometry of all levels for a w x h input, device buffers for max_batch frames per slot.
 int ensure_geometry(orbx_t* h, int w, int hh) {
   if (h->geom_valid && h->g.w0 == w && h->g.h0 == hh) return ORBX_OK;
+  for (auto& s : h->slot)  // asynchronous calls may still be using the buffers of the old geometry
+    if (s.stream) CU(h, cudaStreamSynchronize(s.stream));
   free_geometry(h);
   if (w > 32767 || hh > 32767) return fail(h, ORBX_E_UNSUPPORTED, "image larger than 32767 px");
   FrameGeom g{};
