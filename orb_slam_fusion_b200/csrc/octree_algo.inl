@@ -85,12 +85,12 @@ OT_DEV void ot_excl_scan(int* a, int n) {
   for (int i = 0; i < n; i++) { int v = a[i]; a[i] = s; s += v; }
   a[n] = s;
 #else
-  __shared__ int warp_sums[32];
-  __shared__ int carry;
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += nt) {
+  // warp-shuffle scan; the running total lives in a register of every thread (read back from the
+  // last warp's sum), so a chunk of blockDim.x elements costs two barriers
+  __shared__ int warp_sums[2][32];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  int carry = 0, buf = 0;
+  for (int base = 0; base < n; base += nt, buf ^= 1) {
     const int i = base + tid;
     const int v = i < n ? a[i] : 0;
     int s = v;
@@ -99,23 +99,20 @@ OT_DEV void ot_excl_scan(int* a, int n) {
       const int t = __shfl_up_sync(0xffffffffu, s, o);
       if (lane >= o) s += t;
     }
-    if (lane == 31) warp_sums[wid] = s;
+    if (lane == 31) warp_sums[buf][wid] = s;
     __syncthreads();
-    if (wid == 0) {
-      int ws = lane < (nt >> 5) ? warp_sums[lane] : 0;
+    // every warp scans the (<= 16) warp totals itself: no second barrier, no broadcast through shared memory
+    int ws = lane < nw ? warp_sums[buf][lane] : 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, ws, o);
-        if (lane >= o) ws += t;
-      }
-      warp_sums[lane] = ws;  // inclusive sums of the warps
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, ws, o);
+      if (lane >= o) ws += t;
     }
-    __syncthreads();
-    const int before = carry + (wid ? warp_sums[wid - 1] : 0);
-    if (i < n) a[i] = before + s - v;
-    __syncthreads();
-    if (tid == 0) carry += warp_sums[(nt >> 5) - 1];
-    __syncthreads();
+    const int before_warp = __shfl_sync(0xffffffffu, ws, wid > 0 ? wid - 1 : 0);
+    const int total = __shfl_sync(0xffffffffu, ws, nw - 1);
+    if (i < n) a[i] = carry + (wid ? before_warp : 0) + s - v;
+    carry += total;
+    // warp_sums is double buffered, so the next chunk may overwrite the other buffer right away
   }
   if (tid == 0) a[n] = carry;
   __syncthreads();
