@@ -313,14 +313,15 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
         node_of[p] = totalc + w.newpos[i];
       }
     }
+    if (OT_TID0) sv[SV_TOEXP] = 0;
     OT_SYNC();
     const int n_new = totalc + (n - meff);
-    // nodes to expand next: fresh children with more than one point (:612-650)
-    OT_FOR(i, totalc) w.scan[i] = NCNT[i] > 1;
+    // nodes to expand next: fresh children with more than one point (:612-650).  Only their number is
+    // needed (the order comes from the ranks of the next pass): a count, not a scan.
+    OT_FOR(i, totalc) if (NCNT[i] > 1) ot_atomic_add(&sv[SV_TOEXP], 1);
     OT_SYNC();
-    ot_excl_scan(w.scan, totalc);
     if (OT_TID0) {
-      const int to_expand = w.scan[totalc];
+      const int to_expand = sv[SV_TOEXP];
       sv[SV_N] = n_new;
       sv[SV_F] = totalc;
       if (n_new >= quota || n_new == n) sv[SV_DONE] = 1;                 // :660 / :716
