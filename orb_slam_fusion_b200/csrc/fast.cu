@@ -31,6 +31,7 @@ constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the score pl
 constexpr int kFtRawPitch = 160;              // raw rows are ten 16-byte chunks from X0-16 (128-bit LDGSTS): column = cb + 12
 constexpr int kFtRawPW = kFtRawPitch / 4, kFtRawOrg = 3;  // words per raw row; raw word of stencil word 0
 constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
+static_assert(kFtRawPitch == kFastTileBoxW && kFtRawH == kFastTileBoxH, "TMA box of the host-side tensor maps");
 constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
 constexpr int kFtStrip = 5;                   // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
 constexpr int kFtMaxOut = 1536;               // NMS survivors of one tile (<= (64+4)*(16+2))
@@ -49,11 +50,15 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 7
 #endif
-__global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_constant__ FrameGeom g, const uint8_t* __restrict__ pyr,
+// q = v / d for 0 <= v < 2^15, d < 2^15 with rcp = ceil(2^32 / d) (host: LevelGeom::wcell_rcp / hcell_rcp)
+__device__ __forceinline__ int div_rcp(int v, uint32_t rcp) { return (int)__umulhi((uint32_t)v, rcp); }
+
+__global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_constant__ FrameGeom g, const CUtensorMap* __restrict__ pyr_maps,
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
-  __shared__ __align__(16) uint32_t raw_w[kFtRawH * kFtRawPW];
+  __shared__ __align__(128) uint32_t raw_w[kFtRawH * kFtRawPW];
+  __shared__ __align__(8) unsigned long long tile_bar;  // mbarrier the TMA tile load completes on
   // The blur's u16 intermediate and the detector's score map / lists are live in different phases
   // and share one buffer.
   constexpr int kScoreBytes = kFtScH * kFtPitch, kListBytes = 2 * kFtScH * kFtPitch, kOutBytes = 2 * kFtMaxOut;
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   uint8_t* score = u_mem;
   uint16_t* list = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes);   // (score row << 8) | byte column of pixels to score
   uint16_t* outl = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes + kListBytes);
-  uint16_t* tmp = reinterpret_cast<uint16_t*>(u_mem);                  // blur: (kFtH + 6) rows x kFtW u16
+  uint32_t* tmp2 = reinterpret_cast<uint32_t*>(u_mem);                 // blur: (kFtH + 6) / 2 row pairs x kFtW, (row 2p) | (row 2p+1) << 16
   __shared__ int n_list, n_out, out_base;
   __shared__ uint8_t xedge[kFtPitch], yedge[kFtScH];  // bit 0: first column / row of a cell, bit 1: last
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
@@ -78,34 +83,36 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   const int lo = min(g.ini_th, g.min_th);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
 
-  // ---- 1. raw tile: rows y = Y0-4 .. Y0+35, each ten 16-byte chunks from x = X0-16 (interior rows of the
-  // planes are 16-byte aligned), global -> shared with 128-bit LDGSTS; rows / chunks outside the plane are
-  // zero-filled.  The BORDER_REFLECT_101 halo the blur needs at the image edges (3 px) is patched in
-  // afterwards from the tile itself, only in edge tiles.
-  {
-    const unsigned sbase = (unsigned)__cvta_generic_to_shared(raw_w);
-    const uint8_t* src = pyr + fo + px_off(L, X0 - 16, Y0 - 4);
-    for (int i = tid; i < kFtRawH * (kFtRawPitch / 16); i += 256) {
-      const int r = i / (kFtRawPitch / 16), c = i - r * (kFtRawPitch / 16);
-      const int y = Y0 - 4 + r, x = X0 - 16 + 16 * c;
-      // the plane has 32 B left / >= 19 B right padding: chunks up to x < w + 3 are inside the row
-      const bool ok = y >= 0 && y < L.h && x < L.w + 3;
-      const uint8_t* gp = ok ? src + r * L.pitch + 16 * c : pyr + fo;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sbase + (unsigned)(r * kFtRawPitch + 16 * c)), "l"(gp),
-                   "r"(ok ? 16 : 0));
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
+  // ---- 1. raw tile: rows y = Y0-4 .. Y0+35, 160 bytes each from x = X0-16, fetched by ONE TMA tensor copy
+  // (cp.async.bulk.tensor over the level's padded plane [frame][row][byte]; the part of the box beyond the
+  // plane is zero-filled by the hardware).  What lies in the plane's padding is never used: the
+  // BORDER_REFLECT_101 halo the blur needs at the image edges (3 px) is patched in afterwards from the tile
+  // itself, only in edge tiles, and the detector stays 19 px inside.
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the initialised barrier is visible to the async proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(kFtRawH * kFtRawPitch) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(raw_w)),
+                 "l"(pyr_maps + lev), "r"(X0 - 16 + kPadX), "r"(Y0 - 4 + kPadY), "r"(f), "r"(bar)
+                 : "memory");
   }
-  // (while the copies are in flight)
+  // (while the copy is in flight)
   if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
-    const int m = (X0 - 4 + tid - kEdge + 64 * L.wcell) % L.wcell;
+    const int v = X0 - 4 + tid - kEdge + 64 * L.wcell, m = v - div_rcp(v, L.wcell_rcp) * L.wcell;
     xedge[tid] = (uint8_t)((m == 0) | ((m == L.wcell - 1) << 1));
   } else if (tid < kFtPitch + kFtScH) {
-    const int m = (Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell) % L.hcell;
+    const int v = Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell, m = v - div_rcp(v, L.hcell_rcp) * L.hcell;
     yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
   }
-  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  __syncthreads();
+  __syncthreads();  // every thread sees the initialised barrier
+  {
+    uint32_t done;
+    do {
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar) : "memory");
+    } while (!done);
+  }
   {
     uint8_t* rawb = reinterpret_cast<uint8_t*>(raw_w);
     const bool left = X0 == 0, right = X0 + kFtW + 3 > L.w, top = Y0 == 0, bottom = Y0 + kFtH + 3 > L.h;
@@ -130,48 +137,56 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 
   // ---- 1b. 7x7 Gaussian blur of the tile's owned pixels (clone() + GaussianBlur, orb_extractor.cc:1054-1055;
   // Q8.8 kernel [18,34,48,56,48,34,18]): horizontal pass with DP4A on funnel-shifted byte
-  // windows into u16, vertical pass with DP2A on the packed u16 pairs, 32-bit stores.
+  // windows into u16, stored as vertical PAIRS (row 2p | row 2p+1 << 16) so that the vertical pass is
+  // DP2A with two taps per instruction; 32-bit stores.
   {
     const int rows_out = min(kFtH, L.h - Y0), cols_out = min(kFtW, L.w - X0);
     const int q = tid & 31;
-    if (4 * q < cols_out) {  // horizontal: thread = (quad q, 5 of the rows_out + 6 rows); blur row b = raw row b + 1
+    if (4 * q < cols_out) {  // horizontal: thread = (quad q, row pairs warp, warp+8, warp+16); blur row b = raw row b + 1
       const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
-      const int b0 = (tid >> 5) * 5;
 #pragma unroll
-      for (int i = 0; i < 5; i++) {
-        const int b = b0 + i;
-        if (b < rows_out + 6) {
-          const uint32_t* w = &raw_w[(b + 1) * kFtRawPW + kFtRawOrg + q];
-          const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-          // output X0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
-          const uint32_t h0 = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
-          const uint32_t h1 = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
-          const uint32_t h2 = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
-          const uint32_t h3 = __dp4a(w1, ka, __dp4a(w2, kb, 0u));
-          *reinterpret_cast<uint2*>(&tmp[b * kFtW + 4 * q]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));  // <= 255*256
+      for (int i = 0; i < 3; i++) {
+        const int pr = (tid >> 5) + 8 * i;
+        if (2 * pr < rows_out + 6) {
+          uint32_t hv[2][4];
+#pragma unroll
+          for (int e = 0; e < 2; e++) {
+            const uint32_t* w = &raw_w[(2 * pr + e + 1) * kFtRawPW + kFtRawOrg + q];
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            // output X0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
+            hv[e][0] = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
+            hv[e][1] = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
+            hv[e][2] = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
+            hv[e][3] = __dp4a(w1, ka, __dp4a(w2, kb, 0u));  // each <= 255*256
+          }
+          *reinterpret_cast<uint4*>(&tmp2[pr * kFtW + 4 * q]) =
+              make_uint4(hv[0][0] | (hv[1][0] << 16), hv[0][1] | (hv[1][1] << 16), hv[0][2] | (hv[1][2] << 16), hv[0][3] | (hv[1][3] << 16));
         }
       }
     }
     __syncthreads();
     const int yy0 = (tid >> 5) * 4;
-    if (4 * q < cols_out && yy0 < rows_out) {  // vertical: thread = (quad q, 4 output rows), 10 rows read once
+    if (4 * q < cols_out && yy0 < rows_out) {  // vertical: thread = (quad q, 4 output rows), 5 row pairs read once
+      // output row yy0+o reads rows yy0+o .. yy0+o+6: for even o the pairs p = o/2 .. o/2+3 with taps
+      // (18,34)(48,56)(48,34)(18,0), for odd o the same pairs with taps (0,18)(34,48)(56,48)(34,18)
+      constexpr uint32_t ke[4] = {18u | (34u << 8), 48u | (56u << 8), 48u | (34u << 8), 18u};
+      constexpr uint32_t ko[4] = {18u << 8, 34u | (48u << 8), 56u | (48u << 8), 34u | (18u << 8)};
       uint32_t acc[4][4];
 #pragma unroll
       for (int o = 0; o < 4; o++)
 #pragma unroll
         for (int k = 0; k < 4; k++) acc[o][k] = 32768u;
-      const uint32_t kv[7] = {18, 34, 48, 56, 48, 34, 18};
 #pragma unroll
-      for (int j = 0; j < 10; j++) {
-        const uint2 v = *reinterpret_cast<const uint2*>(&tmp[min(yy0 + j, kFtH + 5) * kFtW + 4 * q]);
+      for (int pj = 0; pj < 5; pj++) {
+        const uint4 v = *reinterpret_cast<const uint4*>(&tmp2[(yy0 / 2 + pj) * kFtW + 4 * q]);
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int o = 0; o < 4; o++) {
-          const int tap = j - o;
-          if (tap >= 0 && tap < 7) {
-            acc[o][0] = __dp2a_lo(v.x, kv[tap], acc[o][0]);        // low u16 x k
-            acc[o][1] = __dp2a_lo(v.x, kv[tap] << 8, acc[o][1]);   // high u16 x k
-            acc[o][2] = __dp2a_lo(v.y, kv[tap], acc[o][2]);
-            acc[o][3] = __dp2a_lo(v.y, kv[tap] << 8, acc[o][3]);
+          const int t = pj - o / 2;
+          if (t >= 0 && t < 4) {
+            const uint32_t kk = (o & 1) ? ko[t] : ke[t];
+#pragma unroll
+            for (int k = 0; k < 4; k++) acc[o][k] = __dp2a_lo(vv[k], kk, acc[o][k]);
           }
         }
       }
@@ -180,7 +195,8 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 #pragma unroll
       for (int o = 0; o < 4; o++) {
         if (yy0 + o < rows_out) {
-          const uint32_t packed = (acc[o][0] >> 16) | ((acc[o][1] >> 16) << 8) | ((acc[o][2] >> 16) << 16) | ((acc[o][3] >> 16) << 24);
+          // byte 2 of each accumulator (< 2^24) is the rounded result
+          const uint32_t packed = __byte_perm(__byte_perm(acc[o][0], acc[o][1], 0x0062), __byte_perm(acc[o][2], acc[o][3], 0x0062), 0x5410);
           uint8_t* dp = d + o * L.pitch;
           *reinterpret_cast<uint32_t*>(dp) = packed;  // <= 3 bytes of a straddling quad land in unused row padding
         }
@@ -192,7 +208,8 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   __syncthreads();  // tmp is dead: its memory becomes the score map and the lists
 
   if (tid == 0) { n_list = 0; n_out = 0; }
-  for (int i = tid; i < kFtScH * kFtRawW; i += 256) reinterpret_cast<uint32_t*>(score)[i] = 0;
+  static_assert(kScoreBytes % 16 == 0, "score map is cleared with 128-bit stores");
+  for (int i = tid; i < kScoreBytes / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   // ---- 2. rejection test, four pixels per thread, + warp compaction.
@@ -262,27 +279,41 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   }
   __syncthreads();
 
-  // ---- 3. dense scoring of the compacted list (response = best - 1, 0 if not a corner at `lo`)
+  // ---- 3. dense scoring of the compacted list (response = best - 1, 0 if not a corner at `lo`).
+  // Warp w owns the contiguous segment [w*seg, (w+1)*seg) of the list and compacts it in place to the
+  // owned pixels that are corners, so that the NMS pass below only runs on those.
   const int nl = n_list;
-  for (int i = tid; i < nl; i += 256) {
-    const int rr = list[i] >> 8, cb = list[i] & 255;
-    const uint8_t* c = &raw[(rr + 3) * kFtRawPitch + cb + 4 * kFtRawOrg];
-    const int dxs[16] = ORBX_RING_DX, dys[16] = ORBX_RING_DY;
-    int r[16];
+  const int seg = (nl + 7) >> 3, s_beg = (tid >> 5) * seg, s_end = min(nl, s_beg + seg);
+  int s_cur = s_beg;
+  for (int i0 = s_beg; i0 < s_end; i0 += 32) {
+    const int i = i0 + lane;
+    bool corner = false;
+    uint16_t item = 0;
+    if (i < s_end) {
+      item = list[i];
+      const int rr = item >> 8, cb = item & 255;
+      const uint8_t* c = &raw[(rr + 3) * kFtRawPitch + cb + 4 * kFtRawOrg];
+      const int dxs[16] = ORBX_RING_DX, dys[16] = ORBX_RING_DY;
+      int r[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtRawPitch + dxs[k]];
-    const int s = fast9_score(c[0], r, lo);
-    if (s > 0) score[rr * kFtPitch + cb] = (uint8_t)s;
+      for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtRawPitch + dxs[k]];
+      const int sc = fast9_score(c[0], r, lo);
+      if (sc > 0) {
+        score[rr * kFtPitch + cb] = (uint8_t)sc;
+        corner = rr >= 1 && rr <= kFtH && cb >= 4 && cb < 4 + kFtW;  // not a halo pixel
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, corner);  // every lane has read its item
+    if (corner) list[s_cur + __popc(bal & ((1u << lane) - 1u))] = item;
+    s_cur += __popc(bal);
   }
   __syncthreads();
 
-  // ---- 4. NMS of the owned pixels; neighbours across a cell edge count as 0
-  for (int i = tid; i < nl; i += 256) {
+  // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0
+  for (int i = s_beg + lane; i < s_cur; i += 32) {
     const int rr = list[i] >> 8, cb = list[i] & 255;
-    if (rr < 1 || rr > kFtH || cb < 4 || cb >= 4 + kFtW) continue;  // halo pixel
     const uint8_t* sp = &score[rr * kFtPitch + cb];
     const int s = sp[0];
-    if (s == 0) continue;
     const int xe = xedge[cb], ye = yedge[rr];
     const bool l_ok = !(xe & 1), r_ok = !(xe & 2), u_ok = !(ye & 1), d_ok = !(ye & 2);
     bool is_max = (!l_ok || s > sp[-1]) && (!r_ok || s > sp[1]) && (!u_ok || s > sp[-kFtPitch]) && (!d_ok || s > sp[kFtPitch]);
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     const int rr = outl[i] >> 8, cb = outl[i] & 255;
     const int s = score[rr * kFtPitch + cb];
     const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
-    const int cell = ((y - kEdge) / L.hcell) * L.ncols + (x - kEdge) / L.wcell;
+    const int cell = div_rcp(y - kEdge, L.hcell_rcp) * L.ncols + div_rcp(x - kEdge, L.wcell_rcp);
     const int pos = out_base + i;
     if (pos < L.cand_cap) {
       // coordinates relative to (16,16) as orb_extractor.cc:816-823
@@ -321,7 +352,7 @@ int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStrea
   cudaMemsetAsync(b.n_cand, 0, sizeof(int32_t) * ORBX_MAX_LEVELS * (size_t)frames, st);
   cudaMemsetAsync(b.cell_strong, 0, sizeof(int32_t) * (size_t)g.total_cells * frames, st);
   dim3 grid(g.total_blur_tiles, 1, frames);
-  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
+  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
   return 1;
 }
 

@@ -170,6 +170,32 @@ cudaError_t dmalloc(Slot& s, T** p, size_t n) {
   return e;
 }
 
+// TMA descriptor of one level's padded planes: u8 tensor [frames][rows][pitch], box = the 160 x 40 tile of
+// k_fast_blur (fast.cu).  The encoder is a driver entry point; it is fetched at run time so the library
+// does not link libcuda.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int rows, int frames, size_t frame_bytes) {
+  static encode_tiled_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return fail(h, ORBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    enc = (encode_tiled_fn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)frames};
+  const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_bytes};  // bytes, multiples of 16
+  const cuuint32_t box[3] = {(cuuint32_t)kFastTileBoxW, (cuuint32_t)kFastTileBoxH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return ORBX_OK;
+}
+
 // Geometry of all levels for a w x h input, device buffers for max_batch frames per slot.
 int ensure_geometry(orbx_t* h, int w, int hh) {
   if (h->geom_valid && h->g.w0 == w && h->g.h0 == hh) return ORBX_OK;
@@ -193,6 +219,8 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
       return fail(h, ORBX_E_UNSUPPORTED, "level %d (%dx%d) is smaller than one 35-px FAST cell plus borders", l, L.w, L.h);
     L.wcell = (int)ceilf(width / L.ncols);
     L.hcell = (int)ceilf(height / L.nrows);
+    L.wcell_rcp = (uint32_t)((0x100000000ull + (uint64_t)L.wcell - 1) / (uint64_t)L.wcell);
+    L.hcell_rcp = (uint32_t)((0x100000000ull + (uint64_t)L.hcell - 1) / (uint64_t)L.hcell);
     L.pitch = (kPadX + L.w + kEdge + 15) / 16 * 16;
     L.plane_off = plane;
     plane += (L.pitch * (L.h + 2 * kPadY) + 255) / 256 * 256;
@@ -265,6 +293,17 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   for (auto& s : h->slot) {
     CU(h, dmalloc(s, &s.b.pyr, B * plane + 256));   // + slack: 16-byte tile loads may run past the last row
     CU(h, dmalloc(s, &s.b.blur, B * plane + 256));
+    {
+      CUtensorMap maps[ORBX_MAX_LEVELS];
+      for (int l = 0; l < g.nlev; l++) {
+        const int rc = encode_plane_map(h, &maps[l], s.b.pyr + g.lv[l].plane_off, g.lv[l].pitch, g.lv[l].h + 2 * kPadY, (int)B, (size_t)plane);
+        if (rc != ORBX_OK) return rc;
+      }
+      CUtensorMap* dm = nullptr;
+      CU(h, dmalloc(s, &dm, (size_t)g.nlev));
+      CU(h, cudaMemcpy(dm, maps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));
+      s.b.pyr_maps = dm;
+    }
     CU(h, dmalloc(s, &s.b.cand_raw_xy, B * cand));
     CU(h, dmalloc(s, &s.b.cand_raw_sc, B * cand));
     CU(h, dmalloc(s, &s.b.cell_strong, B * cells));

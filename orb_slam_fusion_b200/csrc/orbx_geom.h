@@ -36,6 +36,7 @@ struct LevelGeom {
   int tab_off;        // offset of this level's resize tables (entries) in the table arrays
   int blur_tiles_x;   // 128x32 blur tiles across / tile prefix over lower levels
   int blur_tile_base;
+  uint32_t wcell_rcp, hcell_rcp;  // ceil(2^32 / wcell), ceil(2^32 / hcell): exact division of small ints by one IMAD.HI
   int pad_;
 };
 

@@ -1,6 +1,7 @@
 // orbx_kernels.cuh -- internal launch interface between the C ABI (orbx_api.cu) and the kernels.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,8 +29,11 @@ struct BatchBuffers {
   const int16_t* xalpha; // 2 coefficients per destination column
   const int16_t* yofs;   // source row of destination row (already clamped pair in yofs2)
   const int16_t* ybeta;  // 2 coefficients per destination row
+  const CUtensorMap* pyr_maps;  // [nlev] TMA descriptors of the pyramid planes: u8 [frame][padded row][padded byte]
   const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
 };
+
+constexpr int kFastTileBoxW = 160, kFastTileBoxH = 40;  // bytes x rows of the raw tile k_fast_blur fetches by TMA
 
 // Each launcher enqueues on `st` and returns the number of kernels it launched.
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,

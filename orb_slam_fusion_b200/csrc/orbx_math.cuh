@@ -129,6 +129,25 @@ ORBX_HD int imax3(int a, int b, int c) {
 // Returns 0 when the pixel is not a corner at threshold t (best <= t).
 // Sliding 9-window minima / maxima by composition of 3-windows: 16 + 16 three-input ops each.
 ORBX_HD int fast9_score(int c, const int (&r)[16], int t) {
+#if defined(__CUDA_ARCH__)
+  // Both halves of the test in one pass of 16-bit SIMD (VIMNMX3.S16x2): word k holds
+  // (r[k] - c) in the high half and (c - r[k] + 256) in the low half -- one IMAD, the bias keeps the low
+  // half positive so nothing borrows.  min over an arc of the high half is -max_arc(c - r).
+  const uint32_t bias = (uint32_t)(c + 256) - ((uint32_t)c << 16);
+  uint32_t D[16], A[16], B[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) D[k] = (uint32_t)r[k] * 0xFFFFu + bias;
+#pragma unroll
+  for (int k = 0; k < 16; k++) A[k] = __vimin3_s16x2(D[k], D[(k + 1) & 15], D[(k + 2) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) B[k] = __vimin3_s16x2(A[k], A[(k + 3) & 15], A[(k + 6) & 15]);
+  uint32_t m = __vimax3_s16x2(B[0], B[1], B[2]);
+#pragma unroll
+  for (int k = 3; k < 15; k += 2) m = __vimax3_s16x2(m, B[k], B[k + 1]);
+  m = __vmaxs2(m, B[15]);
+  const int best2 = imax((int)(m & 0xFFFFu) - 256, ((int)m) >> 16);
+  return best2 > t ? best2 - 1 : 0;
+#else
   int d[16], a[16], b[16];
 #pragma unroll
   for (int k = 0; k < 16; k++) d[k] = c - r[k];
@@ -150,6 +169,7 @@ ORBX_HD int fast9_score(int c, const int (&r)[16], int t) {
   worst = imin(worst, b[15]);
   best = imax(best, -worst);
   return best > t ? best - 1 : 0;
+#endif
 }
 
 // ---- bilinear resize, 8U fixed point -----------------------------------
