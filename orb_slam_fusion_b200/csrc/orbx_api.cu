@@ -170,13 +170,13 @@ cudaError_t dmalloc(Slot& s, T** p, size_t n) {
   return e;
 }
 
-// TMA descriptor of one level's padded planes: u8 tensor [frames][rows][pitch], box = the 160 x 40 tile of
-// k_fast_blur (fast.cu).  The encoder is a driver entry point; it is fetched at run time so the library
+// TMA descriptor of one level's padded planes: u8 tensor [frames][rows][pitch], box = the tile a CTA of
+// k_fast_blur (fast.cu) or k_resize_tma (pyramid.cu) fetches.  The encoder is a driver entry point; it is fetched at run time so the library
 // does not link libcuda.
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int rows, int frames, size_t frame_bytes) {
+int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int rows, int frames, size_t frame_bytes, int box_w, int box_h) {
   static encode_tiled_fn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -188,7 +188,7 @@ int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int row
   }
   const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)frames};
   const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_bytes};  // bytes, multiples of 16
-  const cuuint32_t box[3] = {(cuuint32_t)kFastTileBoxW, (cuuint32_t)kFastTileBoxH, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -296,9 +296,24 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     {
       CUtensorMap maps[ORBX_MAX_LEVELS];
       for (int l = 0; l < g.nlev; l++) {
-        const int rc = encode_plane_map(h, &maps[l], s.b.pyr + g.lv[l].plane_off, g.lv[l].pitch, g.lv[l].h + 2 * kPadY, (int)B, (size_t)plane);
+        const int rc = encode_plane_map(h, &maps[l], s.b.pyr + g.lv[l].plane_off, g.lv[l].pitch, g.lv[l].h + 2 * kPadY, (int)B, (size_t)plane,
+                                        kFastTileBoxW, kFastTileBoxH);
         if (rc != ORBX_OK) return rc;
       }
+      CUtensorMap rmaps[ORBX_MAX_LEVELS];
+      memset(rmaps, 0, sizeof(rmaps));
+      for (int l = 1; l < g.nlev; l++) {
+        int th, bw, bh;
+        resize_tile_plan(g, l, &th, &bw, &bh);
+        if (!bw) continue;
+        const int rc = encode_plane_map(h, &rmaps[l], s.b.pyr + g.lv[l - 1].plane_off, g.lv[l - 1].pitch, g.lv[l - 1].h + 2 * kPadY, (int)B,
+                                        (size_t)plane, bw, bh);
+        if (rc != ORBX_OK) return rc;
+      }
+      CUtensorMap* drm = nullptr;
+      CU(h, dmalloc(s, &drm, (size_t)g.nlev));
+      CU(h, cudaMemcpy(drm, rmaps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));
+      s.b.rs_maps = drm;
       CUtensorMap* dm = nullptr;
       CU(h, dmalloc(s, &dm, (size_t)g.nlev));
       CU(h, cudaMemcpy(dm, maps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));

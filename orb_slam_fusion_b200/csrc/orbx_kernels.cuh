@@ -30,6 +30,7 @@ struct BatchBuffers {
   const int16_t* yofs;   // source row of destination row (already clamped pair in yofs2)
   const int16_t* ybeta;  // 2 coefficients per destination row
   const CUtensorMap* pyr_maps;  // [nlev] TMA descriptors of the pyramid planes: u8 [frame][padded row][padded byte]
+  const CUtensorMap* rs_maps;   // [nlev] entry l: planes of level l-1 with the source box of k_resize_tma's tiles (resize_tile_plan)
   const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
 };
 
@@ -39,6 +40,8 @@ constexpr int kFastTileBoxW = 160, kFastTileBoxH = 40;  // bytes x rows of the r
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
                   size_t frame_stride, int frames, cudaStream_t st);
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
+// tile plan of the resize of level `lev`: output rows per tile, TMA box (bytes x rows) of the source tile; bw == 0: no TMA
+void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh);
 int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // blur + FAST, one kernel
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);

@@ -201,15 +201,161 @@ __global__ void __launch_bounds__(256, ORBX_RS_MINB) k_resize(const __grid_const
   }
 }
 
+// TMA variant of the same tile (the common case: the source columns of 128 outputs fit BW <= 256 bytes).
+// The source rows [row_lo, row_lo + bh) x [sx_lo, sx_lo + BW) of the tile arrive by ONE tensor copy
+// (cp.async.bulk.tensor over level lev-1's padded planes; the box size is part of the level's tensor map,
+// see resize_tile_plan); what the box covers beyond the plane is zero-filled and only ever multiplied
+// by a zero coefficient.  Dynamic shared memory: bh x BW source bytes, then bh x 128 u16 of H>>4.
+// The innermost TMA coordinate must put the box on a 16-byte boundary of the row (an unaligned start
+// faults with "illegal instruction" on sm_100a), so the box starts at the source column rounded down to 16.
+constexpr int kRsSrcAlign = 15, kRsBwSmall = 176;
+#ifndef ORBX_RS_TMA_MINB
+#define ORBX_RS_TMA_MINB 5
+#endif
+template <int BW>
+__global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
+                                                    const CUtensorMap* __restrict__ rs_maps, const int16_t* __restrict__ xofs,
+                                                    const int16_t* __restrict__ xalpha, const int16_t* __restrict__ yofs,
+                                                    const int16_t* __restrict__ ybeta, int lev, int th, int bh) {
+  extern __shared__ uint8_t rs_smem[];
+  // the TMA destination must be 128-byte aligned; the dynamic region is only 16-byte aligned when the
+  // kernel also has static shared memory, so the base is rounded up here (the launch adds 128 bytes)
+  uint8_t* src_sm = rs_smem + ((128u - ((unsigned)__cvta_generic_to_shared(rs_smem) & 127u)) & 127u);
+  uint16_t* hq = reinterpret_cast<uint16_t*>(src_sm + ((bh * BW + 127) & ~127));
+  unsigned long long& tile_bar = *reinterpret_cast<unsigned long long*>(hq + bh * kRsTW);
+  const LevelGeom& D = g.lv[lev];
+  const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
+  const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
+  const int t = D.tab_off, tid = threadIdx.x;
+  uint8_t* frame = pyr + (size_t)blockIdx.z * g.pyr_frame_bytes;
+  const int row_lo = yofs[2 * (t + y0)], row_hi = yofs[2 * (t + y1 - 1) + 1];
+  const int n_rows = min(row_hi - row_lo + 1, bh);
+  const int sx_lo = xofs[t + x0] & ~kRsSrcAlign;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bh * BW) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(src_sm)),
+                 "l"(rs_maps + lev), "r"(sx_lo + kPadX), "r"(row_lo + kPadY), "r"((int)blockIdx.z), "r"(bar)
+                 : "memory");
+  }
+
+  // ---- horizontal pass: thread = (quad q of output columns, the warp's share of the source rows); the
+  // column tables are read once per thread while the tile is in flight
+  {
+    const int rpg = (n_rows + 7) >> 3;
+    const int q = tid & 31, r0 = (tid >> 5) * rpg;
+    const int dx0 = x0 + 4 * q;
+    const bool active = dx0 < D.w && r0 < n_rows;
+    int sxs[4] = {0, 0, 0, 0}, a0s[4] = {0, 0, 0, 0}, a1s[4] = {0, 0, 0, 0};
+    if (active) {
+      if (dx0 + 4 <= D.w) {
+        const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
+        const int4 al = *reinterpret_cast<const int4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column
+        sxs[0] = sx.x; sxs[1] = sx.y; sxs[2] = sx.z; sxs[3] = sx.w;
+        const int als[4] = {al.x, al.y, al.z, al.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { a0s[k] = (int)(int16_t)(als[k] & 0xFFFF); a1s[k] = als[k] >> 16; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (dx0 + k < D.w) {
+            sxs[k] = xofs[t + dx0 + k];
+            a0s[k] = xalpha[2 * (t + dx0 + k)];
+            a1s[k] = xalpha[2 * (t + dx0 + k) + 1];
+          } else {
+            sxs[k] = sx_lo;
+          }
+        }
+      }
+    }
+    __syncthreads();  // every thread sees the initialised barrier
+    {
+      uint32_t done;
+      do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(bar) : "memory");
+      } while (!done);
+    }
+    if (active) {
+      const uint8_t* sp = src_sm + r0 * BW - sx_lo;
+      const uint8_t* p0 = sp + sxs[0];
+      const uint8_t* p1 = sp + sxs[1];
+      const uint8_t* p2 = sp + sxs[2];
+      const uint8_t* p3 = sp + sxs[3];
+#pragma unroll
+      for (int i = 0; i < (kRsRows + 7) / 8; i++) {
+        if (i < rpg && r0 + i < n_rows) {
+          const uint32_t o0 = (uint32_t)((p0[i * BW] * a0s[0] + p0[i * BW + 1] * a1s[0]) >> 4);
+          const uint32_t o1 = (uint32_t)((p1[i * BW] * a0s[1] + p1[i * BW + 1] * a1s[1]) >> 4);
+          const uint32_t o2 = (uint32_t)((p2[i * BW] * a0s[2] + p2[i * BW + 1] * a1s[2]) >> 4);
+          const uint32_t o3 = (uint32_t)((p3[i * BW] * a0s[3] + p3[i * BW + 1] * a1s[3]) >> 4);
+          *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows).  (b * h) >> 16 is the high word of
+  // b * (h << 16): one IMAD.HI per product, the second one adds the first.
+  {
+    constexpr int kVRows = kRsMaxTH / 8;
+    const int q = tid & 31, yy0 = (tid >> 5) * kVRows;
+    const int dx0 = x0 + 4 * q;
+    if (dx0 < D.w) {
+      uint8_t* d = frame + px_off(D, dx0, y0 + yy0);
+#pragma unroll
+      for (int i = 0; i < kVRows; i++) {
+        const int dy = y0 + yy0 + i;
+        if (dy < y1) {
+          const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));   // (row0 | row1 << 16)
+          const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));  // (b0 | b1 << 16), both in [0, 2048]
+          const int r0 = (int)(yo & 0xFFFF) - row_lo, r1 = (int)(yo >> 16) - row_lo;
+          const uint32_t b0 = yb & 0xFFFFu, b1 = yb >> 16;
+          const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
+          const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
+          // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
+          // cv::resize can never clip and is not spelled out
+          const uint32_t v0 = (__umulhi(b1, u1.x << 16) + (__umulhi(b0, u0.x << 16) + 2u)) >> 2;
+          const uint32_t v1 = (__umulhi(b1, u1.x & 0xFFFF0000u) + (__umulhi(b0, u0.x & 0xFFFF0000u) + 2u)) >> 2;
+          const uint32_t v2 = (__umulhi(b1, u1.y << 16) + (__umulhi(b0, u0.y << 16) + 2u)) >> 2;
+          const uint32_t v3 = (__umulhi(b1, u1.y & 0xFFFF0000u) + (__umulhi(b0, u0.y & 0xFFFF0000u) + 2u)) >> 2;
+          // a quad that straddles the right edge spills <= 3 bytes into the row padding, which nothing
+          // reads before k_border rewrites it
+          *reinterpret_cast<uint32_t*>(d + i * D.pitch) = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
+        }
+      }
+    }
+  }
+}
+
+void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh) {
+  // rows per tile so that the source rows of a tile fit the shared buffer (any scale factor)
+  const double ry = (double)g.lv[lev - 1].h / g.lv[lev].h, rx = (double)g.lv[lev - 1].w / g.lv[lev].w;
+  int t = (int)((kRsRows - 3) / ry);
+  t = t < 1 ? 1 : (t > kRsMaxTH ? kRsMaxTH : t);
+  *th = t;
+  // source span of 128 output columns / t output rows: first tap of the first .. second tap of the last
+  const int need_w = (int)ceil(127.0 * rx) + 3 + kRsSrcAlign, need_h = (int)ceil((t - 1) * ry) + 3;
+  *bw = need_w <= kRsBwSmall ? kRsBwSmall : (need_w <= 256 ? 256 : 0);  // 0: the LDGSTS / gather kernel
+  *bh = need_h < kRsRows ? need_h : kRsRows;
+}
+
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   int n = 0;
   for (int lev = 1; lev < g.nlev; lev++) {
-    // rows per tile so that the source rows of a tile fit the shared buffer (any scale factor)
-    const double ratio = (double)g.lv[lev - 1].h / g.lv[lev].h;
-    int th = (int)((kRsRows - 3) / ratio);
-    th = th < 1 ? 1 : (th > kRsMaxTH ? kRsMaxTH : th);
+    int th, bw, bh;
+    resize_tile_plan(g, lev, &th, &bw, &bh);
     dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-    k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
+    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 2 + 16;  // alignment slack, tile, H rows, mbarrier
+    if (bw == kRsBwSmall)
+      k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+    else if (bw == 256)
+      k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+    else
+      k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
     n++;
   }
   return n;
