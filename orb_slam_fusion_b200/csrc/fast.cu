@@ -43,6 +43,8 @@ __device__ __forceinline__ uint32_t exceeds4(uint32_t a, uint32_t b, uint32_t k)
   return (((d & 0x7f7f7f7fu) + k) | d) & 0x80808080u;
 }
 
+#define G4(a, b, c, d) ((uint32_t)(a) | ((uint32_t)(b) << 8) | ((uint32_t)(c) << 16) | ((uint32_t)(d) << 24))
+
 __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one fold (|overshoot| < len)
   return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
 }
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   uint16_t* outl = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes + kListBytes);
   uint32_t* tmp2 = reinterpret_cast<uint32_t*>(u_mem);                 // blur: (kFtH + 6) / 2 row pairs x kFtW, (row 2p) | (row 2p+1) << 16
   __shared__ int n_list, n_out, out_base;
-  __shared__ uint8_t xedge[kFtPitch], yedge[kFtScH];  // bit 0: first column / row of a cell, bit 1: last
+  __shared__ uint8_t xmask_l[kFtPitch], xmask_r[kFtPitch], ymask_u[kFtScH], ymask_d[kFtScH];  // 0 where the neighbour lies in another cell, else 255
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
   // tile -> (level, tile column, tile row), precomputed on the host
@@ -101,10 +103,12 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   // (while the copy is in flight)
   if (tid < kFtPitch) {  // cell edges of the tile's columns / rows (NMS does not look across them)
     const int v = X0 - 4 + tid - kEdge + 64 * L.wcell, m = v - div_rcp(v, L.wcell_rcp) * L.wcell;
-    xedge[tid] = (uint8_t)((m == 0) | ((m == L.wcell - 1) << 1));
+    xmask_l[tid] = m == 0 ? 0 : 255;            // first column of a cell: no left neighbour
+    xmask_r[tid] = m == L.wcell - 1 ? 0 : 255;  // last column: no right neighbour
   } else if (tid < kFtPitch + kFtScH) {
     const int v = Y0 - 1 + (tid - kFtPitch) - kEdge + 64 * L.hcell, m = v - div_rcp(v, L.hcell_rcp) * L.hcell;
-    yedge[tid - kFtPitch] = (uint8_t)((m == 0) | ((m == L.hcell - 1) << 1));
+    ymask_u[tid - kFtPitch] = m == 0 ? 0 : 255;
+    ymask_d[tid - kFtPitch] = m == L.hcell - 1 ? 0 : 255;
   }
   __syncthreads();  // every thread sees the initialised barrier
   {
@@ -143,7 +147,6 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     const int rows_out = min(kFtH, L.h - Y0), cols_out = min(kFtW, L.w - X0);
     const int q = tid & 31;
     if (4 * q < cols_out) {  // horizontal: thread = (quad q, row pairs warp, warp+8, warp+16); blur row b = raw row b + 1
-      const uint32_t ka = 18u | (34u << 8) | (48u << 16) | (56u << 24), kb = 48u | (34u << 8) | (18u << 16);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         const int pr = (tid >> 5) + 8 * i;
@@ -153,11 +156,12 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
           for (int e = 0; e < 2; e++) {
             const uint32_t* w = &raw_w[(2 * pr + e + 1) * kFtRawPW + kFtRawOrg + q];
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-            // output X0+4q+j is centred on raw byte 4q+4+j: taps 0..3 start at byte 4q+1+j, taps 4..6 at 4q+5+j
-            hv[e][0] = __dp4a(__funnelshift_r(w0, w1, 8), ka, __dp4a(__funnelshift_r(w1, w2, 8), kb, 0u));
-            hv[e][1] = __dp4a(__funnelshift_r(w0, w1, 16), ka, __dp4a(__funnelshift_r(w1, w2, 16), kb, 0u));
-            hv[e][2] = __dp4a(__funnelshift_r(w0, w1, 24), ka, __dp4a(__funnelshift_r(w1, w2, 24), kb, 0u));
-            hv[e][3] = __dp4a(w1, ka, __dp4a(w2, kb, 0u));  // each <= 255*256
+            // output X0+4q+j is centred on raw byte 4q+4+j (byte 0 = w0's first): taps t = 0..6 on bytes 4q+1+j+t.
+            // The taps are shifted inside the coefficient words instead of shifting the pixels.
+            hv[e][0] = __dp4a(w0, G4(0, 18, 34, 48), __dp4a(w1, G4(56, 48, 34, 18), 0u));
+            hv[e][1] = __dp4a(w0, G4(0, 0, 18, 34), __dp4a(w1, G4(48, 56, 48, 34), __dp4a(w2, G4(18, 0, 0, 0), 0u)));
+            hv[e][2] = __dp4a(w0, G4(0, 0, 0, 18), __dp4a(w1, G4(34, 48, 56, 48), __dp4a(w2, G4(34, 18, 0, 0), 0u)));
+            hv[e][3] = __dp4a(w1, G4(18, 34, 48, 56), __dp4a(w2, G4(48, 34, 18, 0), 0u));  // each <= 255*256
           }
           *reinterpret_cast<uint4*>(&tmp2[pr * kFtW + 4 * q]) =
               make_uint4(hv[0][0] | (hv[1][0] << 16), hv[0][1] | (hv[1][1] << 16), hv[0][2] | (hv[1][2] << 16), hv[0][3] | (hv[1][3] << 16));
@@ -280,16 +284,18 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   __syncthreads();
 
   // ---- 3. dense scoring of the compacted list (response = best - 1, 0 if not a corner at `lo`).
-  // Warp w owns the contiguous segment [w*seg, (w+1)*seg) of the list and compacts it in place to the
-  // owned pixels that are corners, so that the NMS pass below only runs on those.
+  // The list is cut in chunks of 32 items; warp w scores the chunks w, w+8, ... and packs the owned
+  // pixels that turn out to be corners back into ITS OWN chunks (already read), densely in that order:
+  // virtual slot v of warp w lives at chunk (v / 32) * 8 + w, lane v % 32.  The NMS pass below then runs
+  // on full warps of corners only.
   const int nl = n_list;
-  const int seg = (nl + 7) >> 3, s_beg = (tid >> 5) * seg, s_end = min(nl, s_beg + seg);
-  int s_cur = s_beg;
-  for (int i0 = s_beg; i0 < s_end; i0 += 32) {
-    const int i = i0 + lane;
+  const int wrp = tid >> 5;
+  int n_corner = 0;  // corners this warp has packed (warp-uniform)
+  for (int c0 = wrp * 32; c0 < nl; c0 += 256) {
+    const int i = c0 + lane;
     bool corner = false;
     uint16_t item = 0;
-    if (i < s_end) {
+    if (i < nl) {
       item = list[i];
       const int rr = item >> 8, cb = item & 255;
       const uint8_t* c = &raw[(rr + 3) * kFtRawPitch + cb + 4 * kFtRawOrg];
@@ -304,24 +310,28 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, corner);  // every lane has read its item
-    if (corner) list[s_cur + __popc(bal & ((1u << lane) - 1u))] = item;
-    s_cur += __popc(bal);
+    if (corner) {
+      const int v = n_corner + __popc(bal & ((1u << lane) - 1u));
+      list[((v >> 5) << 8) + (wrp << 5) + (v & 31)] = item;
+    }
+    n_corner += __popc(bal);
   }
   __syncthreads();
 
-  // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0
-  for (int i = s_beg + lane; i < s_cur; i += 32) {
-    const int rr = list[i] >> 8, cb = list[i] & 255;
+  // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0 (byte masks per column / row)
+  for (int v = lane; v < n_corner; v += 32) {
+    const uint16_t item = list[((v >> 5) << 8) + (wrp << 5) + (v & 31)];
+    const int rr = item >> 8, cb = item & 255;
     const uint8_t* sp = &score[rr * kFtPitch + cb];
     const int s = sp[0];
-    const int xe = xedge[cb], ye = yedge[rr];
-    const bool l_ok = !(xe & 1), r_ok = !(xe & 2), u_ok = !(ye & 1), d_ok = !(ye & 2);
-    bool is_max = (!l_ok || s > sp[-1]) && (!r_ok || s > sp[1]) && (!u_ok || s > sp[-kFtPitch]) && (!d_ok || s > sp[kFtPitch]);
-    is_max = is_max && (!(l_ok && u_ok) || s > sp[-kFtPitch - 1]) && (!(r_ok && u_ok) || s > sp[-kFtPitch + 1]) &&
-             (!(l_ok && d_ok) || s > sp[kFtPitch - 1]) && (!(r_ok && d_ok) || s > sp[kFtPitch + 1]);
-    if (is_max) {
+    const int ml = xmask_l[cb], mr = xmask_r[cb], mu = ymask_u[rr], md = ymask_d[rr];
+    int m = imax3(sp[-1] & ml, sp[1] & mr, sp[-kFtPitch] & mu);
+    m = imax3(m, sp[kFtPitch] & md, sp[-kFtPitch - 1] & (ml & mu));
+    m = imax3(m, sp[-kFtPitch + 1] & (mr & mu), sp[kFtPitch - 1] & (ml & md));
+    m = imax(m, sp[kFtPitch + 1] & (mr & md));
+    if (s > m) {
       const int o = atomicAdd(&n_out, 1);
-      if (o < kFtMaxOut) outl[o] = list[i];
+      if (o < kFtMaxOut) outl[o] = item;
     }
   }
   __syncthreads();
