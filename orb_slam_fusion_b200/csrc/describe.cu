@@ -18,6 +18,17 @@ namespace orbx {
 __constant__ int8_t c_pattern[1024] = {
 #include "../../include/orb_pattern31.inc"
 };
+// umax_ of orb_extractor.cc:452-464 for kHalfPatchSize = 15
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// IC_Angle as DP4A over aligned words: the 31 patch rows are read as 9 aligned 32-bit words each (any
+// alignment a = 0..3 of the patch's first column); item i = 9 * row + word.  Entry [a][i] holds the per-byte
+// weights of that word inside the radius-15 disc -- x: (u + 16) per byte (1..31, 0 outside), y: 1 per byte
+// inside -- and z: row | word << 8.  Filled once per device by k_pattern_init; 4 x 279 x 16 B = 17.9 KB,
+// read by every warp with one coalesced 128-bit load per item.
+constexpr int kOriItems = 31 * 9;
+__device__ uint4 g_ori_w[4 * kOriItems];
+
 // the same pattern as floats, transposed: entry [k][L] = (x0, y0, x1, y1) of bit k of descriptor byte L, so that a
 // warp reads one coalesced 512-byte line per bit (filled once per device by k_pattern_init)
 __device__ float4 g_pattern_f[8 * 32];
@@ -26,12 +37,21 @@ __global__ void k_pattern_init() {
   const int L = t >> 3, k = t & 7;
   const int8_t* p = &c_pattern[(L * 8 + k) * 4];
   g_pattern_f[k * 32 + L] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
+  for (int e = t; e < 4 * kOriItems; e += blockDim.x) {
+    const int a = e / kOriItems, i = e - a * kOriItems, r = i / 9, wc = i - r * 9;
+    const int v = r - kHalfPatch, d = c_umax[v < 0 ? -v : v];
+    const int u0 = 4 * wc - a - kHalfPatch;  // u of byte 0 of this word
+    uint32_t wu = 0, wm = 0;
+    for (int j = 0; j < 4; j++) {
+      const int u = u0 + j;
+      if (u >= -d && u <= d) { wu |= (uint32_t)(u + 16) << (8 * j); wm |= 1u << (8 * j); }
+    }
+    g_ori_w[e] = make_uint4(wu, wm, (uint32_t)r | ((uint32_t)wc << 8), 0u);
+  }
 }
 
-// umax_ of orb_extractor.cc:452-464 for kHalfPatchSize = 15
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-
 constexpr int kPlanThreads = 256;
+constexpr int kWorkLevShift = 24;  // work[] entry = output slot | level << 24 (slots < 2^24), or -1
 
 __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ sel_xy,
                                                        const int32_t* __restrict__ n_sel, int32_t* __restrict__ work,
@@ -56,6 +76,8 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
   __syncthreads();
   const int N = lev_start[g.nlev];
   int32_t* wk = work + (size_t)f * g.sel_frame_cap;
+  for (int i = tid; i < g.sel_frame_cap; i += kPlanThreads) wk[i] = -1;  // entries no keypoint owns
+  __syncthreads();
   const uint32_t* sxy = sel_xy + (size_t)f * g.sel_frame_cap;
   const bool fits = N <= cap && !bad;
   for (int base = 0; base < N; base += kPlanThreads) {
@@ -83,7 +105,7 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
     if (i < N) {
       // lapping keypoints fill the tail backwards (stereoIndex--), the rest the head (monoIndex++)
       const int slot = flag ? (N - 1 - laps_before) : (i - laps_before);
-      wk[g.lv[lev].sel_off + idx] = fits ? slot : -1;
+      wk[g.lv[lev].sel_off + idx] = fits ? (slot | (lev << kWorkLevShift)) : -1;  // k_describe reads slot and level from here
     }
     __syncthreads();
     if (tid == kPlanThreads - 1) carry = before + s;
@@ -114,16 +136,12 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   const int f = blockIdx.y;
   const int s = blockIdx.x * kDescWarps + wid;  // position in the frame's selected list
   if (s >= g.sel_frame_cap) return;
-  int lev = 0;
-#pragma unroll
-  for (int l = 1; l < ORBX_MAX_LEVELS; l++) lev += (l < g.nlev && s >= g.lv[l].sel_off);  // static parameter offsets
+  const size_t so = (size_t)f * g.sel_frame_cap + s;
+  const int wv = work[so];  // slot | level << 24 from k_plan; -1: no keypoint here (or it does not fit)
+  if (wv < 0) return;
+  const int slot = wv & ((1 << kWorkLevShift) - 1), lev = wv >> kWorkLevShift;
   const LevelGeom& L = g.lv[lev];
   const int pitch = L.pitch;  // level fields live in the parameter bank behind a run-time index: read once
-  const int idx = s - L.sel_off;
-  if (idx >= n_sel[f * ORBX_MAX_LEVELS + lev]) return;
-  const size_t so = (size_t)f * g.sel_frame_cap + s;
-  const int slot = work[so];
-  if (slot < 0) return;
   const uint32_t xy = sel_xy[so];
   const int cx = (int)(xy & 0xFFFFu), cy = (int)(xy >> 16);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
@@ -155,24 +173,17 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   {
     const int xa = (cx - kHalfPatch) & ~3, a = (cx - kHalfPatch) - xa;  // aligned start, 0..3 bytes before the patch
     const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);
+    const uint4* wt = g_ori_w + a * kOriItems;
 #pragma unroll
-    for (int t = 0; t < (31 * 9 + 31) / 32; t++) {
+    for (int t = 0; t < (kOriItems + 31) / 32; t++) {
       const int i = lane + 32 * t;
-      if (i < 31 * 9) {
-        const int r = i / 9, wc = i - r * 9;
-        const int v = r - kHalfPatch, av = v < 0 ? -v : v;
-        const int d = c_umax[av];
+      if (i < kOriItems) {
+        const uint4 e = __ldg(wt + i);
+        const int r = (int)(e.z & 255u), wc = (int)(e.z >> 8);
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + r * pitch) + wc);
-        const int u0 = 4 * wc - a - kHalfPatch;  // u of byte 0 of this word
-        uint32_t wu = 0, wm = 0;                 // per-byte weights inside the disc: u + 16 (1..31, unsigned) and 1
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const int u = u0 + j;
-          if (u >= -d && u <= d) { wu |= (uint32_t)(u + 16) << (8 * j); wm |= 1u << (8 * j); }
-        }
-        const int s0 = (int)__dp4a(w, wm, 0u), s1 = (int)__dp4a(w, wu, 0u);  // sum I, sum (u + 16) * I
+        const int s0 = (int)__dp4a(w, e.y, 0u), s1 = (int)__dp4a(w, e.x, 0u);  // sum I, sum (u + 16) * I
         m10 += s1 - 16 * s0;
-        m01 += v * s0;
+        m01 += (r - kHalfPatch) * s0;
       }
     }
   }

@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   uint8_t* src_sm = rs_smem + ((128u - ((unsigned)__cvta_generic_to_shared(rs_smem) & 127u)) & 127u);
   uint16_t* hq = reinterpret_cast<uint16_t*>(src_sm + ((bh * BW + 127) & ~127));
   unsigned long long& tile_bar = *reinterpret_cast<unsigned long long*>(hq + bh * kRsTW);
+  __shared__ uint2 row_tab[kRsMaxTH];
   const LevelGeom& D = g.lv[lev];
   const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
   const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
@@ -243,33 +244,43 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   }
 
   // ---- horizontal pass: thread = (quad q of output columns, the warp's share of the source rows); the
-  // column tables are read once per thread while the tile is in flight
+  // column tables are read once per thread while the tile is in flight.  The <= 8 source bytes a quad
+  // needs (scale < 2) are cut out of three aligned words per row as one 64-bit window; each output is
+  // then PRMT (its two neighbouring bytes) + DP2A with the packed coefficient pair (a0 | a1 << 16).
   {
     const int rpg = (n_rows + 7) >> 3;
     const int q = tid & 31, r0 = (tid >> 5) * rpg;
     const int dx0 = x0 + 4 * q;
     const bool active = dx0 < D.w && r0 < n_rows;
-    int sxs[4] = {0, 0, 0, 0}, a0s[4] = {0, 0, 0, 0}, a1s[4] = {0, 0, 0, 0};
+    int sx0 = sx_lo;
+    uint32_t al[4] = {0, 0, 0, 0}, sel[4] = {0x10, 0x10, 0x10, 0x10};
     if (active) {
+      int sxs[4];
       if (dx0 + 4 <= D.w) {
         const short4 sx = *reinterpret_cast<const short4*>(xofs + t + dx0);
-        const int4 al = *reinterpret_cast<const int4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column
+        const uint4 a4 = *reinterpret_cast<const uint4*>(xalpha + 2 * (t + dx0));  // (a0 | a1 << 16) per column, both in [0, 2048]
         sxs[0] = sx.x; sxs[1] = sx.y; sxs[2] = sx.z; sxs[3] = sx.w;
-        const int als[4] = {al.x, al.y, al.z, al.w};
-#pragma unroll
-        for (int k = 0; k < 4; k++) { a0s[k] = (int)(int16_t)(als[k] & 0xFFFF); a1s[k] = als[k] >> 16; }
+        al[0] = a4.x; al[1] = a4.y; al[2] = a4.z; al[3] = a4.w;
       } else {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          if (dx0 + k < D.w) {
-            sxs[k] = xofs[t + dx0 + k];
-            a0s[k] = xalpha[2 * (t + dx0 + k)];
-            a1s[k] = xalpha[2 * (t + dx0 + k) + 1];
-          } else {
-            sxs[k] = sx_lo;
-          }
+          const bool in = dx0 + k < D.w;
+          sxs[k] = xofs[t + (in ? dx0 + k : dx0)];
+          al[k] = in ? *reinterpret_cast<const uint32_t*>(xalpha + 2 * (t + dx0 + k)) : 0u;
         }
       }
+      sx0 = sxs[0];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint32_t dl = (uint32_t)(sxs[k] - sx0);  // 0..6
+        sel[k] = dl | ((dl + 1u) << 4);
+      }
+    }
+    if (tid < th) {  // the tile's row table for the vertical pass: (row0 | row1 << 16) relative to row_lo, (b0 | b1 << 16)
+      const int dy = min(y0 + tid, D.h - 1);
+      const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));
+      const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));
+      row_tab[tid] = make_uint2(yo - (uint32_t)row_lo * 0x10001u, yb);
     }
     __syncthreads();  // every thread sees the initialised barrier
     {
@@ -279,18 +290,17 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
       } while (!done);
     }
     if (active) {
-      const uint8_t* sp = src_sm + r0 * BW - sx_lo;
-      const uint8_t* p0 = sp + sxs[0];
-      const uint8_t* p1 = sp + sxs[1];
-      const uint8_t* p2 = sp + sxs[2];
-      const uint8_t* p3 = sp + sxs[3];
+      const int off = sx0 - sx_lo, sh = 8 * (off & 3);
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(src_sm + r0 * BW) + (off >> 2);
 #pragma unroll
       for (int i = 0; i < (kRsRows + 7) / 8; i++) {
         if (i < rpg && r0 + i < n_rows) {
-          const uint32_t o0 = (uint32_t)((p0[i * BW] * a0s[0] + p0[i * BW + 1] * a1s[0]) >> 4);
-          const uint32_t o1 = (uint32_t)((p1[i * BW] * a0s[1] + p1[i * BW + 1] * a1s[1]) >> 4);
-          const uint32_t o2 = (uint32_t)((p2[i * BW] * a0s[2] + p2[i * BW + 1] * a1s[2]) >> 4);
-          const uint32_t o3 = (uint32_t)((p3[i * BW] * a0s[3] + p3[i * BW + 1] * a1s[3]) >> 4);
+          const uint32_t w0 = wp[i * (BW / 4)], w1 = wp[i * (BW / 4) + 1], w2 = wp[i * (BW / 4) + 2];
+          const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // bytes sx0 .. sx0+7
+          const uint32_t o0 = __dp2a_lo(al[0], __byte_perm(lo, hi, sel[0]), 0u) >> 4;
+          const uint32_t o1 = __dp2a_lo(al[1], __byte_perm(lo, hi, sel[1]), 0u) >> 4;
+          const uint32_t o2 = __dp2a_lo(al[2], __byte_perm(lo, hi, sel[2]), 0u) >> 4;
+          const uint32_t o3 = __dp2a_lo(al[3], __byte_perm(lo, hi, sel[3]), 0u) >> 4;
           *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
         }
       }
@@ -299,7 +309,7 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   __syncthreads();
 
   // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows).  (b * h) >> 16 is the high word of
-  // b * (h << 16): one IMAD.HI per product, the second one adds the first.
+  // b * (h << 16): one IMAD.HI per product.
   {
     constexpr int kVRows = kRsMaxTH / 8;
     const int q = tid & 31, yy0 = (tid >> 5) * kVRows;
@@ -308,20 +318,18 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
       uint8_t* d = frame + px_off(D, dx0, y0 + yy0);
 #pragma unroll
       for (int i = 0; i < kVRows; i++) {
-        const int dy = y0 + yy0 + i;
-        if (dy < y1) {
-          const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));   // (row0 | row1 << 16)
-          const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));  // (b0 | b1 << 16), both in [0, 2048]
-          const int r0 = (int)(yo & 0xFFFF) - row_lo, r1 = (int)(yo >> 16) - row_lo;
-          const uint32_t b0 = yb & 0xFFFFu, b1 = yb >> 16;
+        if (y0 + yy0 + i < y1) {
+          const uint2 rt = row_tab[yy0 + i];
+          const int r0 = (int)(rt.x & 0xFFFFu), r1 = (int)(rt.x >> 16);
+          const uint32_t b0 = rt.y & 0xFFFFu, b1 = rt.y >> 16;
           const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
           const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
           // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
           // cv::resize can never clip and is not spelled out
-          const uint32_t v0 = (__umulhi(b1, u1.x << 16) + (__umulhi(b0, u0.x << 16) + 2u)) >> 2;
-          const uint32_t v1 = (__umulhi(b1, u1.x & 0xFFFF0000u) + (__umulhi(b0, u0.x & 0xFFFF0000u) + 2u)) >> 2;
-          const uint32_t v2 = (__umulhi(b1, u1.y << 16) + (__umulhi(b0, u0.y << 16) + 2u)) >> 2;
-          const uint32_t v3 = (__umulhi(b1, u1.y & 0xFFFF0000u) + (__umulhi(b0, u0.y & 0xFFFF0000u) + 2u)) >> 2;
+          const uint32_t v0 = (__umulhi(b1, u1.x << 16) + __umulhi(b0, u0.x << 16) + 2u) >> 2;
+          const uint32_t v1 = (__umulhi(b1, u1.x & 0xFFFF0000u) + __umulhi(b0, u0.x & 0xFFFF0000u) + 2u) >> 2;
+          const uint32_t v2 = (__umulhi(b1, u1.y << 16) + __umulhi(b0, u0.y << 16) + 2u) >> 2;
+          const uint32_t v3 = (__umulhi(b1, u1.y & 0xFFFF0000u) + __umulhi(b0, u0.y & 0xFFFF0000u) + 2u) >> 2;
           // a quad that straddles the right edge spills <= 3 bytes into the row padding, which nothing
           // reads before k_border rewrites it
           *reinterpret_cast<uint32_t*>(d + i * D.pitch) = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
