@@ -255,7 +255,58 @@ int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, u
  *   mode 2: 256-bit distances per second of the distance routine the kernels are built with. */
 int orbm_popc_peak(int device, int mode, double* per_s);
 
+/* ------------------------------------------------------------------ vocabulary (bag of words)
+ *
+ * Device-side replacement of the reference's ORBVocabulary = DBoW2::TemplatedVocabulary<FORB>
+ * (3rdparty/DBoW2/DBoW2/TemplatedVocabulary.h) for the calls on the data path:
+ *   loadFromTextFile                       TemplatedVocabulary.h:1246-1330  (system start-up)
+ *   transform(features, BowVector, FeatureVector, levelsup)   :1056-1118
+ *     = Frame::ComputeBoW / KeyFrame::ComputeBoW               src/map/frame.cc:761-766
+ *   transform(feature, word id, weight, node id, levelsup)     :1139-1179
+ * Results are identical to the reference's, doubles included (same operations in the same order). */
+
+typedef struct orbv_vocab orbv_t;
+
+/* Node arrays indexed by node id as loadFromTextFile numbers them (0 = root, then file order; entry 0 of
+ * every array is unused): parent id, leaf flag, 32-byte descriptor, weight.  Children are visited in
+ * increasing node id; leaves receive word ids in increasing node id.  scoring: 0 L1_NORM, 1 L2_NORM,
+ * 2 CHI_SQUARE, 3 KL, 4 BHATTACHARYYA, 5 DOT_PRODUCT; weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY
+ * (DBoW2/BowVector.h:31-44).  All arrays are HOST memory. */
+int orbv_create(int device, int k, int L, int scoring, int weighting, int32_t n_nodes, const int32_t* parent,
+                const uint8_t* is_leaf, const uint8_t* desc, const double* weight, orbv_t** out);
+/* The text format of loadFromTextFile / saveToTextFile ("k L scoring weighting", then one line per node:
+ * "parent isLeaf d0 .. d31 weight").  An empty last line is ignored (the reference's loader appends a
+ * phantom node with an unset descriptor there).  ORBX_E_ARG when the file cannot be read or the header
+ * is out of the reference's accepted range (:1267-1272). */
+int orbv_load_text(int device, const char* path, orbv_t** out);
+void orbv_destroy(orbv_t* v);
+const char* orbv_last_error(const orbv_t* v);
+int orbv_info(const orbv_t* v, int* k, int* L, int* scoring, int* weighting, int32_t* n_nodes, int32_t* n_words);
+int orbv_sync(orbv_t* v);
+long long orbv_launch_count(const orbv_t* v);
+/* largest `cap` orbv_transform accepts (the per-frame sort runs in shared memory) */
+int orbv_max_features(void);
+
+/* Per-feature descent (:1139-1179) for n descriptors: word id, word weight and the id of the node at
+ * level L - levelsup on the path (0 = root when that level is <= 0; when the path ends in a leaf above that
+ * level, where the reference leaves the value unset, that leaf). */
+int orbv_features(orbv_t* v, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* weight,
+                  uint32_t* node_id, int mem, void* stream);
+
+/* Batched transform(features, BowVector, FeatureVector, levelsup) over n_frames frames in the layout
+ * orbx_extract_batch produces: frame f owns desc[(f*cap + i)*32], i < n_per_frame[f] (negative counts = 0;
+ * n_per_frame may be NULL: every frame has cap features).  Outputs, all strided by cap per frame:
+ *   bow_ids / bow_vals [f*cap + j], j < bow_n[f]   the BowVector in increasing word id
+ *   fv_nodes / fv_begin [f*cap + j], j < fv_n[f]   FeatureVector node ids in increasing order and the start
+ *                                                  of each node's features inside the frame's fv_feats
+ *   fv_feats [f*cap + p], p < fv_total[f]          feature indices grouped by node, increasing in a group
+ * Features whose word weight is 0 ("stopped") take no part (:1084).  `mem` applies to every pointer. */
+int orbv_transform(orbv_t* v, const uint8_t* desc, int cap, const int32_t* n_per_frame, int n_frames, int levelsup,
+                   uint32_t* bow_ids, double* bow_vals, int32_t* bow_n, uint32_t* fv_nodes, int32_t* fv_begin,
+                   int32_t* fv_n, uint32_t* fv_feats, int32_t* fv_total, int mem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
+
 #endif

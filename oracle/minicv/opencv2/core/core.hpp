@@ -181,4 +181,6 @@ inline float fastAtan2(float y, float x) { return cvp_fast_atan2(y, x); }
 
 }  // namespace cv
 
+#include "persistence_stub.hpp"
+
 #endif

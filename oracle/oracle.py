@@ -37,7 +37,7 @@ WR_DTYPE = np.dtype([("best_dist", "<i4"), ("best_idx", "<i4"), ("best_level", "
 
 def build(force=False):
     so = os.path.join(_HERE, "liborb_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cvprim.c", "orb_oracle.c", "cvprim.h", "orb_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("cvprim.c", "orb_oracle.c", "cvprim.h", "orb_oracle.h", "bow_oracle.c", "bow_oracle.h")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "liborb_oracle.so"], stdout=subprocess.DEVNULL)
@@ -89,6 +89,18 @@ def lib():
             fn = getattr(L, name)
             fn.restype = rt
             fn.argtypes = at
+        L.orc_vocab_create.restype = vp
+        L.orc_vocab_create.argtypes = [i, i, i, i, i, vp, vp, vp, vp]
+        L.orc_vocab_load_text.restype = vp
+        L.orc_vocab_load_text.argtypes = [C.c_char_p]
+        L.orc_vocab_destroy.argtypes = [vp]
+        L.orc_vocab_nodes.argtypes = [vp]
+        L.orc_vocab_words.argtypes = [vp]
+        L.orc_vocab_arrays.argtypes = [vp] + [C.POINTER(i)] * 4 + [vp] * 4
+        L.orc_bow_features.argtypes = [vp, vp, i, i, vp, vp, vp]
+        L.orc_bow_transform.argtypes = [vp, vp, i, i, vp, vp, C.POINTER(i), vp, vp, C.POINTER(i), vp, C.POINTER(i)]
+        L.orc_synth_vocab.argtypes = [i, i, u64, vp, vp, vp, vp]
+        L.orc_vocab_save_text.argtypes = [C.c_char_p, i, i, i, i, i, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -364,3 +376,82 @@ def synth_descriptors(first, n, seed):
     out = np.empty((n, 32), np.uint8)
     lib().orc_synth_descriptors(_p(out), first, n, seed)
     return out
+
+
+# ---------------------------------------------------------------- bag of words (bow_oracle.c)
+def synth_vocab(k, L, seed=7):
+    """(parent, is_leaf, desc, weight) of the deterministic synthetic vocabulary tree, node-id indexed."""
+    n = lib().orc_synth_vocab(k, L, seed, None, None, None, None)
+    parent = np.zeros(n, np.int32)
+    leaf = np.zeros(n, np.uint8)
+    desc = np.zeros((n, 32), np.uint8)
+    weight = np.zeros(n, np.float64)
+    lib().orc_synth_vocab(k, L, seed, _p(parent), _p(leaf), _p(desc), _p(weight))
+    return parent, leaf, desc, weight
+
+
+def save_vocab_text(path, k, L, parent, leaf, desc, weight, scoring=0, weighting=0):
+    rc = lib().orc_vocab_save_text(os.fsencode(path), k, L, scoring, weighting, len(parent), _p(parent), _p(leaf),
+                                   _p(desc), _p(weight))
+    assert rc == 0
+
+
+def unpack_bow(n, ids, vals, nb, nodes, begin, nf, feats, total):
+    """Common result form: (word ids, values, node ids, [feature index arrays per node])."""
+    ends = list(begin[1:nf]) + [total]
+    return (ids[:nb].copy(), vals[:nb].copy(), nodes[:nf].copy(),
+            [feats[begin[j]:ends[j]].copy() for j in range(nf)])
+
+
+class Vocabulary:
+    """CPU restatement of DBoW2's TemplatedVocabulary<FORB> (load + transform)."""
+
+    def __init__(self, k=None, L=None, parent=None, leaf=None, desc=None, weight=None, scoring=0, weighting=0,
+                 path=None):
+        if path is not None:
+            self.h = lib().orc_vocab_load_text(os.fsencode(path))
+        else:
+            self.h = lib().orc_vocab_create(k, L, scoring, weighting, len(parent), _p(parent), _p(leaf), _p(desc),
+                                            _p(weight))
+        if not self.h:
+            raise ValueError("vocabulary could not be created / loaded")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_vocab_destroy(self.h)
+            self.h = None
+
+    @property
+    def n_nodes(self):
+        return lib().orc_vocab_nodes(self.h)
+
+    @property
+    def n_words(self):
+        return lib().orc_vocab_words(self.h)
+
+    def arrays(self):
+        n = self.n_nodes
+        k, L, sc, we = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        parent, leaf = np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        desc, weight = np.zeros((n, 32), np.uint8), np.zeros(n, np.float64)
+        lib().orc_vocab_arrays(self.h, C.byref(k), C.byref(L), C.byref(sc), C.byref(we), _p(parent), _p(leaf), _p(desc),
+                               _p(weight))
+        return k.value, L.value, sc.value, we.value, parent, leaf, desc, weight
+
+    def features(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid, w, nid = np.zeros(n, np.uint32), np.zeros(n, np.float64), np.zeros(n, np.uint32)
+        lib().orc_bow_features(self.h, _p(desc), n, levelsup, _p(wid), _p(w), _p(nid))
+        return wid, w, nid
+
+    def transform(self, desc, levelsup=4):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        ids, vals = np.zeros(m, np.uint32), np.zeros(m, np.float64)
+        nodes, begin, feats = np.zeros(m, np.uint32), np.zeros(m, np.int32), np.zeros(m, np.uint32)
+        nb, nf, tot = C.c_int(), C.c_int(), C.c_int()
+        lib().orc_bow_transform(self.h, _p(desc), n, levelsup, _p(ids), _p(vals), C.byref(nb), _p(nodes), _p(begin),
+                                C.byref(nf), _p(feats), C.byref(tot))
+        return unpack_bow(n, ids, vals, nb.value, nodes, begin, nf.value, feats, tot.value)

@@ -115,3 +115,65 @@ def knn2(q, d, nthreads=1):
     dist = np.empty((len(q), 2), np.int32)
     lib().ref_knn2(_p(q), len(q), _p(d), len(d), _p(idx), _p(dist), nthreads)
     return idx, dist
+
+
+# ---------------------------------------------------------------- the reference's DBoW2 (libbow_ref.so)
+_BOW_SO = os.path.join(_HERE, "_ref", "libbow_ref.so")
+_BOW = None
+
+
+def bow_available():
+    return available() and os.path.exists(_BOW_SO)
+
+
+def _bow():
+    global _BOW
+    if _BOW is None:
+        if not bow_available():
+            raise RuntimeError("oracle/_ref/libbow_ref.so not built (needs /root/reference)")
+        L = C.CDLL(_BOW_SO)
+        vp, i = C.c_void_p, C.c_int
+        L.refbow_load_text.restype = vp
+        L.refbow_load_text.argtypes = [C.c_char_p]
+        L.refbow_destroy.argtypes = [vp]
+        L.refbow_words.argtypes = [vp]
+        L.refbow_transform.argtypes = [vp, vp, i, i, vp, vp, C.POINTER(i), vp, vp, C.POINTER(i), vp, C.POINTER(i)]
+        L.refbow_words_of.argtypes = [vp, vp, i, vp]
+        _BOW = L
+    return _BOW
+
+
+class Vocabulary:
+    """The reference's ORBVocabulary (TemplatedVocabulary<FORB>) loaded with its own loadFromTextFile."""
+
+    def __init__(self, path):
+        self.h = _bow().refbow_load_text(os.fsencode(path))
+        if not self.h:
+            raise ValueError("loadFromTextFile failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            _bow().refbow_destroy(self.h)
+            self.h = None
+
+    @property
+    def n_words(self):
+        return _bow().refbow_words(self.h)
+
+    def words(self, desc):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        out = np.zeros(len(desc), np.uint32)
+        _bow().refbow_words_of(self.h, _p(desc), len(desc), _p(out))
+        return out
+
+    def transform(self, desc, levelsup=4):
+        from .oracle import unpack_bow
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        m = max(n, 1)
+        ids, vals = np.zeros(m, np.uint32), np.zeros(m, np.float64)
+        nodes, begin, feats = np.zeros(m, np.uint32), np.zeros(m, np.int32), np.zeros(m, np.uint32)
+        nb, nf, tot = C.c_int(), C.c_int(), C.c_int()
+        _bow().refbow_transform(self.h, _p(desc), n, levelsup, _p(ids), _p(vals), C.byref(nb), _p(nodes), _p(begin),
+                                C.byref(nf), _p(feats), C.byref(tot))
+        return unpack_bow(n, ids, vals, nb.value, nodes, begin, nf.value, feats, tot.value)

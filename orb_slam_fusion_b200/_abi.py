@@ -77,6 +77,16 @@ SIGNATURES = {
     "orbm_window_search": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, i32, vp]),
     "orbm_synth_descriptors": (i32, [i32, vp, i64, i64, u64, vp]),
     "orbm_popc_peak": (i32, [i32, i32, C.POINTER(dbl)]),
+    "orbv_create": (i32, [i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]),
+    "orbv_load_text": (i32, [i32, C.c_char_p, C.POINTER(vp)]),
+    "orbv_destroy": (None, [vp]),
+    "orbv_last_error": (C.c_char_p, [vp]),
+    "orbv_info": (i32, [vp, pi32, pi32, pi32, pi32, pi32, pi32]),
+    "orbv_sync": (i32, [vp]),
+    "orbv_launch_count": (C.c_longlong, [vp]),
+    "orbv_max_features": (i32, []),
+    "orbv_features": (i32, [vp, vp, i32, i32, vp, vp, vp, i32, vp]),
+    "orbv_transform": (i32, [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
 }
 
 _LIB = None

@@ -85,4 +85,26 @@ int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t se
 // mode 0: popc.b32 per second; 1: plain 8-popc distances per second; 2: ham256 as built, per second
 int popc_bench(int mode, double* per_s);
 
+
+// ---- vocabulary (bag of words) ----
+// Device view of a DBoW2 vocabulary tree, re-laid out in "slots": the children of every node occupy consecutive
+// slots (breadth-first), so one descent step reads <= k contiguous 32-byte rows.
+struct VocabDev {
+  const uint4* sdesc;     // [n_slots][2]  node descriptors
+  const int2* schild;     // [n_slots]     (first child slot, number of children); 0 children = leaf
+  const int32_t* snode;   // [n_slots]     node id in the reference's numbering (file order)
+  const int32_t* sword;   // [n_slots]     word id of a leaf (0 for inner nodes, like Node())
+  const double* sweight;  // [n_slots]
+  int root_beg, root_cnt; // the root's children
+  int L;                  // m_L: nominal depth, only used for the FeatureVector level (L - levelsup)
+};
+int bow_max_features();  // per frame (shared-memory sort)
+cudaError_t bow_configure();
+int launch_bow_descend(const VocabDev& v, const uint8_t* desc, int cap, const int32_t* n_per_frame, int n_frames, int levelsup,
+                       uint32_t* word_id, double* weight, uint32_t* node_id, cudaStream_t st);
+int launch_bow_frame(int cap, const int32_t* n_per_frame, int n_frames, int tf_weighting, int must_normalize, int l2_norm,
+                     const uint32_t* word_id, const double* weight, const uint32_t* node_id, uint32_t* bow_ids, double* bow_vals,
+                     int32_t* bow_n, uint32_t* fv_nodes, int32_t* fv_begin, int32_t* fv_n, uint32_t* fv_feats, int32_t* fv_total,
+                     cudaStream_t st);
+
 }  // namespace orbx

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def header_functions():
     src = open(os.path.join(ROOT, "include", "orbx.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return set(re.findall(r"\b(orb[xm]_[a-z0-9_]+)\s*\(", src))
+    return set(re.findall(r"\b(orb[xmv]_[a-z0-9_]+)\s*\(", src))
 
 
 def test_library_exports_every_declared_symbol():
@@ -29,7 +29,10 @@ def test_no_gpu_means_an_error_not_a_fallback():
     if torch.cuda.is_available():
         return
     import orb_slam_fusion_b200 as P
-    for make in (lambda: P.OrbExtractor(1000, 1.2, 8, 20, 7), lambda: P.ORBmatcher()):
+    import numpy as np
+    z = np.zeros(2, np.int32)
+    for make in (lambda: P.OrbExtractor(1000, 1.2, 8, 20, 7), lambda: P.ORBmatcher(),
+                 lambda: P.ORBVocabulary(2, 1, z, np.ones(2, np.uint8), np.zeros((2, 32), np.uint8), np.ones(2))):
         try:
             make()
         except P.OrbxError as e:
