@@ -52,6 +52,40 @@ def algorithmic_bytes(w, h, n_kp):
     }
 
 
+def synth_vocabulary(k, L, seed):
+    """ORBvoc-shaped synthetic vocabulary tree in breadth-first node order (numpy, seeded): node arrays as
+    orbv_create takes them.  A child's descriptor is its parent's with ~256 >> level bits flipped; leaf weights
+    are idf-like positive numbers, 1 in 29 words is stopped (weight 0)."""
+    rng = np.random.default_rng(seed)
+    total = (k ** (L + 1) - 1) // (k - 1)
+    parent = np.zeros(total, np.int32)
+    leaf = np.zeros(total, np.uint8)
+    desc = np.zeros((total, 32), np.uint8)
+    weight = np.zeros(total, np.float64)
+    first, prev_first, prev_n = 1, 0, 1
+    for lev in range(1, L + 1):
+        cnt = prev_n * k
+        ids = np.arange(first, first + cnt)
+        par = prev_first + (ids - first) // k
+        parent[ids] = par
+        if lev == 1:
+            desc[ids] = rng.integers(0, 256, (cnt, 32), dtype=np.uint8)
+        else:
+            d = desc[par].copy()
+            rows = np.arange(cnt)
+            for _ in range(256 >> lev):
+                pos = rng.integers(0, 256, cnt)
+                d[rows, pos >> 3] ^= (1 << (pos & 7)).astype(np.uint8)
+            desc[ids] = d
+        if lev == L:
+            leaf[ids] = 1
+            w = (rng.integers(1, 998, cnt)).astype(np.float64) / 64.0
+            w[28::29] = 0.0
+            weight[ids] = w
+        prev_first, prev_n, first = first, cnt, first + cnt
+    return parent, leaf, desc, weight
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -327,6 +361,45 @@ def run_ours(args):
                          "frac_of_popc_roofline": 8 * pairs_per_s / (world * popc),
                          "frac_of_plain_distance_peak": pairs_per_s / (world * plain)})
 
+    # ---- bag of words: Frame::ComputeBoW over this rank's batch of extracted descriptors,
+    # ORBvoc-shaped synthetic vocabulary (k=10, L=6), device-resident, frames sharded like the extraction
+    del db, q
+    vk, vL = 10, 6
+    vparent, vleaf, vdesc, vweight = synth_vocabulary(vk, vL, seed=7)
+    voc = P.ORBVocabulary(vk, vL, vparent, vleaf, vdesc, vweight, device=local)
+    for _ in range(2):
+        bow = voc.transform_batch(desc, n, 4)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(reps):
+        bow = voc.transform_batch(desc, n, 4)
+    b1.record()
+    torch.cuda.synchronize()
+    bow_ms = max_over_ranks(b0.elapsed_time(b1)) / reps
+    barrier()
+    bow_words = float(bow["bow_n"].float().mean().item())
+    bow_out = {"value": world * B / (bow_ms * 1e-3), "unit": "frames/s", "ms_per_batch": bow_ms,
+               "descriptors_per_s": world * float(n_host.sum()) / (bow_ms * 1e-3),
+               "mean_words_per_frame": bow_words,
+               "workload": "transform(features, BowVector, FeatureVector, 4) of %d frames x ~%d descriptors per rank, "
+                           "synthetic vocabulary k=10 L=6 (%d nodes), TF-IDF / L1" % (B, int(mean_kp), len(vparent))}
+    log('bag of words done')
+    if rank == 0 and world == 1:  # the CPU restatement of DBoW2 on one thread, bounded sample (checker side: oracle/)
+        from oracle import oracle as O
+        vo = O.Vocabulary(vk, vL, vparent, vleaf, vdesc, vweight)
+        d_host = desc[:32].cpu().numpy()
+        t0 = time.perf_counter()
+        for f in range(32):
+            ids, vals, nodes, feats = vo.transform(d_host[f, :n_host[f]], 4)
+        dt = time.perf_counter() - t0
+        nb = int(bow["bow_n"][31].item())
+        assert nb == len(ids) and np.array_equal(bow["bow_ids"][31, :nb].cpu().numpy().astype(np.uint32), ids)
+        assert bow["bow_vals"][31, :nb].cpu().numpy().tobytes() == vals.tobytes(), "bag of words != CPU oracle"
+        bow_out["cpu_baseline"] = {"value": 32 / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                                   "sample": "32 frames of this batch through oracle/bow_oracle.c (DBoW2 restatement)"}
+    del voc, bow
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -387,7 +460,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (%.0f MB of frames + %.1f GB working set per step)"
                          % (B * W * H / 1e6, B * 7.5e6 / 1e9)},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-        "p50_ms_per_frame": p50, "matching": matching,
+        "p50_ms_per_frame": p50, "matching": matching, "bow": bow_out,
     }
     print(json.dumps(out))
     if world > 1:

@@ -2,7 +2,7 @@
 // the reference's Frame does (frame.cc:467-476, 834, 1154), compiled against the mini-cv stand-in
 // for OpenCV (oracle/minicv, test infrastructure).  Writes its outputs to a binary file that
 // tests/test_cpp_facade.py compares with the oracle.
-//   facade_test <in.raw> <w> <h> <num_feats> <lap0> <lap1> <out.bin>
+//   facade_test <in.raw> <w> <h> <num_feats> <lap0> <lap1> <out.bin> [<vocabulary.txt>]
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -10,13 +10,14 @@
 
 #include "cam/orb_feature/orb_extractor.h"
 #include "cam/orb_feature/orb_matcher_gpu.h"
+#include "cam/orb_feature/orb_vocabulary_gpu.h"
 
 using namespace ORB_SLAM_FUSION;
 
 static void put(FILE* f, const void* p, size_t n) { fwrite(p, 1, n, f); }
 
 int main(int argc, char** argv) {
-  if (argc != 8) return 2;
+  if (argc != 8 && argc != 9) return 2;
   const int w = atoi(argv[2]), h = atoi(argv[3]), nf = atoi(argv[4]);
   std::vector<int> lap = {atoi(argv[5]), atoi(argv[6])};
   std::vector<uint8_t> buf((size_t)w * h);
@@ -62,6 +63,30 @@ int main(int argc, char** argv) {
   matcher.StereoRowBand(keys, desc, keys, desc, sf, h, 0.f, 40.f, bi, bd);
   put(fo, bi.data(), bi.size() * sizeof(int));
   put(fo, bd.data(), bd.size() * sizeof(int));
+  if (argc == 9) {
+    // Frame::ComputeBoW (frame.cc:761-766): toDescriptorVector + transform(vCurrentDesc, mBowVec, mFeatVec, 4)
+    ORBVocabularyGpu voc(0);
+    if (!voc.loadFromTextFile(argv[8])) return 4;
+    if (ORBVocabularyGpu(0).loadFromTextFile("/nonexistent/voc.txt")) return 5;
+    std::vector<cv::Mat> vdesc;
+    for (int i = 0; i < desc.rows; i++) vdesc.push_back(desc.row(i));
+    std::map<unsigned int, double> bow;
+    std::map<unsigned int, std::vector<unsigned int> > fvec;
+    voc.transform(vdesc, bow, fvec, 4);
+    const int32_t cnt[3] = {(int32_t)voc.size(), (int32_t)bow.size(), (int32_t)fvec.size()};
+    put(fo, cnt, sizeof(cnt));
+    for (std::map<unsigned int, double>::const_iterator it = bow.begin(); it != bow.end(); ++it) {
+      put(fo, &it->first, 4);
+      put(fo, &it->second, 8);
+    }
+    for (std::map<unsigned int, std::vector<unsigned int> >::const_iterator it = fvec.begin(); it != fvec.end(); ++it) {
+      const uint32_t hd[2] = {it->first, (uint32_t)it->second.size()};
+      put(fo, hd, sizeof(hd));
+      put(fo, it->second.data(), it->second.size() * 4);
+    }
+    const uint32_t w0 = desc.rows ? voc.transform(desc.row(0)) : 0;
+    put(fo, &w0, 4);
+  }
   fclose(fo);
   delete extractor;
   return 0;

@@ -23,6 +23,7 @@ def test_facade_compiles_and_links_against_the_c_abi():
     syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
     used = {l.split()[-1] for l in syms.splitlines() if " orbx_" in l or " orbm_" in l}
     assert {"orbx_create", "orbx_extract", "orbx_pyramid_level", "orbm_knn2", "orbm_stereo_rowband"} <= used
+    assert {"orbv_load_text", "orbv_transform"} <= {l.split()[-1] for l in syms.splitlines() if " orbv_" in l}
 
 
 @pytest.mark.gpu
@@ -32,7 +33,11 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     img = oracle.blocks_v1(w, h, 2, 4)
     raw, out = tmp_path / "in.raw", tmp_path / "out.bin"
     img.tofile(raw)
-    subprocess.check_call([exe, str(raw), str(w), str(h), str(nf), str(lap[0]), str(lap[1]), str(out)])
+    vk, vL = 6, 4
+    vparent, vleaf, vdesc, vweight = oracle.synth_vocab(vk, vL, seed=9)
+    voc_path = tmp_path / "voc.txt"
+    oracle.save_vocab_text(str(voc_path), vk, vL, vparent, vleaf, vdesc, vweight)
+    subprocess.check_call([exe, str(raw), str(w), str(h), str(nf), str(lap[0]), str(lap[1]), str(out), str(voc_path)])
     buf = out.read_bytes()
     hdr = np.frombuffer(buf, np.int32, 6)
     mono, n, drows, dcols, empty_rc, levels = (int(v) for v in hdr)
@@ -59,4 +64,17 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     bi = np.frombuffer(buf, np.int32, n, off); off += 4 * n
     bd = np.frombuffer(buf, np.int32, n, off); off += 4 * n
     wi, wd = oracle.stereo_rowband(rk, rd, rk, rd, sf, h, 0.0, 40.0)
-    assert np.array_equal(bi, wi) and np.array_equal(bd, wd) and off == len(buf)
+    assert np.array_equal(bi, wi) and np.array_equal(bd, wd)
+    # ORBVocabularyGpu::transform as Frame::ComputeBoW calls it
+    words, nb, nfv = (int(v) for v in np.frombuffer(buf, np.int32, 3, off)); off += 12
+    vo = oracle.Vocabulary(vk, vL, vparent, vleaf, vdesc, vweight)
+    ids, vals, nodes, feats = vo.transform(rd, 4)
+    assert (words, nb, nfv) == (vo.n_words, len(ids), len(nodes))
+    bow = np.frombuffer(buf, np.dtype([("id", "<u4"), ("v", "<f8")]), nb, off); off += 12 * nb
+    assert np.array_equal(bow["id"], ids) and bow["v"].tobytes() == np.ascontiguousarray(vals).tobytes()
+    for j in range(nfv):
+        node, cnt = (int(v) for v in np.frombuffer(buf, np.uint32, 2, off)); off += 8
+        fl = np.frombuffer(buf, np.uint32, cnt, off); off += 4 * cnt
+        assert node == nodes[j] and np.array_equal(fl, feats[j])
+    assert int(np.frombuffer(buf, np.uint32, 1, off)[0]) == int(vo.features(rd[:1])[0][0]); off += 4
+    assert off == len(buf)
