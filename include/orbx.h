@@ -245,6 +245,17 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
                        const uint8_t* qdesc, int nq, const uint8_t* skip, orbm_window_result* out,
                        int mem, void* stream);
 
+/* The same with the stereo gate the reference applies to keypoints that carry a right-image coordinate
+ * (orb_matcher.cc:89-92 in SearchByProjection(Frame, MapPoints): |mTrackProjXR - mvuRight[idx]| > r * scale;
+ * orb_matcher.cc:1586-1590 in SearchByProjection(CurrentFrame, LastFrame): |ur - mvuRight[i2]| > radius):
+ * keypoint i with kp_u_right[i] > 0 is skipped when |q_u_right[q] - kp_u_right[i]| > q_max_err[q].
+ * kp_u_right (n floats, Frame::mvuRight) may be NULL: then this is orbm_window_search. */
+int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n,
+                              const orbm_grid_geom* geom, const orbm_window_query* queries,
+                              const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right,
+                              const float* q_u_right, const float* q_max_err, orbm_window_result* out,
+                              int mem, void* stream);
+
 /* Deterministic synthetic descriptors: 64-bit word j of row i is
  * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);

@@ -74,6 +74,7 @@ def lib():
         L.orc_distinctive.argtypes = [vp, vp, i, vp, vp]
         L.orc_stereo_refine.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i, f, f, f, vp, vp, vp]
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
+        L.orc_window_search_stereo.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, vp]
         L.orc_splitmix64.restype = u64
         L.orc_splitmix64.argtypes = [u64]
         L.orc_synth_blocks_v1.argtypes = [vp, i, i, sz, u64, u64, i, u64]
@@ -341,16 +342,23 @@ def stereo_refine(levels_left, levels_right, kl, kr, best_idx, best_dist, scale_
     return ur, dp, sad
 
 
-def window_search(kps, desc, geom, queries, qdesc, skip=None):
+def window_search(kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q_u_right=None, q_max_err=None):
     kps = np.ascontiguousarray(kps, KP_DTYPE)
     desc = np.ascontiguousarray(desc, np.uint8)
     queries = np.ascontiguousarray(queries, WQ_DTYPE)
     qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
     out = np.empty(len(queries), WR_DTYPE)
     g = GridGeom(*geom)
-    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
-    lib().orc_window_search(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc),
-                            len(queries), None if sk is None else _p(sk), _p(out))
+    if kp_u_right is None:
+        lib().orc_window_search(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc),
+                                len(queries), None if sk is None else _p(sk), _p(out))
+    else:
+        ur = np.ascontiguousarray(kp_u_right, np.float32)
+        qr = np.ascontiguousarray(q_u_right, np.float32)
+        qe = np.ascontiguousarray(q_max_err, np.float32)
+        lib().orc_window_search_stereo(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc), len(queries),
+                                       None if sk is None else _p(sk), _p(ur), _p(qr), _p(qe), _p(out))
     return out
 
 

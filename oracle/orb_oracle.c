@@ -715,6 +715,13 @@ void orc_stereo_refine(const orc_level_view* left, const orc_level_view* right, 
 void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
                        const orc_window_query* q, const uint8_t* qdesc, int nq,
                        const uint8_t* skip, orc_window_result* out) {
+  orc_window_search_stereo(kps, desc, n, g, q, qdesc, nq, skip, NULL, NULL, NULL, out);
+}
+
+void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                              const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                              orc_window_result* out) {
   const int ncell = g->cols * g->rows;
   int* cnt = (int*)calloc((size_t)ncell + 1, sizeof(int));
   int* cell_of = (int*)malloc(sizeof(int) * (size_t)(n ? n : 1));
@@ -753,6 +760,10 @@ void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_
             const float dx = kps[i].x - x, dy = kps[i].y - y;
             if (!(fabsf(dx) < fr && fabsf(dy) < fr)) continue;
             if (skip && skip[i]) continue; /* orb_matcher.cc:86-87 "already matched" */
+            if (kp_u_right && kp_u_right[i] > 0) { /* stereo observation: orb_matcher.cc:89-92, 1586-1590 */
+              const float er = fabsf(q_u_right[qi] - kp_u_right[i]);
+              if (er > q_max_err[qi]) continue;
+            }
             const int dist = orc_hamming(qdesc + 32 * (size_t)qi, desc + 32 * (size_t)i);
             if (dist < r.best_dist) { /* orb_matcher.cc:98-112 */
               r.best_dist2 = r.best_dist; r.best_dist = dist;

@@ -145,6 +145,12 @@ typedef struct {
 void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
                        const orc_window_query* q, const uint8_t* qdesc, int nq,
                        const uint8_t* skip /* n bytes or NULL */, orc_window_result* out);
+/* the same with the stereo gate of orb_matcher.cc:89-92 / :1586-1590: a keypoint with a right coordinate
+ * (kp_u_right[i] > 0) is skipped when |q_u_right[q] - kp_u_right[i]| > q_max_err[q] */
+void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                              const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                              orc_window_result* out);
 
 /* ---- deterministic synthetic inputs ---- */
 uint64_t orc_splitmix64(uint64_t x);

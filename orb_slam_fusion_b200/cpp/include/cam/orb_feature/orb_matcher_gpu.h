@@ -59,7 +59,11 @@ class ORBmatcherGpu {
   // orb_matcher.cc:66-113 with Frame::GetFeaturesInArea (frame.cc:679-746) for a batch of projections.
   void WindowSearch(const std::vector<cv::KeyPoint>& keys_un, const cv::Mat& desc, float min_x, float min_y,
                     float grid_inv_w, float grid_inv_h, int grid_cols, int grid_rows, const std::vector<Window>& windows,
-                    const cv::Mat& window_desc, const std::vector<uint8_t>* already_matched, std::vector<WindowBest>& out);
+                    const cv::Mat& window_desc, const std::vector<uint8_t>* already_matched, std::vector<WindowBest>& out,
+                    // stereo gate of orb_matcher.cc:89-92 / 1586-1590: Frame::mvuRight, and per window the projected
+                    // right coordinate and the largest accepted |difference| (all three or none)
+                    const std::vector<float>* u_right = nullptr, const std::vector<float>* window_u_right = nullptr,
+                    const std::vector<float>* window_max_err = nullptr);
 
  private:
   orbm_matcher* m_;

@@ -100,14 +100,18 @@ std::vector<int> ORBmatcherGpu::ComputeDistinctiveDescriptors(const std::vector<
 
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,
                                  float inv_w, float inv_h, int cols, int rows, const std::vector<Window>& windows,
-                                 const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out) {
+                                 const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out,
+                                 const std::vector<float>* u_right, const std::vector<float>* window_u_right,
+                                 const std::vector<float>* window_max_err) {
   const std::vector<uint8_t> d = dense_rows(desc), qd = dense_rows(window_desc);
   const orbm_grid_geom g = {min_x, min_y, inv_w, inv_h, cols, rows};
   out.resize(windows.size());
-  check(m_, orbm_window_search(m_, reinterpret_cast<const orbx_kp*>(keys.data()), d.data(), (int)keys.size(), &g,
-                               reinterpret_cast<const orbm_window_query*>(windows.data()), qd.data(), (int)windows.size(),
-                               already ? already->data() : nullptr, reinterpret_cast<orbm_window_result*>(out.data()),
-                               ORBX_MEM_HOST, nullptr));
+  check(m_, orbm_window_search_stereo(m_, reinterpret_cast<const orbx_kp*>(keys.data()), d.data(), (int)keys.size(), &g,
+                                      reinterpret_cast<const orbm_window_query*>(windows.data()), qd.data(), (int)windows.size(),
+                                      already ? already->data() : nullptr, u_right ? u_right->data() : nullptr,
+                                      window_u_right ? window_u_right->data() : nullptr,
+                                      window_max_err ? window_max_err->data() : nullptr,
+                                      reinterpret_cast<orbm_window_result*>(out.data()), ORBX_MEM_HOST, nullptr));
 }
 
 }  // namespace ORB_SLAM_FUSION

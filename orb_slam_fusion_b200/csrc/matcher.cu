@@ -508,7 +508,8 @@ int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points
 __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                        const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                        const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
-                                                       orbm_window_result* __restrict__ out) {
+                                                       const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
+                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out) {
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (qi >= nq) return;
   const orbm_window_query Q = q[qi];
@@ -541,6 +542,10 @@ __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict
       const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
       if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
       if (skip && skip[i]) continue;
+      if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
+        const float ur = kp_u_right[i];
+        if (ur > 0 && fabsf(f_sub(q_u_right[qi], ur)) > q_max_err[qi]) continue;
+      }
       uint32_t kd[8];
       load_row_any(desc + 32 * (size_t)i, kd);
       const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
@@ -566,9 +571,10 @@ __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict
 }
 
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
-                         const uint8_t* qdesc, int nq, const uint8_t* skip, orbm_window_result* out, cudaStream_t st) {
+                         const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
+                         const float* q_max_err, orbm_window_result* out, cudaStream_t st) {
   if (nq <= 0) return 0;
-  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, out);
+  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out);
   return 1;
 }
 

@@ -165,17 +165,25 @@ class ORBmatcher:
         return bi, bm
 
     # ---- projection window
-    def window_search(self, kps, desc, geom, queries, qdesc, skip=None):
+    def window_search(self, kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q_u_right=None, q_max_err=None):
+        """Best / second-best frame keypoint per projected map point (orb_matcher.cc:66-113, 451-479, 1567-1608).
+        kp_u_right (Frame::mvuRight) with q_u_right / q_max_err per query adds the stereo gate of :89-92 / :1586-1590."""
         kps = np.ascontiguousarray(kps, A.KP_DTYPE)
         desc = np.ascontiguousarray(desc, np.uint8)
         queries = np.ascontiguousarray(queries, A.WQ_DTYPE)
         qdesc = np.ascontiguousarray(qdesc, np.uint8)
         sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        ur = qr = qe = None
+        if kp_u_right is not None:
+            ur = np.ascontiguousarray(kp_u_right, np.float32)
+            qr = np.ascontiguousarray(q_u_right, np.float32)
+            qe = np.ascontiguousarray(q_max_err, np.float32)
+            assert len(ur) == len(kps) and len(qr) == len(qe) == len(queries)
         out = np.empty(len(queries), A.WR_DTYPE)
         g = A.GridGeom(*geom)
-        self._check(self._lib.orbm_window_search(self._m, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(g),
-                                                 queries.ctypes.data, qdesc.ctypes.data, len(queries),
-                                                 None if sk is None else sk.ctypes.data, out.ctypes.data, A.MEM_HOST, None))
+        self._check(self._lib.orbm_window_search_stereo(
+            self._m, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(g), queries.ctypes.data, qdesc.ctypes.data,
+            len(queries), A.ptr(sk), A.ptr(ur), A.ptr(qr), A.ptr(qe), out.ctypes.data, A.MEM_HOST, None))
         return out
 
 

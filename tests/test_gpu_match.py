@@ -241,6 +241,18 @@ def test_window_search(P, m, oracle):
     got = m.window_search(k2, d2, geom, q, qdesc)
     want = oracle.window_search(k2, d2, geom, q, qdesc)
     assert got.tobytes() == want.tobytes()
+    # stereo gate (orb_matcher.cc:89-92, 1586-1590): keypoints with a right coordinate must agree with the
+    # projection in the right image; ~half the keypoints are monocular (mvuRight = -1)
+    ur = np.where(rng.random(len(kps)) < 0.5, kps["x"] - rng.uniform(2, 60, len(kps)), -1.0).astype(np.float32)
+    qur = (q["u"] - rng.uniform(2, 60, nq)).astype(np.float32)
+    qerr = (q["r"] * np.float32(1.2) ** np.maximum(lv, 0)).astype(np.float32)
+    qur[::3] = ur[src[::3]] + rng.normal(0, 1, len(qur[::3])).astype(np.float32)     # consistent stereo projections
+    for skip in (None, (rng.random(len(kps)) < 0.3).astype(np.uint8)):
+        got = m.window_search(kps, desc, geom, q, qdesc, skip, ur, qur, qerr)
+        want = oracle.window_search(kps, desc, geom, q, qdesc, skip, ur, qur, qerr)
+        assert got.tobytes() == want.tobytes()
+    plain = oracle.window_search(kps, desc, geom, q, qdesc, skip)
+    assert (want["best_idx"] != plain["best_idx"]).mean() > 0.05 and (want["best_idx"] >= 0).mean() > 0.3
 
 
 def test_popc_peak_microbenchmark(P):
