@@ -24,10 +24,10 @@ __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9
 // IC_Angle as DP4A over aligned words: the 31 patch rows are read as 9 aligned 32-bit words each (any
 // alignment a = 0..3 of the patch's first column); item i = 9 * row + word.  Entry [a][i] holds the per-byte
 // weights of that word inside the radius-15 disc -- x: (u + 16) per byte (1..31, 0 outside), y: 1 per byte
-// inside -- and z: row | word << 8.  Filled once per device by k_pattern_init; 4 x 279 x 16 B = 17.9 KB,
-// read by every warp with one coalesced 128-bit load per item.
+// inside.  Filled once per device by k_pattern_init; 4 x 279 x 8 B = 8.9 KB, read by every warp with one
+// coalesced 64-bit load per item (the pixel loads do not depend on it: row and word come from the item index).
 constexpr int kOriItems = 31 * 9;
-__device__ uint4 g_ori_w[4 * kOriItems];
+__device__ uint2 g_ori_w[4 * kOriItems];
 
 // the same pattern as floats, transposed: entry [k][L] = (x0, y0, x1, y1) of bit k of descriptor byte L, so that a
 // warp reads one coalesced 512-byte line per bit (filled once per device by k_pattern_init)
@@ -46,7 +46,7 @@ __global__ void k_pattern_init() {
       const int u = u0 + j;
       if (u >= -d && u <= d) { wu |= (uint32_t)(u + 16) << (8 * j); wm |= 1u << (8 * j); }
     }
-    g_ori_w[e] = make_uint4(wu, wm, (uint32_t)r | ((uint32_t)wc << 8), 0u);
+    g_ori_w[e] = make_uint2(wu, wm);
   }
 }
 
@@ -138,11 +138,11 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   if (s >= g.sel_frame_cap) return;
   const size_t so = (size_t)f * g.sel_frame_cap + s;
   const int wv = work[so];  // slot | level << 24 from k_plan; -1: no keypoint here (or it does not fit)
+  const uint32_t xy = sel_xy[so];  // (issued together with the load above)
   if (wv < 0) return;
   const int slot = wv & ((1 << kWorkLevShift) - 1), lev = wv >> kWorkLevShift;
   const LevelGeom& L = g.lv[lev];
   const int pitch = L.pitch;  // level fields live in the parameter bank behind a run-time index: read once
-  const uint32_t xy = sel_xy[so];
   const int cx = (int)(xy & 0xFFFFu), cy = (int)(xy >> 16);
   const size_t fo = (size_t)f * g.pyr_frame_bytes;
 
@@ -173,14 +173,14 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   {
     const int xa = (cx - kHalfPatch) & ~3, a = (cx - kHalfPatch) - xa;  // aligned start, 0..3 bytes before the patch
     const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);
-    const uint4* wt = g_ori_w + a * kOriItems;
+    const uint2* wt = g_ori_w + a * kOriItems;
 #pragma unroll
     for (int t = 0; t < (kOriItems + 31) / 32; t++) {
       const int i = lane + 32 * t;
       if (i < kOriItems) {
-        const uint4 e = __ldg(wt + i);
-        const int r = (int)(e.z & 255u), wc = (int)(e.z >> 8);
+        const int r = (i * 57) >> 9, wc = i - r * 9;  // i / 9 for i < 512
         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + r * pitch) + wc);
+        const uint2 e = __ldg(wt + i);
         const int s0 = (int)__dp4a(w, e.y, 0u), s1 = (int)__dp4a(w, e.x, 0u);  // sum I, sum (u + 16) * I
         m10 += s1 - 16 * s0;
         m01 += (r - kHalfPatch) * s0;
