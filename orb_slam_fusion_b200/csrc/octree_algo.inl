@@ -31,6 +31,7 @@
 static inline int ot_atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
 static inline void ot_atomic_max(int* p, int v) { if (v > *p) *p = v; }
 static inline void ot_atomic_min_u(unsigned* p, unsigned v) { if (v < *p) *p = v; }
+static inline void ot_atomic_max64(unsigned long long* p, unsigned long long v) { if (v > *p) *p = v; }
 #else
 #define OT_DEV __device__ __forceinline__
 #define OT_HD __host__ __device__ __forceinline__
@@ -40,6 +41,7 @@ static inline void ot_atomic_min_u(unsigned* p, unsigned v) { if (v < *p) *p = v
 __device__ __forceinline__ int ot_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 __device__ __forceinline__ void ot_atomic_max(int* p, int v) { atomicMax(p, v); }
 __device__ __forceinline__ void ot_atomic_min_u(unsigned* p, unsigned v) { atomicMin(p, v); }
+__device__ __forceinline__ void ot_atomic_max64(unsigned long long* p, unsigned long long v) { atomicMax(p, v); }
 #endif
 
 namespace orbx {
@@ -55,12 +57,13 @@ struct OtWork {
   int* rank;    // [cap]    processing rank of a node in this pass, -1 = not split
   int* seq;     // [cap]    inverse of rank
   int* scan;    // [cap+1]  scratch for prefix sums
+  unsigned long long* best;  // [cap] (response << 32 | ~order key) of the best point of each node
   int* sv;      // small scalar block (>= 16 ints), shared between threads
 };
 
 enum { SV_N = 0, SV_F, SV_M, SV_MEFF, SV_TOTALC, SV_DONE, SV_PHASE, SV_TOEXP, SV_CUR, SV_ERR };
 
-OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1) + 2 * (cap + 1) + 16; }
+OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1 + 2) + 2 * (cap + 1) + 16 + 2; }
 
 OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.cap = cap;
@@ -75,6 +78,8 @@ OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.rank = p; p += cap;
   w.seq = p; p += cap;
   w.scan = p; p += cap + 1;
+  p += ((size_t)p & 7) ? 1 : 0;  // 8-byte alignment (the block itself is at least 8-byte aligned)
+  w.best = (unsigned long long*)p; p += 2 * cap;
   w.sv = p;
 }
 
@@ -128,8 +133,20 @@ OT_DEV int ot_quadrant(int px, int py, int x0, int y0, int x1, int y1) {
 
 // Reference-order key of a candidate (x,y relative to (16,16)): position in to_dist_kps, i.e.
 // cell-row-major, then row-major inside the cell's detection domain (orb_extractor.cc:767-823).
-OT_DEV unsigned ot_order_key(int x, int y, int wcell, int hcell, int ncols) {
-  const int ci = (y - 3) / hcell, cj = (x - 3) / wcell;
+// v / d for 0 <= v, v * d < 2^32, rcp = ceil(2^32 / d): one multiply-high, exact
+OT_DEV int ot_div(int v, int d, unsigned rcp) {
+#if defined(ORBX_HOST_EMUL)
+  (void)rcp;
+  return v / d;
+#else
+  (void)d;
+  return (int)__umulhi((unsigned)v, rcp);
+#endif
+}
+OT_HD unsigned ot_rcp(int d) { return (unsigned)((0x100000000ull + (unsigned long long)d - 1) / (unsigned long long)d); }
+
+OT_DEV unsigned ot_order_key(int x, int y, int wcell, int hcell, int ncols, unsigned wrcp, unsigned hrcp) {
+  const int ci = ot_div(y - 3, hcell, hrcp), cj = ot_div(x - 3, wcell, wrcp);
   const int yr = (y - 3) - ci * hcell, xr = (x - 3) - cj * wcell;
   return (unsigned)(((ci * ncols + cj) * hcell + yr) * wcell + xr);
 }
@@ -208,17 +225,19 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     } else {
       // candidates: children created by the previous pass that hold > 1 point (kps_size_and_nd,
       // :616-650); processed from the back of stable_sort((count, UL.x) ascending) (:671-673)
+      // key = (count, UL.x) packed; 0 marks a node that is not a candidate (candidates have count >= 2)
+      unsigned long long* key = w.best;  // free until the best-point pass at the end
+      OT_FOR(i, n) key[i] = (i < F && CNT[i] > 1) ? (((unsigned long long)CNT[i] << 32) | (unsigned)X0[i]) : 0ull;
+      OT_SYNC();
       OT_FOR(i, n) {
         int r = -1;
-        if (i < F && CNT[i] > 1) {
+        const unsigned long long ki = key[i];
+        if (ki) {
           r = 0;
-          const int ci = CNT[i], xi = X0[i];
+#pragma unroll 8
           for (int j = 0; j < F; j++) {
-            const int cj = CNT[j];
-            if (cj <= 1 || j == i) continue;
-            const int xj = X0[j];
-            const bool before = (cj > ci) || (cj == ci && (xj > xi || (xj == xi && j < i)));
-            r += before;
+            const unsigned long long kj = key[j];
+            r += (int)(kj > ki) + (int)((kj == ki) & (j < i));  // processed before node i
           }
         }
         w.rank[i] = r;
@@ -338,29 +357,24 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     if (OT_TID0) *n_sel = -1;
     return;
   }
-  int* best_sc = w.rank;                 // reuse
-  unsigned* best_key = (unsigned*)w.seq;
-  OT_FOR(i, n) { best_sc[i] = -1; best_key[i] = 0xFFFFFFFFu; }
-  OT_SYNC();
-  OT_FOR(p, P) ot_atomic_max(&best_sc[node_of[p]], (int)sc[p]);
+  // max response, then the earliest point in the reference's candidate order: one 64-bit key per point
+  const unsigned wrcp = ot_rcp(wcell), hrcp = ot_rcp(hcell);
+  OT_FOR(i, n) w.best[i] = 0ull;
   OT_SYNC();
   OT_FOR(p, P) {
-    const int i = node_of[p];
-    if ((int)sc[p] == best_sc[i]) {
-      const uint32_t v = xy[p];
-      ot_atomic_min_u(&best_key[i], ot_order_key((int)(v & 0xFFFFu), (int)(v >> 16), wcell, hcell, ncols));
-    }
+    const uint32_t v = xy[p];
+    const unsigned okey = ot_order_key((int)(v & 0xFFFFu), (int)(v >> 16), wcell, hcell, ncols, wrcp, hrcp);
+    ot_atomic_max64(&w.best[node_of[p]], ((unsigned long long)(sc[p] + 1u) << 32) | (unsigned long long)(0xFFFFFFFFu - okey));
   }
   OT_SYNC();
   OT_FOR(p, P) {
+    const uint32_t v = xy[p];
+    const int x = (int)(v & 0xFFFFu), y = (int)(v >> 16);
+    const unsigned okey = ot_order_key(x, y, wcell, hcell, ncols, wrcp, hrcp);
     const int i = node_of[p];
-    if ((int)sc[p] == best_sc[i]) {
-      const uint32_t v = xy[p];
-      const int x = (int)(v & 0xFFFFu), y = (int)(v >> 16);
-      if (ot_order_key(x, y, wcell, hcell, ncols) == best_key[i]) {
-        sel_xy[i] = ((uint32_t)(y + kFastBorder) << 16) | (uint32_t)(x + kFastBorder);
-        sel_sc[i] = sc[p];
-      }
+    if (w.best[i] == (((unsigned long long)(sc[p] + 1u) << 32) | (unsigned long long)(0xFFFFFFFFu - okey))) {
+      sel_xy[i] = ((uint32_t)(y + kFastBorder) << 16) | (uint32_t)(x + kFastBorder);
+      sel_sc[i] = sc[p];
     }
   }
   if (OT_TID0) *n_sel = n;
