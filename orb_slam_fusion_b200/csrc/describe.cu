@@ -117,7 +117,10 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
   }
 }
 
-constexpr int kDescWarps = 8;
+#ifndef ORBX_DESC_WARPS
+#define ORBX_DESC_WARPS 8
+#endif
+constexpr int kDescWarps = ORBX_DESC_WARPS;
 constexpr int kPatchRows = 37;    // rotated pattern offsets stay within +-18 px (A.7)
 constexpr int kPatchPitch = 80;   // bytes per staged row: 4 x 16-byte chunks from a 16-byte aligned column (<= 15 + 37 bytes used);
                                   // 20 words of pitch spread vertical neighbours over the banks

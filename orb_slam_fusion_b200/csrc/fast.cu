@@ -228,21 +228,21 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   {
     const int wc = tid % kFtRawW, rg = tid / kFtRawW;
     const int x = X0 - 4 + 4 * wc;
-    uint32_t lane_mask = 0;  // 0x80 per byte lane inside the scored column range
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if (x + j >= xlo && x + j < xhi) lane_mask |= 0x80u << (8 * j);
+    // 0x80 per byte lane inside the scored column range [xlo, xhi): drop the first a and keep the first b lanes
+    const int a = min(max(xlo - x, 0), 4), b = min(max(xhi - x, 0), 4);
+    const uint32_t lane_mask = __funnelshift_lc(0u, 0x80808080u, 8 * a) & __funnelshift_rc(0x80808080u, 0u, 8 * (4 - b));
     const bool score_all = lo > 126;  // thresholds beyond the byte trick: score everything
     const int wl = wc > 0 ? -1 : 0, wr = wc < kFtRawW - 1 ? 1 : 0;
     const int rr0 = rg * kFtStrip;
+    // rows of the strip inside the score map and the detection domain: i_lo <= i < i_hi
+    const int y0s = Y0 - 1 + rr0, i_lo = kEdge - y0s, i_hi = min(kFtScH - rr0, L.h - kEdge - y0s);
     const uint32_t* row = &raw_w[(rr0 + 3) * kFtRawPW + kFtRawOrg + wc];
     uint32_t keep[kFtStrip];
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < kFtStrip; i++) {
-      const int rr = rr0 + i, y = Y0 - 1 + rr;
       uint32_t k = 0;
-      if (lane_mask && rr < kFtScH && y >= kEdge && y < L.h - kEdge) {
+      if (lane_mask && i >= i_lo && i < i_hi) {
         const uint32_t* rp = row + i * kFtRawPW;
         const uint32_t c = rp[0];
         const uint32_t up = rp[-3 * kFtRawPW], dn = rp[3 * kFtRawPW];
