@@ -475,10 +475,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="frames per step per GPU")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything any library prints to file descriptor 1 during the run
+    # (NCCL's version banner, for one) is sent to stderr, and the line is written to the saved descriptor
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(out_fd, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
