@@ -1,0 +1,252 @@
+// oracle/ref_frame_shim.cc -- TEST INFRASTRUCTURE, not product code.
+//
+// The reference's own lines for the matcher-side rows of the hot path, compiled where they lie.
+// frame.cc / mappoint.cc / orb_matcher.cc cannot be compiled as files here (they include Eigen, Sophus,
+// DBoW2, boost), so the FUNCTION BODIES are spliced by sed into build intermediates under _ref/
+// (git-ignored, see oracle/Makefile) and compiled inside the minimal class declarations below, which
+// carry exactly the members those bodies touch, under the reference's names:
+//   _ref/frame_stereo.inc        frame.cc:828-986      Frame::ComputeStereoMatches
+//   _ref/frame_grid.inc          frame.cc:438-465      Frame::AssignFeaturesToGrid
+//   _ref/frame_area.inc          frame.cc:679-759      Frame::GetFeaturesInArea, Frame::PosInGrid
+//   _ref/mappoint_distinct.inc   mappoint.cc:365-432   MapPoint::ComputeDistinctiveDescriptors
+//   _ref/matcher_consts.inc      orb_matcher.cc:35-40  TH_HIGH / TH_LOW / HISTO_LENGTH, constructor
+//   _ref/matcher_project.inc     orb_matcher.cc:42-213 ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...),
+//                                                      ORBmatcher::RadiusByViewingCos
+//   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
+// Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
+// orc_distinctive / orc_window_search(_stereo) of oracle/orb_oracle.c.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+
+#include <opencv2/core/core.hpp>
+
+using namespace std;
+
+#define FRAME_GRID_ROWS 48  // include/map/frame.h:40-41
+#define FRAME_GRID_COLS 64
+
+namespace ORB_SLAM_FUSION {
+
+class MapPoint;
+class KeyFrame;
+
+// the one member of OrbExtractor that frame.cc:834,913-933 reads
+struct OrbExtractor {
+  std::vector<cv::Mat> img_pyramid_;
+};
+
+class ORBmatcher {
+ public:
+  ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+  static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+  int SearchByProjection(class Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3,
+                         const bool bFarPoints = false, const float thFarPoints = 50.0f);
+  static const int TH_LOW;
+  static const int TH_HIGH;
+  static const int HISTO_LENGTH;
+
+ protected:
+  float RadiusByViewingCos(const float &viewCos);
+  float mfNNratio;
+  bool mbCheckOrientation;
+};
+
+class Frame {  // include/map/frame.h: the members the spliced bodies use, same names and types
+ public:
+  void ComputeStereoMatches();
+  void AssignFeaturesToGrid();
+  bool PosInGrid(const cv::KeyPoint &kp, int &posX, int &posY);
+  vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const int minLevel = -1,
+                                   const int maxLevel = -1, const bool bRight = false) const;
+
+  OrbExtractor *orb_extractor_left_ = nullptr, *orb_extractor_right_ = nullptr;
+  int N = 0;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysRight, mvKeysUn;
+  std::vector<float> mvuRight, mvDepth;
+  cv::Mat mDescriptors, mDescriptorsRight;
+  std::vector<float> mvScaleFactors, mvInvScaleFactors;
+  float mb = 0, bf_ = 0;
+  std::vector<MapPoint *> mvpMapPoints;
+  static float mfGridElementWidthInv, mfGridElementHeightInv;
+  std::vector<std::size_t> mGrid[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+  int Nleft = -1, Nright = -1;
+  std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
+  std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+};
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+class KeyFrame {
+ public:
+  bool isBad() { return bad; }
+  bool bad = false;
+  cv::Mat mDescriptors;
+};
+
+class MapPoint {  // include/map/mappoint.h
+ public:
+  void ComputeDistinctiveDescriptors();
+  cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+  bool isBad() { return mbBad; }
+  int Observations() { return nObs; }
+
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackDepth = 0, mTrackDepthR = 0, mTrackProjXR = 0, mTrackProjYR = 0;
+  bool mbTrackInView = false, mbTrackInViewR = false;
+  int mnTrackScaleLevel = 0, mnTrackScaleLevelR = -1;
+  float mTrackViewCos = 0, mTrackViewCosR = 0;
+
+  std::map<KeyFrame *, std::tuple<int, int>> mObservations;
+  cv::Mat mDescriptor;
+  bool mbBad = false;
+  int nObs = 0;
+  std::mutex mMutexFeatures;
+};
+
+#include "matcher_consts.inc"
+#include "descriptor_distance.inc"
+#include "frame_grid.inc"
+#include "frame_area.inc"
+#include "frame_stereo.inc"
+#include "mappoint_distinct.inc"
+#include "matcher_project.inc"
+
+}  // namespace ORB_SLAM_FUSION
+
+using namespace ORB_SLAM_FUSION;
+
+extern "C" {
+
+struct reff_level {
+  const uint8_t *px;  // pixel (0,0) of the level (the 19-px border lies around it, like img_pyramid_)
+  int w, h;
+  size_t stride;
+};
+
+// Frame::ComputeStereoMatches on caller-supplied keypoints, descriptors and the two pyramids.
+void reff_stereo_matches(const reff_level *left, const reff_level *right, int n_levels, const void *kl, int nl,
+                         const uint8_t *dl, const void *kr, int nr, const uint8_t *dr, const float *scale,
+                         const float *inv_scale, float bf, float mb, float *u_right, float *depth) {
+  OrbExtractor el, er;
+  for (int l = 0; l < n_levels; l++) {
+    el.img_pyramid_.push_back(cv::Mat(left[l].h, left[l].w, CV_8UC1, (void *)left[l].px, left[l].stride));
+    er.img_pyramid_.push_back(cv::Mat(right[l].h, right[l].w, CV_8UC1, (void *)right[l].px, right[l].stride));
+  }
+  Frame F;
+  F.orb_extractor_left_ = &el;
+  F.orb_extractor_right_ = &er;
+  F.N = nl;
+  F.mvKeys.assign((const cv::KeyPoint *)kl, (const cv::KeyPoint *)kl + nl);
+  F.mvKeysRight.assign((const cv::KeyPoint *)kr, (const cv::KeyPoint *)kr + nr);
+  F.mDescriptors = cv::Mat(nl, 32, CV_8U, (void *)dl);
+  F.mDescriptorsRight = cv::Mat(nr, 32, CV_8U, (void *)dr);
+  F.mvScaleFactors.assign(scale, scale + n_levels);
+  F.mvInvScaleFactors.assign(inv_scale, inv_scale + n_levels);
+  F.bf_ = bf;
+  F.mb = mb;
+  F.ComputeStereoMatches();
+  std::memcpy(u_right, F.mvuRight.data(), sizeof(float) * nl);
+  std::memcpy(depth, F.mvDepth.data(), sizeof(float) * nl);
+}
+
+// MapPoint::ComputeDistinctiveDescriptors for point p = rows [offsets[p], offsets[p+1]) of desc: every row is
+// the left observation of its own key frame (key frames allocated in one array, so the std::map iterates
+// them in row order).  Writes the chosen 32-byte descriptor; chosen[p] = 0 where mDescriptor stays empty.
+void reff_distinctive(const uint8_t *desc, const int *offsets, int n_points, uint8_t *out_desc, int *chosen) {
+  for (int p = 0; p < n_points; p++) {
+    const int n = offsets[p + 1] - offsets[p];
+    std::vector<KeyFrame> kfs(n > 0 ? n : 1);
+    MapPoint mp;
+    for (int i = 0; i < n; i++) {
+      kfs[i].mDescriptors = cv::Mat(1, 32, CV_8U, (void *)(desc + 32 * (size_t)(offsets[p] + i)));
+      mp.mObservations[&kfs[i]] = std::make_tuple(0, -1);
+    }
+    mp.ComputeDistinctiveDescriptors();
+    chosen[p] = !mp.mDescriptor.empty();
+    if (chosen[p]) std::memcpy(out_desc + 32 * (size_t)p, mp.mDescriptor.data, 32);
+  }
+}
+
+struct reff_track_point {  // the MapPoint fields SearchByProjection reads (orb_matcher.cc:53-92)
+  float proj_x, proj_y, proj_xr, view_cos, depth;
+  int level, in_view, bad;
+};
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints) on a
+// monocular / rectified-stereo frame (Nleft == -1): keys_un + descriptors + optional mvuRight, the 64x48 grid built
+// by the reference's AssignFeaturesToGrid.  pre_matched[i] != 0: the frame keypoint already holds a map point
+// with observations.  assigned[i] = index of the map point the call stored in F.mvpMapPoints[i] (-1: untouched).
+int reff_search_by_projection(const void *keys_un, const uint8_t *desc, int n, const float *u_right, float min_x,
+                              float max_x, float min_y, float max_y, const float *scale, int n_levels,
+                              const reff_track_point *pts, const uint8_t *pt_desc, int n_pts, const uint8_t *pre_matched,
+                              float th, float nnratio, int far_points, float th_far, int *assigned) {
+  Frame F;
+  F.N = n;
+  F.mvKeysUn.assign((const cv::KeyPoint *)keys_un, (const cv::KeyPoint *)keys_un + n);
+  F.mDescriptors = cv::Mat(n, 32, CV_8U, (void *)desc);
+  F.mvuRight.assign(n, -1.0f);
+  if (u_right) F.mvuRight.assign(u_right, u_right + n);
+  F.mvScaleFactors.assign(scale, scale + n_levels);
+  Frame::mnMinX = min_x;
+  Frame::mnMaxX = max_x;
+  Frame::mnMinY = min_y;
+  Frame::mnMaxY = max_y;
+  // frame.cc:214-217
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(max_x - min_x);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(max_y - min_y);
+  F.AssignFeaturesToGrid();
+  MapPoint occupied;
+  occupied.nObs = 1;
+  F.mvpMapPoints.assign(n, (MapPoint *)nullptr);
+  for (int i = 0; i < n; i++)
+    if (pre_matched && pre_matched[i]) F.mvpMapPoints[i] = &occupied;
+  std::vector<MapPoint> mps(n_pts > 0 ? n_pts : 1);
+  std::vector<MapPoint *> vp;
+  for (int i = 0; i < n_pts; i++) {
+    MapPoint &m = mps[i];
+    m.mTrackProjX = pts[i].proj_x;
+    m.mTrackProjY = pts[i].proj_y;
+    m.mTrackProjXR = pts[i].proj_xr;
+    m.mTrackViewCos = pts[i].view_cos;
+    m.mTrackDepth = pts[i].depth;
+    m.mnTrackScaleLevel = pts[i].level;
+    m.mbTrackInView = pts[i].in_view != 0;
+    m.mbBad = pts[i].bad != 0;
+    m.nObs = 1;
+    m.mDescriptor = cv::Mat(1, 32, CV_8U, (void *)(pt_desc + 32 * (size_t)i)).clone();
+    vp.push_back(&m);
+  }
+  ORBmatcher matcher(nnratio, true);
+  const int nm = matcher.SearchByProjection(F, vp, th, far_points != 0, th_far);
+  for (int i = 0; i < n; i++) {
+    MapPoint *p = F.mvpMapPoints[i];
+    assigned[i] = (p && p != &occupied) ? (int)(p - mps.data()) : -1;
+  }
+  return nm;
+}
+
+// Frame::GetFeaturesInArea after AssignFeaturesToGrid: the visiting order of the grid lookup.
+int reff_features_in_area(const void *keys_un, int n, float min_x, float max_x, float min_y, float max_y, float x, float y,
+                          float r, int min_level, int max_level, int *out, int cap) {
+  Frame F;
+  F.N = n;
+  F.mvKeysUn.assign((const cv::KeyPoint *)keys_un, (const cv::KeyPoint *)keys_un + n);
+  Frame::mnMinX = min_x;
+  Frame::mnMaxX = max_x;
+  Frame::mnMinY = min_y;
+  Frame::mnMaxY = max_y;
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(max_x - min_x);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(max_y - min_y);
+  F.AssignFeaturesToGrid();
+  const vector<size_t> v = F.GetFeaturesInArea(x, y, r, min_level, max_level);
+  for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
+  return (int)v.size();
+}
+
+}  // extern "C"

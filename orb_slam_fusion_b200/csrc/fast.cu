@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     const int rows_out = min(kFtH, L.h - Y0), cols_out = min(kFtW, L.w - X0);
     const int q = tid & 31;
     if (4 * q < cols_out) {  // horizontal: thread = (quad q, row pairs warp, warp+8, warp+16); blur row b = raw row b + 1
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 3; i++) {
         const int pr = (tid >> 5) + 8 * i;
         if (2 * pr < rows_out + 6) {
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
             hv[e][3] = __dp4a(w1, G4(18, 34, 48, 56), __dp4a(w2, G4(48, 34, 18, 0), 0u));  // each <= 255*256
           }
           *reinterpret_cast<uint4*>(&tmp2[pr * kFtW + 4 * q]) =
-              make_uint4(hv[0][0] | (hv[1][0] << 16), hv[0][1] | (hv[1][1] << 16), hv[0][2] | (hv[1][2] << 16), hv[0][3] | (hv[1][3] << 16));
+              make_uint4(__byte_perm(hv[0][0], hv[1][0], 0x5410), __byte_perm(hv[0][1], hv[1][1], 0x5410), __byte_perm(hv[0][2], hv[1][2], 0x5410),
+                         __byte_perm(hv[0][3], hv[1][3], 0x5410));
         }
       }
     }
@@ -231,27 +232,30 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     // 0x80 per byte lane inside the scored column range [xlo, xhi): drop the first a and keep the first b lanes
     const int a = min(max(xlo - x, 0), 4), b = min(max(xhi - x, 0), 4);
     const uint32_t lane_mask = __funnelshift_lc(0u, 0x80808080u, 8 * a) & __funnelshift_rc(0x80808080u, 0u, 8 * (4 - b));
-    const bool score_all = lo > 126;  // thresholds beyond the byte trick: score everything
+    const uint32_t force = lo > 126 ? 0x80808080u : 0u;  // thresholds beyond the byte trick: score everything
     const int wl = wc > 0 ? -1 : 0, wr = wc < kFtRawW - 1 ? 1 : 0;
     const int rr0 = rg * kFtStrip;
-    // rows of the strip inside the score map and the detection domain: i_lo <= i < i_hi
-    const int y0s = Y0 - 1 + rr0, i_lo = kEdge - y0s, i_hi = min(kFtScH - rr0, L.h - kEdge - y0s);
+    // rows of the strip inside the score map and the detection domain: i_lo <= i < i_hi, as one bit per row.
+    // Rows outside are computed all the same (their loads stay inside the CTA's shared memory) and masked
+    // out: cheaper than a branch per row.
+    const int y0s = Y0 - 1 + rr0, i_lo = max(kEdge - y0s, 0), i_hi = min(min(kFtScH - rr0, L.h - kEdge - y0s), kFtStrip);
+    const uint32_t rowbits = i_hi > i_lo ? (1u << i_hi) - (1u << i_lo) : 0u;
     const uint32_t* row = &raw_w[(rr0 + 3) * kFtRawPW + kFtRawOrg + wc];
     uint32_t keep[kFtStrip];
     int cnt = 0;
 #pragma unroll
     for (int i = 0; i < kFtStrip; i++) {
-      uint32_t k = 0;
-      if (lane_mask && i >= i_lo && i < i_hi) {
-        const uint32_t* rp = row + i * kFtRawPW;
-        const uint32_t c = rp[0];
-        const uint32_t up = rp[-3 * kFtRawPW], dn = rp[3 * kFtRawPW];
-        const uint32_t lf = __byte_perm(rp[wl], c, 0x4321);   // pixels x-3
-        const uint32_t rt = __byte_perm(c, rp[wr], 0x6543);   // pixels x+3
-        k = (exceeds4(dn, c, kthr) | exceeds4(up, c, kthr)) & (exceeds4(rt, c, kthr) | exceeds4(lf, c, kthr));
-        if (score_all) k = 0x80808080u;
-        k &= lane_mask;
-      }
+      const uint32_t m = (rowbits >> i) & 1u ? lane_mask : 0u;
+      const uint32_t* rp = row + i * kFtRawPW;
+      const uint32_t c = rp[0];
+      const uint32_t up = rp[-3 * kFtRawPW], dn = rp[3 * kFtRawPW];
+      const uint32_t lf = __byte_perm(rp[wl], c, 0x4321);   // pixels x-3
+      const uint32_t rt = __byte_perm(c, rp[wr], 0x6543);   // pixels x+3
+      // exceeds4 without its final mask: bit 7 of every byte of (((d & 0x7f) + k) | d) says |a - b| > t
+      const uint32_t d0 = __vabsdiffu4(dn, c), d1 = __vabsdiffu4(up, c), d2 = __vabsdiffu4(rt, c), d3 = __vabsdiffu4(lf, c);
+      const uint32_t s0 = (d0 & 0x7f7f7f7fu) + kthr, s1 = (d1 & 0x7f7f7f7fu) + kthr, s2 = (d2 & 0x7f7f7f7fu) + kthr,
+                     s3 = (d3 & 0x7f7f7f7fu) + kthr;
+      const uint32_t k = (((s0 | d0 | s1 | d1) & (s2 | d2 | s3 | d3)) | force) & m;
       keep[i] = k;
       cnt += __popc(k);
     }
