@@ -179,6 +179,17 @@ typedef const _OutputArray& InputOutputArray;
 
 inline float fastAtan2(float y, float x) { return cvp_fast_atan2(y, x); }
 
+// cv::norm(a, b, NORM_L1) for 8-bit single-channel matrices of equal size (frame.cc:935): sum |a - b| as a double
+inline double norm(const Mat& a, const Mat& b, int normType) {
+  (void)normType;
+  long long s = 0;
+  for (int y = 0; y < a.rows; y++) {
+    const uchar *pa = a.ptr(y), *pb = b.ptr(y);
+    for (int x = 0; x < a.cols; x++) s += pa[x] > pb[x] ? pa[x] - pb[x] : pb[x] - pa[x];
+  }
+  return (double)s;
+}
+
 }  // namespace cv
 
 #include "persistence_stub.hpp"

@@ -107,7 +107,8 @@ void orc_stereo_rowband(const orc_kp* kl, const uint8_t* dl, int nl, const orc_k
  * median-distance outlier cut over all accepted matches.  Levels are given WITH their 19-px
  * REFLECT_101 border (pointer to pixel (0,0), like img_pyramid_).  Outputs: u_right[i], depth[i]
  * (-1 where there is no stereo match), sad[i] (the SAD of accepted matches, -1 otherwise).
- * Parity unpinned: frame.cc cannot be compiled here (Eigen/Sophus/DBoW2), this is a restatement. */
+ * Pinned: frame.cc as a file cannot be compiled here (Eigen/Sophus/DBoW2), but its lines 828-986 are spliced
+ * into oracle/ref_frame_shim.cc and compiled; tests/test_oracle_vs_ref_frame.py compares bit for bit. */
 typedef struct {
   const uint8_t* px;
   int w, h;
@@ -123,11 +124,14 @@ void orc_stereo_refine(const orc_level_view* left, const orc_level_view* right, 
  * map points: point p owns descriptor rows [offsets[p], offsets[p+1]); all-pairs Hamming distances,
  * per row the median (sorted row incl. the 0 self-distance, element int(0.5*(N-1))), the first row
  * with the least median wins.  best_idx[p] is relative to offsets[p] (-1 for a point without rows),
- * best_median[p] its median.  Parity unpinned (mappoint.cc cannot be compiled here). */
+ * best_median[p] its median.  Pinned on mappoint.cc:365-433 spliced into oracle/ref_frame_shim.cc
+ * (tests/test_oracle_vs_ref_frame.py). */
 void orc_distinctive(const uint8_t* desc, const int* offsets, int n_points, int* best_idx, int* best_median);
 
 /* Frame grid (frame.cc:438-465 AssignFeaturesToGrid + :679-746 GetFeaturesInArea) and the
- * best / second-best inner loop of SearchByProjection (orb_matcher.cc:66-113). */
+ * best / second-best inner loop of SearchByProjection (orb_matcher.cc:66-113).  Pinned on frame.cc:438-465,
+ * :679-759 and orb_matcher.cc:42-213 spliced into oracle/ref_frame_shim.cc (tests/test_oracle_vs_ref_frame.py
+ * runs the reference's whole SearchByProjection against this search + the greedy claim restated in the test). */
 typedef struct {
   float min_x, min_y, inv_w, inv_h; /* mnMinX, mnMinY, mfGridElementWidthInv/HeightInv */
   int cols, rows;                   /* FRAME_GRID_COLS=64, FRAME_GRID_ROWS=48 */

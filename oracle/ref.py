@@ -1,7 +1,9 @@
 """ctypes binding of oracle/_ref/liborb_ref.so -- TEST INFRASTRUCTURE.
 
 The library is the reference's own src/cam/orb_feature/orb_extractor.cc compiled unmodified on
-the mini-cv shim (oracle/minicv), plus DescriptorDistance.  It is built in the development
+the mini-cv shim (oracle/minicv), plus DescriptorDistance; _ref/libbow_ref.so is the reference's vendored DBoW2 and
+_ref/libframe_ref.so the reference's own lines of Frame::ComputeStereoMatches, the frame grid,
+MapPoint::ComputeDistinctiveDescriptors and ORBmatcher::SearchByProjection (oracle/ref_frame_shim.cc).  It is built in the development
 container (`make -C oracle ref`, needs /root/reference) and travels to the GPU box as a binary.
 """
 import ctypes as C
@@ -177,3 +179,92 @@ class Vocabulary:
         _bow().refbow_transform(self.h, _p(desc), n, levelsup, _p(ids), _p(vals), C.byref(nb), _p(nodes), _p(begin),
                                 C.byref(nf), _p(feats), C.byref(tot))
         return unpack_bow(n, ids, vals, nb.value, nodes, begin, nf.value, feats, tot.value)
+
+
+# ---------------------------------------------------------------- the reference's frame / map-point / matcher lines (libframe_ref.so)
+_FRAME_SO = os.path.join(_HERE, "_ref", "libframe_ref.so")
+_FRAME = None
+
+TRACK_POINT_DTYPE = np.dtype([("proj_x", "<f4"), ("proj_y", "<f4"), ("proj_xr", "<f4"), ("view_cos", "<f4"), ("depth", "<f4"),
+                              ("level", "<i4"), ("in_view", "<i4"), ("bad", "<i4")])
+
+
+def frame_available():
+    return available() and os.path.exists(_FRAME_SO)
+
+
+def _frame():
+    global _FRAME
+    if _FRAME is None:
+        if not frame_available():
+            raise RuntimeError("oracle/_ref/libframe_ref.so not built (needs /root/reference)")
+        L = C.CDLL(_FRAME_SO)
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.reff_stereo_matches.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, f, f, vp, vp]
+        L.reff_distinctive.argtypes = [vp, vp, i, vp, vp]
+        L.reff_search_by_projection.argtypes = [vp, vp, i, vp, f, f, f, f, vp, i, vp, vp, i, vp, f, f, i, f, vp]
+        L.reff_features_in_area.argtypes = [vp, i, f, f, f, f, f, f, f, i, i, vp, i]
+        _FRAME = L
+    return _FRAME
+
+
+def stereo_matches(levels_left, levels_right, kl, dl, kr, dr, scale_factors, inv_scale_factors, bf, mb):
+    """Frame::ComputeStereoMatches (frame.cc:828-986).  levels_*: per-level arrays WITH the 19-px border."""
+    from .oracle import LevelView
+    keep = []
+
+    def views(levels):
+        arr = (LevelView * len(levels))()
+        for j, a in enumerate(levels):
+            a = np.ascontiguousarray(a, np.uint8)
+            keep.append(a)
+            arr[j] = LevelView(a.ctypes.data + 19 * a.strides[0] + 19, a.shape[1] - 38, a.shape[0] - 38, a.strides[0])
+        return arr
+
+    vl, vr = views(levels_left), views(levels_right)
+    kl, kr = np.ascontiguousarray(kl, KP_DTYPE), np.ascontiguousarray(kr, KP_DTYPE)
+    dl, dr = np.ascontiguousarray(dl, np.uint8), np.ascontiguousarray(dr, np.uint8)
+    sf, isf = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(inv_scale_factors, np.float32)
+    ur, dp = np.empty(len(kl), np.float32), np.empty(len(kl), np.float32)
+    _frame().reff_stereo_matches(C.cast(vl, C.c_void_p), C.cast(vr, C.c_void_p), len(levels_left), _p(kl), len(kl), _p(dl),
+                                 _p(kr), len(kr), _p(dr), _p(sf), _p(isf), float(bf), float(mb), _p(ur), _p(dp))
+    return ur, dp
+
+
+def distinctive(desc, offsets):
+    """MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-433) per point: (chosen descriptor rows, has-descriptor flags)."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    out = np.zeros((n, 32), np.uint8)
+    chosen = np.zeros(n, np.int32)
+    _frame().reff_distinctive(_p(desc), _p(offsets), n, _p(out), _p(chosen))
+    return out, chosen
+
+
+def search_by_projection(keys_un, desc, bounds, scale_factors, points, point_desc, pre_matched=None, u_right=None, th=3.0,
+                         nnratio=0.8, far_points=False, th_far=50.0):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints)
+    (orb_matcher.cc:42-206) on a frame with Nleft == -1.  Returns (nmatches, assigned[n])."""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    points = np.ascontiguousarray(points, TRACK_POINT_DTYPE)
+    point_desc = np.ascontiguousarray(point_desc, np.uint8)
+    pm = None if pre_matched is None else np.ascontiguousarray(pre_matched, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    assigned = np.empty(len(keys_un), np.int32)
+    nm = _frame().reff_search_by_projection(_p(keys_un), _p(desc), len(keys_un), None if ur is None else _p(ur),
+                                            *[float(b) for b in bounds], _p(sf), len(sf), _p(points), _p(point_desc), len(points),
+                                            None if pm is None else _p(pm), float(th), float(nnratio), int(far_points), float(th_far),
+                                            _p(assigned))
+    return nm, assigned
+
+
+def features_in_area(keys_un, bounds, x, y, r, min_level=-1, max_level=-1):
+    """Frame::GetFeaturesInArea (frame.cc:679-746) on the grid of AssignFeaturesToGrid (:438-465): indices in visiting order."""
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    out = np.empty(len(keys_un) + 1, np.int32)
+    n = _frame().reff_features_in_area(_p(keys_un), len(keys_un), *[float(b) for b in bounds], float(x), float(y), float(r),
+                                       int(min_level), int(max_level), _p(out), len(out))
+    return out[:n].copy()

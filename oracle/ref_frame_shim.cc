@@ -8,7 +8,7 @@
 //   _ref/frame_stereo.inc        frame.cc:828-986      Frame::ComputeStereoMatches
 //   _ref/frame_grid.inc          frame.cc:438-465      Frame::AssignFeaturesToGrid
 //   _ref/frame_area.inc          frame.cc:679-759      Frame::GetFeaturesInArea, Frame::PosInGrid
-//   _ref/mappoint_distinct.inc   mappoint.cc:365-432   MapPoint::ComputeDistinctiveDescriptors
+//   _ref/mappoint_distinct.inc   mappoint.cc:365-433   MapPoint::ComputeDistinctiveDescriptors
 //   _ref/matcher_consts.inc      orb_matcher.cc:35-40  TH_HIGH / TH_LOW / HISTO_LENGTH, constructor
 //   _ref/matcher_project.inc     orb_matcher.cc:42-213 ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...),
 //                                                      ORBmatcher::RadiusByViewingCos

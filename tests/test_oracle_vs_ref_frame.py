@@ -1,0 +1,166 @@
+"""CPU: the matcher-side oracle rows against the reference's OWN LINES (oracle/_ref/libframe_ref.so =
+frame.cc:828-986, :438-465, :679-759, mappoint.cc:365-433, orb_matcher.cc:35-213 spliced by line range into the
+member declarations of oracle/ref_frame_shim.cc and compiled on the mini-cv shim).  This pins
+orc_stereo_rowband + orc_stereo_refine (Frame::ComputeStereoMatches), orc_distinctive
+(MapPoint::ComputeDistinctiveDescriptors) and orc_window_search(_stereo) (Frame::GetFeaturesInArea + the inner loop of
+ORBmatcher::SearchByProjection) -- the oracles the GPU tests of tests/test_gpu_match.py compare against."""
+import numpy as np
+import pytest
+
+from oracle import ref as R
+
+pytestmark = pytest.mark.skipif(not R.frame_available(), reason="oracle/_ref not built and /root/reference absent")
+
+W, H = 752, 480
+BF, MB = np.float32(47.90639384423901), np.float32(0.11)   # settings/EuRoC.yaml: Stereo.b * fx, mb = bf / fx
+
+
+def _stereo_pair(oracle, frame, shift, nf=1200):
+    left = oracle.blocks_v1(W, H, 1, frame)
+    right = oracle.blocks_v1(W, H, 1, frame, shift_x=shift, noise_seed=2)
+    el, er = oracle.Extractor(nf), oracle.Extractor(nf)
+    _, kl, dl = el(left)
+    _, kr, dr = er(right)
+    ll = [el.level(l, with_border=True) for l in range(8)]
+    lr = [er.level(l, with_border=True) for l in range(8)]
+    t = el.tables()
+    return kl, dl, kr, dr, ll, lr, t["scale"], t["inv_scale"]
+
+
+@pytest.mark.parametrize("frame,shift", [(3, 12), (5, 30), (6, 0), (7, 47)])
+def test_compute_stereo_matches_identical(oracle, frame, shift):
+    """BASELINE config 2 through the reference's Frame::ComputeStereoMatches vs row band + SAD refinement + median cut."""
+    kl, dl, kr, dr, ll, lr, sf, isf = _stereo_pair(oracle, frame, shift)
+    want_ur, want_dp = R.stereo_matches(ll, lr, kl, dl, kr, dr, sf, isf, BF, MB)
+    max_d = float(BF / MB)                                     # frame.cc:853-856: minZ = mb, maxD = bf / minZ
+    bi, bd = oracle.stereo_rowband(kl, dl, kr, dr, sf, H, 0.0, max_d)
+    ur, dp, sad = oracle.stereo_refine(ll, lr, kl, kr, bi, bd, sf, isf, 75, 0.0, max_d, BF)
+    assert ur.tobytes() == want_ur.tobytes() and dp.tobytes() == want_dp.tobytes()
+    assert (want_ur >= 0).sum() > 300
+
+
+def test_compute_stereo_matches_small_baseline(oracle):
+    """A tight disparity range (maxD = 20 px) rejects most candidates in the row band and in the disparity gate."""
+    kl, dl, kr, dr, ll, lr, sf, isf = _stereo_pair(oracle, 4, 12, nf=800)
+    bf, mb = np.float32(20.0), np.float32(1.0)
+    want_ur, want_dp = R.stereo_matches(ll, lr, kl, dl, kr, dr, sf, isf, bf, mb)
+    bi, bd = oracle.stereo_rowband(kl, dl, kr, dr, sf, H, 0.0, float(bf / mb))
+    ur, dp, _ = oracle.stereo_refine(ll, lr, kl, kr, bi, bd, sf, isf, 75, 0.0, float(bf / mb), bf)
+    assert ur.tobytes() == want_ur.tobytes() and dp.tobytes() == want_dp.tobytes()
+    assert 50 < (want_ur >= 0).sum() < len(kl)
+
+
+def test_distinctive_descriptors_identical(oracle):
+    rng = np.random.default_rng(11)
+    sizes = np.concatenate([[0, 1, 2, 3], rng.integers(2, 40, 200), [150]])
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = np.empty((offsets[-1], 32), np.uint8)
+    for p, (o, n) in enumerate(zip(offsets[:-1], sizes)):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        desc[o:o + n] = base
+        flips = rng.integers(0, 256, (n, 20))
+        for j in range(20):
+            desc[o + np.arange(n), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+        if n > 4 and p % 3 == 0:
+            desc[o + 1] = desc[o]                              # duplicates: equal medians, the first row wins
+    bi, _ = oracle.distinctive(desc, offsets)
+    want, chosen = R.distinctive(desc, offsets)
+    assert np.array_equal(chosen != 0, bi >= 0)
+    for p in range(len(sizes)):
+        if bi[p] >= 0:
+            assert np.array_equal(desc[offsets[p] + bi[p]], want[p]), p
+
+
+def _frame_and_points(oracle, seed, nq=600):
+    img = oracle.blocks_v1(W, H, seed, 0)
+    _, kps, desc = oracle.Extractor(1000)(img)
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, len(kps), nq)
+    pts = np.zeros(nq, R.TRACK_POINT_DTYPE)
+    pts["proj_x"] = kps["x"][src] + rng.normal(0, 4, nq).astype(np.float32)
+    pts["proj_y"] = kps["y"][src] + rng.normal(0, 4, nq).astype(np.float32)
+    pts["view_cos"] = rng.choice([0.9, 0.9985, 1.0], nq).astype(np.float32)
+    pts["depth"] = rng.uniform(1, 80, nq).astype(np.float32)
+    pts["level"] = np.clip(kps["octave"][src] + rng.integers(-1, 2, nq), 0, 7)
+    pts["in_view"] = rng.random(nq) < 0.9
+    pts["bad"] = rng.random(nq) < 0.05
+    pts["proj_x"][:10] = -300.0                                 # windows that miss the grid
+    pts["proj_y"][10:20] = 3000.0
+    qdesc = desc[src].copy()
+    flips = rng.integers(0, 256, (nq, 14))
+    for j in range(14):
+        qdesc[np.arange(nq), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+    qdesc[::9] = desc[src[::9]]                                 # distance-0 ties
+    return kps, desc, pts, qdesc, src, rng
+
+
+def _greedy_with_oracle(oracle, kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, th_far):
+    """orb_matcher.cc:42-134 around the oracle's window search: the greedy claim of frame keypoints in map-point order."""
+    min_x, max_x, min_y, max_y = bounds
+    geom = (min_x, min_y, np.float32(64) / np.float32(max_x - min_x), np.float32(48) / np.float32(max_y - min_y), 64, 48)
+    skip = np.zeros(len(kps), np.uint8) if pre is None else pre.astype(np.uint8).copy()
+    assigned = np.full(len(kps), -1, np.int32)
+    nm = 0
+    for i, p in enumerate(pts):
+        if not p["in_view"] or (far and p["depth"] > th_far) or p["bad"]:
+            continue
+        r = np.float32(2.5) if p["view_cos"] > 0.998 else np.float32(4.0)       # RadiusByViewingCos :208-213
+        if th != 1.0:
+            r = np.float32(r * np.float32(th))
+        rad = np.float32(r * sf[p["level"]])
+        q = np.zeros(1, oracle.WQ_DTYPE)
+        q["u"], q["v"], q["r"] = p["proj_x"], p["proj_y"], rad
+        q["min_level"], q["max_level"] = p["level"] - 1, p["level"]
+        if u_right is None:
+            res = oracle.window_search(kps, desc, geom, q, qdesc[i:i + 1], skip)[0]
+        else:
+            res = oracle.window_search(kps, desc, geom, q, qdesc[i:i + 1], skip, u_right,
+                                       np.array([p["proj_xr"]], np.float32), np.array([rad], np.float32))[0]
+        if res["best_idx"] < 0 or res["best_dist"] > 100:                          # :117 TH_HIGH
+            continue
+        if res["best_level"] == res["best_level2"] and res["best_dist"] > np.float32(nnratio) * np.float32(res["best_dist2"]):
+            continue
+        assigned[res["best_idx"]] = i                                                # :121
+        skip[res["best_idx"]] = 1                                                    # its map point now has observations
+        nm += 1
+    return nm, assigned
+
+
+@pytest.mark.parametrize("seed,th,nnratio,stereo,far", [(1, 3.0, 0.8, False, False), (2, 1.0, 0.8, False, True),
+                                                        (3, 5.0, 0.9, True, False), (4, 15.0, 0.6, True, True)])
+def test_search_by_projection_identical(oracle, seed, th, nnratio, stereo, far):
+    kps, desc, pts, qdesc, src, rng = _frame_and_points(oracle, seed)
+    bounds = (0.0, float(W), 0.0, float(H))
+    sf = oracle.Extractor(1000).tables()["scale"]
+    pre = (rng.random(len(kps)) < 0.2).astype(np.uint8)
+    u_right = None
+    if stereo:
+        u_right = np.where(rng.random(len(kps)) < 0.6, kps["x"] - rng.uniform(2, 60, len(kps)), -1.0).astype(np.float32)
+        pts["proj_xr"] = pts["proj_x"] - rng.uniform(2, 60, len(pts)).astype(np.float32)
+        ok = u_right[src] > 0
+        pts["proj_xr"][ok] = u_right[src][ok] + rng.normal(0, 2, ok.sum()).astype(np.float32)
+    want_nm, want = R.search_by_projection(kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, 40.0)
+    nm, got = _greedy_with_oracle(oracle, kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, 40.0)
+    assert nm == want_nm and np.array_equal(got, want)
+    assert want_nm > 100
+
+
+def test_features_in_area_order(oracle):
+    """The visiting order of the grid lookup (cells column-major, keypoints in index order inside a cell) is what
+    resolves distance ties in every window search: the oracle's best index on all-equal descriptors must be the
+    first index the reference's GetFeaturesInArea returns."""
+    img = oracle.blocks_v1(W, H, 5, 0)
+    _, kps, _ = oracle.Extractor(1000)(img)
+    bounds = (0.0, float(W), 0.0, float(H))
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    same = np.zeros((len(kps), 32), np.uint8)
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        x, y = rng.uniform(-20, W + 20), rng.uniform(-20, H + 20)
+        r = float(rng.choice([2.0, 9.0, 30.0, 90.0]))
+        lo, hi = int(rng.integers(-1, 6)), int(rng.integers(-1, 8))
+        idx = R.features_in_area(kps, bounds, x, y, r, lo, hi)
+        q = np.zeros(1, oracle.WQ_DTYPE)
+        q["u"], q["v"], q["r"], q["min_level"], q["max_level"] = x, y, r, lo, hi
+        res = oracle.window_search(kps, same, geom, q, same[:1])[0]
+        assert res["best_idx"] == (idx[0] if len(idx) else -1)
