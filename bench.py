@@ -384,6 +384,24 @@ def run_ours(args):
                "mean_words_per_frame": bow_words,
                "workload": "transform(features, BowVector, FeatureVector, 4) of %d frames x ~%d descriptors per rank, "
                            "synthetic vocabulary k=10 L=6 (%d nodes), TF-IDF / L1" % (B, int(mean_kp), len(vparent))}
+    # ---- bag-of-words guided matching: ORBmatcher::SearchByBoW (orb_matcher.cc:215-389) of every frame of the batch
+    # against its successor (key frame f -> frame f+1), on the FeatureVectors just computed, device-resident
+    pairs = torch.stack([torch.arange(B, dtype=torch.int32), (torch.arange(B, dtype=torch.int32) + 1) % B], 1).to(dev)
+    for _ in range(2):
+        sb_n, sb_match = m.SearchByBoW(kps, desc, n, bow, pairs, None, 0.7, True)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(reps):
+        sb_n, sb_match = m.SearchByBoW(kps, desc, n, bow, pairs, None, 0.7, True)
+    s1.record()
+    torch.cuda.synchronize()
+    sb_ms = max_over_ranks(s0.elapsed_time(s1)) / reps
+    barrier()
+    bow_out["search_by_bow"] = {"value": world * B / (sb_ms * 1e-3), "unit": "frame pairs/s", "ms_per_batch": sb_ms,
+                                "mean_matches_per_pair": float(sb_n.float().mean().item()),
+                                "workload": "SearchByBoW(KF f, Frame f+1, nnratio 0.7, orientation check) over the %d frames "
+                                            "of the batch, FeatureVectors at levelsup 4" % B}
     log('bag of words done')
     if rank == 0 and world == 1:  # the CPU restatement of DBoW2 on one thread, bounded sample (checker side: oracle/)
         from oracle import oracle as O
@@ -398,6 +416,17 @@ def run_ours(args):
         assert bow["bow_vals"][31, :nb].cpu().numpy().tobytes() == vals.tobytes(), "bag of words != CPU oracle"
         bow_out["cpu_baseline"] = {"value": 32 / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                                    "sample": "32 frames of this batch through oracle/bow_oracle.c (DBoW2 restatement)"}
+        k_host = kps[:33].cpu().numpy().view(O.KP_DTYPE).reshape(33, -1)
+        d33 = desc[:33].cpu().numpy()
+        fvs = [O.pack_feature_vector(*vo.transform(d33[f, :n_host[f]], 4)[2:]) for f in range(33)]
+        t0 = time.perf_counter()
+        for f in range(32):
+            wnm, want = O.search_by_bow(k_host[f, :n_host[f]], d33[f, :n_host[f]], None, fvs[f],
+                                        k_host[f + 1, :n_host[f + 1]], d33[f + 1, :n_host[f + 1]], fvs[f + 1], 0.7, True)
+        dt = time.perf_counter() - t0
+        assert int(sb_n[31].item()) == wnm and np.array_equal(sb_match[31, :n_host[32]].cpu().numpy(), want), "SearchByBoW != CPU oracle"
+        bow_out["search_by_bow"]["cpu_baseline"] = {"value": 32 / dt, "unit": "frame pairs/s", "cores": 1, "kind": "port",
+                                                    "sample": "32 pairs of this batch through orc_search_by_bow (oracle/orb_oracle.c)"}
     del voc, bow
 
     if rank != 0:

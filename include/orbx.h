@@ -256,6 +256,25 @@ int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
                               const float* q_u_right, const float* q_max_err, orbm_window_result* out,
                               int mem, void* stream);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389; callers
+ * tracking.cc:2053, 2909: TrackReferenceKeyFrame and Relocalization) for n_pairs (key frame, frame) pairs taken from
+ * one pool of frames in the [frame][cap] layout orbx_extract_batch and orbv_transform produce: frame f owns
+ * kps[f*cap + i], desc[(f*cap + i)*32], i < n_per_frame[f] (NULL: cap), and its FeatureVector fv_nodes / fv_begin
+ * [f*cap + j], j < fv_n[f], fv_feats[f*cap + p], p < fv_total[f] (see orbv_transform).  has_point[f*cap + i] != 0:
+ * the key frame's feature holds a map point that is not bad (:246-250; NULL: every feature does).  Pair p matches
+ * key frame pair_kf[p] against frame pair_f[p]: per shared vocabulary node every key-frame feature with a map point
+ * takes, in order, the nearest frame feature of the node that is still free (distance <= TH_LOW = 50 and
+ * d1 < nnratio * d2), then (check_orientation) only the matches in the three dominant bins of the 30-bin rotation
+ * histogram survive (ComputeThreeMaxima, :1841-1873).  Outputs: match[p*cap + i] = key-frame feature whose map point
+ * frame feature i receives (vpMapPointMatches[i]; -1 = NULL), n_matches[p] = the return value.  cap <= 2048.
+ * Covers the Nleft == -1 case (monocular and rectified stereo, the EuRoC configuration); the two-camera branches of
+ * :268-291 / :329-356 stay with the reference's host code. */
+int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+                       const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
+                       const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f,
+                       int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                       void* stream);
+
 /* Deterministic synthetic descriptors: 64-bit word j of row i is
  * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);

@@ -75,6 +75,7 @@ def lib():
         L.orc_stereo_refine.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i, f, f, f, vp, vp, vp]
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_window_search_stereo.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, vp]
+        L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         L.orc_splitmix64.restype = u64
         L.orc_splitmix64.argtypes = [u64]
         L.orc_synth_blocks_v1.argtypes = [vp, i, i, sz, u64, u64, i, u64]
@@ -360,6 +361,33 @@ def window_search(kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q
         lib().orc_window_search_stereo(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc), len(queries),
                                        None if sk is None else _p(sk), _p(ur), _p(qr), _p(qe), _p(out))
     return out
+
+
+def pack_feature_vector(nodes, groups):
+    """(node ids, [feature index arrays per node]) -> (nodes u32, begin i32, feats u32): the flat FeatureVector layout."""
+    nodes = np.ascontiguousarray(nodes, np.uint32)
+    begin = np.zeros(max(len(nodes), 1), np.int32)
+    if len(nodes):
+        begin[:len(nodes)] = np.concatenate([[0], np.cumsum([len(g) for g in groups])[:-1]])
+    feats = np.ascontiguousarray(np.concatenate([np.asarray(g, np.uint32) for g in groups]) if len(groups) else np.zeros(0, np.uint32), np.uint32)
+    return nodes, begin, feats
+
+
+def search_by_bow(kps_kf, desc_kf, has_point_kf, fv_kf, kps_f, desc_f, fv_f, nnratio=0.7, check_orientation=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (orb_matcher.cc:215-389, Nleft == -1).  fv_* = (nodes, begin, feats).
+    Returns (nmatches, match_of_f[n_f])."""
+    kps_kf, kps_f = np.ascontiguousarray(kps_kf, KP_DTYPE), np.ascontiguousarray(kps_f, KP_DTYPE)
+    desc_kf, desc_f = np.ascontiguousarray(desc_kf, np.uint8), np.ascontiguousarray(desc_f, np.uint8)
+    hp = None if has_point_kf is None else np.ascontiguousarray(has_point_kf, np.uint8)
+    nk, bk, fk = fv_kf
+    nf, bf_, ff = fv_f
+    fk = fk if len(fk) else np.zeros(1, np.uint32)
+    ff = ff if len(ff) else np.zeros(1, np.uint32)
+    out = np.empty(max(len(kps_f), 1), np.int32)
+    nm = lib().orc_search_by_bow(_p(kps_kf), _p(desc_kf), None if hp is None else _p(hp), _p(nk), _p(bk), len(nk), _p(fk),
+                                 len(fv_kf[2]), _p(kps_f), _p(desc_f), len(kps_f), _p(nf), _p(bf_), len(nf), _p(ff),
+                                 len(fv_f[2]), float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(kps_f)].copy()
 
 
 # ---------------------------------------------------------------- synthetic inputs

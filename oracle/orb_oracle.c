@@ -778,6 +778,80 @@ void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, con
   free(cnt); free(cell_of); free(fill); free(items);
 }
 
+/* ---- ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches), orb_matcher.cc:215-386, for a frame with
+ * Nleft == -1 (monocular / rectified stereo; the two-camera branches of :268-291 and :329-356 are not taken).
+ * The two FeatureVectors are given as sorted node ids + group starts + feature indices (the layout
+ * orc_vocab_transform / orbv_transform produce).  match_of_f[i] = key-frame feature whose map point frame
+ * feature i receives (vpMapPointMatches[i]), -1 = none.  Returns nmatches. */
+static void three_maxima(const int* histo, int L, int* ind1, int* ind2, int* ind3) { /* orb_matcher.cc:1841-1873 */
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = histo[i];
+    if (s > max1) { max3 = max2; max2 = max1; max1 = s; *ind3 = *ind2; *ind2 = *ind1; *ind1 = i; }
+    else if (s > max2) { max3 = max2; max2 = s; *ind3 = *ind2; *ind2 = i; }
+    else if (s > max3) { max3 = s; *ind3 = i; }
+  }
+  if (max2 < 0.1f * (float)max1) { *ind2 = -1; *ind3 = -1; }
+  else if (max3 < 0.1f * (float)max1) { *ind3 = -1; }
+}
+
+int orc_search_by_bow(const orc_kp* kps_kf, const uint8_t* desc_kf, const uint8_t* has_point_kf,
+                      const uint32_t* nodes_kf, const int* begin_kf, int n_nodes_kf, const uint32_t* feats_kf, int total_kf,
+                      const orc_kp* kps_f, const uint8_t* desc_f, int n_f,
+                      const uint32_t* nodes_f, const int* begin_f, int n_nodes_f, const uint32_t* feats_f, int total_f,
+                      float nnratio, int check_orientation, int* match_of_f) {
+  enum { HISTO_LENGTH = 30, TH_LOW = 50 };
+  int nmatches = 0;
+  int hist[HISTO_LENGTH] = {0};
+  int* bin_of = (int*)malloc(sizeof(int) * (size_t)(n_f ? n_f : 1));
+  const float factor = HISTO_LENGTH / 360.0f; /* :228 */
+  for (int i = 0; i < n_f; i++) { match_of_f[i] = -1; bin_of[i] = -1; }
+  int a = 0, b = 0;
+  while (a < n_nodes_kf && b < n_nodes_f) { /* :237-375: the intersection of two sorted maps */
+    if (nodes_kf[a] == nodes_f[b]) {
+      const int k0 = begin_kf[a], k1 = a + 1 < n_nodes_kf ? begin_kf[a + 1] : total_kf;
+      const int f0 = begin_f[b], f1 = b + 1 < n_nodes_f ? begin_f[b + 1] : total_f;
+      for (int ik = k0; ik < k1; ik++) {
+        const int real_kf = (int)feats_kf[ik];
+        if (has_point_kf && !has_point_kf[real_kf]) continue; /* :246-250: no map point, or a bad one */
+        int best1 = 256, best_idx = -1, best2 = 256;
+        for (int jf = f0; jf < f1; jf++) {
+          const int real_f = (int)feats_f[jf];
+          if (match_of_f[real_f] >= 0) continue; /* :265 */
+          const int dist = orc_hamming(desc_kf + 32 * (size_t)real_kf, desc_f + 32 * (size_t)real_f);
+          if (dist < best1) { best2 = best1; best1 = dist; best_idx = real_f; }
+          else if (dist < best2) { best2 = dist; }
+        }
+        if (best1 <= TH_LOW && (float)best1 < nnratio * (float)best2) { /* :307-309 */
+          match_of_f[best_idx] = real_kf;
+          if (check_orientation) { /* :318-328 */
+            float rot = kps_kf[real_kf].angle - kps_f[best_idx].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            bin_of[best_idx] = bin;
+            hist[bin]++;
+          }
+          nmatches++;
+        }
+      }
+      a++; b++;
+    } else if (nodes_kf[a] < nodes_f[b]) {
+      while (a < n_nodes_kf && nodes_kf[a] < nodes_f[b]) a++; /* lower_bound */
+    } else {
+      while (b < n_nodes_f && nodes_f[b] < nodes_kf[a]) b++;
+    }
+  }
+  if (check_orientation) { /* :377-391 */
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+    for (int i = 0; i < n_f; i++)
+      if (match_of_f[i] >= 0 && bin_of[i] != ind1 && bin_of[i] != ind2 && bin_of[i] != ind3) { match_of_f[i] = -1; nmatches--; }
+  }
+  free(bin_of);
+  return nmatches;
+}
+
 /* ---- synthetic inputs, SURVEY.md 8(d) ---- */
 uint64_t orc_splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -156,6 +156,18 @@ void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, con
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
                               orc_window_result* out);
 
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-386; Nleft == -1): per shared
+ * vocabulary node, every key-frame feature with a map point takes the best unclaimed frame feature of the node
+ * (<= TH_LOW, ratio test), in order; then the 30-bin rotation histogram keeps the three dominant bins
+ * (ComputeThreeMaxima :1841-1873).  FeatureVectors as sorted node ids / group starts / feature indices.
+ * match_of_f[i] = key-frame feature matched to frame feature i or -1; returns nmatches.
+ * Pinned on orb_matcher.cc:215-386 + :1841-1873 spliced into oracle/ref_frame_shim.cc. */
+int orc_search_by_bow(const orc_kp* kps_kf, const uint8_t* desc_kf, const uint8_t* has_point_kf,
+                      const uint32_t* nodes_kf, const int* begin_kf, int n_nodes_kf, const uint32_t* feats_kf, int total_kf,
+                      const orc_kp* kps_f, const uint8_t* desc_f, int n_f,
+                      const uint32_t* nodes_f, const int* begin_f, int n_nodes_f, const uint32_t* feats_f, int total_f,
+                      float nnratio, int check_orientation, int* match_of_f);
+
 /* ---- deterministic synthetic inputs ---- */
 uint64_t orc_splitmix64(uint64_t x);
 void orc_synth_blocks_v1(uint8_t* img, int w, int h, size_t stride, uint64_t seed, uint64_t frame,

@@ -204,6 +204,7 @@ def _frame():
         L.reff_distinctive.argtypes = [vp, vp, i, vp, vp]
         L.reff_search_by_projection.argtypes = [vp, vp, i, vp, f, f, f, f, vp, i, vp, vp, i, vp, f, f, i, f, vp]
         L.reff_features_in_area.argtypes = [vp, i, f, f, f, f, f, f, f, i, i, vp, i]
+        L.reff_search_by_bow.argtypes = [vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         _FRAME = L
     return _FRAME
 
@@ -268,3 +269,19 @@ def features_in_area(keys_un, bounds, x, y, r, min_level=-1, max_level=-1):
     n = _frame().reff_features_in_area(_p(keys_un), len(keys_un), *[float(b) for b in bounds], float(x), float(y), float(r),
                                        int(min_level), int(max_level), _p(out), len(out))
     return out[:n].copy()
+
+
+def search_by_bow(kps_kf, desc_kf, has_point_kf, fv_kf, kps_f, desc_f, fv_f, nnratio=0.7, check_orientation=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389 + ComputeThreeMaxima
+    :1841-1873).  fv_* = (nodes u32, begin i32, feats u32).  Returns (nmatches, match_of_f[n_f])."""
+    kps_kf, kps_f = np.ascontiguousarray(kps_kf, KP_DTYPE), np.ascontiguousarray(kps_f, KP_DTYPE)
+    desc_kf, desc_f = np.ascontiguousarray(desc_kf, np.uint8), np.ascontiguousarray(desc_f, np.uint8)
+    hp = None if has_point_kf is None else np.ascontiguousarray(has_point_kf, np.uint8)
+    (nk, bk, fk), (nf, bf_, ff) = fv_kf, fv_f
+    fk2 = fk if len(fk) else np.zeros(1, np.uint32)
+    ff2 = ff if len(ff) else np.zeros(1, np.uint32)
+    out = np.empty(max(len(kps_f), 1), np.int32)
+    nm = _frame().reff_search_by_bow(_p(kps_kf), _p(desc_kf), len(kps_kf), None if hp is None else _p(hp), _p(nk), _p(bk), len(nk),
+                                     _p(fk2), len(fk), _p(kps_f), _p(desc_f), len(kps_f), _p(nf), _p(bf_), len(nf), _p(ff2), len(ff),
+                                     float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(kps_f)].copy()

@@ -12,9 +12,11 @@
 //   _ref/matcher_consts.inc      orb_matcher.cc:35-40  TH_HIGH / TH_LOW / HISTO_LENGTH, constructor
 //   _ref/matcher_project.inc     orb_matcher.cc:42-213 ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...),
 //                                                      ORBmatcher::RadiusByViewingCos
+//   _ref/matcher_bow.inc         orb_matcher.cc:215-389  ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
+//   _ref/matcher_maxima.inc      orb_matcher.cc:1841-1873 ORBmatcher::ComputeThreeMaxima
 //   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
 // Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
-// orc_distinctive / orc_window_search(_stereo) of oracle/orb_oracle.c.
+// orc_distinctive / orc_window_search(_stereo) / orc_search_by_bow of oracle/orb_oracle.c.
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -32,10 +34,15 @@ using namespace std;
 #define FRAME_GRID_ROWS 48  // include/map/frame.h:40-41
 #define FRAME_GRID_COLS 64
 
+namespace DBoW2 {  // 3rdparty/DBoW2/DBoW2/FeatureVector.h:24: a std::map from node id to feature indices
+typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
+}
+
 namespace ORB_SLAM_FUSION {
 
 class MapPoint;
 class KeyFrame;
+struct GeometricCamera {};
 
 // the one member of OrbExtractor that frame.cc:834,913-933 reads
 struct OrbExtractor {
@@ -48,12 +55,14 @@ class ORBmatcher {
   static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
   int SearchByProjection(class Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3,
                          const bool bFarPoints = false, const float thFarPoints = 50.0f);
+  int SearchByBoW(KeyFrame *pKF, class Frame &F, std::vector<MapPoint *> &vpMapPointMatches);
   static const int TH_LOW;
   static const int TH_HIGH;
   static const int HISTO_LENGTH;
 
  protected:
   float RadiusByViewingCos(const float &viewCos);
+  void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);
   float mfNNratio;
   bool mbCheckOrientation;
 };
@@ -80,14 +89,22 @@ class Frame {  // include/map/frame.h: the members the spliced bodies use, same 
   int Nleft = -1, Nright = -1;
   std::vector<int> mvLeftToRightMatch, mvRightToLeftMatch;
   std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
+  DBoW2::FeatureVector mFeatVec;
+  GeometricCamera *cam_ = nullptr, *cam2_ = nullptr;
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
-class KeyFrame {
+class KeyFrame {  // include/map/keyframe.h: what mappoint.cc:365-433 and orb_matcher.cc:215-389 touch
  public:
   bool isBad() { return bad; }
+  std::vector<MapPoint *> GetMapPointMatches() { return mvpMapPoints; }
   bool bad = false;
   cv::Mat mDescriptors;
+  std::vector<MapPoint *> mvpMapPoints;
+  DBoW2::FeatureVector mFeatVec;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
+  int NLeft = -1;
+  GeometricCamera *cam_ = nullptr, *cam2_ = nullptr;
 };
 
 class MapPoint {  // include/map/mappoint.h
@@ -116,6 +133,8 @@ class MapPoint {  // include/map/mappoint.h
 #include "frame_stereo.inc"
 #include "mappoint_distinct.inc"
 #include "matcher_project.inc"
+#include "matcher_bow.inc"
+#include "matcher_maxima.inc"
 
 }  // namespace ORB_SLAM_FUSION
 
@@ -228,6 +247,36 @@ int reff_search_by_projection(const void *keys_un, const uint8_t *desc, int n, c
     MapPoint *p = F.mvpMapPoints[i];
     assigned[i] = (p && p != &occupied) ? (int)(p - mps.data()) : -1;
   }
+  return nm;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches): key frame = (keys, descriptors, has_point flags: the
+// feature holds a map point that is not bad, FeatureVector as sorted nodes / group starts / feature indices), frame
+// likewise.  match_of_f[i] = key-frame feature whose map point vpMapPointMatches[i] is, -1 = NULL.
+int reff_search_by_bow(const void *kps_kf, const uint8_t *desc_kf, int n_kf, const uint8_t *has_point_kf, const uint32_t *nodes_kf,
+                       const int *begin_kf, int n_nodes_kf, const uint32_t *feats_kf, int total_kf, const void *kps_f,
+                       const uint8_t *desc_f, int n_f, const uint32_t *nodes_f, const int *begin_f, int n_nodes_f,
+                       const uint32_t *feats_f, int total_f, float nnratio, int check_orientation, int *match_of_f) {
+  KeyFrame kf;
+  Frame F;
+  kf.mvKeysUn.assign((const cv::KeyPoint *)kps_kf, (const cv::KeyPoint *)kps_kf + n_kf);
+  kf.mvKeys = kf.mvKeysUn;
+  kf.mDescriptors = cv::Mat(n_kf, 32, CV_8U, (void *)desc_kf);
+  std::vector<MapPoint> mps(n_kf > 0 ? n_kf : 1);
+  kf.mvpMapPoints.assign(n_kf, (MapPoint *)nullptr);
+  for (int i = 0; i < n_kf; i++)
+    if (!has_point_kf || has_point_kf[i]) kf.mvpMapPoints[i] = &mps[i];
+  for (int j = 0; j < n_nodes_kf; j++)
+    kf.mFeatVec[nodes_kf[j]].assign(feats_kf + begin_kf[j], feats_kf + (j + 1 < n_nodes_kf ? begin_kf[j + 1] : total_kf));
+  F.N = n_f;
+  F.mvKeys.assign((const cv::KeyPoint *)kps_f, (const cv::KeyPoint *)kps_f + n_f);
+  F.mDescriptors = cv::Mat(n_f, 32, CV_8U, (void *)desc_f);
+  for (int j = 0; j < n_nodes_f; j++)
+    F.mFeatVec[nodes_f[j]].assign(feats_f + begin_f[j], feats_f + (j + 1 < n_nodes_f ? begin_f[j + 1] : total_f));
+  std::vector<MapPoint *> matches;
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  const int nm = matcher.SearchByBoW(&kf, F, matches);
+  for (int i = 0; i < n_f; i++) match_of_f[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
   return nm;
 }
 

@@ -5,10 +5,12 @@
 //   Frame::ComputeStereoMatches       frame.cc:836-900   -> StereoRowBand
 //   Frame::ComputeStereoFishEyeMatches frame.cc:1154-1162 -> KnnMatch2 + RatioTest
 //   SearchByProjection inner loop      orb_matcher.cc:66-113 -> WindowSearch (greedy claim stays on the host)
+//   ORBmatcher::SearchByBoW(KF, Frame) orb_matcher.cc:215-389 -> SearchByBoW (whole function, greedy claim included)
 #ifndef ORBMATCHER_GPU_H
 #define ORBMATCHER_GPU_H
 
 #include <cstdint>
+#include <map>
 #include <opencv2/opencv.hpp>
 #include <vector>
 
@@ -53,6 +55,16 @@ class ORBmatcherGpu {
   // observations[p] holds the descriptor rows of point p (the vDescriptors of :367-398); returns for
   // each point the index of the row with the least median distance to the others (-1 if empty).
   std::vector<int> ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& observations);
+
+  // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1):
+  // keys_kf = pKF->mvKeysUn, desc_kf = pKF->mDescriptors, has_point_kf[i] = pKF's feature i holds a map point that is
+  // not bad, featvec_kf = pKF->mFeatVec; keys_f = F.mvKeys, desc_f = F.mDescriptors, featvec_f = F.mFeatVec
+  // (DBoW2::FeatureVector is this std::map).  match_of_f[i] = index of the key-frame feature whose map point
+  // vpMapPointMatches[i] becomes (-1 = NULL); returns nmatches.  At most 2048 features per side.
+  int SearchByBoW(const std::vector<cv::KeyPoint>& keys_kf, const cv::Mat& desc_kf, const std::vector<uint8_t>& has_point_kf,
+                  const std::map<unsigned int, std::vector<unsigned int> >& featvec_kf, const std::vector<cv::KeyPoint>& keys_f,
+                  const cv::Mat& desc_f, const std::map<unsigned int, std::vector<unsigned int> >& featvec_f, float nnratio,
+                  bool check_orientation, std::vector<int>& match_of_f);
 
   struct Window { float u, v, r; int min_level, max_level; };
   struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };

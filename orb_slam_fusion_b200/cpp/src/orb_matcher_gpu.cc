@@ -1,6 +1,7 @@
 #include "cam/orb_feature/orb_matcher_gpu.h"
 
 #include <climits>
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -96,6 +97,49 @@ std::vector<int> ORBmatcherGpu::ComputeDistinctiveDescriptors(const std::vector<
   check(m_, orbm_distinctive(m_, desc.data(), offsets.data(), (int)obs.size(), max_rows, best.data(), median.data(),
                              ORBX_MEM_HOST, nullptr));
   return best;
+}
+
+int ORBmatcherGpu::SearchByBoW(const std::vector<cv::KeyPoint>& keys_kf, const cv::Mat& desc_kf,
+                               const std::vector<uint8_t>& has_point_kf,
+                               const std::map<unsigned int, std::vector<unsigned int> >& featvec_kf,
+                               const std::vector<cv::KeyPoint>& keys_f, const cv::Mat& desc_f,
+                               const std::map<unsigned int, std::vector<unsigned int> >& featvec_f, float nnratio,
+                               bool check_orientation, std::vector<int>& match_of_f) {
+  typedef std::map<unsigned int, std::vector<unsigned int> > FeatVec;
+  const int nk = (int)keys_kf.size(), nf = (int)keys_f.size();
+  const int cap = std::max(1, std::max(nk, nf));
+  match_of_f.assign((size_t)nf, -1);
+  // a pool of two frames in the [frame][cap] layout of orbm_search_by_bow: 0 = key frame, 1 = frame
+  std::vector<orbx_kp> kps(2 * (size_t)cap);
+  std::vector<uint8_t> desc(2 * (size_t)cap * 32, 0), has(2 * (size_t)cap, 0);
+  std::vector<uint32_t> nodes(2 * (size_t)cap, 0), feats(2 * (size_t)cap, 0);
+  std::vector<int32_t> begin(2 * (size_t)cap, 0);
+  int32_t fv_n[2] = {0, 0}, fv_total[2] = {0, 0};
+  const int32_t npf[2] = {nk, nf};
+  if (nk) std::memcpy(kps.data(), keys_kf.data(), sizeof(orbx_kp) * (size_t)nk);
+  if (nf) std::memcpy(kps.data() + cap, keys_f.data(), sizeof(orbx_kp) * (size_t)nf);
+  const std::vector<uint8_t> dk = dense_rows(desc_kf), df = dense_rows(desc_f);
+  if (nk) std::memcpy(desc.data(), dk.data(), 32 * (size_t)nk);
+  if (nf) std::memcpy(desc.data() + 32 * (size_t)cap, df.data(), 32 * (size_t)nf);
+  for (int i = 0; i < nk; ++i) has[i] = i < (int)has_point_kf.size() ? has_point_kf[i] : 0;
+  const FeatVec* fv[2] = {&featvec_kf, &featvec_f};
+  for (int s = 0; s < 2; ++s) {
+    const size_t o = (size_t)s * cap;
+    for (FeatVec::const_iterator it = fv[s]->begin(); it != fv[s]->end(); ++it) {
+      nodes[o + fv_n[s]] = it->first;
+      begin[o + fv_n[s]] = fv_total[s];
+      ++fv_n[s];
+      for (size_t j = 0; j < it->second.size(); ++j) feats[o + fv_total[s]++] = it->second[j];
+    }
+  }
+  const int32_t pk = 0, pf = 1;
+  std::vector<int32_t> match((size_t)cap, -1);
+  int32_t nm = 0;
+  check(m_, orbm_search_by_bow(m_, kps.data(), desc.data(), cap, 2, npf, nodes.data(), begin.data(), fv_n, feats.data(), fv_total,
+                               has.data(), &pk, &pf, 1, nnratio, check_orientation ? 1 : 0, match.data(), &nm, ORBX_MEM_HOST,
+                               nullptr));
+  for (int i = 0; i < nf; ++i) match_of_f[i] = match[i];
+  return nm;
 }
 
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,

@@ -318,6 +318,124 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
   return 1;
 }
 
+// ------------------------------------------------------------------ SearchByBoW
+// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1) for a batch of
+// (key frame, frame) pairs drawn from one pool of frames in the [frame][cap] layout of orbx_extract_batch /
+// orbv_transform.  One CTA per pair.  A frame feature lies in exactly one FeatureVector node, so the reference's
+// sequential dependence ("skip frame features that already took a map point", :265) never crosses a node: a warp
+// owns a shared node and walks its key-frame features IN ORDER, the lanes split the node's frame features; strict
+// "<, first wins" is the minimum of the key (distance, position in the node), the second-best distance the
+// second-smallest key.  Then the 30-bin rotation histogram and ComputeThreeMaxima (:1841-1873) on the CTA.
+__global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap,
+                                                       const uint32_t* __restrict__ fv_nodes, const int32_t* __restrict__ fv_begin,
+                                                       const int32_t* __restrict__ fv_n, const uint32_t* __restrict__ fv_feats,
+                                                       const int32_t* __restrict__ fv_total, const int32_t* __restrict__ n_per_frame,
+                                                       const uint8_t* __restrict__ has_point, const int32_t* __restrict__ pair_kf,
+                                                       const int32_t* __restrict__ pair_f, float nnratio, int check_orientation,
+                                                       int32_t* __restrict__ match, int32_t* __restrict__ n_matches) {
+  constexpr int kHisto = 30, kThLow = 50;  // ORBmatcher::HISTO_LENGTH, TH_LOW (orb_matcher.cc:36-37)
+  __shared__ int hist[kHisto];
+  __shared__ int keep3[3];
+  __shared__ int n_kept;
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const size_t ok = (size_t)pair_kf[p] * cap, of = (size_t)pair_f[p] * cap;
+  const int nf = n_per_frame ? max(0, min(n_per_frame[pair_f[p]], cap)) : cap;
+  int32_t* mt = match + (size_t)p * cap;
+  for (int i = tid; i < cap; i += 256) mt[i] = -1;
+  if (tid < kHisto) hist[tid] = 0;
+  if (tid == 0) n_kept = 0;
+  __syncthreads();
+  const int nnk = fv_n[pair_kf[p]], nnf = fv_n[pair_f[p]];
+  const int tot_k = fv_total[pair_kf[p]], tot_f = fv_total[pair_f[p]];
+  const uint32_t *nodes_k = fv_nodes + ok, *nodes_f = fv_nodes + of, *feats_k = fv_feats + ok, *feats_f = fv_feats + of;
+  const int32_t *begin_k = fv_begin + ok, *begin_f = fv_begin + of;
+  for (int a = wrp; a < nnk; a += 8) {
+    const uint32_t nid = nodes_k[a];
+    int lo = 0, hi = nnf;  // lower_bound of nid in the frame's sorted node ids
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (nodes_f[mid] < nid) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= nnf || nodes_f[lo] != nid) continue;
+    const int k0 = begin_k[a], k1 = a + 1 < nnk ? begin_k[a + 1] : tot_k;
+    const int f0 = begin_f[lo], f1 = lo + 1 < nnf ? begin_f[lo + 1] : tot_f;
+    for (int ik = k0; ik < k1; ik++) {
+      const int real_k = (int)feats_k[ik];
+      if (has_point && !has_point[ok + real_k]) continue;  // :246-250
+      uint32_t dk[8];
+      load_row(desc + 32 * (ok + real_k), dk);
+      unsigned long long b0 = ~0ull, b1 = ~0ull;
+      for (int jf = f0 + lane; jf < f1; jf += 32) {
+        const int real_f = (int)feats_f[jf];
+        if (real_f >= nf || mt[real_f] >= 0) continue;  // :265 already holds a map point
+        uint32_t df[8];
+        load_row(desc + 32 * (of + real_f), df);
+        const unsigned long long key = ((unsigned long long)ham256(dk, df) << 32) | (unsigned)(jf - f0);
+        b1 = min(b1, max(b0, key));
+        b0 = min(b0, key);
+      }
+      warp_top2(b0, b1);
+      if (lane == 0 && b0 != ~0ull) {
+        const int d1 = (int)(b0 >> 32), d2 = b1 == ~0ull ? 256 : (int)(b1 >> 32);
+        if (d1 <= kThLow && (float)d1 < f_mul(nnratio, (float)d2))  // :307-309
+          mt[feats_f[f0 + (int)(b0 & 0xFFFFFFFFu)]] = real_k;
+      }
+      __syncwarp();  // the claim is visible to the lanes before the next key-frame feature
+    }
+  }
+  __syncthreads();
+  // rotation consistency (:318-328, :372-386): bin of every match, the three dominant bins survive
+  const float factor = 30 / 360.0f;
+  int my_bin[8];  // cap <= 2048: up to 8 frame features per thread
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int i = tid + 256 * r;
+    my_bin[r] = -1;
+    if (i < cap && mt[i] >= 0) {
+      float rot = f_sub(kps[ok + mt[i]].angle, kps[of + i].angle);
+      if (rot < 0.0f) rot = f_add(rot, 360.0f);
+      int bin = (int)roundf(f_mul(rot, factor));
+      if (bin == kHisto) bin = 0;
+      my_bin[r] = bin < 0 ? 0 : (bin > kHisto - 1 ? kHisto - 1 : bin);
+      if (check_orientation) atomicAdd(&hist[my_bin[r]], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < kHisto; i++) {
+      const int s = hist[i];
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+      else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < f_mul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < f_mul(0.1f, (float)max1)) { ind3 = -1; }
+    keep3[0] = ind1; keep3[1] = ind2; keep3[2] = ind3;
+  }
+  __syncthreads();
+  int kept = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (my_bin[r] < 0) continue;
+    if (check_orientation && my_bin[r] != keep3[0] && my_bin[r] != keep3[1] && my_bin[r] != keep3[2]) mt[tid + 256 * r] = -1;
+    else kept++;
+  }
+  if (kept) atomicAdd(&n_kept, kept);
+  __syncthreads();
+  if (tid == 0) n_matches[p] = n_kept;
+}
+
+int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+                         const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
+                         const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f, int n_pairs, float nnratio,
+                         int check_orientation, int32_t* match, int32_t* n_matches, cudaStream_t st) {
+  if (n_pairs <= 0) return 0;
+  k_search_by_bow<<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame, has_point,
+                                           pair_kf, pair_f, nnratio, check_orientation, match, n_matches);
+  return 1;
+}
+
 // ------------------------------------------------------------------ stereo sub-pixel refinement
 // The rest of Frame::ComputeStereoMatches (frame.cc:903-985): for every left keypoint whose row-band
 // match is closer than thOrbDist, an 11x11 SAD over 11 horizontal shifts on the keypoint's pyramid

@@ -353,6 +353,49 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
   return orbm_window_search_stereo(m, kps, desc, n, geom, queries, qdesc, nq, skip, nullptr, nullptr, nullptr, out, mem, stream);
 }
 
+int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+                       const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
+                       const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f,
+                       int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                       void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (cap < 1 || cap > 2048 || n_frames < 1 || n_pairs < 0 || !kps || !desc || !fv_nodes || !fv_begin || !fv_n || !fv_feats ||
+      !fv_total || (n_pairs > 0 && (!pair_kf || !pair_f || !match || !n_matches)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (n_pairs == 0) return ORBX_OK;
+  const size_t fc = (size_t)n_frames * cap;
+  if (mem == ORBX_MEM_HOST) {
+    for (int p = 0; p < n_pairs; p++)
+      if (pair_kf[p] < 0 || pair_kf[p] >= n_frames || pair_f[p] < 0 || pair_f[p] >= n_frames)
+        return fail(m, ORBX_E_ARG, "pair %d refers to a frame outside the pool", p);
+    TRY(arena_reserve(m, pad256(fc * sizeof(orbx_kp)) + pad256(fc * 32) + 3 * pad256(fc * 4) + pad256(fc) + 3 * pad256((size_t)n_frames * 4) +
+                             3 * pad256((size_t)n_pairs * 4) + pad256((size_t)n_pairs * cap * 4)));
+  }
+  const orbx_kp* dk;
+  const uint8_t *dd, *dhp;
+  const uint32_t *dnodes, *dfeats;
+  const int32_t *dbegin, *dfn, *dft, *dnpf, *dpk, *dpf;
+  TRY(stage_in(m, mem, kps, fc, &dk, st));
+  TRY(stage_in(m, mem, desc, fc * 32, &dd, st));
+  TRY(stage_in(m, mem, fv_nodes, fc, &dnodes, st));
+  TRY(stage_in(m, mem, fv_begin, fc, &dbegin, st));
+  TRY(stage_in(m, mem, fv_feats, fc, &dfeats, st));
+  TRY(stage_in(m, mem, has_point, fc, &dhp, st));
+  TRY(stage_in(m, mem, fv_n, (size_t)n_frames, &dfn, st));
+  TRY(stage_in(m, mem, fv_total, (size_t)n_frames, &dft, st));
+  TRY(stage_in(m, mem, n_per_frame, (size_t)n_frames, &dnpf, st));
+  TRY(stage_in(m, mem, pair_kf, (size_t)n_pairs, &dpk, st));
+  TRY(stage_in(m, mem, pair_f, (size_t)n_pairs, &dpf, st));
+  int32_t* dmatch = stage_out(m, mem, match, (size_t)n_pairs * cap);
+  int32_t* dnm = stage_out(m, mem, n_matches, (size_t)n_pairs);
+  m->launches += launch_search_by_bow(dk, dd, cap, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dpk, dpf, n_pairs, nnratio,
+                                      check_orientation, dmatch, dnm, st);
+  TRY(finish_out(m, mem, match, dmatch, (size_t)n_pairs * cap, st));
+  TRY(finish_out(m, mem, n_matches, dnm, (size_t)n_pairs, st));
+  return end(m, mem, st);
+}
+
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream) {
   if (!dst || n < 0) return ORBX_E_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;

@@ -164,6 +164,44 @@ class ORBmatcher:
                                                bm.ctypes.data, A.MEM_HOST, None))
         return bi, bm
 
+    # ---- bag-of-words guided matching
+    def SearchByBoW(self, kps, desc, n_per_frame, fv, pairs, has_point=None, nnratio=0.7, check_orientation=True):
+        """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389) for a batch of
+        (key frame, frame) pairs out of one pool of frames in the [frame][cap] layout of OrbExtractor.extract_batch and
+        ORBVocabulary.transform_batch: kps [F, cap] keypoint records, desc [F, cap, 32], n_per_frame [F] (or None),
+        fv = the dict transform_batch returned, pairs [n_pairs, 2] int32 (key frame, frame), has_point [F, cap] uint8
+        or None.  Returns (n_matches [n_pairs], match [n_pairs, cap]): match[p, i] = key-frame feature whose map point
+        frame feature i receives, -1 = none.  numpy in -> numpy out; CUDA torch tensors in -> CUDA tensors out, the call
+        only enqueues on torch's current stream."""
+        if type(desc).__module__.startswith("torch"):
+            import torch
+            F, cap = desc.shape[0], desc.shape[1]
+            dev = desc.device
+            assert desc.is_cuda and desc.is_contiguous() and kps.is_cuda and kps.is_contiguous() and kps.element_size() * kps[0, 0].numel() == 28
+            pairs = pairs.to(device=dev, dtype=torch.int32)
+            kf, ff = pairs[:, 0].contiguous(), pairs[:, 1].contiguous()
+            match = torch.empty((len(kf), cap), dtype=torch.int32, device=dev)
+            nm = torch.empty(len(kf), dtype=torch.int32, device=dev)
+            mem, stream = A.MEM_DEVICE, A.torch_stream(dev)
+        else:
+            kps = np.ascontiguousarray(kps, A.KP_DTYPE)
+            F, cap = kps.shape
+            desc = np.ascontiguousarray(desc, np.uint8).reshape(F, cap, 32)
+            n_per_frame = None if n_per_frame is None else np.ascontiguousarray(n_per_frame, np.int32)
+            has_point = None if has_point is None else np.ascontiguousarray(has_point, np.uint8).reshape(F, cap)
+            pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+            kf, ff = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+            match = np.empty((len(kf), cap), np.int32)
+            nm = np.empty(len(kf), np.int32)
+            mem, stream = A.MEM_HOST, None
+        for key in ("fv_nodes", "fv_begin", "fv_feats"):
+            assert tuple(fv[key].shape) == (F, cap), key
+        self._check(self._lib.orbm_search_by_bow(self._m, A.ptr(kps), A.ptr(desc), cap, F, A.ptr(n_per_frame), A.ptr(fv["fv_nodes"]),
+                                                 A.ptr(fv["fv_begin"]), A.ptr(fv["fv_n"]), A.ptr(fv["fv_feats"]), A.ptr(fv["fv_total"]),
+                                                 A.ptr(has_point), A.ptr(kf), A.ptr(ff), len(kf), nnratio, int(check_orientation),
+                                                 A.ptr(match), A.ptr(nm), mem, stream))
+        return nm, match
+
     # ---- projection window
     def window_search(self, kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q_u_right=None, q_max_err=None):
         """Best / second-best frame keypoint per projected map point (orb_matcher.cc:66-113, 451-479, 1567-1608).

@@ -86,6 +86,14 @@ int main(int argc, char** argv) {
     }
     const uint32_t w0 = desc.rows ? voc.transform(desc.row(0)) : 0;
     put(fo, &w0, 4);
+    // ORBmatcher::SearchByBoW (orb_matcher.cc:215-389) of the frame against itself: every feature that holds a map
+    // point (every third does not) must claim itself
+    std::vector<uint8_t> has_point(keys.size(), 1);
+    for (size_t i = 0; i < has_point.size(); i += 3) has_point[i] = 0;
+    std::vector<int> match_of_f;
+    const int32_t nmatch = matcher.SearchByBoW(keys, desc, has_point, fvec, keys, desc, fvec, 0.7f, true, match_of_f);
+    put(fo, &nmatch, 4);
+    put(fo, match_of_f.data(), match_of_f.size() * sizeof(int));
   }
   fclose(fo);
   delete extractor;

@@ -24,6 +24,7 @@ def test_facade_compiles_and_links_against_the_c_abi():
     used = {l.split()[-1] for l in syms.splitlines() if " orbx_" in l or " orbm_" in l}
     assert {"orbx_create", "orbx_extract", "orbx_pyramid_level", "orbm_knn2", "orbm_stereo_rowband"} <= used
     assert {"orbv_load_text", "orbv_transform"} <= {l.split()[-1] for l in syms.splitlines() if " orbv_" in l}
+    assert "orbm_search_by_bow" in used
 
 
 @pytest.mark.gpu
@@ -77,4 +78,12 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
         fl = np.frombuffer(buf, np.uint32, cnt, off); off += 4 * cnt
         assert node == nodes[j] and np.array_equal(fl, feats[j])
     assert int(np.frombuffer(buf, np.uint32, 1, off)[0]) == int(vo.features(rd[:1])[0][0]); off += 4
+    # ORBmatcherGpu::SearchByBoW of the frame against itself (orb_matcher.cc:215-389)
+    nmatch = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    match = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    has_point = np.ones(n, np.uint8)
+    has_point[::3] = 0
+    fv = oracle.pack_feature_vector(nodes, feats)
+    wnm, want = oracle.search_by_bow(rk, rd, has_point, fv, rk, rd, fv, 0.7, True)
+    assert nmatch == wnm and np.array_equal(match, want) and wnm > n // 3
     assert off == len(buf)

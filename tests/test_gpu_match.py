@@ -258,3 +258,54 @@ def test_window_search(P, m, oracle):
 def test_popc_peak_microbenchmark(P):
     peak = P.popc_peak(0)
     assert 1e12 < peak < 2e13      # 148 SMs x 16 popc/clk x ~1.9 GHz = 4.5e12
+
+
+def test_search_by_bow(P, m, oracle):
+    """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) (orb_matcher.cc:215-389) batched over pairs of a frame pool:
+    extraction -> bag-of-words transform -> node-restricted greedy matching -> rotation histogram, vs the CPU oracle
+    (which tests/test_oracle_vs_ref_frame.py pins on the reference's own lines)."""
+    w, h, nfeat, k, L = 640, 400, 800, 6, 4
+    vp_ = oracle.synth_vocab(k, L, seed=41)
+    voc, vo = P.ORBVocabulary(k, L, *vp_), oracle.Vocabulary(k, L, *vp_)
+    ex = P.OrbExtractor(nfeat, 1.2, 8, 20, 7)
+    views = [(1, 0, 1), (1, 3, 8), (1, 9, 9), (2, 0, 2), (2, 4, 5), (3, 0, 3)]      # (scene, shift, noise seed)
+    frames = [oracle.blocks_v1(w, h, s, 0, shift_x=sh, noise_seed=ns) for s, sh, ns in views]
+    ext = [ex(f) for f in frames]
+    cap = max(len(e[1]) for e in ext) + 5
+    F = len(frames)
+    kps = np.zeros((F, cap), P.KP_DTYPE)
+    desc = np.zeros((F, cap, 32), np.uint8)
+    npf = np.zeros(F, np.int32)
+    for f, (_, kk, dd) in enumerate(ext):
+        kps[f, :len(kk)], desc[f, :len(kk)], npf[f] = kk, dd, len(kk)
+    rng = np.random.default_rng(5)
+    has_point = (rng.random((F, cap)) < 0.85).astype(np.uint8)
+    pairs = np.array([(0, 1), (1, 0), (0, 2), (3, 4), (4, 3), (0, 3), (5, 5), (2, 1)], np.int32)
+    for levelsup, ratio, ori in [(2, 0.7, True), (3, 0.75, True), (1, 0.9, False), (4, 0.6, True)]:
+        fv = voc.transform_batch(desc, npf, levelsup)
+        nm, match = m.SearchByBoW(kps, desc, npf, fv, pairs, has_point, ratio, ori)
+        for p, (a, b) in enumerate(pairs):
+            fva = oracle.pack_feature_vector(*vo.transform(desc[a, :npf[a]], levelsup)[2:])
+            fvb = oracle.pack_feature_vector(*vo.transform(desc[b, :npf[b]], levelsup)[2:])
+            wnm, want = oracle.search_by_bow(kps[a, :npf[a]], desc[a, :npf[a]], has_point[a, :npf[a]], fva,
+                                             kps[b, :npf[b]], desc[b, :npf[b]], fvb, ratio, ori)
+            assert nm[p] == wnm and np.array_equal(match[p, :npf[b]], want), (levelsup, p)
+            assert (match[p, npf[b]:] == -1).all()
+        assert nm[0] > 40 and nm[6] > 100 and nm[5] < nm[0]      # same scene matches, different scenes mostly do not
+    # no map points at all / an empty pair list
+    nm, match = m.SearchByBoW(kps, desc, npf, fv, pairs[:2], np.zeros((F, cap), np.uint8))
+    assert (nm == 0).all() and (match == -1).all()
+    nm, match = m.SearchByBoW(kps, desc, npf, fv, pairs[:0])
+    assert len(nm) == 0
+    # device-resident pool: CUDA tensors in, CUDA tensors out
+    import torch
+    dev = torch.device("cuda", 0)
+    t = lambda a: torch.from_numpy(a.view(np.uint8) if a.dtype.fields else a).to(dev)   # noqa: E731
+    tk = torch.from_numpy(kps.view(np.float32).reshape(F, cap, 7).copy()).to(dev)
+    td = t(desc)
+    fvd = voc.transform_batch(td, t(npf), 2)
+    nm_d, match_d = m.SearchByBoW(tk, td, t(npf), fvd, torch.from_numpy(pairs), t(has_point), 0.7, True)
+    fvh = voc.transform_batch(desc, npf, 2)
+    nm_h, match_h = m.SearchByBoW(kps, desc, npf, fvh, pairs, has_point, 0.7, True)
+    torch.cuda.synchronize()
+    assert np.array_equal(nm_d.cpu().numpy(), nm_h) and np.array_equal(match_d.cpu().numpy(), match_h)

@@ -164,3 +164,34 @@ def test_features_in_area_order(oracle):
         q["u"], q["v"], q["r"], q["min_level"], q["max_level"] = x, y, r, lo, hi
         res = oracle.window_search(kps, same, geom, q, same[:1])[0]
         assert res["best_idx"] == (idx[0] if len(idx) else -1)
+
+
+def _bow_pair(oracle, seed, shift, k=6, L=4, levelsup=2, nf=800):
+    """Two views of one scene (a key frame and a frame shifted by `shift` px with other noise) and their FeatureVectors."""
+    vocab = oracle.Vocabulary(k, L, *oracle.synth_vocab(k, L, seed=seed + 40))
+    a = oracle.blocks_v1(640, 400, seed, 0)
+    b = oracle.blocks_v1(640, 400, seed, 0, shift_x=shift, noise_seed=seed + 7)
+    ex = oracle.Extractor(nf)
+    _, ka, da = ex(a)
+    _, kb, db = ex(b)
+    fva = oracle.pack_feature_vector(*vocab.transform(da, levelsup)[2:])
+    fvb = oracle.pack_feature_vector(*vocab.transform(db, levelsup)[2:])
+    return ka, da, fva, kb, db, fvb
+
+
+@pytest.mark.parametrize("seed,shift,ratio,ori,levelsup", [(1, 3, 0.7, True, 2), (2, 8, 0.75, True, 3), (3, 0, 0.9, False, 2),
+                                                           (4, 5, 0.6, True, 1), (5, 2, 0.7, True, 4)])
+def test_search_by_bow_identical(oracle, seed, shift, ratio, ori, levelsup):
+    ka, da, fva, kb, db, fvb = _bow_pair(oracle, seed, shift, levelsup=levelsup)
+    rng = np.random.default_rng(seed)
+    has_point = (rng.random(len(ka)) < 0.8).astype(np.uint8)
+    want_nm, want = R.search_by_bow(ka, da, has_point, fva, kb, db, fvb, ratio, ori)
+    nm, got = oracle.search_by_bow(ka, da, has_point, fva, kb, db, fvb, ratio, ori)
+    assert nm == want_nm and np.array_equal(got, want)
+    assert want_nm > 30
+    # all key-frame features hold points; identical frames -> every match is the feature itself
+    nm2, got2 = oracle.search_by_bow(ka, da, None, fva, ka, da, fva, ratio, ori)
+    want_nm2, want2 = R.search_by_bow(ka, da, None, fva, ka, da, fva, ratio, ori)
+    assert nm2 == want_nm2 and np.array_equal(got2, want2)
+    hit = got2 >= 0
+    assert hit.sum() > 100 and (da[got2[hit]] == da[np.nonzero(hit)[0]]).all()
