@@ -275,6 +275,17 @@ int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int c
                        int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
                        void* stream);
 
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (orb_matcher.cc:697-815; caller
+ * loopclosing.cc:571, place recognition) over the same pool / pair layout: both features of a match must hold a good
+ * map point (has_point applies to both sides), the distance gate is the strict d1 < TH_LOW, every feature of key
+ * frame 2 is claimed at most once, and the result is indexed by the feature of key frame 1:
+ * match[p*cap + i] = feature of key frame pair_2[p] whose map point vpMatches12[i] is (-1 = NULL). */
+int orbm_search_by_bow_kf(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+                          const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
+                          const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2,
+                          int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                          void* stream);
+
 /* Deterministic synthetic descriptors: 64-bit word j of row i is
  * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);

@@ -76,6 +76,7 @@ def lib():
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_window_search_stereo.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
+        L.orc_search_by_bow_kf.argtypes = [vp, vp, vp, i, vp, vp, i, vp, i, vp, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         L.orc_splitmix64.restype = u64
         L.orc_splitmix64.argtypes = [u64]
         L.orc_synth_blocks_v1.argtypes = [vp, i, i, sz, u64, u64, i, u64]
@@ -388,6 +389,22 @@ def search_by_bow(kps_kf, desc_kf, has_point_kf, fv_kf, kps_f, desc_f, fv_f, nnr
                                  len(fv_kf[2]), _p(kps_f), _p(desc_f), len(kps_f), _p(nf), _p(bf_), len(nf), _p(ff),
                                  len(fv_f[2]), float(nnratio), int(check_orientation), _p(out))
     return nm, out[:len(kps_f)].copy()
+
+
+def search_by_bow_kf(kps1, desc1, has_point1, fv1, kps2, desc2, has_point2, fv2, nnratio=0.7, check_orientation=True):
+    """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815).  Returns (nmatches, match_of_1[n1])."""
+    kps1, kps2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    hp1 = None if has_point1 is None else np.ascontiguousarray(has_point1, np.uint8)
+    hp2 = None if has_point2 is None else np.ascontiguousarray(has_point2, np.uint8)
+    (n1, b1, f1), (n2, b2, f2) = fv1, fv2
+    f1p = f1 if len(f1) else np.zeros(1, np.uint32)
+    f2p = f2 if len(f2) else np.zeros(1, np.uint32)
+    out = np.empty(max(len(kps1), 1), np.int32)
+    nm = lib().orc_search_by_bow_kf(_p(kps1), _p(desc1), None if hp1 is None else _p(hp1), len(kps1), _p(n1), _p(b1), len(n1), _p(f1p),
+                                    len(f1), _p(kps2), _p(desc2), None if hp2 is None else _p(hp2), len(kps2), _p(n2), _p(b2), len(n2),
+                                    _p(f2p), len(f2), float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(kps1)].copy()
 
 
 # ---------------------------------------------------------------- synthetic inputs

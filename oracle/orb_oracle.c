@@ -852,6 +852,68 @@ int orc_search_by_bow(const orc_kp* kps_kf, const uint8_t* desc_kf, const uint8_
   return nmatches;
 }
 
+/* ---- ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12), orb_matcher.cc:697-815 (NLeft == -1):
+ * both sides need a good map point, a side-2 feature is claimed once (vbMatched2), the threshold is a strict
+ * < TH_LOW, and the result is indexed by the side-1 feature: match_of_1[i] = side-2 feature or -1. */
+int orc_search_by_bow_kf(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_point1, int n1,
+                         const uint32_t* nodes1, const int* begin1, int n_nodes1, const uint32_t* feats1, int total1,
+                         const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_point2, int n2,
+                         const uint32_t* nodes2, const int* begin2, int n_nodes2, const uint32_t* feats2, int total2,
+                         float nnratio, int check_orientation, int* match_of_1) {
+  enum { HISTO_LENGTH = 30, TH_LOW = 50 };
+  int nmatches = 0;
+  int hist[HISTO_LENGTH] = {0};
+  int* bin_of = (int*)malloc(sizeof(int) * (size_t)(n1 ? n1 : 1));
+  uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 ? n2 : 1), 1);
+  const float factor = HISTO_LENGTH / 360.0f; /* :716 */
+  for (int i = 0; i < n1; i++) { match_of_1[i] = -1; bin_of[i] = -1; }
+  int a = 0, b = 0;
+  while (a < n_nodes1 && b < n_nodes2) { /* :725-797 */
+    if (nodes1[a] == nodes2[b]) {
+      const int k0 = begin1[a], k1 = a + 1 < n_nodes1 ? begin1[a + 1] : total1;
+      const int f0 = begin2[b], f1 = b + 1 < n_nodes2 ? begin2[b + 1] : total2;
+      for (int i1 = k0; i1 < k1; i1++) {
+        const int idx1 = (int)feats1[i1];
+        if (has_point1 && !has_point1[idx1]) continue; /* :733-735 */
+        int best1 = 256, best_idx2 = -1, best2 = 256;
+        for (int i2 = f0; i2 < f1; i2++) {
+          const int idx2 = (int)feats2[i2];
+          if (matched2[idx2] || (has_point2 && !has_point2[idx2])) continue; /* :752-754 */
+          const int dist = orc_hamming(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+          if (dist < best1) { best2 = best1; best1 = dist; best_idx2 = idx2; }
+          else if (dist < best2) { best2 = dist; }
+        }
+        if (best1 < TH_LOW && (float)best1 < nnratio * (float)best2) { /* :769-771 */
+          match_of_1[idx1] = best_idx2;
+          matched2[best_idx2] = 1;
+          if (check_orientation) { /* :775-782 */
+            float rot = kps1[idx1].angle - kps2[best_idx2].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            bin_of[idx1] = bin;
+            hist[bin]++;
+          }
+          nmatches++;
+        }
+      }
+      a++; b++;
+    } else if (nodes1[a] < nodes2[b]) {
+      while (a < n_nodes1 && nodes1[a] < nodes2[b]) a++;
+    } else {
+      while (b < n_nodes2 && nodes2[b] < nodes1[a]) b++;
+    }
+  }
+  if (check_orientation) { /* :799-812 */
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+    for (int i = 0; i < n1; i++)
+      if (match_of_1[i] >= 0 && bin_of[i] != ind1 && bin_of[i] != ind2 && bin_of[i] != ind3) { match_of_1[i] = -1; nmatches--; }
+  }
+  free(bin_of); free(matched2);
+  return nmatches;
+}
+
 /* ---- synthetic inputs, SURVEY.md 8(d) ---- */
 uint64_t orc_splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -168,6 +168,15 @@ int orc_search_by_bow(const orc_kp* kps_kf, const uint8_t* desc_kf, const uint8_
                       const uint32_t* nodes_f, const int* begin_f, int n_nodes_f, const uint32_t* feats_f, int total_f,
                       float nnratio, int check_orientation, int* match_of_f);
 
+/* ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815; loop closing): both sides need
+ * a good map point, strict < TH_LOW, each side-2 feature claimed once; match_of_1[i] = side-2 feature or -1.
+ * Pinned on orb_matcher.cc:697-815 spliced into oracle/ref_frame_shim.cc. */
+int orc_search_by_bow_kf(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_point1, int n1,
+                         const uint32_t* nodes1, const int* begin1, int n_nodes1, const uint32_t* feats1, int total1,
+                         const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_point2, int n2,
+                         const uint32_t* nodes2, const int* begin2, int n_nodes2, const uint32_t* feats2, int total2,
+                         float nnratio, int check_orientation, int* match_of_1);
+
 /* ---- deterministic synthetic inputs ---- */
 uint64_t orc_splitmix64(uint64_t x);
 void orc_synth_blocks_v1(uint8_t* img, int w, int h, size_t stride, uint64_t seed, uint64_t frame,

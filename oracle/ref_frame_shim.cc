@@ -13,6 +13,7 @@
 //   _ref/matcher_project.inc     orb_matcher.cc:42-213 ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, ...),
 //                                                      ORBmatcher::RadiusByViewingCos
 //   _ref/matcher_bow.inc         orb_matcher.cc:215-389  ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
+//   _ref/matcher_bow_kf.inc      orb_matcher.cc:697-815  ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)
 //   _ref/matcher_maxima.inc      orb_matcher.cc:1841-1873 ORBmatcher::ComputeThreeMaxima
 //   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
 // Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
@@ -56,6 +57,7 @@ class ORBmatcher {
   int SearchByProjection(class Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3,
                          const bool bFarPoints = false, const float thFarPoints = 50.0f);
   int SearchByBoW(KeyFrame *pKF, class Frame &F, std::vector<MapPoint *> &vpMapPointMatches);
+  int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12);
   static const int TH_LOW;
   static const int TH_HIGH;
   static const int HISTO_LENGTH;
@@ -134,6 +136,7 @@ class MapPoint {  // include/map/mappoint.h
 #include "mappoint_distinct.inc"
 #include "matcher_project.inc"
 #include "matcher_bow.inc"
+#include "matcher_bow_kf.inc"
 #include "matcher_maxima.inc"
 
 }  // namespace ORB_SLAM_FUSION
@@ -277,6 +280,36 @@ int reff_search_by_bow(const void *kps_kf, const uint8_t *desc_kf, int n_kf, con
   ORBmatcher matcher(nnratio, check_orientation != 0);
   const int nm = matcher.SearchByBoW(&kf, F, matches);
   for (int i = 0; i < n_f; i++) match_of_f[i] = matches[i] ? (int)(matches[i] - mps.data()) : -1;
+  return nm;
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12): match_of_1[i] = side-2 feature whose map point
+// vpMatches12[i] is, -1 = NULL.
+static void fill_kf(KeyFrame &kf, std::vector<MapPoint> &mps, const void *kps, const uint8_t *desc, int n, const uint8_t *has_point,
+                    const uint32_t *nodes, const int *begin, int n_nodes, const uint32_t *feats, int total) {
+  kf.mvKeysUn.assign((const cv::KeyPoint *)kps, (const cv::KeyPoint *)kps + n);
+  kf.mvKeys = kf.mvKeysUn;
+  kf.mDescriptors = cv::Mat(n, 32, CV_8U, (void *)desc);
+  kf.mvpMapPoints.assign(n, (MapPoint *)nullptr);
+  for (int i = 0; i < n; i++)
+    if (!has_point || has_point[i]) kf.mvpMapPoints[i] = &mps[i];
+  for (int j = 0; j < n_nodes; j++)
+    kf.mFeatVec[nodes[j]].assign(feats + begin[j], feats + (j + 1 < n_nodes ? begin[j + 1] : total));
+}
+
+int reff_search_by_bow_kf(const void *kps1, const uint8_t *desc1, int n1, const uint8_t *has_point1, const uint32_t *nodes1,
+                          const int *begin1, int n_nodes1, const uint32_t *feats1, int total1, const void *kps2,
+                          const uint8_t *desc2, int n2, const uint8_t *has_point2, const uint32_t *nodes2, const int *begin2,
+                          int n_nodes2, const uint32_t *feats2, int total2, float nnratio, int check_orientation,
+                          int *match_of_1) {
+  KeyFrame k1, k2;
+  std::vector<MapPoint> m1(n1 > 0 ? n1 : 1), m2(n2 > 0 ? n2 : 1);  // MapPoint holds a mutex: sized at construction
+  fill_kf(k1, m1, kps1, desc1, n1, has_point1, nodes1, begin1, n_nodes1, feats1, total1);
+  fill_kf(k2, m2, kps2, desc2, n2, has_point2, nodes2, begin2, n_nodes2, feats2, total2);
+  std::vector<MapPoint *> matches;
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  const int nm = matcher.SearchByBoW(&k1, &k2, matches);
+  for (int i = 0; i < n1; i++) match_of_1[i] = matches[i] ? (int)(matches[i] - m2.data()) : -1;
   return nm;
 }
 

@@ -66,6 +66,14 @@ class ORBmatcherGpu {
                   const cv::Mat& desc_f, const std::map<unsigned int, std::vector<unsigned int> >& featvec_f, float nnratio,
                   bool check_orientation, std::vector<int>& match_of_f);
 
+  // ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vpMatches12) (orb_matcher.cc:697-815, loop closing): both
+  // sides need a good map point; match_of_1[i] = feature of pKF2 whose map point vpMatches12[i] becomes (-1 = NULL).
+  int SearchByBoW(const std::vector<cv::KeyPoint>& keys_un1, const cv::Mat& desc1, const std::vector<uint8_t>& has_point1,
+                  const std::map<unsigned int, std::vector<unsigned int> >& featvec1, const std::vector<cv::KeyPoint>& keys_un2,
+                  const cv::Mat& desc2, const std::vector<uint8_t>& has_point2,
+                  const std::map<unsigned int, std::vector<unsigned int> >& featvec2, float nnratio, bool check_orientation,
+                  std::vector<int>& match_of_1);
+
   struct Window { float u, v, r; int min_level, max_level; };
   struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };
   // orb_matcher.cc:66-113 with Frame::GetFeaturesInArea (frame.cc:679-746) for a batch of projections.
@@ -78,6 +86,11 @@ class ORBmatcherGpu {
                     const std::vector<float>* window_max_err = nullptr);
 
  private:
+  int SearchByBoWImpl(bool keyframes, const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
+                      const std::vector<uint8_t>& has_point1, const std::map<unsigned int, std::vector<unsigned int> >& featvec1,
+                      const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2, const std::vector<uint8_t>* has_point2,
+                      const std::map<unsigned int, std::vector<unsigned int> >& featvec2, float nnratio, bool check_orientation,
+                      std::vector<int>& match);
   orbm_matcher* m_;
 };
 

@@ -99,47 +99,75 @@ std::vector<int> ORBmatcherGpu::ComputeDistinctiveDescriptors(const std::vector<
   return best;
 }
 
+int ORBmatcherGpu::SearchByBoWImpl(bool keyframes, const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
+                                   const std::vector<uint8_t>& has_point1,
+                                   const std::map<unsigned int, std::vector<unsigned int> >& featvec1,
+                                   const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2,
+                                   const std::vector<uint8_t>* has_point2,
+                                   const std::map<unsigned int, std::vector<unsigned int> >& featvec2, float nnratio,
+                                   bool check_orientation, std::vector<int>& match_out) {
+  typedef std::map<unsigned int, std::vector<unsigned int> > FeatVec;
+  const int n1 = (int)keys1.size(), n2 = (int)keys2.size();
+  const int cap = std::max(1, std::max(n1, n2));
+  const int n_out = keyframes ? n1 : n2;  // vpMatches12 is indexed by side 1, vpMapPointMatches by the frame
+  match_out.assign((size_t)n_out, -1);
+  // a pool of two frames in the [frame][cap] layout of orbm_search_by_bow: 0 = side 1, 1 = side 2
+  std::vector<orbx_kp> kps(2 * (size_t)cap);
+  std::vector<uint8_t> desc(2 * (size_t)cap * 32, 0), has(2 * (size_t)cap, 0);
+  std::vector<uint32_t> nodes(2 * (size_t)cap, 0), feats(2 * (size_t)cap, 0);
+  std::vector<int32_t> begin(2 * (size_t)cap, 0);
+  int32_t fv_n[2] = {0, 0}, fv_total[2] = {0, 0};
+  const int32_t npf[2] = {n1, n2};
+  if (n1) std::memcpy(kps.data(), keys1.data(), sizeof(orbx_kp) * (size_t)n1);
+  if (n2) std::memcpy(kps.data() + cap, keys2.data(), sizeof(orbx_kp) * (size_t)n2);
+  const std::vector<uint8_t> d1 = dense_rows(desc1), d2 = dense_rows(desc2);
+  if (n1) std::memcpy(desc.data(), d1.data(), 32 * (size_t)n1);
+  if (n2) std::memcpy(desc.data() + 32 * (size_t)cap, d2.data(), 32 * (size_t)n2);
+  for (int i = 0; i < n1; ++i) has[i] = i < (int)has_point1.size() ? has_point1[i] : 0;
+  for (int i = 0; i < n2; ++i) has[(size_t)cap + i] = has_point2 ? (i < (int)has_point2->size() ? (*has_point2)[i] : 0) : 1;
+  const FeatVec* fv[2] = {&featvec1, &featvec2};
+  for (int s = 0; s < 2; ++s) {
+    const size_t o = (size_t)s * cap;
+    for (FeatVec::const_iterator it = fv[s]->begin(); it != fv[s]->end(); ++it) {
+      size_t cnt = 0;
+      for (size_t j = 0; j < it->second.size(); ++j) cnt += it->second[j] < (unsigned)npf[s];
+      if (fv_total[s] + (int)cnt > cap || fv_n[s] >= cap) throw std::runtime_error("ORBmatcherGpu::SearchByBoW: FeatureVector larger than the frame");
+      nodes[o + fv_n[s]] = it->first;
+      begin[o + fv_n[s]] = fv_total[s];
+      ++fv_n[s];
+      for (size_t j = 0; j < it->second.size(); ++j)
+        if (it->second[j] < (unsigned)npf[s]) feats[o + fv_total[s]++] = it->second[j];
+    }
+  }
+  const int32_t p1 = 0, p2 = 1;
+  std::vector<int32_t> match((size_t)cap, -1);
+  int32_t nm = 0;
+  check(m_, (keyframes ? orbm_search_by_bow_kf : orbm_search_by_bow)(
+                m_, kps.data(), desc.data(), cap, 2, npf, nodes.data(), begin.data(), fv_n, feats.data(), fv_total, has.data(), &p1, &p2,
+                1, nnratio, check_orientation ? 1 : 0, match.data(), &nm, ORBX_MEM_HOST, nullptr));
+  for (int i = 0; i < n_out; ++i) match_out[i] = match[i];
+  return nm;
+}
+
 int ORBmatcherGpu::SearchByBoW(const std::vector<cv::KeyPoint>& keys_kf, const cv::Mat& desc_kf,
                                const std::vector<uint8_t>& has_point_kf,
                                const std::map<unsigned int, std::vector<unsigned int> >& featvec_kf,
                                const std::vector<cv::KeyPoint>& keys_f, const cv::Mat& desc_f,
                                const std::map<unsigned int, std::vector<unsigned int> >& featvec_f, float nnratio,
                                bool check_orientation, std::vector<int>& match_of_f) {
-  typedef std::map<unsigned int, std::vector<unsigned int> > FeatVec;
-  const int nk = (int)keys_kf.size(), nf = (int)keys_f.size();
-  const int cap = std::max(1, std::max(nk, nf));
-  match_of_f.assign((size_t)nf, -1);
-  // a pool of two frames in the [frame][cap] layout of orbm_search_by_bow: 0 = key frame, 1 = frame
-  std::vector<orbx_kp> kps(2 * (size_t)cap);
-  std::vector<uint8_t> desc(2 * (size_t)cap * 32, 0), has(2 * (size_t)cap, 0);
-  std::vector<uint32_t> nodes(2 * (size_t)cap, 0), feats(2 * (size_t)cap, 0);
-  std::vector<int32_t> begin(2 * (size_t)cap, 0);
-  int32_t fv_n[2] = {0, 0}, fv_total[2] = {0, 0};
-  const int32_t npf[2] = {nk, nf};
-  if (nk) std::memcpy(kps.data(), keys_kf.data(), sizeof(orbx_kp) * (size_t)nk);
-  if (nf) std::memcpy(kps.data() + cap, keys_f.data(), sizeof(orbx_kp) * (size_t)nf);
-  const std::vector<uint8_t> dk = dense_rows(desc_kf), df = dense_rows(desc_f);
-  if (nk) std::memcpy(desc.data(), dk.data(), 32 * (size_t)nk);
-  if (nf) std::memcpy(desc.data() + 32 * (size_t)cap, df.data(), 32 * (size_t)nf);
-  for (int i = 0; i < nk; ++i) has[i] = i < (int)has_point_kf.size() ? has_point_kf[i] : 0;
-  const FeatVec* fv[2] = {&featvec_kf, &featvec_f};
-  for (int s = 0; s < 2; ++s) {
-    const size_t o = (size_t)s * cap;
-    for (FeatVec::const_iterator it = fv[s]->begin(); it != fv[s]->end(); ++it) {
-      nodes[o + fv_n[s]] = it->first;
-      begin[o + fv_n[s]] = fv_total[s];
-      ++fv_n[s];
-      for (size_t j = 0; j < it->second.size(); ++j) feats[o + fv_total[s]++] = it->second[j];
-    }
-  }
-  const int32_t pk = 0, pf = 1;
-  std::vector<int32_t> match((size_t)cap, -1);
-  int32_t nm = 0;
-  check(m_, orbm_search_by_bow(m_, kps.data(), desc.data(), cap, 2, npf, nodes.data(), begin.data(), fv_n, feats.data(), fv_total,
-                               has.data(), &pk, &pf, 1, nnratio, check_orientation ? 1 : 0, match.data(), &nm, ORBX_MEM_HOST,
-                               nullptr));
-  for (int i = 0; i < nf; ++i) match_of_f[i] = match[i];
-  return nm;
+  return SearchByBoWImpl(false, keys_kf, desc_kf, has_point_kf, featvec_kf, keys_f, desc_f, nullptr, featvec_f, nnratio,
+                         check_orientation, match_of_f);
+}
+
+int ORBmatcherGpu::SearchByBoW(const std::vector<cv::KeyPoint>& keys_un1, const cv::Mat& desc1,
+                               const std::vector<uint8_t>& has_point1,
+                               const std::map<unsigned int, std::vector<unsigned int> >& featvec1,
+                               const std::vector<cv::KeyPoint>& keys_un2, const cv::Mat& desc2,
+                               const std::vector<uint8_t>& has_point2,
+                               const std::map<unsigned int, std::vector<unsigned int> >& featvec2, float nnratio,
+                               bool check_orientation, std::vector<int>& match_of_1) {
+  return SearchByBoWImpl(true, keys_un1, desc1, has_point1, featvec1, keys_un2, desc2, &has_point2, featvec2, nnratio,
+                         check_orientation, match_of_1);
 }
 
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,

@@ -319,80 +319,94 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
 }
 
 // ------------------------------------------------------------------ SearchByBoW
-// ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1) for a batch of
-// (key frame, frame) pairs drawn from one pool of frames in the [frame][cap] layout of orbx_extract_batch /
-// orbv_transform.  One CTA per pair.  A frame feature lies in exactly one FeatureVector node, so the reference's
-// sequential dependence ("skip frame features that already took a map point", :265) never crosses a node: a warp
-// owns a shared node and walks its key-frame features IN ORDER, the lanes split the node's frame features; strict
-// "<, first wins" is the minimum of the key (distance, position in the node), the second-best distance the
-// second-smallest key.  Then the 30-bin rotation histogram and ComputeThreeMaxima (:1841-1873) on the CTA.
+// ORBmatcher::SearchByBoW for a batch of pairs drawn from one pool of frames in the [frame][cap] layout of
+// orbx_extract_batch / orbv_transform.  One CTA per pair.
+//   KF = false: SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1): side 1 = the key
+//               frame (needs map points), side 2 = the frame; accept d1 <= TH_LOW; match[] is indexed by the side-2 feature
+//               and holds the side-1 feature (vpMapPointMatches[idxF] = pMP of realIdxKF).
+//   KF = true:  SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (:697-815): both sides need map points; accept
+//               d1 < TH_LOW; match[] is indexed by the side-1 feature and holds the side-2 feature.
+// A side-2 feature lies in exactly one FeatureVector node, so the reference's sequential dependence ("skip side-2
+// features that are already claimed", :265 / :752) never crosses a node: a warp owns a shared node and walks its side-1
+// features IN ORDER, the lanes split the node's side-2 features; strict "<, first wins" is the minimum of the key
+// (distance, position in the node), the second-best distance the second-smallest key.  Claimed side-2 features are a
+// bitmap in shared memory.  Then the 30-bin rotation histogram and ComputeThreeMaxima (:1841-1873) on the CTA.
+template <bool KF>
 __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap,
                                                        const uint32_t* __restrict__ fv_nodes, const int32_t* __restrict__ fv_begin,
                                                        const int32_t* __restrict__ fv_n, const uint32_t* __restrict__ fv_feats,
                                                        const int32_t* __restrict__ fv_total, const int32_t* __restrict__ n_per_frame,
-                                                       const uint8_t* __restrict__ has_point, const int32_t* __restrict__ pair_kf,
-                                                       const int32_t* __restrict__ pair_f, float nnratio, int check_orientation,
+                                                       const uint8_t* __restrict__ has_point, const int32_t* __restrict__ pair_1,
+                                                       const int32_t* __restrict__ pair_2, float nnratio, int check_orientation,
                                                        int32_t* __restrict__ match, int32_t* __restrict__ n_matches) {
   constexpr int kHisto = 30, kThLow = 50;  // ORBmatcher::HISTO_LENGTH, TH_LOW (orb_matcher.cc:36-37)
   __shared__ int hist[kHisto];
   __shared__ int keep3[3];
   __shared__ int n_kept;
+  __shared__ uint32_t claimed[64];  // one bit per side-2 feature (cap <= 2048)
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const size_t ok = (size_t)pair_kf[p] * cap, of = (size_t)pair_f[p] * cap;
-  const int nf = n_per_frame ? max(0, min(n_per_frame[pair_f[p]], cap)) : cap;
+  const int fr1 = pair_1[p], fr2 = pair_2[p];
+  const size_t o1 = (size_t)fr1 * cap, o2 = (size_t)fr2 * cap;
+  const int n1 = n_per_frame ? max(0, min(n_per_frame[fr1], cap)) : cap, n2 = n_per_frame ? max(0, min(n_per_frame[fr2], cap)) : cap;
   int32_t* mt = match + (size_t)p * cap;
   for (int i = tid; i < cap; i += 256) mt[i] = -1;
   if (tid < kHisto) hist[tid] = 0;
+  if (tid < 64) claimed[tid] = 0;
   if (tid == 0) n_kept = 0;
   __syncthreads();
-  const int nnk = fv_n[pair_kf[p]], nnf = fv_n[pair_f[p]];
-  const int tot_k = fv_total[pair_kf[p]], tot_f = fv_total[pair_f[p]];
-  const uint32_t *nodes_k = fv_nodes + ok, *nodes_f = fv_nodes + of, *feats_k = fv_feats + ok, *feats_f = fv_feats + of;
-  const int32_t *begin_k = fv_begin + ok, *begin_f = fv_begin + of;
-  for (int a = wrp; a < nnk; a += 8) {
-    const uint32_t nid = nodes_k[a];
-    int lo = 0, hi = nnf;  // lower_bound of nid in the frame's sorted node ids
+  const int nn1 = fv_n[fr1], nn2 = fv_n[fr2];
+  const int tot1 = fv_total[fr1], tot2 = fv_total[fr2];
+  const uint32_t *nodes1 = fv_nodes + o1, *nodes2 = fv_nodes + o2, *feats1 = fv_feats + o1, *feats2 = fv_feats + o2;
+  const int32_t *begin1 = fv_begin + o1, *begin2 = fv_begin + o2;
+  for (int a = wrp; a < nn1; a += 8) {
+    const uint32_t nid = nodes1[a];
+    int lo = 0, hi = nn2;  // lower_bound of nid in side 2's sorted node ids
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (nodes_f[mid] < nid) lo = mid + 1; else hi = mid;
+      if (nodes2[mid] < nid) lo = mid + 1; else hi = mid;
     }
-    if (lo >= nnf || nodes_f[lo] != nid) continue;
-    const int k0 = begin_k[a], k1 = a + 1 < nnk ? begin_k[a + 1] : tot_k;
-    const int f0 = begin_f[lo], f1 = lo + 1 < nnf ? begin_f[lo + 1] : tot_f;
+    if (lo >= nn2 || nodes2[lo] != nid) continue;
+    const int k0 = begin1[a], k1 = a + 1 < nn1 ? begin1[a + 1] : tot1;
+    const int f0 = begin2[lo], f1 = lo + 1 < nn2 ? begin2[lo + 1] : tot2;
     for (int ik = k0; ik < k1; ik++) {
-      const int real_k = (int)feats_k[ik];
-      if (has_point && !has_point[ok + real_k]) continue;  // :246-250
-      uint32_t dk[8];
-      load_row(desc + 32 * (ok + real_k), dk);
+      const int idx1 = (int)feats1[ik];
+      if (idx1 >= n1 || (has_point && !has_point[o1 + idx1])) continue;  // :246-250 / :733-735: no map point, or a bad one
+      uint32_t d1r[8];
+      load_row(desc + 32 * (o1 + idx1), d1r);
       unsigned long long b0 = ~0ull, b1 = ~0ull;
       for (int jf = f0 + lane; jf < f1; jf += 32) {
-        const int real_f = (int)feats_f[jf];
-        if (real_f >= nf || mt[real_f] >= 0) continue;  // :265 already holds a map point
-        uint32_t df[8];
-        load_row(desc + 32 * (of + real_f), df);
-        const unsigned long long key = ((unsigned long long)ham256(dk, df) << 32) | (unsigned)(jf - f0);
+        const int idx2 = (int)feats2[jf];
+        if (idx2 >= n2 || ((claimed[idx2 >> 5] >> (idx2 & 31)) & 1u)) continue;  // :265 / :752 already claimed
+        if (KF && has_point && !has_point[o2 + idx2]) continue;                   // :752-754
+        uint32_t d2r[8];
+        load_row(desc + 32 * (o2 + idx2), d2r);
+        const unsigned long long key = ((unsigned long long)ham256(d1r, d2r) << 32) | (unsigned)(jf - f0);
         b1 = min(b1, max(b0, key));
         b0 = min(b0, key);
       }
       warp_top2(b0, b1);
       if (lane == 0 && b0 != ~0ull) {
         const int d1 = (int)(b0 >> 32), d2 = b1 == ~0ull ? 256 : (int)(b1 >> 32);
-        if (d1 <= kThLow && (float)d1 < f_mul(nnratio, (float)d2))  // :307-309
-          mt[feats_f[f0 + (int)(b0 & 0xFFFFFFFFu)]] = real_k;
+        if ((KF ? d1 < kThLow : d1 <= kThLow) && (float)d1 < f_mul(nnratio, (float)d2)) {  // :307-309 / :769-771
+          const int idx2 = (int)feats2[f0 + (int)(b0 & 0xFFFFFFFFu)];
+          atomicOr(&claimed[idx2 >> 5], 1u << (idx2 & 31));
+          if (KF) mt[idx1] = idx2; else mt[idx2] = idx1;
+        }
       }
-      __syncwarp();  // the claim is visible to the lanes before the next key-frame feature
+      __syncwarp();  // the claim is visible to the lanes before the next side-1 feature
     }
   }
   __syncthreads();
-  // rotation consistency (:318-328, :372-386): bin of every match, the three dominant bins survive
+  // rotation consistency (:318-328, :372-386 / :775-782, :799-812): bin of every match, the three dominant bins survive
   const float factor = 30 / 360.0f;
-  int my_bin[8];  // cap <= 2048: up to 8 frame features per thread
+  int my_bin[8];  // cap <= 2048: up to 8 output slots per thread
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const int i = tid + 256 * r;
     my_bin[r] = -1;
     if (i < cap && mt[i] >= 0) {
-      float rot = f_sub(kps[ok + mt[i]].angle, kps[of + i].angle);
+      const float a1 = KF ? kps[o1 + i].angle : kps[o1 + mt[i]].angle, a2 = KF ? kps[o2 + mt[i]].angle : kps[o2 + i].angle;
+      float rot = f_sub(a1, a2);
       if (rot < 0.0f) rot = f_add(rot, 360.0f);
       int bin = (int)roundf(f_mul(rot, factor));
       if (bin == kHisto) bin = 0;
@@ -428,11 +442,15 @@ __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict
 
 int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
-                         const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f, int n_pairs, float nnratio,
-                         int check_orientation, int32_t* match, int32_t* n_matches, cudaStream_t st) {
+                         const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,
+                         int check_orientation, bool keyframes, int32_t* match, int32_t* n_matches, cudaStream_t st) {
   if (n_pairs <= 0) return 0;
-  k_search_by_bow<<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame, has_point,
-                                           pair_kf, pair_f, nnratio, check_orientation, match, n_matches);
+  if (keyframes)
+    k_search_by_bow<true><<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
+                                                   has_point, pair_1, pair_2, nnratio, check_orientation, match, n_matches);
+  else
+    k_search_by_bow<false><<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
+                                                    has_point, pair_1, pair_2, nnratio, check_orientation, match, n_matches);
   return 1;
 }
 

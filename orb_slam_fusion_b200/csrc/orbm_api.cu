@@ -353,7 +353,7 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
   return orbm_window_search_stereo(m, kps, desc, n, geom, queries, qdesc, nq, skip, nullptr, nullptr, nullptr, out, mem, stream);
 }
 
-int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+static int search_by_bow(bool keyframes, orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
                        const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
                        const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f,
                        int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
@@ -390,10 +390,28 @@ int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int c
   int32_t* dmatch = stage_out(m, mem, match, (size_t)n_pairs * cap);
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)n_pairs);
   m->launches += launch_search_by_bow(dk, dd, cap, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dpk, dpf, n_pairs, nnratio,
-                                      check_orientation, dmatch, dnm, st);
+                                      check_orientation, keyframes, dmatch, dnm, st);
   TRY(finish_out(m, mem, match, dmatch, (size_t)n_pairs * cap, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)n_pairs, st));
   return end(m, mem, st);
+}
+
+int orbm_search_by_bow(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+                       const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
+                       const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f,
+                       int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                       void* stream) {
+  return search_by_bow(false, m, kps, desc, cap, n_frames, n_per_frame, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, has_point,
+                       pair_kf, pair_f, n_pairs, nnratio, check_orientation, match, n_matches, mem, stream);
+}
+
+int orbm_search_by_bow_kf(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
+                          const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
+                          const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2,
+                          int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                          void* stream) {
+  return search_by_bow(true, m, kps, desc, cap, n_frames, n_per_frame, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, has_point,
+                       pair_1, pair_2, n_pairs, nnratio, check_orientation, match, n_matches, mem, stream);
 }
 
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream) {

@@ -82,8 +82,8 @@ bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** py
 // max_rows: the largest number of rows any point owns (sizes the shared memory; <= 6000)
 int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
-                         const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f, int n_pairs, float nnratio,
-                         int check_orientation, int32_t* match, int32_t* n_matches, cudaStream_t st);
+                         const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,
+                         int check_orientation, bool keyframes, int32_t* match, int32_t* n_matches, cudaStream_t st);
 int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
                        int32_t* best_median, cudaStream_t st);
 int launch_synth_descriptors(uint8_t* dst, int64_t first, int64_t n, uint64_t seed, cudaStream_t st);

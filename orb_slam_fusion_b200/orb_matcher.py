@@ -165,7 +165,13 @@ class ORBmatcher:
         return bi, bm
 
     # ---- bag-of-words guided matching
-    def SearchByBoW(self, kps, desc, n_per_frame, fv, pairs, has_point=None, nnratio=0.7, check_orientation=True):
+    def SearchByBoWKeyFrames(self, kps, desc, n_per_frame, fv, pairs, has_point=None, nnratio=0.7, check_orientation=True):
+        """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815, loop closing): same pool and
+        pair layout as SearchByBoW; has_point gates both sides; match[p, i] = feature of key frame 2 matched to
+        feature i of key frame 1, -1 = none."""
+        return self.SearchByBoW(kps, desc, n_per_frame, fv, pairs, has_point, nnratio, check_orientation, _keyframes=True)
+
+    def SearchByBoW(self, kps, desc, n_per_frame, fv, pairs, has_point=None, nnratio=0.7, check_orientation=True, _keyframes=False):
         """ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-389) for a batch of
         (key frame, frame) pairs out of one pool of frames in the [frame][cap] layout of OrbExtractor.extract_batch and
         ORBVocabulary.transform_batch: kps [F, cap] keypoint records, desc [F, cap, 32], n_per_frame [F] (or None),
@@ -196,10 +202,10 @@ class ORBmatcher:
             mem, stream = A.MEM_HOST, None
         for key in ("fv_nodes", "fv_begin", "fv_feats"):
             assert tuple(fv[key].shape) == (F, cap), key
-        self._check(self._lib.orbm_search_by_bow(self._m, A.ptr(kps), A.ptr(desc), cap, F, A.ptr(n_per_frame), A.ptr(fv["fv_nodes"]),
-                                                 A.ptr(fv["fv_begin"]), A.ptr(fv["fv_n"]), A.ptr(fv["fv_feats"]), A.ptr(fv["fv_total"]),
-                                                 A.ptr(has_point), A.ptr(kf), A.ptr(ff), len(kf), nnratio, int(check_orientation),
-                                                 A.ptr(match), A.ptr(nm), mem, stream))
+        fn = self._lib.orbm_search_by_bow_kf if _keyframes else self._lib.orbm_search_by_bow
+        self._check(fn(self._m, A.ptr(kps), A.ptr(desc), cap, F, A.ptr(n_per_frame), A.ptr(fv["fv_nodes"]), A.ptr(fv["fv_begin"]),
+                       A.ptr(fv["fv_n"]), A.ptr(fv["fv_feats"]), A.ptr(fv["fv_total"]), A.ptr(has_point), A.ptr(kf), A.ptr(ff), len(kf),
+                       nnratio, int(check_orientation), A.ptr(match), A.ptr(nm), mem, stream))
         return nm, match
 
     # ---- projection window

@@ -94,6 +94,11 @@ int main(int argc, char** argv) {
     const int32_t nmatch = matcher.SearchByBoW(keys, desc, has_point, fvec, keys, desc, fvec, 0.7f, true, match_of_f);
     put(fo, &nmatch, 4);
     put(fo, match_of_f.data(), match_of_f.size() * sizeof(int));
+    // the key-frame / key-frame form (orb_matcher.cc:697-815)
+    std::vector<int> match_of_1;
+    const int32_t nmatch_kf = matcher.SearchByBoW(keys, desc, has_point, fvec, keys, desc, has_point, fvec, 0.8f, true, match_of_1);
+    put(fo, &nmatch_kf, 4);
+    put(fo, match_of_1.data(), match_of_1.size() * sizeof(int));
   }
   fclose(fo);
   delete extractor;

@@ -86,4 +86,8 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     fv = oracle.pack_feature_vector(nodes, feats)
     wnm, want = oracle.search_by_bow(rk, rd, has_point, fv, rk, rd, fv, 0.7, True)
     assert nmatch == wnm and np.array_equal(match, want) and wnm > n // 3
+    nmatch_kf = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    match_kf = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    wnm, want = oracle.search_by_bow_kf(rk, rd, has_point, fv, rk, rd, has_point, fv, 0.8, True)
+    assert nmatch_kf == wnm and np.array_equal(match_kf, want) and wnm > n // 3
     assert off == len(buf)

@@ -292,6 +292,16 @@ def test_search_by_bow(P, m, oracle):
             assert nm[p] == wnm and np.array_equal(match[p, :npf[b]], want), (levelsup, p)
             assert (match[p, npf[b]:] == -1).all()
         assert nm[0] > 40 and nm[6] > 100 and nm[5] < nm[0]      # same scene matches, different scenes mostly do not
+        # the loop-closing form SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815)
+        nm2, match2 = m.SearchByBoWKeyFrames(kps, desc, npf, fv, pairs, has_point, ratio, ori)
+        for p, (a, b) in enumerate(pairs):
+            fva = oracle.pack_feature_vector(*vo.transform(desc[a, :npf[a]], levelsup)[2:])
+            fvb = oracle.pack_feature_vector(*vo.transform(desc[b, :npf[b]], levelsup)[2:])
+            wnm, want = oracle.search_by_bow_kf(kps[a, :npf[a]], desc[a, :npf[a]], has_point[a, :npf[a]], fva,
+                                                kps[b, :npf[b]], desc[b, :npf[b]], has_point[b, :npf[b]], fvb, ratio, ori)
+            assert nm2[p] == wnm and np.array_equal(match2[p, :npf[a]], want), (levelsup, p)
+            assert (match2[p, npf[a]:] == -1).all()
+        assert nm2[0] > 30 and nm2[6] > 100
     # no map points at all / an empty pair list
     nm, match = m.SearchByBoW(kps, desc, npf, fv, pairs[:2], np.zeros((F, cap), np.uint8))
     assert (nm == 0).all() and (match == -1).all()

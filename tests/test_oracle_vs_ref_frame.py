@@ -195,3 +195,20 @@ def test_search_by_bow_identical(oracle, seed, shift, ratio, ori, levelsup):
     assert nm2 == want_nm2 and np.array_equal(got2, want2)
     hit = got2 >= 0
     assert hit.sum() > 100 and (da[got2[hit]] == da[np.nonzero(hit)[0]]).all()
+
+
+@pytest.mark.parametrize("seed,shift,ratio,ori,levelsup", [(1, 3, 0.9, True, 2), (2, 8, 0.75, True, 3), (3, 0, 0.9, False, 2),
+                                                           (4, 5, 0.6, True, 1), (5, 2, 0.8, True, 4)])
+def test_search_by_bow_keyframes_identical(oracle, seed, shift, ratio, ori, levelsup):
+    """The loop-closing form SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815)."""
+    ka, da, fva, kb, db, fvb = _bow_pair(oracle, seed, shift, levelsup=levelsup)
+    rng = np.random.default_rng(seed + 100)
+    hp1 = (rng.random(len(ka)) < 0.8).astype(np.uint8)
+    hp2 = (rng.random(len(kb)) < 0.8).astype(np.uint8)
+    want_nm, want = R.search_by_bow_kf(ka, da, hp1, fva, kb, db, hp2, fvb, ratio, ori)
+    nm, got = oracle.search_by_bow_kf(ka, da, hp1, fva, kb, db, hp2, fvb, ratio, ori)
+    assert nm == want_nm and np.array_equal(got, want)
+    assert want_nm > 20
+    want_nm2, want2 = R.search_by_bow_kf(ka, da, None, fva, ka, da, None, fva, ratio, ori)
+    nm2, got2 = oracle.search_by_bow_kf(ka, da, None, fva, ka, da, None, fva, ratio, ori)
+    assert nm2 == want_nm2 and np.array_equal(got2, want2) and nm2 > 100
