@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """Join an ncu source-page CSV (per-SASS-instruction executed counts) with nvdisasm --print-line-info of the
 linked library and print executed warp-instructions per source line / per line range.
-usage: ncu_phase.py sass.csv lib.sass kernel_substr [file.cu:lo-hi=name ...]"""
+usage: ncu_phase.py sass.csv lib.sass kernel_substr[|mangled_substr] [file.cu:lo-hi=name ...]"""
 import csv, re, sys, collections
 rows = list(csv.reader(open(sys.argv[1])))
-want = sys.argv[3]
+want, _, want_sass = sys.argv[3].partition('|')
+want_sass = want_sass or want
 ks, cur = [], None
 for r in rows:
     if r and r[0] == 'Kernel Name': cur = {'name': r[1], 'hdr': None, 'rows': []}; ks.append(cur)
@@ -15,7 +16,7 @@ h = k['hdr']; ie = h.index('Instructions Executed'); isrc = h.index('Source')
 # nvdisasm listing: find the function
 lines, cur, infn = [], None, False
 for l in open(sys.argv[2]):
-    if l.startswith('.text.') or re.match(r'\s*\.section\s+\.text\.', l): infn = want in l
+    if l.startswith('.text.') or re.match(r'\s*\.section\s+\.text\.', l): infn = want_sass in l
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
     m = re.match(r'\s*/\*([0-9a-f]{4,5})\*/\s+(.*?);', l)
