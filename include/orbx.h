@@ -256,6 +256,23 @@ int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
                               const float* q_u_right, const float* q_max_err, orbm_window_result* out,
                               int mem, void* stream);
 
+/* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints)
+ * (orb_matcher.cc:42-134; caller tracking.cc:2687, Tracking::SearchLocalPoints) for a frame with Nleft == -1, the
+ * WHOLE function including the greedy claim: query q is the window of one map point that passed the reference's
+ * entry tests (:50-57: in view, not far, not bad), in vpMapPoints order, with r = RadiusByViewingCos * th *
+ * mvScaleFactors[level] and levels [nPredictedLevel-1, nPredictedLevel] (:62-70); `skip` marks frame keypoints that
+ * already hold a map point with observations when the call starts (:86-87); kp_u_right / q_u_right / q_max_err as in
+ * orbm_window_search_stereo (:89-92).  The map points are taken to have observations (true for the tracker's local map
+ * points), so a keypoint claimed by an earlier query is skipped by the later ones, exactly as the reference's loop does:
+ * a first kernel searches every window against the initial state, a second walks the queries in order and re-scans a
+ * window only when its best or second-best keypoint has been claimed in the meantime.  Accept rule (:117-121):
+ * best_dist <= th_high (TH_HIGH = 100) and not (best_level == best_level2 and best_dist > nnratio * best_dist2).
+ * Outputs: assigned[i] = query whose map point F.mvpMapPoints[i] receives (-1: untouched), *n_matches = return value. */
+int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                              const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
+                              float nnratio, int32_t* assigned, int32_t* n_matches, int mem, void* stream);
+
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389; callers
  * tracking.cc:2053, 2909: TrackReferenceKeyFrame and Relocalization) for n_pairs (key frame, frame) pairs taken from
  * one pool of frames in the [frame][cap] layout orbx_extract_batch and orbv_transform produce: frame f owns

@@ -914,6 +914,33 @@ int orc_search_by_bow_kf(const orc_kp* kps1, const uint8_t* desc1, const uint8_t
   return nmatches;
 }
 
+/* ---- ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints), orb_matcher.cc:42-134,
+ * Nleft == -1: the window search above per map point, in order, with the greedy claim: a frame keypoint that holds a map
+ * point with observations is skipped (:86-87), and an accepted match stores the map point (:121).  Queries are the map
+ * points that passed :50-57, with the window of :62-70. */
+int orc_search_by_projection(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                             const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                             const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
+                             float nnratio, int* assigned) {
+  uint8_t* taken = (uint8_t*)calloc((size_t)(n ? n : 1), 1);
+  int nmatches = 0;
+  for (int i = 0; i < n; i++) { assigned[i] = -1; taken[i] = skip ? skip[i] : 0; }
+  for (int qi = 0; qi < nq; qi++) {
+    orc_window_result r;
+    orc_window_search_stereo(kps, desc, n, g, q + qi, qdesc + 32 * (size_t)qi, 1, taken, kp_u_right,
+                             kp_u_right ? q_u_right + qi : NULL, kp_u_right ? q_max_err + qi : NULL, &r);
+    if (r.best_idx < 0) continue;                 /* :75 vIndices.empty() or every candidate skipped: bestDist stays 256 */
+    if (r.best_dist <= th_high) {                 /* :117 */
+      if (r.best_level == r.best_level2 && (float)r.best_dist > nnratio * (float)r.best_dist2) continue; /* :118-119 */
+      assigned[r.best_idx] = qi;                  /* :121 */
+      taken[r.best_idx] = 1;
+      nmatches++;
+    }
+  }
+  free(taken);
+  return nmatches;
+}
+
 /* ---- synthetic inputs, SURVEY.md 8(d) ---- */
 uint64_t orc_splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

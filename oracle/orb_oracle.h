@@ -156,6 +156,14 @@ void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, con
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
                               orc_window_result* out);
 
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, ...) (orb_matcher.cc:42-134, Nleft == -1) as a whole:
+ * the window search per map point in order + the greedy claim.  assigned[i] = query stored in F.mvpMapPoints[i] or -1;
+ * returns nmatches.  Pinned on orb_matcher.cc:42-213 spliced into oracle/ref_frame_shim.cc. */
+int orc_search_by_projection(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                             const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                             const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
+                             float nnratio, int* assigned);
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-386; Nleft == -1): per shared
  * vocabulary node, every key-frame feature with a map point takes the best unclaimed frame feature of the node
  * (<= TH_LOW, ratio test), in order; then the 30-bin rotation histogram keeps the three dominant bins

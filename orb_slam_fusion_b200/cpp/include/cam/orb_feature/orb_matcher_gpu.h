@@ -5,6 +5,7 @@
 //   Frame::ComputeStereoMatches       frame.cc:836-900   -> StereoRowBand
 //   Frame::ComputeStereoFishEyeMatches frame.cc:1154-1162 -> KnnMatch2 + RatioTest
 //   SearchByProjection inner loop      orb_matcher.cc:66-113 -> WindowSearch (greedy claim stays on the host)
+//   SearchByProjection(Frame, MapPoints) orb_matcher.cc:42-134 -> SearchByProjection (whole function, greedy claim on the device)
 //   ORBmatcher::SearchByBoW(KF, Frame) orb_matcher.cc:215-389 -> SearchByBoW (whole function, greedy claim included)
 #ifndef ORBMATCHER_GPU_H
 #define ORBMATCHER_GPU_H
@@ -55,6 +56,20 @@ class ORBmatcherGpu {
   // observations[p] holds the descriptor rows of point p (the vDescriptors of :367-398); returns for
   // each point the index of the row with the least median distance to the others (-1 if empty).
   std::vector<int> ComputeDistinctiveDescriptors(const std::vector<std::vector<cv::Mat> >& observations);
+
+  // ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints)
+  // (orb_matcher.cc:42-134, Nleft == -1; Tracking::SearchLocalPoints, tracking.cc:2687) as a whole.  TrackedPoint carries
+  // the MapPoint fields the function reads (:50-70, :90): mTrackProjX/Y, mTrackProjXR, mTrackViewCos, mTrackDepth,
+  // mnTrackScaleLevel, mbTrackInView, isBad(); point_desc row p = pMP->GetDescriptor().  keys_un / desc / u_right =
+  // F.mvKeysUn / F.mDescriptors / F.mvuRight (u_right may be empty: monocular), already_matched[i] = F.mvpMapPoints[i]
+  // holds a point with observations.  assigned_point[i] = index into `points` of the map point F.mvpMapPoints[i]
+  // receives (-1: untouched); returns nmatches.  The map points are taken to have observations (local map points do).
+  struct TrackedPoint { float proj_x, proj_y, proj_xr, view_cos, depth; int level; bool in_view, bad; };
+  int SearchByProjection(const std::vector<cv::KeyPoint>& keys_un, const cv::Mat& desc, const std::vector<float>& u_right,
+                         const std::vector<float>& scale_factors, float min_x, float min_y, float grid_inv_w, float grid_inv_h,
+                         int grid_cols, int grid_rows, const std::vector<TrackedPoint>& points, const cv::Mat& point_desc,
+                         const std::vector<uint8_t>& already_matched, float th, bool far_points, float th_far_points, float nnratio,
+                         std::vector<int>& assigned_point);
 
   // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1):
   // keys_kf = pKF->mvKeysUn, desc_kf = pKF->mDescriptors, has_point_kf[i] = pKF's feature i holds a map point that is

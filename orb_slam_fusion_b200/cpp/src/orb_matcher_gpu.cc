@@ -99,6 +99,49 @@ std::vector<int> ORBmatcherGpu::ComputeDistinctiveDescriptors(const std::vector<
   return best;
 }
 
+int ORBmatcherGpu::SearchByProjection(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, const std::vector<float>& u_right,
+                                      const std::vector<float>& sf, float min_x, float min_y, float inv_w, float inv_h, int cols,
+                                      int rows, const std::vector<TrackedPoint>& points, const cv::Mat& point_desc,
+                                      const std::vector<uint8_t>& already, float th, bool far_points, float th_far, float nnratio,
+                                      std::vector<int>& assigned_point) {
+  const int n = (int)keys.size();
+  assigned_point.assign((size_t)n, -1);
+  const bool bFactor = th != 1.0;  // orb_matcher.cc:48
+  std::vector<int> origin;
+  std::vector<orbm_window_query> windows;
+  std::vector<float> q_ur, q_err;
+  std::vector<uint8_t> qd;
+  const std::vector<uint8_t> pd = dense_rows(point_desc);
+  for (size_t p = 0; p < points.size(); ++p) {
+    const TrackedPoint& mp = points[p];
+    if (!mp.in_view) continue;                          // :52 (mbTrackInViewR belongs to the two-camera rig)
+    if (far_points && mp.depth > th_far) continue;      // :54
+    if (mp.bad) continue;                               // :56
+    float r = mp.view_cos > 0.998 ? 2.5f : 4.0f;        // RadiusByViewingCos :208-213
+    if (bFactor) r *= th;                               // :64
+    const int lev = mp.level < 0 ? 0 : (mp.level >= (int)sf.size() ? (int)sf.size() - 1 : mp.level);
+    const float radius = r * sf[lev];                   // :67-68
+    const orbm_window_query w = {mp.proj_x, mp.proj_y, radius, mp.level - 1, mp.level};
+    windows.push_back(w);
+    q_ur.push_back(mp.proj_xr);
+    q_err.push_back(radius);                            // :91
+    qd.insert(qd.end(), pd.begin() + 32 * p, pd.begin() + 32 * (p + 1));
+    origin.push_back((int)p);
+  }
+  const std::vector<uint8_t> d = dense_rows(desc);
+  const orbm_grid_geom g = {min_x, min_y, inv_w, inv_h, cols, rows};
+  std::vector<int32_t> assigned((size_t)std::max(n, 1), -1);
+  int32_t nm = 0;
+  const bool stereo = !u_right.empty();
+  check(m_, orbm_search_by_projection(m_, reinterpret_cast<const orbx_kp*>(keys.data()), d.data(), n, &g, windows.data(), qd.data(),
+                                      (int)windows.size(), already.empty() ? nullptr : already.data(),
+                                      stereo ? u_right.data() : nullptr, stereo ? q_ur.data() : nullptr,
+                                      stereo ? q_err.data() : nullptr, TH_HIGH, nnratio, assigned.data(), &nm, ORBX_MEM_HOST, nullptr));
+  for (int i = 0; i < n; ++i)
+    if (assigned[i] >= 0) assigned_point[i] = origin[assigned[i]];
+  return nm;
+}
+
 int ORBmatcherGpu::SearchByBoWImpl(bool keyframes, const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
                                    const std::vector<uint8_t>& has_point1,
                                    const std::map<unsigned int, std::vector<unsigned int> >& featvec1,

@@ -641,14 +641,12 @@ int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points
 // keypoints of a cell in insertion (= index) order (frame.cc:438-465, 718-743); the
 // best / second-best recurrences of orb_matcher.cc:98-112 equal the two smallest keys
 // (distance, cell = ix*rows + iy, keypoint index), so no cell lists have to be built.
-__global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
-                                                       const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
-                                                       const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
-                                                       const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
-                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out) {
-  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (qi >= nq) return;
-  const orbm_window_query Q = q[qi];
+// `claimed` (may be NULL): assigned[] of k_projection_claim -- keypoints an earlier query of the same call took.
+__device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                            const orbm_grid_geom& g, const orbm_window_query& Q, const uint8_t* __restrict__ qd_row,
+                                            const uint8_t* __restrict__ skip, const int32_t* claimed,
+                                            const float* __restrict__ kp_u_right, float q_ur, float q_err, int lane,
+                                            unsigned long long& b0, unsigned long long& b1) {
   // frame.cc:684-712 cell range of the window
   int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
   int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
@@ -660,58 +658,129 @@ __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict
   c1y = c1y > g.rows - 1 ? g.rows - 1 : c1y;
   const bool ok = !(c0x >= g.cols || c1x < 0 || c0y >= g.rows || c1y < 0);
   const bool check_levels = Q.min_level >= 0 || Q.max_level >= 0;
-  unsigned long long b0 = ~0ull, b1 = ~0ull;
-  if (ok) {
-    uint32_t qd[8];
-    load_row_any(qdesc + 32 * (size_t)qi, qd);
-    for (int i = lane; i < n; i += 32) {
-      const orbx_kp K = kps[i];
-      // Frame::PosInGrid (frame.cc:748-760): round, keypoints outside the grid are in no cell
-      const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
-      const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
-      if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
-      if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
-      if (check_levels) {
-        if (K.octave < Q.min_level) continue;
-        if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
-      }
-      const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
-      if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
-      if (skip && skip[i]) continue;
-      if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
-        const float ur = kp_u_right[i];
-        if (ur > 0 && fabsf(f_sub(q_u_right[qi], ur)) > q_max_err[qi]) continue;
-      }
-      uint32_t kd[8];
-      load_row_any(desc + 32 * (size_t)i, kd);
-      const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
-                                     ((unsigned long long)(px * g.rows + py) << 24) | (unsigned long long)i;
-      b1 = min(b1, max(b0, key));
-      b0 = min(b0, key);
+  b0 = ~0ull;
+  b1 = ~0ull;
+  if (!ok) return;
+  uint32_t qd[8];
+  load_row_any(qd_row, qd);
+  for (int i = lane; i < n; i += 32) {
+    const orbx_kp K = kps[i];
+    // Frame::PosInGrid (frame.cc:748-760): round, keypoints outside the grid are in no cell
+    const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
+    const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
+    if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
+    if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
+    if (check_levels) {
+      if (K.octave < Q.min_level) continue;
+      if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
     }
+    const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
+    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+    if (skip && skip[i]) continue;
+    if (claimed && claimed[i] >= 0) continue;
+    if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
+      const float ur = kp_u_right[i];
+      if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
+    }
+    uint32_t kd[8];
+    load_row_any(desc + 32 * (size_t)i, kd);
+    const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
+                                   ((unsigned long long)(px * g.rows + py) << 24) | (unsigned long long)i;
+    b1 = min(b1, max(b0, key));
+    b0 = min(b0, key);
   }
   warp_top2(b0, b1);
-  if (lane == 0) {
-    orbm_window_result r = {256, -1, -1, 256, -1};
-    if (b0 != ~0ull) {
-      r.best_dist = (int32_t)(b0 >> 44);
-      r.best_idx = (int32_t)(b0 & 0xFFFFFFu);
-      r.best_level = kps[r.best_idx].octave;
-    }
-    if (b1 != ~0ull) {
-      r.best_dist2 = (int32_t)(b1 >> 44);
-      r.best_level2 = kps[(int32_t)(b1 & 0xFFFFFFu)].octave;
-    }
-    out[qi] = r;
+}
+
+__device__ __forceinline__ orbm_window_result window_result(const orbx_kp* __restrict__ kps, unsigned long long b0, unsigned long long b1) {
+  orbm_window_result r = {256, -1, -1, 256, -1};
+  if (b0 != ~0ull) {
+    r.best_dist = (int32_t)(b0 >> 44);
+    r.best_idx = (int32_t)(b0 & 0xFFFFFFu);
+    r.best_level = kps[r.best_idx].octave;
   }
+  if (b1 != ~0ull) {
+    r.best_dist2 = (int32_t)(b1 >> 44);
+    r.best_level2 = kps[(int32_t)(b1 & 0xFFFFFFu)].octave;
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                       const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
+                                                       const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                       const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
+                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out,
+                                                       int32_t* __restrict__ idx2_out) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  const orbm_window_query Q = q[qi];
+  unsigned long long b0, b1;
+  window_scan(kps, desc, n, g, Q, qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+              kp_u_right ? q_max_err[qi] : 0.f, lane, b0, b1);
+  if (lane == 0) {
+    out[qi] = window_result(kps, b0, b1);
+    if (idx2_out) idx2_out[qi] = b1 != ~0ull ? (int32_t)(b1 & 0xFFFFFFu) : -1;
+  }
+}
+
+// The greedy claim of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (orb_matcher.cc:42-134,
+// Nleft == -1) over the results of k_window_search, exact: one warp walks the projected map points IN ORDER; a result
+// computed against the call's initial state is still the reference's unless its best or second-best keypoint has been
+// taken by an earlier map point of this call (a keypoint that holds a map point with observations is skipped, :86-87)
+// -- only then the window is scanned again, now against the current claims.
+__global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                         const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
+                                                         const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                         const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
+                                                         const float* __restrict__ q_max_err, const orbm_window_result* __restrict__ res,
+                                                         const int32_t* __restrict__ idx2, int th_high, float nnratio,
+                                                         int32_t* assigned, int32_t* __restrict__ n_matches) {
+  const int lane = threadIdx.x;
+  for (int i = lane; i < n; i += 32) assigned[i] = -1;
+  __syncwarp();
+  int nm = 0;
+  for (int qi = 0; qi < nq; qi++) {
+    orbm_window_result r = res[qi];
+    const int i2 = idx2[qi];
+    const bool dirty = (r.best_idx >= 0 && assigned[r.best_idx] >= 0) || (i2 >= 0 && assigned[i2] >= 0);
+    if (dirty) {  // warp-uniform
+      unsigned long long b0, b1;
+      window_scan(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, assigned, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+                  kp_u_right ? q_max_err[qi] : 0.f, lane, b0, b1);
+      r = window_result(kps, b0, b1);
+    }
+    // orb_matcher.cc:117-134: ratio to the second match only if both are in the same scale level
+    if (r.best_idx >= 0 && r.best_dist <= th_high &&
+        !(r.best_level == r.best_level2 && (float)r.best_dist > f_mul(nnratio, (float)r.best_dist2))) {
+      if (lane == 0) assigned[r.best_idx] = qi;  // F.mvpMapPoints[bestIdx] = pMP (:121); pMP has observations, so it blocks later ones
+      nm++;
+      __syncwarp();
+    }
+  }
+  if (lane == 0) *n_matches = nm;
 }
 
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                          const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                          const float* q_max_err, orbm_window_result* out, cudaStream_t st) {
   if (nq <= 0) return 0;
-  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out);
+  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out, nullptr);
   return 1;
+}
+
+int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
+                                const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
+                                const float* q_max_err, int th_high, float nnratio, orbm_window_result* res,
+                                int32_t* idx2, int32_t* assigned, int32_t* n_matches, cudaStream_t st) {
+  int launches = 1;
+  if (nq > 0) {
+    k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, res, idx2);
+    launches++;
+  }
+  k_projection_claim<<<1, 32, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, res, idx2, th_high,
+                                       nnratio, assigned, n_matches);
+  return launches;
 }
 
 // ------------------------------------------------------------------ popc pipe micro-benchmark

@@ -353,6 +353,49 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
   return orbm_window_search_stereo(m, kps, desc, n, geom, queries, qdesc, nq, skip, nullptr, nullptr, nullptr, out, mem, stream);
 }
 
+int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                              const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
+                              float nnratio, int32_t* assigned, int32_t* n_matches, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (n < 0 || nq < 0 || !geom || geom->cols < 1 || geom->rows < 1 || (int64_t)geom->cols * geom->rows >= (1 << 20) ||
+      n >= (1 << 24) || (n > 0 && (!kps || !desc || !assigned)) || (nq > 0 && (!queries || !qdesc)) || !n_matches ||
+      (kp_u_right && nq > 0 && (!q_u_right || !q_max_err)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  const size_t scratch = pad256((size_t)nq * sizeof(orbm_window_result)) + pad256((size_t)nq * 4);
+  if (mem == ORBX_MEM_HOST) {
+    TRY(arena_reserve(m, pad256((size_t)n * 28) + pad256((size_t)n * 32) + pad256((size_t)nq * sizeof(orbm_window_query)) +
+                             pad256((size_t)nq * 32) + pad256((size_t)n) + pad256((size_t)n * 4) + 2 * pad256((size_t)nq * 4) +
+                             pad256((size_t)n * 4) + 256 + scratch));
+  } else {
+    TRY(arena_reserve(m, scratch));  // device-memory calls still need the per-query scratch
+  }
+  const orbx_kp* dk;
+  const uint8_t *dd, *dqd, *dskip;
+  const orbm_window_query* dq;
+  const float *dur = nullptr, *dqr = nullptr, *dqe = nullptr;
+  TRY(stage_in(m, mem, kps, (size_t)n, &dk, st));
+  TRY(stage_in(m, mem, desc, (size_t)n * 32, &dd, st));
+  TRY(stage_in(m, mem, queries, (size_t)nq, &dq, st));
+  TRY(stage_in(m, mem, qdesc, (size_t)nq * 32, &dqd, st));
+  TRY(stage_in(m, mem, skip, (size_t)n, &dskip, st));
+  if (kp_u_right) {
+    TRY(stage_in(m, mem, kp_u_right, (size_t)n, &dur, st));
+    TRY(stage_in(m, mem, q_u_right, (size_t)nq, &dqr, st));
+    TRY(stage_in(m, mem, q_max_err, (size_t)nq, &dqe, st));
+  }
+  int32_t* dassigned = stage_out(m, mem, assigned, (size_t)n);
+  int32_t* dnm = stage_out(m, mem, n_matches, (size_t)1);
+  orbm_window_result* dres = arena_take<orbm_window_result>(m, (size_t)nq);
+  int32_t* didx2 = arena_take<int32_t>(m, (size_t)nq);
+  m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dres, didx2,
+                                             dassigned, dnm, st);
+  TRY(finish_out(m, mem, assigned, dassigned, (size_t)n, st));
+  TRY(finish_out(m, mem, n_matches, dnm, (size_t)1, st));
+  return end(m, mem, st);
+}
+
 static int search_by_bow(bool keyframes, orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,
                        const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n, const uint32_t* fv_feats,
                        const int32_t* fv_total, const uint8_t* has_point, const int32_t* pair_kf, const int32_t* pair_f,

@@ -63,6 +63,23 @@ int main(int argc, char** argv) {
   matcher.StereoRowBand(keys, desc, keys, desc, sf, h, 0.f, 40.f, bi, bd);
   put(fo, bi.data(), bi.size() * sizeof(int));
   put(fo, bd.data(), bd.size() * sizeof(int));
+  {
+    // ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th = 3) (orb_matcher.cc:42-134): every keypoint projected as a
+    // map point one pixel off, every fifth one not in view, every seventh keypoint already matched
+    std::vector<ORBmatcherGpu::TrackedPoint> pts(keys.size());
+    std::vector<uint8_t> already(keys.size(), 0);
+    for (size_t i = 0; i < keys.size(); i++) {
+      const ORBmatcherGpu::TrackedPoint t = {keys[i].pt.x + 1.0f, keys[i].pt.y - 1.0f, 0.f, i % 2 ? 1.0f : 0.9f, 10.f, keys[i].octave,
+                                             i % 5 != 0, false};
+      pts[i] = t;
+      already[i] = i % 7 == 0;
+    }
+    std::vector<int> assigned;
+    const int32_t nproj = matcher.SearchByProjection(keys, desc, std::vector<float>(), sf, 0.f, 0.f, 64.f / w, 48.f / h, 64, 48, pts, desc,
+                                                     already, 3.0f, false, 50.f, 0.8f, assigned);
+    put(fo, &nproj, 4);
+    put(fo, assigned.data(), assigned.size() * sizeof(int));
+  }
   if (argc == 9) {
     // Frame::ComputeBoW (frame.cc:761-766): toDescriptorVector + transform(vCurrentDesc, mBowVec, mFeatVec, 4)
     ORBVocabularyGpu voc(0);

@@ -66,6 +66,19 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     bd = np.frombuffer(buf, np.int32, n, off); off += 4 * n
     wi, wd = oracle.stereo_rowband(rk, rd, rk, rd, sf, h, 0.0, 40.0)
     assert np.array_equal(bi, wi) and np.array_equal(bd, wd)
+    # ORBmatcherGpu::SearchByProjection (orb_matcher.cc:42-134), the whole function
+    nproj = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    assigned = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    from test_oracle_vs_ref_frame import projection_windows
+    from oracle import ref as R
+    pts = np.zeros(n, R.TRACK_POINT_DTYPE)
+    pts["proj_x"], pts["proj_y"] = rk["x"] + np.float32(1), rk["y"] - np.float32(1)
+    pts["view_cos"] = np.where(np.arange(n) % 2, 1.0, 0.9)
+    pts["depth"], pts["level"], pts["in_view"] = 10.0, rk["octave"], np.arange(n) % 5 != 0
+    keep, q = projection_windows(oracle, sf, pts, 3.0, False, 50.0)
+    geom = (0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h), 64, 48)
+    wnm, want = oracle.search_by_projection(rk, rd, geom, q, rd[keep], (np.arange(n) % 7 == 0).astype(np.uint8), None, None, None, 100, 0.8)
+    assert nproj == wnm and np.array_equal(assigned, np.where(want >= 0, keep[np.maximum(want, 0)], -1)) and wnm > n // 2
     # ORBVocabularyGpu::transform as Frame::ComputeBoW calls it
     words, nb, nfv = (int(v) for v in np.frombuffer(buf, np.int32, 3, off)); off += 12
     vo = oracle.Vocabulary(vk, vL, vparent, vleaf, vdesc, vweight)

@@ -319,3 +319,37 @@ def test_search_by_bow(P, m, oracle):
     nm_h, match_h = m.SearchByBoW(kps, desc, npf, fvh, pairs, has_point, 0.7, True)
     torch.cuda.synchronize()
     assert np.array_equal(nm_d.cpu().numpy(), nm_h) and np.array_equal(match_d.cpu().numpy(), match_h)
+
+
+@pytest.mark.parametrize("seed,th,nnratio,stereo,far", [(1, 3.0, 0.8, False, False), (2, 1.0, 0.8, False, True),
+                                                        (3, 5.0, 0.9, True, False), (4, 15.0, 0.6, True, True)])
+def test_search_by_projection_whole_function(P, m, oracle, seed, th, nnratio, stereo, far):
+    """ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints) (orb_matcher.cc:42-134),
+    greedy claim included, against the oracle and -- where oracle/_ref travelled -- the reference's own lines."""
+    from oracle import ref as R
+    from test_oracle_vs_ref_frame import _frame_and_points, projection_windows, W, H
+    kps, desc, pts, qdesc, src, rng = _frame_and_points(oracle, seed, nq=900)     # 900 points on ~1000 keypoints: many conflicts
+    bounds = (0.0, float(W), 0.0, float(H))
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    sf = oracle.Extractor(1000).tables()["scale"]
+    pre = (rng.random(len(kps)) < 0.2).astype(np.uint8)
+    u_right = qur = qerr = None
+    keep, q = projection_windows(oracle, sf, pts, th, far, 40.0)
+    if stereo:
+        u_right = np.where(rng.random(len(kps)) < 0.6, kps["x"] - rng.uniform(2, 60, len(kps)), -1.0).astype(np.float32)
+        pts["proj_xr"] = pts["proj_x"] - rng.uniform(2, 60, len(pts)).astype(np.float32)
+        ok = u_right[src] > 0
+        pts["proj_xr"][ok] = u_right[src][ok] + rng.normal(0, 2, ok.sum()).astype(np.float32)
+        qur, qerr = pts["proj_xr"][keep], q["r"]
+    nm, got = m.SearchByProjection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
+    wnm, want = oracle.search_by_projection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
+    assert nm == wnm and np.array_equal(got, want) and wnm > 150
+    # the greedy claim matters: without it (every window against the initial state) other keypoints would be assigned
+    free = oracle.window_search(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr)
+    assert len(set(free["best_idx"][free["best_idx"] >= 0])) < (free["best_idx"] >= 0).sum()
+    if R.frame_available():
+        rnm, rwant = R.search_by_projection(kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, 40.0)
+        assert nm == rnm and np.array_equal(np.where(got >= 0, keep[np.maximum(got, 0)], -1), rwant)
+    # no windows / no keypoints
+    nm0, got0 = m.SearchByProjection(kps, desc, geom, q[:0], qdesc[:0], pre)
+    assert nm0 == 0 and (got0 == -1).all()

@@ -94,36 +94,29 @@ def _frame_and_points(oracle, seed, nq=600):
     return kps, desc, pts, qdesc, src, rng
 
 
-def _greedy_with_oracle(oracle, kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, th_far):
-    """orb_matcher.cc:42-134 around the oracle's window search: the greedy claim of frame keypoints in map-point order."""
-    min_x, max_x, min_y, max_y = bounds
-    geom = (min_x, min_y, np.float32(64) / np.float32(max_x - min_x), np.float32(48) / np.float32(max_y - min_y), 64, 48)
-    skip = np.zeros(len(kps), np.uint8) if pre is None else pre.astype(np.uint8).copy()
-    assigned = np.full(len(kps), -1, np.int32)
-    nm = 0
-    for i, p in enumerate(pts):
-        if not p["in_view"] or (far and p["depth"] > th_far) or p["bad"]:
-            continue
+def projection_windows(oracle, sf, pts, th, far, th_far):
+    """orb_matcher.cc:50-70: the map points that pass the entry tests and their windows (the host side of the call)."""
+    keep = [i for i, p in enumerate(pts) if p["in_view"] and not (far and p["depth"] > th_far) and not p["bad"]]
+    q = np.zeros(len(keep), oracle.WQ_DTYPE)
+    for j, i in enumerate(keep):
+        p = pts[i]
         r = np.float32(2.5) if p["view_cos"] > 0.998 else np.float32(4.0)       # RadiusByViewingCos :208-213
         if th != 1.0:
             r = np.float32(r * np.float32(th))
-        rad = np.float32(r * sf[p["level"]])
-        q = np.zeros(1, oracle.WQ_DTYPE)
-        q["u"], q["v"], q["r"] = p["proj_x"], p["proj_y"], rad
-        q["min_level"], q["max_level"] = p["level"] - 1, p["level"]
-        if u_right is None:
-            res = oracle.window_search(kps, desc, geom, q, qdesc[i:i + 1], skip)[0]
-        else:
-            res = oracle.window_search(kps, desc, geom, q, qdesc[i:i + 1], skip, u_right,
-                                       np.array([p["proj_xr"]], np.float32), np.array([rad], np.float32))[0]
-        if res["best_idx"] < 0 or res["best_dist"] > 100:                          # :117 TH_HIGH
-            continue
-        if res["best_level"] == res["best_level2"] and res["best_dist"] > np.float32(nnratio) * np.float32(res["best_dist2"]):
-            continue
-        assigned[res["best_idx"]] = i                                                # :121
-        skip[res["best_idx"]] = 1                                                    # its map point now has observations
-        nm += 1
-    return nm, assigned
+        q[j] = (p["proj_x"], p["proj_y"], np.float32(r * sf[p["level"]]), p["level"] - 1, p["level"])
+    return np.array(keep, np.int64), q
+
+
+def _greedy_with_oracle(oracle, kps, desc, bounds, sf, pts, qdesc, pre, u_right, th, nnratio, far, th_far):
+    """The whole SearchByProjection through the oracle: windows on the host side, search + greedy claim in orc_search_by_projection."""
+    min_x, max_x, min_y, max_y = bounds
+    geom = (min_x, min_y, np.float32(64) / np.float32(max_x - min_x), np.float32(48) / np.float32(max_y - min_y), 64, 48)
+    keep, q = projection_windows(oracle, sf, pts, th, far, th_far)
+    if u_right is None:
+        nm, assigned = oracle.search_by_projection(kps, desc, geom, q, qdesc[keep], pre, None, None, None, 100, nnratio)
+    else:
+        nm, assigned = oracle.search_by_projection(kps, desc, geom, q, qdesc[keep], pre, u_right, pts["proj_xr"][keep], q["r"], 100, nnratio)
+    return nm, np.where(assigned >= 0, keep[np.maximum(assigned, 0)], -1).astype(np.int32)
 
 
 @pytest.mark.parametrize("seed,th,nnratio,stereo,far", [(1, 3.0, 0.8, False, False), (2, 1.0, 0.8, False, True),
