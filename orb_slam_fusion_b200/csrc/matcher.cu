@@ -10,6 +10,8 @@
 // therefore exact under any parallel order.
 #include <limits.h>
 
+#include <stdlib.h>
+
 #include "orbx_kernels.cuh"
 #include "orbx_math.cuh"
 
@@ -641,12 +643,10 @@ int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points
 // keypoints of a cell in insertion (= index) order (frame.cc:438-465, 718-743); the
 // best / second-best recurrences of orb_matcher.cc:98-112 equal the two smallest keys
 // (distance, cell = ix*rows + iy, keypoint index), so no cell lists have to be built.
-// `claimed` (may be NULL): assigned[] of k_projection_claim -- keypoints an earlier query of the same call took.
 __device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                             const orbm_grid_geom& g, const orbm_window_query& Q, const uint8_t* __restrict__ qd_row,
-                                            const uint8_t* __restrict__ skip, const int32_t* claimed,
-                                            const float* __restrict__ kp_u_right, float q_ur, float q_err, int lane,
-                                            unsigned long long& b0, unsigned long long& b1) {
+                                            const uint8_t* __restrict__ skip, const float* __restrict__ kp_u_right, float q_ur,
+                                            float q_err, int lane, unsigned long long& b0, unsigned long long& b1) {
   // frame.cc:684-712 cell range of the window
   int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
   int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
@@ -677,7 +677,6 @@ __device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, con
     const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
     if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
     if (skip && skip[i]) continue;
-    if (claimed && claimed[i] >= 0) continue;
     if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
       const float ur = kp_u_right[i];
       if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
@@ -710,52 +709,159 @@ __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict
                                                        const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                        const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                        const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
-                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out,
-                                                       int32_t* __restrict__ idx2_out) {
+                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out) {
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (qi >= nq) return;
   const orbm_window_query Q = q[qi];
   unsigned long long b0, b1;
-  window_scan(kps, desc, n, g, Q, qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+  window_scan(kps, desc, n, g, Q, qdesc + 32 * (size_t)qi, skip, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
               kp_u_right ? q_max_err[qi] : 0.f, lane, b0, b1);
-  if (lane == 0) {
-    out[qi] = window_result(kps, b0, b1);
-    if (idx2_out) idx2_out[qi] = b1 != ~0ull ? (int32_t)(b1 & 0xFFFFFFu) : -1;
+  if (lane == 0) out[qi] = window_result(kps, b0, b1);
+}
+
+// ---- the whole ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (orb_matcher.cc:42-134, Nleft == -1)
+// Key of the claim path: distance << 48 | cell << 28 | keypoint << 4 | octave (the octave rides along, it never decides).
+__device__ __forceinline__ unsigned long long claim_key(int dist, int cell, int idx, int octave) {
+  return ((unsigned long long)dist << 48) | ((unsigned long long)cell << 28) | ((unsigned long long)idx << 4) | (unsigned)(octave & 15);
+}
+__device__ __forceinline__ void cmpex(unsigned long long& a, unsigned long long& b) {
+  const unsigned long long lo = min(a, b), hi = max(a, b);
+  a = lo;
+  b = hi;
+}
+
+// The four smallest keys of a window (sorted), lanes over the keypoints.  `bitmap` (may be NULL): keypoints claimed by
+// earlier map points of the same call.
+__device__ __forceinline__ void window_top4(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                            const orbm_grid_geom& g, const orbm_window_query& Q, const uint8_t* __restrict__ qd_row,
+                                            const uint8_t* __restrict__ skip, const uint32_t* bitmap,
+                                            const float* __restrict__ kp_u_right, float q_ur, float q_err, int lane,
+                                            unsigned long long (&k)[4]) {
+  int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
+  int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
+  int c0y = (int)floorf(f_mul(f_sub(f_sub(Q.v, g.min_y), Q.r), g.inv_h));
+  int c1y = (int)ceilf(f_mul(f_add(f_sub(Q.v, g.min_y), Q.r), g.inv_h));
+  c0x = c0x < 0 ? 0 : c0x;
+  c1x = c1x > g.cols - 1 ? g.cols - 1 : c1x;
+  c0y = c0y < 0 ? 0 : c0y;
+  c1y = c1y > g.rows - 1 ? g.rows - 1 : c1y;
+  const bool ok = !(c0x >= g.cols || c1x < 0 || c0y >= g.rows || c1y < 0);
+  const bool check_levels = Q.min_level >= 0 || Q.max_level >= 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) k[j] = ~0ull;
+  if (!ok) return;  // warp-uniform
+  uint32_t qd[8];
+  load_row_any(qd_row, qd);
+  for (int i = lane; i < n; i += 32) {
+    const orbx_kp K = kps[i];
+    const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
+    const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
+    if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
+    if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
+    if (check_levels) {
+      if (K.octave < Q.min_level) continue;
+      if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
+    }
+    const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
+    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+    if (skip && skip[i]) continue;
+    if (bitmap && ((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
+    if (kp_u_right) {
+      const float ur = kp_u_right[i];
+      if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
+    }
+    uint32_t kd[8];
+    load_row_any(desc + 32 * (size_t)i, kd);
+    unsigned long long key = claim_key(ham256(qd, kd), px * g.rows + py, i, K.octave);
+#pragma unroll
+    for (int j = 0; j < 4; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the five falls out
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    unsigned long long t[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) t[j] = __shfl_xor_sync(0xffffffffu, k[3 - j], o);  // the partner's list, reversed
+#pragma unroll
+    for (int j = 0; j < 4; j++) k[j] = min(k[j], t[j]);  // the four smallest of the union (a bitonic sequence)
+    cmpex(k[0], k[2]);
+    cmpex(k[1], k[3]);
+    cmpex(k[0], k[1]);
+    cmpex(k[2], k[3]);
   }
 }
 
-// The greedy claim of ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (orb_matcher.cc:42-134,
-// Nleft == -1) over the results of k_window_search, exact: one warp walks the projected map points IN ORDER; a result
-// computed against the call's initial state is still the reference's unless its best or second-best keypoint has been
-// taken by an earlier map point of this call (a keypoint that holds a map point with observations is skipped, :86-87)
-// -- only then the window is scanned again, now against the current claims.
-__global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+__global__ void __launch_bounds__(256) k_window_top4(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                     const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
+                                                     const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                     const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
+                                                     const float* __restrict__ q_max_err, unsigned long long* __restrict__ keys4) {
+  const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (qi >= nq) return;
+  unsigned long long k[4];
+  window_top4(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+              kp_u_right ? q_max_err[qi] : 0.f, lane, k);
+  if (lane < 4) keys4[4 * (size_t)qi + lane] = lane == 0 ? k[0] : lane == 1 ? k[1] : lane == 2 ? k[2] : k[3];
+}
+
+// The greedy claim (:86-87, :117-121), exact: one warp walks the map points IN ORDER.  The four best keypoints of every
+// window were found in parallel against the call's initial state; removing the keypoints that earlier map points of this
+// call have claimed leaves that list in order, so its first two survivors are the reference's best and second best --
+// unless fewer than two survive out of a full list, and only then the window is scanned again against the claims.
+// Claims live in a shared-memory bitmap; the queries' keys are fetched 32 at a time and passed around by shuffles.
+__global__ void __launch_bounds__(32) k_projection_claim_seq(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                          const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                          const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                          const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
-                                                         const float* __restrict__ q_max_err, const orbm_window_result* __restrict__ res,
-                                                         const int32_t* __restrict__ idx2, int th_high, float nnratio,
-                                                         int32_t* assigned, int32_t* __restrict__ n_matches) {
+                                                         const float* __restrict__ q_max_err,
+                                                         const unsigned long long* __restrict__ keys4, int th_high, float nnratio,
+                                                         int32_t* __restrict__ assigned, int32_t* __restrict__ n_matches) {
+  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words
   const int lane = threadIdx.x;
   for (int i = lane; i < n; i += 32) assigned[i] = -1;
+  for (int i = lane; i < (n + 31) / 32; i += 32) claim_bits[i] = 0;
   __syncwarp();
   int nm = 0;
-  for (int qi = 0; qi < nq; qi++) {
-    orbm_window_result r = res[qi];
-    const int i2 = idx2[qi];
-    const bool dirty = (r.best_idx >= 0 && assigned[r.best_idx] >= 0) || (i2 >= 0 && assigned[i2] >= 0);
-    if (dirty) {  // warp-uniform
-      unsigned long long b0, b1;
-      window_scan(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, assigned, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
-                  kp_u_right ? q_max_err[qi] : 0.f, lane, b0, b1);
-      r = window_result(kps, b0, b1);
+  for (int base = 0; base < nq; base += 32) {
+    unsigned long long mine[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    if (base + lane < nq) {
+      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)(base + lane));
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)(base + lane) + 2);
+      mine[0] = a.x; mine[1] = a.y; mine[2] = b.x; mine[3] = b.y;
     }
-    // orb_matcher.cc:117-134: ratio to the second match only if both are in the same scale level
-    if (r.best_idx >= 0 && r.best_dist <= th_high &&
-        !(r.best_level == r.best_level2 && (float)r.best_dist > f_mul(nnratio, (float)r.best_dist2))) {
-      if (lane == 0) assigned[r.best_idx] = qi;  // F.mvpMapPoints[bestIdx] = pMP (:121); pMP has observations, so it blocks later ones
-      nm++;
-      __syncwarp();
+    const int cnt = min(32, nq - base);
+    for (int j = 0; j < cnt; j++) {
+      unsigned long long b0 = ~0ull, b1 = ~0ull;
+      int survivors = 0;
+      bool full = true;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const unsigned long long key = __shfl_sync(0xffffffffu, mine[e], j);
+        if (key == ~0ull) { full = false; continue; }
+        const int idx = (int)((key >> 4) & 0xFFFFFFu);
+        if ((claim_bits[idx >> 5] >> (idx & 31)) & 1u) continue;
+        if (survivors == 0) b0 = key; else if (survivors == 1) b1 = key;
+        survivors++;
+      }
+      const int qi = base + j;
+      if (survivors < 2 && full) {  // the list may continue beyond its four entries (warp-uniform: every lane holds the same keys)
+        unsigned long long k[4];
+        window_top4(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+                    kp_u_right ? q_max_err[qi] : 0.f, lane, k);
+        b0 = k[0];
+        b1 = k[1];
+      }
+      if (b0 == ~0ull) continue;
+      // orb_matcher.cc:117-121: accept within TH_HIGH; the ratio to the second match counts only inside one scale level
+      const int d0 = (int)(b0 >> 48), l0 = (int)(b0 & 15u), idx0 = (int)((b0 >> 4) & 0xFFFFFFu);
+      const int d1 = b1 == ~0ull ? 256 : (int)(b1 >> 48), l1 = b1 == ~0ull ? -1 : (int)(b1 & 15u);
+      if (d0 <= th_high && !(l0 == l1 && (float)d0 > f_mul(nnratio, (float)d1))) {
+        if (lane == 0) {
+          assigned[idx0] = qi;  // F.mvpMapPoints[bestIdx] = pMP (:121); pMP has observations, so it blocks later map points
+          claim_bits[idx0 >> 5] |= 1u << (idx0 & 31);
+        }
+        nm++;
+        __syncwarp();
+      }
     }
   }
   if (lane == 0) *n_matches = nm;
@@ -765,21 +871,122 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
                          const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                          const float* q_max_err, orbm_window_result* out, cudaStream_t st) {
   if (nq <= 0) return 0;
-  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out, nullptr);
+  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out);
   return 1;
 }
 
+// The same claim, 32 map points at a time.  Every lane takes one map point of the batch; a lane may decide in a round
+// when no EARLIER undecided lane of the batch lists any of its (<= 4) keypoints -- then nothing that happens before it in
+// the reference's order can change what it sees, and the lanes that decide together have disjoint lists, so their claims
+// do not interact.  The lowest undecided lane is never blocked, so every round makes progress; without conflicts a batch
+// takes one round.  A lane that has to re-scan its window (fewer than two survivors of a full list) may pick a keypoint
+// outside its list, so it decides alone as the last lane of its round.  lister[i]: bit L = lane L of the batch lists
+// keypoint i (shared memory, n words).
+__global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+                                                         const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
+                                                         const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
+                                                         const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
+                                                         const float* __restrict__ q_max_err,
+                                                         const unsigned long long* __restrict__ keys4, int th_high, float nnratio,
+                                                         int32_t* __restrict__ assigned, int32_t* __restrict__ n_matches) {
+  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then lister[n]
+  const int lane = threadIdx.x, words = (n + 31) / 32;
+  uint32_t* lister = claim_bits + words;
+  for (int i = lane; i < n; i += 32) { assigned[i] = -1; lister[i] = 0; }
+  for (int i = lane; i < words; i += 32) claim_bits[i] = 0;
+  __syncwarp();
+  const unsigned lt = (1u << lane) - 1u;
+  int nm = 0;
+  for (int base = 0; base < nq; base += 32) {
+    const int qi = base + lane;
+    unsigned long long k[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+    if (qi < nq) {
+      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)qi);
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)qi + 2);
+      k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
+    }
+    int idx[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      idx[e] = k[e] == ~0ull ? -1 : (int)((k[e] >> 4) & 0xFFFFFFu);
+      if (idx[e] >= 0) atomicOr(&lister[idx[e]], 1u << lane);
+    }
+    __syncwarp();
+    unsigned undecided = __ballot_sync(0xffffffffu, qi < nq && idx[0] >= 0);  // an empty list decides nothing (:75)
+    while (undecided) {
+      const bool mine = (undecided >> lane) & 1u;
+      unsigned before = 0;
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (mine && idx[e] >= 0) before |= lister[idx[e]];
+      unsigned ready = __ballot_sync(0xffffffffu, mine && (before & undecided & lt) == 0);
+      // survivors of the list under the claims so far
+      unsigned long long b0 = ~0ull, b1 = ~0ull;
+      int survivors = 0;
+      if ((ready >> lane) & 1u) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          if (idx[e] < 0 || ((claim_bits[idx[e] >> 5] >> (idx[e] & 31)) & 1u)) continue;
+          if (survivors == 0) b0 = k[e]; else if (survivors == 1) b1 = k[e];
+          survivors++;
+        }
+      }
+      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < 2 && idx[3] >= 0);
+      if (rescan) {  // the first lane that must look beyond its list ends the round
+        const int r = __ffs(rescan) - 1;
+        ready &= (2u << r) - 1u;
+        const int rq = base + r;
+        unsigned long long t[4];
+        window_top4(kps, desc, n, g, q[rq], qdesc + 32 * (size_t)rq, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[rq] : 0.f,
+                    kp_u_right ? q_max_err[rq] : 0.f, lane, t);
+        if (lane == r) { b0 = t[0]; b1 = t[1]; }
+      }
+      bool accept = false;
+      if (((ready >> lane) & 1u) && b0 != ~0ull) {
+        // orb_matcher.cc:117-121: accept within TH_HIGH; the ratio to the second match counts only inside one scale level
+        const int d0 = (int)(b0 >> 48), l0 = (int)(b0 & 15u), i0 = (int)((b0 >> 4) & 0xFFFFFFu);
+        const int d1 = b1 == ~0ull ? 256 : (int)(b1 >> 48), l1 = b1 == ~0ull ? -1 : (int)(b1 & 15u);
+        accept = d0 <= th_high && !(l0 == l1 && (float)d0 > f_mul(nnratio, (float)d1));
+        if (accept) {
+          assigned[i0] = qi;  // F.mvpMapPoints[bestIdx] = pMP (:121); pMP has observations, so it blocks later map points
+          atomicOr(&claim_bits[i0 >> 5], 1u << (i0 & 31));
+        }
+      }
+      nm += __popc(__ballot_sync(0xffffffffu, accept));
+      undecided &= ~ready;
+      __syncwarp();
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      if (idx[e] >= 0) lister[idx[e]] = 0;
+    __syncwarp();
+  }
+  if (lane == 0) *n_matches = nm;
+}
+
+size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 4 * sizeof(unsigned long long); }
+
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
-                                const float* q_max_err, int th_high, float nnratio, orbm_window_result* res,
-                                int32_t* idx2, int32_t* assigned, int32_t* n_matches, cudaStream_t st) {
+                                const float* q_max_err, int th_high, float nnratio, void* scratch, int32_t* assigned,
+                                int32_t* n_matches, cudaStream_t st) {
+  unsigned long long* keys4 = static_cast<unsigned long long*>(scratch);
   int launches = 1;
   if (nq > 0) {
-    k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, res, idx2);
+    k_window_top4<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4);
     launches++;
   }
-  k_projection_claim<<<1, 32, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, res, idx2, th_high,
-                                       nnratio, assigned, n_matches);
+  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem = bits + (size_t)(n + 1) * sizeof(uint32_t);
+  const char* force_seq = getenv("ORBM_CLAIM_SEQUENTIAL");  // test hook: the one-map-point-at-a-time kernel of very large frames
+  if (smem <= 200 * 1024 && !(force_seq && force_seq[0] == '1')) {  // the batched claim keeps one word per keypoint in shared memory (up to ~50 k keypoints)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_projection_claim<<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
+                                            nnratio, assigned, n_matches);
+  } else {
+    if (bits > 48 * 1024) cudaFuncSetAttribute(k_projection_claim_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bits);
+    k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
+                                                nnratio, assigned, n_matches);
+  }
   return launches;
 }
 

@@ -363,7 +363,8 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
       n >= (1 << 24) || (n > 0 && (!kps || !desc || !assigned)) || (nq > 0 && (!queries || !qdesc)) || !n_matches ||
       (kp_u_right && nq > 0 && (!q_u_right || !q_max_err)))
     return fail(m, ORBX_E_ARG, "bad argument");
-  const size_t scratch = pad256((size_t)nq * sizeof(orbm_window_result)) + pad256((size_t)nq * 4);
+  if ((size_t)((n + 31) / 32 + 1) * 4 > 200 * 1024) return fail(m, ORBX_E_UNSUPPORTED, "more than 1.6 M keypoints in one frame");
+  const size_t scratch = pad256(projection_scratch_bytes(nq));
   if (mem == ORBX_MEM_HOST) {
     TRY(arena_reserve(m, pad256((size_t)n * 28) + pad256((size_t)n * 32) + pad256((size_t)nq * sizeof(orbm_window_query)) +
                              pad256((size_t)nq * 32) + pad256((size_t)n) + pad256((size_t)n * 4) + 2 * pad256((size_t)nq * 4) +
@@ -387,9 +388,8 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
   }
   int32_t* dassigned = stage_out(m, mem, assigned, (size_t)n);
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)1);
-  orbm_window_result* dres = arena_take<orbm_window_result>(m, (size_t)nq);
-  int32_t* didx2 = arena_take<int32_t>(m, (size_t)nq);
-  m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dres, didx2,
+  void* dscratch = arena_take<uint8_t>(m, projection_scratch_bytes(nq));
+  m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dscratch,
                                              dassigned, dnm, st);
   TRY(finish_out(m, mem, assigned, dassigned, (size_t)n, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)1, st));

@@ -1,5 +1,7 @@
 """GPU parity of the Hamming matching kernels through the C ABI against the golden BFMatcher vectors
 and the CPU oracle: distances, 2-NN with ties, sharded merge, ratio test, stereo row band, windows."""
+import os
+
 import numpy as np
 import pytest
 
@@ -344,6 +346,12 @@ def test_search_by_projection_whole_function(P, m, oracle, seed, th, nnratio, st
     nm, got = m.SearchByProjection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
     wnm, want = oracle.search_by_projection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
     assert nm == wnm and np.array_equal(got, want) and wnm > 150
+    os.environ["ORBM_CLAIM_SEQUENTIAL"] = "1"          # the fallback kernel of frames too large for the shared-memory tables
+    try:
+        nm_s, got_s = m.SearchByProjection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
+    finally:
+        del os.environ["ORBM_CLAIM_SEQUENTIAL"]
+    assert nm_s == wnm and np.array_equal(got_s, want)
     # the greedy claim matters: without it (every window against the initial state) other keypoints would be assigned
     free = oracle.window_search(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr)
     assert len(set(free["best_idx"][free["best_idx"] >= 0])) < (free["best_idx"] >= 0).sum()
