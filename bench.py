@@ -279,7 +279,8 @@ def run_ours(args):
     log('device-resident timing done: %.3f ms' % ms)
     # ---- end to end through the C ABI with pinned host buffers
     eb = ex_e2e = None
-    eb = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=min(128, B))
+    E2E_CHUNK = min(64, B)  # frames per pipelined chunk of the host-memory path (the handle's max_batch)
+    eb = P.OrbExtractor(NFEAT, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=E2E_CHUNK)
     h_frames = torch.empty((B, H, W), dtype=torch.uint8, pin_memory=True)
     h_frames.copy_(frames)
     h_kps = torch.empty((B, cap, 7), dtype=torch.float32, pin_memory=True)
@@ -306,7 +307,8 @@ def run_ours(args):
     barrier()
     assert np.array_equal(h_n.numpy(), n_host), "host-memory path disagrees with device-memory path"
     e2e = {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
-           "d2h_bytes_per_step": B * (cap * (28 + 32) + 8), "ms_per_step": 1e3 * e2e_s / args.steps}
+           "d2h_bytes_per_step": B * (cap * (28 + 32) + 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+           "chunk_frames": E2E_CHUNK, "h2d_gbs": world * B * W * H * args.steps / e2e_s / 1e9}
     del eb, h_kps, h_desc
 
     log('e2e done')

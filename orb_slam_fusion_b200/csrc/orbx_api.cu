@@ -31,10 +31,16 @@ struct Slot {
   int32_t* d_n = nullptr;       // [max_batch] n, then [max_batch] n_mono
   int32_t* h_n = nullptr;       // pinned mirror of d_n
   cudaStream_t stream = nullptr;
+  // host-memory batches: the frames of a chunk travel on the handle's copy stream; ev_h2d tells this slot's stream
+  // that they have arrived, ev_import tells the copy stream that k_import has consumed the staging buffer
+  cudaEvent_t ev_h2d = nullptr, ev_import = nullptr;
+  bool import_pending = false;  // ev_import has been recorded for the chunk that last used d_img
   std::vector<void*> allocs;
 };
 
 }  // namespace
+
+constexpr int kOutSlack = 64;  // records per frame the device output rows hold beyond out_cap
 
 struct orbx_extractor {
   orbx_params p{};
@@ -46,6 +52,8 @@ struct orbx_extractor {
   size_t img_pitch = 0;
   int out_cap = 0;
   Slot slot[kSlots];
+  cudaStream_t copy_stream = nullptr;  // H2D of host-memory batches (keeps the copy engine busy across chunks)
+  long long chunk_counter = 0;         // host-memory chunks alternate between the slots across calls too
   void* d_tables = nullptr;
   uint32_t* d_tile_tab = nullptr;
   int last_frames = 0;       // frames of the last chunk processed on slot 0
@@ -335,8 +343,10 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     s.b.yofs = dt + 3 * (size_t)tab;
     s.b.ybeta = dt + 5 * (size_t)tab;
     s.b.tile_tab = h->d_tile_tab;
-    CU(h, dmalloc(s, &s.d_kps, B * sel));
-    CU(h, dmalloc(s, &s.d_desc, B * sel * 32));
+    // kOutSlack extra records per frame: a caller whose row pitch (`cap`) is a little above out_cap gets its
+    // pitch on the device too, so that the results go back over PCIe as ONE linear copy per chunk
+    CU(h, dmalloc(s, &s.d_kps, B * (sel + kOutSlack)));
+    CU(h, dmalloc(s, &s.d_desc, B * (sel + kOutSlack) * 32));
     CU(h, dmalloc(s, &s.d_n, 2 * B));
     CU(h, cudaMallocHost((void**)&s.h_n, 2 * B * sizeof(int32_t)));
     // the padding of the planes is never written by the pipeline kernels; define it once
@@ -353,7 +363,7 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
 // The kernel sequence of OrbExtractor::operator() for `frames` device-resident frames.
 void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int frames,
                       int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono,
-                      int out_frame0, cudaStream_t st) {
+                      int out_frame0, cudaStream_t st, cudaEvent_t after_import = nullptr) {
   FrameGeom g = h->g;
   g.lap0 = lap0;
   g.lap1 = lap1;
@@ -368,6 +378,7 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   };
   mark();
   n += launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
+  if (after_import) cudaEventRecord(after_import, st);  // the staging buffer may be overwritten from here on
   mark();
   n += launch_pyramid(g, s.b, frames, st);
   mark();
@@ -384,25 +395,28 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
 // as ONE linear copy with their padding (a 2-D copy is one DMA descriptor per 752-byte row and runs
 // at a fraction of the link rate); the import kernel reads any row stride.
 int stage_frames(orbx_t* h, Slot& s, const uint8_t* src, int w, int hh, size_t row_stride, size_t frame_stride, int nf,
-                 size_t* d_row_stride, size_t* d_frame_stride) {
+                 size_t* d_row_stride, size_t* d_frame_stride, cudaStream_t st = nullptr) {
+  if (!st) st = s.stream;
   const bool linear = row_stride <= (size_t)w + 64 && (nf == 1 || frame_stride == row_stride * (size_t)hh);
   const size_t rs = linear ? row_stride : h->img_pitch, fs = rs * (size_t)hh;
   const size_t need = fs * (size_t)nf + 16;
   if (need > s.img_bytes) {
     CU(h, cudaStreamSynchronize(s.stream));
+    if (st != s.stream) CU(h, cudaStreamSynchronize(st));
     if (s.d_img) cudaFree(s.d_img);
     s.d_img = nullptr;
     s.img_bytes = 0;
+    s.import_pending = false;
     CU(h, cudaMalloc((void**)&s.d_img, need));
     s.img_bytes = need;
   }
   if (linear) {
     CU(h, cudaMemcpyAsync(s.d_img, src, fs * (size_t)(nf - 1) + row_stride * (size_t)(hh - 1) + (size_t)w,
-                          cudaMemcpyHostToDevice, s.stream));
+                          cudaMemcpyHostToDevice, st));
   } else {
     for (int f = 0; f < nf; f++)
       CU(h, cudaMemcpy2DAsync(s.d_img + (size_t)f * fs, rs, src + (size_t)f * frame_stride, row_stride, (size_t)w,
-                              (size_t)hh, cudaMemcpyHostToDevice, s.stream));
+                              (size_t)hh, cudaMemcpyHostToDevice, st));
   }
   *d_row_stride = rs;
   *d_frame_stride = fs;
@@ -447,7 +461,10 @@ int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** o
   build_tables(h);
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return ORBX_E_CUDA; }
   for (auto& s : h->slot)
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_import, cudaEventDisableTiming) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
   *out = h;
   return ORBX_OK;
 }
@@ -455,13 +472,18 @@ int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** o
 void orbx_destroy(orbx_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   for (auto& s : h->slot)
     if (s.stream) cudaStreamSynchronize(s.stream);
   free_geometry(h);
   for (cudaEvent_t e : h->ev_used) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
-  for (auto& s : h->slot)
+  for (auto& s : h->slot) {
     if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_import) cudaEventDestroy(s.ev_import);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
 }
 
@@ -489,6 +511,7 @@ int orbx_max_keypoints(const orbx_t* h) {
 int orbx_sync(orbx_t* h) {
   if (!h) return ORBX_E_ARG;
   CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamSynchronize(h->copy_stream));
   for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
   return ORBX_OK;
 }
@@ -553,25 +576,34 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     return ORBX_OK;
   }
 
-  // host memory: chunks alternate between two working sets, each on its own stream, so the
-  // copies of one chunk overlap the kernels of the other
-  const int dcap = cap < h->out_cap ? cap : h->out_cap;
-  int chunk = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += B, chunk++) {
-    Slot& s = h->slot[chunk % kSlots];
+  // host memory: chunks alternate between two working sets, each with its own stream for kernels and result
+  // copies; the frames travel on a third stream that only waits for k_import to have consumed the staging buffer
+  // of the slot (not for the slot's whole pipeline), so the H2D engine never idles between chunks
+  const int dcap = cap <= h->out_cap + kOutSlack ? cap : h->out_cap;  // device row pitch of the outputs: the caller's when the rows can hold it (one linear D2H per chunk)
+  for (int f0 = 0; f0 < n_frames; f0 += B) {
+    Slot& s = h->slot[h->chunk_counter++ % kSlots];
     const int nf = n_frames - f0 < B ? n_frames - f0 : B;
     const uint8_t* src = imgs + (size_t)f0 * frame_stride;
     size_t drs, dfs;
-    rc = stage_frames(h, s, src, w, hh, row_stride, frame_stride, nf, &drs, &dfs);
+    if (s.import_pending) CU(h, cudaStreamWaitEvent(h->copy_stream, s.ev_import, 0));
+    rc = stage_frames(h, s, src, w, hh, row_stride, frame_stride, nf, &drs, &dfs, h->copy_stream);
     if (rc) return rc;
-    enqueue_pipeline(h, s, s.d_img, drs, dfs, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n, s.d_n + B, 0, s.stream);
-    CU(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), s.d_kps, (size_t)dcap * sizeof(orbx_kp),
-                            (size_t)dcap * sizeof(orbx_kp), nf, cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, s.d_desc, (size_t)dcap * 32, (size_t)dcap * 32, nf,
-                            cudaMemcpyDeviceToHost, s.stream));
+    CU(h, cudaEventRecord(s.ev_h2d, h->copy_stream));
+    CU(h, cudaStreamWaitEvent(s.stream, s.ev_h2d, 0));
+    enqueue_pipeline(h, s, s.d_img, drs, dfs, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n, s.d_n + B, 0, s.stream, s.ev_import);
+    s.import_pending = true;
+    if (dcap == cap) {
+      CU(h, cudaMemcpyAsync(kps + (size_t)f0 * cap, s.d_kps, (size_t)nf * cap * sizeof(orbx_kp), cudaMemcpyDeviceToHost, s.stream));
+      CU(h, cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, s.d_desc, (size_t)nf * cap * 32, cudaMemcpyDeviceToHost, s.stream));
+    } else {
+      CU(h, cudaMemcpy2DAsync(kps + (size_t)f0 * cap, (size_t)cap * sizeof(orbx_kp), s.d_kps, (size_t)dcap * sizeof(orbx_kp),
+                              (size_t)dcap * sizeof(orbx_kp), nf, cudaMemcpyDeviceToHost, s.stream));
+      CU(h, cudaMemcpy2DAsync(desc + (size_t)f0 * cap * 32, (size_t)cap * 32, s.d_desc, (size_t)dcap * 32, (size_t)dcap * 32, nf,
+                              cudaMemcpyDeviceToHost, s.stream));
+    }
     CU(h, cudaMemcpyAsync(n + f0, s.d_n, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     CU(h, cudaMemcpyAsync(n_mono + f0, s.d_n + B, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-    if (chunk % kSlots == 0) h->last_frames = nf;
+    if (&s == &h->slot[0]) h->last_frames = nf;
   }
   if (mem == ORBX_MEM_HOST)
     for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
