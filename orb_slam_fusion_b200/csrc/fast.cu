@@ -363,8 +363,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 }
 
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
-  cudaMemsetAsync(b.n_cand, 0, sizeof(int32_t) * ORBX_MAX_LEVELS * (size_t)frames, st);
-  cudaMemsetAsync(b.cell_strong, 0, sizeof(int32_t) * (size_t)g.total_cells * frames, st);
+  // n_cand and cell_strong were zeroed by k_import, the first kernel of every pipeline
   dim3 grid(g.total_blur_tiles, 1, frames);
   k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
   return 1;

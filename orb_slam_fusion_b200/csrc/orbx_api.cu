@@ -65,7 +65,8 @@ struct orbx_extractor {
   size_t graph_rs = 0, graph_fs = 0;
   const void* graph_img = nullptr;   // staging buffer the graph reads
   int graph_launches = 0;            // kernels one replay launches
-  uint8_t* h_out = nullptr;          // pinned: out_cap keypoint records, then out_cap descriptor rows
+  uint8_t* h_out = nullptr;          // pinned: out_cap keypoint records, out_cap descriptor rows, then n and n_mono
+  uint8_t* d_single = nullptr;       // the same block on the device: the single-frame path returns everything in ONE copy
   // optional per-stage timing (orbx_set_profiling): one event set per enqueued chunk
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // free events
@@ -155,6 +156,7 @@ void free_slot(Slot& s) {
   if (s.d_img) cudaFree(s.d_img);
   s.img_bytes = 0;
   s.d_img = nullptr; s.d_kps = nullptr; s.d_desc = nullptr; s.d_n = nullptr;
+  s.import_pending = false;
 }
 
 void free_geometry(orbx_t* h) {
@@ -162,6 +164,8 @@ void free_geometry(orbx_t* h) {
   h->graph = nullptr;
   if (h->h_out) cudaFreeHost(h->h_out);
   h->h_out = nullptr;
+  if (h->d_single) cudaFree(h->d_single);
+  h->d_single = nullptr;
   for (auto& s : h->slot) free_slot(s);
   if (h->d_tables) cudaFree(h->d_tables);
   h->d_tables = nullptr;
@@ -621,23 +625,24 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   rc = ensure_geometry(h, w, hh);
   if (rc) return rc;
   Slot& s = h->slot[0];
-  const int B = h->max_batch;
   h->border_done = false;
   size_t drs, dfs;
   rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
   if (rc) return rc;
   h->last_frames = 1;
   const size_t kp_bytes = (size_t)h->out_cap * sizeof(orbx_kp), desc_bytes = (size_t)h->out_cap * 32;
-  if (!h->h_out) CU(h, cudaMallocHost((void**)&h->h_out, kp_bytes + desc_bytes));
+  const size_t single_bytes = kp_bytes + desc_bytes + 2 * sizeof(int32_t);
+  if (!h->h_out) CU(h, cudaMallocHost((void**)&h->h_out, single_bytes));
+  if (!h->d_single) CU(h, cudaMalloc((void**)&h->d_single, single_bytes));
+  orbx_kp* const dk = reinterpret_cast<orbx_kp*>(h->d_single);
+  uint8_t* const dd = h->d_single + kp_bytes;
+  int32_t* const dn = reinterpret_cast<int32_t*>(h->d_single + kp_bytes + desc_bytes);  // 28 * cap + 32 * cap is a multiple of 4
   if (h->profiling) {
     // stage events cannot be timed inside a graph: plain launches
-    enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
-    CU(h, cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaMemcpyAsync(h->h_out, s.d_kps, kp_bytes, cudaMemcpyDeviceToHost, s.stream));
-    CU(h, cudaMemcpyAsync(h->h_out + kp_bytes, s.d_desc, desc_bytes, cudaMemcpyDeviceToHost, s.stream));
+    enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, dk, dd, h->out_cap, dn, dn + 1, 0, s.stream);
+    CU(h, cudaMemcpyAsync(h->h_out, h->d_single, single_bytes, cudaMemcpyDeviceToHost, s.stream));
   } else {
-    // 12 kernels + 2 memsets + 4 result copies replayed as one graph launch (single-frame latency is
+    // 12 kernels + the result copy replayed as one graph launch (single-frame latency is
     // launch- and dependency-bound, SURVEY.md section 7 "hard parts")
     if (h->graph && (h->graph_lap0 != lap0 || h->graph_lap1 != lap1 || h->graph_rs != drs || h->graph_fs != dfs ||
                      h->graph_img != s.d_img)) {
@@ -648,11 +653,8 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
       cudaGraph_t graph = nullptr;
       CU(h, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = h->launches;
-      enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, s.d_kps, s.d_desc, h->out_cap, s.d_n, s.d_n + B, 0, s.stream);
-      cudaMemcpyAsync(s.h_n, s.d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream);
-      cudaMemcpyAsync(s.h_n + 1, s.d_n + B, sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream);
-      cudaMemcpyAsync(h->h_out, s.d_kps, kp_bytes, cudaMemcpyDeviceToHost, s.stream);
-      cudaMemcpyAsync(h->h_out + kp_bytes, s.d_desc, desc_bytes, cudaMemcpyDeviceToHost, s.stream);
+      enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, dk, dd, h->out_cap, dn, dn + 1, 0, s.stream);
+      cudaMemcpyAsync(h->h_out, h->d_single, single_bytes, cudaMemcpyDeviceToHost, s.stream);
       h->graph_launches = (int)(h->launches - launches_before);
       h->launches = launches_before;
       CU(h, cudaStreamEndCapture(s.stream, &graph));
@@ -665,7 +667,8 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
     h->launches += h->graph_launches;
   }
   CU(h, cudaStreamSynchronize(s.stream));
-  const int N = s.h_n[0];
+  const int32_t* const hn = reinterpret_cast<const int32_t*>(h->h_out + kp_bytes + desc_bytes);
+  const int N = hn[0];
   if (N < 0) return fail(h, ORBX_E_UNSUPPORTED, "quadtree node table overflow");
   *n = N;
   if (N > cap) return fail(h, ORBX_E_CAP, "%d keypoints, capacity %d", N, cap);
@@ -674,7 +677,7 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
     memcpy(kps, h->h_out, (size_t)N * sizeof(orbx_kp));
     memcpy(desc, h->h_out + kp_bytes, (size_t)N * 32);
   }
-  *n_mono = s.h_n[1];
+  *n_mono = hn[1];
   return ORBX_OK;
 }
 

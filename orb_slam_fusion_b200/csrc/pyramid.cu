@@ -13,10 +13,15 @@ namespace orbx {
 // Copies the caller's frames into the padded level-0 planes.  16 bytes per thread.
 __global__ void __launch_bounds__(256) k_import(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                 const uint8_t* __restrict__ src, size_t row_stride,
-                                                size_t frame_stride, int aligned16, int chunks_per_row) {
+                                                size_t frame_stride, int aligned16, int chunks_per_row,
+                                                int32_t* __restrict__ n_cand, int32_t* __restrict__ cell_strong) {
   // one thread per 16-byte chunk of a frame (rows x chunks flattened, so narrow images still fill the CTAs)
   const int f = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // The first kernel of the pipeline also zeroes the counters k_fast_blur accumulates into (two memset nodes less
+  // in the single-frame graph); the grid has at least w*h/16 threads per frame, far more than cells.
+  for (int c = i; c < g.total_cells; c += gridDim.x * blockDim.x) cell_strong[(size_t)f * g.total_cells + c] = 0;
+  if (i < ORBX_MAX_LEVELS) n_cand[f * ORBX_MAX_LEVELS + i] = 0;
   const LevelGeom& L = g.lv[0];
   const int y = i / chunks_per_row;
   if (y >= L.h) return;
@@ -46,7 +51,7 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
   const int aligned = ((reinterpret_cast<uintptr_t>(src) | row_stride | frame_stride) & 15) == 0;
   const int cpr = (g.lv[0].w + 15) / 16;
   dim3 grid((cpr * g.lv[0].h + 255) / 256, frames);
-  k_import<<<grid, 256, 0, st>>>(g, b.pyr, src, row_stride, frame_stride, aligned, cpr);
+  k_import<<<grid, 256, 0, st>>>(g, b.pyr, src, row_stride, frame_stride, aligned, cpr, b.n_cand, b.cell_strong);
   return 1;
 }
 
