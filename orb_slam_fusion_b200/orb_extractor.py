@@ -96,6 +96,15 @@ class OrbExtractor:
             break
         return nm.value, kps[:n.value].copy(), desc[:n.value].copy()
 
+    def extract_into(self, img, kps, desc, lapping_areas=(0, 0)):
+        """operator() into caller-owned arrays (kps [cap] KP_DTYPE, desc [cap,32] uint8): the bare blocking C-ABI call
+        orbx_extract, no allocation or copy on the Python side.  Returns (mono_index, n)."""
+        h, w = img.shape
+        n, nm = C.c_int(0), C.c_int(0)
+        self._check(self._lib.orbx_extract(self._h, img.ctypes.data, w, h, img.strides[0], int(lapping_areas[0]),
+                                           int(lapping_areas[1]), kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(n), C.byref(nm)))
+        return nm.value, n.value
+
     def extract_batch(self, imgs, lapping_areas=(0, 0), cap=None, stream=None):
         """Batched operator().  `imgs`: [F,H,W] uint8 numpy array (host memory: blocks, returns numpy
         arrays) or CUDA torch tensor (device memory: enqueues on `stream` and returns CUDA tensors).

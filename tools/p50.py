@@ -13,3 +13,9 @@ for _ in range(500):
     t0 = time.perf_counter(); out = ex(img); lat.append(time.perf_counter() - t0)
 assert out[1].tobytes() == ref[1].tobytes() and np.array_equal(out[2], ref[2])
 print("p50 %.4f ms  p10 %.4f  p90 %.4f" % (1e3 * np.median(lat), 1e3 * np.percentile(lat, 10), 1e3 * np.percentile(lat, 90)))
+k1, d1 = np.empty(ex.max_keypoints(), P.KP_DTYPE), np.empty((ex.max_keypoints(), 32), np.uint8)
+lat = []
+for _ in range(1000):
+    t0 = time.perf_counter(); nm, n = ex.extract_into(img, k1, d1); lat.append(time.perf_counter() - t0)
+assert k1[:n].tobytes() == ref[1].tobytes() and np.array_equal(d1[:n], ref[2])
+print("bare C-ABI call: p50 %.4f ms  p10 %.4f  p90 %.4f" % (1e3 * np.median(lat), 1e3 * np.percentile(lat, 10), 1e3 * np.percentile(lat, 90)))
