@@ -25,7 +25,8 @@
 
 namespace orbx {
 
-constexpr int kFtW = 128, kFtH = 32;          // tile of owned pixels (same tiling as the blur kernel)
+constexpr int kFtW = 128, kFtH = kFastTileH;   // tile of owned pixels
+constexpr int kFtThreads = 8 * kFtH, kFtWarps = kFtThreads / 32;  // one warp per four owned rows
 constexpr int kFtRawW = 34;                   // words per row the stencils use: bytes X0-4 .. X0+131
 constexpr int kFtPitch = 4 * kFtRawW;         // 136: byte pitch of the score plane (column cb = x - X0 + 4)
 constexpr int kFtRawPitch = 160;              // raw rows are ten 16-byte chunks from X0-16 (128-bit LDGSTS): column = cb + 12
@@ -34,7 +35,7 @@ constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
 static_assert(kFtRawPitch == kFastTileBoxW && kFtRawH == kFastTileBoxH, "TMA box of the host-side tensor maps");
 constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
 constexpr int kFtStrip = 5;                   // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
-constexpr int kFtMaxOut = 1536;               // NMS survivors of one tile (<= (64+4)*(16+2))
+constexpr int kFtMaxOut = ((kFtW + 8) / 2) * ((kFtH + 3) / 2) + 64;  // NMS survivors of one tile: at most every other pixel of every other row
 
 // byte-wise |a - b| > t for four pixels at once; t <= 126.  VABSDIFF4 is a native instruction,
 // the compare is the high-bit trick (no byte carries: (d & 0x7f) + (0x7f - t) <= 0xfe).
@@ -55,7 +56,7 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
 // q = v / d for 0 <= v < 2^15, d < 2^15 with rcp = ceil(2^32 / d) (host: LevelGeom::wcell_rcp / hcell_rcp)
 __device__ __forceinline__ int div_rcp(int v, uint32_t rcp) { return (int)__umulhi((uint32_t)v, rcp); }
 
-__global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_constant__ FrameGeom g, const CUtensorMap* __restrict__ pyr_maps,
+__global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads) k_fast_blur(const __grid_constant__ FrameGeom g, const CUtensorMap* __restrict__ pyr_maps,
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     if (top || bottom) {
       if (left || right) __syncthreads();  // rows copy the patched columns
       // rows: y = -k <- k and y = h-1+k <- h-1-k (k = 1..3), all 34 words
-      for (int i = tid; i < 3 * kFtRawPW; i += 256) {
+      for (int i = tid; i < 3 * kFtRawPW; i += kFtThreads) {
         const int k = i / kFtRawPW + 1, c = i - (k - 1) * kFtRawPW;
         if (top) raw_w[(4 - k) * kFtRawPW + c] = raw_w[(4 + k) * kFtRawPW + c];
         if (bottom && L.h - 1 + k <= Y0 + kFtH + 2) raw_w[(L.h - 1 + k - Y0 + 4) * kFtRawPW + c] = raw_w[(L.h - 1 - k - Y0 + 4) * kFtRawPW + c];
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     if (4 * q < cols_out) {  // horizontal: thread = (quad q, row pairs warp, warp+8, warp+16); blur row b = raw row b + 1
 #pragma unroll 1
       for (int i = 0; i < 3; i++) {
-        const int pr = (tid >> 5) + 8 * i;
+        const int pr = (tid >> 5) + kFtWarps * i;
         if (2 * pr < rows_out + 6) {
           uint32_t hv[2][4];
 #pragma unroll
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 
   if (tid == 0) { n_list = 0; n_out = 0; }
   static_assert(kScoreBytes % 16 == 0, "score map is cleared with 128-bit stores");
-  for (int i = tid; i < kScoreBytes / 16; i += 256) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kScoreBytes / 16; i += kFtThreads) reinterpret_cast<uint4*>(score)[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
   // ---- 2. rejection test, four pixels per thread, + warp compaction.
@@ -295,7 +296,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   const int nl = n_list;
   const int wrp = tid >> 5;
   int n_corner = 0;  // corners this warp has packed (warp-uniform)
-  for (int c0 = wrp * 32; c0 < nl; c0 += 256) {
+  for (int c0 = wrp * 32; c0 < nl; c0 += kFtThreads) {
     const int i = c0 + lane;
     bool corner = false;
     uint16_t item = 0;
@@ -316,7 +317,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
     const unsigned bal = __ballot_sync(0xffffffffu, corner);  // every lane has read its item
     if (corner) {
       const int v = n_corner + __popc(bal & ((1u << lane) - 1u));
-      list[((v >> 5) << 8) + (wrp << 5) + (v & 31)] = item;
+      list[(v >> 5) * kFtThreads + (wrp << 5) + (v & 31)] = item;
     }
     n_corner += __popc(bal);
   }
@@ -324,7 +325,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 
   // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0 (byte masks per column / row)
   for (int v = lane; v < n_corner; v += 32) {
-    const uint16_t item = list[((v >> 5) << 8) + (wrp << 5) + (v & 31)];
+    const uint16_t item = list[(v >> 5) * kFtThreads + (wrp << 5) + (v & 31)];
     const int rr = item >> 8, cb = item & 255;
     const uint8_t* sp = &score[rr * kFtPitch + cb];
     const int s = sp[0];
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
   if (tid == 0) out_base = atomicAdd(n_cand + f * ORBX_MAX_LEVELS + lev, no);
   __syncthreads();
   const size_t cbase = (size_t)f * g.cand_frame_cap + L.cand_off;
-  for (int i = tid; i < no; i += 256) {
+  for (int i = tid; i < no; i += kFtThreads) {
     const int rr = outl[i] >> 8, cb = outl[i] & 255;
     const int s = score[rr * kFtPitch + cb];
     const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(256, ORBX_FAST_MINB) k_fast_blur(const __grid_
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   // n_cand and cell_strong were zeroed by k_import, the first kernel of every pipeline
   dim3 grid(g.total_blur_tiles, 1, frames);
-  k_fast_blur<<<grid, 256, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
+  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
   return 1;
 }
 

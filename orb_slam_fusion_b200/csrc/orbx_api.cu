@@ -259,7 +259,7 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
     tab += ((L.w > L.h ? L.w : L.h) + 7) / 8 * 8;  // keeps every level's tables 16-byte aligned
     L.blur_tiles_x = (L.w + 127) / 128;
     L.blur_tile_base = tiles;
-    tiles += L.blur_tiles_x * ((L.h + 31) / 32);
+    tiles += L.blur_tiles_x * ((L.h + kFastTileH - 1) / kFastTileH);
   }
   g.total_cells = cells;
   g.pyr_frame_bytes = plane;

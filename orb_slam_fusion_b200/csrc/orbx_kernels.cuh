@@ -34,7 +34,11 @@ struct BatchBuffers {
   const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
 };
 
-constexpr int kFastTileBoxW = 160, kFastTileBoxH = 40;  // bytes x rows of the raw tile k_fast_blur fetches by TMA
+#ifndef ORBX_FAST_TILE_H
+#define ORBX_FAST_TILE_H 32
+#endif
+constexpr int kFastTileH = ORBX_FAST_TILE_H;  // rows of owned pixels per k_fast_blur tile (32: 256-thread CTAs, 64: 512-thread CTAs)
+constexpr int kFastTileBoxW = 160, kFastTileBoxH = kFastTileH + 8;  // bytes x rows of the raw tile k_fast_blur fetches by TMA
 
 // Each launcher enqueues on `st` and returns the number of kernels it launched.
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
