@@ -361,3 +361,55 @@ def test_search_by_projection_whole_function(P, m, oracle, seed, th, nnratio, st
     # no windows / no keypoints
     nm0, got0 = m.SearchByProjection(kps, desc, geom, q[:0], qdesc[:0], pre)
     assert nm0 == 0 and (got0 == -1).all()
+
+
+def test_search_by_bow_random_feature_vectors_and_errors(P, m, oracle):
+    """FeatureVectors that do not come from a vocabulary: random node ids (many on one side only), ragged groups,
+    features missing from every node (stopped words), duplicate descriptors (ties); plus the argument checks."""
+    rng = np.random.default_rng(21)
+    F, cap = 6, 300
+    kps = np.zeros((F, cap), P.KP_DTYPE)
+    kps["angle"] = rng.uniform(0, 360, (F, cap)).astype(np.float32)
+    base = rng.integers(0, 256, (40, 32), dtype=np.uint8)                 # 40 "landmarks": near-duplicates across frames
+    desc = base[rng.integers(0, 40, (F, cap))].copy()
+    flips = rng.integers(0, 256, (F, cap, 6))
+    for j in range(6):
+        np.bitwise_xor.at(desc, (np.arange(F)[:, None], np.arange(cap)[None, :], flips[:, :, j] // 8),
+                          (1 << (flips[:, :, j] % 8)).astype(np.uint8))
+    npf = rng.integers(cap // 2, cap + 1, F).astype(np.int32)
+    npf[0] = cap
+    fv = {k: np.zeros((F, cap), np.uint32 if k != "fv_begin" else np.int32) for k in ("fv_nodes", "fv_begin", "fv_feats")}
+    fv["fv_n"], fv["fv_total"] = np.zeros(F, np.int32), np.zeros(F, np.int32)
+    packed = []
+    for f in range(F):
+        feats = rng.permutation(npf[f])[: int(npf[f] * 0.9)]             # 10 % of the features are in no node
+        nodes = np.sort(rng.choice(60, size=int(rng.integers(5, 40)), replace=False)).astype(np.uint32)
+        cuts = np.sort(rng.integers(0, len(feats) + 1, len(nodes) - 1))
+        groups = [np.sort(g).astype(np.uint32) for g in np.split(feats, cuts)]
+        keep = [i for i, g in enumerate(groups) if len(g)]                # std::map holds no empty vectors
+        nodes, groups = nodes[keep], [groups[i] for i in keep]
+        nd, bg, ft = oracle.pack_feature_vector(nodes, groups)
+        packed.append((nd, bg, ft))
+        fv["fv_nodes"][f, :len(nd)], fv["fv_begin"][f, :len(nd)], fv["fv_feats"][f, :len(ft)] = nd, bg[:len(nd)], ft
+        fv["fv_n"][f], fv["fv_total"][f] = len(nd), len(ft)
+    has_point = (rng.random((F, cap)) < 0.7).astype(np.uint8)
+    pairs = np.array([(a, b) for a in range(F) for b in range(F)], np.int32)
+    for ratio, ori in [(0.9, True), (0.6, False)]:
+        nm, match = m.SearchByBoW(kps, desc, npf, fv, pairs, has_point, ratio, ori)
+        nm2, match2 = m.SearchByBoWKeyFrames(kps, desc, npf, fv, pairs, has_point, ratio, ori)
+        for p, (a, b) in enumerate(pairs):
+            wnm, want = oracle.search_by_bow(kps[a, :npf[a]], desc[a, :npf[a]], has_point[a, :npf[a]], packed[a],
+                                             kps[b, :npf[b]], desc[b, :npf[b]], packed[b], ratio, ori)
+            assert nm[p] == wnm and np.array_equal(match[p, :npf[b]], want), ("frame form", p)
+            wnm, want = oracle.search_by_bow_kf(kps[a, :npf[a]], desc[a, :npf[a]], has_point[a, :npf[a]], packed[a],
+                                                kps[b, :npf[b]], desc[b, :npf[b]], has_point[b, :npf[b]], packed[b], ratio, ori)
+            assert nm2[p] == wnm and np.array_equal(match2[p, :npf[a]], want), ("key-frame form", p)
+        assert nm.sum() > 200
+    with pytest.raises(P.OrbxError):                                      # a pair outside the pool
+        m.SearchByBoW(kps, desc, npf, fv, np.array([[0, F]], np.int32))
+    big = 2049
+    with pytest.raises(P.OrbxError):                                      # more features per frame than a CTA handles
+        m.SearchByBoW(np.zeros((1, big), P.KP_DTYPE), np.zeros((1, big, 32), np.uint8), None,
+                      {"fv_nodes": np.zeros((1, big), np.uint32), "fv_begin": np.zeros((1, big), np.int32),
+                       "fv_feats": np.zeros((1, big), np.uint32), "fv_n": np.zeros(1, np.int32), "fv_total": np.zeros(1, np.int32)},
+                      np.array([[0, 0]], np.int32))
