@@ -52,6 +52,35 @@ def algorithmic_bytes(w, h, n_kp):
     }
 
 
+def cv2_primitive_times(frames):
+    """SURVEY.md 8(d) cross-check: the OpenCV primitives of the path (7 resizes, 8 clone + GaussianBlur, FAST with
+    NMS at iniThFAST on the 8 levels) in real, SIMD-optimised OpenCV on one thread.  The shim under the compiled reference
+    (oracle/minicv) is plain C, so this is the floor a reference built against real OpenCV cannot beat -- its
+    quadtree, orientation and descriptor loops (the reference's own C++) come on top."""
+    try:
+        import cv2
+    except ImportError:
+        return None
+    cv2.setNumThreads(1)
+    fast = cv2.FastFeatureDetector_create(INI_TH, True)  # the reference detects at iniThFAST and retries at minThFAST only in empty cells
+    sizes = level_sizes(W, H)
+    best = None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for f in frames:
+            lv = [f]
+            for (w, h) in sizes[1:]:
+                lv.append(cv2.resize(lv[-1], (w, h), interpolation=cv2.INTER_LINEAR))
+            for im in lv:
+                fast.detect(im)
+                cv2.GaussianBlur(im.copy(), (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        dt = (time.perf_counter() - t0) / len(frames)
+        best = dt if best is None else min(best, dt)
+    return {"ms_per_frame": 1e3 * best, "frames_per_s_bound": 1.0 / best, "cores": 1, "opencv": cv2.__version__,
+            "what": "7 cv2.resize + 8 (copy + cv2.GaussianBlur 7x7) + 8 cv2.FAST(iniThFAST, nms) per 752x480 frame, "
+                    "cv2.setNumThreads(1); excludes the reference's own quadtree / orientation / descriptor code"}
+
+
 def synth_vocabulary(k, L, seed):
     """ORBvoc-shaped synthetic vocabulary tree in breadth-first node order (numpy, seeded): node arrays as
     orbv_create takes them.  A child's descriptor is its parent's with ~256 >> level bits flipped; leaf weights
@@ -483,6 +512,7 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "frames/s", "cores": 1, "kind": kind,
                "sample": "%d blocks-v1 752x480 frames, one extractor object on one thread; host has %d logical cores"
                          % (nfr, os.cpu_count() or 0)}
+        cpu["cv2_primitives"] = cv2_primitive_times(h_frames[:8].numpy())
 
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
