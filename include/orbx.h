@@ -274,6 +274,22 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
                               float nnratio, int32_t* assigned, int32_t* n_matches, int mem, void* stream);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (orb_matcher.cc:1518-1728;
+ * Tracking::TrackWithMotionModel, tracking.cc:2192, 2203) for frames with Nleft == -1, everything after the projection
+ * (:1539-1566 stays host geometry): query q = one map point of the last frame that projects into the current one, in
+ * LastFrame order, with the window (u, v, radius = th * scale[nLastOctave]) and the level range of its motion case
+ * (:1568-1576: forward [nLastOctave, -1], backward [0, nLastOctave], else [nLastOctave-1, nLastOctave+1]), its
+ * descriptor and q_angle = the last frame's keypoint angle; q_u_right = u - bf * invzc and q_max_err = radius drive the
+ * stereo gate (:1586-1590).  Each query takes the nearest keypoint that holds no map point with observations (`skip`
+ * at the start, then the claims of earlier queries; strict <, first wins) if its distance is <= th_high (TH_HIGH);
+ * with check_orientation the matches outside the three dominant bins of the 30-bin rotation histogram are dropped
+ * (:1706-1725).  assigned[i] = query stored in CurrentFrame.mvpMapPoints[i] (-1: untouched), *n_matches = return value. */
+int orbm_search_by_projection_last(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                                   const orbm_window_query* queries, const uint8_t* qdesc, const float* q_angle, int nq,
+                                   const uint8_t* skip, const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                                   int th_high, int check_orientation, int32_t* assigned, int32_t* n_matches, int mem,
+                                   void* stream);
+
 /* ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389; callers
  * tracking.cc:2053, 2909: TrackReferenceKeyFrame and Relocalization) for n_pairs (key frame, frame) pairs taken from
  * one pool of frames in the [frame][cap] layout orbx_extract_batch and orbv_transform produce: frame f owns

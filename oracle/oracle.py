@@ -76,6 +76,7 @@ def lib():
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_window_search_stereo.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, vp]
         L.orc_search_by_projection.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, i, f, vp]
+        L.orc_search_by_projection_last.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, vp, i, vp, vp, vp, vp, i, i, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         L.orc_search_by_bow_kf.argtypes = [vp, vp, vp, i, vp, vp, i, vp, i, vp, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         L.orc_splitmix64.restype = u64
@@ -383,6 +384,28 @@ def search_by_projection(kps, desc, geom, queries, qdesc, skip=None, kp_u_right=
                                         None if sk is None else _p(sk), None if ur is None else _p(ur),
                                         None if qr is None else _p(qr), None if qe is None else _p(qe), int(th_high),
                                         float(nnratio), _p(out))
+    return nm, out[:len(kps)].copy()
+
+
+def search_by_projection_last(kps, desc, geom, queries, qdesc, q_angle, skip=None, kp_u_right=None, q_u_right=None,
+                              q_max_err=None, th_high=100, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728) after the projection:
+    (nmatches, assigned[n])."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, WQ_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    qa = np.ascontiguousarray(q_angle, np.float32)
+    sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    ur = qr = qe = None
+    if kp_u_right is not None:
+        ur, qr, qe = (np.ascontiguousarray(a, np.float32) for a in (kp_u_right, q_u_right, q_max_err))
+    out = np.empty(max(len(kps), 1), np.int32)
+    g = GridGeom(*geom)
+    nm = lib().orc_search_by_projection_last(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc), _p(qa), len(queries),
+                                             None if sk is None else _p(sk), None if ur is None else _p(ur),
+                                             None if qr is None else _p(qr), None if qe is None else _p(qe), int(th_high),
+                                             int(check_orientation), _p(out))
     return nm, out[:len(kps)].copy()
 
 

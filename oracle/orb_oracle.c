@@ -941,6 +941,47 @@ int orc_search_by_projection(const orc_kp* kps, const uint8_t* desc, int n, cons
   return nmatches;
 }
 
+/* ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono), orb_matcher.cc:1518-1728
+ * (Nleft == -1), after the projection: per last-frame map point (in order) the nearest unclaimed keypoint of its window,
+ * accepted within TH_HIGH (:1578-1604), then the rotation histogram (:1606-1624, :1706-1725). */
+int orc_search_by_projection_last(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                                  const orc_window_query* q, const uint8_t* qdesc, const float* q_angle, int nq,
+                                  const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
+                                  const float* q_max_err, int th_high, int check_orientation, int* assigned) {
+  enum { HISTO_LENGTH = 30 };
+  uint8_t* taken = (uint8_t*)calloc((size_t)(n ? n : 1), 1);
+  int* bin_of = (int*)malloc(sizeof(int) * (size_t)(n ? n : 1));
+  int hist[HISTO_LENGTH] = {0};
+  const float factor = HISTO_LENGTH / 360.0f; /* :1527 */
+  int nmatches = 0;
+  for (int i = 0; i < n; i++) { assigned[i] = -1; bin_of[i] = -1; taken[i] = skip ? skip[i] : 0; }
+  for (int qi = 0; qi < nq; qi++) {
+    orc_window_result r;
+    orc_window_search_stereo(kps, desc, n, g, q + qi, qdesc + 32 * (size_t)qi, 1, taken, kp_u_right,
+                             kp_u_right ? q_u_right + qi : NULL, kp_u_right ? q_max_err + qi : NULL, &r);
+    if (r.best_idx < 0 || r.best_dist > th_high) continue; /* :1604 */
+    assigned[r.best_idx] = qi;
+    taken[r.best_idx] = 1;
+    nmatches++;
+    if (check_orientation) { /* :1608-1624 */
+      float rot = q_angle[qi] - kps[r.best_idx].angle;
+      if (rot < 0.0) rot += 360.0f;
+      int bin = (int)roundf(rot * factor);
+      if (bin == HISTO_LENGTH) bin = 0;
+      bin_of[r.best_idx] = bin;
+      hist[bin]++;
+    }
+  }
+  if (check_orientation) { /* :1706-1725 */
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+    for (int i = 0; i < n; i++)
+      if (assigned[i] >= 0 && bin_of[i] != ind1 && bin_of[i] != ind2 && bin_of[i] != ind3) { assigned[i] = -1; nmatches--; }
+  }
+  free(taken); free(bin_of);
+  return nmatches;
+}
+
 /* ---- synthetic inputs, SURVEY.md 8(d) ---- */
 uint64_t orc_splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

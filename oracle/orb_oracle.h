@@ -164,6 +164,14 @@ int orc_search_by_projection(const orc_kp* kps, const uint8_t* desc, int n, cons
                              const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
                              float nnratio, int* assigned);
 
+/* ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (orb_matcher.cc:1518-1728,
+ * Nleft == -1) after the projection: nearest unclaimed keypoint per window within th_high, greedy claim, rotation
+ * histogram.  Pinned on orb_matcher.cc:1518-1728 spliced into oracle/ref_frame_shim.cc. */
+int orc_search_by_projection_last(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                                  const orc_window_query* q, const uint8_t* qdesc, const float* q_angle, int nq,
+                                  const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
+                                  const float* q_max_err, int th_high, int check_orientation, int* assigned);
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches) (orb_matcher.cc:215-386; Nleft == -1): per shared
  * vocabulary node, every key-frame feature with a map point takes the best unclaimed frame feature of the node
  * (<= TH_LOW, ratio test), in order; then the 30-bin rotation histogram keeps the three dominant bins

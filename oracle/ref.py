@@ -302,3 +302,26 @@ def search_by_bow_kf(kps1, desc1, has_point1, fv1, kps2, desc2, has_point2, fv2,
                                         _p(f1p), len(f1), _p(kps2), _p(desc2), len(kps2), None if hp2 is None else _p(hp2), _p(n2),
                                         _p(b2), len(n2), _p(f2p), len(f2), float(nnratio), int(check_orientation), _p(out))
     return nm, out[:len(kps1)].copy()
+
+
+def search_by_projection_last(keys_un, desc, bounds, scale_factors, bf, mb, cam4, t_cw, t_lw, last_keys, last_has_point, last_outlier,
+                              last_world, last_desc, pre_matched=None, u_right=None, th=7.0, mono=False, check_orientation=True):
+    """ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (orb_matcher.cc:1518-1728) with
+    translation-only poses and a pinhole camera (fx, fy, cx, cy).  Returns (nmatches, assigned[n])."""
+    L = _frame()
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.reff_search_by_projection_last.argtypes = [vp, vp, i, vp, f, f, f, f, vp, i, f, f, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, f, i, i, vp]
+    keys_un, last_keys = np.ascontiguousarray(keys_un, KP_DTYPE), np.ascontiguousarray(last_keys, KP_DTYPE)
+    desc, last_desc = np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(last_desc, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    cam4, t_cw, t_lw = (np.ascontiguousarray(a, np.float32) for a in (cam4, t_cw, t_lw))
+    hp, ol = np.ascontiguousarray(last_has_point, np.uint8), np.ascontiguousarray(last_outlier, np.uint8)
+    world = np.ascontiguousarray(last_world, np.float32).reshape(-1, 3)
+    pm = None if pre_matched is None else np.ascontiguousarray(pre_matched, np.uint8)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    assigned = np.empty(max(len(keys_un), 1), np.int32)
+    nm = L.reff_search_by_projection_last(_p(keys_un), _p(desc), len(keys_un), None if ur is None else _p(ur),
+                                          *[float(b) for b in bounds], _p(sf), len(sf), float(bf), float(mb), _p(cam4), _p(t_cw),
+                                          _p(t_lw), _p(last_keys), len(last_keys), _p(hp), _p(ol), _p(world), _p(last_desc),
+                                          None if pm is None else _p(pm), float(th), int(mono), int(check_orientation), _p(assigned))
+    return nm, assigned[:len(keys_un)].copy()

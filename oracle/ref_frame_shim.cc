@@ -14,6 +14,7 @@
 //                                                      ORBmatcher::RadiusByViewingCos
 //   _ref/matcher_bow.inc         orb_matcher.cc:215-389  ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
 //   _ref/matcher_bow_kf.inc      orb_matcher.cc:697-815  ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)
+//   _ref/matcher_project_last.inc orb_matcher.cc:1518-1728 ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
 //   _ref/matcher_maxima.inc      orb_matcher.cc:1841-1873 ORBmatcher::ComputeThreeMaxima
 //   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
 // Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
@@ -35,6 +36,31 @@ using namespace std;
 #define FRAME_GRID_ROWS 48  // include/map/frame.h:40-41
 #define FRAME_GRID_COLS 64
 
+// Stand-ins for the two Eigen / Sophus types orb_matcher.cc:1518-1728 touches, with exactly the operations it uses.  The
+// pose is a pure translation (the harness chooses the poses), so x3Dc = x3Dw + t is one float add per component.
+namespace Eigen {
+struct Vector3f {
+  float v[3];
+  Vector3f() : v{0, 0, 0} {}
+  Vector3f(float a, float b, float c) : v{a, b, c} {}
+  float operator()(int i) const { return v[i]; }
+};
+struct Vector2f {
+  float v[2];
+  Vector2f() : v{0, 0} {}
+  Vector2f(float a, float b) : v{a, b} {}
+  float operator()(int i) const { return v[i]; }
+};
+}  // namespace Eigen
+namespace Sophus {
+struct SE3f {
+  Eigen::Vector3f t;
+  SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t(0), -t(1), -t(2)); return r; }
+  Eigen::Vector3f translation() const { return t; }
+  Eigen::Vector3f operator*(const Eigen::Vector3f &p) const { return Eigen::Vector3f(p(0) + t(0), p(1) + t(1), p(2) + t(2)); }
+};
+}  // namespace Sophus
+
 namespace DBoW2 {  // 3rdparty/DBoW2/DBoW2/FeatureVector.h:24: a std::map from node id to feature indices
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
 }
@@ -43,7 +69,10 @@ namespace ORB_SLAM_FUSION {
 
 class MapPoint;
 class KeyFrame;
-struct GeometricCamera {};
+struct GeometricCamera {  // a pinhole camera (camera_models/pinhole.cc: fx * x / z + cx)
+  float fx = 1, fy = 1, cx = 0, cy = 0;
+  Eigen::Vector2f Project(const Eigen::Vector3f &p) { return Eigen::Vector2f(fx * p(0) / p(2) + cx, fy * p(1) / p(2) + cy); }
+};
 
 // the one member of OrbExtractor that frame.cc:834,913-933 reads
 struct OrbExtractor {
@@ -56,6 +85,7 @@ class ORBmatcher {
   static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
   int SearchByProjection(class Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3,
                          const bool bFarPoints = false, const float thFarPoints = 50.0f);
+  int SearchByProjection(class Frame &CurrentFrame, const class Frame &LastFrame, const float th, const bool bMono);
   int SearchByBoW(KeyFrame *pKF, class Frame &F, std::vector<MapPoint *> &vpMapPointMatches);
   int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12);
   static const int TH_LOW;
@@ -93,6 +123,10 @@ class Frame {  // include/map/frame.h: the members the spliced bodies use, same 
   std::vector<std::size_t> mGridRight[FRAME_GRID_COLS][FRAME_GRID_ROWS];
   DBoW2::FeatureVector mFeatVec;
   GeometricCamera *cam_ = nullptr, *cam2_ = nullptr;
+  Sophus::SE3f pose, Trl;
+  Sophus::SE3f GetPose() const { return pose; }
+  Sophus::SE3f GetRelativePoseTrl() const { return Trl; }
+  std::vector<bool> mvbOutlier;
 };
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 
@@ -113,6 +147,8 @@ class MapPoint {  // include/map/mappoint.h
  public:
   void ComputeDistinctiveDescriptors();
   cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+  Eigen::Vector3f GetWorldPos() { return world; }
+  Eigen::Vector3f world;
   bool isBad() { return mbBad; }
   int Observations() { return nObs; }
 
@@ -135,6 +171,7 @@ class MapPoint {  // include/map/mappoint.h
 #include "frame_stereo.inc"
 #include "mappoint_distinct.inc"
 #include "matcher_project.inc"
+#include "matcher_project_last.inc"
 #include "matcher_bow.inc"
 #include "matcher_bow_kf.inc"
 #include "matcher_maxima.inc"
@@ -310,6 +347,62 @@ int reff_search_by_bow_kf(const void *kps1, const uint8_t *desc1, int n1, const 
   ORBmatcher matcher(nnratio, check_orientation != 0);
   const int nm = matcher.SearchByBoW(&k1, &k2, matches);
   for (int i = 0; i < n1; i++) match_of_1[i] = matches[i] ? (int)(matches[i] - m2.data()) : -1;
+  return nm;
+}
+
+// ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono): the current frame as in
+// reff_search_by_projection (+ bf, mb and a pinhole camera), the last frame as keypoints (octave, angle), per feature a
+// map point or none (has_point), outlier flags, world positions and descriptors; both poses are pure translations.
+// assigned[i] = last-frame feature whose map point CurrentFrame.mvpMapPoints[i] receives (-1: untouched).
+int reff_search_by_projection_last(const void *keys_un, const uint8_t *desc, int n, const float *u_right, float min_x, float max_x,
+                                   float min_y, float max_y, const float *scale, int n_levels, float bf, float mb, const float *cam4,
+                                   const float *t_cw, const float *t_lw, const void *last_keys, int n_last,
+                                   const uint8_t *last_has_point, const uint8_t *last_outlier, const float *last_world,
+                                   const uint8_t *last_desc, const uint8_t *pre_matched, float th, int mono, int check_orientation,
+                                   int *assigned) {
+  Frame F, L;
+  GeometricCamera cam;
+  cam.fx = cam4[0]; cam.fy = cam4[1]; cam.cx = cam4[2]; cam.cy = cam4[3];
+  F.cam_ = &cam;
+  F.N = n;
+  F.mvKeysUn.assign((const cv::KeyPoint *)keys_un, (const cv::KeyPoint *)keys_un + n);
+  F.mvKeys = F.mvKeysUn;
+  F.mDescriptors = cv::Mat(n, 32, CV_8U, (void *)desc);
+  F.mvuRight.assign(n, -1.0f);
+  if (u_right) F.mvuRight.assign(u_right, u_right + n);
+  F.mvScaleFactors.assign(scale, scale + n_levels);
+  F.bf_ = bf;
+  F.mb = mb;
+  F.pose.t = Eigen::Vector3f(t_cw[0], t_cw[1], t_cw[2]);
+  Frame::mnMinX = min_x; Frame::mnMaxX = max_x; Frame::mnMinY = min_y; Frame::mnMaxY = max_y;
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(max_x - min_x);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(max_y - min_y);
+  F.AssignFeaturesToGrid();
+  MapPoint occupied;
+  occupied.nObs = 1;
+  F.mvpMapPoints.assign(n, (MapPoint *)nullptr);
+  for (int i = 0; i < n; i++)
+    if (pre_matched && pre_matched[i]) F.mvpMapPoints[i] = &occupied;
+  L.N = n_last;
+  L.mvKeysUn.assign((const cv::KeyPoint *)last_keys, (const cv::KeyPoint *)last_keys + n_last);
+  L.mvKeys = L.mvKeysUn;
+  L.pose.t = Eigen::Vector3f(t_lw[0], t_lw[1], t_lw[2]);
+  std::vector<MapPoint> mps(n_last > 0 ? n_last : 1);
+  L.mvpMapPoints.assign(n_last, (MapPoint *)nullptr);
+  L.mvbOutlier.assign(n_last, false);
+  for (int i = 0; i < n_last; i++) {
+    if (last_has_point[i]) L.mvpMapPoints[i] = &mps[i];
+    L.mvbOutlier[i] = last_outlier[i] != 0;
+    mps[i].nObs = 1;
+    mps[i].world = Eigen::Vector3f(last_world[3 * i], last_world[3 * i + 1], last_world[3 * i + 2]);
+    mps[i].mDescriptor = cv::Mat(1, 32, CV_8U, (void *)(last_desc + 32 * (size_t)i)).clone();
+  }
+  ORBmatcher matcher(0.9f, check_orientation != 0);
+  const int nm = matcher.SearchByProjection(F, L, th, mono != 0);
+  for (int i = 0; i < n; i++) {
+    MapPoint *p = F.mvpMapPoints[i];
+    assigned[i] = (p && p != &occupied) ? (int)(p - mps.data()) : -1;
+  }
   return nm;
 }
 

@@ -71,6 +71,19 @@ class ORBmatcherGpu {
                          const std::vector<uint8_t>& already_matched, float th, bool far_points, float th_far_points, float nnratio,
                          std::vector<int>& assigned_point);
 
+  // ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono) (orb_matcher.cc:1518-1728,
+  // Nleft == -1; Tracking::TrackWithMotionModel) after the projection of :1539-1566, which stays host geometry:
+  // ProjectedPoint p = one map point of the last frame that projects into the current one, in LastFrame order:
+  // (u, v) = cam_->Project(Tcw * x3Dw), invzc, last_octave / last_angle = LastFrame's keypoint; point_desc row p =
+  // pMP->GetDescriptor().  forward / backward = bForward / bBackward of :1535-1536.  assigned_point[i] = index into
+  // `points` of the map point CurrentFrame.mvpMapPoints[i] receives (-1: untouched); returns nmatches.
+  struct ProjectedPoint { float u, v, invzc; int last_octave; float last_angle; };
+  int SearchByProjectionLastFrame(const std::vector<cv::KeyPoint>& keys_un, const cv::Mat& desc, const std::vector<float>& u_right,
+                                  const std::vector<float>& scale_factors, float bf, float min_x, float min_y, float grid_inv_w,
+                                  float grid_inv_h, int grid_cols, int grid_rows, const std::vector<ProjectedPoint>& points,
+                                  const cv::Mat& point_desc, const std::vector<uint8_t>& already_matched, float th, bool forward,
+                                  bool backward, bool check_orientation, std::vector<int>& assigned_point);
+
   // ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, vpMapPointMatches) (orb_matcher.cc:215-389, Nleft == -1):
   // keys_kf = pKF->mvKeysUn, desc_kf = pKF->mDescriptors, has_point_kf[i] = pKF's feature i holds a map point that is
   // not bad, featvec_kf = pKF->mFeatVec; keys_f = F.mvKeys, desc_f = F.mDescriptors, featvec_f = F.mFeatVec

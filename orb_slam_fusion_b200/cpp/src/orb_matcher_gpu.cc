@@ -142,6 +142,41 @@ int ORBmatcherGpu::SearchByProjection(const std::vector<cv::KeyPoint>& keys, con
   return nm;
 }
 
+int ORBmatcherGpu::SearchByProjectionLastFrame(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc,
+                                               const std::vector<float>& u_right, const std::vector<float>& sf, float bf, float min_x,
+                                               float min_y, float inv_w, float inv_h, int cols, int rows,
+                                               const std::vector<ProjectedPoint>& points, const cv::Mat& point_desc,
+                                               const std::vector<uint8_t>& already, float th, bool forward, bool backward,
+                                               bool check_orientation, std::vector<int>& assigned_point) {
+  const int n = (int)keys.size(), nq = (int)points.size();
+  assigned_point.assign((size_t)n, -1);
+  std::vector<orbm_window_query> windows((size_t)nq);
+  std::vector<float> q_ur((size_t)nq), q_err((size_t)nq), q_angle((size_t)nq);
+  for (int p = 0; p < nq; ++p) {
+    const ProjectedPoint& pt = points[p];
+    const int o = pt.last_octave < 0 ? 0 : (pt.last_octave >= (int)sf.size() ? (int)sf.size() - 1 : pt.last_octave);
+    const float radius = th * sf[o];                                            // :1566
+    const orbm_window_query w = {pt.u, pt.v, radius, forward ? o : (backward ? 0 : o - 1),  // :1568-1576
+                                 forward ? -1 : (backward ? o : o + 1)};
+    windows[p] = w;
+    q_ur[p] = pt.u - bf * pt.invzc;                                             // :1587
+    q_err[p] = radius;                                                          // :1589
+    q_angle[p] = pt.last_angle;
+  }
+  const std::vector<uint8_t> d = dense_rows(desc), qd = dense_rows(point_desc);
+  const orbm_grid_geom g = {min_x, min_y, inv_w, inv_h, cols, rows};
+  std::vector<int32_t> assigned((size_t)std::max(n, 1), -1);
+  int32_t nm = 0;
+  const bool stereo = !u_right.empty();
+  check(m_, orbm_search_by_projection_last(m_, reinterpret_cast<const orbx_kp*>(keys.data()), d.data(), n, &g, windows.data(), qd.data(),
+                                           q_angle.data(), nq, already.empty() ? nullptr : already.data(),
+                                           stereo ? u_right.data() : nullptr, stereo ? q_ur.data() : nullptr,
+                                           stereo ? q_err.data() : nullptr, TH_HIGH, check_orientation ? 1 : 0, assigned.data(), &nm,
+                                           ORBX_MEM_HOST, nullptr));
+  for (int i = 0; i < n; ++i) assigned_point[i] = assigned[i];
+  return nm;
+}
+
 int ORBmatcherGpu::SearchByBoWImpl(bool keyframes, const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
                                    const std::vector<uint8_t>& has_point1,
                                    const std::map<unsigned int, std::vector<unsigned int> >& featvec1,

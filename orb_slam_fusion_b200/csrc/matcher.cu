@@ -882,12 +882,18 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
 // takes one round.  A lane that has to re-scan its window (fewer than two survivors of a full list) may pick a keypoint
 // outside its list, so it decides alone as the last lane of its round.  lister[i]: bit L = lane L of the batch lists
 // keypoint i (shared memory, n words).
+// LAST = false: the accept rule of SearchByProjection(Frame&, vector<MapPoint*>&) (:117-121, ratio inside one scale level).
+// LAST = true:  SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728, Nleft == -1): the best
+//               unclaimed keypoint within TH_HIGH is taken (:1596-1604), then the 30-bin rotation histogram between the
+//               last frame's keypoint angle (q_angle) and the claimed keypoint's keeps the three dominant bins (:1706-1725).
+template <bool LAST>
 __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                          const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                          const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                          const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
                                                          const float* __restrict__ q_max_err,
                                                          const unsigned long long* __restrict__ keys4, int th_high, float nnratio,
+                                                         const float* __restrict__ q_angle, int check_orientation,
                                                          int32_t* __restrict__ assigned, int32_t* __restrict__ n_matches) {
   extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then lister[n]
   const int lane = threadIdx.x, words = (n + 31) / 32;
@@ -931,7 +937,7 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
           survivors++;
         }
       }
-      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < 2 && idx[3] >= 0);
+      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[3] >= 0);
       if (rescan) {  // the first lane that must look beyond its list ends the round
         const int r = __ffs(rescan) - 1;
         ready &= (2u << r) - 1u;
@@ -946,7 +952,7 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
         // orb_matcher.cc:117-121: accept within TH_HIGH; the ratio to the second match counts only inside one scale level
         const int d0 = (int)(b0 >> 48), l0 = (int)(b0 & 15u), i0 = (int)((b0 >> 4) & 0xFFFFFFu);
         const int d1 = b1 == ~0ull ? 256 : (int)(b1 >> 48), l1 = b1 == ~0ull ? -1 : (int)(b1 & 15u);
-        accept = d0 <= th_high && !(l0 == l1 && (float)d0 > f_mul(nnratio, (float)d1));
+        accept = d0 <= th_high && (LAST || !(l0 == l1 && (float)d0 > f_mul(nnratio, (float)d1)));
         if (accept) {
           assigned[i0] = qi;  // F.mvpMapPoints[bestIdx] = pMP (:121); pMP has observations, so it blocks later map points
           atomicOr(&claim_bits[i0 >> 5], 1u << (i0 & 31));
@@ -961,6 +967,43 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       if (idx[e] >= 0) lister[idx[e]] = 0;
     __syncwarp();
   }
+  if (LAST && check_orientation) {  // rotation consistency (:1612-1624, :1706-1725); lister[0..29] serves as the histogram
+    const float factor = 30 / 360.0f;
+    __syncwarp();
+    if (lane < 30) lister[lane] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const int qi = assigned[i];
+      if (qi < 0) continue;
+      float rot = f_sub(q_angle[qi], kps[i].angle);
+      if (rot < 0.0f) rot = f_add(rot, 360.0f);
+      int bin = (int)roundf(f_mul(rot, factor));
+      if (bin == 30) bin = 0;
+      atomicAdd(&lister[bin < 0 ? 0 : (bin > 29 ? 29 : bin)], 1u);
+    }
+    __syncwarp();
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;  // ComputeThreeMaxima (:1841-1873), every lane alike
+    for (int i = 0; i < 30; i++) {
+      const int sz = (int)lister[i];
+      if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
+      else if (sz > max3) { max3 = sz; ind3 = i; }
+    }
+    if ((float)max2 < f_mul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < f_mul(0.1f, (float)max1)) { ind3 = -1; }
+    int dropped = 0;
+    for (int i = lane; i < n; i += 32) {
+      const int qi = assigned[i];
+      if (qi < 0) continue;
+      float rot = f_sub(q_angle[qi], kps[i].angle);
+      if (rot < 0.0f) rot = f_add(rot, 360.0f);
+      int bin = (int)roundf(f_mul(rot, factor));
+      if (bin == 30) bin = 0;
+      bin = bin < 0 ? 0 : (bin > 29 ? 29 : bin);
+      if (bin != ind1 && bin != ind2 && bin != ind3) { assigned[i] = -1; dropped++; }
+    }
+    nm -= __reduce_add_sync(0xffffffffu, dropped);
+  }
   if (lane == 0) *n_matches = nm;
 }
 
@@ -968,20 +1011,24 @@ size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 4 *
 
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
-                                const float* q_max_err, int th_high, float nnratio, void* scratch, int32_t* assigned,
-                                int32_t* n_matches, cudaStream_t st) {
+                                const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
+                                bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st) {
   unsigned long long* keys4 = static_cast<unsigned long long*>(scratch);
   int launches = 1;
   if (nq > 0) {
     k_window_top4<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4);
     launches++;
   }
-  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem = bits + (size_t)(n + 1) * sizeof(uint32_t);
+  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem = bits + (size_t)(n + 32) * sizeof(uint32_t);
   const char* force_seq = getenv("ORBM_CLAIM_SEQUENTIAL");  // test hook: the one-map-point-at-a-time kernel of very large frames
-  if (smem <= 200 * 1024 && !(force_seq && force_seq[0] == '1')) {  // the batched claim keeps one word per keypoint in shared memory (up to ~50 k keypoints)
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_projection_claim<<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
-                                            nnratio, assigned, n_matches);
+  if (last_frame) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_projection_claim<true><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
+                                                  nnratio, q_angle, check_orientation, assigned, n_matches);
+  } else if (smem <= 200 * 1024 && !(force_seq && force_seq[0] == '1')) {  // one word per keypoint in shared memory (up to ~50 k keypoints)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_projection_claim<false><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
+                                                   nnratio, nullptr, 0, assigned, n_matches);
   } else {
     if (bits > 48 * 1024) cudaFuncSetAttribute(k_projection_claim_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bits);
     k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,

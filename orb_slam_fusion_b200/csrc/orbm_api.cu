@@ -353,7 +353,7 @@ int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n
   return orbm_window_search_stereo(m, kps, desc, n, geom, queries, qdesc, nq, skip, nullptr, nullptr, nullptr, out, mem, stream);
 }
 
-int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+static int search_by_projection(bool last_frame, const float* q_angle, int check_orientation, orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
                               const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
                               float nnratio, int32_t* assigned, int32_t* n_matches, int mem, void* stream) {
@@ -364,11 +364,13 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
       (kp_u_right && nq > 0 && (!q_u_right || !q_max_err)))
     return fail(m, ORBX_E_ARG, "bad argument");
   if ((size_t)((n + 31) / 32 + 1) * 4 > 200 * 1024) return fail(m, ORBX_E_UNSUPPORTED, "more than 1.6 M keypoints in one frame");
+  if (last_frame && (size_t)n * 4 > 180 * 1024) return fail(m, ORBX_E_UNSUPPORTED, "more than 46 k keypoints in one frame");
+  if (last_frame && check_orientation && nq > 0 && !q_angle) return fail(m, ORBX_E_ARG, "orientation check without angles");
   const size_t scratch = pad256(projection_scratch_bytes(nq));
   if (mem == ORBX_MEM_HOST) {
     TRY(arena_reserve(m, pad256((size_t)n * 28) + pad256((size_t)n * 32) + pad256((size_t)nq * sizeof(orbm_window_query)) +
                              pad256((size_t)nq * 32) + pad256((size_t)n) + pad256((size_t)n * 4) + 2 * pad256((size_t)nq * 4) +
-                             pad256((size_t)n * 4) + 256 + scratch));
+                             pad256((size_t)n * 4) + pad256((size_t)nq * 4) + 256 + scratch));
   } else {
     TRY(arena_reserve(m, scratch));  // device-memory calls still need the per-query scratch
   }
@@ -386,14 +388,33 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
     TRY(stage_in(m, mem, q_u_right, (size_t)nq, &dqr, st));
     TRY(stage_in(m, mem, q_max_err, (size_t)nq, &dqe, st));
   }
+  const float* dqa = nullptr;
+  if (q_angle) TRY(stage_in(m, mem, q_angle, (size_t)nq, &dqa, st));
   int32_t* dassigned = stage_out(m, mem, assigned, (size_t)n);
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)1);
   void* dscratch = arena_take<uint8_t>(m, projection_scratch_bytes(nq));
-  m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dscratch,
-                                             dassigned, dnm, st);
+  m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dqa,
+                                             check_orientation, last_frame, dscratch, dassigned, dnm, st);
   TRY(finish_out(m, mem, assigned, dassigned, (size_t)n, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)1, st));
   return end(m, mem, st);
+}
+
+int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                              const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err, int th_high,
+                              float nnratio, int32_t* assigned, int32_t* n_matches, int mem, void* stream) {
+  return search_by_projection(false, nullptr, 0, m, kps, desc, n, geom, queries, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err,
+                              th_high, nnratio, assigned, n_matches, mem, stream);
+}
+
+int orbm_search_by_projection_last(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                                   const orbm_window_query* queries, const uint8_t* qdesc, const float* q_angle, int nq,
+                                   const uint8_t* skip, const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                                   int th_high, int check_orientation, int32_t* assigned, int32_t* n_matches, int mem,
+                                   void* stream) {
+  return search_by_projection(true, q_angle, check_orientation, m, kps, desc, n, geom, queries, qdesc, nq, skip, kp_u_right, q_u_right,
+                              q_max_err, th_high, 0.f, assigned, n_matches, mem, stream);
 }
 
 static int search_by_bow(bool keyframes, orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const int32_t* n_per_frame,

@@ -87,8 +87,8 @@ bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** py
 size_t projection_scratch_bytes(int nq);  // per-query key lists of launch_search_by_projection
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
-                                const float* q_max_err, int th_high, float nnratio, void* scratch, int32_t* assigned,
-                                int32_t* n_matches, cudaStream_t st);
+                                const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
+                                bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st);
 int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                          const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,

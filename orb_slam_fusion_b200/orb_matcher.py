@@ -187,6 +187,30 @@ class ORBmatcher:
             self.nnratio if nnratio is None else float(nnratio), assigned.ctypes.data, C.addressof(nm), A.MEM_HOST, None))
         return nm.value, assigned[:len(kps)].copy()
 
+    def SearchByProjectionLast(self, kps, desc, geom, queries, qdesc, q_angle, skip=None, kp_u_right=None, q_u_right=None,
+                               q_max_err=None, th_high=None, check_orientation=None):
+        """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728, Nleft == -1) after
+        the projection: queries = the windows of the last frame's map points that project into the frame, in order,
+        q_angle their keypoint angles.  Returns (nmatches, assigned[n])."""
+        kps = np.ascontiguousarray(kps, A.KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        queries = np.ascontiguousarray(queries, A.WQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        qa = np.ascontiguousarray(q_angle, np.float32)
+        sk = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        ur = qr = qe = None
+        if kp_u_right is not None:
+            ur, qr, qe = (np.ascontiguousarray(a, np.float32) for a in (kp_u_right, q_u_right, q_max_err))
+        assigned = np.empty(max(len(kps), 1), np.int32)
+        nm = C.c_int32(0)
+        g = A.GridGeom(*geom)
+        self._check(self._lib.orbm_search_by_projection_last(
+            self._m, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(g), queries.ctypes.data, qdesc.ctypes.data, qa.ctypes.data,
+            len(queries), A.ptr(sk), A.ptr(ur), A.ptr(qr), A.ptr(qe), self.TH_HIGH if th_high is None else int(th_high),
+            int(self.check_ori if check_orientation is None else check_orientation), assigned.ctypes.data, C.addressof(nm),
+            A.MEM_HOST, None))
+        return nm.value, assigned[:len(kps)].copy()
+
     # ---- bag-of-words guided matching
     def SearchByBoWKeyFrames(self, kps, desc, n_per_frame, fv, pairs, has_point=None, nnratio=0.7, check_orientation=True):
         """ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (orb_matcher.cc:697-815, loop closing): same pool and

@@ -79,6 +79,18 @@ int main(int argc, char** argv) {
                                                      already, 3.0f, false, 50.f, 0.8f, assigned);
     put(fo, &nproj, 4);
     put(fo, assigned.data(), assigned.size() * sizeof(int));
+    // ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th = 7, bMono) (orb_matcher.cc:1518-1728): the frame against itself
+    // moved by (2, -1) px, neutral motion case, orientation check on
+    std::vector<ORBmatcherGpu::ProjectedPoint> lp(keys.size());
+    for (size_t i = 0; i < keys.size(); i++) {
+      const ORBmatcherGpu::ProjectedPoint t = {keys[i].pt.x + 2.0f, keys[i].pt.y - 1.0f, 0.1f, keys[i].octave, keys[i].angle};
+      lp[i] = t;
+    }
+    std::vector<int> assigned_last;
+    const int32_t nlast = matcher.SearchByProjectionLastFrame(keys, desc, std::vector<float>(), sf, 47.9f, 0.f, 0.f, 64.f / w, 48.f / h, 64, 48,
+                                                              lp, desc, already, 7.0f, false, false, true, assigned_last);
+    put(fo, &nlast, 4);
+    put(fo, assigned_last.data(), assigned_last.size() * sizeof(int));
   }
   if (argc == 9) {
     // Frame::ComputeBoW (frame.cc:761-766): toDescriptorVector + transform(vCurrentDesc, mBowVec, mFeatVec, 4)

@@ -79,6 +79,16 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     geom = (0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h), 64, 48)
     wnm, want = oracle.search_by_projection(rk, rd, geom, q, rd[keep], (np.arange(n) % 7 == 0).astype(np.uint8), None, None, None, 100, 0.8)
     assert nproj == wnm and np.array_equal(assigned, np.where(want >= 0, keep[np.maximum(want, 0)], -1)) and wnm > n // 2
+    # ORBmatcherGpu::SearchByProjectionLastFrame (orb_matcher.cc:1518-1728)
+    nlast = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    assigned_last = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    ql = np.zeros(n, oracle.WQ_DTYPE)
+    ql["u"], ql["v"] = rk["x"] + np.float32(2), rk["y"] - np.float32(1)
+    ql["r"] = np.float32(7.0) * sf[np.clip(rk["octave"], 0, 7)]
+    ql["min_level"], ql["max_level"] = rk["octave"] - 1, rk["octave"] + 1
+    wnm, want = oracle.search_by_projection_last(rk, rd, geom, ql, rd, rk["angle"], (np.arange(n) % 7 == 0).astype(np.uint8), None, None,
+                                                 None, 100, True)
+    assert nlast == wnm and np.array_equal(assigned_last, want) and wnm > n // 2
     # ORBVocabularyGpu::transform as Frame::ComputeBoW calls it
     words, nb, nfv = (int(v) for v in np.frombuffer(buf, np.int32, 3, off)); off += 12
     vo = oracle.Vocabulary(vk, vL, vparent, vleaf, vdesc, vweight)

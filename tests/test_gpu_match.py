@@ -413,3 +413,30 @@ def test_search_by_bow_random_feature_vectors_and_errors(P, m, oracle):
                       {"fv_nodes": np.zeros((1, big), np.uint32), "fv_begin": np.zeros((1, big), np.int32),
                        "fv_feats": np.zeros((1, big), np.uint32), "fv_n": np.zeros(1, np.int32), "fv_total": np.zeros(1, np.int32)},
                       np.array([[0, 0]], np.int32))
+
+
+@pytest.mark.parametrize("seed,th,t_lw_z,mono,stereo,ori", [(1, 7.0, 0.0, False, True, True), (2, 15.0, 0.5, False, True, True),
+                                                            (3, 15.0, -0.6, False, False, True), (4, 7.0, 0.5, True, False, False)])
+def test_search_by_projection_last_frame(P, m, oracle, seed, th, t_lw_z, mono, stereo, ori):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728; TrackWithMotionModel)
+    after the projection: windows + greedy claim + rotation histogram on the device vs the oracle and the reference's lines."""
+    from oracle import ref as R
+    from test_oracle_vs_ref_frame import last_frame_case, last_frame_windows, W, H, BF_LAST, MB_LAST, CAM4
+    kps, desc, last, ldesc, has_point, outlier, world, t_cw, src, rng = last_frame_case(oracle, seed, n_last=900)
+    bounds = (0.0, float(W), 0.0, float(H))
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    sf = oracle.Extractor(1000).tables()["scale"]
+    t_lw = np.array([0.0, 0.0, t_lw_z], np.float32)
+    pre = (rng.random(len(kps)) < 0.15).astype(np.uint8)
+    u_right = np.where(rng.random(len(kps)) < 0.6, kps["x"] - rng.uniform(2, 40, len(kps)), -1.0).astype(np.float32) if stereo else None
+    keep, q, qur = last_frame_windows(oracle, sf, last, has_point, outlier, world, t_cw, t_lw, th, mono, bounds)
+    args = (kps, desc, geom, q, ldesc[keep], last["angle"][keep], pre, u_right, qur if stereo else None, q["r"] if stereo else None, 100, ori)
+    nm, got = m.SearchByProjectionLast(*args)
+    wnm, want = oracle.search_by_projection_last(*args)
+    assert nm == wnm and np.array_equal(got, want) and wnm > 150
+    if R.frame_available():
+        rnm, rwant = R.search_by_projection_last(kps, desc, bounds, sf, BF_LAST, MB_LAST, CAM4, t_cw, t_lw, last, has_point, outlier,
+                                                 world, ldesc, pre, u_right, th, mono, ori)
+        assert nm == rnm and np.array_equal(np.where(got >= 0, keep[np.maximum(got, 0)], -1), rwant)
+    nm0, got0 = m.SearchByProjectionLast(kps, desc, geom, q[:0], ldesc[:0], last["angle"][:0], pre)
+    assert nm0 == 0 and (got0 == -1).all()

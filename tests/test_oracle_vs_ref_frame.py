@@ -205,3 +205,82 @@ def test_search_by_bow_keyframes_identical(oracle, seed, shift, ratio, ori, leve
     want_nm2, want2 = R.search_by_bow_kf(ka, da, None, fva, ka, da, None, fva, ratio, ori)
     nm2, got2 = oracle.search_by_bow_kf(ka, da, None, fva, ka, da, None, fva, ratio, ori)
     assert nm2 == want_nm2 and np.array_equal(got2, want2) and nm2 > 100
+
+
+CAM4 = np.array([458.654, 457.296, 367.215, 248.375], np.float32)          # settings/EuRoC.yaml Camera1 fx fy cx cy
+BF_LAST, MB_LAST = np.float32(47.90639384423901), np.float32(0.11)
+
+
+def last_frame_case(oracle, seed, n_last=700):
+    """A current frame and a `last frame` whose map points project near the current keypoints (translation-only poses)."""
+    img = oracle.blocks_v1(W, H, seed, 0)
+    _, kps, desc = oracle.Extractor(1000)(img)
+    rng = np.random.default_rng(seed + 50)
+    src = rng.integers(0, len(kps), n_last)
+    t_cw = np.array([0.10, -0.05, 0.20], np.float32)
+    z = rng.uniform(2.0, 30.0, n_last).astype(np.float32)
+    u = (kps["x"][src] + rng.normal(0, 3, n_last)).astype(np.float32)
+    v = (kps["y"][src] + rng.normal(0, 3, n_last)).astype(np.float32)
+    xc = ((u - CAM4[2]) * z / CAM4[0]).astype(np.float32)
+    yc = ((v - CAM4[3]) * z / CAM4[1]).astype(np.float32)
+    world = np.stack([xc - t_cw[0], yc - t_cw[1], z - t_cw[2]], 1).astype(np.float32)
+    world[:15, 2] = -5.0                                                       # behind the camera
+    world[15:30, 0] += 500.0                                                   # projects outside the image
+    last = np.zeros(n_last, oracle.KP_DTYPE)
+    last["octave"] = np.clip(kps["octave"][src] + rng.integers(-1, 2, n_last), 0, 7)
+    last["angle"] = np.where(rng.random(n_last) < 0.8, kps["angle"][src] + rng.normal(0, 4, n_last), rng.uniform(0, 360, n_last)) % 360
+    last["angle"] = last["angle"].astype(np.float32)
+    ldesc = desc[src].copy()
+    flips = rng.integers(0, 256, (n_last, 14))
+    for j in range(14):
+        ldesc[np.arange(n_last), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+    has_point = (rng.random(n_last) < 0.85).astype(np.uint8)
+    outlier = (rng.random(n_last) < 0.05).astype(np.uint8)
+    return kps, desc, last, ldesc, has_point, outlier, world, t_cw, src, rng
+
+
+def last_frame_windows(oracle, sf, last, has_point, outlier, world, t_cw, t_lw, th, mono, bounds):
+    """orb_matcher.cc:1529-1576 and :1587 in float32, the host side of the call: (kept last-frame indices, windows, u_right, angles)."""
+    twc = -t_cw
+    tlc_z = np.float32(twc[2] + t_lw[2])
+    forward, backward = bool(tlc_z > MB_LAST and not mono), bool(-tlc_z > MB_LAST and not mono)
+    keep, q, qur = [], [], []
+    for i in range(len(last)):
+        if not has_point[i] or outlier[i]:
+            continue
+        xc, yc, zc = (np.float32(world[i, k] + t_cw[k]) for k in range(3))
+        invzc = np.float32(1.0 / np.float64(zc))
+        if invzc < 0:
+            continue
+        u = np.float32(np.float32(np.float32(CAM4[0] * xc) / zc) + CAM4[2])
+        v = np.float32(np.float32(np.float32(CAM4[1] * yc) / zc) + CAM4[3])
+        if u < bounds[0] or u > bounds[1] or v < bounds[2] or v > bounds[3]:
+            continue
+        o = int(last["octave"][i])
+        radius = np.float32(np.float32(th) * sf[o])
+        lo, hi = (o, -1) if forward else ((0, o) if backward else (o - 1, o + 1))
+        keep.append(i)
+        q.append((u, v, radius, lo, hi))
+        qur.append(np.float32(u - np.float32(BF_LAST * invzc)))
+    return np.array(keep, np.int64), np.array(q, oracle.WQ_DTYPE), np.array(qur, np.float32)
+
+
+@pytest.mark.parametrize("seed,th,t_lw_z,mono,stereo,ori", [(1, 7.0, 0.0, False, True, True), (2, 15.0, 0.5, False, True, True),
+                                                            (3, 15.0, -0.6, False, False, True), (4, 7.0, 0.5, True, False, False)])
+def test_search_by_projection_last_frame_identical(oracle, seed, th, t_lw_z, mono, stereo, ori):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728): forward / backward / neutral level
+    windows, stereo gate, greedy claim, rotation histogram."""
+    kps, desc, last, ldesc, has_point, outlier, world, t_cw, src, rng = last_frame_case(oracle, seed)
+    bounds = (0.0, float(W), 0.0, float(H))
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    sf = oracle.Extractor(1000).tables()["scale"]
+    t_lw = np.array([0.0, 0.0, t_lw_z], np.float32)
+    pre = (rng.random(len(kps)) < 0.15).astype(np.uint8)
+    u_right = np.where(rng.random(len(kps)) < 0.6, kps["x"] - rng.uniform(2, 40, len(kps)), -1.0).astype(np.float32) if stereo else None
+    want_nm, want = R.search_by_projection_last(kps, desc, bounds, sf, BF_LAST, MB_LAST, CAM4, t_cw, t_lw, last, has_point, outlier,
+                                                world, ldesc, pre, u_right, th, mono, ori)
+    keep, q, qur = last_frame_windows(oracle, sf, last, has_point, outlier, world, t_cw, t_lw, th, mono, bounds)
+    nm, got = oracle.search_by_projection_last(kps, desc, geom, q, ldesc[keep], last["angle"][keep], pre, u_right,
+                                               qur if stereo else None, q["r"] if stereo else None, 100, ori)
+    assert nm == want_nm and np.array_equal(np.where(got >= 0, keep[np.maximum(got, 0)], -1), want)
+    assert want_nm > 100
