@@ -283,7 +283,11 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
  * stereo gate (:1586-1590).  Each query takes the nearest keypoint that holds no map point with observations (`skip`
  * at the start, then the claims of earlier queries; strict <, first wins) if its distance is <= th_high (TH_HIGH);
  * with check_orientation the matches outside the three dominant bins of the 30-bin rotation histogram are dropped
- * (:1706-1725).  assigned[i] = query stored in CurrentFrame.mvpMapPoints[i] (-1: untouched), *n_matches = return value. */
+ * (:1706-1725).  assigned[i] = query stored in CurrentFrame.mvpMapPoints[i] (-1: untouched), *n_matches = return value.
+ * The relocalisation form SearchByProjection(CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (:1730-1840,
+ * tracking.cc:2978, 2992) is the same search after ITS projection: windows (u, v, th * scale[nPredictedLevel],
+ * nPredictedLevel - 1 .. nPredictedLevel + 1) of pKF's map points that pass :1751-1771, q_angle = pKF->mvKeysUn[i].angle,
+ * skip[i] = CurrentFrame.mvpMapPoints[i] != NULL (:1791), no stereo gate (kp_u_right = NULL), th_high = ORBdist. */
 int orbm_search_by_projection_last(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
                                    const orbm_window_query* queries, const uint8_t* qdesc, const float* q_angle, int nq,
                                    const uint8_t* skip, const float* kp_u_right, const float* q_u_right, const float* q_max_err,
