@@ -287,7 +287,12 @@ int orbm_search_by_projection(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
  * The relocalisation form SearchByProjection(CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (:1730-1840,
  * tracking.cc:2978, 2992) is the same search after ITS projection: windows (u, v, th * scale[nPredictedLevel],
  * nPredictedLevel - 1 .. nPredictedLevel + 1) of pKF's map points that pass :1751-1771, q_angle = pKF->mvKeysUn[i].angle,
- * skip[i] = CurrentFrame.mvpMapPoints[i] != NULL (:1791), no stereo gate (kp_u_right = NULL), th_high = ORBdist. */
+ * skip[i] = CurrentFrame.mvpMapPoints[i] != NULL (:1791), no stereo gate (kp_u_right = NULL), th_high = ORBdist.
+ * The loop-closing forms SearchByProjection(KeyFrame* pKF, Sim3 Scw, vpPoints, [vpPointsKFs,] vpMatched, [vpMatchedKF,] th,
+ * ratioHamming) (:391-488, :490-596; loopclosing.cc:671, 702, 877) map onto it as well, without the orientation check:
+ * windows (u, v, th * scale[nPredictedLevel], nPredictedLevel - 1 .. nPredictedLevel) over pKF's keypoints
+ * (KeyFrame::GetFeaturesInArea, keyframe.cc:729-773, visits the same grid in the same order), skip[i] = vpMatched[i] != NULL
+ * (:461), th_high = TH_LOW * ratioHamming (:483), check_orientation = 0. */
 int orbm_search_by_projection_last(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
                                    const orbm_window_query* queries, const uint8_t* qdesc, const float* q_angle, int nq,
                                    const uint8_t* skip, const float* kp_u_right, const float* q_u_right, const float* q_max_err,
