@@ -329,6 +329,26 @@ int orbm_search_by_bow_kf(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, in
                           int n_pairs, float nnratio, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
                           void* stream);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (orb_matcher.cc:817-1040; caller
+ * LocalMapping::CreateNewMapPoints, localmapping.cc:382) for key frames with one pinhole camera (cam2_ == NULL, NLeft == -1),
+ * over the pool / pair layout of orbm_search_by_bow.  has_point[f*cap + i] != 0: the feature holds a map point -- such
+ * features take no part on either side (:883-886, :911; required); u_right[f*cap + i] = KeyFrame::mvuRight (>= 0: stereo
+ * observation).  Per pair: pair_f12[p*9 ..] = the fundamental matrix F12 of Pinhole::EpipolarConstrain (pinhole_model.cc:
+ * 116-119: K1^-T [t12]x R12 K2^-1, a product of Eigen matrices the host keeps), row-major; pair_ep[p*2 ..] = the epipole
+ * pKF2->cam_->Project(T2w * Cw) (:829-830).  scale_factors / level_sigma2 [n_levels] = mvScaleFactors / mvLevelSigma2.
+ * A feature of key frame 1 takes the nearest (of equally near: the last) unclaimed feature of key frame 2 in its
+ * vocabulary node with distance <= TH_LOW that lies >= 10 * sqrt(scale) px from the epipole (only if neither side is a
+ * stereo observation, :932-939) and passes the epipolar line test (:121-134; skipped when `coarse`); then the rotation
+ * histogram (check_orientation).  match[p*cap + i] = feature of key frame 2 matched to feature i of key frame 1 (the pairs
+ * of vMatchedPairs; -1: none), n_matches[p] = the return value.  cap <= 2048. */
+int orbm_search_for_triangulation(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames,
+                                  const int32_t* n_per_frame, const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n,
+                                  const uint32_t* fv_feats, const int32_t* fv_total, const uint8_t* has_point, const float* u_right,
+                                  const int32_t* pair_1, const int32_t* pair_2, int n_pairs, const float* pair_f12,
+                                  const float* pair_ep, const float* scale_factors, const float* level_sigma2, int n_levels,
+                                  int only_stereo, int coarse, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                                  void* stream);
+
 /* Deterministic synthetic descriptors: 64-bit word j of row i is
  * splitmix64(seed ^ (4*(first+i)+j)).  `dst` is device memory. */
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream);

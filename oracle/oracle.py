@@ -79,6 +79,8 @@ def lib():
         L.orc_search_by_projection_last.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, vp, i, vp, vp, vp, vp, i, i, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
         L.orc_search_by_bow_kf.argtypes = [vp, vp, vp, i, vp, vp, i, vp, i, vp, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
+        L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, i, vp, i, vp, vp, vp, vp, i, vp, vp, i, vp, i,
+                                                   vp, vp, vp, vp, i, i, i, vp]
         L.orc_splitmix64.restype = u64
         L.orc_splitmix64.argtypes = [u64]
         L.orc_synth_blocks_v1.argtypes = [vp, i, i, sz, u64, u64, i, u64]
@@ -449,6 +451,25 @@ def search_by_bow_kf(kps1, desc1, has_point1, fv1, kps2, desc2, has_point2, fv2,
     nm = lib().orc_search_by_bow_kf(_p(kps1), _p(desc1), None if hp1 is None else _p(hp1), len(kps1), _p(n1), _p(b1), len(n1), _p(f1p),
                                     len(f1), _p(kps2), _p(desc2), None if hp2 is None else _p(hp2), len(kps2), _p(n2), _p(b2), len(n2),
                                     _p(f2p), len(f2), float(nnratio), int(check_orientation), _p(out))
+    return nm, out[:len(kps1)].copy()
+
+
+def search_for_triangulation(kps1, desc1, has_point1, u_right1, fv1, kps2, desc2, has_point2, u_right2, fv2, f12, ep,
+                             scale_factors, level_sigma2, only_stereo=False, coarse=False, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040), one pinhole camera per key frame: (nmatches, match_of_1[n1])."""
+    kps1, kps2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    hp1, hp2 = np.ascontiguousarray(has_point1, np.uint8), np.ascontiguousarray(has_point2, np.uint8)
+    ur1, ur2 = np.ascontiguousarray(u_right1, np.float32), np.ascontiguousarray(u_right2, np.float32)
+    f12, ep = np.ascontiguousarray(f12, np.float32).reshape(9), np.ascontiguousarray(ep, np.float32)
+    sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+    (n1, b1, f1), (n2, b2, f2) = fv1, fv2
+    f1p = f1 if len(f1) else np.zeros(1, np.uint32)
+    f2p = f2 if len(f2) else np.zeros(1, np.uint32)
+    out = np.empty(max(len(kps1), 1), np.int32)
+    nm = lib().orc_search_for_triangulation(_p(kps1), _p(desc1), _p(hp1), _p(ur1), len(kps1), _p(n1), _p(b1), len(n1), _p(f1p), len(f1),
+                                            _p(kps2), _p(desc2), _p(hp2), _p(ur2), len(kps2), _p(n2), _p(b2), len(n2), _p(f2p), len(f2),
+                                            _p(f12), _p(ep), _p(sf), _p(s2), int(only_stereo), int(coarse), int(check_orientation), _p(out))
     return nm, out[:len(kps1)].copy()
 
 

@@ -982,6 +982,93 @@ int orc_search_by_projection_last(const orc_kp* kps, const uint8_t* desc, int n,
   return nmatches;
 }
 
+/* ---- ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse), orb_matcher.cc:817-1040, for
+ * key frames without a second camera (cam2_ == NULL, NLeft == -1) and pinhole cameras: per shared vocabulary node every
+ * feature of key frame 1 WITHOUT a map point takes the nearest (ties: the LAST) feature of key frame 2 in the node that has
+ * no map point, is not claimed yet, is within TH_LOW, lies away from the epipole (:917-924, monocular pairs only) and on
+ * the epipolar line (Pinhole::EpipolarConstrain, pinhole_model.cc:121-134, with F12 given); then the rotation histogram.
+ * match_of_1[i] = feature of key frame 2 (vMatches12) or -1; returns nmatches. */
+int orc_search_for_triangulation(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_point1, const float* u_right1, int n1,
+                                 const uint32_t* nodes1, const int* begin1, int n_nodes1, const uint32_t* feats1, int total1,
+                                 const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_point2, const float* u_right2, int n2,
+                                 const uint32_t* nodes2, const int* begin2, int n_nodes2, const uint32_t* feats2, int total2,
+                                 const float* f12 /* row-major 3x3 */, const float* ep, const float* scale_factors,
+                                 const float* level_sigma2, int only_stereo, int coarse, int check_orientation, int* match_of_1) {
+  enum { HISTO_LENGTH = 30, TH_LOW = 50 };
+  int nmatches = 0;
+  int hist[HISTO_LENGTH] = {0};
+  int* bin_of = (int*)malloc(sizeof(int) * (size_t)(n1 ? n1 : 1));
+  uint8_t* matched2 = (uint8_t*)calloc((size_t)(n2 ? n2 : 1), 1);
+  const float factor = HISTO_LENGTH / 360.0f; /* :868 */
+  for (int i = 0; i < n1; i++) { match_of_1[i] = -1; bin_of[i] = -1; }
+  int a = 0, b = 0;
+  while (a < n_nodes1 && b < n_nodes2) { /* :875-1008 */
+    if (nodes1[a] == nodes2[b]) {
+      const int k0 = begin1[a], k1 = a + 1 < n_nodes1 ? begin1[a + 1] : total1;
+      const int f0 = begin2[b], f1 = b + 1 < n_nodes2 ? begin2[b + 1] : total2;
+      for (int i1 = k0; i1 < k1; i1++) {
+        const int idx1 = (int)feats1[i1];
+        if (has_point1[idx1]) continue;                       /* :883-886 */
+        const int stereo1 = u_right1[idx1] >= 0;              /* :888 */
+        if (only_stereo && !stereo1) continue;
+        int best_dist = TH_LOW, best_idx2 = -1;
+        for (int i2 = f0; i2 < f1; i2++) {
+          const int idx2 = (int)feats2[i2];
+          if (matched2[idx2] || has_point2[idx2]) continue;   /* :911 */
+          const int stereo2 = u_right2[idx2] >= 0;
+          if (only_stereo && !stereo2) continue;
+          const int dist = orc_hamming(desc1 + 32 * (size_t)idx1, desc2 + 32 * (size_t)idx2);
+          if (dist > TH_LOW || dist > best_dist) continue;    /* :922 */
+          if (!stereo1 && !stereo2) {                         /* :932-939 */
+            const float distex = ep[0] - kps2[idx2].x, distey = ep[1] - kps2[idx2].y;
+            if (distex * distex + distey * distey < 100 * scale_factors[kps2[idx2].octave]) continue;
+          }
+          int ok = coarse;
+          if (!ok) { /* pinhole_model.cc:121-134 */
+            const float x1 = kps1[idx1].x, y1 = kps1[idx1].y, unc = level_sigma2[kps2[idx2].octave];
+            const float la = x1 * f12[0] + y1 * f12[3] + f12[6];
+            const float lb = x1 * f12[1] + y1 * f12[4] + f12[7];
+            const float lc = x1 * f12[2] + y1 * f12[5] + f12[8];
+            const float num = la * kps2[idx2].x + lb * kps2[idx2].y + lc;
+            const float den = la * la + lb * lb;
+            if (den != 0) {
+              const float dsqr = num * num / den;
+              ok = dsqr < 3.84 * unc;
+            }
+          }
+          if (ok) { best_idx2 = idx2; best_dist = dist; }     /* :977-984 */
+        }
+        if (best_idx2 >= 0) {                                 /* :987-1006 */
+          match_of_1[idx1] = best_idx2;
+          matched2[best_idx2] = 1;
+          nmatches++;
+          if (check_orientation) {
+            float rot = kps1[idx1].angle - kps2[best_idx2].angle;
+            if (rot < 0.0) rot += 360.0f;
+            int bin = (int)roundf(rot * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            bin_of[idx1] = bin;
+            hist[bin]++;
+          }
+        }
+      }
+      a++; b++;
+    } else if (nodes1[a] < nodes2[b]) {
+      while (a < n_nodes1 && nodes1[a] < nodes2[b]) a++;
+    } else {
+      while (b < n_nodes2 && nodes2[b] < nodes1[a]) b++;
+    }
+  }
+  if (check_orientation) { /* :1010-1027 */
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(hist, HISTO_LENGTH, &ind1, &ind2, &ind3);
+    for (int i = 0; i < n1; i++)
+      if (match_of_1[i] >= 0 && bin_of[i] != ind1 && bin_of[i] != ind2 && bin_of[i] != ind3) { match_of_1[i] = -1; nmatches--; }
+  }
+  free(bin_of); free(matched2);
+  return nmatches;
+}
+
 /* ---- synthetic inputs, SURVEY.md 8(d) ---- */
 uint64_t orc_splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;

@@ -193,6 +193,17 @@ int orc_search_by_bow_kf(const orc_kp* kps1, const uint8_t* desc1, const uint8_t
                          const uint32_t* nodes2, const int* begin2, int n_nodes2, const uint32_t* feats2, int total2,
                          float nnratio, int check_orientation, int* match_of_1);
 
+/* ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040; LocalMapping::CreateNewMapPoints) for key frames with one
+ * pinhole camera: bag-of-words guided nearest match between features WITHOUT map points, epipole and epipolar gates
+ * (F12 row-major, ep = epipole in image 2), greedy claim, rotation histogram.  match_of_1[i] = feature of key frame 2 or
+ * -1; returns nmatches.  Pinned on orb_matcher.cc:817-1040 + pinhole_model.cc:121-134 spliced into oracle/ref_frame_shim.cc. */
+int orc_search_for_triangulation(const orc_kp* kps1, const uint8_t* desc1, const uint8_t* has_point1, const float* u_right1, int n1,
+                                 const uint32_t* nodes1, const int* begin1, int n_nodes1, const uint32_t* feats1, int total1,
+                                 const orc_kp* kps2, const uint8_t* desc2, const uint8_t* has_point2, const float* u_right2, int n2,
+                                 const uint32_t* nodes2, const int* begin2, int n_nodes2, const uint32_t* feats2, int total2,
+                                 const float* f12, const float* ep, const float* scale_factors, const float* level_sigma2,
+                                 int only_stereo, int coarse, int check_orientation, int* match_of_1);
+
 /* ---- deterministic synthetic inputs ---- */
 uint64_t orc_splitmix64(uint64_t x);
 void orc_synth_blocks_v1(uint8_t* img, int w, int h, size_t stride, uint64_t seed, uint64_t frame,

@@ -325,3 +325,29 @@ def search_by_projection_last(keys_un, desc, bounds, scale_factors, bf, mb, cam4
                                           _p(t_lw), _p(last_keys), len(last_keys), _p(hp), _p(ol), _p(world), _p(last_desc),
                                           None if pm is None else _p(pm), float(th), int(mono), int(check_orientation), _p(assigned))
     return nm, assigned[:len(keys_un)].copy()
+
+
+def search_for_triangulation(kps1, desc1, has_point1, u_right1, fv1, kps2, desc2, has_point2, u_right2, fv2, f12, cam4, c2,
+                             scale_factors, level_sigma2, only_stereo=False, coarse=False, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040) with Pinhole::EpipolarConstrain's own line test
+    (pinhole_model.cc:121-134) on a given F12; c2 = T2w * Cw fixes the epipole.  Returns (nmatches, match_of_1[n1], epipole)."""
+    L = _frame()
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.reff_search_for_triangulation.argtypes = [vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, vp, i, vp, i,
+                                                vp, vp, vp, vp, vp, i, f, i, i, i, vp, vp]
+    kps1, kps2 = np.ascontiguousarray(kps1, KP_DTYPE), np.ascontiguousarray(kps2, KP_DTYPE)
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    hp1, hp2 = np.ascontiguousarray(has_point1, np.uint8), np.ascontiguousarray(has_point2, np.uint8)
+    ur1, ur2 = np.ascontiguousarray(u_right1, np.float32), np.ascontiguousarray(u_right2, np.float32)
+    f12, cam4, c2 = (np.ascontiguousarray(a, np.float32).ravel() for a in (f12, cam4, c2))
+    sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+    (n1, b1, f1), (n2, b2, f2) = fv1, fv2
+    f1p = f1 if len(f1) else np.zeros(1, np.uint32)
+    f2p = f2 if len(f2) else np.zeros(1, np.uint32)
+    out = np.empty(max(len(kps1), 1), np.int32)
+    ep = np.zeros(2, np.float32)
+    nm = L.reff_search_for_triangulation(_p(kps1), _p(desc1), len(kps1), _p(hp1), _p(ur1), _p(n1), _p(b1), len(n1), _p(f1p), len(f1),
+                                         _p(kps2), _p(desc2), len(kps2), _p(hp2), _p(ur2), _p(n2), _p(b2), len(n2), _p(f2p), len(f2),
+                                         _p(f12), _p(cam4), _p(c2), _p(sf), _p(s2), len(sf), 0.6, int(only_stereo), int(coarse),
+                                         int(check_orientation), _p(ep), _p(out))
+    return nm, out[:len(kps1)].copy(), ep

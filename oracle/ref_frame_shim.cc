@@ -15,6 +15,8 @@
 //   _ref/matcher_bow.inc         orb_matcher.cc:215-389  ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vpMapPointMatches)
 //   _ref/matcher_bow_kf.inc      orb_matcher.cc:697-815  ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12)
 //   _ref/matcher_project_last.inc orb_matcher.cc:1518-1728 ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
+//   _ref/matcher_triangulation.inc orb_matcher.cc:817-1040 ORBmatcher::SearchForTriangulation
+//   _ref/pinhole_epipolar.inc    pinhole_model.cc:121-134  the epipolar-line test of Pinhole::EpipolarConstrain (F12 given)
 //   _ref/matcher_maxima.inc      orb_matcher.cc:1841-1873 ORBmatcher::ComputeThreeMaxima
 //   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
 // Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
@@ -52,9 +54,18 @@ struct Vector2f {
   float operator()(int i) const { return v[i]; }
 };
 }  // namespace Eigen
+namespace Eigen {
+struct Matrix3f {
+  float m[9];  // row-major
+  Matrix3f() : m{1, 0, 0, 0, 1, 0, 0, 0, 1} {}
+  float operator()(int r, int c) const { return m[3 * r + c]; }
+};
+}  // namespace Eigen
 namespace Sophus {
 struct SE3f {
   Eigen::Vector3f t;
+  SE3f operator*(const SE3f &o) const { SE3f r; r.t = Eigen::Vector3f(t(0) + o.t(0), t(1) + o.t(1), t(2) + o.t(2)); return r; }
+  Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
   SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t(0), -t(1), -t(2)); return r; }
   Eigen::Vector3f translation() const { return t; }
   Eigen::Vector3f operator*(const Eigen::Vector3f &p) const { return Eigen::Vector3f(p(0) + t(0), p(1) + t(1), p(2) + t(2)); }
@@ -69,9 +80,17 @@ namespace ORB_SLAM_FUSION {
 
 class MapPoint;
 class KeyFrame;
-struct GeometricCamera {  // a pinhole camera (camera_models/pinhole.cc: fx * x / z + cx)
+struct GeometricCamera {  // a pinhole camera (camera_models/pinhole_model.cc: fx * x / z + cx)
   float fx = 1, fy = 1, cx = 0, cy = 0;
   Eigen::Vector2f Project(const Eigen::Vector3f &p) { return Eigen::Vector2f(fx * p(0) / p(2) + cx, fy * p(1) / p(2) + cy); }
+  // Pinhole::EpipolarConstrain (pinhole_model.cc:109-135): the fundamental matrix of :116-119 is a product of Eigen
+  // matrices (K1^-T [t12]x R12 K2^-1); the harness supplies it, the line test below is the reference's own :121-134.
+  Eigen::Matrix3f F12_given;
+  bool EpipolarConstrain(GeometricCamera *cam_2, const cv::KeyPoint &kp_1, const cv::KeyPoint &kp_2, const Eigen::Matrix3f &R12_eig,
+                         const Eigen::Vector3f &t12_eig, const float sigma_lev, const float unc) {
+    const Eigen::Matrix3f &F12 = F12_given;
+#include "pinhole_epipolar.inc"
+  }
 };
 
 // the one member of OrbExtractor that frame.cc:834,913-933 reads
@@ -86,6 +105,8 @@ class ORBmatcher {
   int SearchByProjection(class Frame &F, const std::vector<MapPoint *> &vpMapPoints, const float th = 3,
                          const bool bFarPoints = false, const float thFarPoints = 50.0f);
   int SearchByProjection(class Frame &CurrentFrame, const class Frame &LastFrame, const float th, const bool bMono);
+  int SearchForTriangulation(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<std::pair<size_t, size_t> > &vMatchedPairs,
+                             const bool bOnlyStereo, const bool bCoarse = false);
   int SearchByBoW(KeyFrame *pKF, class Frame &F, std::vector<MapPoint *> &vpMapPointMatches);
   int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12);
   static const int TH_LOW;
@@ -139,8 +160,17 @@ class KeyFrame {  // include/map/keyframe.h: what mappoint.cc:365-433 and orb_ma
   std::vector<MapPoint *> mvpMapPoints;
   DBoW2::FeatureVector mFeatVec;
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn, mvKeysRight;
-  int NLeft = -1;
+  int NLeft = -1, N = 0;
   GeometricCamera *cam_ = nullptr, *cam2_ = nullptr;
+  // orb_matcher.cc:817-1040
+  MapPoint *GetMapPoint(const size_t &idx) { return mvpMapPoints[idx]; }
+  std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+  Sophus::SE3f pose;  // Tcw, translation only
+  Sophus::SE3f GetPose() { return pose; }
+  Sophus::SE3f GetPoseInverse() { return pose.inverse(); }
+  Sophus::SE3f GetRightPose() { return pose; }
+  Sophus::SE3f GetRightPoseInverse() { return pose.inverse(); }
+  Eigen::Vector3f GetCameraCenter() { return pose.inverse().translation(); }
 };
 
 class MapPoint {  // include/map/mappoint.h
@@ -174,6 +204,7 @@ class MapPoint {  // include/map/mappoint.h
 #include "matcher_project_last.inc"
 #include "matcher_bow.inc"
 #include "matcher_bow_kf.inc"
+#include "matcher_triangulation.inc"
 #include "matcher_maxima.inc"
 
 }  // namespace ORB_SLAM_FUSION
@@ -403,6 +434,41 @@ int reff_search_by_projection_last(const void *keys_un, const uint8_t *desc, int
     MapPoint *p = F.mvpMapPoints[i];
     assigned[i] = (p && p != &occupied) ? (int)(p - mps.data()) : -1;
   }
+  return nm;
+}
+
+// ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse): two key frames with one pinhole
+// camera each (fill_kf + mvuRight, scale factors, level sigma^2); F12 (row-major) is handed to the camera stand-in, the
+// poses are translations chosen so that the epipole cam_->Project(T2w * Cw) is (ep_x, ep_y) = cam(c2).
+int reff_search_for_triangulation(const void *kps1, const uint8_t *desc1, int n1, const uint8_t *has_point1, const float *u_right1,
+                                  const uint32_t *nodes1, const int *begin1, int n_nodes1, const uint32_t *feats1, int total1,
+                                  const void *kps2, const uint8_t *desc2, int n2, const uint8_t *has_point2, const float *u_right2,
+                                  const uint32_t *nodes2, const int *begin2, int n_nodes2, const uint32_t *feats2, int total2,
+                                  const float *f12, const float *cam4, const float *c2 /* T2w * Cw */, const float *scale,
+                                  const float *sigma2, int n_levels, float nnratio, int only_stereo, int coarse,
+                                  int check_orientation, float *ep_out, int *match_of_1) {
+  KeyFrame k1, k2;
+  std::vector<MapPoint> m1(n1 > 0 ? n1 : 1), m2(n2 > 0 ? n2 : 1);
+  fill_kf(k1, m1, kps1, desc1, n1, has_point1, nodes1, begin1, n_nodes1, feats1, total1);
+  fill_kf(k2, m2, kps2, desc2, n2, has_point2, nodes2, begin2, n_nodes2, feats2, total2);
+  GeometricCamera cam1, cam2;
+  cam1.fx = cam2.fx = cam4[0]; cam1.fy = cam2.fy = cam4[1]; cam1.cx = cam2.cx = cam4[2]; cam1.cy = cam2.cy = cam4[3];
+  for (int i = 0; i < 9; i++) cam1.F12_given.m[i] = f12[i];
+  k1.cam_ = &cam1; k2.cam_ = &cam2;
+  k1.N = n1; k2.N = n2;
+  k1.mvuRight.assign(u_right1, u_right1 + n1);
+  k2.mvuRight.assign(u_right2, u_right2 + n2);
+  k1.mvScaleFactors.assign(scale, scale + n_levels); k2.mvScaleFactors = k1.mvScaleFactors;
+  k1.mvLevelSigma2.assign(sigma2, sigma2 + n_levels); k2.mvLevelSigma2 = k1.mvLevelSigma2;
+  // Cw = -t1 with t1 = 0, so Cw = 0 and C2 = T2w * Cw = t2 = c2
+  k2.pose.t = Eigen::Vector3f(c2[0], c2[1], c2[2]);
+  const Eigen::Vector2f ep = cam2.Project(k2.pose * k1.GetCameraCenter());
+  ep_out[0] = ep(0); ep_out[1] = ep(1);
+  std::vector<std::pair<size_t, size_t> > pairs;
+  ORBmatcher matcher(nnratio, check_orientation != 0);
+  const int nm = matcher.SearchForTriangulation(&k1, &k2, pairs, only_stereo != 0, coarse != 0);
+  for (int i = 0; i < n1; i++) match_of_1[i] = -1;
+  for (size_t j = 0; j < pairs.size(); j++) match_of_1[pairs[j].first] = (int)pairs[j].second;
   return nm;
 }
 

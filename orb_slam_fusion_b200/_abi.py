@@ -78,6 +78,8 @@ SIGNATURES = {
     "orbm_search_by_projection_last": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp]),
     "orbm_search_by_bow": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32, vp]),
     "orbm_search_by_bow_kf": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32, vp]),
+    "orbm_search_for_triangulation": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, i32,
+                                            vp, vp, i32, vp]),
     "orbm_window_search": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, i32, vp]),
     "orbm_window_search_stereo": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, vp, vp, vp, i32, vp]),
     "orbm_synth_descriptors": (i32, [i32, vp, i64, i64, u64, vp]),

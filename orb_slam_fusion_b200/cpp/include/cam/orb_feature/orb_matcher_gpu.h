@@ -12,6 +12,7 @@
 
 #include <cstdint>
 #include <map>
+#include <utility>
 #include <opencv2/opencv.hpp>
 #include <vector>
 
@@ -101,6 +102,18 @@ class ORBmatcherGpu {
                   const cv::Mat& desc2, const std::vector<uint8_t>& has_point2,
                   const std::map<unsigned int, std::vector<unsigned int> >& featvec2, float nnratio, bool check_orientation,
                   std::vector<int>& match_of_1);
+
+  // ORBmatcher::SearchForTriangulation(pKF1, pKF2, vMatchedPairs, bOnlyStereo, bCoarse) (orb_matcher.cc:817-1040) for key
+  // frames with one pinhole camera: keys_un / desc / has_point (GetMapPoint(i) != NULL) / u_right (mvuRight) / featvec of
+  // both key frames, f12 = the F12 of Pinhole::EpipolarConstrain (pinhole_model.cc:116-119), row-major, epipole =
+  // pKF2->cam_->Project(T2w * Cw) (:829-830), scale_factors / level_sigma2 = mvScaleFactors / mvLevelSigma2.
+  int SearchForTriangulation(const std::vector<cv::KeyPoint>& keys_un1, const cv::Mat& desc1, const std::vector<uint8_t>& has_point1,
+                             const std::vector<float>& u_right1, const std::map<unsigned int, std::vector<unsigned int> >& featvec1,
+                             const std::vector<cv::KeyPoint>& keys_un2, const cv::Mat& desc2, const std::vector<uint8_t>& has_point2,
+                             const std::vector<float>& u_right2, const std::map<unsigned int, std::vector<unsigned int> >& featvec2,
+                             const float f12[9], float epipole_x, float epipole_y, const std::vector<float>& scale_factors,
+                             const std::vector<float>& level_sigma2, bool only_stereo, bool coarse, bool check_orientation,
+                             std::vector<std::pair<size_t, size_t> >& matched_pairs);
 
   struct Window { float u, v, r; int min_level, max_level; };
   struct WindowBest { int best_dist, best_idx, best_level, best_dist2, best_level2; };

@@ -248,6 +248,63 @@ int ORBmatcherGpu::SearchByBoW(const std::vector<cv::KeyPoint>& keys_un1, const 
                          check_orientation, match_of_1);
 }
 
+int ORBmatcherGpu::SearchForTriangulation(const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
+                                          const std::vector<uint8_t>& has_point1, const std::vector<float>& u_right1,
+                                          const std::map<unsigned int, std::vector<unsigned int> >& featvec1,
+                                          const std::vector<cv::KeyPoint>& keys2, const cv::Mat& desc2,
+                                          const std::vector<uint8_t>& has_point2, const std::vector<float>& u_right2,
+                                          const std::map<unsigned int, std::vector<unsigned int> >& featvec2, const float f12[9],
+                                          float epipole_x, float epipole_y, const std::vector<float>& sf,
+                                          const std::vector<float>& sigma2, bool only_stereo, bool coarse, bool check_orientation,
+                                          std::vector<std::pair<size_t, size_t> >& matched_pairs) {
+  typedef std::map<unsigned int, std::vector<unsigned int> > FeatVec;
+  const int n1 = (int)keys1.size(), n2 = (int)keys2.size();
+  const int cap = std::max(1, std::max(n1, n2));
+  matched_pairs.clear();
+  std::vector<orbx_kp> kps(2 * (size_t)cap);
+  std::vector<uint8_t> desc(2 * (size_t)cap * 32, 0), has(2 * (size_t)cap, 1);
+  std::vector<float> ur(2 * (size_t)cap, -1.0f);
+  std::vector<uint32_t> nodes(2 * (size_t)cap, 0), feats(2 * (size_t)cap, 0);
+  std::vector<int32_t> begin(2 * (size_t)cap, 0);
+  int32_t fv_n[2] = {0, 0}, fv_total[2] = {0, 0};
+  const int32_t npf[2] = {n1, n2};
+  if (n1) std::memcpy(kps.data(), keys1.data(), sizeof(orbx_kp) * (size_t)n1);
+  if (n2) std::memcpy(kps.data() + cap, keys2.data(), sizeof(orbx_kp) * (size_t)n2);
+  const std::vector<uint8_t> d1 = dense_rows(desc1), d2 = dense_rows(desc2);
+  if (n1) std::memcpy(desc.data(), d1.data(), 32 * (size_t)n1);
+  if (n2) std::memcpy(desc.data() + 32 * (size_t)cap, d2.data(), 32 * (size_t)n2);
+  for (int i = 0; i < n1; ++i) { has[i] = i < (int)has_point1.size() ? has_point1[i] : 0; ur[i] = i < (int)u_right1.size() ? u_right1[i] : -1.0f; }
+  for (int i = 0; i < n2; ++i) {
+    has[(size_t)cap + i] = i < (int)has_point2.size() ? has_point2[i] : 0;
+    ur[(size_t)cap + i] = i < (int)u_right2.size() ? u_right2[i] : -1.0f;
+  }
+  const FeatVec* fv[2] = {&featvec1, &featvec2};
+  for (int s = 0; s < 2; ++s) {
+    const size_t o = (size_t)s * cap;
+    for (FeatVec::const_iterator it = fv[s]->begin(); it != fv[s]->end(); ++it) {
+      size_t cnt = 0;
+      for (size_t j = 0; j < it->second.size(); ++j) cnt += it->second[j] < (unsigned)npf[s];
+      if (fv_total[s] + (int)cnt > cap || fv_n[s] >= cap) throw std::runtime_error("ORBmatcherGpu::SearchForTriangulation: FeatureVector larger than the key frame");
+      nodes[o + fv_n[s]] = it->first;
+      begin[o + fv_n[s]] = fv_total[s];
+      ++fv_n[s];
+      for (size_t j = 0; j < it->second.size(); ++j)
+        if (it->second[j] < (unsigned)npf[s]) feats[o + fv_total[s]++] = it->second[j];
+    }
+  }
+  const int32_t p1 = 0, p2 = 1;
+  const float ep[2] = {epipole_x, epipole_y};
+  std::vector<int32_t> match((size_t)cap, -1);
+  int32_t nm = 0;
+  check(m_, orbm_search_for_triangulation(m_, kps.data(), desc.data(), cap, 2, npf, nodes.data(), begin.data(), fv_n, feats.data(), fv_total,
+                                          has.data(), ur.data(), &p1, &p2, 1, f12, ep, sf.data(), sigma2.data(), (int)sf.size(),
+                                          only_stereo ? 1 : 0, coarse ? 1 : 0, check_orientation ? 1 : 0, match.data(), &nm,
+                                          ORBX_MEM_HOST, nullptr));
+  for (int i = 0; i < n1; ++i)  // :1030-1037
+    if (match[i] >= 0) matched_pairs.push_back(std::make_pair((size_t)i, (size_t)match[i]));
+  return nm;
+}
+
 void ORBmatcherGpu::WindowSearch(const std::vector<cv::KeyPoint>& keys, const cv::Mat& desc, float min_x, float min_y,
                                  float inv_w, float inv_h, int cols, int rows, const std::vector<Window>& windows,
                                  const cv::Mat& window_desc, const std::vector<uint8_t>* already, std::vector<WindowBest>& out,

@@ -456,6 +456,157 @@ int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const
   return 1;
 }
 
+// ------------------------------------------------------------------ SearchForTriangulation
+// ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040; LocalMapping::CreateNewMapPoints) for key frames with one
+// pinhole camera (cam2_ == NULL, NLeft == -1), batched over pairs like k_search_by_bow: a warp owns a shared vocabulary
+// node and walks the features of key frame 1 that have NO map point in order; the lanes test the node's features of key
+// frame 2 (no map point, not claimed, within TH_LOW, away from the epipole :932-939, on the epipolar line
+// pinhole_model.cc:121-134 with the pair's F12).  The reference keeps the LAST of equally near candidates
+// (`dist > bestDist` skips, equality replaces): minimum of the key (distance, -position).
+__global__ void __launch_bounds__(256) k_search_for_triangulation(
+    const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap, const uint32_t* __restrict__ fv_nodes,
+    const int32_t* __restrict__ fv_begin, const int32_t* __restrict__ fv_n, const uint32_t* __restrict__ fv_feats,
+    const int32_t* __restrict__ fv_total, const int32_t* __restrict__ n_per_frame, const uint8_t* __restrict__ has_point,
+    const float* __restrict__ u_right, const int32_t* __restrict__ pair_1, const int32_t* __restrict__ pair_2,
+    const float* __restrict__ pair_f12, const float* __restrict__ pair_ep, const float* __restrict__ scale_factors,
+    const float* __restrict__ level_sigma2, int n_levels, int only_stereo, int coarse, int check_orientation,
+    int32_t* __restrict__ match, int32_t* __restrict__ n_matches) {
+  constexpr int kHisto = 30, kThLow = 50;
+  __shared__ int hist[kHisto];
+  __shared__ int keep3[3];
+  __shared__ int n_kept;
+  __shared__ uint32_t claimed[64];  // one bit per feature of key frame 2 (cap <= 2048)
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int fr1 = pair_1[p], fr2 = pair_2[p];
+  const size_t o1 = (size_t)fr1 * cap, o2 = (size_t)fr2 * cap;
+  const int n1 = n_per_frame ? max(0, min(n_per_frame[fr1], cap)) : cap, n2 = n_per_frame ? max(0, min(n_per_frame[fr2], cap)) : cap;
+  int32_t* mt = match + (size_t)p * cap;
+  for (int i = tid; i < cap; i += 256) mt[i] = -1;
+  if (tid < kHisto) hist[tid] = 0;
+  if (tid < 64) claimed[tid] = 0;
+  if (tid == 0) n_kept = 0;
+  __syncthreads();
+  float F[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) F[i] = pair_f12[9 * (size_t)p + i];
+  const float epx = pair_ep[2 * (size_t)p], epy = pair_ep[2 * (size_t)p + 1];
+  const int nn1 = fv_n[fr1], nn2 = fv_n[fr2];
+  const int tot1 = fv_total[fr1], tot2 = fv_total[fr2];
+  const uint32_t *nodes1 = fv_nodes + o1, *nodes2 = fv_nodes + o2, *feats1 = fv_feats + o1, *feats2 = fv_feats + o2;
+  const int32_t *begin1 = fv_begin + o1, *begin2 = fv_begin + o2;
+  for (int a = wrp; a < nn1; a += 8) {
+    const uint32_t nid = nodes1[a];
+    int lo = 0, hi = nn2;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (nodes2[mid] < nid) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= nn2 || nodes2[lo] != nid) continue;
+    const int k0 = begin1[a], k1 = a + 1 < nn1 ? begin1[a + 1] : tot1;
+    const int f0 = begin2[lo], f1 = lo + 1 < nn2 ? begin2[lo + 1] : tot2;
+    for (int ik = k0; ik < k1; ik++) {
+      const int idx1 = (int)feats1[ik];
+      if (idx1 >= n1 || has_point[o1 + idx1]) continue;           // :883-886 a map point already
+      const bool stereo1 = u_right[o1 + idx1] >= 0;               // :888
+      if (only_stereo && !stereo1) continue;
+      const orbx_kp K1 = kps[o1 + idx1];
+      uint32_t d1r[8];
+      load_row(desc + 32 * (o1 + idx1), d1r);
+      // epipolar line of K1 in image 2 (pinhole_model.cc:121-124), the same for every candidate
+      const float la = f_add(f_add(f_mul(K1.x, F[0]), f_mul(K1.y, F[3])), F[6]);
+      const float lb = f_add(f_add(f_mul(K1.x, F[1]), f_mul(K1.y, F[4])), F[7]);
+      const float lc = f_add(f_add(f_mul(K1.x, F[2]), f_mul(K1.y, F[5])), F[8]);
+      const float den = f_add(f_mul(la, la), f_mul(lb, lb));
+      unsigned long long best = ~0ull;
+      for (int jf = f0 + lane; jf < f1; jf += 32) {
+        const int idx2 = (int)feats2[jf];
+        if (idx2 >= n2 || ((claimed[idx2 >> 5] >> (idx2 & 31)) & 1u) || has_point[o2 + idx2]) continue;  // :911
+        const bool stereo2 = u_right[o2 + idx2] >= 0;
+        if (only_stereo && !stereo2) continue;
+        uint32_t d2r[8];
+        load_row(desc + 32 * (o2 + idx2), d2r);
+        const int dist = ham256(d1r, d2r);
+        if (dist > kThLow) continue;                               // :922
+        const orbx_kp K2 = kps[o2 + idx2];
+        const int oc = K2.octave < 0 ? 0 : (K2.octave >= n_levels ? n_levels - 1 : K2.octave);
+        if (!stereo1 && !stereo2) {                                // :932-939 too close to the epipole
+          const float ex = f_sub(epx, K2.x), ey = f_sub(epy, K2.y);
+          if (f_add(f_mul(ex, ex), f_mul(ey, ey)) < f_mul(100.0f, scale_factors[oc])) continue;
+        }
+        if (!coarse) {                                             // pinhole_model.cc:126-134
+          const float num = f_add(f_add(f_mul(la, K2.x), f_mul(lb, K2.y)), lc);
+          if (den == 0) continue;
+          const float dsqr = f_div(f_mul(num, num), den);
+          if (!((double)dsqr < 3.84 * (double)level_sigma2[oc])) continue;
+        }
+        best = min(best, ((unsigned long long)dist << 32) | (unsigned)(0x7FFFFFFF - (jf - f0)));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (lane == 0 && best != ~0ull) {                            // :987-992
+        const int idx2 = (int)feats2[f0 + (0x7FFFFFFF - (int)(best & 0xFFFFFFFFu))];
+        atomicOr(&claimed[idx2 >> 5], 1u << (idx2 & 31));
+        mt[idx1] = idx2;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // rotation consistency (:994-1003, :1010-1027)
+  const float factor = 30 / 360.0f;
+  int my_bin[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const int i = tid + 256 * r;
+    my_bin[r] = -1;
+    if (i < cap && mt[i] >= 0) {
+      float rot = f_sub(kps[o1 + i].angle, kps[o2 + mt[i]].angle);
+      if (rot < 0.0f) rot = f_add(rot, 360.0f);
+      int bin = (int)roundf(f_mul(rot, factor));
+      if (bin == kHisto) bin = 0;
+      my_bin[r] = bin < 0 ? 0 : (bin > kHisto - 1 ? kHisto - 1 : bin);
+      if (check_orientation) atomicAdd(&hist[my_bin[r]], 1);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+    for (int i = 0; i < kHisto; i++) {
+      const int s = hist[i];
+      if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+      else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+      else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if ((float)max2 < f_mul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
+    else if ((float)max3 < f_mul(0.1f, (float)max1)) { ind3 = -1; }
+    keep3[0] = ind1; keep3[1] = ind2; keep3[2] = ind3;
+  }
+  __syncthreads();
+  int kept = 0;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (my_bin[r] < 0) continue;
+    if (check_orientation && my_bin[r] != keep3[0] && my_bin[r] != keep3[1] && my_bin[r] != keep3[2]) mt[tid + 256 * r] = -1;
+    else kept++;
+  }
+  if (kept) atomicAdd(&n_kept, kept);
+  __syncthreads();
+  if (tid == 0) n_matches[p] = n_kept;
+}
+
+int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+                                    const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
+                                    const uint8_t* has_point, const float* u_right, const int32_t* pair_1, const int32_t* pair_2,
+                                    int n_pairs, const float* pair_f12, const float* pair_ep, const float* scale_factors,
+                                    const float* level_sigma2, int n_levels, int only_stereo, int coarse, int check_orientation,
+                                    int32_t* match, int32_t* n_matches, cudaStream_t st) {
+  if (n_pairs <= 0) return 0;
+  k_search_for_triangulation<<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame, has_point,
+                                                      u_right, pair_1, pair_2, pair_f12, pair_ep, scale_factors, level_sigma2, n_levels,
+                                                      only_stereo, coarse, check_orientation, match, n_matches);
+  return 1;
+}
+
 // ------------------------------------------------------------------ stereo sub-pixel refinement
 // The rest of Frame::ComputeStereoMatches (frame.cc:903-985): for every left keypoint whose row-band
 // match is closer than thOrbDist, an 11x11 SAD over 11 horizontal shifts on the keypoint's pyramid

@@ -478,6 +478,59 @@ int orbm_search_by_bow_kf(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, in
                        pair_1, pair_2, n_pairs, nnratio, check_orientation, match, n_matches, mem, stream);
 }
 
+int orbm_search_for_triangulation(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames,
+                                  const int32_t* n_per_frame, const uint32_t* fv_nodes, const int32_t* fv_begin, const int32_t* fv_n,
+                                  const uint32_t* fv_feats, const int32_t* fv_total, const uint8_t* has_point, const float* u_right,
+                                  const int32_t* pair_1, const int32_t* pair_2, int n_pairs, const float* pair_f12,
+                                  const float* pair_ep, const float* scale_factors, const float* level_sigma2, int n_levels,
+                                  int only_stereo, int coarse, int check_orientation, int32_t* match, int32_t* n_matches, int mem,
+                                  void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (cap < 1 || cap > 2048 || n_frames < 1 || n_pairs < 0 || n_levels < 1 || n_levels > ORBX_MAX_LEVELS || !kps || !desc || !fv_nodes ||
+      !fv_begin || !fv_n || !fv_feats || !fv_total || !has_point || !u_right || !scale_factors || !level_sigma2 ||
+      (n_pairs > 0 && (!pair_1 || !pair_2 || !pair_f12 || !pair_ep || !match || !n_matches)))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (n_pairs == 0) return ORBX_OK;
+  const size_t fc = (size_t)n_frames * cap;
+  if (mem == ORBX_MEM_HOST) {
+    for (int p = 0; p < n_pairs; p++)
+      if (pair_1[p] < 0 || pair_1[p] >= n_frames || pair_2[p] < 0 || pair_2[p] >= n_frames)
+        return fail(m, ORBX_E_ARG, "pair %d refers to a frame outside the pool", p);
+    TRY(arena_reserve(m, pad256(fc * sizeof(orbx_kp)) + pad256(fc * 32) + 4 * pad256(fc * 4) + pad256(fc) + 3 * pad256((size_t)n_frames * 4) +
+                             3 * pad256((size_t)n_pairs * 4) + pad256((size_t)n_pairs * 36) + pad256((size_t)n_pairs * 8) + 2 * 256 +
+                             pad256((size_t)n_pairs * cap * 4)));
+  }
+  const orbx_kp* dk;
+  const uint8_t *dd, *dhp;
+  const uint32_t *dnodes, *dfeats;
+  const int32_t *dbegin, *dfn, *dft, *dnpf, *dp1, *dp2;
+  const float *dur, *df12, *dep, *dsf, *ds2;
+  TRY(stage_in(m, mem, kps, fc, &dk, st));
+  TRY(stage_in(m, mem, desc, fc * 32, &dd, st));
+  TRY(stage_in(m, mem, fv_nodes, fc, &dnodes, st));
+  TRY(stage_in(m, mem, fv_begin, fc, &dbegin, st));
+  TRY(stage_in(m, mem, fv_feats, fc, &dfeats, st));
+  TRY(stage_in(m, mem, has_point, fc, &dhp, st));
+  TRY(stage_in(m, mem, u_right, fc, &dur, st));
+  TRY(stage_in(m, mem, fv_n, (size_t)n_frames, &dfn, st));
+  TRY(stage_in(m, mem, fv_total, (size_t)n_frames, &dft, st));
+  TRY(stage_in(m, mem, n_per_frame, (size_t)n_frames, &dnpf, st));
+  TRY(stage_in(m, mem, pair_1, (size_t)n_pairs, &dp1, st));
+  TRY(stage_in(m, mem, pair_2, (size_t)n_pairs, &dp2, st));
+  TRY(stage_in(m, mem, pair_f12, (size_t)n_pairs * 9, &df12, st));
+  TRY(stage_in(m, mem, pair_ep, (size_t)n_pairs * 2, &dep, st));
+  TRY(stage_in(m, mem, scale_factors, (size_t)n_levels, &dsf, st));
+  TRY(stage_in(m, mem, level_sigma2, (size_t)n_levels, &ds2, st));
+  int32_t* dmatch = stage_out(m, mem, match, (size_t)n_pairs * cap);
+  int32_t* dnm = stage_out(m, mem, n_matches, (size_t)n_pairs);
+  m->launches += launch_search_for_triangulation(dk, dd, cap, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dur, dp1, dp2, n_pairs, df12, dep,
+                                                 dsf, ds2, n_levels, only_stereo, coarse, check_orientation, dmatch, dnm, st);
+  TRY(finish_out(m, mem, match, dmatch, (size_t)n_pairs * cap, st));
+  TRY(finish_out(m, mem, n_matches, dnm, (size_t)n_pairs, st));
+  return end(m, mem, st);
+}
+
 int orbm_synth_descriptors(int device, uint8_t* dst, int64_t first, int64_t n, uint64_t seed, void* stream) {
   if (!dst || n < 0) return ORBX_E_ARG;
   if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;

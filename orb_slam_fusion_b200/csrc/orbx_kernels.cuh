@@ -89,6 +89,12 @@ int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, 
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                                 const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
                                 bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st);
+int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+                                    const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
+                                    const uint8_t* has_point, const float* u_right, const int32_t* pair_1, const int32_t* pair_2,
+                                    int n_pairs, const float* pair_f12, const float* pair_ep, const float* scale_factors,
+                                    const float* level_sigma2, int n_levels, int only_stereo, int coarse, int check_orientation,
+                                    int32_t* match, int32_t* n_matches, cudaStream_t st);
 int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                          const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,

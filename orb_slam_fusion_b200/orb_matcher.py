@@ -255,6 +255,32 @@ class ORBmatcher:
                        nnratio, int(check_orientation), A.ptr(match), A.ptr(nm), mem, stream))
         return nm, match
 
+    def SearchForTriangulation(self, kps, desc, n_per_frame, fv, pairs, has_point, u_right, pair_f12, pair_ep, scale_factors,
+                               level_sigma2, only_stereo=False, coarse=False, check_orientation=None):
+        """ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040) for a batch of key-frame pairs of one frame pool
+        (layout of SearchByBoW); has_point / u_right [F, cap], pair_f12 [n_pairs, 3, 3] (Pinhole::EpipolarConstrain's F12),
+        pair_ep [n_pairs, 2] (epipole in image 2).  Returns (n_matches [n_pairs], match [n_pairs, cap]): match[p, i] =
+        feature of key frame 2 matched to feature i of key frame 1, -1 = none."""
+        kps = np.ascontiguousarray(kps, A.KP_DTYPE)
+        F, cap = kps.shape
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(F, cap, 32)
+        npf = None if n_per_frame is None else np.ascontiguousarray(n_per_frame, np.int32)
+        hp = np.ascontiguousarray(has_point, np.uint8).reshape(F, cap)
+        ur = np.ascontiguousarray(u_right, np.float32).reshape(F, cap)
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        p1, p2 = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        f12 = np.ascontiguousarray(pair_f12, np.float32).reshape(len(pairs), 9)
+        ep = np.ascontiguousarray(pair_ep, np.float32).reshape(len(pairs), 2)
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        match = np.empty((len(pairs), cap), np.int32)
+        nm = np.empty(len(pairs), np.int32)
+        self._check(self._lib.orbm_search_for_triangulation(
+            self._m, A.ptr(kps), A.ptr(desc), cap, F, A.ptr(npf), A.ptr(fv["fv_nodes"]), A.ptr(fv["fv_begin"]), A.ptr(fv["fv_n"]),
+            A.ptr(fv["fv_feats"]), A.ptr(fv["fv_total"]), A.ptr(hp), A.ptr(ur), A.ptr(p1), A.ptr(p2), len(pairs), A.ptr(f12), A.ptr(ep),
+            A.ptr(sf), A.ptr(s2), len(sf), int(only_stereo), int(coarse),
+            int(self.check_ori if check_orientation is None else check_orientation), A.ptr(match), A.ptr(nm), A.MEM_HOST, None))
+        return nm, match
+
     # ---- projection window
     def window_search(self, kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q_u_right=None, q_max_err=None):
         """Best / second-best frame keypoint per projected map point (orb_matcher.cc:66-113, 451-479, 1567-1608).

@@ -440,3 +440,43 @@ def test_search_by_projection_last_frame(P, m, oracle, seed, th, t_lw_z, mono, s
         assert nm == rnm and np.array_equal(np.where(got >= 0, keep[np.maximum(got, 0)], -1), rwant)
     nm0, got0 = m.SearchByProjectionLast(kps, desc, geom, q[:0], ldesc[:0], last["angle"][:0], pre)
     assert nm0 == 0 and (got0 == -1).all()
+
+
+def test_search_for_triangulation(P, m, oracle):
+    """ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040; LocalMapping::CreateNewMapPoints) batched over pairs of a
+    key-frame pool: bag-of-words guided matching of features without map points, epipole and epipolar-line gates, greedy
+    claim, rotation histogram -- vs the oracle (pinned on the reference's lines by tests/test_oracle_vs_ref_frame.py)."""
+    from test_oracle_vs_ref_frame import CAM4
+    w, h, nfeat, k, L = 640, 400, 800, 6, 4
+    vp_ = oracle.synth_vocab(k, L, seed=43)
+    voc, vo = P.ORBVocabulary(k, L, *vp_), oracle.Vocabulary(k, L, *vp_)
+    ex = P.OrbExtractor(nfeat, 1.2, 8, 20, 7)
+    views = [(1, 0, 1), (1, 12, 8), (1, 6, 9), (2, 0, 2), (2, 9, 5)]
+    ext = [ex(oracle.blocks_v1(w, h, s, 0, shift_x=sh, noise_seed=ns)) for s, sh, ns in views]
+    cap = max(len(e[1]) for e in ext) + 3
+    F = len(views)
+    kps, desc, npf = np.zeros((F, cap), P.KP_DTYPE), np.zeros((F, cap, 32), np.uint8), np.zeros(F, np.int32)
+    for f, (_, kk, dd) in enumerate(ext):
+        kps[f, :len(kk)], desc[f, :len(kk)], npf[f] = kk, dd, len(kk)
+    rng = np.random.default_rng(8)
+    has_point = (rng.random((F, cap)) < 0.4).astype(np.uint8)
+    u_right = np.where(rng.random((F, cap)) < 0.5, kps["x"] - rng.uniform(1, 40, (F, cap)), -1.0).astype(np.float32)
+    pairs = np.array([(0, 1), (1, 0), (0, 2), (2, 1), (3, 4), (4, 3), (0, 3), (1, 1)], np.int32)
+    f12 = np.zeros((len(pairs), 3, 3), np.float32)
+    f12[:, 1, 2], f12[:, 2, 1] = -np.float32(0.11) / CAM4[1], np.float32(0.11) / CAM4[1]
+    f12 += rng.normal(0, 2e-9, f12.shape).astype(np.float32)
+    ep = np.stack([rng.uniform(-2000, 2000, len(pairs)), rng.uniform(-500, 900, len(pairs))], 1).astype(np.float32)
+    ep[2] = (330.0, 210.0)                                                 # an epipole inside the image
+    t = ex.GetScaleFactors(), ex.GetScaleSigmaSquares()
+    for levelsup, only_stereo, coarse, ori in [(3, False, False, True), (2, True, False, True), (3, False, True, False)]:
+        fv = voc.transform_batch(desc, npf, levelsup)
+        nm, match = m.SearchForTriangulation(kps, desc, npf, fv, pairs, has_point, u_right, f12, ep, t[0], t[1], only_stereo, coarse, ori)
+        for p, (a, b) in enumerate(pairs):
+            fva = oracle.pack_feature_vector(*vo.transform(desc[a, :npf[a]], levelsup)[2:])
+            fvb = oracle.pack_feature_vector(*vo.transform(desc[b, :npf[b]], levelsup)[2:])
+            wnm, want = oracle.search_for_triangulation(kps[a, :npf[a]], desc[a, :npf[a]], has_point[a, :npf[a]], u_right[a, :npf[a]], fva,
+                                                        kps[b, :npf[b]], desc[b, :npf[b]], has_point[b, :npf[b]], u_right[b, :npf[b]], fvb,
+                                                        f12[p], ep[p], t[0], t[1], only_stereo, coarse, ori)
+            assert nm[p] == wnm and np.array_equal(match[p, :npf[a]], want), (levelsup, p)
+            assert (match[p, npf[a]:] == -1).all()
+        assert nm[0] > (8 if only_stereo else 25) and nm[6] < nm[0]

@@ -284,3 +284,33 @@ def test_search_by_projection_last_frame_identical(oracle, seed, th, t_lw_z, mon
                                                qur if stereo else None, q["r"] if stereo else None, 100, ori)
     assert nm == want_nm and np.array_equal(np.where(got >= 0, keep[np.maximum(got, 0)], -1), want)
     assert want_nm > 100
+
+
+def triangulation_case(oracle, seed, shift, levelsup=3):
+    ka, da, fva, kb, db, fvb = _bow_pair(oracle, seed, shift, levelsup=levelsup)
+    rng = np.random.default_rng(seed + 300)
+    hp1 = (rng.random(len(ka)) < 0.4).astype(np.uint8)          # features that already have a map point are skipped
+    hp2 = (rng.random(len(kb)) < 0.4).astype(np.uint8)
+    ur1 = np.where(rng.random(len(ka)) < 0.5, ka["x"] - rng.uniform(1, 40, len(ka)), -1.0).astype(np.float32)
+    ur2 = np.where(rng.random(len(kb)) < 0.5, kb["x"] - rng.uniform(1, 40, len(kb)), -1.0).astype(np.float32)
+    tx = np.float32(0.11)
+    f12 = np.zeros((3, 3), np.float32)                          # pure x translation, equal pinhole cameras: horizontal lines
+    f12[1, 2], f12[2, 1] = -tx / CAM4[1], tx / CAM4[1]
+    f12 += rng.normal(0, 2e-9, (3, 3)).astype(np.float32)       # ... slightly tilted
+    t = oracle.Extractor(800).tables()
+    return ka, da, hp1, ur1, fva, kb, db, hp2, ur2, fvb, f12, t["scale"], t["sigma2"]
+
+
+@pytest.mark.parametrize("seed,shift,only_stereo,coarse,ori,c2", [(1, 12, False, False, True, (0.5, 0.01, 0.05)),
+                                                                  (2, 6, False, False, True, (0.02, -0.01, 1.0)),
+                                                                  (3, 9, True, False, True, (0.02, -0.01, 1.0)),
+                                                                  (4, 12, False, True, False, (-0.3, 0.2, 1.0))])
+def test_search_for_triangulation_identical(oracle, seed, shift, only_stereo, coarse, ori, c2):
+    """SearchForTriangulation (orb_matcher.cc:817-1040) + the line test of Pinhole::EpipolarConstrain (pinhole_model.cc:121-134)."""
+    ka, da, hp1, ur1, fva, kb, db, hp2, ur2, fvb, f12, sf, s2 = triangulation_case(oracle, seed, shift)
+    want_nm, want, ep = R.search_for_triangulation(ka, da, hp1, ur1, fva, kb, db, hp2, ur2, fvb, f12, CAM4, c2, sf, s2,
+                                                   only_stereo, coarse, ori)
+    nm, got = oracle.search_for_triangulation(ka, da, hp1, ur1, fva, kb, db, hp2, ur2, fvb, f12, ep, sf, s2, only_stereo, coarse, ori)
+    assert nm == want_nm and np.array_equal(got, want)
+    assert want_nm > (10 if only_stereo else 25)
+    assert (got[hp1 != 0] == -1).all() and (hp2[got[got >= 0]] == 0).all()
