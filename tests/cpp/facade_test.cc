@@ -128,6 +128,19 @@ int main(int argc, char** argv) {
     const int32_t nmatch_kf = matcher.SearchByBoW(keys, desc, has_point, fvec, keys, desc, has_point, fvec, 0.8f, true, match_of_1);
     put(fo, &nmatch_kf, 4);
     put(fo, match_of_1.data(), match_of_1.size() * sizeof(int));
+    // ORBmatcher::SearchForTriangulation (orb_matcher.cc:817-1040) of the frame against itself: horizontal epipolar lines,
+    // epipole far away, every third feature already holds a map point
+    std::vector<uint8_t> with_point(keys.size(), 0);
+    for (size_t i = 0; i < with_point.size(); i += 3) with_point[i] = 1;
+    std::vector<float> no_right(keys.size(), -1.0f);
+    const float f12[9] = {0.f, 0.f, 0.f, 0.f, 0.f, -2.4e-4f, 0.f, 2.4e-4f, 0.f};
+    std::vector<std::pair<size_t, size_t> > tri_pairs;
+    const int32_t ntri = matcher.SearchForTriangulation(keys, desc, with_point, no_right, fvec, keys, desc, with_point, no_right, fvec, f12,
+                                                        -5000.f, 200.f, sf, extractor->GetScaleSigmaSquares(), false, false, true, tri_pairs);
+    put(fo, &ntri, 4);
+    std::vector<int> tri(keys.size(), -1);
+    for (size_t j = 0; j < tri_pairs.size(); j++) tri[tri_pairs[j].first] = (int)tri_pairs[j].second;
+    put(fo, tri.data(), tri.size() * sizeof(int));
   }
   fclose(fo);
   delete extractor;

@@ -113,4 +113,14 @@ def test_facade_outputs_equal_oracle(oracle, tmp_path, w, h, nf, lap):
     match_kf = np.frombuffer(buf, np.int32, n, off); off += 4 * n
     wnm, want = oracle.search_by_bow_kf(rk, rd, has_point, fv, rk, rd, has_point, fv, 0.8, True)
     assert nmatch_kf == wnm and np.array_equal(match_kf, want) and wnm > n // 3
+    # ORBmatcherGpu::SearchForTriangulation (orb_matcher.cc:817-1040)
+    ntri = int(np.frombuffer(buf, np.int32, 1, off)[0]); off += 4
+    tri = np.frombuffer(buf, np.int32, n, off); off += 4 * n
+    with_point = np.zeros(n, np.uint8)
+    with_point[::3] = 1
+    f12 = np.array([0, 0, 0, 0, 0, -2.4e-4, 0, 2.4e-4, 0], np.float32)
+    wnm, want = oracle.search_for_triangulation(rk, rd, with_point, np.full(n, -1, np.float32), fv, rk, rd, with_point,
+                                                np.full(n, -1, np.float32), fv, f12, np.array([-5000, 200], np.float32), sf,
+                                                ref.tables()["sigma2"], False, False, True)
+    assert ntri == wnm and np.array_equal(tri, want) and wnm > n // 3
     assert off == len(buf)
