@@ -256,6 +256,20 @@ int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
                               const float* q_u_right, const float* q_max_err, orbm_window_result* out,
                               int mem, void* stream);
 
+/* The search of ORBmatcher::Fuse(KeyFrame* pKF, const vector<MapPoint*>&, th, bRight) (orb_matcher.cc:1130-1187, the same
+ * loop in Fuse(pKF, Scw, ...) :1214-1386; LocalMapping::SearchInNeighbors, loop closing) for key frames with NLeft == -1:
+ * per projected map point the nearest keypoint of the window (u, v, r = th * scale[nPredictedLevel], levels
+ * [nPredictedLevel-1, nPredictedLevel]) whose reprojection error passes the chi-square gate against its OWN level's
+ * variance: with a right coordinate (kp_u_right[i] >= 0) (ex^2 + ey^2 + er^2) * inv_level_sigma2[octave] <= 7.8, er =
+ * q_u_right[q] - kp_u_right[i]; else (ex^2 + ey^2) * inv_level_sigma2[octave] <= 5.99 (:1159-1178).  No claims: the map
+ * points are independent; best_dist <= TH_LOW and the Replace / AddObservation bookkeeping (:1190-1206) stay with the
+ * caller.  kp_u_right (KeyFrame::mvuRight) may be NULL (monocular).  Only best_dist / best_idx / best_level of `out`
+ * are defined by the reference. */
+int orbm_window_search_fuse(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                            const orbm_window_query* queries, const uint8_t* qdesc, int nq, const float* kp_u_right,
+                            const float* q_u_right, const float* inv_level_sigma2, int n_levels, orbm_window_result* out,
+                            int mem, void* stream);
+
 /* ORBmatcher::SearchByProjection(Frame& F, const vector<MapPoint*>& vpMapPoints, th, bFarPoints, thFarPoints)
  * (orb_matcher.cc:42-134; caller tracking.cc:2687, Tracking::SearchLocalPoints) for a frame with Nleft == -1, the
  * WHOLE function including the greedy claim: query q is the window of one map point that passed the reference's

@@ -75,6 +75,7 @@ def lib():
         L.orc_stereo_refine.argtypes = [vp, vp, i, vp, i, vp, vp, vp, vp, vp, i, f, f, f, vp, vp, vp]
         L.orc_window_search.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp]
         L.orc_window_search_stereo.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, vp]
+        L.orc_window_search_fuse.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp]
         L.orc_search_by_projection.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, i, vp, vp, vp, vp, i, f, vp]
         L.orc_search_by_projection_last.argtypes = [vp, vp, i, C.POINTER(GridGeom), vp, vp, vp, i, vp, vp, vp, vp, i, i, vp]
         L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
@@ -365,6 +366,23 @@ def window_search(kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q
         qe = np.ascontiguousarray(q_max_err, np.float32)
         lib().orc_window_search_stereo(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc), len(queries),
                                        None if sk is None else _p(sk), _p(ur), _p(qr), _p(qe), _p(out))
+    return out
+
+
+def window_search_fuse(kps, desc, geom, queries, qdesc, inv_level_sigma2, kp_u_right=None, q_u_right=None):
+    """The search of ORBmatcher::Fuse (orb_matcher.cc:1130-1187)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    queries = np.ascontiguousarray(queries, WQ_DTYPE)
+    qdesc = np.ascontiguousarray(qdesc, np.uint8)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    ur = qr = None
+    if kp_u_right is not None:
+        ur, qr = np.ascontiguousarray(kp_u_right, np.float32), np.ascontiguousarray(q_u_right, np.float32)
+    out = np.empty(len(queries), WR_DTYPE)
+    g = GridGeom(*geom)
+    lib().orc_window_search_fuse(_p(kps), _p(desc), len(kps), C.byref(g), _p(queries), _p(qdesc), len(queries),
+                                 None if ur is None else _p(ur), None if qr is None else _p(qr), _p(inv), _p(out))
     return out
 
 

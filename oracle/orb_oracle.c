@@ -718,6 +718,16 @@ void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_
   orc_window_search_stereo(kps, desc, n, g, q, qdesc, nq, skip, NULL, NULL, NULL, out);
 }
 
+static const float* g_fuse_inv_sigma2 = NULL; /* set only inside orc_window_search_fuse (test infrastructure, one thread) */
+
+void orc_window_search_fuse(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g, const orc_window_query* q,
+                            const uint8_t* qdesc, int nq, const float* kp_u_right, const float* q_u_right,
+                            const float* inv_level_sigma2, orc_window_result* out) {
+  g_fuse_inv_sigma2 = inv_level_sigma2;
+  orc_window_search_stereo(kps, desc, n, g, q, qdesc, nq, NULL, kp_u_right, q_u_right, NULL, out);
+  g_fuse_inv_sigma2 = NULL;
+}
+
 void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
                               const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
@@ -760,6 +770,18 @@ void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, con
             const float dx = kps[i].x - x, dy = kps[i].y - y;
             if (!(fabsf(dx) < fr && fabsf(dy) < fr)) continue;
             if (skip && skip[i]) continue; /* orb_matcher.cc:86-87 "already matched" */
+            if (g_fuse_inv_sigma2) { /* ORBmatcher::Fuse, orb_matcher.cc:1159-1178 */
+              const float ex = x - kps[i].x, ey = y - kps[i].y;
+              const float inv = g_fuse_inv_sigma2[kps[i].octave];
+              if (kp_u_right && kp_u_right[i] >= 0) {
+                const float er = q_u_right[qi] - kp_u_right[i];
+                const float e2 = ex * ex + ey * ey + er * er;
+                if (e2 * inv > 7.8) continue;
+              } else {
+                const float e2 = ex * ex + ey * ey;
+                if (e2 * inv > 5.99) continue;
+              }
+            } else
             if (kp_u_right && kp_u_right[i] > 0) { /* stereo observation: orb_matcher.cc:89-92, 1586-1590 */
               const float er = fabsf(q_u_right[qi] - kp_u_right[i]);
               if (er > q_max_err[qi]) continue;

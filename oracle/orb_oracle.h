@@ -156,6 +156,13 @@ void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, con
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
                               orc_window_result* out);
 
+/* The search of ORBmatcher::Fuse (orb_matcher.cc:1130-1187): the window search with the chi-square reprojection gate of
+ * :1159-1178 (7.8 with a right coordinate >= 0, else 5.99) instead of the tracker's stereo gate; no skip flags.
+ * Pinned on orb_matcher.cc:1144-1187 spliced into oracle/ref_frame_shim.cc. */
+void orc_window_search_fuse(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g, const orc_window_query* q,
+                            const uint8_t* qdesc, int nq, const float* kp_u_right, const float* q_u_right,
+                            const float* inv_level_sigma2, orc_window_result* out);
+
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, ...) (orb_matcher.cc:42-134, Nleft == -1) as a whole:
  * the window search per map point in order + the greedy claim.  assigned[i] = query stored in F.mvpMapPoints[i] or -1;
  * returns nmatches.  Pinned on orb_matcher.cc:42-213 spliced into oracle/ref_frame_shim.cc. */

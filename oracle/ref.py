@@ -351,3 +351,21 @@ def search_for_triangulation(kps1, desc1, has_point1, u_right1, fv1, kps2, desc2
                                          _p(f12), _p(cam4), _p(c2), _p(sf), _p(s2), len(sf), 0.6, int(only_stereo), int(coarse),
                                          int(check_orientation), _p(ep), _p(out))
     return nm, out[:len(kps1)].copy(), ep
+
+
+def fuse_search(keys_un, desc, bounds, inv_level_sigma2, pt_u, pt_v, pt_ur, pt_radius, pt_level, pt_desc, u_right=None):
+    """The candidate loop of ORBmatcher::Fuse (orb_matcher.cc:1145-1190) after KeyFrame::GetFeaturesInArea, per projected
+    map point: (best_idx, best_dist)."""
+    L = _frame()
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.reff_fuse_search.argtypes = [vp, vp, i, vp, f, f, f, f, vp, i, vp, vp, vp, vp, vp, vp, i, vp, vp]
+    keys_un = np.ascontiguousarray(keys_un, KP_DTYPE)
+    desc, pt_desc = np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(pt_desc, np.uint8)
+    inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    pu, pv, pr, prad = (np.ascontiguousarray(a, np.float32) for a in (pt_u, pt_v, pt_ur, pt_radius))
+    plev = np.ascontiguousarray(pt_level, np.int32)
+    ur = None if u_right is None else np.ascontiguousarray(u_right, np.float32)
+    bi, bd = np.empty(len(pu), np.int32), np.empty(len(pu), np.int32)
+    L.reff_fuse_search(_p(keys_un), _p(desc), len(keys_un), None if ur is None else _p(ur), *[float(b) for b in bounds], _p(inv), len(inv),
+                       _p(pu), _p(pv), _p(pr), _p(prad), _p(plev), _p(pt_desc), len(pu), _p(bi), _p(bd))
+    return bi, bd

@@ -17,6 +17,7 @@
 //   _ref/matcher_project_last.inc orb_matcher.cc:1518-1728 ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th, bMono)
 //   _ref/matcher_triangulation.inc orb_matcher.cc:817-1040 ORBmatcher::SearchForTriangulation
 //   _ref/pinhole_epipolar.inc    pinhole_model.cc:121-134  the epipolar-line test of Pinhole::EpipolarConstrain (F12 given)
+//   _ref/matcher_fuse_loop.inc   orb_matcher.cc:1145-1190  the candidate loop of ORBmatcher::Fuse (spliced into reff_fuse_search)
 //   _ref/matcher_maxima.inc      orb_matcher.cc:1841-1873 ORBmatcher::ComputeThreeMaxima
 //   _ref/descriptor_distance.inc orb_matcher.cc:1877-1891
 // Used by tests/test_oracle_vs_ref_frame.py to pin orc_stereo_rowband / orc_stereo_refine /
@@ -164,7 +165,12 @@ class KeyFrame {  // include/map/keyframe.h: what mappoint.cc:365-433 and orb_ma
   GeometricCamera *cam_ = nullptr, *cam2_ = nullptr;
   // orb_matcher.cc:817-1040
   MapPoint *GetMapPoint(const size_t &idx) { return mvpMapPoints[idx]; }
-  std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2;
+  std::vector<float> mvuRight, mvScaleFactors, mvLevelSigma2, mvInvLevelSigma2;
+  // KeyFrame::GetFeaturesInArea (keyframe.cc:729-773) visits the frame's grid exactly like Frame::GetFeaturesInArea without a level gate
+  Frame *grid = nullptr;
+  std::vector<size_t> GetFeaturesInArea(const float &x, const float &y, const float &r, const bool bRight = false) const {
+    return grid->GetFeaturesInArea(x, y, r, -1, -1, bRight);
+  }
   Sophus::SE3f pose;  // Tcw, translation only
   Sophus::SE3f GetPose() { return pose; }
   Sophus::SE3f GetPoseInverse() { return pose.inverse(); }
@@ -210,6 +216,9 @@ class MapPoint {  // include/map/mappoint.h
 }  // namespace ORB_SLAM_FUSION
 
 using namespace ORB_SLAM_FUSION;
+
+// the spliced loop of Fuse calls DescriptorDistance unqualified (it is a member function there)
+static inline int DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return ORBmatcher::DescriptorDistance(a, b); }
 
 extern "C" {
 
@@ -470,6 +479,45 @@ int reff_search_for_triangulation(const void *kps1, const uint8_t *desc1, int n1
   for (int i = 0; i < n1; i++) match_of_1[i] = -1;
   for (size_t j = 0; j < pairs.size(); j++) match_of_1[pairs[j].first] = (int)pairs[j].second;
   return nm;
+}
+
+// The search of ORBmatcher::Fuse(pKF, vpMapPoints, th, bRight) for one key frame (NLeft == -1) and n_pts projected map
+// points: uv, ur, nPredictedLevel and radius are given (the geometry of :1060-1131 stays with the caller); the candidate
+// loop is the reference's own lines 1145-1190.  best_idx / best_dist per point (-1 / 256 when nothing passes).
+void reff_fuse_search(const void *keys_un, const uint8_t *desc, int n, const float *u_right, float min_x, float max_x, float min_y,
+                      float max_y, const float *inv_sigma2, int n_levels, const float *pt_u, const float *pt_v, const float *pt_ur,
+                      const float *pt_radius, const int *pt_level, const uint8_t *pt_desc, int n_pts, int *best_idx, int *best_dist) {
+  Frame F;
+  F.N = n;
+  F.mvKeysUn.assign((const cv::KeyPoint *)keys_un, (const cv::KeyPoint *)keys_un + n);
+  Frame::mnMinX = min_x; Frame::mnMaxX = max_x; Frame::mnMinY = min_y; Frame::mnMaxY = max_y;
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(max_x - min_x);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(max_y - min_y);
+  F.AssignFeaturesToGrid();
+  KeyFrame kf;
+  KeyFrame *pKF = &kf;
+  kf.grid = &F;
+  kf.mvKeysUn = F.mvKeysUn;
+  kf.mvKeys = F.mvKeysUn;
+  kf.mDescriptors = cv::Mat(n, 32, CV_8U, (void *)desc);
+  kf.mvuRight.assign(n, -1.0f);
+  if (u_right) kf.mvuRight.assign(u_right, u_right + n);
+  kf.mvInvLevelSigma2.assign(inv_sigma2, inv_sigma2 + n_levels);
+  const bool bRight = false;
+  for (int p = 0; p < n_pts; p++) {
+    const Eigen::Vector2f uv(pt_u[p], pt_v[p]);
+    const float ur = pt_ur[p];
+    const int nPredictedLevel = pt_level[p];
+    const float radius = pt_radius[p];
+    const vector<size_t> vIndices = pKF->GetFeaturesInArea(uv(0), uv(1), radius, bRight);  // :1133-1134
+    MapPoint mp;
+    MapPoint *pMP = &mp;
+    mp.mDescriptor = cv::Mat(1, 32, CV_8U, (void *)(pt_desc + 32 * (size_t)p)).clone();
+    const cv::Mat dMP = pMP->GetDescriptor();  // :1143
+#include "matcher_fuse_loop.inc"
+    best_idx[p] = bestIdx;
+    best_dist[p] = bestDist;
+  }
 }
 
 // Frame::GetFeaturesInArea after AssignFeaturesToGrid: the visiting order of the grid lookup.

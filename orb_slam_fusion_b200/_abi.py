@@ -74,6 +74,7 @@ SIGNATURES = {
     "orbm_stereo_rowband": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp, i32, vp]),
     "orbm_stereo_refine": (i32, [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, f32, f32, f32, vp, vp, vp, i32, vp]),
     "orbm_distinctive": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, vp]),
+    "orbm_window_search_fuse": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, vp, i32, vp, i32, vp]),
     "orbm_search_by_projection": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, vp, vp, i32, f32, vp, vp, i32, vp]),
     "orbm_search_by_projection_last": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp]),
     "orbm_search_by_bow": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, f32, i32, vp, vp, i32, vp]),

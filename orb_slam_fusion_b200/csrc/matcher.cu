@@ -797,7 +797,8 @@ int launch_distinctive(const uint8_t* desc, const int32_t* offsets, int n_points
 __device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                             const orbm_grid_geom& g, const orbm_window_query& Q, const uint8_t* __restrict__ qd_row,
                                             const uint8_t* __restrict__ skip, const float* __restrict__ kp_u_right, float q_ur,
-                                            float q_err, int lane, unsigned long long& b0, unsigned long long& b1) {
+                                            float q_err, int lane, unsigned long long& b0, unsigned long long& b1,
+                                            const float* __restrict__ inv_sigma2 = nullptr, int n_levels = 0) {
   // frame.cc:684-712 cell range of the window
   int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
   int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
@@ -828,7 +829,19 @@ __device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, con
     const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
     if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
     if (skip && skip[i]) continue;
-    if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
+    if (inv_sigma2) {  // ORBmatcher::Fuse (orb_matcher.cc:1159-1178): reprojection error against the keypoint's level variance
+      const float ex = f_sub(Q.u, K.x), ey = f_sub(Q.v, K.y);
+      const float inv = inv_sigma2[K.octave < 0 ? 0 : (K.octave >= n_levels ? n_levels - 1 : K.octave)];
+      const float kr = kp_u_right ? kp_u_right[i] : -1.0f;
+      if (kr >= 0) {
+        const float er = f_sub(q_ur, kr);
+        const float e2 = f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(er, er));
+        if ((double)f_mul(e2, inv) > 7.8) continue;
+      } else {
+        const float e2 = f_add(f_mul(ex, ex), f_mul(ey, ey));
+        if ((double)f_mul(e2, inv) > 5.99) continue;
+      }
+    } else if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
       const float ur = kp_u_right[i];
       if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
     }
@@ -860,13 +873,14 @@ __global__ void __launch_bounds__(256) k_window_search(const orbx_kp* __restrict
                                                        const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                        const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                        const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
-                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out) {
+                                                       const float* __restrict__ q_max_err, orbm_window_result* __restrict__ out,
+                                                       const float* __restrict__ inv_sigma2, int n_levels) {
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (qi >= nq) return;
   const orbm_window_query Q = q[qi];
   unsigned long long b0, b1;
-  window_scan(kps, desc, n, g, Q, qdesc + 32 * (size_t)qi, skip, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
-              kp_u_right ? q_max_err[qi] : 0.f, lane, b0, b1);
+  window_scan(kps, desc, n, g, Q, qdesc + 32 * (size_t)qi, skip, kp_u_right, q_u_right ? q_u_right[qi] : 0.f,
+              q_max_err ? q_max_err[qi] : 0.f, lane, b0, b1, inv_sigma2, n_levels);
   if (lane == 0) out[qi] = window_result(kps, b0, b1);
 }
 
@@ -1020,9 +1034,10 @@ __global__ void __launch_bounds__(32) k_projection_claim_seq(const orbx_kp* __re
 
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                          const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
-                         const float* q_max_err, orbm_window_result* out, cudaStream_t st) {
+                         const float* q_max_err, orbm_window_result* out, cudaStream_t st, const float* inv_sigma2, int n_levels) {
   if (nq <= 0) return 0;
-  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out);
+  k_window_search<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, out, inv_sigma2,
+                                                n_levels);
   return 1;
 }
 

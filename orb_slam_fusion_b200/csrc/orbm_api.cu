@@ -312,21 +312,22 @@ int orbm_distinctive(orbm_t* m, const uint8_t* desc, const int32_t* offsets, int
   return end(m, mem, st);
 }
 
-int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
-                              const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
-                              const float* kp_u_right, const float* q_u_right, const float* q_max_err,
-                              orbm_window_result* out, int mem, void* stream) {
+static int window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                         const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                         const float* kp_u_right, const float* q_u_right, const float* q_max_err, const float* inv_sigma2,
+                         int n_levels, orbm_window_result* out, int mem, void* stream) {
   cudaStream_t st;
   TRY(begin(m, mem, stream, &st));
   if (n < 0 || nq < 0 || !geom || geom->cols < 1 || geom->rows < 1 || (int64_t)geom->cols * geom->rows >= (1 << 20) ||
       n >= (1 << 24) || (n > 0 && (!kps || !desc)) || (nq > 0 && (!queries || !qdesc || !out)) ||
-      (kp_u_right && nq > 0 && (!q_u_right || !q_max_err)))
+      (kp_u_right && nq > 0 && (!q_u_right || (!q_max_err && !inv_sigma2))) ||
+      (inv_sigma2 && (n_levels < 1 || n_levels > ORBX_MAX_LEVELS)))
     return fail(m, ORBX_E_ARG, "bad argument");
   if (nq == 0) return ORBX_OK;
   if (mem == ORBX_MEM_HOST)
     TRY(arena_reserve(m, pad256((size_t)n * 28) + pad256((size_t)n * 32) + pad256((size_t)nq * sizeof(orbm_window_query)) +
                              pad256((size_t)nq * 32) + pad256((size_t)n) + pad256((size_t)n * 4) + 2 * pad256((size_t)nq * 4) +
-                             pad256((size_t)nq * sizeof(orbm_window_result))));
+                             pad256((size_t)nq * sizeof(orbm_window_result)) + 256));
   const orbx_kp* dk;
   const uint8_t *dd, *dqd, *dskip;
   const orbm_window_query* dq;
@@ -339,12 +340,30 @@ int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc
   if (kp_u_right) {
     TRY(stage_in(m, mem, kp_u_right, (size_t)n, &dur, st));
     TRY(stage_in(m, mem, q_u_right, (size_t)nq, &dqr, st));
-    TRY(stage_in(m, mem, q_max_err, (size_t)nq, &dqe, st));
+    if (q_max_err) TRY(stage_in(m, mem, q_max_err, (size_t)nq, &dqe, st));
   }
+  const float* dis = nullptr;
+  if (inv_sigma2) TRY(stage_in(m, mem, inv_sigma2, (size_t)n_levels, &dis, st));
   orbm_window_result* dout = stage_out(m, mem, out, (size_t)nq);
-  m->launches += launch_window_search(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, dout, st);
+  m->launches += launch_window_search(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, dout, st, dis, n_levels);
   TRY(finish_out(m, mem, out, dout, (size_t)nq, st));
   return end(m, mem, st);
+}
+
+int orbm_window_search_stereo(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                              const orbm_window_query* queries, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                              const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                              orbm_window_result* out, int mem, void* stream) {
+  return window_search(m, kps, desc, n, geom, queries, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, nullptr, 0, out, mem, stream);
+}
+
+int orbm_window_search_fuse(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,
+                            const orbm_window_query* queries, const uint8_t* qdesc, int nq, const float* kp_u_right,
+                            const float* q_u_right, const float* inv_level_sigma2, int n_levels, orbm_window_result* out,
+                            int mem, void* stream) {
+  if (!inv_level_sigma2) return m ? fail(m, ORBX_E_ARG, "inv_level_sigma2 is required") : ORBX_E_ARG;
+  return window_search(m, kps, desc, n, geom, queries, qdesc, nq, nullptr, kp_u_right, q_u_right, nullptr, inv_level_sigma2, n_levels,
+                       out, mem, stream);
 }
 
 int orbm_window_search(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, int n, const orbm_grid_geom* geom,

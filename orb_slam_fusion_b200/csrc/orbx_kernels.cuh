@@ -75,7 +75,7 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
 int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom,
                          const orbm_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
                          const float* kp_u_right, const float* q_u_right, const float* q_max_err,
-                         orbm_window_result* out, cudaStream_t st);
+                         orbm_window_result* out, cudaStream_t st, const float* inv_sigma2 = nullptr, int n_levels = 0);  // inv_sigma2: the chi-square gate of ORBmatcher::Fuse
 int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
                          const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, const int32_t* best_idx,
                          const int32_t* best_dist, int th_orb_dist, float min_d, float max_d, float bf, float* u_right,

@@ -164,6 +164,24 @@ class ORBmatcher:
                                                bm.ctypes.data, A.MEM_HOST, None))
         return bi, bm
 
+    def window_search_fuse(self, kps, desc, geom, queries, qdesc, inv_level_sigma2, kp_u_right=None, q_u_right=None):
+        """The search of ORBmatcher::Fuse (orb_matcher.cc:1130-1187): nearest keypoint per projected map point under the
+        chi-square reprojection gate (7.8 with a right coordinate, 5.99 without)."""
+        kps = np.ascontiguousarray(kps, A.KP_DTYPE)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        queries = np.ascontiguousarray(queries, A.WQ_DTYPE)
+        qdesc = np.ascontiguousarray(qdesc, np.uint8)
+        inv = np.ascontiguousarray(inv_level_sigma2, np.float32)
+        ur = qr = None
+        if kp_u_right is not None:
+            ur, qr = np.ascontiguousarray(kp_u_right, np.float32), np.ascontiguousarray(q_u_right, np.float32)
+        out = np.empty(len(queries), A.WR_DTYPE)
+        g = A.GridGeom(*geom)
+        self._check(self._lib.orbm_window_search_fuse(self._m, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(g), queries.ctypes.data,
+                                                      qdesc.ctypes.data, len(queries), A.ptr(ur), A.ptr(qr), inv.ctypes.data, len(inv),
+                                                      out.ctypes.data, A.MEM_HOST, None))
+        return out
+
     def SearchByProjection(self, kps, desc, geom, queries, qdesc, skip=None, kp_u_right=None, q_u_right=None, q_max_err=None,
                            th_high=None, nnratio=None):
         """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, ...) (orb_matcher.cc:42-134, Nleft == -1)

@@ -480,3 +480,19 @@ def test_search_for_triangulation(P, m, oracle):
             assert nm[p] == wnm and np.array_equal(match[p, :npf[a]], want), (levelsup, p)
             assert (match[p, npf[a]:] == -1).all()
         assert nm[0] > (8 if only_stereo else 25) and nm[6] < nm[0]
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False)])
+def test_window_search_fuse(P, m, oracle, seed, stereo):
+    """The search of ORBmatcher::Fuse (orb_matcher.cc:1130-1187) on the device vs the oracle and the reference's own loop."""
+    from oracle import ref as R
+    from test_oracle_vs_ref_frame import fuse_case, W, H
+    kps, desc, q, qdesc, qur, lev, u_right, inv_s2 = fuse_case(oracle, seed, nq=1200)
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    got = m.window_search_fuse(kps, desc, geom, q, qdesc, inv_s2, u_right if stereo else None, qur if stereo else None)
+    want = oracle.window_search_fuse(kps, desc, geom, q, qdesc, inv_s2, u_right if stereo else None, qur if stereo else None)
+    assert got.tobytes() == want.tobytes() and (want["best_idx"] >= 0).mean() > 0.3
+    if R.frame_available():
+        wi, wd = R.fuse_search(kps, desc, (0.0, float(W), 0.0, float(H)), inv_s2, q["u"], q["v"], qur, q["r"], lev, qdesc,
+                               u_right if stereo else None)
+        assert np.array_equal(got["best_idx"], wi) and np.array_equal(got["best_dist"], wd)

@@ -314,3 +314,36 @@ def test_search_for_triangulation_identical(oracle, seed, shift, only_stereo, co
     assert nm == want_nm and np.array_equal(got, want)
     assert want_nm > (10 if only_stereo else 25)
     assert (got[hp1 != 0] == -1).all() and (hp2[got[got >= 0]] == 0).all()
+
+
+def fuse_case(oracle, seed, nq=700):
+    img = oracle.blocks_v1(W, H, seed, 0)
+    _, kps, desc = oracle.Extractor(1000)(img)
+    rng = np.random.default_rng(seed + 900)
+    src = rng.integers(0, len(kps), nq)
+    t = oracle.Extractor(1000).tables()
+    lev = np.clip(kps["octave"][src] + rng.integers(-1, 2, nq), 0, 7).astype(np.int32)
+    q = np.zeros(nq, oracle.WQ_DTYPE)
+    q["u"] = kps["x"][src] + rng.normal(0, 2.5, nq).astype(np.float32)     # chi-square gate: some pass, some do not
+    q["v"] = kps["y"][src] + rng.normal(0, 2.5, nq).astype(np.float32)
+    q["r"] = (np.float32(3.0) * t["scale"][lev]).astype(np.float32)
+    q["min_level"], q["max_level"] = lev - 1, lev
+    u_right = np.where(rng.random(len(kps)) < 0.5, kps["x"] - rng.uniform(1, 40, len(kps)), -1.0).astype(np.float32)
+    qur = np.where(u_right[src] >= 0, u_right[src] + rng.normal(0, 2.0, nq), q["u"] - 20).astype(np.float32)
+    qdesc = desc[src].copy()
+    flips = rng.integers(0, 256, (nq, 14))
+    for j in range(14):
+        qdesc[np.arange(nq), flips[:, j] // 8] ^= (1 << (flips[:, j] % 8)).astype(np.uint8)
+    return kps, desc, q, qdesc, qur, lev, u_right, t["inv_sigma2"]
+
+
+@pytest.mark.parametrize("seed,stereo", [(1, True), (2, False), (3, True)])
+def test_fuse_search_identical(oracle, seed, stereo):
+    """The candidate loop of ORBmatcher::Fuse (orb_matcher.cc:1145-1190): level gate, chi-square reprojection gate, nearest."""
+    kps, desc, q, qdesc, qur, lev, u_right, inv_s2 = fuse_case(oracle, seed)
+    bounds = (0.0, float(W), 0.0, float(H))
+    geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+    wi, wd = R.fuse_search(kps, desc, bounds, inv_s2, q["u"], q["v"], qur, q["r"], lev, qdesc, u_right if stereo else None)
+    got = oracle.window_search_fuse(kps, desc, geom, q, qdesc, inv_s2, u_right if stereo else None, qur if stereo else None)
+    assert np.array_equal(got["best_idx"], wi) and np.array_equal(got["best_dist"], wd)
+    assert (wi >= 0).mean() > 0.3 and (wi < 0).mean() > 0.05
