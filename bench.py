@@ -394,6 +394,44 @@ def run_ours(args):
                          "frac_of_popc_roofline": 8 * pairs_per_s / (world * popc),
                          "frac_of_plain_distance_peak": pairs_per_s / (world * plain)})
 
+    # ---- the tracker's projection matchers as whole calls (host buffers through the C ABI, like the reference's call sites):
+    # SearchByProjection(Frame&, vector<MapPoint*>&) and SearchByProjection(CurrentFrame, LastFrame) on one frame of the batch,
+    # one window per keypoint (a 3-px-off projection of the keypoint itself), rank 0
+    if rank == 0:
+        n0 = int(n_host[0])
+        k0 = kps[0, :n0].cpu().numpy().view(P.KP_DTYPE).reshape(-1)
+        d0 = desc[0, :n0].cpu().numpy()
+        rng = np.random.default_rng(0)
+        sfac = np.float32(SCALE) ** np.arange(NLEV, dtype=np.float32)
+        qw = np.zeros(n0, P.WQ_DTYPE)
+        qw["u"] = k0["x"] + rng.normal(0, 3, n0).astype(np.float32)
+        qw["v"] = k0["y"] + rng.normal(0, 3, n0).astype(np.float32)
+        qw["r"] = (np.float32(4.0 * 3.0) * sfac[np.clip(k0["octave"], 0, NLEV - 1)]).astype(np.float32)
+        qw["min_level"], qw["max_level"] = k0["octave"] - 1, k0["octave"]
+        geom = (0.0, 0.0, np.float32(64) / np.float32(W), np.float32(48) / np.float32(H), 64, 48)
+
+        def p50_us(fn, reps=200):
+            for _ in range(20):
+                fn()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return 1e6 * float(np.median(ts))
+
+        nm_a, _ = m.SearchByProjection(k0, d0, geom, qw, d0, None, None, None, None, 100, 0.8)
+        nm_b, _ = m.SearchByProjectionLast(k0, d0, geom, qw, d0, k0["angle"], None, None, None, None, 100, True)
+        matching["tracker"] = {
+            "keypoints": n0, "windows": n0,
+            "search_by_projection_us": p50_us(lambda: m.SearchByProjection(k0, d0, geom, qw, d0, None, None, None, None, 100, 0.8)),
+            "search_by_projection_matches": int(nm_a),
+            "search_by_projection_last_frame_us": p50_us(lambda: m.SearchByProjectionLast(k0, d0, geom, qw, d0, k0["angle"], None, None,
+                                                                                          None, None, 100, True)),
+            "search_by_projection_last_frame_matches": int(nm_b),
+            "what": "p50 of one blocking whole-function call through the C ABI with host buffers (window search + greedy claim "
+                    "[+ rotation histogram]), orb_matcher.cc:42-134 and :1518-1728 after the projection"}
+
     # ---- bag of words: Frame::ComputeBoW over this rank's batch of extracted descriptors,
     # ORBvoc-shaped synthetic vocabulary (k=10, L=6), device-resident, frames sharded like the extraction
     del db, q
