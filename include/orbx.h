@@ -278,7 +278,7 @@ int orbm_window_search_fuse(orbm_t* m, const orbx_kp* kps, const uint8_t* desc, 
  * already hold a map point with observations when the call starts (:86-87); kp_u_right / q_u_right / q_max_err as in
  * orbm_window_search_stereo (:89-92).  The map points are taken to have observations (true for the tracker's local map
  * points), so a keypoint claimed by an earlier query is skipped by the later ones, exactly as the reference's loop does:
- * a first kernel finds the four best keypoints of every window against the initial state, a second walks the queries in
+ * a first kernel finds the eight best keypoints of every window against the initial state, a second walks the queries in
  * order, drops the keypoints claimed in the meantime from those lists and re-scans a window only when fewer than two
  * of a full list survive.  Accept rule (:117-121):
  * best_dist <= th_high (TH_HIGH = 100) and not (best_level == best_level2 and best_dist > nnratio * best_dist2).

@@ -895,13 +895,14 @@ __device__ __forceinline__ void cmpex(unsigned long long& a, unsigned long long&
   b = hi;
 }
 
-// The four smallest keys of a window (sorted), lanes over the keypoints.  `bitmap` (may be NULL): keypoints claimed by
+// The KL (4 or 8) smallest keys of a window (sorted), lanes over the keypoints.  `bitmap` (may be NULL): keypoints claimed by
 // earlier map points of the same call.
-__device__ __forceinline__ void window_top4(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+template <int KL>
+__device__ __forceinline__ void window_topk(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                             const orbm_grid_geom& g, const orbm_window_query& Q, const uint8_t* __restrict__ qd_row,
                                             const uint8_t* __restrict__ skip, const uint32_t* bitmap,
                                             const float* __restrict__ kp_u_right, float q_ur, float q_err, int lane,
-                                            unsigned long long (&k)[4]) {
+                                            unsigned long long (&k)[KL], const uint32_t* cellinfo = nullptr) {
   int c0x = (int)floorf(f_mul(f_sub(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
   int c1x = (int)ceilf(f_mul(f_add(f_sub(Q.u, g.min_x), Q.r), g.inv_w));
   int c0y = (int)floorf(f_mul(f_sub(f_sub(Q.v, g.min_y), Q.r), g.inv_h));
@@ -913,11 +914,17 @@ __device__ __forceinline__ void window_top4(const orbx_kp* __restrict__ kps, con
   const bool ok = !(c0x >= g.cols || c1x < 0 || c0y >= g.rows || c1y < 0);
   const bool check_levels = Q.min_level >= 0 || Q.max_level >= 0;
 #pragma unroll
-  for (int j = 0; j < 4; j++) k[j] = ~0ull;
+  for (int j = 0; j < KL; j++) k[j] = ~0ull;
   if (!ok) return;  // warp-uniform
   uint32_t qd[8];
   load_row_any(qd_row, qd);
   for (int i = lane; i < n; i += 32) {
+    if (cellinfo) {  // (valid << 31 | px << 10 | py) of every keypoint, computed once per call: most keypoints end here
+      const uint32_t ci = cellinfo[i];
+      const int cpx = (int)((ci >> 10) & 0x3FFu), cpy = (int)(ci & 0x3FFu);
+      if (!(ci >> 31) || cpx < c0x || cpx > c1x || cpy < c0y || cpy > c1y) continue;
+      if ((bitmap[i >> 5] >> (i & 31)) & 1u) continue;
+    }
     const orbx_kp K = kps[i];
     const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
     const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
@@ -939,33 +946,38 @@ __device__ __forceinline__ void window_top4(const orbx_kp* __restrict__ kps, con
     load_row_any(desc + 32 * (size_t)i, kd);
     unsigned long long key = claim_key(ham256(qd, kd), px * g.rows + py, i, K.octave);
 #pragma unroll
-    for (int j = 0; j < 4; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the five falls out
+    for (int j = 0; j < KL; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the KL + 1 falls out
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t[4];
+    unsigned long long t[KL];
 #pragma unroll
-    for (int j = 0; j < 4; j++) t[j] = __shfl_xor_sync(0xffffffffu, k[3 - j], o);  // the partner's list, reversed
+    for (int j = 0; j < KL; j++) t[j] = __shfl_xor_sync(0xffffffffu, k[KL - 1 - j], o);  // the partner's list, reversed
 #pragma unroll
-    for (int j = 0; j < 4; j++) k[j] = min(k[j], t[j]);  // the four smallest of the union (a bitonic sequence)
-    cmpex(k[0], k[2]);
-    cmpex(k[1], k[3]);
-    cmpex(k[0], k[1]);
-    cmpex(k[2], k[3]);
+    for (int j = 0; j < KL; j++) k[j] = min(k[j], t[j]);  // the KL smallest of the union (a bitonic sequence)
+#pragma unroll
+    for (int d = KL / 2; d > 0; d >>= 1)  // bitonic merge: sorted again
+#pragma unroll
+      for (int j = 0; j < KL; j++)
+        if ((j & d) == 0) cmpex(k[j], k[j | d]);
   }
 }
 
-__global__ void __launch_bounds__(256) k_window_top4(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
+template <int KL>
+__global__ void __launch_bounds__(256) k_window_topk(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                      const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                      const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                      const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
                                                      const float* __restrict__ q_max_err, unsigned long long* __restrict__ keys4) {
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (qi >= nq) return;
-  unsigned long long k[4];
-  window_top4(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
-              kp_u_right ? q_max_err[qi] : 0.f, lane, k);
-  if (lane < 4) keys4[4 * (size_t)qi + lane] = lane == 0 ? k[0] : lane == 1 ? k[1] : lane == 2 ? k[2] : k[3];
+  unsigned long long k[KL];
+  window_topk<KL>(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+                  kp_u_right ? q_max_err[qi] : 0.f, lane, k);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < KL; j++) keys4[KL * (size_t)qi + j] = k[j];
+  }
 }
 
 // The greedy claim (:86-87, :117-121), exact: one warp walks the map points IN ORDER.  The four best keypoints of every
@@ -1010,8 +1022,8 @@ __global__ void __launch_bounds__(32) k_projection_claim_seq(const orbx_kp* __re
       const int qi = base + j;
       if (survivors < 2 && full) {  // the list may continue beyond its four entries (warp-uniform: every lane holds the same keys)
         unsigned long long k[4];
-        window_top4(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
-                    kp_u_right ? q_max_err[qi] : 0.f, lane, k);
+        window_topk<4>(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
+                       kp_u_right ? q_max_err[qi] : 0.f, lane, k);
         b0 = k[0];
         b1 = k[1];
       }
@@ -1052,34 +1064,45 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
 // LAST = true:  SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728, Nleft == -1): the best
 //               unclaimed keypoint within TH_HIGH is taken (:1596-1604), then the 30-bin rotation histogram between the
 //               last frame's keypoint angle (q_angle) and the claimed keypoint's keeps the three dominant bins (:1706-1725).
-template <bool LAST>
+template <bool LAST, int KL>
 __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                          const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                          const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                          const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
                                                          const float* __restrict__ q_max_err,
                                                          const unsigned long long* __restrict__ keys4, int th_high, float nnratio,
-                                                         const float* __restrict__ q_angle, int check_orientation,
+                                                         const float* __restrict__ q_angle, int check_orientation, int with_cells,
                                                          int32_t* __restrict__ assigned, int32_t* __restrict__ n_matches) {
-  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then lister[n]
+  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then lister[n + 32], then (with_cells) cellinfo[n]
   const int lane = threadIdx.x, words = (n + 31) / 32;
   uint32_t* lister = claim_bits + words;
-  for (int i = lane; i < n; i += 32) { assigned[i] = -1; lister[i] = 0; }
+  uint32_t* cellinfo = with_cells ? lister + n + 32 : nullptr;  // grid cell of every keypoint: re-scans reject most keypoints on one word
+  for (int i = lane; i < n; i += 32) {
+    assigned[i] = -1;
+    lister[i] = 0;
+    if (cellinfo) {
+      const int px = (int)roundf(f_mul(f_sub(kps[i].x, g.min_x), g.inv_w)), py = (int)roundf(f_mul(f_sub(kps[i].y, g.min_y), g.inv_h));
+      cellinfo[i] = (px < 0 || px >= g.cols || py < 0 || py >= g.rows) ? 0u : (0x80000000u | ((uint32_t)px << 10) | (uint32_t)py);
+    }
+  }
   for (int i = lane; i < words; i += 32) claim_bits[i] = 0;
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
   int nm = 0;
   for (int base = 0; base < nq; base += 32) {
     const int qi = base + lane;
-    unsigned long long k[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-    if (qi < nq) {
-      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)qi);
-      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(keys4 + 4 * (size_t)qi + 2);
-      k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
-    }
-    int idx[4];
+    unsigned long long k[KL];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
+    for (int e = 0; e < KL; e += 2) {
+      k[e] = k[e + 1] = ~0ull;
+      if (qi < nq) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys4 + KL * (size_t)qi + e);
+        k[e] = a.x; k[e + 1] = a.y;
+      }
+    }
+    int idx[KL];
+#pragma unroll
+    for (int e = 0; e < KL; e++) {
       idx[e] = k[e] == ~0ull ? -1 : (int)((k[e] >> 4) & 0xFFFFFFu);
       if (idx[e] >= 0) atomicOr(&lister[idx[e]], 1u << lane);
     }
@@ -1089,7 +1112,7 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       const bool mine = (undecided >> lane) & 1u;
       unsigned before = 0;
 #pragma unroll
-      for (int e = 0; e < 4; e++)
+      for (int e = 0; e < KL; e++)
         if (mine && idx[e] >= 0) before |= lister[idx[e]];
       unsigned ready = __ballot_sync(0xffffffffu, mine && (before & undecided & lt) == 0);
       // survivors of the list under the claims so far
@@ -1097,20 +1120,20 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       int survivors = 0;
       if ((ready >> lane) & 1u) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < KL; e++) {
           if (idx[e] < 0 || ((claim_bits[idx[e] >> 5] >> (idx[e] & 31)) & 1u)) continue;
           if (survivors == 0) b0 = k[e]; else if (survivors == 1) b1 = k[e];
           survivors++;
         }
       }
-      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[3] >= 0);
+      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[KL - 1] >= 0);
       if (rescan) {  // the first lane that must look beyond its list ends the round
         const int r = __ffs(rescan) - 1;
         ready &= (2u << r) - 1u;
         const int rq = base + r;
         unsigned long long t[4];
-        window_top4(kps, desc, n, g, q[rq], qdesc + 32 * (size_t)rq, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[rq] : 0.f,
-                    kp_u_right ? q_max_err[rq] : 0.f, lane, t);
+        window_topk<4>(kps, desc, n, g, q[rq], qdesc + 32 * (size_t)rq, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[rq] : 0.f,
+                       kp_u_right ? q_max_err[rq] : 0.f, lane, t, cellinfo);
         if (lane == r) { b0 = t[0]; b1 = t[1]; }
       }
       bool accept = false;
@@ -1129,7 +1152,7 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       __syncwarp();
     }
 #pragma unroll
-    for (int e = 0; e < 4; e++)
+    for (int e = 0; e < KL; e++)
       if (idx[e] >= 0) lister[idx[e]] = 0;
     __syncwarp();
   }
@@ -1173,31 +1196,38 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
   if (lane == 0) *n_matches = nm;
 }
 
-size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 4 * sizeof(unsigned long long); }
+size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 8 * sizeof(unsigned long long); }
 
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                                 const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
                                 bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st) {
-  unsigned long long* keys4 = static_cast<unsigned long long*>(scratch);
+  unsigned long long* keys = static_cast<unsigned long long*>(scratch);
+  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem0 = bits + (size_t)(n + 32) * sizeof(uint32_t);
+  const int with_cells = geom.cols <= 1024 && geom.rows <= 1024 && smem0 + (size_t)n * sizeof(uint32_t) <= 200 * 1024;
+  const size_t smem = smem0 + (with_cells ? (size_t)n * sizeof(uint32_t) : 0);
+  const char* force_seq = getenv("ORBM_CLAIM_SEQUENTIAL");  // test hook: the one-map-point-at-a-time kernel of very large frames
+  const bool sequential = !last_frame && (smem0 > 200 * 1024 || (force_seq && force_seq[0] == '1'));
+  // lists of 4 keypoints per window where one survivor decides (last-frame form, sequential fallback), of 8 where the ratio
+  // rule needs two: in dense frames most listed keypoints are claimed by the time a late window is decided
+  const bool k8 = !last_frame && !sequential;
   int launches = 1;
   if (nq > 0) {
-    k_window_top4<<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4);
+    if (k8) k_window_topk<8><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys);
+    else k_window_topk<4><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys);
     launches++;
   }
-  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem = bits + (size_t)(n + 32) * sizeof(uint32_t);
-  const char* force_seq = getenv("ORBM_CLAIM_SEQUENTIAL");  // test hook: the one-map-point-at-a-time kernel of very large frames
   if (last_frame) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_projection_claim<true><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
-                                                  nnratio, q_angle, check_orientation, assigned, n_matches);
-  } else if (smem <= 200 * 1024 && !(force_seq && force_seq[0] == '1')) {  // one word per keypoint in shared memory (up to ~50 k keypoints)
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_projection_claim<false><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
-                                                   nnratio, nullptr, 0, assigned, n_matches);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_projection_claim<true, 4><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
+                                                     nnratio, q_angle, check_orientation, with_cells, assigned, n_matches);
+  } else if (!sequential) {  // one word per keypoint in shared memory (up to ~50 k keypoints)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_projection_claim<false, 8><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
+                                                      nnratio, nullptr, 0, with_cells, assigned, n_matches);
   } else {
     if (bits > 48 * 1024) cudaFuncSetAttribute(k_projection_claim_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bits);
-    k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys4, th_high,
+    k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
                                                 nnratio, assigned, n_matches);
   }
   return launches;
