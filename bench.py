@@ -293,7 +293,13 @@ def run_ours(args):
     e1.record()
     torch.cuda.synchronize()
     t_region1 = time.time()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms_local = e0.elapsed_time(e1)
+    ms = max_over_ranks(ms_local)
+    ms_ranks = [ms_local]
+    if world > 1:  # every rank's own device time: the reported value uses the slowest
+        tl = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(tl, torch.tensor([ms_local], dtype=torch.float64, device=dev))
+        ms_ranks = [float(t.item()) for t in tl]
     barrier()
     clocks.stop()
     clk = clocks.summary(t_region0, t_region1)
@@ -554,7 +560,8 @@ def run_ours(args):
 
     out = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [round(x / args.steps, 4) for x in ms_ranks],
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
                    "frames_per_step_per_gpu": B, "mean_keypoints_per_frame": mean_kp,
