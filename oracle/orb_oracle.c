@@ -718,20 +718,29 @@ void orc_window_search(const orc_kp* kps, const uint8_t* desc, int n, const orc_
   orc_window_search_stereo(kps, desc, n, g, q, qdesc, nq, skip, NULL, NULL, NULL, out);
 }
 
-static const float* g_fuse_inv_sigma2 = NULL; /* set only inside orc_window_search_fuse (test infrastructure, one thread) */
+static void window_search_impl(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                               const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                               const float* g_fuse_inv_sigma2 /* non-NULL: the chi-square gate of Fuse replaces the stereo gate */,
+                               orc_window_result* out);
 
 void orc_window_search_fuse(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g, const orc_window_query* q,
                             const uint8_t* qdesc, int nq, const float* kp_u_right, const float* q_u_right,
                             const float* inv_level_sigma2, orc_window_result* out) {
-  g_fuse_inv_sigma2 = inv_level_sigma2;
-  orc_window_search_stereo(kps, desc, n, g, q, qdesc, nq, NULL, kp_u_right, q_u_right, NULL, out);
-  g_fuse_inv_sigma2 = NULL;
+  window_search_impl(kps, desc, n, g, q, qdesc, nq, NULL, kp_u_right, q_u_right, NULL, inv_level_sigma2, out);
 }
 
 void orc_window_search_stereo(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
                               const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
                               orc_window_result* out) {
+  window_search_impl(kps, desc, n, g, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, NULL, out);
+}
+
+static void window_search_impl(const orc_kp* kps, const uint8_t* desc, int n, const orc_grid_geom* g,
+                               const orc_window_query* q, const uint8_t* qdesc, int nq, const uint8_t* skip,
+                               const float* kp_u_right, const float* q_u_right, const float* q_max_err,
+                               const float* g_fuse_inv_sigma2, orc_window_result* out) {
   const int ncell = g->cols * g->rows;
   int* cnt = (int*)calloc((size_t)ncell + 1, sizeof(int));
   int* cell_of = (int*)malloc(sizeof(int) * (size_t)(n ? n : 1));
