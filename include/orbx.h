@@ -161,6 +161,10 @@ void orbm_destroy(orbm_t* m);
 const char* orbm_last_error(const orbm_t* m);
 int orbm_sync(orbm_t* m);
 long long orbm_launch_count(const orbm_t* m);
+/* Test / debug switches.  ORBM_OPT_CLAIM_SEQUENTIAL = 1: orbm_search_by_projection resolves the greedy claim one map
+ * point at a time (the kernel very large frames fall back to) instead of 32 at a time. */
+#define ORBM_OPT_CLAIM_SEQUENTIAL 1
+int orbm_set_option(orbm_t* m, int option, int value);
 
 /* ORBmatcher::DescriptorDistance (orb_matcher.cc:1877-1891) for n independent pairs:
  * out[i] = popcount(a[i] xor b[i]) over 256 bits. */
@@ -184,6 +188,33 @@ int orbm_top2_merge(orbm_t* m, const int64_t* idx_parts, const int32_t* dist_par
  * (float distances, double product). */
 int orbm_ratio_test(orbm_t* m, const int64_t* idx, const int32_t* dist, int nq, double ratio,
                     uint8_t* accept, int mem, void* stream);
+
+/* ---- the database sharded over the GPUs of one node (BASELINE config 5) ----
+ * The reference has no multi-GPU path; this is frame.cc:1154-1162 (knnMatch(k=2) + ratio) over a database whose
+ * rows are split into one contiguous slice per rank.  NCCL is bound at run time (the library does not link it): the
+ * process's own libnccl.so.2 if one is loaded, else the system's; ORBX_NCCL_LIB overrides.  A host that has no NCCL
+ * headers can bootstrap a communicator with the three helpers below and any channel that carries 128 bytes from
+ * rank 0 to the others (MPI, a file, torch.distributed); a host that already owns an ncclComm_t passes it as is. */
+#ifndef NCCL_H_
+typedef struct ncclComm* ncclComm_t; /* the same declaration as nccl.h:33 */
+#endif
+#define ORBM_NCCL_ID_BYTES 128 /* NCCL_UNIQUE_ID_BYTES */
+int orbm_nccl_unique_id(uint8_t id[ORBM_NCCL_ID_BYTES]);  /* ncclGetUniqueId, called on one rank */
+/* ncclCommInitRank on `device`; collective over the n_ranks callers */
+int orbm_nccl_comm_create(const uint8_t id[ORBM_NCCL_ID_BYTES], int n_ranks, int rank, int device, ncclComm_t* comm);
+int orbm_nccl_comm_destroy(ncclComm_t comm);
+int orbm_nccl_version(void); /* ncclGetVersion of the bound library, 0 if none can be loaded */
+
+/* Collective over the ranks of `comm`, same q / nq / ratio on every rank: rank r holds database rows
+ * [db_index_base, db_index_base + nd_local) in db_local.  Each rank finds its local top-2 per query (the kernel of
+ * orbm_knn2), packs them as 64-bit keys (distance << 40 | global row), ONE ncclAllGather of nq * 16 bytes per rank
+ * runs on the call's stream, and one kernel merges the gathered keys by their integer order -- the (distance, row)
+ * order of knnMatch, associative, hence bit-identical to orbm_knn2 over the whole database -- and applies the ratio
+ * test of frame.cc:1162.  Every rank receives the full result: idx / dist [nq][2] as orbm_knn2 (global rows),
+ * accept[nq] as orbm_ratio_test (may be NULL).  comm == NULL: a single rank (no NCCL needed).  Global rows < 2^40. */
+int orbm_knn2_sharded(orbm_t* m, ncclComm_t comm, const uint8_t* q, int nq, const uint8_t* db_local, int64_t nd_local,
+                      int64_t db_index_base, double ratio, int64_t* idx, int32_t* dist, uint8_t* accept, int mem,
+                      void* stream);
 
 /* Row-band stereo search of Frame::ComputeStereoMatches (frame.cc:836-900): for every left
  * keypoint the right keypoint of minimum distance among those whose row band

@@ -3,7 +3,7 @@ Hamming matching kernels and the bag-of-words transform) as hand-written sm_100a
 
 Only what the hot path needs lives here: csrc/ (kernels + C ABI) and the host-side mirror of the
 reference's OrbExtractor / ORBmatcher interface.  There is no CPU fallback."""
-from ._abi import KP_DTYPE, WQ_DTYPE, WR_DTYPE, OrbxError, LIB_PATH  # noqa: F401
+from ._abi import KP_DTYPE, WQ_DTYPE, WR_DTYPE, OrbxError, LIB_PATH, OPT_CLAIM_SEQUENTIAL  # noqa: F401
 from .orb_extractor import OrbExtractor, synth_frames  # noqa: F401
 from .orb_matcher import ORBmatcher, synth_descriptors, popc_peak  # noqa: F401
 from .orb_vocabulary import ORBVocabulary  # noqa: F401

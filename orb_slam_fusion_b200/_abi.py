@@ -16,6 +16,8 @@ OK, E_EMPTY, E_ARG, E_CAP, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -
 MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
 STAGE_LEVEL, STAGE_BLUR, STAGE_CAND, STAGE_SELECTED = 0, 1, 2, 3
 MAX_LEVELS = 16
+OPT_CLAIM_SEQUENTIAL = 1
+NCCL_ID_BYTES = 128
 EDGE = 19
 
 # cv::KeyPoint layout (28 bytes)
@@ -67,6 +69,12 @@ SIGNATURES = {
     "orbm_last_error": (C.c_char_p, [vp]),
     "orbm_sync": (i32, [vp]),
     "orbm_launch_count": (C.c_longlong, [vp]),
+    "orbm_set_option": (i32, [vp, i32, i32]),
+    "orbm_nccl_unique_id": (i32, [vp]),
+    "orbm_nccl_comm_create": (i32, [vp, i32, i32, i32, C.POINTER(vp)]),
+    "orbm_nccl_comm_destroy": (i32, [vp]),
+    "orbm_nccl_version": (i32, []),
+    "orbm_knn2_sharded": (i32, [vp, vp, vp, i32, vp, i64, i64, dbl, vp, vp, vp, i32, vp]),
     "orbm_hamming_pairs": (i32, [vp, vp, vp, i64, vp, i32, vp]),
     "orbm_knn2": (i32, [vp, vp, i32, vp, i64, i64, vp, vp, i32, vp]),
     "orbm_top2_merge": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, vp]),

@@ -62,15 +62,16 @@ int OrbExtractor::operator()(cv::InputArray img, cv::InputArray /*msk*/, std::ve
   assert(image.type() == CV_8UC1);  // :1019
   int cap = orbx_max_keypoints(handle_), n = 0, n_mono = 0;
   cv::Mat desc_buf;
+  int rc = ORBX_OK;
   for (int attempt = 0; attempt < 2; ++attempt) {
     kps.resize(cap);
     desc_buf.create(cap, 32, CV_8U);
-    const int rc = orbx_extract(handle_, image.data, image.cols, image.rows, image.step, lapping_areas[0], lapping_areas[1],
+    rc = orbx_extract(handle_, image.data, image.cols, image.rows, image.step, lapping_areas[0], lapping_areas[1],
                                 reinterpret_cast<orbx_kp*>(kps.data()), desc_buf.data, cap, &n, &n_mono);
     if (rc == ORBX_E_CAP) { cap = n; continue; }  // capacity grows once the image geometry is known
-    if (rc != ORBX_OK) throw std::runtime_error(orbx_last_error(handle_));
     break;
   }
+  if (rc != ORBX_OK) throw std::runtime_error(orbx_last_error(handle_));  // includes a second ORBX_E_CAP
   kps.resize(n);
   if (n == 0) {
     descs.release();  // :1033-1034

@@ -209,6 +209,68 @@ int launch_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t
   return 2;
 }
 
+// ------------------------------------------------------------------ database sharded over GPUs
+// Every rank scans its row slice; its top-2 per query leave as two packed 64-bit keys (distance << 40 | GLOBAL row, ~0 =
+// missing), so ONE all-gather of nq x 16 bytes per rank carries everything, and the integer order of the keys is the
+// (distance, row) order of knnMatch -- the merge over ranks is a min / second-min, associative and therefore bit-identical
+// to the search of the whole database on one GPU.
+__global__ void __launch_bounds__(128) k_knn2_merge_keys(const unsigned long long* __restrict__ partial, int n_chunks, int nq,
+                                                         int64_t index_base, unsigned long long* __restrict__ keys) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  for (int c = 0; c < n_chunks; c++) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(partial + ((size_t)c * nq + qi) * 2);
+    b1 = min(b1, max(b0, v.x));
+    b0 = min(b0, v.x);
+    b1 = min(b1, v.y);  // v.y >= v.x
+  }
+  // the row field of a partial key is local to the slice: adding the base cannot carry into the distance (rows < 2^40)
+  if (b0 != ~0ull) b0 += (unsigned long long)index_base;
+  if (b1 != ~0ull) b1 += (unsigned long long)index_base;
+  *reinterpret_cast<ulonglong2*>(keys + 2 * (size_t)qi) = make_ulonglong2(b0, b1);
+}
+
+// merge of the gathered keys [n_parts][nq][2] + the ratio test of frame.cc:1162, one thread per query
+__global__ void __launch_bounds__(128) k_top2_keys_ratio(const unsigned long long* __restrict__ keys, int n_parts, int nq, double ratio,
+                                                         int64_t* __restrict__ idx, int32_t* __restrict__ dist,
+                                                         uint8_t* __restrict__ accept) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long b0 = ~0ull, b1 = ~0ull;
+  for (int p = 0; p < n_parts; p++) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(keys + ((size_t)p * nq + qi) * 2);
+    b1 = min(b1, max(b0, v.x));
+    b0 = min(b0, v.x);
+    b1 = min(b1, v.y);
+  }
+  const unsigned long long mask = (1ull << kPartShift) - 1;
+  const int32_t d0 = b0 == ~0ull ? INT_MAX : (int32_t)(b0 >> kPartShift), d1 = b1 == ~0ull ? INT_MAX : (int32_t)(b1 >> kPartShift);
+  idx[2 * qi] = b0 == ~0ull ? -1 : (int64_t)(b0 & mask);
+  idx[2 * qi + 1] = b1 == ~0ull ? -1 : (int64_t)(b1 & mask);
+  dist[2 * qi] = d0;
+  dist[2 * qi + 1] = d1;
+  if (accept) accept[qi] = b0 != ~0ull && b1 != ~0ull && ((double)(float)d0 < __dmul_rn((double)(float)d1, ratio));
+}
+
+int launch_knn2_keys(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t index_base, void* partials,
+                     unsigned long long* keys, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  int64_t rows;
+  const int chunks = knn2_chunks(nd, &rows);
+  dim3 grid(chunks, (nq + kKnnQBlock - 1) / kKnnQBlock);
+  k_knn2<<<grid, kKnnThreads, 0, st>>>(q, nq, db, nd, rows, reinterpret_cast<unsigned long long*>(partials));
+  k_knn2_merge_keys<<<(nq + 127) / 128, 128, 0, st>>>(reinterpret_cast<const unsigned long long*>(partials), chunks, nq, index_base, keys);
+  return 2;
+}
+
+int launch_top2_keys_ratio(const unsigned long long* keys, int n_parts, int nq, double ratio, int64_t* idx, int32_t* dist,
+                           uint8_t* accept, cudaStream_t st) {
+  if (nq <= 0) return 0;
+  k_top2_keys_ratio<<<(nq + 127) / 128, 128, 0, st>>>(keys, n_parts, nq, ratio, idx, dist, accept);
+  return 1;
+}
+
 // ------------------------------------------------------------------ merge of sharded top-2 lists
 __device__ __forceinline__ bool key_less(int32_t da, int64_t ia, int32_t db_, int64_t ib) {
   // missing entries (idx < 0) sort last; otherwise (distance, index) ascending
@@ -1110,11 +1172,26 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
     unsigned undecided = __ballot_sync(0xffffffffu, qi < nq && idx[0] >= 0);  // an empty list decides nothing (:75)
     while (undecided) {
       const bool mine = (undecided >> lane) & 1u;
+      // `before`: earlier undecided lanes that list one of my keypoints.  `safe`: my listed keypoints that are unclaimed and
+      // that no earlier undecided lane lists -- nothing that precedes me in the reference's order can take those.
       unsigned before = 0;
+      int safe = 0;
 #pragma unroll
       for (int e = 0; e < KL; e++)
-        if (mine && idx[e] >= 0) before |= lister[idx[e]];
-      unsigned ready = __ballot_sync(0xffffffffu, mine && (before & undecided & lt) == 0);
+        if (mine && idx[e] >= 0) {
+          const unsigned l = lister[idx[e]] & undecided & lt;
+          before |= l;
+          if (l == 0 && !((claim_bits[idx[e] >> 5] >> (idx[e] & 31)) & 1u)) safe++;
+        }
+      // A lane with a full list and too few safe keypoints may have to scan its window again and can then claim a keypoint
+      // OUTSIDE its list, which the "who lists me" words know nothing about.  The lowest such lane is a barrier: no later
+      // lane decides before it (the keypoint it ends up with may be one of theirs), and it decides only as the lowest
+      // undecided lane of the batch, alone in its round, so its scan sees every claim that precedes it.  The lanes below
+      // the barrier all hold enough safe keypoints, claim inside their lists, and the list rule is exact for them.
+      const unsigned may_rescan = __ballot_sync(0xffffffffu, mine && idx[KL - 1] >= 0 && safe < (LAST ? 1 : 2));
+      const int barrier = may_rescan ? __ffs(may_rescan) - 1 : 32;
+      unsigned ready = __ballot_sync(0xffffffffu, mine && before == 0 && lane < barrier);
+      if (barrier < 32 && (undecided & ((1u << barrier) - 1u)) == 0) ready = 1u << barrier;
       // survivors of the list under the claims so far
       unsigned long long b0 = ~0ull, b1 = ~0ull;
       int survivors = 0;
@@ -1196,18 +1273,28 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
   if (lane == 0) *n_matches = nm;
 }
 
+// opt in to the dynamic shared memory of the claim kernels, once per device (orbm_create)
+cudaError_t projection_configure() {
+  const int cap = 200 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(k_projection_claim<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_projection_claim<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_projection_claim_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  return e;
+}
+
 size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 8 * sizeof(unsigned long long); }
 
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                                 const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
-                                bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st) {
+                                bool last_frame, bool force_sequential, void* scratch, int32_t* assigned, int32_t* n_matches,
+                                cudaStream_t st) {
   unsigned long long* keys = static_cast<unsigned long long*>(scratch);
   const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem0 = bits + (size_t)(n + 32) * sizeof(uint32_t);
   const int with_cells = geom.cols <= 1024 && geom.rows <= 1024 && smem0 + (size_t)n * sizeof(uint32_t) <= 200 * 1024;
   const size_t smem = smem0 + (with_cells ? (size_t)n * sizeof(uint32_t) : 0);
-  const char* force_seq = getenv("ORBM_CLAIM_SEQUENTIAL");  // test hook: the one-map-point-at-a-time kernel of very large frames
-  const bool sequential = !last_frame && (smem0 > 200 * 1024 || (force_seq && force_seq[0] == '1'));
+  // force_sequential (orbm_set_option, a test hook): the one-map-point-at-a-time kernel of very large frames
+  const bool sequential = !last_frame && (smem0 > 200 * 1024 || force_sequential);
   // lists of 4 keypoints per window where one survivor decides (last-frame form, sequential fallback), of 8 where the ratio
   // rule needs two: in dense frames most listed keypoints are claimed by the time a late window is decided
   const bool k8 = !last_frame && !sequential;
@@ -1218,15 +1305,12 @@ int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, 
     launches++;
   }
   if (last_frame) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_projection_claim<true, 4><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
                                                      nnratio, q_angle, check_orientation, with_cells, assigned, n_matches);
   } else if (!sequential) {  // one word per keypoint in shared memory (up to ~50 k keypoints)
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_projection_claim<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_projection_claim<false, 8><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
                                                       nnratio, nullptr, 0, with_cells, assigned, n_matches);
   } else {
-    if (bits > 48 * 1024) cudaFuncSetAttribute(k_projection_claim_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bits);
     k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
                                                 nnratio, assigned, n_matches);
   }

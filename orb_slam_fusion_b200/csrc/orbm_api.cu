@@ -6,6 +6,7 @@
 
 #include <new>
 
+#include "nccl_dl.cuh"
 #include "orbx_kernels.cuh"
 
 using namespace orbx;
@@ -17,6 +18,14 @@ struct orbm_matcher {
   size_t arena_bytes = 0, arena_used = 0;
   void* partials = nullptr;  // knn2 per-chunk top-2
   size_t partial_bytes = 0;
+  unsigned long long* keys = nullptr;  // sharded search: this rank's packed top-2, then the gathered keys of every rank
+  size_t key_bytes = 0;
+  // Handle-owned scratch (arena, partials, keys) is shared by every call: a call that runs on another stream than the
+  // previous one first waits for the event the previous call recorded behind its last use of the scratch.
+  cudaEvent_t busy_ev = nullptr;
+  cudaStream_t busy_stream = nullptr;
+  bool busy = false;
+  int claim_sequential = 0;  // ORBM_OPT_CLAIM_SEQUENTIAL
   long long launches = 0;
   char err[256] = "";
 };
@@ -42,7 +51,7 @@ int fail(orbm_t* m, int code, const char* fmt, ...) {
 int arena_reserve(orbm_t* m, size_t bytes) {
   m->arena_used = 0;
   if (bytes <= m->arena_bytes) return ORBX_OK;
-  CU(m, cudaStreamSynchronize(m->stream));
+  if (m->busy) CU(m, cudaEventSynchronize(m->busy_ev));  // the previous call, whatever stream it ran on, is done with the arena
   if (m->arena) cudaFree(m->arena);
   m->arena = nullptr;
   m->arena_bytes = 0;
@@ -87,10 +96,14 @@ int begin(orbm_t* m, int mem, void* stream, cudaStream_t* st) {
   if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) return fail(m, ORBX_E_ARG, "bad mem kind");
   CU(m, cudaSetDevice(m->device));
   *st = (mem == ORBX_MEM_DEVICE && stream) ? (cudaStream_t)stream : m->stream;
+  if (m->busy && m->busy_stream != *st) CU(m, cudaStreamWaitEvent(*st, m->busy_ev, 0));
   return ORBX_OK;
 }
 
 int end(orbm_t* m, int mem, cudaStream_t st) {
+  CU(m, cudaEventRecord(m->busy_ev, st));
+  m->busy_stream = st;
+  m->busy = true;
   if (mem == ORBX_MEM_HOST) CU(m, cudaStreamSynchronize(st));
   CU(m, cudaGetLastError());
   return ORBX_OK;
@@ -101,6 +114,19 @@ int end(orbm_t* m, int mem, cudaStream_t st) {
     const int rc_ = (x);      \
     if (rc_) return rc_;      \
   } while (0)
+
+// grow a handle-owned device buffer; the previous call (on whatever stream) must be done with the old one first
+int buffer_reserve(orbm_t* m, void** buf, size_t* have, size_t want) {
+  if (want <= *have) return ORBX_OK;
+  if (m->busy) CU(m, cudaEventSynchronize(m->busy_ev));
+  if (*buf) cudaFree(*buf);
+  *buf = nullptr;
+  *have = 0;
+  CU(m, cudaMalloc(buf, want));
+  *have = want;
+  return ORBX_OK;
+}
+int partials_reserve(orbm_t* m, size_t bytes) { return buffer_reserve(m, &m->partials, &m->partial_bytes, bytes); }
 
 }  // namespace
 
@@ -113,7 +139,10 @@ int orbm_create(int device, orbm_t** out) {
   orbm_t* m = new (std::nothrow) orbm_matcher();
   if (!m) return ORBX_E_NOMEM;
   m->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&m->busy_ev, cudaEventDisableTiming) != cudaSuccess || projection_configure() != cudaSuccess) {
+    if (m->busy_ev) cudaEventDestroy(m->busy_ev);
+    if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
     return ORBX_E_CUDA;
   }
@@ -125,8 +154,11 @@ void orbm_destroy(orbm_t* m) {
   if (!m) return;
   cudaSetDevice(m->device);
   cudaStreamSynchronize(m->stream);
+  if (m->busy) cudaEventSynchronize(m->busy_ev);
   if (m->arena) cudaFree(m->arena);
   if (m->partials) cudaFree(m->partials);
+  if (m->keys) cudaFree(m->keys);
+  cudaEventDestroy(m->busy_ev);
   cudaStreamDestroy(m->stream);
   delete m;
 }
@@ -141,6 +173,12 @@ int orbm_sync(orbm_t* m) {
 }
 
 long long orbm_launch_count(const orbm_t* m) { return m ? m->launches : 0; }
+
+int orbm_set_option(orbm_t* m, int option, int value) {
+  if (!m) return ORBX_E_ARG;
+  if (option == ORBM_OPT_CLAIM_SEQUENTIAL) { m->claim_sequential = value != 0; return ORBX_OK; }
+  return fail(m, ORBX_E_ARG, "unknown option %d", option);
+}
 
 int orbm_hamming_pairs(orbm_t* m, const uint8_t* a, const uint8_t* b, int64_t n, int32_t* out, int mem, void* stream) {
   cudaStream_t st;
@@ -164,15 +202,7 @@ int orbm_knn2(orbm_t* m, const uint8_t* q, int nq, const uint8_t* db, int64_t nd
   if (nq < 0 || nd < 0 || (nq > 0 && (!q || !idx || !dist)) || (nd > 0 && !db)) return fail(m, ORBX_E_ARG, "bad argument");
   if (nq == 0) return ORBX_OK;
   if (((uintptr_t)db & 15) != 0 && mem == ORBX_MEM_DEVICE) return fail(m, ORBX_E_ARG, "device database must be 16-byte aligned");
-  const size_t pb = knn2_partial_bytes(nq, nd);
-  if (pb > m->partial_bytes) {
-    CU(m, cudaStreamSynchronize(st));
-    if (m->partials) cudaFree(m->partials);
-    m->partials = nullptr;
-    m->partial_bytes = 0;
-    CU(m, cudaMalloc(&m->partials, pb));
-    m->partial_bytes = pb;
-  }
+  TRY(partials_reserve(m, knn2_partial_bytes(nq, nd)));
   if (mem == ORBX_MEM_HOST)
     TRY(arena_reserve(m, pad256((size_t)nq * 32) + pad256((size_t)nd * 32) + pad256((size_t)nq * 16) + pad256((size_t)nq * 8)));
   const uint8_t *dq, *ddb;
@@ -221,6 +251,88 @@ int orbm_ratio_test(orbm_t* m, const int64_t* idx, const int32_t* dist, int nq, 
   uint8_t* dacc = stage_out(m, mem, accept, (size_t)nq);
   m->launches += launch_ratio_test(di, dd, nq, ratio, dacc, st);
   TRY(finish_out(m, mem, accept, dacc, (size_t)nq, st));
+  return end(m, mem, st);
+}
+
+/* ---- database sharded over the GPUs of one node ---- */
+
+int orbm_nccl_unique_id(uint8_t id[ORBM_NCCL_ID_BYTES]) {
+  const NcclApi* nc = nccl_api(nullptr);
+  if (!nc || !id) return nc ? ORBX_E_ARG : ORBX_E_UNSUPPORTED;
+  static_assert(sizeof(NcclUniqueId) == ORBM_NCCL_ID_BYTES, "ncclUniqueId is 128 bytes");
+  NcclUniqueId u;
+  if (nc->GetUniqueId(&u) != 0) return ORBX_E_CUDA;
+  memcpy(id, &u, sizeof(u));
+  return ORBX_OK;
+}
+
+int orbm_nccl_comm_create(const uint8_t id[ORBM_NCCL_ID_BYTES], int n_ranks, int rank, int device, ncclComm_t* comm) {
+  const NcclApi* nc = nccl_api(nullptr);
+  if (!nc) return ORBX_E_UNSUPPORTED;
+  if (!id || !comm || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ORBX_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return ORBX_E_CUDA;
+  NcclUniqueId u;
+  memcpy(&u, id, sizeof(u));
+  void* c = nullptr;
+  if (nc->CommInitRank(&c, n_ranks, u, rank) != 0) return ORBX_E_CUDA;
+  *comm = (ncclComm_t)c;
+  return ORBX_OK;
+}
+
+int orbm_nccl_comm_destroy(ncclComm_t comm) {
+  const NcclApi* nc = nccl_api(nullptr);
+  if (!nc) return ORBX_E_UNSUPPORTED;
+  return comm && nc->CommDestroy((void*)comm) != 0 ? ORBX_E_CUDA : ORBX_OK;
+}
+
+int orbm_nccl_version(void) {
+  const NcclApi* nc = nccl_api(nullptr);
+  int v = 0;
+  return nc && nc->GetVersion(&v) == 0 ? v : 0;
+}
+
+int orbm_knn2_sharded(orbm_t* m, ncclComm_t comm, const uint8_t* q, int nq, const uint8_t* db_local, int64_t nd_local,
+                      int64_t db_index_base, double ratio, int64_t* idx, int32_t* dist, uint8_t* accept, int mem, void* stream) {
+  cudaStream_t st;
+  TRY(begin(m, mem, stream, &st));
+  if (nq < 0 || nd_local < 0 || db_index_base < 0 || db_index_base + nd_local >= ((int64_t)1 << 40) ||
+      (nq > 0 && (!q || !idx || !dist)) || (nd_local > 0 && !db_local))
+    return fail(m, ORBX_E_ARG, "bad argument");
+  if (((uintptr_t)db_local & 15) != 0 && mem == ORBX_MEM_DEVICE) return fail(m, ORBX_E_ARG, "device database must be 16-byte aligned");
+  int n_ranks = 1;
+  const NcclApi* nc = nullptr;
+  if (comm) {
+    const char* why = "";
+    nc = nccl_api(&why);
+    if (!nc) return fail(m, ORBX_E_UNSUPPORTED, "%s", why);
+    const int rc = nc->CommCount((void*)comm, &n_ranks);
+    if (rc != 0 || n_ranks < 1) return fail(m, ORBX_E_ARG, "ncclCommCount: %s", nc->GetErrorString(rc));
+  }
+  if (nq == 0) return ORBX_OK;  // every rank passes the same nq, so no rank waits in the collective
+  TRY(partials_reserve(m, knn2_partial_bytes(nq, nd_local)));
+  const size_t key_count = (size_t)nq * 2;
+  TRY(buffer_reserve(m, (void**)&m->keys, &m->key_bytes, (size_t)(n_ranks + 1) * key_count * sizeof(unsigned long long)));
+  if (mem == ORBX_MEM_HOST)
+    TRY(arena_reserve(m, pad256((size_t)nq * 32) + pad256((size_t)nd_local * 32) + pad256((size_t)nq * 16) + pad256((size_t)nq * 8) +
+                             pad256((size_t)nq)));
+  const uint8_t *dq, *ddb;
+  TRY(stage_in(m, mem, q, (size_t)nq * 32, &dq, st));
+  TRY(stage_in(m, mem, db_local, (size_t)nd_local * 32, &ddb, st));
+  int64_t* didx = stage_out(m, mem, idx, (size_t)nq * 2);
+  int32_t* ddist = stage_out(m, mem, dist, (size_t)nq * 2);
+  uint8_t* dacc = accept ? stage_out(m, mem, accept, (size_t)nq) : nullptr;
+  unsigned long long* mine = m->keys;                // [nq][2]
+  unsigned long long* all = m->keys + key_count;     // [n_ranks][nq][2]
+  m->launches += launch_knn2_keys(dq, nq, ddb, nd_local, db_index_base, m->partials, n_ranks > 1 ? mine : all, st);
+  if (n_ranks > 1) {
+    // the one exchange step of the path: 16 bytes per query and rank, on the stream the kernels run on
+    const int rc = nc->AllGather(mine, all, key_count, kNcclUint64, (void*)comm, st);
+    if (rc != 0) return fail(m, ORBX_E_CUDA, "ncclAllGather: %s", nc->GetErrorString(rc));
+  }
+  m->launches += launch_top2_keys_ratio(all, n_ranks, nq, ratio, didx, ddist, dacc, st);
+  TRY(finish_out(m, mem, idx, didx, (size_t)nq * 2, st));
+  TRY(finish_out(m, mem, dist, ddist, (size_t)nq * 2, st));
+  if (accept) TRY(finish_out(m, mem, accept, dacc, (size_t)nq, st));
   return end(m, mem, st);
 }
 
@@ -278,8 +390,14 @@ int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const
   float* dur = stage_out(m, mem, u_right, (size_t)nl);
   float* ddp = stage_out(m, mem, depth, (size_t)nl);
   int32_t* dsad = stage_out(m, mem, sad, (size_t)nl);
+  // the pyramids belong to the extractors: read them after the extractors' last kernels, and let the extractors' next
+  // frame wait for this read
+  CU(m, orbx_pyramid_acquire(left, st));
+  CU(m, orbx_pyramid_acquire(right, st));
   m->launches += launch_stereo_refine(gl, pl, gr, pr, sf, isf, dkl, nl, dkr, dbi, dbd, th_orb_dist, min_d, max_d, bf, dur, ddp,
                                       dsad, st);
+  CU(m, orbx_pyramid_release(left, st));
+  if (right != left) CU(m, orbx_pyramid_release(right, st));
   TRY(finish_out(m, mem, u_right, dur, (size_t)nl, st));
   TRY(finish_out(m, mem, depth, ddp, (size_t)nl, st));
   TRY(finish_out(m, mem, sad, dsad, (size_t)nl, st));
@@ -413,7 +531,7 @@ static int search_by_projection(bool last_frame, const float* q_angle, int check
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)1);
   void* dscratch = arena_take<uint8_t>(m, projection_scratch_bytes(nq));
   m->launches += launch_search_by_projection(dk, dd, n, *geom, dq, dqd, nq, dskip, dur, dqr, dqe, th_high, nnratio, dqa,
-                                             check_orientation, last_frame, dscratch, dassigned, dnm, st);
+                                             check_orientation, last_frame, m->claim_sequential != 0, dscratch, dassigned, dnm, st);
   TRY(finish_out(m, mem, assigned, dassigned, (size_t)n, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)1, st));
   return end(m, mem, st);

@@ -22,6 +22,11 @@ struct orbv_vocab {
   std::vector<void*> allocs;
   uint8_t* arena = nullptr;  // staging of host-memory calls + per-feature scratch
   size_t arena_bytes = 0, arena_used = 0;
+  // the arena is shared by every call: a call on another stream than the previous one waits for the event the
+  // previous call recorded behind its last use of it
+  cudaEvent_t busy_ev = nullptr;
+  cudaStream_t busy_stream = nullptr;
+  bool busy = false;
   long long launches = 0;
   char err[256] = "";
 };
@@ -54,7 +59,7 @@ size_t pad256(size_t b) { return (b + 255) / 256 * 256; }
 int arena_reserve(orbv_t* v, size_t bytes) {
   v->arena_used = 0;
   if (bytes <= v->arena_bytes) return ORBX_OK;
-  CU(v, cudaStreamSynchronize(v->stream));
+  if (v->busy) CU(v, cudaEventSynchronize(v->busy_ev));
   if (v->arena) cudaFree(v->arena);
   v->arena = nullptr;
   v->arena_bytes = 0;
@@ -137,10 +142,15 @@ int begin(orbv_t* v, int mem, void* stream, cudaStream_t* st) {
   if (mem != ORBX_MEM_HOST && mem != ORBX_MEM_DEVICE) return fail(v, ORBX_E_ARG, "bad mem kind");
   CU(v, cudaSetDevice(v->device));
   *st = (mem == ORBX_MEM_DEVICE && stream) ? (cudaStream_t)stream : v->stream;
+  if (!v->busy_ev) CU(v, cudaEventCreateWithFlags(&v->busy_ev, cudaEventDisableTiming));
+  if (v->busy && v->busy_stream != *st) CU(v, cudaStreamWaitEvent(*st, v->busy_ev, 0));
   return ORBX_OK;
 }
 
 int end(orbv_t* v, int mem, cudaStream_t st) {
+  CU(v, cudaEventRecord(v->busy_ev, st));
+  v->busy_stream = st;
+  v->busy = true;
   if (mem == ORBX_MEM_HOST) CU(v, cudaStreamSynchronize(st));
   CU(v, cudaGetLastError());
   return ORBX_OK;
@@ -233,6 +243,8 @@ void orbv_destroy(orbv_t* v) {
   if (!v) return;
   cudaSetDevice(v->device);
   if (v->stream) cudaStreamSynchronize(v->stream);
+  if (v->busy) cudaEventSynchronize(v->busy_ev);
+  if (v->busy_ev) cudaEventDestroy(v->busy_ev);
   for (void* p : v->allocs) cudaFree(p);
   if (v->arena) cudaFree(v->arena);
   if (v->stream) cudaStreamDestroy(v->stream);

@@ -35,8 +35,32 @@ struct Slot {
   // that they have arrived, ev_import tells the copy stream that k_import has consumed the staging buffer
   cudaEvent_t ev_h2d = nullptr, ev_import = nullptr;
   bool import_pending = false;  // ev_import has been recorded for the chunk that last used d_img
+  // Ordering between the slot's own stream and foreign streams (ORBX_MEM_DEVICE calls on a caller's stream, the
+  // matcher's stream reading the pyramid in orbm_stereo_refine): every use goes through slot_acquire / slot_release.
+  mutable cudaEvent_t ev_own = nullptr, ev_foreign = nullptr;
+  mutable cudaStream_t foreign = nullptr;
+  mutable bool foreign_pending = false;  // the last use ran on `foreign`; ev_foreign was recorded behind it
+  mutable bool own_used = false;
   std::vector<void*> allocs;
 };
+
+// Before work on slot `s` is enqueued on `st`: wait for the last use of the slot's working set if it ran on another stream.
+cudaError_t slot_acquire(const Slot& s, cudaStream_t st) {
+  cudaError_t e = cudaSuccess;
+  if (s.foreign_pending && s.foreign != st) e = cudaStreamWaitEvent(st, s.ev_foreign, 0);
+  if (e == cudaSuccess && st != s.stream && s.own_used) {
+    e = cudaEventRecord(s.ev_own, s.stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, s.ev_own, 0);
+  }
+  return e;
+}
+// After the work has been enqueued.
+cudaError_t slot_release(const Slot& s, cudaStream_t st) {
+  if (st == s.stream) { s.foreign_pending = false; s.own_used = true; return cudaSuccess; }
+  s.foreign = st;
+  s.foreign_pending = true;
+  return cudaEventRecord(s.ev_foreign, st);
+}
 
 }  // namespace
 
@@ -447,6 +471,9 @@ bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** py
   *device = h->device;
   return true;
 }
+// a reader on another stream (orbm_stereo_refine on the matcher's stream) brackets its kernels with these
+cudaError_t orbx_pyramid_acquire(const orbx_extractor* h, cudaStream_t st) { return slot_acquire(h->slot[0], st); }
+cudaError_t orbx_pyramid_release(const orbx_extractor* h, cudaStream_t st) { return slot_release(h->slot[0], st); }
 }  // namespace orbx
 
 extern "C" {
@@ -466,6 +493,8 @@ int orbx_create(const orbx_params* params, int device, int max_batch, orbx_t** o
   if (cudaSetDevice(device) != cudaSuccess) { delete h; return ORBX_E_CUDA; }
   for (auto& s : h->slot)
     if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_own, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.ev_foreign, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s.ev_import, cudaEventDisableTiming) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { orbx_destroy(h); return ORBX_E_CUDA; }
@@ -477,8 +506,10 @@ void orbx_destroy(orbx_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-  for (auto& s : h->slot)
+  for (auto& s : h->slot) {
     if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.foreign_pending) cudaEventSynchronize(s.ev_foreign);
+  }
   free_geometry(h);
   for (cudaEvent_t e : h->ev_used) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -486,6 +517,8 @@ void orbx_destroy(orbx_t* h) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
     if (s.ev_import) cudaEventDestroy(s.ev_import);
+    if (s.ev_own) cudaEventDestroy(s.ev_own);
+    if (s.ev_foreign) cudaEventDestroy(s.ev_foreign);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -570,12 +603,14 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
   if (mem == ORBX_MEM_DEVICE) {
     Slot& s = h->slot[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    CU(h, slot_acquire(s, st));
     for (int f0 = 0; f0 < n_frames; f0 += B) {
       const int nf = n_frames - f0 < B ? n_frames - f0 : B;
       enqueue_pipeline(h, s, imgs + (size_t)f0 * frame_stride, row_stride, frame_stride, nf, lap0, lap1, kps, desc, cap,
                        n, n_mono, f0, st);
       h->last_frames = nf;
     }
+    CU(h, slot_release(s, st));
     CU(h, cudaGetLastError());
     return ORBX_OK;
   }
@@ -594,7 +629,9 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     if (rc) return rc;
     CU(h, cudaEventRecord(s.ev_h2d, h->copy_stream));
     CU(h, cudaStreamWaitEvent(s.stream, s.ev_h2d, 0));
+    CU(h, slot_acquire(s, s.stream));
     enqueue_pipeline(h, s, s.d_img, drs, dfs, nf, lap0, lap1, s.d_kps, s.d_desc, dcap, s.d_n, s.d_n + B, 0, s.stream, s.ev_import);
+    CU(h, slot_release(s, s.stream));
     s.import_pending = true;
     if (dcap == cap) {
       CU(h, cudaMemcpyAsync(kps + (size_t)f0 * cap, s.d_kps, (size_t)nf * cap * sizeof(orbx_kp), cudaMemcpyDeviceToHost, s.stream));
@@ -626,6 +663,8 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   if (rc) return rc;
   Slot& s = h->slot[0];
   h->border_done = false;
+  CU(h, slot_acquire(s, s.stream));
+  CU(h, slot_release(s, s.stream));
   size_t drs, dfs;
   rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
   if (rc) return rc;
@@ -689,6 +728,8 @@ int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int hh, size_t st
   rc = ensure_geometry(h, w, hh);
   if (rc) return rc;
   Slot& s = h->slot[0];
+  CU(h, slot_acquire(s, s.stream));
+  CU(h, slot_release(s, s.stream));
   size_t drs, dfs;
   rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
   if (rc) return rc;
@@ -713,6 +754,8 @@ int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int*
   if (dst_stride < (size_t)(L.w + 2 * kEdge)) return fail(h, ORBX_E_ARG, "dst_stride too small");
   CU(h, cudaSetDevice(h->device));
   Slot& s = h->slot[0];
+  CU(h, slot_acquire(s, s.stream));  // the pyramid may have been produced on a caller's stream (ORBX_MEM_DEVICE)
+  CU(h, slot_release(s, s.stream));
   if (!h->border_done) {
     h->launches += launch_border(h->g, s.b, h->last_frames, s.stream);
     h->border_done = true;
@@ -731,6 +774,8 @@ int orbx_stage_download(orbx_t* h, int frame, int stage, int lev, void* dst, siz
   Slot& s = h->slot[0];
   const FrameGeom& g = h->g;
   const LevelGeom& L = g.lv[lev];
+  CU(h, slot_acquire(s, s.stream));
+  CU(h, slot_release(s, s.stream));
   CU(h, cudaStreamSynchronize(s.stream));
   if (stage == ORBX_STAGE_LEVEL || stage == ORBX_STAGE_BLUR) {
     const size_t need = (size_t)L.w * L.h;

@@ -65,6 +65,11 @@ int launch_hamming_pairs(const uint8_t* a, const uint8_t* b, int64_t n, int32_t*
 size_t knn2_partial_bytes(int nq, int64_t nd);
 int launch_knn2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t index_base, void* partials,
                 int64_t* idx, int32_t* dist, cudaStream_t st);
+// sharded database: local top-2 as packed keys (distance << 40 | global row), then the merge of the gathered keys + ratio test
+int launch_knn2_keys(const uint8_t* q, int nq, const uint8_t* db, int64_t nd, int64_t index_base, void* partials,
+                     unsigned long long* keys, cudaStream_t st);
+int launch_top2_keys_ratio(const unsigned long long* keys, int n_parts, int nq, double ratio, int64_t* idx, int32_t* dist,
+                           uint8_t* accept, cudaStream_t st);
 int launch_top2_merge(const int64_t* idx_parts, const int32_t* dist_parts, int n_parts, int nq, int64_t* idx,
                       int32_t* dist, cudaStream_t st);
 int launch_ratio_test(const int64_t* idx, const int32_t* dist, int nq, double ratio, uint8_t* accept,
@@ -83,12 +88,17 @@ int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameG
 // the pyramid of frame 0 of an extractor's last single-frame / first-chunk call (defined in orbx_api.cu)
 bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
                        int* device);
+// order a reader of that pyramid on stream `st` after the extractor's last use, and the extractor's next use after the reader
+cudaError_t orbx_pyramid_acquire(const orbx_extractor* h, cudaStream_t st);
+cudaError_t orbx_pyramid_release(const orbx_extractor* h, cudaStream_t st);
 // max_rows: the largest number of rows any point owns (sizes the shared memory; <= 6000)
 size_t projection_scratch_bytes(int nq);  // per-query key lists of launch_search_by_projection
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
                                 const float* q_max_err, int th_high, float nnratio, const float* q_angle, int check_orientation,
-                                bool last_frame, void* scratch, int32_t* assigned, int32_t* n_matches, cudaStream_t st);
+                                bool last_frame, bool force_sequential, void* scratch, int32_t* assigned, int32_t* n_matches,
+                                cudaStream_t st);
+cudaError_t projection_configure();  // once per device: dynamic shared memory opt-in of the claim kernels
 int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
                                     const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                                     const uint8_t* has_point, const float* u_right, const int32_t* pair_1, const int32_t* pair_2,

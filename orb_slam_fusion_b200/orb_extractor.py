@@ -92,8 +92,8 @@ class OrbExtractor:
             if rc == A.E_CAP:
                 cap = n.value
                 continue
-            self._check(rc)
             break
+        self._check(rc)    # raises when the second attempt does not fit either
         return nm.value, kps[:n.value].copy(), desc[:n.value].copy()
 
     def extract_into(self, img, kps, desc, lapping_areas=(0, 0)):
@@ -112,6 +112,7 @@ class OrbExtractor:
         if _is_torch(imgs):
             import torch
             assert imgs.is_cuda and imgs.dtype == torch.uint8 and imgs.dim() == 3 and imgs.stride(2) == 1
+            assert imgs.device.index == self.device, "frames live on cuda:%d, the extractor on cuda:%d" % (imgs.device.index, self.device)
             F, h, w = imgs.shape
             cap = cap or self._cap_for(h, w)
             dev = imgs.device
@@ -128,13 +129,22 @@ class OrbExtractor:
         assert imgs.dtype == np.uint8 and imgs.ndim == 3 and imgs.strides[2] == 1
         F, h, w = imgs.shape
         cap = cap or self._cap_for(h, w)
-        kps = np.empty((F, cap), A.KP_DTYPE)
-        desc = np.empty((F, cap, 32), np.uint8)
-        n = np.empty(F, np.int32)
-        nm = np.empty(F, np.int32)
-        self._check(self._lib.orbx_extract_batch(self._h, imgs.ctypes.data, F, w, h, imgs.strides[1], imgs.strides[0],
-                                                 A.MEM_HOST, int(lapping_areas[0]), int(lapping_areas[1]),
-                                                 kps.ctypes.data, desc.ctypes.data, cap, n.ctypes.data, nm.ctypes.data, None))
+        for attempt in range(2):
+            kps = np.empty((F, cap), A.KP_DTYPE)
+            desc = np.empty((F, cap, 32), np.uint8)
+            n = np.empty(F, np.int32)
+            nm = np.empty(F, np.int32)
+            self._check(self._lib.orbx_extract_batch(self._h, imgs.ctypes.data, F, w, h, imgs.strides[1], imgs.strides[0],
+                                                     A.MEM_HOST, int(lapping_areas[0]), int(lapping_areas[1]),
+                                                     kps.ctypes.data, desc.ctypes.data, cap, n.ctypes.data, nm.ctypes.data, None))
+            if F == 0 or n.min() >= 0:
+                break
+            # n[f] = -(needed): frame f did not fit `cap`; INT32_MIN: the quadtree's node table overflowed
+            if n.min() == np.iinfo(np.int32).min:
+                raise A.OrbxError(A.E_UNSUPPORTED, "quadtree node table overflow in frame %d" % int(n.argmin()))
+            if attempt == 1:
+                raise A.OrbxError(A.E_CAP, "frame %d needs %d keypoint slots, cap is %d" % (int(n.argmin()), -int(n.min()), cap))
+            cap = -int(n.min())
         return n, nm, kps, desc
 
     def extract_batch_into(self, img_ptr, F, w, h, row_stride, frame_stride, mem, lap, kps_ptr, desc_ptr, cap, n_ptr,
@@ -144,7 +154,11 @@ class OrbExtractor:
                                                  int(lap[1]), kps_ptr, desc_ptr, cap, n_ptr, nm_ptr, stream))
 
     def _cap_for(self, h, w):
-        return self._lib.orbx_max_keypoints(self._h) + 8
+        # orbx_max_keypoints is exact for the geometry of the LAST call and conservative before the first; a new image size
+        # can need more than the previous one, so never go below the geometry-free bound (frames that still do not fit
+        # report n[f] = -(needed) and extract_batch retries)
+        free_bound = sum(max(int(q) + 3, 64) + 2 for q in self.features_per_level())
+        return max(self._lib.orbx_max_keypoints(self._h), free_bound) + 8
 
     def sync(self):
         self._check(self._lib.orbx_sync(self._h))
@@ -166,7 +180,9 @@ class OrbExtractor:
 
     # ---- ComputePyramid / img_pyramid_, orb_extractor.h:76-78
     def ComputePyramid(self, img):
-        img = np.ascontiguousarray(img, np.uint8)
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 2, "CV_8UC1 expected (:1019)"
+        img = np.ascontiguousarray(img)
         h, w = img.shape
         self._check(self._lib.orbx_compute_pyramid(self._h, img.ctypes.data, w, h, img.strides[0]))
 

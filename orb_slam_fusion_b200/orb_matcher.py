@@ -80,6 +80,35 @@ class ORBmatcher:
                                         idx.ctypes.data, dist.ctypes.data, A.MEM_HOST, None))
         return idx, dist
 
+    def knn2_sharded(self, comm, q, db_local, index_base=0, ratio=0.7):
+        """orbm_knn2_sharded: collective 2-NN + ratio test over a database sharded by rows over the ranks of the
+        NCCL communicator `comm` (an ncclComm_t address, e.g. sharding.NcclComm.handle; None = one rank).
+        Returns (idx[nq,2] int64 global rows, dist[nq,2] int32, accept[nq]) -- identical on every rank."""
+        if _is_torch(q):
+            import torch
+            assert q.dtype == torch.uint8 and db_local.dtype == torch.uint8 and q.is_contiguous() and db_local.is_contiguous()
+            assert q.device == db_local.device and q.device.index == self.device, "tensors must live on the matcher's GPU"
+            nq, nd = q.shape[0], db_local.shape[0]
+            idx = torch.empty((nq, 2), dtype=torch.int64, device=q.device)
+            dist = torch.empty((nq, 2), dtype=torch.int32, device=q.device)
+            acc = torch.empty(nq, dtype=torch.uint8, device=q.device)
+            self._check(self._lib.orbm_knn2_sharded(self._m, comm, q.data_ptr(), nq, db_local.data_ptr(), nd, int(index_base),
+                                                    float(ratio), idx.data_ptr(), dist.data_ptr(), acc.data_ptr(), A.MEM_DEVICE,
+                                                    self._stream(q)))
+            return idx, dist, acc
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32)
+        db_local = np.ascontiguousarray(db_local, np.uint8).reshape(-1, 32)
+        idx = np.empty((len(q), 2), np.int64)
+        dist = np.empty((len(q), 2), np.int32)
+        acc = np.empty(len(q), np.uint8)
+        self._check(self._lib.orbm_knn2_sharded(self._m, comm, q.ctypes.data, len(q), db_local.ctypes.data, len(db_local),
+                                                int(index_base), float(ratio), idx.ctypes.data, dist.ctypes.data, acc.ctypes.data,
+                                                A.MEM_HOST, None))
+        return idx, dist, acc.astype(bool)
+
+    def set_option(self, option, value):
+        self._check(self._lib.orbm_set_option(self._m, int(option), int(value)))
+
     def top2_merge(self, idx_parts, dist_parts):
         """Merge [P,nq,2] partial top-2 lists into the global top-2."""
         if _is_torch(idx_parts):

@@ -346,11 +346,11 @@ def test_search_by_projection_whole_function(P, m, oracle, seed, th, nnratio, st
     nm, got = m.SearchByProjection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
     wnm, want = oracle.search_by_projection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
     assert nm == wnm and np.array_equal(got, want) and wnm > 150
-    os.environ["ORBM_CLAIM_SEQUENTIAL"] = "1"          # the fallback kernel of frames too large for the shared-memory tables
+    m.set_option(P.OPT_CLAIM_SEQUENTIAL, 1)            # the fallback kernel of frames too large for the shared-memory tables
     try:
         nm_s, got_s = m.SearchByProjection(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr, 100, nnratio)
     finally:
-        del os.environ["ORBM_CLAIM_SEQUENTIAL"]
+        m.set_option(P.OPT_CLAIM_SEQUENTIAL, 0)
     assert nm_s == wnm and np.array_equal(got_s, want)
     # the greedy claim matters: without it (every window against the initial state) other keypoints would be assigned
     free = oracle.window_search(kps, desc, geom, q, qdesc[keep], pre, u_right, qur, qerr)
@@ -496,3 +496,96 @@ def test_window_search_fuse(P, m, oracle, seed, stereo):
         wi, wd = R.fuse_search(kps, desc, (0.0, float(W), 0.0, float(H)), inv_s2, q["u"], q["v"], qur, q["r"], lev, qdesc,
                                u_right if stereo else None)
         assert np.array_equal(got["best_idx"], wi) and np.array_equal(got["best_dist"], wd)
+
+
+def _claim_case(P, scenario, KL):
+    """Hand-built frames for the two orders of events the batched greedy claim must get right (the claim walks the map points
+    32 at a time; KL = length of the per-window candidate lists: 8 for the ratio form, 4 for the last-frame form).  All query
+    descriptors are zero, so the distance to a keypoint is the popcount of its descriptor; all keypoints sit on level 0.
+    (a) q33's whole list was claimed by the previous batch and its next-best keypoint `w` is the best of q32, one lane earlier:
+        q32 must get w, q33 the keypoint after it.
+    (b) q33 (blocked by q32 in round one) loses its whole list and re-scans: its next-best `y` is the best of the LATER q34,
+        which must not take y first."""
+    pts, pops, names = [], [], {}
+
+    def kp(name, x, y, pop):
+        names[name] = len(pts)
+        pts.append((x, y))
+        pops.append(pop)
+
+    queries = []  # (u, v, r)
+    if scenario == "a":
+        for k in range(KL):
+            kp("c%d" % k, 100 + 10 * k, 100, 1 + k)
+        xw = 100 + 10 * KL
+        kp("w", xw, 100, 10)
+        kp("x", xw + 10, 100, 40)
+        kp("x2", xw + 20, 100, 60)
+        for k in range(KL - 1):
+            kp("e%d" % k, xw + 30 + 10 * k, 100, 20 + k)
+        for k in range(KL):                                   # previous batch: every c_k is claimed by its own tiny window
+            queries.append((100 + 10 * k, 100, 3))
+        queries += [(700, 400, 3)] * (32 - KL)                # empty windows fill the batch
+        queries.append(((xw + xw + 30 + 10 * (KL - 2)) / 2, 100, (30 + 10 * (KL - 2)) / 2 + 4))   # q32: w .. e_last
+        queries.append(((100 + xw + 20) / 2, 100, (xw + 20 - 100) / 2 + 4))                        # q33: c_0 .. x2
+        expect = {("c%d" % k): k for k in range(KL)}
+        expect.update({"w": 32, "x": 33})
+    else:
+        kp("a1", 100, 100, 1)
+        for k in range(1, KL):
+            kp("p%d" % k, 100 + 10 * k, 100, 1 + k)
+        xy = 100 + 10 * KL
+        kp("y", xy, 100, 30)
+        kp("y2", xy + 10, 100, 60)
+        kp("z1", xy, 112, 50)
+        for k in range(1, KL):
+            queries.append((100 + 10 * k, 100, 3))
+        queries += [(700, 400, 3)] * (32 - (KL - 1))
+        queries.append((100, 100, 3))                                                   # q32 = A: claims a1
+        queries.append(((100 + xy + 10) / 2, 100, (xy + 10 - 100) / 2 + 4))             # q33 = E: a1, p*, y, y2 (and z1)
+        queries.append((xy, 106, 8))                                                    # q34 = L: y and z1
+        expect = {("p%d" % k): k - 1 for k in range(1, KL)}
+        expect.update({"a1": 32, "y": 33, "z1": 34})
+    n = len(pts)
+    kps = np.zeros(n, P.KP_DTYPE)
+    kps["x"], kps["y"] = [p[0] for p in pts], [p[1] for p in pts]
+    kps["size"], kps["angle"], kps["octave"], kps["class_id"] = 31, 0, 0, -1
+    desc = np.zeros((n, 32), np.uint8)
+    for i, pop in enumerate(pops):
+        bits = np.arange(pop)
+        np.bitwise_or.at(desc[i], bits // 8, (1 << (bits % 8)).astype(np.uint8))
+    q = np.zeros(len(queries), P.WQ_DTYPE)
+    q["u"], q["v"], q["r"] = [a[0] for a in queries], [a[1] for a in queries], [a[2] for a in queries]
+    q["min_level"], q["max_level"] = 0, 0
+    want = np.full(n, -1, np.int32)
+    for name, qi in expect.items():
+        want[names[name]] = qi
+    return kps, desc, q, np.zeros((len(queries), 32), np.uint8), want
+
+
+@pytest.mark.parametrize("scenario", ["a", "b"])
+def test_projection_claim_order_when_a_list_is_exhausted(P, m, oracle, scenario):
+    """The two cases the batched claim got wrong before the barrier rule (a lane that may have to scan its window again blocks
+    every later lane and decides alone): hand-built, checked against the oracle AND the outcome worked out by hand."""
+    geom = (0.0, 0.0, np.float32(64) / np.float32(752), np.float32(48) / np.float32(480), 64, 48)
+    # ratio form, lists of eight (orb_matcher.cc:42-134)
+    kps, desc, q, qdesc, want = _claim_case(P, scenario, 8)
+    pre = np.zeros(len(kps), np.uint8)
+    wnm, owant = oracle.search_by_projection(kps, desc, geom, q, qdesc, pre, None, None, None, 100, 0.8)
+    assert np.array_equal(owant, want), "the oracle disagrees with the hand-derived outcome"
+    nm, got = m.SearchByProjection(kps, desc, geom, q, qdesc, pre, None, None, None, 100, 0.8)
+    assert nm == wnm and np.array_equal(got, want)
+    m.set_option(P.OPT_CLAIM_SEQUENTIAL, 1)
+    try:
+        nm_s, got_s = m.SearchByProjection(kps, desc, geom, q, qdesc, pre, None, None, None, 100, 0.8)
+    finally:
+        m.set_option(P.OPT_CLAIM_SEQUENTIAL, 0)
+    assert nm_s == wnm and np.array_equal(got_s, want)
+    # last-frame form, lists of four (orb_matcher.cc:1518-1728), no orientation check
+    kps, desc, q, qdesc, want = _claim_case(P, scenario, 4)
+    pre = np.zeros(len(kps), np.uint8)
+    ang = np.zeros(len(q), np.float32)
+    wnm, owant = oracle.search_by_projection_last(kps, desc, geom, q, qdesc, ang, pre, None, None, None, 100, False)
+    assert np.array_equal(owant, want), "the oracle disagrees with the hand-derived outcome"
+    nm, got = m.SearchByProjectionLast(kps, desc, geom, q, qdesc, ang, pre, None, None, None, 100, False)
+    assert nm == wnm and np.array_equal(got, want)
