@@ -200,12 +200,15 @@ def _frame():
             raise RuntimeError("oracle/_ref/libframe_ref.so not built (needs /root/reference)")
         L = C.CDLL(_FRAME_SO)
         vp, i, f = C.c_void_p, C.c_int, C.c_float
-        L.reff_stereo_matches.argtypes = [vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, f, f, vp, vp]
-        L.reff_distinctive.argtypes = [vp, vp, i, vp, vp]
-        L.reff_search_by_projection.argtypes = [vp, vp, i, vp, f, f, f, f, vp, i, vp, vp, i, vp, f, f, i, f, vp]
-        L.reff_features_in_area.argtypes = [vp, i, f, f, f, f, f, f, f, i, i, vp, i]
-        L.reff_search_by_bow_kf.argtypes = [vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, i, vp, i, f, i, vp]
-        L.reff_search_by_bow.argtypes = [vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp]
+        # (tests/test_cpp_matcher.py binds this module to a library that exports only the matcher entry points)
+        for name, at in [("reff_stereo_matches", [vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, f, f, vp, vp]),
+                         ("reff_distinctive", [vp, vp, i, vp, vp]),
+                         ("reff_search_by_projection", [vp, vp, i, vp, f, f, f, f, vp, i, vp, vp, i, vp, f, f, i, f, vp]),
+                         ("reff_features_in_area", [vp, i, f, f, f, f, f, f, f, i, i, vp, i]),
+                         ("reff_search_by_bow_kf", [vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, vp, i, vp, i, f, i, vp]),
+                         ("reff_search_by_bow", [vp, vp, i, vp, vp, vp, i, vp, i, vp, vp, i, vp, vp, i, vp, i, f, i, vp])]:
+            if hasattr(L, name):
+                getattr(L, name).argtypes = at
         _FRAME = L
     return _FRAME
 

@@ -126,6 +126,8 @@ class ORBmatcherGpu {
                     const std::vector<float>* u_right = nullptr, const std::vector<float>* window_u_right = nullptr,
                     const std::vector<float>* window_max_err = nullptr);
 
+  orbm_matcher* handle() { return m_; }  // for callers that go to the C ABI directly (cpp/src/orb_matcher.cc)
+
  private:
   int SearchByBoWImpl(bool keyframes, const std::vector<cv::KeyPoint>& keys1, const cv::Mat& desc1,
                       const std::vector<uint8_t>& has_point1, const std::map<unsigned int, std::vector<unsigned int> >& featvec1,

@@ -396,7 +396,7 @@ int launch_stereo_rowband(const orbx_kp* kl, const uint8_t* dl, int nl, const or
 // (distance, position in the node), the second-best distance the second-smallest key.  Claimed side-2 features are a
 // bitmap in shared memory.  Then the 30-bin rotation histogram and ComputeThreeMaxima (:1841-1873) on the CTA.
 template <bool KF>
-__global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap,
+__global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap, int n_frames,
                                                        const uint32_t* __restrict__ fv_nodes, const int32_t* __restrict__ fv_begin,
                                                        const int32_t* __restrict__ fv_n, const uint32_t* __restrict__ fv_feats,
                                                        const int32_t* __restrict__ fv_total, const int32_t* __restrict__ n_per_frame,
@@ -410,6 +410,11 @@ __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict
   __shared__ uint32_t claimed[64];  // one bit per side-2 feature (cap <= 2048)
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int fr1 = pair_1[p], fr2 = pair_2[p];
+  if ((unsigned)fr1 >= (unsigned)n_frames || (unsigned)fr2 >= (unsigned)n_frames) {  // a pair outside the pool (device-memory callers are not pre-checked)
+    for (int i = tid; i < cap; i += 256) match[(size_t)p * cap + i] = -1;
+    if (tid == 0) n_matches[p] = -1;
+    return;
+  }
   const size_t o1 = (size_t)fr1 * cap, o2 = (size_t)fr2 * cap;
   const int n1 = n_per_frame ? max(0, min(n_per_frame[fr1], cap)) : cap, n2 = n_per_frame ? max(0, min(n_per_frame[fr2], cap)) : cap;
   int32_t* mt = match + (size_t)p * cap;
@@ -504,16 +509,16 @@ __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict
   if (tid == 0) n_matches[p] = n_kept;
 }
 
-int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                          const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,
                          int check_orientation, bool keyframes, int32_t* match, int32_t* n_matches, cudaStream_t st) {
   if (n_pairs <= 0) return 0;
   if (keyframes)
-    k_search_by_bow<true><<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
+    k_search_by_bow<true><<<n_pairs, 256, 0, st>>>(kps, desc, cap, n_frames, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
                                                    has_point, pair_1, pair_2, nnratio, check_orientation, match, n_matches);
   else
-    k_search_by_bow<false><<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
+    k_search_by_bow<false><<<n_pairs, 256, 0, st>>>(kps, desc, cap, n_frames, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame,
                                                     has_point, pair_1, pair_2, nnratio, check_orientation, match, n_matches);
   return 1;
 }
@@ -526,7 +531,7 @@ int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const
 // pinhole_model.cc:121-134 with the pair's F12).  The reference keeps the LAST of equally near candidates
 // (`dist > bestDist` skips, equality replaces): minimum of the key (distance, -position).
 __global__ void __launch_bounds__(256) k_search_for_triangulation(
-    const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap, const uint32_t* __restrict__ fv_nodes,
+    const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int cap, int n_frames, const uint32_t* __restrict__ fv_nodes,
     const int32_t* __restrict__ fv_begin, const int32_t* __restrict__ fv_n, const uint32_t* __restrict__ fv_feats,
     const int32_t* __restrict__ fv_total, const int32_t* __restrict__ n_per_frame, const uint8_t* __restrict__ has_point,
     const float* __restrict__ u_right, const int32_t* __restrict__ pair_1, const int32_t* __restrict__ pair_2,
@@ -540,6 +545,11 @@ __global__ void __launch_bounds__(256) k_search_for_triangulation(
   __shared__ uint32_t claimed[64];  // one bit per feature of key frame 2 (cap <= 2048)
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int fr1 = pair_1[p], fr2 = pair_2[p];
+  if ((unsigned)fr1 >= (unsigned)n_frames || (unsigned)fr2 >= (unsigned)n_frames) {  // a pair outside the pool (device-memory callers are not pre-checked)
+    for (int i = tid; i < cap; i += 256) match[(size_t)p * cap + i] = -1;
+    if (tid == 0) n_matches[p] = -1;
+    return;
+  }
   const size_t o1 = (size_t)fr1 * cap, o2 = (size_t)fr2 * cap;
   const int n1 = n_per_frame ? max(0, min(n_per_frame[fr1], cap)) : cap, n2 = n_per_frame ? max(0, min(n_per_frame[fr2], cap)) : cap;
   int32_t* mt = match + (size_t)p * cap;
@@ -656,14 +666,14 @@ __global__ void __launch_bounds__(256) k_search_for_triangulation(
   if (tid == 0) n_matches[p] = n_kept;
 }
 
-int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const uint32_t* fv_nodes, const int32_t* fv_begin,
                                     const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                                     const uint8_t* has_point, const float* u_right, const int32_t* pair_1, const int32_t* pair_2,
                                     int n_pairs, const float* pair_f12, const float* pair_ep, const float* scale_factors,
                                     const float* level_sigma2, int n_levels, int only_stereo, int coarse, int check_orientation,
                                     int32_t* match, int32_t* n_matches, cudaStream_t st) {
   if (n_pairs <= 0) return 0;
-  k_search_for_triangulation<<<n_pairs, 256, 0, st>>>(kps, desc, cap, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame, has_point,
+  k_search_for_triangulation<<<n_pairs, 256, 0, st>>>(kps, desc, cap, n_frames, fv_nodes, fv_begin, fv_n, fv_feats, fv_total, n_per_frame, has_point,
                                                       u_right, pair_1, pair_2, pair_f12, pair_ep, scale_factors, level_sigma2, n_levels,
                                                       only_stereo, coarse, check_orientation, match, n_matches);
   return 1;
@@ -685,7 +695,7 @@ __device__ __forceinline__ int refl(int p, int len) { return p < 0 ? -p : (p >= 
 
 __global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ StereoLevels P, const uint8_t* __restrict__ pyr_l,
                                                        const uint8_t* __restrict__ pyr_r, const orbx_kp* __restrict__ kl, int nl,
-                                                       const orbx_kp* __restrict__ kr, const int32_t* __restrict__ best_idx,
+                                                       const orbx_kp* __restrict__ kr, int nr, const int32_t* __restrict__ best_idx,
                                                        const int32_t* __restrict__ best_dist, int th_orb_dist, float min_d,
                                                        float max_d, float bf, float* __restrict__ u_right,
                                                        float* __restrict__ depth, int32_t* __restrict__ sad) {
@@ -696,7 +706,7 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ S
   const int bi = best_idx[il];
   const orbx_kp L = kl[il];
   const int oct = L.octave;
-  if (bi >= 0 && best_dist[il] < th_orb_dist && oct >= 0 && oct < P.gl.nlev) {
+  if (bi >= 0 && bi < nr && best_dist[il] < th_orb_dist && oct >= 0 && oct < P.gl.nlev) {
     const float ur0 = kr[bi].x;
     const float scale = P.isf[oct];
     const float sul = roundf(f_mul(L.x, scale)), svl = roundf(f_mul(L.y, scale)), sur0 = roundf(f_mul(ur0, scale));
@@ -784,7 +794,7 @@ __global__ void __launch_bounds__(1024) k_stereo_median_cut(int nl, const int32_
 }
 
 int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
-                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, const int32_t* best_idx,
+                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, int nr, const int32_t* best_idx,
                          const int32_t* best_dist, int th_orb_dist, float min_d, float max_d, float bf, float* u_right,
                          float* depth, int32_t* sad, cudaStream_t st) {
   if (nl <= 0) return 0;
@@ -792,7 +802,7 @@ int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameG
   P.gl = gl;
   P.gr = gr;
   for (int i = 0; i < ORBX_MAX_LEVELS; i++) { P.sf[i] = i < gl.nlev ? sf[i] : 1.f; P.isf[i] = i < gl.nlev ? isf[i] : 1.f; }
-  k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(P, pyr_l, pyr_r, kl, nl, kr, best_idx, best_dist, th_orb_dist, min_d, max_d, bf,
+  k_stereo_refine<<<(nl + 7) / 8, 256, 0, st>>>(P, pyr_l, pyr_r, kl, nl, kr, nr, best_idx, best_dist, th_orb_dist, min_d, max_d, bf,
                                                 u_right, depth, sad);
   k_stereo_median_cut<<<1, 1024, 0, st>>>(nl, sad, u_right, depth);
   return 2;

@@ -394,7 +394,7 @@ int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const
   // frame wait for this read
   CU(m, orbx_pyramid_acquire(left, st));
   CU(m, orbx_pyramid_acquire(right, st));
-  m->launches += launch_stereo_refine(gl, pl, gr, pr, sf, isf, dkl, nl, dkr, dbi, dbd, th_orb_dist, min_d, max_d, bf, dur, ddp,
+  m->launches += launch_stereo_refine(gl, pl, gr, pr, sf, isf, dkl, nl, dkr, nr, dbi, dbd, th_orb_dist, min_d, max_d, bf, dur, ddp,
                                       dsad, st);
   CU(m, orbx_pyramid_release(left, st));
   if (right != left) CU(m, orbx_pyramid_release(right, st));
@@ -590,7 +590,7 @@ static int search_by_bow(bool keyframes, orbm_t* m, const orbx_kp* kps, const ui
   TRY(stage_in(m, mem, pair_f, (size_t)n_pairs, &dpf, st));
   int32_t* dmatch = stage_out(m, mem, match, (size_t)n_pairs * cap);
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)n_pairs);
-  m->launches += launch_search_by_bow(dk, dd, cap, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dpk, dpf, n_pairs, nnratio,
+  m->launches += launch_search_by_bow(dk, dd, cap, n_frames, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dpk, dpf, n_pairs, nnratio,
                                       check_orientation, keyframes, dmatch, dnm, st);
   TRY(finish_out(m, mem, match, dmatch, (size_t)n_pairs * cap, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)n_pairs, st));
@@ -661,7 +661,7 @@ int orbm_search_for_triangulation(orbm_t* m, const orbx_kp* kps, const uint8_t* 
   TRY(stage_in(m, mem, level_sigma2, (size_t)n_levels, &ds2, st));
   int32_t* dmatch = stage_out(m, mem, match, (size_t)n_pairs * cap);
   int32_t* dnm = stage_out(m, mem, n_matches, (size_t)n_pairs);
-  m->launches += launch_search_for_triangulation(dk, dd, cap, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dur, dp1, dp2, n_pairs, df12, dep,
+  m->launches += launch_search_for_triangulation(dk, dd, cap, n_frames, dnodes, dbegin, dfn, dfeats, dft, dnpf, dhp, dur, dp1, dp2, n_pairs, df12, dep,
                                                  dsf, ds2, n_levels, only_stereo, coarse, check_orientation, dmatch, dnm, st);
   TRY(finish_out(m, mem, match, dmatch, (size_t)n_pairs * cap, st));
   TRY(finish_out(m, mem, n_matches, dnm, (size_t)n_pairs, st));

@@ -82,7 +82,7 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
                          const float* kp_u_right, const float* q_u_right, const float* q_max_err,
                          orbm_window_result* out, cudaStream_t st, const float* inv_sigma2 = nullptr, int n_levels = 0);  // inv_sigma2: the chi-square gate of ORBmatcher::Fuse
 int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
-                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, const int32_t* best_idx,
+                         const float* isf, const orbx_kp* kl, int nl, const orbx_kp* kr, int nr, const int32_t* best_idx,
                          const int32_t* best_dist, int th_orb_dist, float min_d, float max_d, float bf, float* u_right,
                          float* depth, int32_t* sad, cudaStream_t st);
 // the pyramid of frame 0 of an extractor's last single-frame / first-chunk call (defined in orbx_api.cu)
@@ -99,13 +99,13 @@ int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, 
                                 bool last_frame, bool force_sequential, void* scratch, int32_t* assigned, int32_t* n_matches,
                                 cudaStream_t st);
 cudaError_t projection_configure();  // once per device: dynamic shared memory opt-in of the claim kernels
-int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+int launch_search_for_triangulation(const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const uint32_t* fv_nodes, const int32_t* fv_begin,
                                     const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                                     const uint8_t* has_point, const float* u_right, const int32_t* pair_1, const int32_t* pair_2,
                                     int n_pairs, const float* pair_f12, const float* pair_ep, const float* scale_factors,
                                     const float* level_sigma2, int n_levels, int only_stereo, int coarse, int check_orientation,
                                     int32_t* match, int32_t* n_matches, cudaStream_t st);
-int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, const uint32_t* fv_nodes, const int32_t* fv_begin,
+int launch_search_by_bow(const orbx_kp* kps, const uint8_t* desc, int cap, int n_frames, const uint32_t* fv_nodes, const int32_t* fv_begin,
                          const int32_t* fv_n, const uint32_t* fv_feats, const int32_t* fv_total, const int32_t* n_per_frame,
                          const uint8_t* has_point, const int32_t* pair_1, const int32_t* pair_2, int n_pairs, float nnratio,
                          int check_orientation, bool keyframes, int32_t* match, int32_t* n_matches, cudaStream_t st);
