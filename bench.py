@@ -29,11 +29,13 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT, NLEV, SCALE, INI_TH, MIN_TH = 752, 480, 1000, 8, 1.2, 20, 7
 METRIC = "orb_frames_per_s_752x480_1000kp"
 DB_ROWS, N_QUERIES = 10_000_000, 1000
+KNN_XU_OPS, KNN_ALU_OPS = 6, 19   # per 256-bit pair in k_knn2's inner loop: 6 POPC; 8 LOP3 (xor) + 4 LOP3 (carry-save) + 3 IADD3 / LEA + 1 key + 3 VIMNMX
+WORKLOAD = "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7"
 
 
-def level_sizes(w, h):
+def level_sizes(w, h, nlev=NLEV):
     s, out = np.float32(1.0), []
-    for l in range(NLEV):
+    for l in range(nlev):
         if l:
             s = np.float32(np.float64(s) * np.float64(np.float32(SCALE)))
         inv = np.float32(1.0) / s
@@ -130,10 +132,10 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu):
-        self.rows, self.proc = [], None
+    def __init__(self, gpu, power=False):
+        self.rows, self.proc, self.power = [], None, power
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu), "--query-gpu=" + self.Q + (",power.draw" if power else ""),
                                           "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
@@ -168,8 +170,18 @@ class ClockSampler:
         mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[2 + k] == "Active" for r in rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "where": where}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm), "where": where}
+        if self.power:
+            pw = []
+            for r in rows:
+                try:
+                    pw.append(float(r[6]))
+                except (IndexError, ValueError):
+                    pass
+            out["power_w_median"] = float(np.median(pw)) if pw else None
+            out["power_w_max"] = max(pw) if pw else None
+        return out
 
 
 # ---------------------------------------------------------------------------- reference arm (CPU)
@@ -207,7 +219,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    per_thread = 4
+    per_thread = max(1, -(-args.batch // threads))  # the repo arm's frames per step, split over the host threads
     for _ in range(args.warmup):
         cpu_reference_rate(threads, 1)
     rates, total = [], 0.0
@@ -221,12 +233,186 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
-                   "frames_per_step": threads * per_thread},
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.batch},
+        "workload_detail": {"frames_per_step_timed": threads * per_thread, "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
+
+
+# ---------------------------------------------------------------------------- BASELINE configs 2, 3, 4
+def algorithmic_bytes_total(w, h, n_kp, nlev=NLEV):
+    """B = sum_{l<7} px_l + sum_{l>=1} px_l + sum px + 2 sum px + N * 749 + N * 572."""
+    px = [a * b for a, b in level_sizes(w, h, nlev)]
+    return sum(px[:-1]) + sum(px[1:]) + 3 * sum(px) + n_kp * (749 + 512 + 32 + 28)
+
+
+def time_batches(torch, step, steps, warmup, barrier, max_over_ranks):
+    for _ in range(warmup):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    return ms / steps
+
+
+def run_other_configs(P, A, torch, world, rank, local, dev, barrier, max_over_ranks, peak, with_cpu):
+    """BASELINE.json configs 2-4, each with its own roofline and, at N=1, a bounded CPU leg on
+    the reference's own code (oracle/_ref).  Config 5 is the `matching` key."""
+    out = {}
+    stream = A.torch_stream(dev)
+
+    def batch_case(w, h, nfeat, n_frames, chunk, first_frame, steps):
+        ex = P.OrbExtractor(nfeat, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=chunk)
+        frames = P.synth_frames("blocks", n_frames, w, h, seed=1, first_frame=first_frame, device=local)
+        cap = ex.max_keypoints() + 8
+        kps = torch.empty((n_frames, cap, 7), dtype=torch.float32, device=dev)
+        desc = torch.empty((n_frames, cap, 32), dtype=torch.uint8, device=dev)
+        n = torch.empty(n_frames, dtype=torch.int32, device=dev)
+        nm = torch.empty(n_frames, dtype=torch.int32, device=dev)
+
+        def step():
+            ex.extract_batch_into(frames.data_ptr(), n_frames, w, h, frames.stride(1), frames.stride(0), A.MEM_DEVICE, (0, 0),
+                                  kps.data_ptr(), desc.data_ptr(), cap, n.data_ptr(), nm.data_ptr(), stream)
+        step()
+        torch.cuda.synchronize()
+        if int(n.min().item()) < 0:   # the geometry-free capacity was too small for this image size: size it from the first pass
+            cap = int(-n.min().item()) + 8
+            kps = torch.empty((n_frames, cap, 7), dtype=torch.float32, device=dev)
+            desc = torch.empty((n_frames, cap, 32), dtype=torch.uint8, device=dev)
+        ms = time_batches(torch, step, steps, 3, barrier, max_over_ranks)
+        nh = n.cpu().numpy()
+        assert (nh > 0).all(), "extraction failed"
+        return ms, float(nh.mean()), ex, frames
+
+    # ---- config 3: KITTI-shaped 1241x376, 2000 features, batch of 64 frames (every rank its own 64: weak)
+    ms3, kp3, ex3, fr3 = batch_case(1241, 376, 2000, 64, 64, rank * 64, 20)
+    b3 = algorithmic_bytes_total(1241, 376, kp3)
+    v3 = world * 64 / (ms3 * 1e-3)
+    out["config3"] = {"workload": "64 blocks-v1 frames 1241x376, 2000 features, 8 levels per GPU per step", "value": v3, "unit": "frames/s",
+                      "ms_per_batch": ms3, "mean_keypoints_per_frame": kp3,
+                      "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": b3, "achieved": b3 * v3 / world / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": b3 * v3 / world / 1e9 / peak},
+                      "l2": "working set 0.7 GB per step (pyramid + blurred planes of 64 frames) exceeds the 126 MB L2"}
+    if with_cpu:
+        out["config3"]["cpu_baseline"] = cpu_reference_case(1241, 376, 2000, 12)
+    del ex3, fr3
+
+    # ---- config 4: 4096 frames 1280x720, 1000 features, sharded by frame over the ranks (strong scaling, no collective)
+    total4 = 4096
+    f0, f1 = total4 * rank // world, total4 * (rank + 1) // world
+    ms4, kp4, ex4, fr4 = batch_case(1280, 720, 1000, f1 - f0, 256, f0, 3)
+    b4 = algorithmic_bytes_total(1280, 720, kp4)
+    v4 = total4 / (ms4 * 1e-3)
+    out["config4"] = {"workload": "4096 blocks-v1 frames 1280x720, 1000 features, frames [r*4096/G, (r+1)*4096/G) on rank r, 256-frame chunks",
+                      "value": v4, "unit": "frames/s", "scaling": "strong", "ms_per_pass": ms4, "frames_per_rank": f1 - f0,
+                      "mean_keypoints_per_frame": kp4,
+                      "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": b4, "achieved": b4 * v4 / world / 1e9, "peak": peak,
+                                   "unit": "GB/s", "frac": b4 * v4 / world / 1e9 / peak}}
+    if with_cpu:
+        out["config4"]["cpu_baseline"] = cpu_reference_case(1280, 720, 1000, 8)
+    del ex4, fr4
+    torch.cuda.empty_cache()
+
+    # ---- config 2: EuRoC-shaped stereo pair, 1200 features per side + ComputeStereoMatches, one blocking stereo frame at a
+    # time through the C ABI with host buffers (frame.cc:139-235 = two extractions + :828-986), rank 0
+    if rank == 0:
+        import orb_slam_fusion_b200.orb_matcher  # noqa: F401
+        m = P.ORBmatcher(device=local)
+        exl = P.OrbExtractor(1200, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=1)
+        exr = P.OrbExtractor(1200, SCALE, NLEV, INI_TH, MIN_TH, device=local, max_batch=1)
+        pair = P.synth_frames("blocks", 1, W, H, seed=1, first_frame=3, device=local)
+        right = P.synth_frames("blocks", 1, W, H, seed=1, first_frame=3, shift_x=12, noise_seed=2, device=local)
+        hl, hr = pair[0].cpu().numpy(), right[0].cpu().numpy()
+        bf, mb = np.float32(47.90639384423901), np.float32(0.11)   # settings/EuRoC.yaml: fx * baseline; minZ = mb (frame.cc:853-856)
+        cap = 1400
+        kl, dl = np.empty(cap, P.KP_DTYPE), np.empty((cap, 32), np.uint8)
+        kr, dr = np.empty(cap, P.KP_DTYPE), np.empty((cap, 32), np.uint8)
+
+        def stereo_frame():
+            _, nl = exl.extract_into(hl, kl, dl)
+            _, nr = exr.extract_into(hr, kr, dr)
+            return m.ComputeStereoMatches(exl, exr, kl[:nl], dl[:nl], kr[:nr], dr[:nr], bf, mb), nl, nr
+        for _ in range(20):
+            (ur, dp), nl, nr = stereo_frame()
+        lat = []
+        for _ in range(300):
+            t0 = time.perf_counter()
+            stereo_frame()
+            lat.append(time.perf_counter() - t0)
+        p50 = 1e3 * float(np.median(lat))
+        b2 = 2 * algorithmic_bytes_total(W, H, (nl + nr) / 2)
+        out["config2"] = {"workload": "stereo pair 2 x 752x480, 1200 features per side: two blocking extractions + ComputeStereoMatches "
+                                      "(row band + SAD refinement + median cut), host buffers through the C ABI",
+                          "p50_ms_per_stereo_frame": p50, "stereo_frames_per_s": 1e3 / p50, "keypoints": [int(nl), int(nr)],
+                          "stereo_matches": int((ur >= 0).sum()),
+                          "roofline": {"bound": "latency", "algorithmic_bytes_per_stereo_frame": b2, "achieved": b2 / (p50 * 1e-3) / 1e9,
+                                       "peak": peak, "unit": "GB/s", "frac": b2 / (p50 * 1e-3) / 1e9 / peak,
+                                       "note": "one 1.1 MB pyramid per side is L2-resident: a blocking stereo frame is launch- and dependency-bound, "
+                                               "SURVEY.md 8(d) asks for ms here"}}
+        if with_cpu:
+            out["config2"]["cpu_baseline"] = cpu_stereo_case(hl, hr, bf, mb, (kl[:nl].copy(), dl[:nl].copy(), kr[:nr].copy(), dr[:nr].copy(), ur, dp))
+        del exl, exr, m
+    return out
+
+
+def cpu_reference_case(w, h, nfeat, n_frames):
+    """The reference's extractor (oracle/_ref, else the oracle port) on one thread over n_frames frames of another geometry."""
+    from oracle import oracle as O
+    from oracle import ref as R
+    kind = "reference" if R.available(try_build=False) else "port"
+    ex = (R.Extractor if kind == "reference" else O.Extractor)(nfeat, SCALE, NLEV, INI_TH, MIN_TH)
+    imgs = [O.blocks_v1(w, h, 1, f) for f in range(n_frames)]
+    ex(imgs[0])
+    t0 = time.perf_counter()
+    for im in imgs:
+        ex(im)
+    dt = time.perf_counter() - t0
+    return {"value": n_frames / dt, "unit": "frames/s", "cores": 1, "kind": kind,
+            "sample": "%d blocks-v1 %dx%d frames, %d features, one extractor object on one thread" % (n_frames, w, h, nfeat)}
+
+
+def cpu_stereo_case(hl, hr, bf, mb, gpu):
+    """frame.cc:139-235 on the host: the reference's extractor on both images (sequentially, one thread) + the reference's own
+    ComputeStereoMatches lines (oracle/_ref/libframe_ref.so); also checks the GPU's mvuRight / mvDepth against them."""
+    from oracle import oracle as O
+    from oracle import ref as R
+    if not (R.available(try_build=False) and R.frame_available()):
+        return None
+    exl, exr = R.Extractor(1200, SCALE, NLEV, INI_TH, MIN_TH), R.Extractor(1200, SCALE, NLEV, INI_TH, MIN_TH)
+    ol, orr = O.Extractor(1200, SCALE, NLEV, INI_TH, MIN_TH), O.Extractor(1200, SCALE, NLEV, INI_TH, MIN_TH)
+    t = ol.tables()
+    reps, t_ex, t_st = 5, 0.0, 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        _, kl, dl = exl(hl)
+        _, kr, dr = exr(hr)
+        t1 = time.perf_counter()
+        ol.compute_pyramid(hl)
+        orr.compute_pyramid(hr)
+        ll = [ol.level(l, with_border=True) for l in range(NLEV)]
+        lr = [orr.level(l, with_border=True) for l in range(NLEV)]
+        t2 = time.perf_counter()
+        ur, dp = R.stereo_matches(ll, lr, kl, dl, kr, dr, t["scale"], t["inv_scale"], bf, mb)
+        t3 = time.perf_counter()
+        t_ex += t1 - t0
+        t_st += t3 - t2
+    # the reference's ComputeStereoMatches lines on the GPU's own keypoints / descriptors must give the GPU's mvuRight / mvDepth
+    gkl, gdl, gkr, gdr, gpu_ur, gpu_dp = gpu
+    wur, wdp = R.stereo_matches(ll, lr, gkl, gdl, gkr, gdr, t["scale"], t["inv_scale"], bf, mb)
+    same = bool(wur.tobytes() == gpu_ur.tobytes() and wdp.tobytes() == gpu_dp.tobytes())
+    assert same, "GPU ComputeStereoMatches != the reference's lines on the same stereo pair"
+    return {"value": 1e3 * (t_ex + t_st) / reps, "unit": "ms per stereo frame", "cores": 1, "kind": "reference",
+            "extraction_ms": 1e3 * t_ex / reps, "stereo_matches_ms": 1e3 * t_st / reps, "equal_to_gpu": same,
+            "sample": "%d stereo frames: two extractions on one thread (the reference uses two, frame.cc:179-182) + the reference's "
+                      "ComputeStereoMatches lines (frame.cc:828-986)" % reps}
 
 # ---------------------------------------------------------------------------- B200 arm
 def run_ours(args):
@@ -312,6 +498,24 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
 
     log('device-resident timing done: %.3f ms' % ms)
+    # ---- the same step back to back for >= 2 s (the 20-step region above lasts ~50 ms): clocks and power under sustained load
+    sus_steps = int(max(args.steps, np.ceil(2200.0 / max(ms / args.steps, 1e-3))))
+    sclk = ClockSampler(local, power=True)
+    sclk.wait_first()
+    barrier()
+    t_s0 = time.time()
+    s0e, s1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0e.record()
+    for _ in range(sus_steps):
+        step()
+    s1e.record()
+    torch.cuda.synchronize()
+    t_s1 = time.time()
+    sus_ms = max_over_ranks(s0e.elapsed_time(s1e))
+    barrier()
+    sclk.stop()
+    sustained = {"value": world * B * sus_steps / (sus_ms * 1e-3), "unit": "frames/s", "steps": sus_steps, "seconds": sus_ms * 1e-3,
+                 "ms_per_step": sus_ms / sus_steps, "clocks": sclk.summary(t_s0, t_s1)}
     # ---- end to end through the C ABI with pinned host buffers
     eb = ex_e2e = None
     E2E_CHUNK = min(64, B)  # frames per pipelined chunk of the host-memory path (the handle's max_batch)
@@ -341,9 +545,20 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     assert np.array_equal(h_n.numpy(), n_host), "host-memory path disagrees with device-memory path"
+    # the host-memory path must return exactly what the device-memory path wrote: every keypoint record and descriptor row
+    d_kps, d_desc, d_nm = kps.cpu().numpy(), desc.cpu().numpy(), nm.cpu().numpy()
+    hk, hd = h_kps.numpy(), h_desc.numpy()
+    assert np.array_equal(h_nm.numpy(), d_nm), "n_mono differs between the host-memory and the device-memory path"
+    for f in range(B):
+        c = int(n_host[f])
+        assert hk[f, :c].tobytes() == d_kps[f, :c].tobytes() and np.array_equal(hd[f, :c], d_desc[f, :c]), \
+            "frame %d: host-memory path returned other keypoints / descriptors than the device-memory path" % f
+    del d_kps, d_desc, hk, hd
     e2e = {"value": world * B * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": B * W * H,
            "d2h_bytes_per_step": B * (cap * (28 + 32) + 8), "ms_per_step": 1e3 * e2e_s / args.steps,
-           "chunk_frames": E2E_CHUNK, "h2d_gbs": world * B * W * H * args.steps / e2e_s / 1e9}
+           "chunk_frames": E2E_CHUNK, "h2d_gbs": world * B * W * H * args.steps / e2e_s / 1e9,
+           "h2d_gbs_per_rank": B * W * H * args.steps / e2e_s / 1e9,
+           "checked": "n, n_mono, every keypoint record and descriptor row equal the device-memory path's"}
     del eb, h_kps, h_desc
 
     log('e2e done')
@@ -370,10 +585,33 @@ def run_ours(args):
     r0, r1 = DB_ROWS * rank // world, DB_ROWS * (rank + 1) // world
     db = P.synth_descriptors(r0, r1 - r0, seed=7, device=local)
     q = P.synth_descriptors(0, N_QUERIES, seed=8, device=local)
+    # known answers in EVERY shard: query i's true match (8 flipped bits) sits at global row
+    # i * 9973 + 12345 -- spread over all shards -- and every 10th query also has a decoy 2 bits further away in the shard
+    # "opposite" to its match, so the ratio test must reject it and the merged second neighbour must come from another rank
+    qi = torch.arange(N_QUERIES, device=dev, dtype=torch.int64)
+    true_row = qi * 9973 + 12345
+    decoy_row = (true_row + DB_ROWS // 2) % DB_ROWS
+    planted = q.clone()
+    planted[:, 0] ^= 0xFF
+    decoy = planted.clone()
+    decoy[:, 1] ^= 0x03
+    mine = (true_row >= r0) & (true_row < r1)
+    db[true_row[mine] - r0] = planted[mine]
+    dmine = (decoy_row >= r0) & (decoy_row < r1) & (qi % 10 == 0)
+    db[decoy_row[dmine] - r0] = decoy[dmine]
     from orb_slam_fusion_b200 import sharding
 
     def match_step():
-        return sharding.sharded_knn2(m, q, db, r0, 0.7)
+        return sharding.sharded_knn2(m, q, db, r0, 0.7)   # orbm_knn2_sharded: ONE C-ABI call, one NCCL all-gather inside
+
+    g_idx, g_dist, g_acc = match_step()
+    torch.cuda.synchronize()
+    has_decoy = (qi % 10 == 0)
+    assert torch.equal(g_idx[:, 0], true_row) and bool((g_dist[:, 0] == 8).all()), "rank %d: merged nearest neighbour is not the planted row" % rank
+    assert torch.equal(g_idx[has_decoy, 1], decoy_row[has_decoy]) and bool((g_dist[has_decoy, 1] == 10).all()), \
+        "rank %d: merged second neighbour is not the planted decoy" % rank
+    assert bool((g_dist[~has_decoy, 1] > 60).all()), "rank %d: an unexpected near row" % rank
+    assert torch.equal(g_acc.bool(), ~has_decoy), "rank %d: ratio test result" % rank
 
     for _ in range(2):
         match_step()
@@ -392,12 +630,23 @@ def run_ours(args):
     pairs_per_s = N_QUERIES * DB_ROWS / (match_ms * 1e-3)
     matching = {"value": pairs_per_s, "unit": "pair-distances/s", "ms_per_search": match_ms,
                 "queries_per_s": N_QUERIES / (match_ms * 1e-3), "workload": "1000 queries x 10M rows, top-2 + ratio 0.7",
-                "sharding": "database rows over %d rank(s), all-gather of per-rank top-2" % world}
+                "sharding": "database rows over %d rank(s); orbm_knn2_sharded: local top-2 as packed 64-bit keys, ONE ncclAllGather of "
+                            "16 B per query and rank on the call's stream, merge + ratio in one kernel" % world,
+                "verified": "every rank: planted true matches (all shards) are the merged nearest neighbours, planted decoys in the "
+                            "opposite shard the merged second neighbours, ratio test rejects exactly those"}
     if rank == 0:
         popc = P.popc_peak(0, local)
         plain = P.popc_peak(1, local)
+        # The bound that binds: a pair costs KNN_XU_OPS popc on the XU pipe (16 lanes / clk / SM, measured above as
+        # popc_peak_per_s) and KNN_ALU_OPS LOP3 / IADD3 / VIMNMX on the ALU pipe (64 lanes / clk / SM = 4x the popc rate);
+        # the kernel cannot beat the slower of the two pipes.  Counts from the SASS of k_knn2's inner loop (profiles/).
+        alu_peak = 4.0 * popc
+        two_pipe = min(popc / KNN_XU_OPS, alu_peak / KNN_ALU_OPS)
         matching.update({"popc_peak_per_s": popc, "plain_distance_peak_per_s": plain,
-                         "frac_of_popc_roofline": 8 * pairs_per_s / (world * popc),
+                         "roofline": {"bound": "xu+alu pipes", "xu_ops_per_pair": KNN_XU_OPS, "alu_ops_per_pair": KNN_ALU_OPS,
+                                      "xu_bound_pairs_per_s": popc / KNN_XU_OPS, "alu_bound_pairs_per_s": alu_peak / KNN_ALU_OPS,
+                                      "peak": two_pipe, "achieved": pairs_per_s / world, "unit": "pair-distances/s/GPU",
+                                      "frac": pairs_per_s / world / two_pipe},
                          "frac_of_plain_distance_peak": pairs_per_s / (world * plain)})
 
     # ---- the tracker's projection matchers as whole calls (host buffers through the C ABI, like the reference's call sites):
@@ -506,6 +755,11 @@ def run_ours(args):
                                                     "sample": "32 pairs of this batch through orc_search_by_bow (oracle/orb_oracle.c)"}
     del voc, bow
 
+    # ---- BASELINE configs 2, 3, 4 (every rank takes part in 3 and 4)
+    del kps, desc
+    other_configs = run_other_configs(P, A, torch, world, rank, local, dev, barrier, max_over_ranks, measured_peaks()[0], world == 1)
+    log('configs 2-4 done')
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -531,7 +785,24 @@ def run_ours(args):
             traffic = tr["bytes_per_launch"] * B / tr["frames_per_launch"]
     except OSError:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    # The limiter of the dominant kernel is instruction issue, not HBM: executed warp-instructions per frame and the share of
+    # them on the integer ALU pipe come from the committed ncu capture (profiles/inst_counts.json, like `traffic`);
+    # issue bound = instructions / (4 SMSPs x 148 SMs x clock), ALU-pipe bound = 2 clocks per ALU warp-instruction per SMSP.
+    issue = None
+    try:
+        ic = json.load(open(os.path.join(ROOT, "profiles", "inst_counts.json"))).get(dom)
+        if ic:
+            clk_hz = 1e6 * (clk.get("sm_mhz") or 1965.0)
+            inst = ic["warp_inst_per_frame"] * B
+            t_issue = inst / (592.0 * clk_hz) * 1e3
+            t_alu = 2.0 * ic["alu_pipe_share"] * inst / (592.0 * clk_hz) * 1e3
+            issue = {"warp_inst_per_launch": inst, "thread_inst_per_pixel": ic.get("thread_inst_per_pixel"),
+                     "issue_bound_ms": t_issue, "frac_of_issue_bound": t_issue / per_launch_ms[dom],
+                     "alu_pipe_share": ic["alu_pipe_share"], "alu_pipe_bound_ms": t_alu, "frac_of_alu_pipe_bound": t_alu / per_launch_ms[dom],
+                     "source": ic.get("source")}
+    except OSError:
+        pass
+    roofline = {"bound": "hbm", "binding_limit": "instruction issue / integer ALU pipe (see `issue`)", "issue": issue, "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_frame": alg_stage[dom], "frames_per_launch": B,
                 "launch_ms": per_launch_ms[dom],
@@ -563,10 +834,11 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "ms_per_step_per_rank": [round(x / args.steps, 4) for x in ms_ranks],
         "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7",
-                   "frames_per_step_per_gpu": B, "mean_keypoints_per_frame": mean_kp,
-                   "l2": "inputs larger than L2 (%.0f MB of frames + %.1f GB working set per step)"
-                         % (B * W * H / 1e6, B * 7.5e6 / 1e9)},
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B},
+        "workload_detail": {"mean_keypoints_per_frame": mean_kp,
+                            "l2": "inputs larger than L2 (%.0f MB of frames + %.1f GB working set per step)"
+                                  % (B * W * H / 1e6, B * 7.5e6 / 1e9)},
+        "sustained": sustained, "configs": other_configs,
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         "p50_ms_per_frame": p50, "matching": matching, "bow": bow_out,
     }

@@ -10,6 +10,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "orbx_kernels.cuh"
 #include "orbx_math.cuh"
 
@@ -404,17 +406,28 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
     cudaEventRecord(e, st);
     h->ev_used.push_back(e);
   };
+  // NVTX ranges around the launches of the five stages: free when no tool is attached
   mark();
+  nvtxRangePushA("orbx:import");
   n += launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
+  nvtxRangePop();
   if (after_import) cudaEventRecord(after_import, st);  // the staging buffer may be overwritten from here on
   mark();
+  nvtxRangePushA("orbx:pyramid");
   n += launch_pyramid(g, s.b, frames, st);
+  nvtxRangePop();
   mark();
+  nvtxRangePushA("orbx:fast_blur");
   n += launch_fast(g, s.b, frames, st);
+  nvtxRangePop();
   mark();
+  nvtxRangePushA("orbx:octree");
   n += launch_octree(g, s.b, frames, st);
+  nvtxRangePop();
   mark();
+  nvtxRangePushA("orbx:describe");
   n += launch_describe(g, s.b, frames, d_kps, d_desc, cap, d_n, d_nmono, out_frame0, st);
+  nvtxRangePop();
   mark();
   h->launches += n;
 }
