@@ -116,6 +116,12 @@ int orbx_sync(orbx_t* h);
 /* Number of kernels the handle has launched so far (bench.py's gpu_launches claim). */
 long long orbx_launch_count(const orbx_t* h);
 
+/* Debug counter: FAST candidates the detector dropped on this handle's device since the last reset because a
+ * per-tile or per-level list was full.  The capacities are upper bounds by construction (3x3 non-maximum suppression
+ * keeps at most every other pixel of every other row), so the value is 0; the parity tests assert that.  Blocks until
+ * the handle's streams are idle. */
+int orbx_debug_dropped(orbx_t* h, long long* dropped, int reset);
+
 /* Per-stage device time, measured with CUDA events recorded on the launching stream between the
  * stages of every enqueued chunk while profiling is on.  ms[k] accumulates milliseconds of stage k
  * (ORBX_STAGE_T_*), *chunks the number of chunks (kernel sequences) measured; `reset` clears the

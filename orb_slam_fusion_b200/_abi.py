@@ -60,6 +60,7 @@ SIGNATURES = {
     "orbx_extract_batch": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, i32, i32, vp, vp, i32, vp, vp, vp]),
     "orbx_sync": (i32, [vp]),
     "orbx_launch_count": (C.c_longlong, [vp]),
+    "orbx_debug_dropped": (i32, [vp, C.POINTER(C.c_longlong), i32]),
     "orbx_set_profiling": (i32, [vp, i32]),
     "orbx_stage_times": (i32, [vp, vp, C.POINTER(C.c_longlong), i32]),
     "orbx_stage_download": (i32, [vp, i32, i32, i32, vp, sz, pi32]),

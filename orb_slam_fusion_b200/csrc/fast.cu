@@ -50,6 +50,10 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
   return p < 0 ? -p : (p >= len ? 2 * (len - 1) - p : p);
 }
 
+// Candidates the kernel had to drop because a list was full.  Both capacities are upper bounds by construction (at most
+// every other pixel of every other row survives a 3x3 NMS), so this stays 0; the fuzz tests assert it (orbx_debug_dropped).
+__device__ unsigned int g_fast_dropped = 0;
+
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 7
 #endif
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   uint16_t* list = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes);   // (score row << 8) | byte column of pixels to score
   uint16_t* outl = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes + kListBytes);
   uint32_t* tmp2 = reinterpret_cast<uint32_t*>(u_mem);                 // blur: (kFtH + 6) / 2 row pairs x kFtW, (row 2p) | (row 2p+1) << 16
-  __shared__ int n_list, n_out, out_base;
+  __shared__ int n_list, n_out, out_base, warp_corners[kFtWarps];
   __shared__ uint8_t xmask_l[kFtPitch], xmask_r[kFtPitch], ymask_u[kFtScH], ymask_d[kFtScH];  // 0 where the neighbour lies in another cell, else 255
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     const int rows_out = min(kFtH, L.h - Y0), cols_out = min(kFtW, L.w - X0);
     const int q = tid & 31;
     if (4 * q < cols_out) {  // horizontal: thread = (quad q, row pairs warp, warp+8, warp+16); blur row b = raw row b + 1
-#pragma unroll 1
+#pragma unroll
       for (int i = 0; i < 3; i++) {
         const int pr = (tid >> 5) + kFtWarps * i;
         if (2 * pr < rows_out + 6) {
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   // Thread (wc, rg) walks raw word column wc (x = X0-4+4wc+j) down the kFtStrip score rows of row
   // group rg (y = Y0-1+rr, raw row rr+3): column masks, neighbour indices and addresses are set up
   // once per thread, and the warp scan + shared atomic of the compaction run once per strip.
-  const uint32_t kthr = (uint32_t)(0x7f - lo) * 0x01010101u;
+  const uint32_t kthr = lo > 126 ? 0x80808080u : (uint32_t)(0x7f - lo) * 0x01010101u;  // thresholds beyond the byte trick: everything passes
   const int xlo = max(kEdge, X0 - 1), xhi = min(L.w - kEdge, X0 + kFtW + 1);  // scored columns [xlo, xhi)
   {
     const int wc = tid % kFtRawW, rg = tid / kFtRawW;
@@ -233,7 +237,6 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     // 0x80 per byte lane inside the scored column range [xlo, xhi): drop the first a and keep the first b lanes
     const int a = min(max(xlo - x, 0), 4), b = min(max(xhi - x, 0), 4);
     const uint32_t lane_mask = __funnelshift_lc(0u, 0x80808080u, 8 * a) & __funnelshift_rc(0x80808080u, 0u, 8 * (4 - b));
-    const uint32_t force = lo > 126 ? 0x80808080u : 0u;  // thresholds beyond the byte trick: score everything
     const int wl = wc > 0 ? -1 : 0, wr = wc < kFtRawW - 1 ? 1 : 0;
     const int rr0 = rg * kFtStrip;
     // rows of the strip inside the score map and the detection domain: i_lo <= i < i_hi, as one bit per row.
@@ -252,11 +255,13 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
       const uint32_t up = rp[-3 * kFtRawPW], dn = rp[3 * kFtRawPW];
       const uint32_t lf = __byte_perm(rp[wl], c, 0x4321);   // pixels x-3
       const uint32_t rt = __byte_perm(c, rp[wr], 0x6543);   // pixels x+3
-      // exceeds4 without its final mask: bit 7 of every byte of (((d & 0x7f) + k) | d) says |a - b| > t
-      const uint32_t d0 = __vabsdiffu4(dn, c), d1 = __vabsdiffu4(up, c), d2 = __vabsdiffu4(rt, c), d3 = __vabsdiffu4(lf, c);
-      const uint32_t s0 = (d0 & 0x7f7f7f7fu) + kthr, s1 = (d1 & 0x7f7f7f7fu) + kthr, s2 = (d2 & 0x7f7f7f7fu) + kthr,
-                     s3 = (d3 & 0x7f7f7f7fu) + kthr;
-      const uint32_t k = (((s0 | d0 | s1 | d1) & (s2 | d2 | s3 | d3)) | force) & m;
+      // |a - b| > t per byte: bit 7 of (((d & 0x7f) + (0x7f - t)) | d).  The two differences of an opposite pair are OR-ed
+      // BEFORE the threshold: (d0 | d1) >= max(d0, d1) bytewise, so the test can only let MORE pixels through than
+      // "d0 > t or d1 > t" (for t = 2^k - 1, the EuRoC minThFAST = 7 included, exactly the same ones) -- it is a pre-filter,
+      // the scoring pass decides -- and costs two thresholds per quad instead of four.
+      const uint32_t m01 = __vabsdiffu4(dn, c) | __vabsdiffu4(up, c), m23 = __vabsdiffu4(rt, c) | __vabsdiffu4(lf, c);
+      const uint32_t s01 = (m01 & 0x7f7f7f7fu) + kthr, s23 = (m23 & 0x7f7f7f7fu) + kthr;
+      const uint32_t k = (s01 | m01) & (s23 | m23) & m;
       keep[i] = k;
       cnt += __popc(k);
     }
@@ -321,22 +326,37 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     }
     n_corner += __popc(bal);
   }
+  if (lane == 0) warp_corners[wrp] = n_corner;
   __syncthreads();
 
-  // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0 (byte masks per column / row)
-  for (int v = lane; v < n_corner; v += 32) {
-    const uint16_t item = list[(v >> 5) * kFtThreads + (wrp << 5) + (v & 31)];
-    const int rr = item >> 8, cb = item & 255;
-    const uint8_t* sp = &score[rr * kFtPitch + cb];
-    const int s = sp[0];
-    const int ml = xmask_l[cb], mr = xmask_r[cb], mu = ymask_u[rr], md = ymask_d[rr];
-    int m = imax3(sp[-1] & ml, sp[1] & mr, sp[-kFtPitch] & mu);
-    m = imax3(m, sp[kFtPitch] & md, sp[-kFtPitch - 1] & (ml & mu));
-    m = imax3(m, sp[-kFtPitch + 1] & (mr & mu), sp[kFtPitch - 1] & (ml & md));
-    m = imax(m, sp[kFtPitch + 1] & (mr & md));
-    if (s > m) {
-      const int o = atomicAdd(&n_out, 1);
-      if (o < kFtMaxOut) outl[o] = item;
+  // ---- 4. NMS of the owned corners; neighbours across a cell edge count as 0 (byte masks per column / row).
+  // The warps packed their corners separately; the CTA walks the concatenation of the eight lists, so the pass takes
+  // ceil(corners / 256) rounds of full warps instead of ceil(corners of a warp / 32) rounds of every warp.
+  {
+    int pre[kFtWarps + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int k = 0; k < kFtWarps; k++) pre[k + 1] = pre[k] + warp_corners[k];
+    for (int gi = tid; gi < pre[kFtWarps]; gi += kFtThreads) {
+      int w = 0, off = 0;
+#pragma unroll
+      for (int k = 1; k < kFtWarps; k++)
+        if (gi >= pre[k]) { w = k; off = pre[k]; }
+      const int v = gi - off;
+      const uint16_t item = list[(v >> 5) * kFtThreads + (w << 5) + (v & 31)];
+      const int rr = item >> 8, cb = item & 255;
+      const uint8_t* sp = &score[rr * kFtPitch + cb];
+      const int s = sp[0];
+      const int ml = xmask_l[cb], mr = xmask_r[cb], mu = ymask_u[rr], md = ymask_d[rr];
+      int m = imax3(sp[-1] & ml, sp[1] & mr, sp[-kFtPitch] & mu);
+      m = imax3(m, sp[kFtPitch] & md, sp[-kFtPitch - 1] & (ml & mu));
+      m = imax3(m, sp[-kFtPitch + 1] & (mr & mu), sp[kFtPitch - 1] & (ml & md));
+      m = imax(m, sp[kFtPitch + 1] & (mr & md));
+      if (s > m) {
+        const int o = atomicAdd(&n_out, 1);
+        if (o < kFtMaxOut) outl[o] = item;
+        else atomicAdd(&g_fast_dropped, 1u);  // never expected: kFtMaxOut is the NMS bound of a tile
+      }
     }
   }
   __syncthreads();
@@ -353,6 +373,7 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
     const int cell = div_rcp(y - kEdge, L.hcell_rcp) * L.ncols + div_rcp(x - kEdge, L.wcell_rcp);
     const int pos = out_base + i;
+    if (pos >= L.cand_cap) atomicAdd(&g_fast_dropped, 1u);  // never expected: cand_cap is the NMS bound of the level
     if (pos < L.cand_cap) {
       // coordinates relative to (16,16) as orb_extractor.cc:816-823
       cand_xy[cbase + pos] = ((uint32_t)(y - kFastBorder) << 16) | (uint32_t)(x - kFastBorder);
@@ -361,6 +382,15 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     }
     if (s >= g.ini_th) cell_strong[(size_t)f * g.total_cells + L.cell_base + cell] = 1;
   }
+}
+
+cudaError_t fast_dropped(unsigned int* out, bool reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_fast_dropped, sizeof(unsigned int));
+  if (e == cudaSuccess && reset) {
+    const unsigned int zero = 0;
+    e = cudaMemcpyToSymbol(g_fast_dropped, &zero, sizeof(unsigned int));
+  }
+  return e;
 }
 
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {

@@ -568,6 +568,16 @@ int orbx_sync(orbx_t* h) {
 
 long long orbx_launch_count(const orbx_t* h) { return h ? h->launches : 0; }
 
+int orbx_debug_dropped(orbx_t* h, long long* dropped, int reset) {
+  if (!h || !dropped) return ORBX_E_ARG;
+  CU(h, cudaSetDevice(h->device));
+  for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
+  unsigned int v = 0;
+  CU(h, fast_dropped(&v, reset != 0));
+  *dropped = (long long)v;
+  return ORBX_OK;
+}
+
 int orbx_set_profiling(orbx_t* h, int on) {
   if (!h) return ORBX_E_ARG;
   h->profiling = on != 0;

@@ -48,6 +48,7 @@ int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaSt
 void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh);
 int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // blur + FAST, one kernel
+cudaError_t fast_dropped(unsigned int* out, bool reset);  // candidates dropped by k_fast_blur since the last reset (expected: 0)
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_pattern_init(cudaStream_t st);  // fills the device-resident float pattern table (once per device / geometry)
 // writes frame f of the batch to kps[(out_frame0 + f) * cap + slot], n[out_frame0 + f], ...

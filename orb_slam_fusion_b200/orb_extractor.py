@@ -128,6 +128,7 @@ class OrbExtractor:
         imgs = np.asarray(imgs)
         assert imgs.dtype == np.uint8 and imgs.ndim == 3 and imgs.strides[2] == 1
         F, h, w = imgs.shape
+        explicit_cap = cap is not None   # a caller's own capacity is honoured: frames that do not fit report n[f] = -(needed)
         cap = cap or self._cap_for(h, w)
         for attempt in range(2):
             kps = np.empty((F, cap), A.KP_DTYPE)
@@ -137,7 +138,7 @@ class OrbExtractor:
             self._check(self._lib.orbx_extract_batch(self._h, imgs.ctypes.data, F, w, h, imgs.strides[1], imgs.strides[0],
                                                      A.MEM_HOST, int(lapping_areas[0]), int(lapping_areas[1]),
                                                      kps.ctypes.data, desc.ctypes.data, cap, n.ctypes.data, nm.ctypes.data, None))
-            if F == 0 or n.min() >= 0:
+            if F == 0 or n.min() >= 0 or (explicit_cap and n.min() != np.iinfo(np.int32).min):
                 break
             # n[f] = -(needed): frame f did not fit `cap`; INT32_MIN: the quadtree's node table overflowed
             if n.min() == np.iinfo(np.int32).min:
@@ -165,6 +166,12 @@ class OrbExtractor:
 
     def launch_count(self):
         return self._lib.orbx_launch_count(self._h)
+
+    def debug_dropped(self, reset=True):
+        """FAST candidates dropped on this device because a list was full (expected 0, see orbx_debug_dropped)."""
+        v = C.c_longlong()
+        self._check(self._lib.orbx_debug_dropped(self._h, C.byref(v), int(reset)))
+        return v.value
 
     STAGE_NAMES = ("import", "pyramid", "fast_blur", "octree", "describe")
 

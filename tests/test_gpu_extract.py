@@ -309,5 +309,7 @@ def test_fuzz_geometries_and_parameters(P, oracle):
         ref = oracle.Extractor(nf, sf, nl, ini, mn, trig=oracle.TRIG_CR)
         rn, rk, rd = ref(img, lap)
         assert got[0] == rn and got[1].tobytes() == rk.tobytes() and np.array_equal(got[2], rd), (trial, w, h, nf, nl, sf, ini, mn, lap, kind)
+        # the detector's list capacities are bounds, not truncation points: nothing was dropped (orbx_debug_dropped)
+        assert ex.debug_dropped() == 0, (trial, w, h, kind)
         done += 1
     assert done >= 40
