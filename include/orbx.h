@@ -90,6 +90,13 @@ int orbx_max_keypoints(const orbx_t* h);
 int orbx_extract(orbx_t* h, const uint8_t* img, int w, int h_, size_t stride, int lap0, int lap1,
                  orbx_kp* kps, uint8_t* desc, int cap, int* n, int* n_mono);
 
+/* The same call in two halves, so that one host thread can have the left and the right image of a stereo pair in
+ * flight on two handles at once (the reference runs them on two threads, frame.cc:179-182): _begin copies the image
+ * and enqueues the whole pipeline on the handle's stream, _end waits and hands the result over exactly like
+ * orbx_extract.  orbx_extract == _begin + _end. */
+int orbx_extract_begin(orbx_t* h, const uint8_t* img, int w, int h_, size_t stride, int lap0, int lap1);
+int orbx_extract_end(orbx_t* h, orbx_kp* kps, uint8_t* desc, int cap, int* n, int* n_mono);
+
 /* OrbExtractor::ComputePyramid (orb_extractor.cc:1093-1117; public, orb_extractor.h:78). */
 int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int h_, size_t stride);
 
@@ -242,6 +249,15 @@ int orbm_stereo_rowband(orbm_t* m, const orbx_kp* kl, const uint8_t* dl, int nl,
 int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const orbx_kp* kl, int nl, const orbx_kp* kr,
                        int nr, const int32_t* best_idx, const int32_t* best_dist, int th_orb_dist, float min_d, float max_d,
                        float bf, float* u_right, float* depth, int32_t* sad, int mem, void* stream);
+
+/* Frame::ComputeStereoMatches (frame.cc:828-986) as ONE call for the frames the two extractors processed last with
+ * orbx_extract / orbx_extract_end: their keypoints, descriptors and pyramids are still on the device, so nothing is
+ * uploaded; row band search (:836-900) -> SAD refinement (:903-972) -> median cut (:974-985) run back to back on the
+ * matcher's stream and one copy brings mvuRight / mvDepth back.  minZ = mb, minD = 0, maxD = bf / minZ (:853-856);
+ * thOrbDist = (TH_HIGH + TH_LOW) / 2 (:832).  u_right / depth: host arrays of `cap` floats, cap >= the left extractor's
+ * keypoint count (else ORBX_E_CAP); *nl returns that count. */
+int orbm_stereo_matches_last(orbm_t* m, const orbx_t* left, const orbx_t* right, float bf, float mb, float* u_right,
+                             float* depth, int cap, int* nl);
 
 /* MapPoint::ComputeDistinctiveDescriptors (mappoint.cc:365-428) for a batch of
  * map points: point p owns descriptor rows [offsets[p], offsets[p+1]) of `desc`; per point the row

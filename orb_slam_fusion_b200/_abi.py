@@ -55,6 +55,8 @@ SIGNATURES = {
     "orbx_tables": (i32, [vp, vp, vp, vp, vp, vp]),
     "orbx_max_keypoints": (i32, [vp]),
     "orbx_extract": (i32, [vp, vp, i32, i32, sz, i32, i32, vp, vp, i32, pi32, pi32]),
+    "orbx_extract_begin": (i32, [vp, vp, i32, i32, sz, i32, i32]),
+    "orbx_extract_end": (i32, [vp, vp, vp, i32, pi32, pi32]),
     "orbx_compute_pyramid": (i32, [vp, vp, i32, i32, sz]),
     "orbx_pyramid_level": (i32, [vp, i32, vp, sz, pi32, pi32]),
     "orbx_extract_batch": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, i32, i32, vp, vp, i32, vp, vp, vp]),
@@ -82,6 +84,7 @@ SIGNATURES = {
     "orbm_ratio_test": (i32, [vp, vp, vp, i32, dbl, vp, i32, vp]),
     "orbm_stereo_rowband": (i32, [vp, vp, vp, i32, vp, vp, i32, vp, i32, i32, f32, f32, vp, vp, i32, vp]),
     "orbm_stereo_refine": (i32, [vp, vp, vp, vp, i32, vp, i32, vp, vp, i32, f32, f32, f32, vp, vp, vp, i32, vp]),
+    "orbm_stereo_matches_last": (i32, [vp, vp, vp, f32, f32, vp, vp, i32, pi32]),
     "orbm_distinctive": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, vp]),
     "orbm_window_search_fuse": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, vp, i32, vp, i32, vp]),
     "orbm_search_by_projection": (i32, [vp, vp, vp, i32, C.POINTER(GridGeom), vp, vp, i32, vp, vp, vp, vp, i32, f32, vp, vp, i32, vp]),

@@ -765,24 +765,32 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ S
 
 // frame.cc:974-985: median of the accepted SAD distances (element size/2 of the list sorted by
 // (distance, left index)); every match with distance >= 1.5 * 1.4 * median is dropped.  One CTA.
+constexpr int kMedianStage = 8192;  // SAD values staged in shared memory (frames with more left keypoints read them from global memory)
 __global__ void __launch_bounds__(1024) k_stereo_median_cut(int nl, const int32_t* __restrict__ sad, float* __restrict__ u_right,
                                                             float* __restrict__ depth) {
   __shared__ int n_acc;
   __shared__ float th;
+  __shared__ int32_t staged[kMedianStage];
   if (threadIdx.x == 0) { n_acc = 0; th = 0.f; }
   __syncthreads();
+  const bool in_smem = nl <= kMedianStage;
   int cnt = 0;
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) cnt += sad[i] >= 0;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    const int d = sad[i];
+    if (in_smem) staged[i] = d;
+    cnt += d >= 0;
+  }
   if (cnt) atomicAdd(&n_acc, cnt);
   __syncthreads();
   const int n = n_acc;
   if (n == 0) return;
+  const int32_t* v = in_smem ? staged : sad;  // the rank loop reads every value once per thread: warp-wide broadcasts from shared memory
   for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-    const int d = sad[i];
+    const int d = v[i];
     if (d < 0) continue;
     int rank = 0;  // number of accepted (distance, index) pairs below this one
     for (int j = 0; j < nl; j++) {
-      const int e = sad[j];
+      const int e = v[j];
       rank += (e >= 0) && (e < d || (e == d && j < i));
     }
     if (rank == n / 2) th = f_mul(f_mul(1.5f, 1.4f), (float)d);
@@ -790,7 +798,7 @@ __global__ void __launch_bounds__(1024) k_stereo_median_cut(int nl, const int32_
   __syncthreads();
   const float t = th;
   for (int i = threadIdx.x; i < nl; i += blockDim.x)
-    if (sad[i] >= 0 && !((float)sad[i] < t)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+    if (v[i] >= 0 && !((float)v[i] < t)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
 }
 
 int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,

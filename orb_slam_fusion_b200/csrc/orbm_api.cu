@@ -404,6 +404,44 @@ int orbm_stereo_refine(orbm_t* m, const orbx_t* left, const orbx_t* right, const
   return end(m, mem, st);
 }
 
+int orbm_stereo_matches_last(orbm_t* m, const orbx_t* left, const orbx_t* right, float bf, float mb, float* u_right, float* depth,
+                             int cap, int* nl_out) {
+  cudaStream_t st;
+  TRY(begin(m, ORBX_MEM_HOST, nullptr, &st));
+  if (!left || !right || !u_right || !depth || !nl_out || !(mb > 0.f)) return fail(m, ORBX_E_ARG, "bad argument");
+  FrameGeom gl, gr;
+  const uint8_t *pl, *pr, *ddl, *ddr;
+  const orbx_kp *dkl, *dkr;
+  const float *sf, *isf, *sf_r, *isf_r;
+  int dl, dr, nl, nr;
+  if (!orbx_peek_pyramid(left, &gl, &pl, &sf, &isf, &dl) || !orbx_peek_pyramid(right, &gr, &pr, &sf_r, &isf_r, &dr) ||
+      !orbx_peek_single(left, &dkl, &ddl, &nl) || !orbx_peek_single(right, &dkr, &ddr, &nr))
+    return fail(m, ORBX_E_ARG, "both extractors must hold the result of a single-frame call");
+  if (dl != m->device || dr != m->device || gl.nlev != gr.nlev) return fail(m, ORBX_E_ARG, "extractors on another device / level count");
+  *nl_out = nl;
+  if (nl > cap) return fail(m, ORBX_E_CAP, "%d left keypoints, capacity %d", nl, cap);
+  if (nl == 0) return ORBX_OK;
+  const float min_d = 0.f, max_d = bf / mb;  // frame.cc:853-856
+  TRY(arena_reserve(m, pad256((size_t)gl.nlev * 4) + 5 * pad256((size_t)nl * 4)));
+  float* dsf = arena_take<float>(m, (size_t)gl.nlev);
+  int32_t* dbi = arena_take<int32_t>(m, (size_t)nl);
+  int32_t* dbd = arena_take<int32_t>(m, (size_t)nl);
+  float* dur = arena_take<float>(m, (size_t)nl);   // dur and ddp are adjacent: one copy brings both back
+  float* ddp = arena_take<float>(m, (size_t)nl);
+  int32_t* dsad = arena_take<int32_t>(m, (size_t)nl);
+  CU(m, cudaMemcpyAsync(dsf, sf, (size_t)gl.nlev * 4, cudaMemcpyHostToDevice, st));
+  CU(m, orbx_pyramid_acquire(left, st));   // keypoints, descriptors and pyramids were written on the extractors' streams
+  CU(m, orbx_pyramid_acquire(right, st));
+  m->launches += launch_stereo_rowband(dkl, ddl, nl, dkr, ddr, nr, dsf, gl.nlev, gl.lv[0].h, min_d, max_d, dbi, dbd, st);
+  m->launches += launch_stereo_refine(gl, pl, gr, pr, sf, isf, dkl, nl, dkr, nr, dbi, dbd, 75 /* (TH_HIGH + TH_LOW) / 2, frame.cc:832 */,
+                                      min_d, max_d, bf, dur, ddp, dsad, st);
+  CU(m, orbx_pyramid_release(left, st));
+  if (right != left) CU(m, orbx_pyramid_release(right, st));
+  CU(m, cudaMemcpyAsync(u_right, dur, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+  CU(m, cudaMemcpyAsync(depth, ddp, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+  return end(m, ORBX_MEM_HOST, st);
+}
+
 int orbm_distinctive(orbm_t* m, const uint8_t* desc, const int32_t* offsets, int n_points, int max_rows, int32_t* best_idx,
                      int32_t* best_median, int mem, void* stream) {
   cudaStream_t st;

@@ -93,6 +93,8 @@ struct orbx_extractor {
   int graph_launches = 0;            // kernels one replay launches
   uint8_t* h_out = nullptr;          // pinned: out_cap keypoint records, out_cap descriptor rows, then n and n_mono
   uint8_t* d_single = nullptr;       // the same block on the device: the single-frame path returns everything in ONE copy
+  bool single_pending = false;       // orbx_extract_begin has enqueued a frame that orbx_extract_end has not collected
+  int single_n = -1;                 // keypoints of the last collected single frame (they stay in d_single)
   // optional per-stage timing (orbx_set_profiling): one event set per enqueued chunk
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;   // free events
@@ -484,6 +486,14 @@ bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** py
   *device = h->device;
   return true;
 }
+// the last single frame's keypoints / descriptors as they lie on the device (d_single), for Frame::ComputeStereoMatches
+bool orbx_peek_single(const orbx_extractor* h, const orbx_kp** kps, const uint8_t** desc, int* n) {
+  if (!h || !h->d_single || h->single_n < 0 || h->single_pending) return false;
+  *kps = reinterpret_cast<const orbx_kp*>(h->d_single);
+  *desc = h->d_single + (size_t)h->out_cap * sizeof(orbx_kp);
+  *n = h->single_n;
+  return true;
+}
 // a reader on another stream (orbm_stereo_refine on the matcher's stream) brackets its kernels with these
 cudaError_t orbx_pyramid_acquire(const orbx_extractor* h, cudaStream_t st) { return slot_acquire(h->slot[0], st); }
 cudaError_t orbx_pyramid_release(const orbx_extractor* h, cudaStream_t st) { return slot_release(h->slot[0], st); }
@@ -675,12 +685,11 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
   return ORBX_OK;
 }
 
-int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, int lap0, int lap1, orbx_kp* kps,
-                 uint8_t* desc, int cap, int* n, int* n_mono) {
+int orbx_extract_begin(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, int lap0, int lap1) {
   if (!h) return ORBX_E_ARG;
   int rc = check_image(h, img, w, hh, stride);
   if (rc) return rc;
-  if (!n || !n_mono) return fail(h, ORBX_E_ARG, "null output");
+  h->single_pending = false;
   CU(h, cudaSetDevice(h->device));
   rc = ensure_geometry(h, w, hh);
   if (rc) return rc;
@@ -728,9 +737,22 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
     CU(h, cudaGraphLaunch(h->graph, s.stream));
     h->launches += h->graph_launches;
   }
+  h->single_pending = true;
+  return ORBX_OK;
+}
+
+int orbx_extract_end(orbx_t* h, orbx_kp* kps, uint8_t* desc, int cap, int* n, int* n_mono) {
+  if (!h) return ORBX_E_ARG;
+  if (!n || !n_mono) return fail(h, ORBX_E_ARG, "null output");
+  if (!h->single_pending) return fail(h, ORBX_E_ARG, "orbx_extract_end without orbx_extract_begin");
+  h->single_pending = false;
+  CU(h, cudaSetDevice(h->device));
+  Slot& s = h->slot[0];
+  const size_t kp_bytes = (size_t)h->out_cap * sizeof(orbx_kp), desc_bytes = (size_t)h->out_cap * 32;
   CU(h, cudaStreamSynchronize(s.stream));
   const int32_t* const hn = reinterpret_cast<const int32_t*>(h->h_out + kp_bytes + desc_bytes);
   const int N = hn[0];
+  h->single_n = N;
   if (N < 0) return fail(h, ORBX_E_UNSUPPORTED, "quadtree node table overflow");
   *n = N;
   if (N > cap) return fail(h, ORBX_E_CAP, "%d keypoints, capacity %d", N, cap);
@@ -741,6 +763,14 @@ int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, in
   }
   *n_mono = hn[1];
   return ORBX_OK;
+}
+
+int orbx_extract(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride, int lap0, int lap1, orbx_kp* kps,
+                 uint8_t* desc, int cap, int* n, int* n_mono) {
+  if (!h) return ORBX_E_ARG;
+  if (!n || !n_mono) return fail(h, ORBX_E_ARG, "null output");
+  const int rc = orbx_extract_begin(h, img, w, hh, stride, lap0, lap1);
+  return rc ? rc : orbx_extract_end(h, kps, desc, cap, n, n_mono);
 }
 
 int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {

@@ -89,6 +89,7 @@ int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameG
 // the pyramid of frame 0 of an extractor's last single-frame / first-chunk call (defined in orbx_api.cu)
 bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
                        int* device);
+bool orbx_peek_single(const orbx_extractor* h, const orbx_kp** kps, const uint8_t** desc, int* n);  // last single frame, device-resident
 // order a reader of that pyramid on stream `st` after the extractor's last use, and the extractor's next use after the reader
 cudaError_t orbx_pyramid_acquire(const orbx_extractor* h, cudaStream_t st);
 cudaError_t orbx_pyramid_release(const orbx_extractor* h, cudaStream_t st);

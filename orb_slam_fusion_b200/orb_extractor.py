@@ -105,6 +105,19 @@ class OrbExtractor:
                                            int(lapping_areas[1]), kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(n), C.byref(nm)))
         return nm.value, n.value
 
+    def extract_begin(self, img, lapping_areas=(0, 0)):
+        """First half of operator() (orbx_extract_begin): copies the image and enqueues the pipeline, returns at once.
+        Two extractors can so work on the two images of a stereo pair at the same time from one host thread."""
+        h, w = img.shape
+        self._check(self._lib.orbx_extract_begin(self._h, img.ctypes.data, w, h, img.strides[0], int(lapping_areas[0]),
+                                                 int(lapping_areas[1])))
+
+    def extract_end(self, kps, desc):
+        """Second half (orbx_extract_end) into caller-owned arrays; returns (mono_index, n)."""
+        n, nm = C.c_int(0), C.c_int(0)
+        self._check(self._lib.orbx_extract_end(self._h, kps.ctypes.data, desc.ctypes.data, len(kps), C.byref(n), C.byref(nm)))
+        return nm.value, n.value
+
     def extract_batch(self, imgs, lapping_areas=(0, 0), cap=None, stream=None):
         """Batched operator().  `imgs`: [F,H,W] uint8 numpy array (host memory: blocks, returns numpy
         arrays) or CUDA torch tensor (device memory: enqueues on `stream` and returns CUDA tensors).

@@ -181,6 +181,17 @@ class ORBmatcher:
         ur, dp, _ = self.stereo_refine(ex_left, ex_right, kl, kr, bi, bd, min_d, max_d, bf)
         return ur, dp
 
+    def stereo_matches_last(self, ex_left, ex_right, bf, mb, u_right=None, depth=None):
+        """Frame::ComputeStereoMatches (frame.cc:828-986) as one call on what the two extractors left on the device with
+        their last single-frame call (orbm_stereo_matches_last): nothing is uploaded.  Returns (mvuRight, mvDepth)."""
+        cap = ex_left.max_keypoints() if u_right is None else len(u_right)
+        ur = np.empty(cap, np.float32) if u_right is None else u_right
+        dp = np.empty(cap, np.float32) if depth is None else depth
+        nl = C.c_int(0)
+        self._check(self._lib.orbm_stereo_matches_last(self._m, ex_left._h, ex_right._h, float(bf), float(mb), ur.ctypes.data,
+                                                       dp.ctypes.data, cap, C.byref(nl)))
+        return ur[:nl.value], dp[:nl.value]
+
     def ComputeDistinctiveDescriptors(self, desc, offsets):
         """mappoint.cc:365-428 for a batch of map points: (best row per point, its median distance)."""
         desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)

@@ -180,6 +180,16 @@ def test_stereo_refine_and_full_stereo_matches(P, m, oracle):
         assert np.array_equal(sad, wsad) and ur.tobytes() == wur.tobytes() and dp.tobytes() == wdp.tobytes()
         ur2, dp2 = m.ComputeStereoMatches(exl, exr, kl, dl, kr, dr, bf, mb)
         assert ur2.tobytes() == wur.tobytes() and dp2.tobytes() == wdp.tobytes()
+        # the one-call form on the device-resident results of the two extractors, images in flight together
+        exl.extract_begin(left)
+        exr.extract_begin(right)
+        kl2, dl2 = np.empty(len(kl) + 8, P.KP_DTYPE), np.empty((len(kl) + 8, 32), np.uint8)
+        kr2, dr2 = np.empty(len(kr) + 8, P.KP_DTYPE), np.empty((len(kr) + 8, 32), np.uint8)
+        _, nl2 = exl.extract_end(kl2, dl2)
+        _, nr2 = exr.extract_end(kr2, dr2)
+        assert kl2[:nl2].tobytes() == kl.tobytes() and np.array_equal(dr2[:nr2], dr)
+        ur3, dp3 = m.stereo_matches_last(exl, exr, bf, mb)
+        assert ur3.tobytes() == wur.tobytes() and dp3.tobytes() == wdp.tobytes()
         ok = wur >= 0
         assert ok.sum() > 400
         assert abs(np.median(kl["x"][ok] - wur[ok]) - shift) < 0.6 or shift == 0
