@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 W, H, NFEAT, NLEV, SCALE, INI_TH, MIN_TH = 752, 480, 1000, 8, 1.2, 20, 7
 METRIC = "orb_frames_per_s_752x480_1000kp"
 DB_ROWS, N_QUERIES = 10_000_000, 1000
-KNN_XU_OPS, KNN_ALU_OPS = 6, 19   # per 256-bit pair in k_knn2's inner loop: 6 POPC; 8 LOP3 (xor) + 4 LOP3 (carry-save) + 3 IADD3 / LEA + 1 key + 3 VIMNMX
+KNN_XU_OPS, KNN_ALU_OPS = 6, 24   # per 256-bit pair in k_knn2's unrolled inner loop (profiles/r2_sass_excerpt.txt: 72 POPC, 235 LOP3, 36 VIMNMX, 17 IADD3 for 12 pairs;
+                                  # the 57 IMAD that do the additions issue on the FMA pipe and are not the limiter)
 WORKLOAD = "config 1 batched: blocks-v1 752x480, 1000 features, 8 levels, scale 1.2, FAST 20/7"
 
 

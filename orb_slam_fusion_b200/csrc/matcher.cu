@@ -179,8 +179,12 @@ __global__ void __launch_bounds__(128) k_knn2_merge(const unsigned long long* __
 }
 
 static int knn2_chunks(int64_t nd, int64_t* chunk_rows) {
-  // two waves of CTAs over 148 SMs for large databases, >= one tile per chunk for small ones
-  int64_t n_chunks = 296;
+  // Two CTAs are resident per SM (119 registers x 256 threads).  More chunks than one wave of 296 let the SMs that finish
+  // early pick up another chunk; measured on B200, 1000 queries (tools/knn2_slice_time.py): 10 M rows 15.02 / 14.92 / 14.87 /
+  // 14.90 ms at 296 / 444 / 592 / 740 chunks, 5 M rows 7.53 / 7.48 / 7.46 / 7.63, 2.5 M rows 3.79 / 3.76 / 3.87 / 3.98,
+  // 1.25 M rows (one rank's slice of the 8-GPU search) 1.97 / 1.91 / 2.07.  >= one tile per chunk for small databases.
+  static const int forced = [] { const char* e = getenv("ORBM_KNN_CHUNKS"); const int c = e ? atoi(e) : 0; return c > 0 && c <= 4096 ? c : 0; }();  // A/B runs
+  int64_t n_chunks = forced ? forced : (nd >= 4000000 ? 592 : 444);
   const int64_t tiles = (nd + kKnnTile - 1) / kKnnTile;
   if (n_chunks > tiles) n_chunks = tiles > 0 ? tiles : 1;
   int64_t rows = (nd + n_chunks - 1) / n_chunks;
