@@ -34,7 +34,11 @@ constexpr int kFtRawPW = kFtRawPitch / 4, kFtRawOrg = 3;  // words per raw row; 
 constexpr int kFtRawH = kFtH + 8;             // rows Y0-4 .. Y0+35
 static_assert(kFtRawPitch == kFastTileBoxW && kFtRawH == kFastTileBoxH, "TMA box of the host-side tensor maps");
 constexpr int kFtScH = kFtH + 2;              // score rows Y0-1 .. Y0+32
-constexpr int kFtStrip = 5;                   // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
+#ifndef ORBX_FAST_STRIP
+#define ORBX_FAST_STRIP 5
+#endif
+constexpr int kFtStrip = ORBX_FAST_STRIP;      // score rows per thread in the rejection pass: 34 columns x 7 groups x 5 rows
+static_assert(kFtRawW * ((kFtScH + kFtStrip - 1) / kFtStrip) <= kFtThreads, "one thread per (word column, strip)");
 constexpr int kFtMaxOut = ((kFtW + 8) / 2) * ((kFtH + 3) / 2) + 64;  // NMS survivors of one tile: at most every other pixel of every other row
 
 // byte-wise |a - b| > t for four pixels at once; t <= 126.  VABSDIFF4 is a native instruction,
@@ -64,20 +68,36 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
-  __shared__ __align__(128) uint32_t raw_w[kFtRawH * kFtRawPW];
-  __shared__ __align__(8) unsigned long long tile_bar;  // mbarrier the TMA tile load completes on
   // The blur's u16 intermediate and the detector's score map / lists are live in different phases
   // and share one buffer.
   constexpr int kScoreBytes = kFtScH * kFtPitch, kListBytes = 2 * kFtScH * kFtPitch, kOutBytes = 2 * kFtMaxOut;
   constexpr int kTmpBytes = 2 * (kFtH + 6) * kFtW;
   constexpr int kUnionBytes = kScoreBytes + kListBytes + kOutBytes > kTmpBytes ? kScoreBytes + kListBytes + kOutBytes : kTmpBytes;
-  __shared__ __align__(16) uint8_t u_mem[kUnionBytes];
+  // ONE shared object: every array is the same base plus a constant, so the shared-window base (three uniform-datapath
+  // instructions wherever a separate __shared__ array is first touched in a region) is formed once
+  struct __align__(128) Smem {
+    uint32_t raw_w[kFtRawH * kFtRawPW];
+    uint8_t u_mem[(kUnionBytes + 15) / 16 * 16];
+    unsigned long long tile_bar;  // mbarrier the TMA tile load completes on
+    int n_list, n_out, out_base, warp_corners[kFtWarps];
+    uint8_t xmask_l[kFtPitch], xmask_r[kFtPitch], ymask_u[kFtScH], ymask_d[kFtScH];  // 0 where the neighbour lies in another cell, else 255
+  };
+  __shared__ Smem sm;
+  uint32_t(&raw_w)[kFtRawH * kFtRawPW] = sm.raw_w;
+  unsigned long long& tile_bar = sm.tile_bar;
+  uint8_t* const u_mem = sm.u_mem;
   uint8_t* score = u_mem;
   uint16_t* list = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes);   // (score row << 8) | byte column of pixels to score
   uint16_t* outl = reinterpret_cast<uint16_t*>(u_mem + kScoreBytes + kListBytes);
   uint32_t* tmp2 = reinterpret_cast<uint32_t*>(u_mem);                 // blur: (kFtH + 6) / 2 row pairs x kFtW, (row 2p) | (row 2p+1) << 16
-  __shared__ int n_list, n_out, out_base, warp_corners[kFtWarps];
-  __shared__ uint8_t xmask_l[kFtPitch], xmask_r[kFtPitch], ymask_u[kFtScH], ymask_d[kFtScH];  // 0 where the neighbour lies in another cell, else 255
+  int& n_list = sm.n_list;
+  int& n_out = sm.n_out;
+  int& out_base = sm.out_base;
+  int(&warp_corners)[kFtWarps] = sm.warp_corners;
+  uint8_t(&xmask_l)[kFtPitch] = sm.xmask_l;
+  uint8_t(&xmask_r)[kFtPitch] = sm.xmask_r;
+  uint8_t(&ymask_u)[kFtScH] = sm.ymask_u;
+  uint8_t(&ymask_d)[kFtScH] = sm.ymask_d;
   const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
   // tile -> (level, tile column, tile row), precomputed on the host
