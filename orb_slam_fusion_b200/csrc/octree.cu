@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeo
   const size_t sbase = (size_t)f * g.sel_frame_cap + L.sel_off;
   int P = n_cand[f * ORBX_MAX_LEVELS + lev];
   if (P > L.cand_cap) P = L.cand_cap;
-  __shared__ int nsel_sh, n_keep;
+  int& nsel_sh = w.misc[0];  // (scalars in the same shared object as the tree: one shared-window base for the kernel)
+  int& n_keep = w.misc[1];
   // The iniThFAST -> minThFAST retry of orb_extractor.cc:783-801: k_fast emitted every FAST(min, nms)
   // survivor with its cell (in node_of); a cell that holds a survivor with response >= ini keeps only
   // those, any other cell keeps all.  The filtered list is what the reference hands to the quadtree.

@@ -59,11 +59,13 @@ struct OtWork {
   int* scan;    // [cap+1]  scratch for prefix sums
   unsigned long long* best;  // [cap] (response << 32 | ~order key) of the best point of each node
   int* sv;      // small scalar block (>= 16 ints), shared between threads
+  int* wsum;    // [2][32] warp totals of the block scan (device only; part of the same shared object as everything else)
+  int* misc;    // [2] scalars of the calling kernel
 };
 
 enum { SV_N = 0, SV_F, SV_M, SV_MEFF, SV_TOTALC, SV_DONE, SV_PHASE, SV_TOEXP, SV_CUR, SV_ERR };
 
-OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1 + 2) + 2 * (cap + 1) + 16 + 2; }
+OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1 + 2) + 2 * (cap + 1) + 16 + 2 + 64 + 2; }
 
 OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.cap = cap;
@@ -80,19 +82,22 @@ OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.scan = p; p += cap + 1;
   p += ((size_t)p & 7) ? 1 : 0;  // 8-byte alignment (the block itself is at least 8-byte aligned)
   w.best = (unsigned long long*)p; p += 2 * cap;
-  w.sv = p;
+  w.sv = p; p += 16;
+  w.wsum = p; p += 64;
+  w.misc = p;
 }
 
 // exclusive prefix sum of a[0..n) in place; a[n] receives the total.  Block-wide.
-OT_DEV void ot_excl_scan(int* a, int n) {
+OT_DEV void ot_excl_scan(int* a, int n, int* wsum) {
 #if defined(ORBX_HOST_EMUL)
+  (void)wsum;
   int s = 0;
   for (int i = 0; i < n; i++) { int v = a[i]; a[i] = s; s += v; }
   a[n] = s;
 #else
   // warp-shuffle scan; the running total lives in a register of every thread (read back from the
   // last warp's sum), so a chunk of blockDim.x elements costs two barriers
-  __shared__ int warp_sums[2][32];
+  int(*warp_sums)[32] = reinterpret_cast<int(*)[32]>(wsum);  // in the kernel's one shared object: no second shared-window base
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
   int carry = 0, buf = 0;
   for (int base = 0; base < n; base += nt, buf ^= 1) {
@@ -187,7 +192,7 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
   // erase empty roots, keep order
   OT_FOR(i, n_roots) w.scan[i] = w.cnt[0][i] > 0;
   OT_SYNC();
-  ot_excl_scan(w.scan, n_roots);
+  ot_excl_scan(w.scan, n_roots, w.wsum);
   OT_FOR(i, n_roots) {
     if (w.cnt[0][i] > 0) {
       const int j = w.scan[i];
@@ -214,7 +219,7 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     if (!fine) {
       OT_FOR(i, n) w.scan[i] = CNT[i] > 1;  // !no_more_ (:597-603)
       OT_SYNC();
-      ot_excl_scan(w.scan, n);
+      ot_excl_scan(w.scan, n, w.wsum);
       OT_FOR(i, n) {
         const int r = CNT[i] > 1 ? w.scan[i] : -1;
         w.rank[i] = r;
@@ -245,7 +250,7 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
       }
       OT_SYNC();
       OT_FOR(i, n) if (w.rank[i] >= 0) w.seq[w.rank[i]] = i;
-      ot_excl_scan(w.scan, n);
+      ot_excl_scan(w.scan, n, w.wsum);
       if (OT_TID0) sv[SV_M] = w.scan[n];
       OT_SYNC();
     }
@@ -271,7 +276,7 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
       w.scan[r] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
     }
     OT_SYNC();
-    ot_excl_scan(w.scan, m);  // scan[r] = children created before node r, scan[m] = total
+    ot_excl_scan(w.scan, m, w.wsum);  // scan[r] = children created before node r, scan[m] = total
     if (OT_TID0) sv[SV_MEFF] = m;
     OT_SYNC();
     if (fine) {
@@ -304,7 +309,7 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     // kept nodes: rank among the kept ones in list order (scan buffer is reused, so stash totals)
     OT_FOR(i, n) w.newpos[i] = !(w.rank[i] >= 0 && w.rank[i] < meff);
     OT_SYNC();
-    ot_excl_scan(w.newpos, n);
+    ot_excl_scan(w.newpos, n, w.wsum);
     OT_FOR(i, n) {
       const bool split = w.rank[i] >= 0 && w.rank[i] < meff;
       if (split) {

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   uint8_t* src_sm = rs_smem + ((128u - ((unsigned)__cvta_generic_to_shared(rs_smem) & 127u)) & 127u);
   uint16_t* hq = reinterpret_cast<uint16_t*>(src_sm + ((bh * BW + 127) & ~127));
   unsigned long long& tile_bar = *reinterpret_cast<unsigned long long*>(hq + bh * kRsTW);
-  __shared__ uint2 row_tab[kRsMaxTH];
+  // the row table lives in the same (dynamic) shared object as everything else: one shared-window base for the kernel
+  uint2* row_tab = reinterpret_cast<uint2*>(hq + bh * kRsTW + 8);
   const LevelGeom& D = g.lv[lev];
   const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
   const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
@@ -362,7 +363,7 @@ int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaSt
     int th, bw, bh;
     resize_tile_plan(g, lev, &th, &bw, &bh);
     dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 2 + 16;  // alignment slack, tile, H rows, mbarrier
+    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 2 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows, mbarrier, row table
     if (bw == kRsBwSmall)
       k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
     else if (bw == 256)
