@@ -29,6 +29,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <tuple>
 #include <vector>
 
@@ -47,6 +48,10 @@ struct Vector3f {
   Vector3f() : v{0, 0, 0} {}
   Vector3f(float a, float b, float c) : v{a, b, c} {}
   float operator()(int i) const { return v[i]; }
+  Vector3f operator-(const Vector3f &o) const { return Vector3f(v[0] - o.v[0], v[1] - o.v[1], v[2] - o.v[2]); }
+  Vector3f operator/(float s) const { return Vector3f(v[0] / s, v[1] / s, v[2] / s); }
+  float dot(const Vector3f &o) const { return v[0] * o.v[0] + v[1] * o.v[1] + v[2] * o.v[2]; }
+  float norm() const { return std::sqrt(dot(*this)); }
 };
 struct Vector2f {
   float v[2];
@@ -65,12 +70,25 @@ struct Matrix3f {
 namespace Sophus {
 struct SE3f {
   Eigen::Vector3f t;
+  SE3f() {}
+  SE3f(const Eigen::Matrix3f &, const Eigen::Vector3f &tt) : t(tt) {}
   SE3f operator*(const SE3f &o) const { SE3f r; r.t = Eigen::Vector3f(t(0) + o.t(0), t(1) + o.t(1), t(2) + o.t(2)); return r; }
   Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
   SE3f inverse() const { SE3f r; r.t = Eigen::Vector3f(-t(0), -t(1), -t(2)); return r; }
   Eigen::Vector3f translation() const { return t; }
   Eigen::Vector3f operator*(const Eigen::Vector3f &p) const { return Eigen::Vector3f(p(0) + t(0), p(1) + t(1), p(2) + t(2)); }
 };
+template <class T>
+struct Sim3 {  // scale + translation (the rotation of the harness' similarity is the identity)
+  float s = 1;
+  Eigen::Vector3f t;
+  Eigen::Matrix3f rotationMatrix() const { return Eigen::Matrix3f(); }
+  Eigen::Vector3f translation() const { return t; }
+  float scale() const { return s; }
+  Sim3 inverse() const { Sim3 r; r.s = 1 / s; r.t = Eigen::Vector3f(-t(0) / s, -t(1) / s, -t(2) / s); return r; }
+  Eigen::Vector3f operator*(const Eigen::Vector3f &p) const { return Eigen::Vector3f(s * p(0) + t(0), s * p(1) + t(1), s * p(2) + t(2)); }
+};
+typedef Sim3<float> Sim3f;
 }  // namespace Sophus
 
 namespace DBoW2 {  // 3rdparty/DBoW2/DBoW2/FeatureVector.h:24: a std::map from node id to feature indices
@@ -110,6 +128,17 @@ class ORBmatcher {
                              const bool bOnlyStereo, const bool bCoarse = false);
   int SearchByBoW(KeyFrame *pKF, class Frame &F, std::vector<MapPoint *> &vpMapPointMatches);
   int SearchByBoW(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12);
+  int SearchByProjection(class Frame &CurrentFrame, KeyFrame *pKF, const std::set<MapPoint *> &sAlreadyFound, const float th, const int ORBdist);
+  int SearchByProjection(KeyFrame *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint *> &vpPoints, std::vector<MapPoint *> &vpMatched,
+                         int th, float ratioHamming = 1.0);
+  int SearchByProjection(KeyFrame *pKF, Sophus::Sim3<float> &Scw, const std::vector<MapPoint *> &vpPoints,
+                         const std::vector<KeyFrame *> &vpPointsKFs, std::vector<MapPoint *> &vpMatched,
+                         std::vector<KeyFrame *> &vpMatchedKF, int th, float ratioHamming = 1.0);
+  int SearchForInitialization(class Frame &F1, class Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12,
+                              int windowSize = 10);
+  int SearchBySim3(KeyFrame *pKF1, KeyFrame *pKF2, std::vector<MapPoint *> &vpMatches12, const Sophus::Sim3f &S12, const float th);
+  int Fuse(KeyFrame *pKF, const vector<MapPoint *> &vpMapPoints, const float th = 3.0, const bool bRight = false);
+  int Fuse(KeyFrame *pKF, Sophus::Sim3f &Scw, const std::vector<MapPoint *> &vpPoints, float th, vector<MapPoint *> &vpReplacePoint);
   static const int TH_LOW;
   static const int TH_HIGH;
   static const int HISTO_LENGTH;
@@ -172,6 +201,15 @@ class KeyFrame {  // include/map/keyframe.h: what mappoint.cc:365-433 and orb_ma
     return grid->GetFeaturesInArea(x, y, r, -1, -1, bRight);
   }
   Sophus::SE3f pose;  // Tcw, translation only
+  // orb_matcher.cc:391-596, 1042-1516, 1730-1840
+  float fx = 1, fy = 1, cx = 0, cy = 0, bf_ = 0;
+  int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+  int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
+  float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
+  bool IsInImage(const float &x, const float &y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }  // keyframe.cc:775-777
+  std::set<MapPoint *> GetMapPoints();
+  void AddMapPoint(MapPoint *mp, const size_t &idx);
+  Eigen::Vector3f GetRightCameraCenter() { return pose.inverse().translation(); }
   Sophus::SE3f GetPose() { return pose; }
   Sophus::SE3f GetPoseInverse() { return pose.inverse(); }
   Sophus::SE3f GetRightPose() { return pose; }
@@ -198,7 +236,33 @@ class MapPoint {  // include/map/mappoint.h
   bool mbBad = false;
   int nObs = 0;
   std::mutex mMutexFeatures;
+  // the rest of the MapPoint interface the other matcher methods call, with the harness' values behind it
+  int id = 0, predicted_level = 0;
+  Eigen::Vector3f normal;
+  float min_dist = 0, max_dist = 1e30f;
+  std::map<KeyFrame *, int> in_kf;
+  Eigen::Vector3f GetNormal() { return normal; }
+  float GetMaxDistanceInvariance() { return max_dist; }
+  float GetMinDistanceInvariance() { return min_dist; }
+  int PredictScale(const float &, KeyFrame *) { return predicted_level; }
+  int PredictScale(const float &, Frame *) { return predicted_level; }
+  bool IsInKeyFrame(KeyFrame *kf) { return in_kf.count(kf) != 0; }
+  std::tuple<int, int> GetIndexInKeyFrame(KeyFrame *kf) {
+    std::map<KeyFrame *, int>::iterator it = in_kf.find(kf);
+    return std::make_tuple(it == in_kf.end() ? -1 : it->second, -1);
+  }
+  void AddObservation(KeyFrame *kf, int idx) { in_kf[kf] = idx; nObs++; log.push_back(std::make_tuple(1, id, idx)); }
+  void Replace(MapPoint *other) { mbBad = true; log.push_back(std::make_tuple(2, id, other->id)); }
+  static std::vector<std::tuple<int, int, int> > log;  // (1 AddObservation | 2 Replace | 3 AddMapPoint, point id, keypoint / other id)
 };
+std::vector<std::tuple<int, int, int> > MapPoint::log;
+std::set<MapPoint *> KeyFrame::GetMapPoints() {
+  std::set<MapPoint *> s;
+  for (size_t i = 0; i < mvpMapPoints.size(); i++)
+    if (mvpMapPoints[i] && !mvpMapPoints[i]->isBad()) s.insert(mvpMapPoints[i]);
+  return s;
+}
+void KeyFrame::AddMapPoint(MapPoint *mp, const size_t &idx) { mvpMapPoints[idx] = mp; MapPoint::log.push_back(std::make_tuple(3, mp->id, (int)idx)); }
 
 #include "matcher_consts.inc"
 #include "descriptor_distance.inc"
@@ -212,6 +276,13 @@ class MapPoint {  // include/map/mappoint.h
 #include "matcher_bow_kf.inc"
 #include "matcher_triangulation.inc"
 #include "matcher_maxima.inc"
+#include "matcher_project_sim3.inc"
+#include "matcher_project_sim3_kfs.inc"
+#include "matcher_init.inc"
+#include "matcher_fuse.inc"
+#include "matcher_fuse_sim3.inc"
+#include "matcher_sim3.inc"
+#include "matcher_project_reloc.inc"
 
 }  // namespace ORB_SLAM_FUSION
 
@@ -537,5 +608,8 @@ int reff_features_in_area(const void *keys_un, int n, float min_x, float max_x, 
   for (size_t i = 0; i < v.size() && (int)i < cap; i++) out[i] = (int)v[i];
   return (int)v.size();
 }
+
+// the class-level entry points of the remaining ORBmatcher methods, shared with tests/cpp/matcher_facade_harness.cc
+#include "matcher_harness.inc"
 
 }  // extern "C"

@@ -211,4 +211,7 @@ void facade_descriptor_distance(const uint8_t *a, const uint8_t *b, int n, int *
     out[i] = ORBmatcher::DescriptorDistance(cv::Mat(1, 32, CV_8U, (void *)(a + 32 * (size_t)i)), cv::Mat(1, 32, CV_8U, (void *)(b + 32 * (size_t)i)));
 }
 
+// the class-level entry points of the remaining ORBmatcher methods, shared with oracle/ref_frame_shim.cc
+#include "matcher_harness.inc"
+
 }  // extern "C"

@@ -202,6 +202,7 @@ class KeyFrame {
   int mnGridCols = FRAME_GRID_COLS, mnGridRows = FRAME_GRID_ROWS;
   float mfGridElementWidthInv = 0, mfGridElementHeightInv = 0;
   Sophus::SE3f pose;
+  Frame *grid = nullptr;  // (harness bookkeeping shared with oracle/ref_frame_shim.cc; the product's class never reads it)
 };
 
 }  // namespace ORB_SLAM_FUSION
