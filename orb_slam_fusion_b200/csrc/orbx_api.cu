@@ -298,6 +298,7 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
   if (octree_smem_bytes(node_cap) > 200 * 1024)
     return fail(h, ORBX_E_UNSUPPORTED, "per-level quota %d needs more shared memory than one SM has", node_cap);
   CU(h, octree_configure(node_cap));
+  CU(h, resize_configure());
   h->launches += launch_pattern_init(h->slot[0].stream);
   CU(h, cudaStreamSynchronize(h->slot[0].stream));
 

@@ -57,6 +57,7 @@ int launch_describe(const FrameGeom& g, const BatchBuffers& b, int frames, orbx_
 int launch_synth(int kind, uint8_t* dst, int frames, int w, int h, size_t row_stride, size_t frame_stride,
                  uint64_t seed, uint64_t first_frame, int shift_x, uint64_t noise_seed, cudaStream_t st);
 
+cudaError_t resize_configure();                   // opt in to the dynamic shared memory of k_resize_tma
 cudaError_t octree_configure(int node_cap);  // opt in to the dynamic shared memory the tree needs
 size_t octree_smem_bytes(int node_cap);
 

@@ -226,10 +226,12 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   // the TMA destination must be 128-byte aligned; the dynamic region is only 16-byte aligned when the
   // kernel also has static shared memory, so the base is rounded up here (the launch adds 128 bytes)
   uint8_t* src_sm = rs_smem + ((128u - ((unsigned)__cvta_generic_to_shared(rs_smem) & 127u)) & 127u);
-  uint16_t* hq = reinterpret_cast<uint16_t*>(src_sm + ((bh * BW + 127) & ~127));
+  // H >> 4 (15 bits) is kept PRE-SHIFTED as (H >> 4) << 16 in 32-bit words: the vertical pass multiplies with IMAD.HI and needs
+  // neither a shift nor a mask per product
+  uint32_t* hq = reinterpret_cast<uint32_t*>(src_sm + ((bh * BW + 127) & ~127));
   unsigned long long& tile_bar = *reinterpret_cast<unsigned long long*>(hq + bh * kRsTW);
   // the row table lives in the same (dynamic) shared object as everything else: one shared-window base for the kernel
-  uint2* row_tab = reinterpret_cast<uint2*>(hq + bh * kRsTW + 8);
+  uint2* row_tab = reinterpret_cast<uint2*>(hq + bh * kRsTW + 4);
   const LevelGeom& D = g.lv[lev];
   const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
   const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
@@ -286,7 +288,8 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
       const int dy = min(y0 + tid, D.h - 1);
       const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));
       const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));
-      row_tab[tid] = make_uint2(yo - (uint32_t)row_lo * 0x10001u, yb);
+      // byte offsets of the two H rows inside hq (row * 128 words * 4 bytes < 2^16), (b0 | b1 << 16)
+      row_tab[tid] = make_uint2((yo - (uint32_t)row_lo * 0x10001u) * (uint32_t)(kRsTW * 4), yb);
     }
     __syncthreads();  // every thread sees the initialised barrier
     {
@@ -303,11 +306,12 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
         if (i < rpg && r0 + i < n_rows) {
           const uint32_t w0 = wp[i * (BW / 4)], w1 = wp[i * (BW / 4) + 1], w2 = wp[i * (BW / 4) + 2];
           const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // bytes sx0 .. sx0+7
-          const uint32_t o0 = __dp2a_lo(al[0], __byte_perm(lo, hi, sel[0]), 0u) >> 4;
-          const uint32_t o1 = __dp2a_lo(al[1], __byte_perm(lo, hi, sel[1]), 0u) >> 4;
-          const uint32_t o2 = __dp2a_lo(al[2], __byte_perm(lo, hi, sel[2]), 0u) >> 4;
-          const uint32_t o3 = __dp2a_lo(al[3], __byte_perm(lo, hi, sel[3]), 0u) >> 4;
-          *reinterpret_cast<uint2*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+          // (H >> 4) << 16 == (H & ~15) << 12: H < 2^20, nothing is lost at the top
+          const uint32_t o0 = (__dp2a_lo(al[0], __byte_perm(lo, hi, sel[0]), 0u) & ~15u) << 12;
+          const uint32_t o1 = (__dp2a_lo(al[1], __byte_perm(lo, hi, sel[1]), 0u) & ~15u) << 12;
+          const uint32_t o2 = (__dp2a_lo(al[2], __byte_perm(lo, hi, sel[2]), 0u) & ~15u) << 12;
+          const uint32_t o3 = (__dp2a_lo(al[3], __byte_perm(lo, hi, sel[3]), 0u) & ~15u) << 12;
+          *reinterpret_cast<uint4*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint4(o0, o1, o2, o3);
         }
       }
     }
@@ -326,16 +330,16 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
       for (int i = 0; i < kVRows; i++) {
         if (y0 + yy0 + i < y1) {
           const uint2 rt = row_tab[yy0 + i];
-          const int r0 = (int)(rt.x & 0xFFFFu), r1 = (int)(rt.x >> 16);
           const uint32_t b0 = rt.y & 0xFFFFu, b1 = rt.y >> 16;
-          const uint2 u0 = *reinterpret_cast<const uint2*>(&hq[r0 * kRsTW + 4 * q]);
-          const uint2 u1 = *reinterpret_cast<const uint2*>(&hq[r1 * kRsTW + 4 * q]);
+          const uint8_t* hb = reinterpret_cast<const uint8_t*>(hq) + 16 * q;
+          const uint4 u0 = *reinterpret_cast<const uint4*>(hb + (rt.x & 0xFFFFu));
+          const uint4 u1 = *reinterpret_cast<const uint4*>(hb + (rt.x >> 16));
           // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
           // cv::resize can never clip and is not spelled out
-          const uint32_t v0 = (__umulhi(b1, u1.x << 16) + __umulhi(b0, u0.x << 16) + 2u) >> 2;
-          const uint32_t v1 = (__umulhi(b1, u1.x & 0xFFFF0000u) + __umulhi(b0, u0.x & 0xFFFF0000u) + 2u) >> 2;
-          const uint32_t v2 = (__umulhi(b1, u1.y << 16) + __umulhi(b0, u0.y << 16) + 2u) >> 2;
-          const uint32_t v3 = (__umulhi(b1, u1.y & 0xFFFF0000u) + __umulhi(b0, u0.y & 0xFFFF0000u) + 2u) >> 2;
+          const uint32_t v0 = (__umulhi(b1, u1.x) + __umulhi(b0, u0.x) + 2u) >> 2;
+          const uint32_t v1 = (__umulhi(b1, u1.y) + __umulhi(b0, u0.y) + 2u) >> 2;
+          const uint32_t v2 = (__umulhi(b1, u1.z) + __umulhi(b0, u0.z) + 2u) >> 2;
+          const uint32_t v3 = (__umulhi(b1, u1.w) + __umulhi(b0, u0.w) + 2u) >> 2;
           // a quad that straddles the right edge spills <= 3 bytes into the row padding, which nothing
           // reads before k_border rewrites it
           *reinterpret_cast<uint32_t*>(d + i * D.pitch) = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
@@ -357,13 +361,19 @@ void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh) {
   *bh = need_h < kRsRows ? need_h : kRsRows;
 }
 
+cudaError_t resize_configure() {  // scale factors near 2 need more than the default 48 KB of dynamic shared memory
+  cudaError_t e = cudaFuncSetAttribute(k_resize_tma<kRsBwSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resize_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  return e;
+}
+
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   int n = 0;
   for (int lev = 1; lev < g.nlev; lev++) {
     int th, bw, bh;
     resize_tile_plan(g, lev, &th, &bw, &bh);
     dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 2 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows, mbarrier, row table
+    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
     if (bw == kRsBwSmall)
       k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
     else if (bw == 256)
