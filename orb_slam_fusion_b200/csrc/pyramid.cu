@@ -214,6 +214,12 @@ __global__ void __launch_bounds__(256, ORBX_RS_MINB) k_resize(const __grid_const
 // The innermost TMA coordinate must put the box on a 16-byte boundary of the row (an unaligned start
 // faults with "illegal instruction" on sm_100a), so the box starts at the source column rounded down to 16.
 constexpr int kRsSrcAlign = 15, kRsBwSmall = 176;
+__device__ __forceinline__ uint32_t mulhi_plain(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));  // volatile: not to be fused into mad.hi
+  return d;
+}
+__device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b) { return a + b + 2u; }
 #ifndef ORBX_RS_TMA_MINB
 #define ORBX_RS_TMA_MINB 5
 #endif
@@ -336,10 +342,12 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
           const uint4 u1 = *reinterpret_cast<const uint4*>(hb + (rt.x >> 16));
           // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
           // cv::resize can never clip and is not spelled out
-          const uint32_t v0 = (__umulhi(b1, u1.x) + __umulhi(b0, u0.x) + 2u) >> 2;
-          const uint32_t v1 = (__umulhi(b1, u1.y) + __umulhi(b0, u0.y) + 2u) >> 2;
-          const uint32_t v2 = (__umulhi(b1, u1.z) + __umulhi(b0, u0.z) + 2u) >> 2;
-          const uint32_t v3 = (__umulhi(b1, u1.w) + __umulhi(b0, u0.w) + 2u) >> 2;
+          // two plain multiply-highs and ONE three-input add per pixel (left to itself the compiler chains the second
+          // product as a 64-bit multiply-add, which costs a zeroed register pair and a separate +2 per pixel)
+          const uint32_t v0 = add3(mulhi_plain(b1, u1.x), mulhi_plain(b0, u0.x)) >> 2;
+          const uint32_t v1 = add3(mulhi_plain(b1, u1.y), mulhi_plain(b0, u0.y)) >> 2;
+          const uint32_t v2 = add3(mulhi_plain(b1, u1.z), mulhi_plain(b0, u0.z)) >> 2;
+          const uint32_t v3 = add3(mulhi_plain(b1, u1.w), mulhi_plain(b0, u0.w)) >> 2;
           // a quad that straddles the right edge spills <= 3 bytes into the row padding, which nothing
           // reads before k_border rewrites it
           *reinterpret_cast<uint32_t*>(d + i * D.pitch) = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410);
