@@ -58,6 +58,29 @@ __device__ __forceinline__ int reflect1(int p, int len) {  // reflect-101, one f
 // every other pixel of every other row survives a 3x3 NMS), so this stays 0; the fuzz tests assert it (orbx_debug_dropped).
 __device__ unsigned int g_fast_dropped = 0;
 
+// Shared-memory accesses through a 32-bit shared-window address held in a register (see the note in the scoring loop).
+template <int OFF = 0>
+__device__ __forceinline__ int lds_u8(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// the 16 ring pixels of a candidate from the raw tile: byte loads at compile-time offsets from one 32-bit shared address
+constexpr int kRingDx[16] = ORBX_RING_DX, kRingDy[16] = ORBX_RING_DY;
+template <int K>
+__device__ __forceinline__ void ring_load(uint32_t c, int (&r)[16]) {
+  asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(r[K]) : "r"(c), "n"(kRingDy[K] * kFtRawPitch + kRingDx[K]));
+  if constexpr (K < 15) ring_load<K + 1>(c, r);
+}
+
 #ifndef ORBX_FAST_MINB
 #define ORBX_FAST_MINB 7
 #endif
@@ -321,28 +344,31 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   const int nl = n_list;
   const int wrp = tid >> 5;
   int n_corner = 0;  // corners this warp has packed (warp-uniform)
+  // 32-bit shared-window addresses held in registers, explicit ld / st.shared: left to generic pointers the compiler
+  // re-forms the window base (five uniform-datapath instructions) at every use inside these loops
+  const uint32_t sm_raw = (uint32_t)__cvta_generic_to_shared(raw_w) + 4 * kFtRawOrg + 3 * kFtRawPitch;
+  const uint32_t sm_score = (uint32_t)__cvta_generic_to_shared(score), sm_list = (uint32_t)__cvta_generic_to_shared(list);
   for (int c0 = wrp * 32; c0 < nl; c0 += kFtThreads) {
     const int i = c0 + lane;
     bool corner = false;
-    uint16_t item = 0;
+    uint32_t item = 0;
     if (i < nl) {
-      item = list[i];
-      const int rr = item >> 8, cb = item & 255;
-      const uint8_t* c = &raw[(rr + 3) * kFtRawPitch + cb + 4 * kFtRawOrg];
-      const int dxs[16] = ORBX_RING_DX, dys[16] = ORBX_RING_DY;
-      int r[16];
-#pragma unroll
-      for (int k = 0; k < 16; k++) r[k] = c[dys[k] * kFtRawPitch + dxs[k]];
-      const int sc = fast9_score(c[0], r, lo);
+      item = lds_u16(sm_list + 2u * (uint32_t)i);
+      const int rr = (int)(item >> 8), cb = (int)(item & 255u);
+      const uint32_t c = sm_raw + (uint32_t)(rr * kFtRawPitch + cb);
+      int r[16], ctr;
+      ring_load<0>(c, r);
+      asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ctr) : "r"(c));
+      const int sc = fast9_score(ctr, r, lo);
       if (sc > 0) {
-        score[rr * kFtPitch + cb] = (uint8_t)sc;
+        sts_u8(sm_score + (uint32_t)(rr * kFtPitch + cb), (uint32_t)sc);
         corner = rr >= 1 && rr <= kFtH && cb >= 4 && cb < 4 + kFtW;  // not a halo pixel
       }
     }
     const unsigned bal = __ballot_sync(0xffffffffu, corner);  // every lane has read its item
     if (corner) {
       const int v = n_corner + __popc(bal & ((1u << lane) - 1u));
-      list[(v >> 5) * kFtThreads + (wrp << 5) + (v & 31)] = item;
+      sts_u16(sm_list + 2u * (uint32_t)((v >> 5) * kFtThreads + (wrp << 5) + (v & 31)), item);
     }
     n_corner += __popc(bal);
   }
@@ -357,24 +383,27 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
     pre[0] = 0;
 #pragma unroll
     for (int k = 0; k < kFtWarps; k++) pre[k + 1] = pre[k] + warp_corners[k];
+    const uint32_t sm_xl = (uint32_t)__cvta_generic_to_shared(xmask_l), sm_xr = (uint32_t)__cvta_generic_to_shared(xmask_r);
+    const uint32_t sm_yu = (uint32_t)__cvta_generic_to_shared(ymask_u), sm_yd = (uint32_t)__cvta_generic_to_shared(ymask_d);
+    const uint32_t sm_outl = (uint32_t)__cvta_generic_to_shared(outl);
     for (int gi = tid; gi < pre[kFtWarps]; gi += kFtThreads) {
       int w = 0, off = 0;
 #pragma unroll
       for (int k = 1; k < kFtWarps; k++)
         if (gi >= pre[k]) { w = k; off = pre[k]; }
       const int v = gi - off;
-      const uint16_t item = list[(v >> 5) * kFtThreads + (w << 5) + (v & 31)];
-      const int rr = item >> 8, cb = item & 255;
-      const uint8_t* sp = &score[rr * kFtPitch + cb];
-      const int s = sp[0];
-      const int ml = xmask_l[cb], mr = xmask_r[cb], mu = ymask_u[rr], md = ymask_d[rr];
-      int m = imax3(sp[-1] & ml, sp[1] & mr, sp[-kFtPitch] & mu);
-      m = imax3(m, sp[kFtPitch] & md, sp[-kFtPitch - 1] & (ml & mu));
-      m = imax3(m, sp[-kFtPitch + 1] & (mr & mu), sp[kFtPitch - 1] & (ml & md));
-      m = imax(m, sp[kFtPitch + 1] & (mr & md));
+      const uint32_t item = lds_u16(sm_list + 2u * (uint32_t)((v >> 5) * kFtThreads + (w << 5) + (v & 31)));
+      const uint32_t rr = item >> 8, cb = item & 255u;
+      const uint32_t sp = sm_score + rr * kFtPitch + cb;
+      const int s = lds_u8(sp);
+      const int ml = lds_u8(sm_xl + cb), mr = lds_u8(sm_xr + cb), mu = lds_u8(sm_yu + rr), md = lds_u8(sm_yd + rr);
+      int m = imax3(lds_u8<-1>(sp) & ml, lds_u8<1>(sp) & mr, lds_u8<-kFtPitch>(sp) & mu);
+      m = imax3(m, lds_u8<kFtPitch>(sp) & md, lds_u8<-kFtPitch - 1>(sp) & (ml & mu));
+      m = imax3(m, lds_u8<-kFtPitch + 1>(sp) & (mr & mu), lds_u8<kFtPitch - 1>(sp) & (ml & md));
+      m = imax(m, lds_u8<kFtPitch + 1>(sp) & (mr & md));
       if (s > m) {
         const int o = atomicAdd(&n_out, 1);
-        if (o < kFtMaxOut) outl[o] = item;
+        if (o < kFtMaxOut) sts_u16(sm_outl + 2u * (uint32_t)o, item);
         else atomicAdd(&g_fast_dropped, 1u);  // never expected: kFtMaxOut is the NMS bound of a tile
       }
     }
@@ -388,8 +417,9 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   __syncthreads();
   const size_t cbase = (size_t)f * g.cand_frame_cap + L.cand_off;
   for (int i = tid; i < no; i += kFtThreads) {
-    const int rr = outl[i] >> 8, cb = outl[i] & 255;
-    const int s = score[rr * kFtPitch + cb];
+    const uint32_t item = lds_u16((uint32_t)__cvta_generic_to_shared(outl) + 2u * (uint32_t)i);
+    const int rr = (int)(item >> 8), cb = (int)(item & 255u);
+    const int s = lds_u8(sm_score + (uint32_t)(rr * kFtPitch + cb));
     const int x = X0 - 4 + cb, y = Y0 - 1 + rr;
     const int cell = div_rcp(y - kEdge, L.hcell_rcp) * L.ncols + div_rcp(x - kEdge, L.wcell_rcp);
     const int pos = out_base + i;
