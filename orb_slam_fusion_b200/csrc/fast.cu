@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   uint8_t(&xmask_r)[kFtPitch] = sm.xmask_r;
   uint8_t(&ymask_u)[kFtScH] = sm.ymask_u;
   uint8_t(&ymask_d)[kFtScH] = sm.ymask_d;
-  const uint8_t* raw = reinterpret_cast<const uint8_t*>(raw_w);
 
   // tile -> (level, tile column, tile row), precomputed on the host
   const uint32_t tinfo = __ldg(tile_tab + blockIdx.x);
@@ -447,6 +446,16 @@ int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStrea
   // n_cand and cell_strong were zeroed by k_import, the first kernel of every pipeline
   dim3 grid(g.total_blur_tiles, 1, frames);
   k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
+  return 1;
+}
+
+// levels [lev, lev_end) only (the single-frame pipeline forks per level: level l's tiles need nothing but level l's plane)
+int launch_fast_levels(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, int lev_end, cudaStream_t st) {
+  const int first = g.lv[lev].blur_tile_base;
+  const int count = (lev_end < g.nlev ? g.lv[lev_end].blur_tile_base : g.total_blur_tiles) - first;
+  dim3 grid(count, 1, frames);
+  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong,
+                                          b.tile_tab + first);
   return 1;
 }
 

@@ -10,14 +10,13 @@
 
 namespace orbx {
 
-__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
-                                                const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
-                                                uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
-                                                int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
-                                                uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
-                                                int32_t* __restrict__ n_sel) {
+__device__ __forceinline__ void octree_problem(const FrameGeom& g, const int lev, const int f, const uint32_t* __restrict__ raw_xy,
+                                               const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
+                                               uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
+                                               int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
+                                               uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
+                                               int32_t* __restrict__ n_sel) {
   extern __shared__ int ot_mem[];
-  const int lev = blockIdx.x, f = blockIdx.y;
   const LevelGeom& L = g.lv[lev];
   OtWork w;
   ot_carve(w, ot_mem, g.node_cap);
@@ -68,10 +67,37 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeo
   if (threadIdx.x == 0) n_sel[f * ORBX_MAX_LEVELS + lev] = nsel_sh;
 }
 
+__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
+                                                const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
+                                                uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
+                                                int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
+                                                uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
+                                                int32_t* __restrict__ n_sel) {
+  octree_problem(g, blockIdx.x, blockIdx.y, raw_xy, raw_sc, cell_strong, cand_xy, cand_sc, node_of, n_cand, sel_xy, sel_sc, n_sel);
+}
+
+// the same problem for the levels lev, lev + 1, ... (grid = frames x levels): the single-frame pipeline runs levels as parallel branches
+__global__ void __launch_bounds__(256) k_octree_level(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
+                                                      const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
+                                                      uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
+                                                      int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
+                                                      uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
+                                                      int32_t* __restrict__ n_sel, int lev) {
+  octree_problem(g, lev + blockIdx.y, blockIdx.x, raw_xy, raw_sc, cell_strong, cand_xy, cand_sc, node_of, n_cand, sel_xy, sel_sc, n_sel);
+}
+
 size_t octree_smem_bytes(int node_cap) { return sizeof(int) * (size_t)ot_work_ints(node_cap); }
 
 cudaError_t octree_configure(int node_cap) {
-  return cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(node_cap));
+  cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(node_cap));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem_bytes(node_cap));
+  return e;
+}
+
+int launch_octree_levels(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, int lev_end, cudaStream_t st) {
+  k_octree_level<<<dim3(frames, lev_end - lev), 256, octree_smem_bytes(g.node_cap), st>>>(g, b.cand_raw_xy, b.cand_raw_sc, b.cell_strong, b.cand_xy, b.cand_sc,
+                                                                    b.node_of, b.n_cand, b.sel_xy, b.sel_sc, b.n_sel, lev);
+  return 1;
 }
 
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {

@@ -93,6 +93,9 @@ struct orbx_extractor {
   int graph_launches = 0;            // kernels one replay launches
   uint8_t* h_out = nullptr;          // pinned: out_cap keypoint records, out_cap descriptor rows, then n and n_mono
   uint8_t* d_single = nullptr;       // the same block on the device: the single-frame path returns everything in ONE copy
+  // single-frame graph: the levels run as parallel branches (fork after level l exists, join before the slot plan)
+  cudaStream_t fork_stream[ORBX_MAX_LEVELS] = {};
+  cudaEvent_t ev_level[ORBX_MAX_LEVELS] = {}, ev_branch[ORBX_MAX_LEVELS] = {};
   bool single_pending = false;       // orbx_extract_begin has enqueued a frame that orbx_extract_end has not collected
   int single_n = -1;                 // keypoints of the last collected single frame (they stay in d_single)
   // optional per-stage timing (orbx_set_profiling): one event set per enqueued chunk
@@ -435,6 +438,45 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   h->launches += n;
 }
 
+// The same kernels for ONE frame as a forked dependency graph (recorded by stream capture): level l's detector tiles and
+// quadtree need nothing but level l's plane, so they leave the resize chain as a branch as soon as that plane exists and
+// all branches join before the slot plan.  The critical path drops from import + 7 resizes + detector + quadtree of ALL
+// levels to import + 7 resizes + the smallest level's detector and quadtree (the big level-0 quadtree runs beside the chain).
+int enqueue_single_forked(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int lap0, int lap1,
+                          orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono, cudaStream_t st) {
+  FrameGeom g = h->g;
+  g.lap0 = lap0;
+  g.lap1 = lap1;
+  for (int l = 0; l < g.nlev; l++) {
+    if (!h->fork_stream[l] && cudaStreamCreateWithFlags(&h->fork_stream[l], cudaStreamNonBlocking) != cudaSuccess) return -1;
+    if (!h->ev_level[l] && cudaEventCreateWithFlags(&h->ev_level[l], cudaEventDisableTiming) != cudaSuccess) return -1;
+    if (!h->ev_branch[l] && cudaEventCreateWithFlags(&h->ev_branch[l], cudaEventDisableTiming) != cudaSuccess) return -1;
+  }
+  // levels < n_fork leave as branches; the rest run on the trunk in one detector and one quadtree launch after the chain
+  static const int fork_env = [] { const char* e = getenv("ORBX_SINGLE_FORK_LEVELS"); return e ? atoi(e) : -1; }();  // A/B knob
+  // measured on B200 (tools/p50_pinned.py, 752x480, 8 levels): p50 0.1077 ms unforked, 0.1005 with 7 branches, 0.0994 with 5 --
+  // the three smallest levels are cheaper as one detector + one quadtree launch behind the chain than as three more branches
+  const int n_fork = fork_env >= 0 && fork_env < g.nlev ? fork_env : (g.nlev > 3 ? g.nlev - 3 : 0);
+  int n = launch_import(g, s.b, d_src, row_stride, frame_stride, 1, st);
+  for (int l = 0; l < g.nlev; l++) {
+    if (l > 0) n += launch_resize_level(g, s.b, 1, l, st);
+    if (l < n_fork) {
+      cudaStream_t br = h->fork_stream[l];
+      cudaEventRecord(h->ev_level[l], st);
+      cudaStreamWaitEvent(br, h->ev_level[l], 0);
+      n += launch_fast_levels(g, s.b, 1, l, l + 1, br);
+      n += launch_octree_levels(g, s.b, 1, l, l + 1, br);
+      cudaEventRecord(h->ev_branch[l], br);
+    }
+  }
+  n += launch_fast_levels(g, s.b, 1, n_fork, g.nlev, st);
+  n += launch_octree_levels(g, s.b, 1, n_fork, g.nlev, st);
+  for (int l = 0; l < n_fork; l++) cudaStreamWaitEvent(st, h->ev_branch[l], 0);
+  n += launch_describe(g, s.b, 1, d_kps, d_desc, cap, d_n, d_nmono, 0, st);
+  h->launches += n;
+  return n;
+}
+
 // Host frames -> device staging buffer of slot `s`.  Rows that are (nearly) contiguous go over PCIe
 // as ONE linear copy with their padding (a 2-D copy is one DMA descriptor per 752-byte row and runs
 // at a fraction of the link rate); the import kernel reads any row stride.
@@ -537,6 +579,11 @@ void orbx_destroy(orbx_t* h) {
   free_geometry(h);
   for (cudaEvent_t e : h->ev_used) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  for (int l = 0; l < ORBX_MAX_LEVELS; l++) {
+    if (h->fork_stream[l]) cudaStreamDestroy(h->fork_stream[l]);
+    if (h->ev_level[l]) cudaEventDestroy(h->ev_level[l]);
+    if (h->ev_branch[l]) cudaEventDestroy(h->ev_branch[l]);
+  }
   for (auto& s : h->slot) {
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
@@ -723,9 +770,17 @@ int orbx_extract_begin(orbx_t* h, const uint8_t* img, int w, int hh, size_t stri
     }
     if (!h->graph) {
       cudaGraph_t graph = nullptr;
+      // streams and events of the branches are created before the capture starts
+      for (int l = 0; l < h->g.nlev; l++) {
+        if (!h->fork_stream[l]) CU(h, cudaStreamCreateWithFlags(&h->fork_stream[l], cudaStreamNonBlocking));
+        if (!h->ev_level[l]) CU(h, cudaEventCreateWithFlags(&h->ev_level[l], cudaEventDisableTiming));
+        if (!h->ev_branch[l]) CU(h, cudaEventCreateWithFlags(&h->ev_branch[l], cudaEventDisableTiming));
+      }
       CU(h, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
       const long long launches_before = h->launches;
-      enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, dk, dd, h->out_cap, dn, dn + 1, 0, s.stream);
+      static const bool linear = [] { const char* e = getenv("ORBX_SINGLE_LINEAR"); return e && e[0] == '1'; }();  // A/B: the unforked chain
+      if (linear) enqueue_pipeline(h, s, s.d_img, drs, dfs, 1, lap0, lap1, dk, dd, h->out_cap, dn, dn + 1, 0, s.stream);
+      else enqueue_single_forked(h, s, s.d_img, drs, dfs, lap0, lap1, dk, dd, h->out_cap, dn, dn + 1, s.stream);
       cudaMemcpyAsync(h->h_out, h->d_single, single_bytes, cudaMemcpyDeviceToHost, s.stream);
       h->graph_launches = (int)(h->launches - launches_before);
       h->launches = launches_before;

@@ -46,6 +46,10 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 // tile plan of the resize of level `lev`: output rows per tile, TMA box (bytes x rows) of the source tile; bw == 0: no TMA
 void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh);
+// per-level launchers: the single-frame pipeline runs level l's detector and quadtree as a branch beside the resize chain
+int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, cudaStream_t st);
+int launch_fast_levels(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, int lev_end, cudaStream_t st);    // levels [lev, lev_end)
+int launch_octree_levels(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, int lev_end, cudaStream_t st);
 int launch_border(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // blur + FAST, one kernel
 cudaError_t fast_dropped(unsigned int* out, bool reset);  // candidates dropped by k_fast_blur since the last reset (expected: 0)

@@ -375,21 +375,23 @@ cudaError_t resize_configure() {  // scale factors near 2 need more than the def
   return e;
 }
 
+int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, cudaStream_t st) {
+  int th, bw, bh;
+  resize_tile_plan(g, lev, &th, &bw, &bh);
+  dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
+  const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
+  if (bw == kRsBwSmall)
+    k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+  else if (bw == 256)
+    k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+  else
+    k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
+  return 1;
+}
+
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   int n = 0;
-  for (int lev = 1; lev < g.nlev; lev++) {
-    int th, bw, bh;
-    resize_tile_plan(g, lev, &th, &bw, &bh);
-    dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-    const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
-    if (bw == kRsBwSmall)
-      k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
-    else if (bw == 256)
-      k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
-    else
-      k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
-    n++;
-  }
+  for (int lev = 1; lev < g.nlev; lev++) n += launch_resize_level(g, b, frames, lev, st);
   return n;
 }
 
