@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeo
                                                 int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
                                                 uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
                                                 int32_t* __restrict__ n_sel) {
-  octree_problem(g, blockIdx.x, blockIdx.y, raw_xy, raw_sc, cell_strong, cand_xy, cand_sc, node_of, n_cand, sel_xy, sel_sc, n_sel);
+  // level-major launch order (level = blockIdx.y, the slow index): the long level-0 problems of all frames start first and
+  // the short top-level ones fill the tail of the launch
+  octree_problem(g, blockIdx.y, blockIdx.x, raw_xy, raw_sc, cell_strong, cand_xy, cand_sc, node_of, n_cand, sel_xy, sel_sc, n_sel);
 }
 
 // the same problem for the levels lev, lev + 1, ... (grid = frames x levels): the single-frame pipeline runs levels as parallel branches
@@ -101,7 +103,7 @@ int launch_octree_levels(const FrameGeom& g, const BatchBuffers& b, int frames, 
 }
 
 int launch_octree(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
-  dim3 grid(g.nlev, frames);
+  dim3 grid(frames, g.nlev);
   // The passes are short and barrier-bound.  Batches: 128-thread CTAs waste fewer idle warps (0.31 vs 0.45 ms per
   // 512 frames); a single frame has only 8 CTAs in flight and wants the shorter point loops of 256 threads
   // (54 vs 65 us).  ORBX_OCTREE_THREADS overrides (A/B runs).
