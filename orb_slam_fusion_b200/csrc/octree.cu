@@ -67,7 +67,10 @@ __device__ __forceinline__ void octree_problem(const FrameGeom& g, const int lev
   if (threadIdx.x == 0) n_sel[f * ORBX_MAX_LEVELS + lev] = nsel_sh;
 }
 
-__global__ void __launch_bounds__(256) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
+#ifndef ORBX_OCTREE_MINB
+#define ORBX_OCTREE_MINB 5  // 48 registers: 0.193 -> 0.187 ms per 512 frames (4: 0.200, 6: 0.201)
+#endif
+__global__ void __launch_bounds__(256, ORBX_OCTREE_MINB) k_octree(const __grid_constant__ FrameGeom g, const uint32_t* __restrict__ raw_xy,
                                                 const uint8_t* __restrict__ raw_sc, const int32_t* __restrict__ cell_strong,
                                                 uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                                 int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
