@@ -768,6 +768,7 @@ def run_ours(args):
     other_configs = run_other_configs(P, A, torch, world, rank, local, dev, barrier, max_over_ranks, measured_peaks()[0], world == 1)
     log('configs 2-4 done')
 
+    sharding.close_comms()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

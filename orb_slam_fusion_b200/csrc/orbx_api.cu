@@ -442,16 +442,12 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
 // quadtree need nothing but level l's plane, so they leave the resize chain as a branch as soon as that plane exists and
 // all branches join before the slot plan.  The critical path drops from import + 7 resizes + detector + quadtree of ALL
 // levels to import + 7 resizes + the smallest level's detector and quadtree (the big level-0 quadtree runs beside the chain).
-int enqueue_single_forked(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int lap0, int lap1,
-                          orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono, cudaStream_t st) {
+// (the branches' streams and events exist before the capture starts: orbx_extract_begin creates them)
+void enqueue_single_forked(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int lap0, int lap1,
+                           orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono, cudaStream_t st) {
   FrameGeom g = h->g;
   g.lap0 = lap0;
   g.lap1 = lap1;
-  for (int l = 0; l < g.nlev; l++) {
-    if (!h->fork_stream[l] && cudaStreamCreateWithFlags(&h->fork_stream[l], cudaStreamNonBlocking) != cudaSuccess) return -1;
-    if (!h->ev_level[l] && cudaEventCreateWithFlags(&h->ev_level[l], cudaEventDisableTiming) != cudaSuccess) return -1;
-    if (!h->ev_branch[l] && cudaEventCreateWithFlags(&h->ev_branch[l], cudaEventDisableTiming) != cudaSuccess) return -1;
-  }
   // levels < n_fork leave as branches; the rest run on the trunk in one detector and one quadtree launch after the chain
   static const int fork_env = [] { const char* e = getenv("ORBX_SINGLE_FORK_LEVELS"); return e ? atoi(e) : -1; }();  // A/B knob
   // measured on B200 (tools/p50_pinned.py, 752x480, 8 levels): p50 0.1077 ms unforked, 0.1005 with 7 branches, 0.0994 with 5 --
@@ -474,7 +470,6 @@ int enqueue_single_forked(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_s
   for (int l = 0; l < n_fork; l++) cudaStreamWaitEvent(st, h->ev_branch[l], 0);
   n += launch_describe(g, s.b, 1, d_kps, d_desc, cap, d_n, d_nmono, 0, st);
   h->launches += n;
-  return n;
 }
 
 // Host frames -> device staging buffer of slot `s`.  Rows that are (nearly) contiguous go over PCIe

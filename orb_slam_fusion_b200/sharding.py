@@ -89,6 +89,13 @@ def nccl_comm(device, group=None):
     return _COMMS[key]
 
 
+def close_comms():
+    """Destroy the cached communicators (before torch.distributed.destroy_process_group)."""
+    for c in _COMMS.values():
+        c.close()
+    _COMMS.clear()
+
+
 def sharded_knn2(matcher, q, db_local, index_base, ratio=0.7, group=None):
     """2-NN + ratio test of `q` against a database whose rows are sharded over the ranks of `group`.
     `db_local` is this rank's slice and `index_base` its first global row.  Returns

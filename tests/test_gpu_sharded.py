@@ -74,6 +74,7 @@ def _worker(rank, world, port, nq, nd, out_dir):
     np.savez(os.path.join(out_dir, "r%d.npz" % rank), idx=idx.cpu().numpy(), dist=dd.cpu().numpy(), acc=acc.cpu().numpy(),
              launches=m.launch_count())
     dist.barrier()
+    S.close_comms()
     dist.destroy_process_group()
 
 
