@@ -1047,20 +1047,36 @@ __device__ __forceinline__ void window_topk(const orbx_kp* __restrict__ kps, con
   }
 }
 
+// Can two windows hold a common keypoint?  A candidate of a window lies strictly inside its square (|x - u| < r, |y - v| < r)
+// and inside its level range, so two windows whose squares are further apart than the sum of their radii (one pixel of
+// slack for the rounding of the float tests), or whose level ranges are disjoint, cannot.  NaN / infinite windows answer yes.
+__device__ __forceinline__ bool windows_may_share(const orbm_window_query& A, const orbm_window_query& B) {
+  const float s = f_add(f_add(A.r, B.r), 1.0f);
+  if (fabsf(f_sub(A.u, B.u)) > s || fabsf(f_sub(A.v, B.v)) > s) return false;
+  const int a0 = A.min_level < 0 ? 0 : A.min_level, a1 = A.max_level < 0 ? 0x7fffffff : A.max_level;
+  const int b0 = B.min_level < 0 ? 0 : B.min_level, b1 = B.max_level < 0 ? 0x7fffffff : B.max_level;
+  return !(a0 > b1 || b0 > a1);
+}
+
+// One warp per window: its KL best keys against the call's initial state, and conflict[qi]: bit X = the window of query
+// (qi & ~31) + X, X < (qi & 31), may share a keypoint with this one (the claim kernel's batches are 32 consecutive queries).
 template <int KL>
 __global__ void __launch_bounds__(256) k_window_topk(const orbx_kp* __restrict__ kps, const uint8_t* __restrict__ desc, int n,
                                                      const orbm_grid_geom g, const orbm_window_query* __restrict__ q,
                                                      const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                      const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
-                                                     const float* __restrict__ q_max_err, unsigned long long* __restrict__ keys4) {
+                                                     const float* __restrict__ q_max_err, unsigned long long* __restrict__ keys4,
+                                                     uint32_t* __restrict__ conflict) {
   const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (qi >= nq) return;
   unsigned long long k[KL];
   window_topk<KL>(kps, desc, n, g, q[qi], qdesc + 32 * (size_t)qi, skip, nullptr, kp_u_right, kp_u_right ? q_u_right[qi] : 0.f,
                   kp_u_right ? q_max_err[qi] : 0.f, lane, k);
+  const unsigned cm = __ballot_sync(0xffffffffu, lane < (qi & 31) && windows_may_share(q[qi], q[(qi & ~31) + lane]));
   if (lane == 0) {
 #pragma unroll
     for (int j = 0; j < KL; j++) keys4[KL * (size_t)qi + j] = k[j];
+    conflict[qi] = cm;
   }
 }
 
@@ -1138,12 +1154,13 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
 }
 
 // The same claim, 32 map points at a time.  Every lane takes one map point of the batch; a lane may decide in a round
-// when no EARLIER undecided lane of the batch lists any of its (<= 4) keypoints -- then nothing that happens before it in
-// the reference's order can change what it sees, and the lanes that decide together have disjoint lists, so their claims
-// do not interact.  The lowest undecided lane is never blocked, so every round makes progress; without conflicts a batch
-// takes one round.  A lane that has to re-scan its window (fewer than two survivors of a full list) may pick a keypoint
-// outside its list, so it decides alone as the last lane of its round.  lister[i]: bit L = lane L of the batch lists
-// keypoint i (shared memory, n words).
+// when no EARLIER undecided lane of the batch has a window that can share a keypoint with its own (conflict words of
+// k_window_topk).  Whatever such a lane ends up claiming -- out of its list or, after a re-scan, anywhere in its window --
+// lies outside this lane's window, and the other way round, so nothing that precedes the lane in the reference's order
+// is missing from the claims it sees and nothing it does disturbs them: the lanes of one round have pairwise disjoint
+// windows.  The lowest undecided lane is never blocked, so every round makes progress; a batch of well separated windows
+// takes one round, a batch of identical windows 32.  A lane whose full list has too few unclaimed survivors scans its
+// window again against the claims (the warp does these scans one after the other; their order does not matter).
 // LAST = false: the accept rule of SearchByProjection(Frame&, vector<MapPoint*>&) (:117-121, ratio inside one scale level).
 // LAST = true:  SearchByProjection(CurrentFrame, LastFrame, th, bMono) (orb_matcher.cc:1518-1728, Nleft == -1): the best
 //               unclaimed keypoint within TH_HIGH is taken (:1596-1604), then the 30-bin rotation histogram between the
@@ -1154,16 +1171,16 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
                                                          const uint8_t* __restrict__ qdesc, int nq, const uint8_t* __restrict__ skip,
                                                          const float* __restrict__ kp_u_right, const float* __restrict__ q_u_right,
                                                          const float* __restrict__ q_max_err,
-                                                         const unsigned long long* __restrict__ keys4, int th_high, float nnratio,
+                                                         const unsigned long long* __restrict__ keys4, const uint32_t* __restrict__ conflict,
+                                                         int th_high, float nnratio,
                                                          const float* __restrict__ q_angle, int check_orientation, int with_cells,
                                                          int32_t* __restrict__ assigned, int32_t* __restrict__ n_matches) {
-  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then lister[n + 32], then (with_cells) cellinfo[n]
+  extern __shared__ uint32_t claim_bits[];  // (n + 31) / 32 words, then hist[32], then (with_cells) cellinfo[n]
   const int lane = threadIdx.x, words = (n + 31) / 32;
-  uint32_t* lister = claim_bits + words;
-  uint32_t* cellinfo = with_cells ? lister + n + 32 : nullptr;  // grid cell of every keypoint: re-scans reject most keypoints on one word
+  uint32_t* hist = claim_bits + words;
+  uint32_t* cellinfo = with_cells ? hist + 32 : nullptr;  // grid cell of every keypoint: re-scans reject most keypoints on one word
   for (int i = lane; i < n; i += 32) {
     assigned[i] = -1;
-    lister[i] = 0;
     if (cellinfo) {
       const int px = (int)roundf(f_mul(f_sub(kps[i].x, g.min_x), g.inv_w)), py = (int)roundf(f_mul(f_sub(kps[i].y, g.min_y), g.inv_h));
       cellinfo[i] = (px < 0 || px >= g.cols || py < 0 || py >= g.rows) ? 0u : (0x80000000u | ((uint32_t)px << 10) | (uint32_t)py);
@@ -1171,10 +1188,10 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
   }
   for (int i = lane; i < words; i += 32) claim_bits[i] = 0;
   __syncwarp();
-  const unsigned lt = (1u << lane) - 1u;
   int nm = 0;
   for (int base = 0; base < nq; base += 32) {
     const int qi = base + lane;
+    const unsigned blockers = qi < nq ? conflict[qi] : 0u;
     unsigned long long k[KL];
 #pragma unroll
     for (int e = 0; e < KL; e += 2) {
@@ -1186,34 +1203,10 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
     }
     int idx[KL];
 #pragma unroll
-    for (int e = 0; e < KL; e++) {
-      idx[e] = k[e] == ~0ull ? -1 : (int)((k[e] >> 4) & 0xFFFFFFu);
-      if (idx[e] >= 0) atomicOr(&lister[idx[e]], 1u << lane);
-    }
-    __syncwarp();
+    for (int e = 0; e < KL; e++) idx[e] = k[e] == ~0ull ? -1 : (int)((k[e] >> 4) & 0xFFFFFFu);
     unsigned undecided = __ballot_sync(0xffffffffu, qi < nq && idx[0] >= 0);  // an empty list decides nothing (:75)
     while (undecided) {
-      const bool mine = (undecided >> lane) & 1u;
-      // `before`: earlier undecided lanes that list one of my keypoints.  `safe`: my listed keypoints that are unclaimed and
-      // that no earlier undecided lane lists -- nothing that precedes me in the reference's order can take those.
-      unsigned before = 0;
-      int safe = 0;
-#pragma unroll
-      for (int e = 0; e < KL; e++)
-        if (mine && idx[e] >= 0) {
-          const unsigned l = lister[idx[e]] & undecided & lt;
-          before |= l;
-          if (l == 0 && !((claim_bits[idx[e] >> 5] >> (idx[e] & 31)) & 1u)) safe++;
-        }
-      // A lane with a full list and too few safe keypoints may have to scan its window again and can then claim a keypoint
-      // OUTSIDE its list, which the "who lists me" words know nothing about.  The lowest such lane is a barrier: no later
-      // lane decides before it (the keypoint it ends up with may be one of theirs), and it decides only as the lowest
-      // undecided lane of the batch, alone in its round, so its scan sees every claim that precedes it.  The lanes below
-      // the barrier all hold enough safe keypoints, claim inside their lists, and the list rule is exact for them.
-      const unsigned may_rescan = __ballot_sync(0xffffffffu, mine && idx[KL - 1] >= 0 && safe < (LAST ? 1 : 2));
-      const int barrier = may_rescan ? __ffs(may_rescan) - 1 : 32;
-      unsigned ready = __ballot_sync(0xffffffffu, mine && before == 0 && lane < barrier);
-      if (barrier < 32 && (undecided & ((1u << barrier) - 1u)) == 0) ready = 1u << barrier;
+      const unsigned ready = __ballot_sync(0xffffffffu, ((undecided >> lane) & 1u) && (blockers & undecided) == 0);
       // survivors of the list under the claims so far
       unsigned long long b0 = ~0ull, b1 = ~0ull;
       int survivors = 0;
@@ -1225,10 +1218,10 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
           survivors++;
         }
       }
-      const unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[KL - 1] >= 0);
-      if (rescan) {  // the first lane that must look beyond its list ends the round
+      unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[KL - 1] >= 0);
+      while (rescan) {  // the list may continue beyond its KL entries
         const int r = __ffs(rescan) - 1;
-        ready &= (2u << r) - 1u;
+        rescan &= rescan - 1;
         const int rq = base + r;
         unsigned long long t[4];
         window_topk<4>(kps, desc, n, g, q[rq], qdesc + 32 * (size_t)rq, skip, claim_bits, kp_u_right, kp_u_right ? q_u_right[rq] : 0.f,
@@ -1250,15 +1243,11 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       undecided &= ~ready;
       __syncwarp();
     }
-#pragma unroll
-    for (int e = 0; e < KL; e++)
-      if (idx[e] >= 0) lister[idx[e]] = 0;
-    __syncwarp();
   }
-  if (LAST && check_orientation) {  // rotation consistency (:1612-1624, :1706-1725); lister[0..29] serves as the histogram
+  if (LAST && check_orientation) {  // rotation consistency (:1612-1624, :1706-1725)
     const float factor = 30 / 360.0f;
     __syncwarp();
-    if (lane < 30) lister[lane] = 0;
+    if (lane < 30) hist[lane] = 0;
     __syncwarp();
     for (int i = lane; i < n; i += 32) {
       const int qi = assigned[i];
@@ -1267,12 +1256,12 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
       if (rot < 0.0f) rot = f_add(rot, 360.0f);
       int bin = (int)roundf(f_mul(rot, factor));
       if (bin == 30) bin = 0;
-      atomicAdd(&lister[bin < 0 ? 0 : (bin > 29 ? 29 : bin)], 1u);
+      atomicAdd(&hist[bin < 0 ? 0 : (bin > 29 ? 29 : bin)], 1u);
     }
     __syncwarp();
     int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;  // ComputeThreeMaxima (:1841-1873), every lane alike
     for (int i = 0; i < 30; i++) {
-      const int sz = (int)lister[i];
+      const int sz = (int)hist[i];
       if (sz > max1) { max3 = max2; max2 = max1; max1 = sz; ind3 = ind2; ind2 = ind1; ind1 = i; }
       else if (sz > max2) { max3 = max2; max2 = sz; ind3 = ind2; ind2 = i; }
       else if (sz > max3) { max3 = sz; ind3 = i; }
@@ -1304,7 +1293,8 @@ cudaError_t projection_configure() {
   return e;
 }
 
-size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * 8 * sizeof(unsigned long long); }
+// per query: up to 8 keys, then one conflict word
+size_t projection_scratch_bytes(int nq) { return (size_t)(nq > 0 ? nq : 1) * (8 * sizeof(unsigned long long) + sizeof(uint32_t)); }
 
 int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, orbm_grid_geom geom, const orbm_window_query* q,
                                 const uint8_t* qdesc, int nq, const uint8_t* skip, const float* kp_u_right, const float* q_u_right,
@@ -1312,7 +1302,8 @@ int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, 
                                 bool last_frame, bool force_sequential, void* scratch, int32_t* assigned, int32_t* n_matches,
                                 cudaStream_t st) {
   unsigned long long* keys = static_cast<unsigned long long*>(scratch);
-  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem0 = bits + (size_t)(n + 32) * sizeof(uint32_t);
+  uint32_t* conflict = reinterpret_cast<uint32_t*>(keys + 8 * (size_t)(nq > 0 ? nq : 1));
+  const size_t bits = (size_t)((n + 31) / 32 + 1) * sizeof(uint32_t), smem0 = bits + 32 * sizeof(uint32_t);
   const int with_cells = geom.cols <= 1024 && geom.rows <= 1024 && smem0 + (size_t)n * sizeof(uint32_t) <= 200 * 1024;
   const size_t smem = smem0 + (with_cells ? (size_t)n * sizeof(uint32_t) : 0);
   // force_sequential (orbm_set_option, a test hook): the one-map-point-at-a-time kernel of very large frames
@@ -1322,15 +1313,15 @@ int launch_search_by_projection(const orbx_kp* kps, const uint8_t* desc, int n, 
   const bool k8 = !last_frame && !sequential;
   int launches = 1;
   if (nq > 0) {
-    if (k8) k_window_topk<8><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys);
-    else k_window_topk<4><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys);
+    if (k8) k_window_topk<8><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, conflict);
+    else k_window_topk<4><<<(nq + 7) / 8, 256, 0, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, conflict);
     launches++;
   }
   if (last_frame) {
-    k_projection_claim<true, 4><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
+    k_projection_claim<true, 4><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, conflict, th_high,
                                                      nnratio, q_angle, check_orientation, with_cells, assigned, n_matches);
-  } else if (!sequential) {  // one word per keypoint in shared memory (up to ~50 k keypoints)
-    k_projection_claim<false, 8><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,
+  } else if (!sequential) {
+    k_projection_claim<false, 8><<<1, 32, smem, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, conflict, th_high,
                                                       nnratio, nullptr, 0, with_cells, assigned, n_matches);
   } else {
     k_projection_claim_seq<<<1, 32, bits, st>>>(kps, desc, n, geom, q, qdesc, nq, skip, kp_u_right, q_u_right, q_max_err, keys, th_high,

@@ -599,3 +599,48 @@ def test_projection_claim_order_when_a_list_is_exhausted(P, m, oracle, scenario)
     assert np.array_equal(owant, want), "the oracle disagrees with the hand-derived outcome"
     nm, got = m.SearchByProjectionLast(kps, desc, geom, q, qdesc, ang, pre, None, None, None, 100, False)
     assert nm == wnm and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("seed,n,nq,spread,rmax", [(1, 60, 200, 30.0, 40.0), (2, 400, 500, 120.0, 25.0), (3, 1500, 1000, 700.0, 18.0),
+                                                   (4, 25, 96, 5.0, 1e6), (5, 300, 333, 60.0, 12.0)])
+def test_projection_claim_crowded_windows(P, m, oracle, seed, n, nq, spread, rmax):
+    """The batched claim lets map points with disjoint windows decide together; here the windows crowd into a small part of
+    the image (spread = side of the square the keypoints and projections fall in), so most of a batch overlaps, lists run
+    dry and windows are scanned again -- every order-of-events case at once.  Few distinct descriptor values (ties), mixed
+    levels, level ranges of every kind, some huge / empty windows.  Both forms against the oracle and the sequential kernel."""
+    rng = np.random.default_rng(seed)
+    geom = (0.0, 0.0, np.float32(64) / np.float32(752), np.float32(48) / np.float32(480), 64, 48)
+    kps = np.zeros(n, P.KP_DTYPE)
+    kps["x"] = (100 + rng.random(n) * spread).astype(np.float32)
+    kps["y"] = (80 + rng.random(n) * min(spread, 390.0)).astype(np.float32)
+    kps["octave"] = rng.integers(0, 4, n)
+    kps["angle"] = (rng.random(n) * 360).astype(np.float32)
+    kps["size"], kps["class_id"] = 31, -1
+    words = rng.integers(0, 256, (6, 32)).astype(np.uint8)
+    desc = words[rng.integers(0, 6, n)].copy()
+    desc[:, 0] ^= rng.integers(0, 4, n).astype(np.uint8)
+    q = np.zeros(nq, P.WQ_DTYPE)
+    q["u"] = (100 + rng.random(nq) * spread).astype(np.float32)
+    q["v"] = (80 + rng.random(nq) * min(spread, 390.0)).astype(np.float32)
+    q["r"] = np.minimum(2 + rng.random(nq) * 38, rmax).astype(np.float32) if rmax < 1e5 else np.float32(rmax)
+    lo = rng.integers(-1, 3, nq)
+    q["min_level"], q["max_level"] = lo, np.where(rng.random(nq) < 0.2, -1, lo + rng.integers(0, 3, nq))
+    q["r"][rng.random(nq) < 0.05] = 0.0                                         # empty windows in between
+    qdesc = words[rng.integers(0, 6, nq)].copy()
+    qdesc[:, 1] ^= rng.integers(0, 4, nq).astype(np.uint8)
+    pre = (rng.random(n) < 0.1).astype(np.uint8)
+    for th_high, ratio in ((100, 0.8), (256, 1.0), (40, 0.6)):
+        wnm, want = oracle.search_by_projection(kps, desc, geom, q, qdesc, pre, None, None, None, th_high, ratio)
+        nm, got = m.SearchByProjection(kps, desc, geom, q, qdesc, pre, None, None, None, th_high, ratio)
+        assert nm == wnm and np.array_equal(got, want), (th_high, ratio)
+        m.set_option(P.OPT_CLAIM_SEQUENTIAL, 1)
+        try:
+            nm_s, got_s = m.SearchByProjection(kps, desc, geom, q, qdesc, pre, None, None, None, th_high, ratio)
+        finally:
+            m.set_option(P.OPT_CLAIM_SEQUENTIAL, 0)
+        assert nm_s == wnm and np.array_equal(got_s, want)
+    ang = (rng.random(nq) * 360).astype(np.float32)
+    for ori in (False, True):
+        wnm, want = oracle.search_by_projection_last(kps, desc, geom, q, qdesc, ang, pre, None, None, None, 100, ori)
+        nm, got = m.SearchByProjectionLast(kps, desc, geom, q, qdesc, ang, pre, None, None, None, 100, ori)
+        assert nm == wnm and np.array_equal(got, want), ori
