@@ -16,7 +16,7 @@ __device__ __forceinline__ void octree_problem(const FrameGeom& g, const int lev
                                                int32_t* __restrict__ node_of, int32_t* __restrict__ n_cand,
                                                uint32_t* __restrict__ sel_xy, uint8_t* __restrict__ sel_sc,
                                                int32_t* __restrict__ n_sel) {
-  extern __shared__ int ot_mem[];
+  extern __shared__ __align__(16) int ot_mem[];
   const LevelGeom& L = g.lv[lev];
   OtWork w;
   ot_carve(w, ot_mem, g.node_cap);

@@ -50,7 +50,9 @@ namespace orbx {
 // in shared memory on the device.
 struct OtWork {
   int cap;
-  int *x0[2], *y0[2], *x1[2], *y1[2], *cnt[2];  // node tables, double buffered, in list order
+  int* tab;     // node tables, double buffered, in list order: x0, y0, x1, y1, cnt of buffer b at tab + (5 * b + k) * cap
+                // (addressed by arithmetic, not through an array of pointers: a run-time index into such an array puts
+                // the struct in local memory and turns every table access into a generic 64-bit load)
   int* cc;      // [cap][4] child point counts of nodes being split
   int* cpos;    // [cap][4] new list position of each non-empty child
   int* newpos;  // [cap+1]  new list position of nodes that are kept
@@ -63,6 +65,9 @@ struct OtWork {
   int* misc;    // [2] scalars of the calling kernel
 };
 
+OT_DEV int* ot_tab(const OtWork& w, int b, int k) { return w.tab + (5 * b + k) * w.cap; }
+enum { OT_X0 = 0, OT_Y0, OT_X1, OT_Y1, OT_CNT };
+
 enum { SV_N = 0, SV_F, SV_M, SV_MEFF, SV_TOTALC, SV_DONE, SV_PHASE, SV_TOEXP, SV_CUR, SV_ERR };
 
 OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1 + 2) + 2 * (cap + 1) + 16 + 2 + 64 + 2; }
@@ -70,17 +75,14 @@ OT_HD int ot_work_ints(int cap) { return cap * (10 + 4 + 4 + 1 + 1 + 2) + 2 * (c
 OT_DEV void ot_carve(OtWork& w, int* mem, int cap) {
   w.cap = cap;
   int* p = mem;
-  for (int b = 0; b < 2; b++) {
-    w.x0[b] = p; p += cap; w.y0[b] = p; p += cap; w.x1[b] = p; p += cap; w.y1[b] = p; p += cap;
-    w.cnt[b] = p; p += cap;
-  }
+  w.tab = p; p += 10 * cap;
   w.cc = p; p += 4 * cap;
   w.cpos = p; p += 4 * cap;
   w.newpos = p; p += cap + 1;
   w.rank = p; p += cap;
   w.seq = p; p += cap;
   w.scan = p; p += cap + 1;
-  p += ((size_t)p & 7) ? 1 : 0;  // 8-byte alignment (the block itself is at least 8-byte aligned)
+  p += (p - mem) & 1;  // 8-byte alignment (the block itself is at least 8-byte aligned); index arithmetic keeps the pointer's address space known
   w.best = (unsigned long long*)p; p += 2 * cap;
   w.sv = p; p += 16;
   w.wsum = p; p += 64;
@@ -169,12 +171,12 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
   // ---- roots (:548-585) ----
   OT_FOR(i, w.cap) {
     if (i < n_roots) {
-      w.x0[0][i] = (int)f_mul(root_hx, (float)i);
-      w.x1[0][i] = (int)f_mul(root_hx, (float)(i + 1));
-      w.y0[0][i] = 0;
-      w.y1[0][i] = height;
+      ot_tab(w, 0, OT_X0)[i] = (int)f_mul(root_hx, (float)i);
+      ot_tab(w, 0, OT_X1)[i] = (int)f_mul(root_hx, (float)(i + 1));
+      ot_tab(w, 0, OT_Y0)[i] = 0;
+      ot_tab(w, 0, OT_Y1)[i] = height;
     }
-    w.cnt[0][i] = 0;
+    ot_tab(w, 0, OT_CNT)[i] = 0;
   }
   if (OT_TID0) { sv[SV_DONE] = 0; sv[SV_PHASE] = 0; sv[SV_F] = 0; sv[SV_ERR] = (n_roots > w.cap); }
   OT_SYNC();
@@ -186,18 +188,17 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     int r = (int)f_div((float)(xy[p] & 0xFFFFu), root_hx);
     if (r >= n_roots) r = n_roots - 1;
     node_of[p] = r;
-    ot_atomic_add(&w.cnt[0][r], 1);
+    ot_atomic_add(&ot_tab(w, 0, OT_CNT)[r], 1);
   }
   OT_SYNC();
   // erase empty roots, keep order
-  OT_FOR(i, n_roots) w.scan[i] = w.cnt[0][i] > 0;
+  OT_FOR(i, n_roots) w.scan[i] = ot_tab(w, 0, OT_CNT)[i] > 0;
   OT_SYNC();
   ot_excl_scan(w.scan, n_roots, w.wsum);
   OT_FOR(i, n_roots) {
-    if (w.cnt[0][i] > 0) {
+    if (ot_tab(w, 0, OT_CNT)[i] > 0) {
       const int j = w.scan[i];
-      w.x0[1][j] = w.x0[0][i]; w.y0[1][j] = w.y0[0][i]; w.x1[1][j] = w.x1[0][i]; w.y1[1][j] = w.y1[0][i];
-      w.cnt[1][j] = w.cnt[0][i];
+      for (int k = OT_X0; k <= OT_CNT; k++) ot_tab(w, 1, k)[j] = ot_tab(w, 0, k)[i];
     }
   }
   OT_SYNC();
@@ -211,9 +212,9 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     const int n = sv[SV_N];
     const int F = sv[SV_F];
     const int fine = sv[SV_PHASE];
-    int* X0 = w.x0[cur]; int* Y0 = w.y0[cur]; int* X1 = w.x1[cur]; int* Y1 = w.y1[cur]; int* CNT = w.cnt[cur];
-    int* NX0 = w.x0[cur ^ 1]; int* NY0 = w.y0[cur ^ 1]; int* NX1 = w.x1[cur ^ 1]; int* NY1 = w.y1[cur ^ 1];
-    int* NCNT = w.cnt[cur ^ 1];
+    int *X0 = ot_tab(w, cur, OT_X0), *Y0 = ot_tab(w, cur, OT_Y0), *X1 = ot_tab(w, cur, OT_X1), *Y1 = ot_tab(w, cur, OT_Y1), *CNT = ot_tab(w, cur, OT_CNT);
+    int *NX0 = ot_tab(w, cur ^ 1, OT_X0), *NY0 = ot_tab(w, cur ^ 1, OT_Y0), *NX1 = ot_tab(w, cur ^ 1, OT_X1), *NY1 = ot_tab(w, cur ^ 1, OT_Y1);
+    int* NCNT = ot_tab(w, cur ^ 1, OT_CNT);
 
     // processing rank of the nodes split in this pass
     if (!fine) {
