@@ -7,8 +7,8 @@
 //
 //   k_plan     one CTA per frame: output slot of every selected keypoint (prefix sum of the
 //              lapping flags in the reference's traversal order), n and n_mono.
-//   k_describe one warp per keypoint: lanes = the 31 patch columns for the intensity centroid
-//              (each row is one coalesced 31-byte read), then lane L builds descriptor byte L
+//   k_describe one warp per keypoint: the intensity centroid over the patch's rows read as aligned 64-bit units
+//              (DP4A with signed per-byte weights), then lane L builds descriptor byte L
 //              (16 gathers from the blurred level) and the warp stores the 32-byte row at once.
 #include "orbx_kernels.cuh"
 #include "orbx_math.cuh"
@@ -21,13 +21,20 @@ __constant__ int8_t c_pattern[1024] = {
 // umax_ of orb_extractor.cc:452-464 for kHalfPatchSize = 15
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
-// IC_Angle as DP4A over aligned words: the 31 patch rows are read as 9 aligned 32-bit words each (any
-// alignment a = 0..3 of the patch's first column); item i = 9 * row + word.  Entry [a][i] holds the per-byte
-// weights of that word inside the radius-15 disc -- x: (u + 16) per byte (1..31, 0 outside), y: 1 per byte
-// inside.  Filled once per device by k_pattern_init; 4 x 279 x 8 B = 8.9 KB, read by every warp with one
-// coalesced 64-bit load per item (the pixel loads do not depend on it: row and word come from the item index).
-constexpr int kOriItems = 31 * 9;
-__device__ uint2 g_ori_w[4 * kOriItems];
+// IC_Angle as DP4A over aligned 64-bit units: the 31 patch rows are read as 5 aligned 8-byte units each (40 bytes cover
+// the 31 columns for any alignment a = 0..7 of the patch's first column); item i = 5 * row + unit.  Entry [a][i] holds
+// the per-byte SIGNED weights of that unit inside the radius-15 disc -- (x, y): u per byte of the low / high word,
+// (z, w): v per byte (0 outside the disc) -- so that m10 and m01 are accumulated by DP4A itself (dp4a.u32.s32 with the
+// running sum as addend): four instructions per 8 pixels and nothing else.  Filled once per device by k_pattern_init;
+// 8 x 155 x 16 B = 19.8 KB, read by every warp with one coalesced 128-bit load per item (the pixel loads do not depend
+// on it: row and unit come from the item index).
+constexpr int kOriItems = 31 * 5;
+__device__ uint4 g_ori_w[8 * kOriItems];
+__device__ __forceinline__ int dp4a_us(uint32_t pix, uint32_t w, int acc) {  // unsigned pixels x signed weights
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(w), "r"(acc));
+  return d;
+}
 
 // the same pattern as floats, transposed: entry [k][L] = (x0, y0, x1, y1) of bit k of descriptor byte L, so that a
 // warp reads one coalesced 512-byte line per bit (filled once per device by k_pattern_init)
@@ -37,16 +44,19 @@ __global__ void k_pattern_init() {
   const int L = t >> 3, k = t & 7;
   const int8_t* p = &c_pattern[(L * 8 + k) * 4];
   g_pattern_f[k * 32 + L] = make_float4((float)p[0], (float)p[1], (float)p[2], (float)p[3]);
-  for (int e = t; e < 4 * kOriItems; e += blockDim.x) {
-    const int a = e / kOriItems, i = e - a * kOriItems, r = i / 9, wc = i - r * 9;
+  for (int e = t; e < 8 * kOriItems; e += blockDim.x) {
+    const int a = e / kOriItems, i = e - a * kOriItems, r = i / 5, c = i - r * 5;
     const int v = r - kHalfPatch, d = c_umax[v < 0 ? -v : v];
-    const int u0 = 4 * wc - a - kHalfPatch;  // u of byte 0 of this word
-    uint32_t wu = 0, wm = 0;
-    for (int j = 0; j < 4; j++) {
+    const int u0 = 8 * c - a - kHalfPatch;  // u of byte 0 of this unit
+    uint32_t wu[2] = {0, 0}, wv[2] = {0, 0};
+    for (int j = 0; j < 8; j++) {
       const int u = u0 + j;
-      if (u >= -d && u <= d) { wu |= (uint32_t)(u + 16) << (8 * j); wm |= 1u << (8 * j); }
+      if (u >= -d && u <= d) {
+        wu[j >> 2] |= (uint32_t)(uint8_t)(int8_t)u << (8 * (j & 3));
+        wv[j >> 2] |= (uint32_t)(uint8_t)(int8_t)v << (8 * (j & 3));
+      }
     }
-    g_ori_w[e] = make_uint2(wu, wm);
+    g_ori_w[e] = make_uint4(wu[0], wu[1], wv[0], wv[1]);
   }
 }
 
@@ -172,24 +182,22 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   }
 
   // ---- IC_Angle (:76-100): m10 = sum u*I, m01 = sum v*I over the radius-15 disc.  The 31 rows are read as
-  // aligned 32-bit words (9 per row cover any alignment): item = (row v, word wc), 279 items over the 32
-  // lanes = 9 loads per lane instead of 31 byte loads; DP4A with per-byte weights (u inside the disc, else 0).
+  // aligned 64-bit units (5 per row cover any alignment): item = (row v, unit c), 155 items over the 32
+  // lanes = 5 loads per lane instead of 31 byte loads; DP4A with per-byte signed weights (u, v inside the disc, else 0).
   int m10 = 0, m01 = 0;
   {
-    const int xa = (cx - kHalfPatch) & ~3, a = (cx - kHalfPatch) - xa;  // aligned start, 0..3 bytes before the patch
-    const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);
-    const uint2* wt = g_ori_w + a * kOriItems;
+    const int xa = (cx - kHalfPatch) & ~7, a = (cx - kHalfPatch) - xa;  // aligned start, 0..7 bytes before the patch
+    const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);    // 8-byte aligned: rows start on 16-byte boundaries
+    const uint4* wt = g_ori_w + a * kOriItems;
 #pragma unroll
     for (int t = 0; t < (kOriItems + 31) / 32; t++) {
       const int i = lane + 32 * t;
       if (i < kOriItems) {
-        // (carrying row and word offset in the table entry instead -- 16-byte entries -- was measured slower: 0.480 vs 0.432 ms)
-        const int r = (i * 57) >> 9, wc = i - r * 9;  // i / 9 for i < 512
-        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(base + r * pitch) + wc);
-        const uint2 e = __ldg(wt + i);
-        const int s0 = (int)__dp4a(w, e.y, 0u), s1 = (int)__dp4a(w, e.x, 0u);  // sum I, sum (u + 16) * I
-        m10 += s1 - 16 * s0;
-        m01 += (r - kHalfPatch) * s0;
+        const int r = (i * 205) >> 10, c = i - r * 5;  // i / 5 for i < 1024
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(base + r * pitch) + c);
+        const uint4 e = __ldg(wt + i);
+        m10 = dp4a_us(w.y, e.y, dp4a_us(w.x, e.x, m10));
+        m01 = dp4a_us(w.y, e.w, dp4a_us(w.x, e.z, m01));
       }
     }
   }

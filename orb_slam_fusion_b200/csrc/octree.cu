@@ -62,7 +62,7 @@ __device__ __forceinline__ void octree_problem(const FrameGeom& g, const int lev
   P = n_keep;
   if (threadIdx.x == 0) n_cand[f * ORBX_MAX_LEVELS + lev] = P;  // the count ORBX_STAGE_CAND reports
   ot_select(cand_xy + cbase, cand_sc + cbase, P, node_of + cbase, w, L.w - 2 * kFastBorder, L.h - 2 * kFastBorder,
-            L.n_roots, L.root_hx, L.quota, L.wcell, L.hcell, L.ncols, sel_xy + sbase, sel_sc + sbase, &nsel_sh);
+            L.n_roots, L.root_hx, L.quota, L.wcell, L.hcell, L.ncols, L.wcell_rcp, L.hcell_rcp, sel_xy + sbase, sel_sc + sbase, &nsel_sh);
   __syncthreads();
   if (threadIdx.x == 0) n_sel[f * ORBX_MAX_LEVELS + lev] = nsel_sh;
 }

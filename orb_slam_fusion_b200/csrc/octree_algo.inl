@@ -164,8 +164,8 @@ OT_DEV unsigned ot_order_key(int x, int y, int wcell, int hcell, int ncols, unsi
 // Returns (via *n_sel) -1 if the node table capacity was exceeded.
 OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of, OtWork& w,
                       int width, int height /* max_x-min_x, max_y-min_y */, int n_roots,
-                      float root_hx, int quota, int wcell, int hcell, int ncols, uint32_t* sel_xy,
-                      uint8_t* sel_sc, int* n_sel) {
+                      float root_hx, int quota, int wcell, int hcell, int ncols, unsigned wrcp, unsigned hrcp,
+                      uint32_t* sel_xy, uint8_t* sel_sc, int* n_sel) {
   int* sv = w.sv;
   int cur = 0;
   // ---- roots (:548-585) ----
@@ -364,7 +364,6 @@ OT_DEV void ot_select(const uint32_t* xy, const uint8_t* sc, int P, int* node_of
     return;
   }
   // max response, then the earliest point in the reference's candidate order: one 64-bit key per point
-  const unsigned wrcp = ot_rcp(wcell), hrcp = ot_rcp(hcell);
   OT_FOR(i, n) w.best[i] = 0ull;
   OT_SYNC();
   OT_FOR(p, P) {

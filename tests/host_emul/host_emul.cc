@@ -60,7 +60,7 @@ int emul_octree(const int* xyr, int n, int w, int h, int quota, int wcell, int h
   std::vector<uint8_t> ssc(cap);
   int nsel = 0;
   ot_select(xy.data(), sc.data(), n, node_of.data(), wk, width, height, n_roots, hx, quota, wcell, hcell,
-            ncols, sxy.data(), ssc.data(), &nsel);
+            ncols, ot_rcp(wcell), ot_rcp(hcell), sxy.data(), ssc.data(), &nsel);
   for (int i = 0; i < nsel && i < cap_out; i++) {
     out_xyr[3 * i] = (int)(sxy[i] & 0xFFFF);
     out_xyr[3 * i + 1] = (int)(sxy[i] >> 16);
