@@ -232,12 +232,13 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   // the TMA destination must be 128-byte aligned; the dynamic region is only 16-byte aligned when the
   // kernel also has static shared memory, so the base is rounded up here (the launch adds 128 bytes)
   uint8_t* src_sm = rs_smem + ((128u - ((unsigned)__cvta_generic_to_shared(rs_smem) & 127u)) & 127u);
-  // H >> 4 (15 bits) is kept PRE-SHIFTED as (H >> 4) << 16 in 32-bit words: the vertical pass multiplies with IMAD.HI and needs
-  // neither a shift nor a mask per product
+  // The horizontal sums are kept as H & ~15 in 32-bit words and the row coefficients as b << 12: (b * (H >> 4)) >> 16 ==
+  // (b * (H & ~15)) >> 20 == the high word of (b << 12) * (H & ~15), so the vertical pass is one IMAD.HI per product and
+  // the horizontal pass pays one mask per value (no shift)
   uint32_t* hq = reinterpret_cast<uint32_t*>(src_sm + ((bh * BW + 127) & ~127));
   unsigned long long& tile_bar = *reinterpret_cast<unsigned long long*>(hq + bh * kRsTW);
   // the row table lives in the same (dynamic) shared object as everything else: one shared-window base for the kernel
-  uint2* row_tab = reinterpret_cast<uint2*>(hq + bh * kRsTW + 4);
+  uint4* row_tab = reinterpret_cast<uint4*>(hq + bh * kRsTW + 4);
   const LevelGeom& D = g.lv[lev];
   const int x0 = blockIdx.x * kRsTW, y0 = blockIdx.y * th;
   const int y1 = min(y0 + th, D.h);  // output rows [y0, y1)
@@ -290,12 +291,12 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
         sel[k] = dl | ((dl + 1u) << 4);
       }
     }
-    if (tid < th) {  // the tile's row table for the vertical pass: (row0 | row1 << 16) relative to row_lo, (b0 | b1 << 16)
+    if (tid < th) {  // the tile's row table for the vertical pass: byte offsets of the two H rows, b0 << 12, b1 << 12
       const int dy = min(y0 + tid, D.h - 1);
       const uint32_t yo = *reinterpret_cast<const uint32_t*>(yofs + 2 * (t + dy));
       const uint32_t yb = *reinterpret_cast<const uint32_t*>(ybeta + 2 * (t + dy));
-      // byte offsets of the two H rows inside hq (row * 128 words * 4 bytes < 2^16), (b0 | b1 << 16)
-      row_tab[tid] = make_uint2((yo - (uint32_t)row_lo * 0x10001u) * (uint32_t)(kRsTW * 4), yb);
+      row_tab[tid] = make_uint4(((yo & 0xFFFFu) - (uint32_t)row_lo) * (uint32_t)(kRsTW * 4), ((yo >> 16) - (uint32_t)row_lo) * (uint32_t)(kRsTW * 4),
+                                (yb & 0xFFFFu) << 12, (yb >> 16) << 12);
     }
     __syncthreads();  // every thread sees the initialised barrier
     {
@@ -312,11 +313,10 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
         if (i < rpg && r0 + i < n_rows) {
           const uint32_t w0 = wp[i * (BW / 4)], w1 = wp[i * (BW / 4) + 1], w2 = wp[i * (BW / 4) + 2];
           const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // bytes sx0 .. sx0+7
-          // (H >> 4) << 16 == (H & ~15) << 12: H < 2^20, nothing is lost at the top
-          const uint32_t o0 = (__dp2a_lo(al[0], __byte_perm(lo, hi, sel[0]), 0u) & ~15u) << 12;
-          const uint32_t o1 = (__dp2a_lo(al[1], __byte_perm(lo, hi, sel[1]), 0u) & ~15u) << 12;
-          const uint32_t o2 = (__dp2a_lo(al[2], __byte_perm(lo, hi, sel[2]), 0u) & ~15u) << 12;
-          const uint32_t o3 = (__dp2a_lo(al[3], __byte_perm(lo, hi, sel[3]), 0u) & ~15u) << 12;
+          const uint32_t o0 = __dp2a_lo(al[0], __byte_perm(lo, hi, sel[0]), 0u) & ~15u;
+          const uint32_t o1 = __dp2a_lo(al[1], __byte_perm(lo, hi, sel[1]), 0u) & ~15u;
+          const uint32_t o2 = __dp2a_lo(al[2], __byte_perm(lo, hi, sel[2]), 0u) & ~15u;
+          const uint32_t o3 = __dp2a_lo(al[3], __byte_perm(lo, hi, sel[3]), 0u) & ~15u;
           *reinterpret_cast<uint4*>(&hq[(r0 + i) * kRsTW + 4 * q]) = make_uint4(o0, o1, o2, o3);
         }
       }
@@ -324,8 +324,8 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   }
   __syncthreads();
 
-  // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows).  (b * h) >> 16 is the high word of
-  // b * (h << 16): one IMAD.HI per product.
+  // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows).  (b * (H >> 4)) >> 16 is the high word of
+  // (b << 12) * (H & ~15): one IMAD.HI per product, both factors as stored.
   {
     constexpr int kVRows = kRsMaxTH / 8;
     const int q = tid & 31, yy0 = (tid >> 5) * kVRows;
@@ -335,11 +335,11 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
 #pragma unroll
       for (int i = 0; i < kVRows; i++) {
         if (y0 + yy0 + i < y1) {
-          const uint2 rt = row_tab[yy0 + i];
-          const uint32_t b0 = rt.y & 0xFFFFu, b1 = rt.y >> 16;
+          const uint4 rt = row_tab[yy0 + i];
+          const uint32_t b0 = rt.z, b1 = rt.w;  // << 12
           const uint8_t* hb = reinterpret_cast<const uint8_t*>(hq) + 16 * q;
-          const uint4 u0 = *reinterpret_cast<const uint4*>(hb + (rt.x & 0xFFFFu));
-          const uint4 u1 = *reinterpret_cast<const uint4*>(hb + (rt.x >> 16));
+          const uint4 u0 = *reinterpret_cast<const uint4*>(hb + rt.x);
+          const uint4 u1 = *reinterpret_cast<const uint4*>(hb + rt.y);
           // b0 + b1 <= 2049 and h <= 255 * 2049 / 16, so the sum is in [0, 1022]: the saturate_cast of
           // cv::resize can never clip and is not spelled out
           // two plain multiply-highs and ONE three-input add per pixel (left to itself the compiler chains the second
@@ -379,7 +379,7 @@ int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, i
   int th, bw, bh;
   resize_tile_plan(g, lev, &th, &bw, &bh);
   dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-  const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint2) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
+  const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint4) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
   if (bw == kRsBwSmall)
     k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
   else if (bw == 256)
