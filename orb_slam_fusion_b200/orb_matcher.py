@@ -294,9 +294,20 @@ class ORBmatcher:
             match = torch.empty((len(kf), cap), dtype=torch.int32, device=dev)
             nm = torch.empty(len(kf), dtype=torch.int32, device=dev)
             mem, stream = A.MEM_DEVICE, A.torch_stream(dev)
+            # the C ABI takes plain pointers: a tensor of another width, layout or device would be reinterpreted silently
+            for key in ("fv_nodes", "fv_begin", "fv_n", "fv_feats", "fv_total"):
+                t = fv[key]
+                assert t.is_cuda and t.device == dev and t.is_contiguous() and t.element_size() == 4, key
+            if n_per_frame is not None:
+                assert n_per_frame.device == dev and n_per_frame.dtype == torch.int32 and n_per_frame.is_contiguous()
+            if has_point is not None:
+                assert has_point.device == dev and has_point.element_size() == 1 and has_point.is_contiguous() and tuple(has_point.shape) == (F, cap)
         else:
             kps = np.ascontiguousarray(kps, A.KP_DTYPE)
             F, cap = kps.shape
+            fv = {k: np.ascontiguousarray(v) for k, v in fv.items()}
+            for key in ("fv_nodes", "fv_begin", "fv_n", "fv_feats", "fv_total"):
+                assert fv[key].dtype.itemsize == 4, key
             desc = np.ascontiguousarray(desc, np.uint8).reshape(F, cap, 32)
             n_per_frame = None if n_per_frame is None else np.ascontiguousarray(n_per_frame, np.int32)
             has_point = None if has_point is None else np.ascontiguousarray(has_point, np.uint8).reshape(F, cap)
