@@ -114,7 +114,12 @@ int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int*
  * the handle's GPU, the call only enqueues work on `stream` (NULL = the handle's stream) and
  * returns; use orbx_sync).  Outputs: kps[f*cap + i], desc[(f*cap + i)*32], n[f], n_mono[f].
  * Frames with more than cap keypoints report n[f] = -(needed) and write nothing for f.
- * n_frames may exceed max_batch: the call loops over chunks. */
+ * n_frames may exceed max_batch: the call loops over chunks.
+ * ORBX_MEM_DEVICE frames whose base address, row_stride and frame_stride are multiples of 16 bytes are
+ * read IN PLACE (no copy into the handle's pyramid: level 0 is the caller's buffer); like any input of an
+ * asynchronous call they must stay unchanged until the call's work has completed on the stream.  After
+ * such a call the handle holds no level-0 plane: orbx_pyramid_level(0) and the level-0 image of
+ * orbx_stage_download return ORBX_E_ARG until the next call that copies its frames. */
 int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int h_, size_t row_stride,
                        size_t frame_stride, int mem, int lap0, int lap1, orbx_kp* kps, uint8_t* desc,
                        int cap, int32_t* n, int32_t* n_mono, void* stream);

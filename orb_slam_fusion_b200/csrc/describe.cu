@@ -187,14 +187,18 @@ __global__ void __launch_bounds__(32 * kDescWarps, ORBX_DESC_MINB) k_describe(co
   int m10 = 0, m01 = 0;
   {
     const int xa = (cx - kHalfPatch) & ~7, a = (cx - kHalfPatch) - xa;  // aligned start, 0..7 bytes before the patch
-    const uint8_t* base = pyr + fo + px_off(L, xa, cy - kHalfPatch);    // 8-byte aligned: rows start on 16-byte boundaries
+    // 8-byte aligned: rows start on 16-byte boundaries (plane rows, and the caller's rows when level 0 is read in place)
+    const bool ext = lev == 0 && g.ext0 != nullptr;
+    const uint8_t* base = ext ? g.ext0 + (size_t)f * g.ext0_frame + (size_t)(cy - kHalfPatch) * g.ext0_pitch + xa
+                              : pyr + fo + px_off(L, xa, cy - kHalfPatch);
+    const int rpitch = ext ? (int)g.ext0_pitch : pitch;
     const uint4* wt = g_ori_w + a * kOriItems;
 #pragma unroll
     for (int t = 0; t < (kOriItems + 31) / 32; t++) {
       const int i = lane + 32 * t;
       if (i < kOriItems) {
         const int r = (i * 205) >> 10, c = i - r * 5;  // i / 5 for i < 1024
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(base + r * pitch) + c);
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(base + r * rpitch) + c);
         const uint4 e = __ldg(wt + i);
         m10 = dp4a_us(w.y, e.y, dp4a_us(w.x, e.x, m10));
         m01 = dp4a_us(w.y, e.w, dp4a_us(w.x, e.z, m01));

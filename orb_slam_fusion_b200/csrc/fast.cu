@@ -87,7 +87,7 @@ __device__ __forceinline__ void ring_load(uint32_t c, int (&r)[16]) {
 // q = v / d for 0 <= v < 2^15, d < 2^15 with rcp = ceil(2^32 / d) (host: LevelGeom::wcell_rcp / hcell_rcp)
 __device__ __forceinline__ int div_rcp(int v, uint32_t rcp) { return (int)__umulhi((uint32_t)v, rcp); }
 
-__global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads) k_fast_blur(const __grid_constant__ FrameGeom g, const CUtensorMap* __restrict__ pyr_maps,
+__global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads) k_fast_blur(const __grid_constant__ FrameGeom g, const CUtensorMap* __restrict__ pyr_maps, const __grid_constant__ CUtensorMap ext0_map,
                                               uint8_t* __restrict__ blur, uint32_t* __restrict__ cand_xy, uint8_t* __restrict__ cand_sc,
                                               int32_t* __restrict__ cand_cell, int32_t* __restrict__ n_cand,
                                               int32_t* __restrict__ cell_strong, const uint32_t* __restrict__ tile_tab) {
@@ -139,12 +139,16 @@ __global__ void __launch_bounds__(kFtThreads, ORBX_FAST_MINB * 256 / kFtThreads)
   // itself, only in edge tiles, and the detector stays 19 px inside.
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
   if (tid == 0) {
+    // level 0 read in place: the tile comes straight from the caller's frames; there is no padding around them, so the box
+    // coordinates are the image's own (negative ones and those beyond the image are zero-filled like the plane's padding)
+    const bool ext = lev == 0 && g.ext0 != nullptr;
+    const CUtensorMap* map = ext ? &ext0_map : pyr_maps + lev;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // the initialised barrier is visible to the async proxy
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(kFtRawH * kFtRawPitch) : "memory");
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
                      (unsigned)__cvta_generic_to_shared(raw_w)),
-                 "l"(pyr_maps + lev), "r"(X0 - 16 + kPadX), "r"(Y0 - 4 + kPadY), "r"(f), "r"(bar)
+                 "l"(map), "r"(X0 - 16 + (ext ? 0 : kPadX)), "r"(Y0 - 4 + (ext ? 0 : kPadY)), "r"(f), "r"(bar)
                  : "memory");
   }
   // (while the copy is in flight)
@@ -445,7 +449,7 @@ cudaError_t fast_dropped(unsigned int* out, bool reset) {
 int launch_fast(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
   // n_cand and cell_strong were zeroed by k_import, the first kernel of every pipeline
   dim3 grid(g.total_blur_tiles, 1, frames);
-  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
+  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.ext0_fast_map, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong, b.tile_tab);
   return 1;
 }
 
@@ -454,7 +458,7 @@ int launch_fast_levels(const FrameGeom& g, const BatchBuffers& b, int frames, in
   const int first = g.lv[lev].blur_tile_base;
   const int count = (lev_end < g.nlev ? g.lv[lev_end].blur_tile_base : g.total_blur_tiles) - first;
   dim3 grid(count, 1, frames);
-  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong,
+  k_fast_blur<<<grid, kFtThreads, 0, st>>>(g, b.pyr_maps, b.ext0_fast_map, b.blur, b.cand_raw_xy, b.cand_raw_sc, b.node_of, b.n_cand, b.cell_strong,
                                           b.tile_tab + first);
   return 1;
 }

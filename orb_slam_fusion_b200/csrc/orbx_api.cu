@@ -84,6 +84,7 @@ struct orbx_extractor {
   uint32_t* d_tile_tab = nullptr;
   int last_frames = 0;       // frames of the last chunk processed on slot 0
   bool border_done = false;  // REFLECT_101 frames of slot 0's pyramid are up to date
+  bool level0_external = false;  // the last call on slot 0 read level 0 in place from the caller's frames: slot 0 holds no level-0 plane
   long long launches = 0;
   // single-frame path: the kernel sequence + result copies captured once as a CUDA graph
   cudaGraphExec_t graph = nullptr;
@@ -219,7 +220,7 @@ cudaError_t dmalloc(Slot& s, T** p, size_t n) {
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int rows, int frames, size_t frame_bytes, int box_w, int box_h) {
+int encode_map(orbx_t* h, CUtensorMap* out, const void* base, size_t width, size_t pitch, int rows, int frames, size_t frame_bytes, int box_w, int box_h) {
   static encode_tiled_fn enc = nullptr;
   if (!enc) {
     void* fn = nullptr;
@@ -229,14 +230,18 @@ int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int row
       return fail(h, ORBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     enc = (encode_tiled_fn)fn;
   }
-  const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)frames};
+  const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)frames};
   const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_bytes};  // bytes, multiples of 16
   const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return ORBX_OK;
+}
+
+int encode_plane_map(orbx_t* h, CUtensorMap* out, void* base, int pitch, int rows, int frames, size_t frame_bytes, int box_w, int box_h) {
+  return encode_map(h, out, base, (size_t)pitch, (size_t)pitch, rows, frames, frame_bytes, box_w, box_h);
 }
 
 // Geometry of all levels for a w x h input, device buffers for max_batch frames per slot.
@@ -399,10 +404,15 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
 // The kernel sequence of OrbExtractor::operator() for `frames` device-resident frames.
 void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_stride, size_t frame_stride, int frames,
                       int lap0, int lap1, orbx_kp* d_kps, uint8_t* d_desc, int cap, int32_t* d_n, int32_t* d_nmono,
-                      int out_frame0, cudaStream_t st, cudaEvent_t after_import = nullptr) {
+                      int out_frame0, cudaStream_t st, cudaEvent_t after_import = nullptr, bool in_place = false) {
   FrameGeom g = h->g;
   g.lap0 = lap0;
   g.lap1 = lap1;
+  if (in_place) {  // level 0 = the caller's frames (s.b.ext0_*_map describe them)
+    g.ext0 = d_src;
+    g.ext0_pitch = (unsigned)row_stride;
+    g.ext0_frame = (unsigned long long)frame_stride;
+  }
   int n = 0;
   auto mark = [&]() {
     if (!h->profiling) return;
@@ -415,7 +425,7 @@ void enqueue_pipeline(orbx_t* h, Slot& s, const uint8_t* d_src, size_t row_strid
   // NVTX ranges around the launches of the five stages: free when no tool is attached
   mark();
   nvtxRangePushA("orbx:import");
-  n += launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
+  n += in_place ? launch_zero_counters(g, s.b, frames, st) : launch_import(g, s.b, d_src, row_stride, frame_stride, frames, st);
   nvtxRangePop();
   if (after_import) cudaEventRecord(after_import, st);  // the staging buffer may be overwritten from here on
   mark();
@@ -516,7 +526,7 @@ int check_image(orbx_t* h, const uint8_t* img, int w, int hh, size_t stride) {
 namespace orbx {
 bool orbx_peek_pyramid(const orbx_extractor* h, FrameGeom* g, const uint8_t** pyr, const float** sf, const float** isf,
                        int* device) {
-  if (!h || !h->geom_valid || h->last_frames < 1) return false;
+  if (!h || !h->geom_valid || h->last_frames < 1 || h->level0_external) return false;
   *g = h->g;
   *pyr = h->slot[0].b.pyr;
   *sf = h->scale;
@@ -680,11 +690,26 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     Slot& s = h->slot[0];
     cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
     CU(h, slot_acquire(s, st));
+    // Frames that lie on 16-byte boundaries are not copied into the pyramid slab: the detector and the first resize fetch
+    // their tiles through TMA descriptors over the caller's buffer and the orientation reads it directly (level 0 "in
+    // place"; the frames must stay unchanged until the call's work has completed on the stream, as for any asynchronous
+    // call).  Level 1 must be one the TMA resize handles (scale factor below ~2), else the frames are imported as before.
+    static const bool no_in_place = getenv("ORBX_NO_IN_PLACE") != nullptr;  // A/B knob
+    int th1 = 0, bw1 = 0, bh1 = 0;
+    if (h->g.nlev > 1) resize_tile_plan(h->g, 1, &th1, &bw1, &bh1);
+    const bool in_place = !no_in_place && ((reinterpret_cast<uintptr_t>(imgs) | row_stride | frame_stride) & 15) == 0 &&
+                          row_stride <= 0xFFFFFFFFull && (h->g.nlev < 2 || bw1 != 0);
     for (int f0 = 0; f0 < n_frames; f0 += B) {
       const int nf = n_frames - f0 < B ? n_frames - f0 : B;
-      enqueue_pipeline(h, s, imgs + (size_t)f0 * frame_stride, row_stride, frame_stride, nf, lap0, lap1, kps, desc, cap,
-                       n, n_mono, f0, st);
+      const uint8_t* src = imgs + (size_t)f0 * frame_stride;
+      if (in_place) {
+        rc = encode_map(h, &s.b.ext0_fast_map, src, (size_t)w, row_stride, hh, nf, frame_stride, kFastTileBoxW, kFastTileBoxH);
+        if (rc == ORBX_OK && h->g.nlev > 1) rc = encode_map(h, &s.b.ext0_rs_map, src, (size_t)w, row_stride, hh, nf, frame_stride, bw1, bh1);
+        if (rc != ORBX_OK) { slot_release(s, st); return rc; }
+      }
+      enqueue_pipeline(h, s, src, row_stride, frame_stride, nf, lap0, lap1, kps, desc, cap, n, n_mono, f0, st, nullptr, in_place);
       h->last_frames = nf;
+      h->level0_external = in_place;
     }
     CU(h, slot_release(s, st));
     CU(h, cudaGetLastError());
@@ -720,7 +745,7 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     }
     CU(h, cudaMemcpyAsync(n + f0, s.d_n, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     CU(h, cudaMemcpyAsync(n_mono + f0, s.d_n + B, nf * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-    if (&s == &h->slot[0]) h->last_frames = nf;
+    if (&s == &h->slot[0]) { h->last_frames = nf; h->level0_external = false; }
   }
   if (mem == ORBX_MEM_HOST)
     for (auto& s : h->slot) CU(h, cudaStreamSynchronize(s.stream));
@@ -744,6 +769,7 @@ int orbx_extract_begin(orbx_t* h, const uint8_t* img, int w, int hh, size_t stri
   rc = stage_frames(h, s, img, w, hh, stride, stride * (size_t)hh, 1, &drs, &dfs);
   if (rc) return rc;
   h->last_frames = 1;
+  h->level0_external = false;
   const size_t kp_bytes = (size_t)h->out_cap * sizeof(orbx_kp), desc_bytes = (size_t)h->out_cap * 32;
   const size_t single_bytes = kp_bytes + desc_bytes + 2 * sizeof(int32_t);
   if (!h->h_out) CU(h, cudaMallocHost((void**)&h->h_out, single_bytes));
@@ -842,6 +868,7 @@ int orbx_compute_pyramid(orbx_t* h, const uint8_t* img, int w, int hh, size_t st
   nl += launch_border(h->g, s.b, 1, s.stream);
   h->launches += nl;
   h->last_frames = 1;
+  h->level0_external = false;
   h->border_done = true;
   CU(h, cudaStreamSynchronize(s.stream));
   return ORBX_OK;
@@ -855,6 +882,7 @@ int orbx_pyramid_level(orbx_t* h, int lev, uint8_t* dst, size_t dst_stride, int*
   if (w) *w = L.w;
   if (hh) *hh = L.h;
   if (!dst) return ORBX_OK;
+  if (lev == 0 && h->level0_external) return fail(h, ORBX_E_ARG, "level 0 of the last call was read in place from the caller's frames");
   if (dst_stride < (size_t)(L.w + 2 * kEdge)) return fail(h, ORBX_E_ARG, "dst_stride too small");
   CU(h, cudaSetDevice(h->device));
   Slot& s = h->slot[0];
@@ -881,6 +909,8 @@ int orbx_stage_download(orbx_t* h, int frame, int stage, int lev, void* dst, siz
   CU(h, slot_acquire(s, s.stream));
   CU(h, slot_release(s, s.stream));
   CU(h, cudaStreamSynchronize(s.stream));
+  if (stage == ORBX_STAGE_LEVEL && lev == 0 && h->level0_external)
+    return fail(h, ORBX_E_ARG, "level 0 of the last call was read in place from the caller's frames");
   if (stage == ORBX_STAGE_LEVEL || stage == ORBX_STAGE_BLUR) {
     const size_t need = (size_t)L.w * L.h;
     *count = (int)need;

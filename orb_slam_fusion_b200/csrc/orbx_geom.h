@@ -51,6 +51,11 @@ struct FrameGeom {
   int lap0, lap1;
   int node_cap;          // quadtree node-table capacity (per level problem)
   int total_blur_tiles;
+  // Level 0 read IN PLACE from the caller's device frames (set per call; NULL: level 0 is the padded plane of the pyramid
+  // slab, filled by k_import).  Base, row stride and frame stride are multiples of 16 bytes.
+  const uint8_t* ext0;
+  unsigned ext0_pitch;             // bytes per row
+  unsigned long long ext0_frame;   // bytes per frame
   LevelGeom lv[ORBX_MAX_LEVELS];
 };
 

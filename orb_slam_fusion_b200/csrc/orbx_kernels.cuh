@@ -32,6 +32,10 @@ struct BatchBuffers {
   const CUtensorMap* pyr_maps;  // [nlev] TMA descriptors of the pyramid planes: u8 [frame][padded row][padded byte]
   const CUtensorMap* rs_maps;   // [nlev] entry l: planes of level l-1 with the source box of k_resize_tma's tiles (resize_tile_plan)
   const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
+  // host copies, passed to the kernels as __grid_constant__ parameters: TMA descriptors over the CALLER's frames
+  // [frame][row][byte] when level 0 is read in place (FrameGeom::ext0) -- the detector's tile box and the source box of
+  // the resize of level 1
+  CUtensorMap ext0_fast_map, ext0_rs_map;
 };
 
 #ifndef ORBX_FAST_TILE_H
@@ -43,6 +47,7 @@ constexpr int kFastTileBoxW = 160, kFastTileBoxH = kFastTileH + 8;  // bytes x r
 // Each launcher enqueues on `st` and returns the number of kernels it launched.
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
                   size_t frame_stride, int frames, cudaStream_t st);
+int launch_zero_counters(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // what k_import does besides copying (level 0 in place)
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 // tile plan of the resize of level `lev`: output rows per tile, TMA box (bytes x rows) of the source tile; bw == 0: no TMA
 void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh);

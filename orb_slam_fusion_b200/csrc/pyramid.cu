@@ -46,6 +46,18 @@ __global__ void __launch_bounds__(256) k_import(const __grid_constant__ FrameGeo
   }
 }
 
+// Level 0 in place: nothing to copy, only the counters k_fast_blur accumulates into.
+__global__ void __launch_bounds__(256) k_zero_counters(const __grid_constant__ FrameGeom g, int32_t* __restrict__ n_cand,
+                                                       int32_t* __restrict__ cell_strong) {
+  const int f = blockIdx.y;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.total_cells; c += gridDim.x * blockDim.x) cell_strong[(size_t)f * g.total_cells + c] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < ORBX_MAX_LEVELS) n_cand[f * ORBX_MAX_LEVELS + threadIdx.x] = 0;
+}
+int launch_zero_counters(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st) {
+  k_zero_counters<<<dim3((g.total_cells + 255) / 256, frames), 256, 0, st>>>(g, b.n_cand, b.cell_strong);
+  return 1;
+}
+
 int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src, size_t row_stride,
                   size_t frame_stride, int frames, cudaStream_t st) {
   const int aligned = ((reinterpret_cast<uintptr_t>(src) | row_stride | frame_stride) & 15) == 0;
@@ -225,7 +237,8 @@ __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b) { return a + b 
 #endif
 template <int BW>
 __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
-                                                    const CUtensorMap* __restrict__ rs_maps, const int16_t* __restrict__ xofs,
+                                                    const CUtensorMap* __restrict__ rs_maps, const __grid_constant__ CUtensorMap ext0_map,
+                                                    const int16_t* __restrict__ xofs,
                                                     const int16_t* __restrict__ xalpha, const int16_t* __restrict__ yofs,
                                                     const int16_t* __restrict__ ybeta, int lev, int th, int bh) {
   extern __shared__ uint8_t rs_smem[];
@@ -249,12 +262,15 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   const int sx_lo = xofs[t + x0] & ~kRsSrcAlign;
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&tile_bar);
   if (tid == 0) {
+    // level 1 of a call that reads level 0 in place takes its source rows from the caller's frames (no padding around them)
+    const bool ext = lev == 1 && g.ext0 != nullptr;
+    const CUtensorMap* map = ext ? &ext0_map : rs_maps + lev;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar));
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bh * BW) : "memory");
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(
                      (unsigned)__cvta_generic_to_shared(src_sm)),
-                 "l"(rs_maps + lev), "r"(sx_lo + kPadX), "r"(row_lo + kPadY), "r"((int)blockIdx.z), "r"(bar)
+                 "l"(map), "r"(sx_lo + (ext ? 0 : kPadX)), "r"(row_lo + (ext ? 0 : kPadY)), "r"((int)blockIdx.z), "r"(bar)
                  : "memory");
   }
 
@@ -381,9 +397,9 @@ int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, i
   dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
   const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint4) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
   if (bw == kRsBwSmall)
-    k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+    k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
   else if (bw == 256)
-    k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+    k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
   else
     k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
   return 1;

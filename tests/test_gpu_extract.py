@@ -185,6 +185,48 @@ def test_batch_host_and_device(P, oracle):
     assert (n2 == -np.array([len(want[0][1]), len(want[1][1])])).all()
 
 
+@pytest.mark.parametrize("w,h", [(752, 480), (750, 331), (320, 240)])
+def test_device_frames_read_in_place(P, oracle, w, h):
+    """Device-memory batches whose frames lie on 16-byte boundaries are not copied into the pyramid slab (level 0 is read
+    through TMA descriptors over the caller's buffer and directly by the orientation); any other layout is imported.
+    Every layout must give the host path's result: contiguous aligned frames, rows and frames with padding (a view into a
+    larger tensor), a base address off the 16-byte grid, widths that are not a multiple of 16; stage downloads of level 0
+    are refused after an in-place call (the slot holds no copy) and work again after an imported one."""
+    import torch
+    from orb_slam_fusion_b200 import _abi as A
+    F = 5
+    imgs = np.stack([oracle.blocks_v1(w, h, 3, f) for f in range(F)])
+    ex = P.OrbExtractor(500, 1.2, 8, 20, 7, max_batch=2)   # 3 chunks: the descriptors are rebuilt per chunk
+    n, nm, kps, desc = ex.extract_batch(imgs)
+
+    def same(out):
+        dn, dnm, dk, dd = out
+        torch.cuda.synchronize()
+        dn, dnm = dn.cpu().numpy(), dnm.cpu().numpy()
+        dk = dk.cpu().numpy().view(P.KP_DTYPE).reshape(F, -1)
+        dd = dd.cpu().numpy()
+        assert np.array_equal(dn, n) and np.array_equal(dnm, nm)
+        for f in range(F):
+            assert dk[f, :n[f]].tobytes() == kps[f, :n[f]].tobytes() and np.array_equal(dd[f, :n[f]], desc[f, :n[f]])
+
+    pitch = (w + 15) // 16 * 16 + 32
+    big = torch.zeros((F, h + 3, pitch), dtype=torch.uint8, device="cuda")       # rows and frames with padding, 16-byte aligned
+    big[:, :h, :w] = torch.from_numpy(imgs).cuda()
+    view = big[:, :h, :w]
+    assert view.data_ptr() % 16 == 0 and view.stride(1) % 16 == 0 and view.stride(0) % 16 == 0
+    same(ex.extract_batch(view))
+    with pytest.raises(RuntimeError):
+        ex.stage(A.STAGE_LEVEL, 0)                                               # level 0 was read in place
+    assert ex.stage(A.STAGE_LEVEL, 1).shape[0] > 0
+    flat = torch.zeros(F * h * pitch + 64, dtype=torch.uint8, device="cuda")     # the same layout 8 bytes off the grid: imported
+    off = flat[8:8 + F * h * pitch].view(F, h, pitch)
+    off[:, :, :w] = torch.from_numpy(imgs).cuda()
+    assert off.data_ptr() % 16 == 8
+    same(ex.extract_batch(off[:, :, :w]))
+    assert np.array_equal(ex.stage(A.STAGE_LEVEL, 0, frame=0), imgs[4])          # frame 0 of the last chunk
+    same(ex.extract_batch(torch.from_numpy(imgs).cuda()))                        # contiguous: in place when w % 16 == 0
+
+
 def test_device_synth_equals_oracle_generators(P, oracle):
     fr = P.synth_frames("blocks", 3, 752, 480, seed=1, first_frame=5).cpu().numpy()
     for f in range(3):
