@@ -11,7 +11,7 @@ import sys
 import tempfile
 
 lib = os.path.abspath(sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "orb_slam_fusion_b200", "liborbx_b200.so"))
-KERNELS = ["k_import", "k_resize_tma", "k_fast_blur", "k_octree", "k_plan", "k_describe", "k_knn2", "k_knn2_merge_keys", "k_top2_keys_ratio",
+KERNELS = ["k_import", "k_zero_counters", "k_resize_tma", "k_fast_blur", "k_octree", "k_plan", "k_describe", "k_knn2", "k_knn2_merge_keys", "k_top2_keys_ratio",
            "k_stereo_rowband", "k_stereo_refine", "k_window_topk", "k_projection_claim", "k_search_by_bow", "k_bow_descend"]
 PROOF = re.compile(r"^(UTMALDG|SYNCS|IDP|VIMNMX3|VABSDIFF4|POPC|REDUX|LDGSTS|UBLKCP|BAR)")
 with tempfile.TemporaryDirectory() as td:
