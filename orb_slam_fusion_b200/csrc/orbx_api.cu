@@ -698,7 +698,7 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     int th1 = 0, bw1 = 0, bh1 = 0;
     if (h->g.nlev > 1) resize_tile_plan(h->g, 1, &th1, &bw1, &bh1);
     const bool in_place = !no_in_place && ((reinterpret_cast<uintptr_t>(imgs) | row_stride | frame_stride) & 15) == 0 &&
-                          row_stride <= 0xFFFFFFFFull && (h->g.nlev < 2 || bw1 != 0);
+                          row_stride <= 0xFFFFFFFFull && frame_stride >= row_stride * (size_t)hh && (h->g.nlev < 2 || bw1 != 0);  // (overlapping / repeated frames: imported)
     for (int f0 = 0; f0 < n_frames; f0 += B) {
       const int nf = n_frames - f0 < B ? n_frames - f0 : B;
       const uint8_t* src = imgs + (size_t)f0 * frame_stride;
