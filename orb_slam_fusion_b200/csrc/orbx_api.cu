@@ -349,20 +349,22 @@ int ensure_geometry(orbx_t* h, int w, int hh) {
                                         kFastTileBoxW, kFastTileBoxH);
         if (rc != ORBX_OK) return rc;
       }
-      CUtensorMap rmaps[ORBX_MAX_LEVELS];
-      memset(rmaps, 0, sizeof(rmaps));
-      for (int l = 1; l < g.nlev; l++) {
-        int th, bw, bh;
-        resize_tile_plan(g, l, &th, &bw, &bh);
-        if (!bw) continue;
-        const int rc = encode_plane_map(h, &rmaps[l], s.b.pyr + g.lv[l - 1].plane_off, g.lv[l - 1].pitch, g.lv[l - 1].h + 2 * kPadY, (int)B,
-                                        (size_t)plane, bw, bh);
-        if (rc != ORBX_OK) return rc;
+      for (int plan = 0; plan < 2; plan++) {  // 0: batch tile plan, 1: single-frame tile plan
+        CUtensorMap rmaps[ORBX_MAX_LEVELS];
+        memset(rmaps, 0, sizeof(rmaps));
+        for (int l = 1; l < g.nlev; l++) {
+          int th, bw, bh;
+          resize_tile_plan(g, l, plan == 0 ? kRsBatchFrames : 1, &th, &bw, &bh);
+          if (!bw) continue;
+          const int rc = encode_plane_map(h, &rmaps[l], s.b.pyr + g.lv[l - 1].plane_off, g.lv[l - 1].pitch, g.lv[l - 1].h + 2 * kPadY, (int)B,
+                                          (size_t)plane, bw, bh);
+          if (rc != ORBX_OK) return rc;
+        }
+        CUtensorMap* drm = nullptr;
+        CU(h, dmalloc(s, &drm, (size_t)g.nlev));
+        CU(h, cudaMemcpy(drm, rmaps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));
+        (plan == 0 ? s.b.rs_maps : s.b.rs_maps_single) = drm;
       }
-      CUtensorMap* drm = nullptr;
-      CU(h, dmalloc(s, &drm, (size_t)g.nlev));
-      CU(h, cudaMemcpy(drm, rmaps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));
-      s.b.rs_maps = drm;
       CUtensorMap* dm = nullptr;
       CU(h, dmalloc(s, &dm, (size_t)g.nlev));
       CU(h, cudaMemcpy(dm, maps, sizeof(CUtensorMap) * g.nlev, cudaMemcpyHostToDevice));
@@ -696,13 +698,14 @@ int orbx_extract_batch(orbx_t* h, const uint8_t* imgs, int n_frames, int w, int 
     // call).  Level 1 must be one the TMA resize handles (scale factor below ~2), else the frames are imported as before.
     static const bool no_in_place = getenv("ORBX_NO_IN_PLACE") != nullptr;  // A/B knob
     int th1 = 0, bw1 = 0, bh1 = 0;
-    if (h->g.nlev > 1) resize_tile_plan(h->g, 1, &th1, &bw1, &bh1);
+    if (h->g.nlev > 1) resize_tile_plan(h->g, 1, n_frames < B ? n_frames : B, &th1, &bw1, &bh1);
     const bool in_place = !no_in_place && ((reinterpret_cast<uintptr_t>(imgs) | row_stride | frame_stride) & 15) == 0 &&
                           row_stride <= 0xFFFFFFFFull && frame_stride >= row_stride * (size_t)hh && (h->g.nlev < 2 || bw1 != 0);  // (overlapping / repeated frames: imported)
     for (int f0 = 0; f0 < n_frames; f0 += B) {
       const int nf = n_frames - f0 < B ? n_frames - f0 : B;
       const uint8_t* src = imgs + (size_t)f0 * frame_stride;
       if (in_place) {
+        if (h->g.nlev > 1) resize_tile_plan(h->g, 1, nf, &th1, &bw1, &bh1);  // the box of THIS chunk's tile plan
         rc = encode_map(h, &s.b.ext0_fast_map, src, (size_t)w, row_stride, hh, nf, frame_stride, kFastTileBoxW, kFastTileBoxH);
         if (rc == ORBX_OK && h->g.nlev > 1) rc = encode_map(h, &s.b.ext0_rs_map, src, (size_t)w, row_stride, hh, nf, frame_stride, bw1, bh1);
         if (rc != ORBX_OK) { slot_release(s, st); return rc; }

@@ -30,7 +30,8 @@ struct BatchBuffers {
   const int16_t* yofs;   // source row of destination row (already clamped pair in yofs2)
   const int16_t* ybeta;  // 2 coefficients per destination row
   const CUtensorMap* pyr_maps;  // [nlev] TMA descriptors of the pyramid planes: u8 [frame][padded row][padded byte]
-  const CUtensorMap* rs_maps;   // [nlev] entry l: planes of level l-1 with the source box of k_resize_tma's tiles (resize_tile_plan)
+  const CUtensorMap* rs_maps;   // [nlev] entry l: planes of level l-1 with the source box of k_resize_tma's tiles (resize_tile_plan of a batch)
+  const CUtensorMap* rs_maps_single;  // the same with the box of the single-frame tile plan (frames < kRsBatchFrames)
   const uint32_t* tile_tab;  // [total_blur_tiles] (level << 24) | (tile row << 12) | tile column of the 128x32 tiles
   // host copies, passed to the kernels as __grid_constant__ parameters: TMA descriptors over the CALLER's frames
   // [frame][row][byte] when level 0 is read in place (FrameGeom::ext0) -- the detector's tile box and the source box of
@@ -50,7 +51,8 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 int launch_zero_counters(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);  // what k_import does besides copying (level 0 in place)
 int launch_pyramid(const FrameGeom& g, const BatchBuffers& b, int frames, cudaStream_t st);
 // tile plan of the resize of level `lev`: output rows per tile, TMA box (bytes x rows) of the source tile; bw == 0: no TMA
-void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh);
+constexpr int kRsBatchFrames = 16;  // launches of at least this many frames use the batch tile plan
+void resize_tile_plan(const FrameGeom& g, int lev, int frames, int* th, int* bw, int* bh);
 // per-level launchers: the single-frame pipeline runs level l's detector and quadtree as a branch beside the resize chain
 int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, cudaStream_t st);
 int launch_fast_levels(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, int lev_end, cudaStream_t st);    // levels [lev, lev_end)

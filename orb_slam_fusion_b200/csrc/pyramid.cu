@@ -77,6 +77,18 @@ int launch_import(const FrameGeom& g, const BatchBuffers& b, const uint8_t* src,
 #define ORBX_RS_TH 32
 #endif
 constexpr int kRsTW = 128, kRsMaxTH = ORBX_RS_TH, kRsRows = 2 * kRsMaxTH + 4;
+// The TMA kernel's own tile heights (dynamic shared memory).  Batches: 48 output rows per CTA -- the per-CTA set-up (column
+// tables, TMA, row table) is a quarter of the kernel's instructions at 32 rows, and 48 is where its amortisation stops
+// paying against occupancy (per 512 frames: 32 rows 0.479 ms, 40: 0.451, 48: 0.448, 56: 0.470, 64: 0.474).  A single frame
+// has fewer tiles than the GPU has SMs, so it keeps 32-row tiles: shorter CTAs, shorter chain.
+#ifndef ORBX_RS_TMA_TH
+#define ORBX_RS_TMA_TH 48
+#endif
+#ifndef ORBX_RS_TMA_TH_SINGLE
+#define ORBX_RS_TMA_TH_SINGLE 32
+#endif
+constexpr int kRsTmaTH = ORBX_RS_TMA_TH, kRsTmaTHSingle = ORBX_RS_TMA_TH_SINGLE;
+static_assert(kRsTmaTHSingle <= kRsTmaTH && kRsTmaTH % 8 == 0, "the single-frame tile fits the batch tile's buffers");
 constexpr int kRsSrcChunks = 19, kRsSrcPitch = 16 * kRsSrcChunks;  // staged source columns per tile (scale <= ~2.2)
 
 #ifndef ORBX_RS_MINB
@@ -235,7 +247,7 @@ __device__ __forceinline__ uint32_t add3(uint32_t a, uint32_t b) { return a + b 
 #ifndef ORBX_RS_TMA_MINB
 #define ORBX_RS_TMA_MINB 5
 #endif
-template <int BW>
+template <int BW, int TH>  // TH: the launch's maximum tile height (batch or single-frame plan), rows per warp = TH / 8
 __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __grid_constant__ FrameGeom g, uint8_t* __restrict__ pyr,
                                                     const CUtensorMap* __restrict__ rs_maps, const __grid_constant__ CUtensorMap ext0_map,
                                                     const int16_t* __restrict__ xofs,
@@ -325,7 +337,7 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
       const int off = sx0 - sx_lo, sh = 8 * (off & 3);
       const uint32_t* wp = reinterpret_cast<const uint32_t*>(src_sm + r0 * BW) + (off >> 2);
 #pragma unroll
-      for (int i = 0; i < (kRsRows + 7) / 8; i++) {
+      for (int i = 0; i < (2 * TH + 4 + 7) / 8; i++) {
         if (i < rpg && r0 + i < n_rows) {
           const uint32_t w0 = wp[i * (BW / 4)], w1 = wp[i * (BW / 4) + 1], w2 = wp[i * (BW / 4) + 2];
           const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);  // bytes sx0 .. sx0+7
@@ -340,10 +352,10 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   }
   __syncthreads();
 
-  // ---- vertical pass: thread = (quad q, kRsMaxTH / 8 output rows).  (b * (H >> 4)) >> 16 is the high word of
+  // ---- vertical pass: thread = (quad q, kRsTmaTH / 8 output rows).  (b * (H >> 4)) >> 16 is the high word of
   // (b << 12) * (H & ~15): one IMAD.HI per product, both factors as stored.
   {
-    constexpr int kVRows = kRsMaxTH / 8;
+    constexpr int kVRows = TH / 8;
     const int q = tid & 31, yy0 = (tid >> 5) * kVRows;
     const int dx0 = x0 + 4 * q;
     if (dx0 < D.w) {
@@ -373,33 +385,43 @@ __global__ void __launch_bounds__(256, ORBX_RS_TMA_MINB) k_resize_tma(const __gr
   }
 }
 
-void resize_tile_plan(const FrameGeom& g, int lev, int* th, int* bw, int* bh) {
+void resize_tile_plan(const FrameGeom& g, int lev, int frames, int* th, int* bw, int* bh) {
   // rows per tile so that the source rows of a tile fit the shared buffer (any scale factor)
   const double ry = (double)g.lv[lev - 1].h / g.lv[lev].h, rx = (double)g.lv[lev - 1].w / g.lv[lev].w;
-  int t = (int)((kRsRows - 3) / ry);
-  t = t < 1 ? 1 : (t > kRsMaxTH ? kRsMaxTH : t);
-  *th = t;
-  // source span of 128 output columns / t output rows: first tap of the first .. second tap of the last
-  const int need_w = (int)ceil(127.0 * rx) + 3 + kRsSrcAlign, need_h = (int)ceil((t - 1) * ry) + 3;
+  // source span of 128 output columns: first tap of the first .. second tap of the last
+  const int need_w = (int)ceil(127.0 * rx) + 3 + kRsSrcAlign;
   *bw = need_w <= kRsBwSmall ? kRsBwSmall : (need_w <= 256 ? 256 : 0);  // 0: the LDGSTS / gather kernel
-  *bh = need_h < kRsRows ? need_h : kRsRows;
+  const int max_th = *bw ? (frames >= kRsBatchFrames ? kRsTmaTH : kRsTmaTHSingle) : kRsMaxTH, max_rows = *bw ? 2 * max_th + 4 : kRsRows;
+  int t = (int)((max_rows - 3) / ry);
+  t = t < 1 ? 1 : (t > max_th ? max_th : t);
+  *th = t;
+  const int need_h = (int)ceil((t - 1) * ry) + 3;  // source rows of t output rows
+  *bh = need_h < max_rows ? need_h : max_rows;
 }
 
 cudaError_t resize_configure() {  // scale factors near 2 need more than the default 48 KB of dynamic shared memory
-  cudaError_t e = cudaFuncSetAttribute(k_resize_tma<kRsBwSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resize_tma<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(k_resize_tma<kRsBwSmall, kRsTmaTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resize_tma<256, kRsTmaTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resize_tma<kRsBwSmall, kRsTmaTHSingle>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resize_tma<256, kRsTmaTHSingle>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   return e;
 }
 
 int launch_resize_level(const FrameGeom& g, const BatchBuffers& b, int frames, int lev, cudaStream_t st) {
   int th, bw, bh;
-  resize_tile_plan(g, lev, &th, &bw, &bh);
+  resize_tile_plan(g, lev, frames, &th, &bw, &bh);
+  const CUtensorMap* maps = frames >= kRsBatchFrames ? b.rs_maps : b.rs_maps_single;
   dim3 grid((g.lv[lev].w + kRsTW - 1) / kRsTW, (g.lv[lev].h + th - 1) / th, frames);
-  const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint4) * kRsMaxTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
-  if (bw == kRsBwSmall)
-    k_resize_tma<kRsBwSmall><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+  const size_t smem = 128 + (size_t)((bh * bw + 127) & ~127) + (size_t)bh * kRsTW * 4 + 16 + sizeof(uint4) * kRsTmaTH;  // alignment slack, tile, H rows (u32), mbarrier, row table
+  const bool batch = frames >= kRsBatchFrames;
+  if (bw == kRsBwSmall && batch)
+    k_resize_tma<kRsBwSmall, kRsTmaTH><<<grid, 256, smem, st>>>(g, b.pyr, maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+  else if (bw == kRsBwSmall)
+    k_resize_tma<kRsBwSmall, kRsTmaTHSingle><<<grid, 256, smem, st>>>(g, b.pyr, maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+  else if (bw == 256 && batch)
+    k_resize_tma<256, kRsTmaTH><<<grid, 256, smem, st>>>(g, b.pyr, maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
   else if (bw == 256)
-    k_resize_tma<256><<<grid, 256, smem, st>>>(g, b.pyr, b.rs_maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
+    k_resize_tma<256, kRsTmaTHSingle><<<grid, 256, smem, st>>>(g, b.pyr, maps, b.ext0_rs_map, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th, bh);
   else
     k_resize<<<grid, 256, 0, st>>>(g, b.pyr, b.xofs, b.xalpha, b.yofs, b.ybeta, lev, th);
   return 1;
