@@ -1179,6 +1179,8 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
   const int lane = threadIdx.x, words = (n + 31) / 32;
   uint32_t* hist = claim_bits + words;
   uint32_t* cellinfo = with_cells ? hist + 32 : nullptr;  // grid cell of every keypoint: re-scans reject most keypoints on one word
+  // (one warp, alone on its SM: every loop over the keypoints is unrolled so that its global loads are in flight together)
+#pragma unroll 4
   for (int i = lane; i < n; i += 32) {
     assigned[i] = -1;
     if (cellinfo) {
@@ -1189,33 +1191,54 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
   for (int i = lane; i < words; i += 32) claim_bits[i] = 0;
   __syncwarp();
   int nm = 0;
-  for (int base = 0; base < nq; base += 32) {
+  // the lists of the NEXT batch are fetched while this one is decided
+  unsigned long long nk[KL];
+  unsigned nblockers = 0;
+  auto fetch = [&](int base) {
     const int qi = base + lane;
-    const unsigned blockers = qi < nq ? conflict[qi] : 0u;
-    unsigned long long k[KL];
+    nblockers = qi < nq ? conflict[qi] : 0u;
 #pragma unroll
     for (int e = 0; e < KL; e += 2) {
-      k[e] = k[e + 1] = ~0ull;
+      nk[e] = nk[e + 1] = ~0ull;
       if (qi < nq) {
         const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(keys4 + KL * (size_t)qi + e);
-        k[e] = a.x; k[e + 1] = a.y;
+        nk[e] = a.x; nk[e + 1] = a.y;
       }
     }
+  };
+  fetch(0);
+  for (int base = 0; base < nq; base += 32) {
+    const int qi = base + lane;
+    const unsigned blockers = nblockers;
+    unsigned long long k[KL];
+#pragma unroll
+    for (int e = 0; e < KL; e++) k[e] = nk[e];
+    fetch(base + 32);
     int idx[KL];
 #pragma unroll
     for (int e = 0; e < KL; e++) idx[e] = k[e] == ~0ull ? -1 : (int)((k[e] >> 4) & 0xFFFFFFu);
     unsigned undecided = __ballot_sync(0xffffffffu, qi < nq && idx[0] >= 0);  // an empty list decides nothing (:75)
     while (undecided) {
       const unsigned ready = __ballot_sync(0xffffffffu, ((undecided >> lane) & 1u) && (blockers & undecided) == 0);
-      // survivors of the list under the claims so far
+      // survivors of the list under the claims so far.  The warp runs alone on its SM, so what counts is the length of the
+      // dependent chain, not the instruction count: the KL claim bits are fetched side by side into one mask and the first
+      // two set bits pick the keys, instead of a running survivor count that makes every entry wait for the one before
       unsigned long long b0 = ~0ull, b1 = ~0ull;
       int survivors = 0;
       if ((ready >> lane) & 1u) {
+        unsigned alive = 0;
 #pragma unroll
         for (int e = 0; e < KL; e++) {
-          if (idx[e] < 0 || ((claim_bits[idx[e] >> 5] >> (idx[e] & 31)) & 1u)) continue;
-          if (survivors == 0) b0 = k[e]; else if (survivors == 1) b1 = k[e];
-          survivors++;
+          const int ie = idx[e] < 0 ? 0 : idx[e];
+          const unsigned claimed = (claim_bits[ie >> 5] >> (ie & 31)) & 1u;
+          alive |= (unsigned)(idx[e] >= 0 && !claimed) << e;
+        }
+        survivors = __popc(alive);
+        const int f0 = __ffs(alive) - 1, f1 = __ffs(alive & (alive - 1u)) - 1;
+#pragma unroll
+        for (int e = 0; e < KL; e++) {
+          b0 = e == f0 ? k[e] : b0;
+          b1 = e == f1 ? k[e] : b1;
         }
       }
       unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[KL - 1] >= 0);
@@ -1249,14 +1272,15 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
     __syncwarp();
     if (lane < 30) hist[lane] = 0;
     __syncwarp();
+#pragma unroll 4
     for (int i = lane; i < n; i += 32) {
       const int qi = assigned[i];
-      if (qi < 0) continue;
-      float rot = f_sub(q_angle[qi], kps[i].angle);
+      const bool has = qi >= 0;
+      float rot = f_sub(q_angle[has ? qi : 0], kps[i].angle);
       if (rot < 0.0f) rot = f_add(rot, 360.0f);
       int bin = (int)roundf(f_mul(rot, factor));
       if (bin == 30) bin = 0;
-      atomicAdd(&hist[bin < 0 ? 0 : (bin > 29 ? 29 : bin)], 1u);
+      if (has) atomicAdd(&hist[bin < 0 ? 0 : (bin > 29 ? 29 : bin)], 1u);
     }
     __syncwarp();
     int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;  // ComputeThreeMaxima (:1841-1873), every lane alike
@@ -1269,15 +1293,16 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
     if ((float)max2 < f_mul(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
     else if ((float)max3 < f_mul(0.1f, (float)max1)) { ind3 = -1; }
     int dropped = 0;
+#pragma unroll 4
     for (int i = lane; i < n; i += 32) {
       const int qi = assigned[i];
-      if (qi < 0) continue;
-      float rot = f_sub(q_angle[qi], kps[i].angle);
+      const bool has = qi >= 0;
+      float rot = f_sub(q_angle[has ? qi : 0], kps[i].angle);
       if (rot < 0.0f) rot = f_add(rot, 360.0f);
       int bin = (int)roundf(f_mul(rot, factor));
       if (bin == 30) bin = 0;
       bin = bin < 0 ? 0 : (bin > 29 ? 29 : bin);
-      if (bin != ind1 && bin != ind2 && bin != ind3) { assigned[i] = -1; dropped++; }
+      if (has && bin != ind1 && bin != ind2 && bin != ind3) { assigned[i] = -1; dropped++; }
     }
     nm -= __reduce_add_sync(0xffffffffu, dropped);
   }
