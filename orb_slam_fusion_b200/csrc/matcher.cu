@@ -1002,35 +1002,53 @@ __device__ __forceinline__ void window_topk(const orbx_kp* __restrict__ kps, con
   if (!ok) return;  // warp-uniform
   uint32_t qd[8];
   load_row_any(qd_row, qd);
-  for (int i = lane; i < n; i += 32) {
-    if (cellinfo) {  // (valid << 31 | px << 10 | py) of every keypoint, computed once per call: most keypoints end here
-      const uint32_t ci = cellinfo[i];
-      const int cpx = (int)((ci >> 10) & 0x3FFu), cpy = (int)(ci & 0x3FFu);
-      if (!(ci >> 31) || cpx < c0x || cpx > c1x || cpy < c0y || cpy > c1y) continue;
-      if ((bitmap[i >> 5] >> (i & 31)) & 1u) continue;
-    }
-    const orbx_kp K = kps[i];
-    const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
-    const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
-    if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
-    if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
-    if (check_levels) {
-      if (K.octave < Q.min_level) continue;
-      if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
-    }
-    const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
-    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
-    if (skip && skip[i]) continue;
-    if (bitmap && ((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
-    if (kp_u_right) {
-      const float ur = kp_u_right[i];
-      if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
-    }
-    uint32_t kd[8];
-    load_row_any(desc + 32 * (size_t)i, kd);
-    unsigned long long key = claim_key(ham256(qd, kd), px * g.rows + py, i, K.octave);
+  // Four keypoints per turn: their positions and levels are loaded first, side by side, and the window tests are one
+  // predicate each; only the few keypoints inside the window go on to the descriptor.  (A loop that bails out of every
+  // keypoint with `continue` keeps one load in flight per warp, and a warp of this kernel has little company on its SM.)
+  constexpr int kU = 4;
+  for (int i0 = lane; i0 < n; i0 += 32 * kU) {
+    float kx[kU], ky[kU];
+    int ko[kU];
+    bool in[kU];
 #pragma unroll
-    for (int j = 0; j < KL; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the KL + 1 falls out
+    for (int u = 0; u < kU; u++) {
+      const int i = i0 + 32 * u;
+      in[u] = i < n;
+      if (in[u] && cellinfo) {  // (valid << 31 | px << 10 | py) of every keypoint, computed once per call: most keypoints end here
+        const uint32_t ci = cellinfo[i];
+        const int cpx = (int)((ci >> 10) & 0x3FFu), cpy = (int)(ci & 0x3FFu);
+        in[u] = (ci >> 31) && cpx >= c0x && cpx <= c1x && cpy >= c0y && cpy <= c1y && !((bitmap[i >> 5] >> (i & 31)) & 1u);
+      }
+      kx[u] = ky[u] = 0.f;
+      ko[u] = 0;
+      if (in[u]) { kx[u] = kps[i].x; ky[u] = kps[i].y; ko[u] = kps[i].octave; }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      if (!in[u]) continue;
+      const int i = i0 + 32 * u;
+      const int px = (int)roundf(f_mul(f_sub(kx[u], g.min_x), g.inv_w));
+      const int py = (int)roundf(f_mul(f_sub(ky[u], g.min_y), g.inv_h));
+      if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
+      if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
+      if (check_levels) {
+        if (ko[u] < Q.min_level) continue;
+        if (Q.max_level >= 0 && ko[u] > Q.max_level) continue;
+      }
+      const float dx = f_sub(kx[u], Q.u), dy = f_sub(ky[u], Q.v);
+      if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+      if (skip && skip[i]) continue;
+      if (bitmap && ((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
+      if (kp_u_right) {
+        const float ur = kp_u_right[i];
+        if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
+      }
+      uint32_t kd[8];
+      load_row_any(desc + 32 * (size_t)i, kd);
+      unsigned long long key = claim_key(ham256(qd, kd), px * g.rows + py, i, ko[u]);
+#pragma unroll
+      for (int j = 0; j < KL; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the KL + 1 falls out
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -1153,6 +1171,20 @@ int launch_window_search(const orbx_kp* kps, const uint8_t* desc, int n, orbm_gr
   return 1;
 }
 
+// k[f] for a run-time f (registers cannot be indexed): binary select tree; f < 0 gives the empty key
+template <int KL>
+__device__ __forceinline__ unsigned long long pick_key(const unsigned long long (&k)[KL], int f) {
+  static_assert(KL == 4 || KL == 8, "list lengths of the claim kernels");
+  unsigned long long t[KL / 2];
+#pragma unroll
+  for (int j = 0; j < KL / 2; j++) t[j] = (f & 1) ? k[2 * j + 1] : k[2 * j];
+#pragma unroll
+  for (int j = 0; j < KL / 4; j++) t[j] = (f & 2) ? t[2 * j + 1] : t[2 * j];
+  unsigned long long r = t[0];
+  if (KL == 8) r = (f & 4) ? t[1] : t[0];
+  return f < 0 ? ~0ull : r;
+}
+
 // The same claim, 32 map points at a time.  Every lane takes one map point of the batch; a lane may decide in a round
 // when no EARLIER undecided lane of the batch has a window that can share a keypoint with its own (conflict words of
 // k_window_topk).  Whatever such a lane ends up claiming -- out of its list or, after a re-scan, anywhere in its window --
@@ -1235,11 +1267,8 @@ __global__ void __launch_bounds__(32) k_projection_claim(const orbx_kp* __restri
         }
         survivors = __popc(alive);
         const int f0 = __ffs(alive) - 1, f1 = __ffs(alive & (alive - 1u)) - 1;
-#pragma unroll
-        for (int e = 0; e < KL; e++) {
-          b0 = e == f0 ? k[e] : b0;
-          b1 = e == f1 ? k[e] : b1;
-        }
+        b0 = pick_key<KL>(k, f0);  // (a select tree of depth log2 KL, not a chain of KL)
+        b1 = pick_key<KL>(k, f1);
       }
       unsigned rescan = __ballot_sync(0xffffffffu, ((ready >> lane) & 1u) && survivors < (LAST ? 1 : 2) && idx[KL - 1] >= 0);
       while (rescan) {  // the list may continue beyond its KL entries
