@@ -90,7 +90,17 @@ __global__ void __launch_bounds__(kPlanThreads) k_plan(const __grid_constant__ F
   __syncthreads();
   const uint32_t* sxy = sel_xy + (size_t)f * g.sel_frame_cap;
   const bool fits = N <= cap && !bad;
-  for (int base = 0; base < N; base += kPlanThreads) {
+  // No keypoint lies left of column 19 (level coordinates, scaled up by >= 1), so a lapping area that ends before it --
+  // {0, 0}, every camera that is not a fisheye pair -- flags nothing: slots are the traversal order itself, no scan
+  const bool no_laps = g.lap1 < kEdge;
+  if (no_laps) {
+    for (int i = tid; i < N; i += kPlanThreads) {
+      int lev = 0;
+      while (i >= lev_start[lev + 1]) lev++;
+      wk[g.lv[lev].sel_off + (i - lev_start[lev])] = fits ? (i | (lev << kWorkLevShift)) : -1;
+    }
+  }
+  for (int base = 0; base < (no_laps ? 0 : N); base += kPlanThreads) {
     const int i = base + tid;
     int flag = 0, lev = 0, idx = 0;
     if (i < N) {
