@@ -352,21 +352,36 @@ __global__ void __launch_bounds__(256) k_stereo_rowband(const orbx_kp* __restric
   if (row >= 0 && row < n_rows && !(max_u < 0)) {
     uint32_t ql[8];
     load_row_any(dl + 32 * (size_t)il, ql);
-    for (int ir = lane; ir < nr; ir += 32) {
-      const orbx_kp R = kr[ir];
-      if (R.octave < L.octave - 1 || R.octave > L.octave + 1) continue;
-      const int oc = R.octave < 0 ? 0 : (R.octave >= n_levels ? n_levels - 1 : R.octave);
-      const float r = f_mul(2.0f, sf[oc]);
-      const int maxr = (int)ceilf(f_add(R.y, r)), minr = (int)floorf(f_sub(R.y, r));
-      if (row < minr || row > maxr) continue;
-      if (!(R.x >= min_u && R.x <= max_u)) continue;
-      uint32_t qr[8];
-      load_row_any(dr + 32 * (size_t)ir, qr);
-      const int d = ham256(ql, qr);
-      if (d < 100) {  // ORBmatcher::TH_HIGH: bestDist starts there, strict <
-        const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)ir;
-        b1 = min(b1, max(b0, key));
-        b0 = min(b0, key);
+    // four right keypoints per turn: positions and levels loaded side by side, the band tests as predicates (a loop that
+    // leaves every keypoint through `continue` keeps one load in flight per warp)
+    constexpr int kU = 4;
+    for (int i0 = lane; i0 < nr; i0 += 32 * kU) {
+      float rx[kU], ry[kU];
+      int ro[kU];
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int ir = i0 + 32 * u;
+        rx[u] = ry[u] = 0.f;
+        ro[u] = -100;  // fails the level test
+        if (ir < nr) { rx[u] = kr[ir].x; ry[u] = kr[ir].y; ro[u] = kr[ir].octave; }
+      }
+#pragma unroll
+      for (int u = 0; u < kU; u++) {
+        const int ir = i0 + 32 * u;
+        if (ro[u] < L.octave - 1 || ro[u] > L.octave + 1) continue;
+        const int oc = ro[u] < 0 ? 0 : (ro[u] >= n_levels ? n_levels - 1 : ro[u]);
+        const float r = f_mul(2.0f, sf[oc]);
+        const int maxr = (int)ceilf(f_add(ry[u], r)), minr = (int)floorf(f_sub(ry[u], r));
+        if (row < minr || row > maxr) continue;
+        if (!(rx[u] >= min_u && rx[u] <= max_u)) continue;
+        uint32_t qr[8];
+        load_row_any(dr + 32 * (size_t)ir, qr);
+        const int d = ham256(ql, qr);
+        if (d < 100) {  // ORBmatcher::TH_HIGH: bestDist starts there, strict <
+          const unsigned long long key = ((unsigned long long)d << 32) | (unsigned)ir;
+          b1 = min(b1, max(b0, key));
+          b0 = min(b0, key);
+        }
       }
     }
   }
@@ -769,40 +784,40 @@ __global__ void __launch_bounds__(256) k_stereo_refine(const __grid_constant__ S
 
 // frame.cc:974-985: median of the accepted SAD distances (element size/2 of the list sorted by
 // (distance, left index)); every match with distance >= 1.5 * 1.4 * median is dropped.  One CTA.
+// Only the VALUE of that element matters, and the k-th smallest value x of a set is the largest v with
+// #{d < v} <= k: v is built bit by bit from the top, one block-wide count (a counting barrier per 1024 values) per bit --
+// 15 steps for SAD sums (< 2^15), 31 for anything else -- instead of ranking every value against every other.
 constexpr int kMedianStage = 8192;  // SAD values staged in shared memory (frames with more left keypoints read them from global memory)
 __global__ void __launch_bounds__(1024) k_stereo_median_cut(int nl, const int32_t* __restrict__ sad, float* __restrict__ u_right,
                                                             float* __restrict__ depth) {
-  __shared__ int n_acc;
-  __shared__ float th;
   __shared__ int32_t staged[kMedianStage];
-  if (threadIdx.x == 0) { n_acc = 0; th = 0.f; }
-  __syncthreads();
   const bool in_smem = nl <= kMedianStage;
-  int cnt = 0;
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-    const int d = sad[i];
-    if (in_smem) staged[i] = d;
-    cnt += d >= 0;
+  const int tid = threadIdx.x, slots = (nl + 1023) / 1024;
+  int n = 0, wide = 0;
+  for (int s = 0; s < slots; s++) {
+    const int i = s * 1024 + tid;
+    const int d = i < nl ? sad[i] : -1;
+    if (in_smem && i < nl) staged[i] = d;
+    n += __syncthreads_count(d >= 0);
+    wide |= d >= (1 << 15);
   }
-  if (cnt) atomicAdd(&n_acc, cnt);
-  __syncthreads();
-  const int n = n_acc;
-  if (n == 0) return;
-  const int32_t* v = in_smem ? staged : sad;  // the rank loop reads every value once per thread: warp-wide broadcasts from shared memory
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
-    const int d = v[i];
-    if (d < 0) continue;
-    int rank = 0;  // number of accepted (distance, index) pairs below this one
-    for (int j = 0; j < nl; j++) {
-      const int e = v[j];
-      rank += (e >= 0) && (e < d || (e == d && j < i));
+  if (n == 0) return;  // (block-uniform)
+  const int32_t* v = in_smem ? staged : sad;
+  const int k = n / 2;
+  int x = 0;
+  for (int b = __syncthreads_or(wide) ? 30 : 14; b >= 0; b--) {
+    const int t = x | (1 << b);
+    int c = 0;
+    for (int s = 0; s < slots; s++) {
+      const int i = s * 1024 + tid;
+      const int d = i < nl ? v[i] : -1;
+      c += __syncthreads_count(d >= 0 && d < t);
     }
-    if (rank == n / 2) th = f_mul(f_mul(1.5f, 1.4f), (float)d);
+    if (c <= k) x = t;
   }
-  __syncthreads();
-  const float t = th;
-  for (int i = threadIdx.x; i < nl; i += blockDim.x)
-    if (v[i] >= 0 && !((float)v[i] < t)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
+  const float th = f_mul(f_mul(1.5f, 1.4f), (float)x);
+  for (int i = tid; i < nl; i += 1024)
+    if (v[i] >= 0 && !((float)v[i] < th)) { u_right[i] = -1.0f; depth[i] = -1.0f; }
 }
 
 int launch_stereo_refine(const FrameGeom& gl, const uint8_t* pyr_l, const FrameGeom& gr, const uint8_t* pyr_r, const float* sf,
