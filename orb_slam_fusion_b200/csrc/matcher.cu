@@ -914,42 +914,57 @@ __device__ __forceinline__ void window_scan(const orbx_kp* __restrict__ kps, con
   if (!ok) return;
   uint32_t qd[8];
   load_row_any(qd_row, qd);
-  for (int i = lane; i < n; i += 32) {
-    const orbx_kp K = kps[i];
-    // Frame::PosInGrid (frame.cc:748-760): round, keypoints outside the grid are in no cell
-    const int px = (int)roundf(f_mul(f_sub(K.x, g.min_x), g.inv_w));
-    const int py = (int)roundf(f_mul(f_sub(K.y, g.min_y), g.inv_h));
-    if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
-    if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
-    if (check_levels) {
-      if (K.octave < Q.min_level) continue;
-      if (Q.max_level >= 0 && K.octave > Q.max_level) continue;
+  // four keypoints per turn: positions and levels loaded side by side, the window tests as predicates (see window_topk)
+  constexpr int kU = 4;
+  for (int i0 = lane; i0 < n; i0 += 32 * kU) {
+    float kx[kU], ky[kU];
+    int ko[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const int i = i0 + 32 * u;
+      kx[u] = ky[u] = 0.f;
+      ko[u] = 0;
+      if (i < n) { kx[u] = kps[i].x; ky[u] = kps[i].y; ko[u] = kps[i].octave; }
     }
-    const float dx = f_sub(K.x, Q.u), dy = f_sub(K.y, Q.v);
-    if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
-    if (skip && skip[i]) continue;
-    if (inv_sigma2) {  // ORBmatcher::Fuse (orb_matcher.cc:1159-1178): reprojection error against the keypoint's level variance
-      const float ex = f_sub(Q.u, K.x), ey = f_sub(Q.v, K.y);
-      const float inv = inv_sigma2[K.octave < 0 ? 0 : (K.octave >= n_levels ? n_levels - 1 : K.octave)];
-      const float kr = kp_u_right ? kp_u_right[i] : -1.0f;
-      if (kr >= 0) {
-        const float er = f_sub(q_ur, kr);
-        const float e2 = f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(er, er));
-        if ((double)f_mul(e2, inv) > 7.8) continue;
-      } else {
-        const float e2 = f_add(f_mul(ex, ex), f_mul(ey, ey));
-        if ((double)f_mul(e2, inv) > 5.99) continue;
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const int i = i0 + 32 * u;
+      if (i >= n) continue;
+      // Frame::PosInGrid (frame.cc:748-760): round, keypoints outside the grid are in no cell
+      const int px = (int)roundf(f_mul(f_sub(kx[u], g.min_x), g.inv_w));
+      const int py = (int)roundf(f_mul(f_sub(ky[u], g.min_y), g.inv_h));
+      if (px < 0 || px >= g.cols || py < 0 || py >= g.rows) continue;
+      if (px < c0x || px > c1x || py < c0y || py > c1y) continue;
+      if (check_levels) {
+        if (ko[u] < Q.min_level) continue;
+        if (Q.max_level >= 0 && ko[u] > Q.max_level) continue;
       }
-    } else if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
-      const float ur = kp_u_right[i];
-      if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
+      const float dx = f_sub(kx[u], Q.u), dy = f_sub(ky[u], Q.v);
+      if (!(fabsf(dx) < Q.r && fabsf(dy) < Q.r)) continue;
+      if (skip && skip[i]) continue;
+      if (inv_sigma2) {  // ORBmatcher::Fuse (orb_matcher.cc:1159-1178): reprojection error against the keypoint's level variance
+        const float ex = f_sub(Q.u, kx[u]), ey = f_sub(Q.v, ky[u]);
+        const float inv = inv_sigma2[ko[u] < 0 ? 0 : (ko[u] >= n_levels ? n_levels - 1 : ko[u])];
+        const float kr = kp_u_right ? kp_u_right[i] : -1.0f;
+        if (kr >= 0) {
+          const float er = f_sub(q_ur, kr);
+          const float e2 = f_add(f_add(f_mul(ex, ex), f_mul(ey, ey)), f_mul(er, er));
+          if ((double)f_mul(e2, inv) > 7.8) continue;
+        } else {
+          const float e2 = f_add(f_mul(ex, ex), f_mul(ey, ey));
+          if ((double)f_mul(e2, inv) > 5.99) continue;
+        }
+      } else if (kp_u_right) {  // stereo observations must also agree in the right image (orb_matcher.cc:89-92, 1586-1590)
+        const float ur = kp_u_right[i];
+        if (ur > 0 && fabsf(f_sub(q_ur, ur)) > q_err) continue;
+      }
+      uint32_t kd[8];
+      load_row_any(desc + 32 * (size_t)i, kd);
+      const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
+                                     ((unsigned long long)(px * g.rows + py) << 24) | (unsigned long long)i;
+      b1 = min(b1, max(b0, key));
+      b0 = min(b0, key);
     }
-    uint32_t kd[8];
-    load_row_any(desc + 32 * (size_t)i, kd);
-    const unsigned long long key = ((unsigned long long)ham256(qd, kd) << 44) |
-                                   ((unsigned long long)(px * g.rows + py) << 24) | (unsigned long long)i;
-    b1 = min(b1, max(b0, key));
-    b0 = min(b0, key);
   }
   warp_top2(b0, b1);
 }
