@@ -425,9 +425,10 @@ __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict
   constexpr int kHisto = 30, kThLow = 50;  // ORBmatcher::HISTO_LENGTH, TH_LOW (orb_matcher.cc:36-37)
   __shared__ int hist[kHisto];
   __shared__ int keep3[3];
-  __shared__ int n_kept;
+  __shared__ int n_kept, next_node;
   __shared__ uint32_t claimed[64];  // one bit per side-2 feature (cap <= 2048)
-  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  __shared__ uint32_t s_nodes2[2048];  // side 2's sorted node ids (<= cap of them): every warp searches them for its nodes
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
   const int fr1 = pair_1[p], fr2 = pair_2[p];
   if ((unsigned)fr1 >= (unsigned)n_frames || (unsigned)fr2 >= (unsigned)n_frames) {  // a pair outside the pool (device-memory callers are not pre-checked)
     for (int i = tid; i < cap; i += 256) match[(size_t)p * cap + i] = -1;
@@ -440,22 +441,76 @@ __global__ void __launch_bounds__(256) k_search_by_bow(const orbx_kp* __restrict
   for (int i = tid; i < cap; i += 256) mt[i] = -1;
   if (tid < kHisto) hist[tid] = 0;
   if (tid < 64) claimed[tid] = 0;
-  if (tid == 0) n_kept = 0;
+  if (tid == 0) { n_kept = 0; next_node = 0; }
   __syncthreads();
   const int nn1 = fv_n[fr1], nn2 = fv_n[fr2];
   const int tot1 = fv_total[fr1], tot2 = fv_total[fr2];
   const uint32_t *nodes1 = fv_nodes + o1, *nodes2 = fv_nodes + o2, *feats1 = fv_feats + o1, *feats2 = fv_feats + o2;
   const int32_t *begin1 = fv_begin + o1, *begin2 = fv_begin + o2;
-  for (int a = wrp; a < nn1; a += 8) {
+  for (int i = tid; i < nn2 && i < 2048; i += 256) s_nodes2[i] = nodes2[i];
+  __syncthreads();
+  // the shared nodes are independent of each other (a side-2 feature lies in one node) and of very different sizes: the warps
+  // draw them from a counter instead of taking every eighth (a quarter of the stall samples sat at the barrier below)
+  for (;;) {
+    int a = 0;
+    if (lane == 0) a = atomicAdd(&next_node, 1);
+    a = __shfl_sync(0xffffffffu, a, 0);
+    if (a >= nn1) break;
     const uint32_t nid = nodes1[a];
-    int lo = 0, hi = nn2;  // lower_bound of nid in side 2's sorted node ids
+    int lo = 0, hi = nn2;  // lower_bound of nid in side 2's sorted node ids (in shared memory: a chain of dependent loads)
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (nodes2[mid] < nid) lo = mid + 1; else hi = mid;
+      if (s_nodes2[mid] < nid) lo = mid + 1; else hi = mid;
     }
-    if (lo >= nn2 || nodes2[lo] != nid) continue;
+    if (lo >= nn2 || s_nodes2[lo] != nid) continue;
     const int k0 = begin1[a], k1 = a + 1 < nn1 ? begin1[a + 1] : tot1;
     const int f0 = begin2[lo], f1 = lo + 1 < nn2 ? begin2[lo + 1] : tot2;
+    if (f1 - f0 <= 32) {
+      // The usual node (a handful of features on either side): both sides are loaded ONCE, side by side -- lane j keeps
+      // side-2 feature j of the node, lane i side-1 feature i of the current chunk of 32 -- and the walk over the side-1
+      // features, which must stay sequential (a claimed side-2 feature is skipped by the later ones), touches no global
+      // memory: the side-1 descriptor travels by shuffles, every lane compares it with its own side-2 descriptor.
+      int idx2 = -1;
+      uint32_t d2r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (f0 + lane < f1) {
+        idx2 = (int)feats2[f0 + lane];
+        if (idx2 >= n2 || (KF && has_point && !has_point[o2 + idx2])) idx2 = -1;  // :752-754
+      }
+      if (idx2 >= 0) load_row(desc + 32 * (o2 + idx2), d2r);
+      for (int kc = k0; kc < k1; kc += 32) {
+        int idx1 = -1;
+        uint32_t d1m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (kc + lane < k1) {
+          idx1 = (int)feats1[kc + lane];
+          if (idx1 >= n1 || (has_point && !has_point[o1 + idx1])) idx1 = -1;  // :246-250 / :733-735: no map point, or a bad one
+        }
+        if (idx1 >= 0) load_row(desc + 32 * (o1 + idx1), d1m);
+        const int cnt = min(32, k1 - kc);
+        for (int i = 0; i < cnt; i++) {
+          const int i1 = __shfl_sync(0xffffffffu, idx1, i);
+          if (i1 < 0) continue;  // (warp-uniform)
+          uint32_t d1r[8];
+#pragma unroll
+          for (int w8 = 0; w8 < 8; w8++) d1r[w8] = __shfl_sync(0xffffffffu, d1m[w8], i);
+          // one key per lane, (distance << 5) | position in the node (= lane): the two smallest by two REDUX.MIN
+          unsigned key = 0xFFFFFFFFu;
+          if (idx2 >= 0 && !((claimed[idx2 >> 5] >> (idx2 & 31)) & 1u))  // :265 / :752 already claimed
+            key = ((unsigned)ham256(d1r, d2r) << 5) | (unsigned)lane;
+          const unsigned b0 = __reduce_min_sync(0xffffffffu, key);
+          const unsigned b1 = __reduce_min_sync(0xffffffffu, key == b0 ? 0xFFFFFFFFu : key);
+          const int win2 = __shfl_sync(0xffffffffu, idx2, (int)(b0 & 31u));
+          if (lane == 0 && b0 != 0xFFFFFFFFu) {
+            const int d1 = (int)(b0 >> 5), d2 = b1 == 0xFFFFFFFFu ? 256 : (int)(b1 >> 5);
+            if ((KF ? d1 < kThLow : d1 <= kThLow) && (float)d1 < f_mul(nnratio, (float)d2)) {  // :307-309 / :769-771
+              atomicOr(&claimed[win2 >> 5], 1u << (win2 & 31));
+              if (KF) mt[i1] = win2; else mt[win2] = i1;
+            }
+          }
+          __syncwarp();  // the claim is visible to the lanes before the next side-1 feature
+        }
+      }
+      continue;
+    }
     for (int ik = k0; ik < k1; ik++) {
       const int idx1 = (int)feats1[ik];
       if (idx1 >= n1 || (has_point && !has_point[o1 + idx1])) continue;  // :246-250 / :733-735: no map point, or a bad one
