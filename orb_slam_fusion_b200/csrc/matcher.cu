@@ -324,14 +324,21 @@ int launch_ratio_test(const int64_t* idx, const int32_t* dist, int nq, double ra
 }
 
 // ------------------------------------------------------------------ warp top-2 of 64-bit keys
+// The two smallest of the lanes' (b0 <= b1) pairs.  Keys are UNIQUE (each carries the index of its candidate) or the
+// empty key ~0.  The minimum of 64-bit keys is two REDUX.MIN (high words, then the low words of the lanes that hold the
+// smallest high word); the runner-up is the minimum again with the winner's lane offering its second key.  Four REDUX
+// and a few selects instead of five butterfly rounds of 64-bit shuffles and compares.
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((unsigned long long)mh << 32) | ml;
+}
 __device__ __forceinline__ void warp_top2(unsigned long long& b0, unsigned long long& b1) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, b0, o), o1 = __shfl_xor_sync(0xffffffffu, b1, o);
-    const unsigned long long hi = max(b0, o0);
-    b0 = min(b0, o0);
-    b1 = min(hi, min(b1, o1));
-  }
+  const unsigned long long m0 = warp_min_u64(b0);
+  const unsigned long long m1 = warp_min_u64(b0 == m0 ? b1 : b0);
+  b0 = m0;
+  b1 = m1;
 }
 
 // ------------------------------------------------------------------ stereo row band
