@@ -1142,19 +1142,21 @@ __device__ __forceinline__ void window_topk(const orbx_kp* __restrict__ kps, con
       for (int j = 0; j < KL; j++) cmpex(k[j], key);  // insertion: k stays sorted, the largest of the KL + 1 falls out
     }
   }
+  // The KL smallest of the lanes' sorted lists (keys are unique: each carries its keypoint): KL rounds of "warp minimum of
+  // the heads (two REDUX.MIN), its owner pops" -- about 20 instructions a round, where a bitonic merge network over 64-bit
+  // keys took five shuffle rounds of KL keys each with KL compare-exchanges (85 % of k_window_topk's instructions)
+  unsigned long long out[KL];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t[KL];
+  for (int r = 0; r < KL; r++) {
+    const unsigned long long m = warp_min_u64(k[0]);
+    out[r] = m;
+    const bool pop = k[0] == m && m != ~0ull;
 #pragma unroll
-    for (int j = 0; j < KL; j++) t[j] = __shfl_xor_sync(0xffffffffu, k[KL - 1 - j], o);  // the partner's list, reversed
-#pragma unroll
-    for (int j = 0; j < KL; j++) k[j] = min(k[j], t[j]);  // the KL smallest of the union (a bitonic sequence)
-#pragma unroll
-    for (int d = KL / 2; d > 0; d >>= 1)  // bitonic merge: sorted again
-#pragma unroll
-      for (int j = 0; j < KL; j++)
-        if ((j & d) == 0) cmpex(k[j], k[j | d]);
+    for (int j = 0; j < KL - 1; j++) k[j] = pop ? k[j + 1] : k[j];
+    k[KL - 1] = pop ? ~0ull : k[KL - 1];
   }
+#pragma unroll
+  for (int j = 0; j < KL; j++) k[j] = out[j];
 }
 
 // Can two windows hold a common keypoint?  A candidate of a window lies strictly inside its square (|x - u| < r, |y - v| < r)
