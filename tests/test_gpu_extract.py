@@ -227,6 +227,32 @@ def test_device_frames_read_in_place(P, oracle, w, h):
     same(ex.extract_batch(torch.from_numpy(imgs).cuda()))                        # contiguous: in place when w % 16 == 0
 
 
+@pytest.mark.parametrize("w,h,nf,nl,sf", [(752, 480, 1000, 8, 1.2), (640, 368, 700, 5, 1.5), (1090, 693, 1500, 8, 1.1),
+                                           (800, 600, 900, 4, 2.0), (333, 517, 400, 6, 1.25)])
+def test_batch_tile_plan_equals_single_frame(P, oracle, w, h, nf, nl, sf):
+    """Launches of 16 or more frames use their own resize tile plan (48-row tiles, their own TMA boxes) and, for aligned
+    device frames, read level 0 in place; fewer frames use the single-frame plan.  18 frames through the batch paths
+    (device memory, host memory) must equal the same frames one at a time -- which other tests pin to the oracle --
+    and frame 0 is checked against the oracle directly."""
+    import torch
+    F = 18
+    imgs = np.stack([oracle.blocks_v1(w, h, 7, f) if f % 5 else oracle.uniform_v1(w, h, 7, f) for f in range(F)])
+    ex = P.OrbExtractor(nf, sf, nl, 20, 7, max_batch=F)
+    singles = [ex(imgs[f]) for f in range(F)]
+    rn, rk, rd = oracle.Extractor(nf, sf, nl, 20, 7, trig=oracle.TRIG_CR)(imgs[0])
+    assert singles[0][0] == rn and singles[0][1].tobytes() == rk.tobytes() and np.array_equal(singles[0][2], rd)
+    n, nm, kps, desc = ex.extract_batch(imgs)                                   # host memory, one chunk of 18
+    dn, dnm, dk, dd = ex.extract_batch(torch.from_numpy(imgs).cuda())           # device memory (in place when w % 16 == 0)
+    torch.cuda.synchronize()
+    dk = dk.cpu().numpy().view(P.KP_DTYPE).reshape(F, -1)
+    for (a_n, a_nm, a_k, a_d) in [(n, nm, kps, desc), (dn.cpu().numpy(), dnm.cpu().numpy(), dk, dd.cpu().numpy())]:
+        for f in range(F):
+            sm, sk, sd = singles[f]
+            assert a_n[f] == len(sk) and a_nm[f] == sm, f
+            assert a_k[f, :len(sk)].tobytes() == sk.tobytes() and np.array_equal(a_d[f, :len(sk)], sd), f
+    assert ex.debug_dropped() == 0
+
+
 def test_device_synth_equals_oracle_generators(P, oracle):
     fr = P.synth_frames("blocks", 3, 752, 480, seed=1, first_frame=5).cpu().numpy()
     for f in range(3):
