@@ -43,10 +43,22 @@ __global__ void __launch_bounds__(128) k_bow_descend(const VocabDev v, const uin
   while (cnt > 0) {  // do { } while (!isLeaf()) of :1156-1174; an empty vocabulary never gets here with cnt > 0
     ++level;
     int best_d = 1 << 30;
-    for (int c = 0; c < cnt; c++) {
-      const uint4* r = v.sdesc + 2 * (size_t)(beg + c);
-      const int d = ham256(q0, q1, __ldg(r), __ldg(r + 1));
-      if (d < best_d) { best_d = d; best_slot = beg + c; }  // strict <: the first minimum wins (:1166)
+    // the children's rows are fetched five at a time, side by side, before any of them is compared (a loop of load - compare
+    // keeps one row in flight per thread, and the three deepest levels miss L1)
+    constexpr int kG = 5;
+    for (int c0 = 0; c0 < cnt; c0 += kG) {
+      uint4 r0[kG], r1[kG];
+#pragma unroll
+      for (int u = 0; u < kG; u++) {
+        const uint4* r = v.sdesc + 2 * (size_t)(beg + min(c0 + u, cnt - 1));
+        r0[u] = __ldg(r);
+        r1[u] = __ldg(r + 1);
+      }
+#pragma unroll
+      for (int u = 0; u < kG; u++) {
+        const int d = ham256(q0, q1, r0[u], r1[u]);
+        if (c0 + u < cnt && d < best_d) { best_d = d; best_slot = beg + c0 + u; }  // strict <: the first minimum wins (:1166)
+      }
     }
     if (level == nid_level) { nid = (uint32_t)__ldg(v.snode + best_slot); nid_set = true; }
     const int2 ch = __ldg(v.schild + best_slot);
